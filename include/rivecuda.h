@@ -1,0 +1,301 @@
+/*
+ * rivecuda.h -- the thin C ABI between Rive's API-agnostic renderer front end
+ * and the B200-native (sm_100a) CUDA back end.
+ *
+ * This is the drop-in boundary. Every entry point below replaces one (group
+ * of) virtual method(s) of the reference's abstract backend class
+ * `rive::gpu::RenderContextImpl`
+ *   (reference: renderer/include/rive/renderer/render_context_impl.hpp:26-243)
+ * and the structs mirror, as plain C PODs, what the reference hands a backend:
+ * `gpu::FlushDescriptor` (renderer/include/rive/renderer/gpu.hpp:1320-1438),
+ * `gpu::DrawBatch` (gpu.hpp:1219-1282) and `gpu::AtlasDrawBatch`
+ * (gpu.hpp:822-827).
+ *
+ * The nine host-written per-flush buffers keep the reference's exact byte
+ * layout (gpu.hpp: FlushUniforms 1466-1537, PathData 1593-1621, PaintData
+ * 1627-1656, PaintAuxData 1660-1694, ContourData 1698-1719, GradientSpan
+ * 248-272, TessVertexSpan 291-376, TriangleVertex 1722-1740,
+ * ImageDrawInstance 1743-1774). The kernels read those bytes as the reference's
+ * shaders do; nothing is re-packed on the host.
+ *
+ * Conventions: plain pointers and sizes only, no C++ or torch types. Every
+ * function returns 0 on success and a nonzero CUDA-style status on failure;
+ * rivecuda_last_error() returns a thread-local message for the last failure.
+ * A context owns one CUDA device, one stream, and all device memory created
+ * through it. A context is not thread safe (the reference's RenderContext is
+ * single threaded per context); use one context per thread/GPU.
+ *
+ * There is NO CPU fallback behind this ABI: rivecuda_create() fails if no
+ * sm_100-class CUDA device is usable.
+ */
+#ifndef RIVECUDA_H
+#define RIVECUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RIVECUDA_ABI_VERSION 1u
+
+typedef struct rivecuda_ctx rivecuda_ctx;
+typedef struct rivecuda_target rivecuda_target;             /* RenderTarget   */
+typedef struct rivecuda_texture rivecuda_texture;           /* gpu::Texture   */
+typedef struct rivecuda_renderbuffer rivecuda_renderbuffer; /* RenderBuffer   */
+
+/* The nine mapped resource buffers of RenderContextImpl
+ * (render_context_impl.hpp:109-177: resize / map / unmap X Buffer). */
+typedef enum rivecuda_buffer_kind
+{
+    RIVECUDA_BUFFER_FLUSH_UNIFORM = 0, /* 256 B per logical flush            */
+    RIVECUDA_BUFFER_PATH = 1,          /* PathData, 64 B                     */
+    RIVECUDA_BUFFER_PAINT = 2,         /* PaintData, 8 B                     */
+    RIVECUDA_BUFFER_PAINT_AUX = 3,     /* PaintAuxData, 128 B                */
+    RIVECUDA_BUFFER_CONTOUR = 4,       /* ContourData, 16 B                  */
+    RIVECUDA_BUFFER_GRAD_SPAN = 5,     /* GradientSpan, 16 B                 */
+    RIVECUDA_BUFFER_TESS_SPAN = 6,     /* TessVertexSpan, 64 B               */
+    RIVECUDA_BUFFER_TRIANGLE = 7,      /* TriangleVertex, 12 B               */
+    RIVECUDA_BUFFER_IMAGE_DRAW = 8,    /* ImageDrawInstance, 64 B (256 B     */
+                                       /* stride, see render_context.cpp)    */
+    RIVECUDA_BUFFER_KIND_COUNT = 9
+} rivecuda_buffer_kind;
+
+/* gpu::DrawType values the CUDA back end accepts (gpu.hpp:657-726). The
+ * numeric values are the reference's. In rasterOrdering mode only these can
+ * appear (gpu.cpp:32-44 get_valid_draw_types). */
+typedef enum rivecuda_draw_type
+{
+    RIVECUDA_DRAW_MIDPOINT_FAN_PATCHES = 0,
+    RIVECUDA_DRAW_MIDPOINT_FAN_CENTER_AA_PATCHES = 1,
+    RIVECUDA_DRAW_OUTER_CURVE_PATCHES = 2,
+    RIVECUDA_DRAW_INTERIOR_TRIANGULATION = 3,
+    RIVECUDA_DRAW_FEATHER_ATLAS_BLIT = 4,
+    RIVECUDA_DRAW_IMAGE_RECT = 5, /* atomic mode only: rejected */
+    RIVECUDA_DRAW_IMAGE_MESH = 6
+} rivecuda_draw_type;
+
+/* gpu::LoadAction (gpu.hpp:792-797). */
+typedef enum rivecuda_load_action
+{
+    RIVECUDA_LOAD_CLEAR = 0,
+    RIVECUDA_LOAD_PRESERVE = 1,
+    RIVECUDA_LOAD_DONT_CARE = 2
+} rivecuda_load_action;
+
+/* gpu::ShaderFeatures bits (gpu.hpp:840-856). */
+enum
+{
+    RIVECUDA_FEATURE_CLIPPING = 1 << 0,
+    RIVECUDA_FEATURE_CLIP_RECT = 1 << 1,
+    RIVECUDA_FEATURE_ADVANCED_BLEND = 1 << 2,
+    RIVECUDA_FEATURE_FEATHER = 1 << 3,
+    RIVECUDA_FEATURE_EVEN_ODD = 1 << 4,
+    RIVECUDA_FEATURE_NESTED_CLIPPING = 1 << 5,
+    RIVECUDA_FEATURE_HSL_BLEND_MODES = 1 << 6,
+    RIVECUDA_FEATURE_DITHER = 1 << 7,
+    RIVECUDA_FEATURE_MODULATED_IMAGE = 1 << 8
+};
+
+/* gpu::ShaderMiscFlags bits that reach a rasterOrdering backend
+ * (gpu.hpp:905-966). */
+enum
+{
+    RIVECUDA_MISC_CLOCKWISE_FILL = 1 << 1
+};
+
+/* rive::ImageSampler key (include/rive/shapes/paint/image_sampler.hpp:8-27):
+ * wrapX | wrapY<<2 | filter<<4; wrap: 0 clamp, 1 repeat, 2 mirror; filter: 0
+ * bilinear, 1 nearest. */
+typedef uint8_t rivecuda_sampler_key;
+
+/* POD mirror of gpu::DrawBatch (gpu.hpp:1219-1282), one per node of
+ * FlushDescriptor::drawList, in list order. */
+typedef struct rivecuda_draw_batch
+{
+    uint32_t draw_type;          /* rivecuda_draw_type                        */
+    uint32_t shader_misc_flags;  /* RIVECUDA_MISC_*                           */
+    uint32_t draw_contents;      /* gpu::DrawContents bits (gpu.hpp:1128)     */
+    uint32_t shader_features;    /* RIVECUDA_FEATURE_*                        */
+    uint32_t element_count;      /* instances, or vertices for triangle runs  */
+    uint32_t base_element;       /* base instance, or base vertex             */
+    uint32_t index_count_per_instance;
+    uint32_t base_index;
+    uint32_t first_blend_mode;   /* rive::BlendMode of first draw in batch    */
+    uint32_t barriers;           /* gpu::BarrierFlags (informational)         */
+    uint32_t image_sampler;      /* rivecuda_sampler_key                      */
+    uint32_t reserved0;
+    const rivecuda_texture* image_texture;      /* or NULL                    */
+    const rivecuda_renderbuffer* vertex_buffer; /* imageMesh only             */
+    const rivecuda_renderbuffer* uv_buffer;     /* imageMesh only             */
+    const rivecuda_renderbuffer* index_buffer;  /* imageMesh only             */
+} rivecuda_draw_batch;
+
+/* POD mirror of gpu::AtlasDrawBatch (gpu.hpp:822-827). */
+typedef struct rivecuda_atlas_batch
+{
+    uint16_t scissor_left, scissor_top, scissor_right, scissor_bottom;
+    uint32_t patch_count;
+    uint32_t base_patch;
+} rivecuda_atlas_batch;
+
+/* POD mirror of gpu::FlushDescriptor (gpu.hpp:1320-1438). first_* are ELEMENT
+ * indices into the frame-wide mapped buffers, exactly as in the reference. */
+typedef struct rivecuda_flush_desc
+{
+    uint32_t abi_version; /* RIVECUDA_ABI_VERSION */
+    uint32_t interlock_mode; /* must be 0 (gpu::InterlockMode::rasterOrdering) */
+    rivecuda_target* render_target;
+    uint32_t combined_shader_features;
+    uint32_t color_load_action; /* rivecuda_load_action */
+    uint32_t color_clear_value; /* rive::ColorInt, 0xAARRGGBB, unpremultiplied */
+    uint32_t coverage_clear_value;
+    int32_t update_bounds[4];   /* renderTargetUpdateBounds L,T,R,B */
+    uint32_t feather_atlas_texture_width, feather_atlas_texture_height;
+    uint32_t feather_atlas_content_width, feather_atlas_content_height;
+    uint64_t flush_uniform_data_offset_in_bytes;
+    uint32_t path_count;
+    uint32_t contour_count;
+    uint32_t grad_span_count;
+    uint32_t tess_vertex_span_count;
+    uint64_t first_path, first_paint, first_paint_aux, first_contour;
+    uint64_t first_grad_span, first_tess_vertex_span;
+    uint32_t grad_data_height;
+    uint32_t tess_data_height;
+    uint8_t clockwise_fill_override;
+    uint8_t has_triangle_vertices;
+    uint8_t wireframe;
+    uint8_t dither_mode; /* gpu::DitherMode: 0 none, 1 interleavedGradientNoise */
+    uint32_t reserved0;
+} rivecuda_flush_desc;
+
+/* Device-side timings of the most recent rivecuda_flush(), in milliseconds,
+ * measured with CUDA events on the context's stream. */
+typedef struct rivecuda_flush_timings
+{
+    float color_ramp_ms;   /* K1 (color_ramp.glsl replacement)       */
+    float tessellate_ms;   /* K2 (tessellate.glsl replacement)       */
+    float atlas_ms;        /* K3 (render_atlas.glsl replacement)     */
+    float setup_bin_ms;    /* K4 patch vertex expansion + tile bin   */
+    float raster_ms;       /* K5 tile raster + resolve + store       */
+    float total_ms;
+    uint32_t kernel_launches;
+    uint32_t triangle_count;   /* triangles that survived cull/setup  */
+    uint32_t tile_entry_count; /* (triangle,tile) pairs binned        */
+    uint32_t reserved0;
+} rivecuda_flush_timings;
+
+/* ---- context ----------------------------------------------------------- */
+
+/* Create a context on CUDA device `device`. Uploads the static patch vertex /
+ * index buffers (gpu.cpp:669 GeneratePatchBufferData, rebuilt natively) and the
+ * two Gaussian-integral tables (gpu.hpp:2088-2090). */
+int rivecuda_create(int device, rivecuda_ctx** out_ctx);
+void rivecuda_destroy(rivecuda_ctx* ctx);
+const char* rivecuda_last_error(void);
+uint32_t rivecuda_abi_version(void);
+
+/* ---- mapped resource buffers (rings of 3, pinned host + device copy) ---- */
+
+/* RenderContextImpl::resize{FlushUniform,Path,...}Buffer(sizeInBytes). */
+int rivecuda_buffer_resize(rivecuda_ctx* ctx, uint32_t kind, size_t size_in_bytes);
+/* RenderContextImpl::map*Buffer(mapSizeInBytes): rotate the ring and return
+ * write-only pinned host memory. */
+int rivecuda_buffer_map(rivecuda_ctx* ctx, uint32_t kind, size_t map_size_in_bytes, void** out_host_ptr);
+/* RenderContextImpl::unmap*Buffer(mapSizeInBytes): enqueue the async H2D copy
+ * of the mapped range on the context's stream. */
+int rivecuda_buffer_unmap(rivecuda_ctx* ctx, uint32_t kind, size_t map_size_in_bytes);
+
+/* ---- per-flush textures -------------------------------------------------- */
+
+/* RenderContextImpl::resizeGradientTexture / resizeTessellationTexture /
+ * resizeFeatherAtlasTexture (render_context_impl.hpp:177-183). */
+int rivecuda_resize_gradient_texture(rivecuda_ctx* ctx, uint32_t width, uint32_t height);
+int rivecuda_resize_tessellation_texture(rivecuda_ctx* ctx, uint32_t width, uint32_t height);
+int rivecuda_resize_feather_atlas_texture(rivecuda_ctx* ctx, uint32_t width, uint32_t height);
+
+/* ---- render targets, image textures, mesh buffers ------------------------ */
+
+/* A device-resident premultiplied RGBA8 framebuffer (row-major, top-down;
+ * what RenderTargetVulkan is to the Vulkan backend). */
+int rivecuda_target_create(rivecuda_ctx* ctx, uint32_t width, uint32_t height, rivecuda_target** out);
+void rivecuda_target_destroy(rivecuda_ctx* ctx, rivecuda_target* target);
+/* Synchronising D2H read / H2D write of the whole target (RGBA8, w*h*4 bytes). */
+int rivecuda_target_read_pixels(rivecuda_ctx* ctx, const rivecuda_target* target, void* host_rgba8, size_t size_in_bytes);
+int rivecuda_target_write_pixels(rivecuda_ctx* ctx, rivecuda_target* target, const void* host_rgba8, size_t size_in_bytes);
+/* Raw device pointer of the target's RGBA8 pixels (for zero-copy interop and
+ * for the NCCL band gather). */
+int rivecuda_target_device_ptr(rivecuda_ctx* ctx, const rivecuda_target* target, void** out_device_ptr);
+
+/* RenderContextImpl::makeImageTexture (render_context_impl.hpp:61-70), rgba32
+ * premultiplied input. mip_level_count levels are packed largest first; if
+ * generate_remaining_mips is nonzero only level 0 is supplied and a box-filter
+ * chain is generated on the device. */
+int rivecuda_texture_create(rivecuda_ctx* ctx,
+                            uint32_t width,
+                            uint32_t height,
+                            uint32_t mip_level_count,
+                            const uint8_t* rgba8_premul,
+                            int generate_remaining_mips,
+                            rivecuda_texture** out);
+void rivecuda_texture_destroy(rivecuda_ctx* ctx, rivecuda_texture* texture);
+
+/* RenderContextImpl::makeRenderBuffer (render_context_impl.hpp:36-38) and
+ * RenderBuffer::map/unmap (include/rive/renderer.hpp:51-88).
+ * type: 0 index (u16), 1 vertex (float2). */
+int rivecuda_renderbuffer_create(rivecuda_ctx* ctx, uint32_t type, uint32_t flags, size_t size_in_bytes, rivecuda_renderbuffer** out);
+void rivecuda_renderbuffer_destroy(rivecuda_ctx* ctx, rivecuda_renderbuffer* rb);
+int rivecuda_renderbuffer_map(rivecuda_ctx* ctx, rivecuda_renderbuffer* rb, void** out_host_ptr);
+int rivecuda_renderbuffer_unmap(rivecuda_ctx* ctx, rivecuda_renderbuffer* rb);
+
+/* ---- flushing ------------------------------------------------------------ */
+
+/* RenderContextImpl::prepareToFlush(nextFrameNumber, safeFrameNumber). */
+int rivecuda_prepare_to_flush(rivecuda_ctx* ctx, uint64_t next_frame_number, uint64_t safe_frame_number);
+
+/* RenderContextImpl::flush(const gpu::FlushDescriptor&): enqueue
+ *   1. colour ramps  2. tessellation  3. feather atlas  4. the draw list
+ * on the context's stream. Asynchronous: returns after enqueueing. */
+int rivecuda_flush(rivecuda_ctx* ctx,
+                   const rivecuda_flush_desc* desc,
+                   const rivecuda_draw_batch* batches,
+                   uint32_t batch_count,
+                   const rivecuda_atlas_batch* atlas_fill_batches,
+                   uint32_t atlas_fill_batch_count,
+                   const rivecuda_atlas_batch* atlas_stroke_batches,
+                   uint32_t atlas_stroke_batch_count);
+
+/* RenderContextImpl::postFlush. */
+int rivecuda_post_flush(rivecuda_ctx* ctx);
+
+/* Block until all work enqueued on the context's stream has finished. */
+int rivecuda_sync(rivecuda_ctx* ctx);
+
+/* The context's cudaStream_t, as void*. */
+int rivecuda_stream(rivecuda_ctx* ctx, void** out_stream);
+
+/* ---- introspection (parity tests, bench) --------------------------------- */
+
+/* Enable per-kernel CUDA-event timing of subsequent flushes (off by default:
+ * the events serialise nothing but cost a few microseconds each). */
+int rivecuda_set_profiling(rivecuda_ctx* ctx, int enabled);
+/* Timings of the most recent flush; synchronises the stream. */
+int rivecuda_get_flush_timings(rivecuda_ctx* ctx, rivecuda_flush_timings* out);
+
+/* Copy the tessellation "texture" (16 B per vertex: float x, float y, float
+ * theta-or-packed, uint contourIDWithFlags; vertex i at texel (i & 2047, i >>
+ * 11)) of the most recent flush to host memory. */
+int rivecuda_debug_read_tessellation(rivecuda_ctx* ctx, void* host_dst, size_t first_vertex, size_t vertex_count);
+/* Copy rows [0,height) of the 512-wide RGBA8 gradient texture. */
+int rivecuda_debug_read_gradient(rivecuda_ctx* ctx, void* host_dst, uint32_t height);
+/* Copy the feather atlas (float32 coverage, atlas width x height). */
+int rivecuda_debug_read_atlas(rivecuda_ctx* ctx, void* host_dst, uint32_t width, uint32_t height);
+/* The static patch vertex (269 x 32 B) and index (441 x u16) buffers. */
+int rivecuda_debug_read_patch_buffers(rivecuda_ctx* ctx, void* host_vertices, size_t vertices_size, void* host_indices, size_t indices_size);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* RIVECUDA_H */

@@ -1,0 +1,120 @@
+/*
+ * TestingWindow backend for RenderContextCUDAImpl, so the reference's GM
+ * sources (tests/gm/*.cpp) run unmodified against the CUDA backend -- the
+ * analogue of tests/common/testing_window_vulkan_texture.cpp for `--backend
+ * cuda`. Also provides the TestingWindow singletons that the
+ * reference defines in tests/common/testing_window.cpp (which we cannot
+ * compile here because it references every other backend).
+ */
+#include "testing_window_cuda.hpp"
+
+#include "rive/renderer/rive_renderer.hpp"
+
+#include <cstdio>
+#include <cstdlib>
+
+TestingWindow* s_TestingWindow = nullptr;
+TestingWindow::Backend TestingWindow::s_Backend = TestingWindow::Backend::external;
+TestingWindow::Target TestingWindow::s_Target = TestingWindow::Target::host;
+
+TestingWindow* TestingWindow::Get()
+{
+    if (s_TestingWindow == nullptr)
+    {
+        fprintf(stderr, "TestingWindow::Get(): no window has been Set()\n");
+        abort();
+    }
+    return s_TestingWindow;
+}
+
+void TestingWindow::Set(TestingWindow* inWindow) { s_TestingWindow = inWindow; }
+
+void TestingWindow::Destroy()
+{
+    delete s_TestingWindow;
+    s_TestingWindow = nullptr;
+}
+
+using namespace rive;
+using namespace rive::gpu;
+
+TestingWindowCUDA::TestingWindowCUDA(const RenderContextCUDAImpl::ContextOptions& options) :
+    m_renderContext(RenderContextCUDAImpl::MakeContext(options))
+{
+    if (m_renderContext == nullptr)
+    {
+        fprintf(stderr, "TestingWindowCUDA: failed to create a CUDA context\n");
+        abort();
+    }
+}
+
+TestingWindowCUDA::~TestingWindowCUDA()
+{
+    m_renderTarget = nullptr;
+    m_renderContext = nullptr;
+}
+
+rive::Factory* TestingWindowCUDA::factory() { return m_renderContext.get(); }
+
+void TestingWindowCUDA::resize(int width, int height)
+{
+    if (m_renderTarget == nullptr || m_width != static_cast<uint32_t>(width) ||
+        m_height != static_cast<uint32_t>(height))
+    {
+        m_renderTarget =
+            m_renderContext->static_impl_cast<RenderContextCUDAImpl>()
+                ->makeRenderTarget(width, height);
+    }
+    TestingWindow::resize(width, height);
+}
+
+std::unique_ptr<rive::Renderer> TestingWindowCUDA::beginFrame(
+    const FrameOptions& options)
+{
+    RenderContext::FrameDescriptor frameDescriptor = {
+        .renderTargetWidth = m_width,
+        .renderTargetHeight = m_height,
+        .loadAction = options.doClear ? LoadAction::clear
+                                      : LoadAction::preserveRenderTarget,
+        .clearColor = options.clearColor,
+        .msaaSampleCount = 0,
+        .disableRasterOrdering = false,
+        .triangulationThresholds = options.triangulationThresholds,
+        .wireframe = options.wireframe,
+        .fillsDisabled = options.fillsDisabled,
+        .strokesDisabled = options.strokesDisabled,
+        .clockwiseFillOverride = false,
+    };
+    m_renderContext->beginFrame(frameDescriptor);
+    return std::make_unique<RiveRenderer>(m_renderContext.get());
+}
+
+void TestingWindowCUDA::flushPLSContext(RenderTarget* offscreenRenderTarget)
+{
+    ++m_frameNumber;
+    m_renderContext->flush({
+        .renderTarget = offscreenRenderTarget != nullptr ? offscreenRenderTarget
+                                                         : m_renderTarget.get(),
+        .currentFrameNumber = m_frameNumber,
+        .safeFrameNumber = m_frameNumber > 2 ? m_frameNumber - 2 : 0,
+    });
+}
+
+void TestingWindowCUDA::endFrame(std::vector<uint8_t>* pixelData)
+{
+    flushPLSContext(nullptr);
+    if (pixelData != nullptr)
+    {
+        m_renderTarget->readPixels(pixelData);
+    }
+}
+
+rive::gpu::RenderContext* TestingWindowCUDA::renderContext() const
+{
+    return m_renderContext.get();
+}
+
+rive::gpu::RenderTarget* TestingWindowCUDA::renderTarget() const
+{
+    return m_renderTarget.get();
+}

@@ -1,0 +1,31 @@
+/*
+ * TestingWindow backend for RenderContextCUDAImpl ("--backend cuda").
+ * Mirrors tests/common/testing_window_null.cpp / _vulkan_texture.cpp.
+ */
+#pragma once
+
+#include "common/testing_window.hpp"
+#include "render_context_cuda_impl.hpp"
+
+class TestingWindowCUDA : public TestingWindow
+{
+public:
+    explicit TestingWindowCUDA(
+        const rive::gpu::RenderContextCUDAImpl::ContextOptions& options = {});
+    ~TestingWindowCUDA() override;
+
+    rive::Factory* factory() override;
+    void resize(int width, int height) override;
+    std::unique_ptr<rive::Renderer> beginFrame(const FrameOptions&) override;
+    void endFrame(std::vector<uint8_t>* pixelData = nullptr) override;
+    void flushPLSContext(
+        rive::gpu::RenderTarget* offscreenRenderTarget = nullptr) override;
+
+    rive::gpu::RenderContext* renderContext() const override;
+    rive::gpu::RenderTarget* renderTarget() const override;
+
+private:
+    std::unique_ptr<rive::gpu::RenderContext> m_renderContext;
+    rive::rcp<rive::gpu::RenderTargetCUDA> m_renderTarget;
+    uint64_t m_frameNumber = 0;
+};

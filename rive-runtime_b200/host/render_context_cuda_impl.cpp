@@ -1,0 +1,513 @@
+/*
+ * RenderContextCUDAImpl: translation of the reference's backend interface
+ * (render_context_impl.hpp:26-243) onto the C ABI of include/rivecuda.h.
+ * No device code lives here.
+ */
+#include "render_context_cuda_impl.hpp"
+
+#include "rive/renderer/rive_render_image.hpp"
+
+#include <dlfcn.h>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+
+namespace rive::gpu
+{
+// ---------------------------------------------------------------------------
+// ABI loading
+
+[[noreturn]] static void abi_fatal(const char* what, const char* detail)
+{
+    fprintf(stderr,
+            "RenderContextCUDAImpl: %s (%s). There is no CPU fallback.\n",
+            what,
+            detail != nullptr ? detail : "?");
+    abort();
+}
+
+static std::string directory_of_this_binary()
+{
+    Dl_info info;
+    if (dladdr(reinterpret_cast<void*>(&directory_of_this_binary), &info) != 0 &&
+        info.dli_fname != nullptr)
+    {
+        std::string path(info.dli_fname);
+        size_t slash = path.find_last_of('/');
+        if (slash != std::string::npos)
+            return path.substr(0, slash + 1);
+    }
+    return "";
+}
+
+const RiveCudaABI& RiveCudaABI::Load(const char* libraryPath)
+{
+    static RiveCudaABI s_abi;
+    static bool s_loaded = false;
+    if (s_loaded)
+        return s_abi;
+
+    std::string path;
+    if (libraryPath != nullptr)
+        path = libraryPath;
+    else if (const char* env = getenv("RIVECUDA_LIB"))
+        path = env;
+
+    void* lib = nullptr;
+    if (!path.empty())
+    {
+        lib = dlopen(path.c_str(), RTLD_NOW | RTLD_LOCAL);
+    }
+    else
+    {
+        // Look next to this binary first, then on the loader path.
+        path = directory_of_this_binary() + "librivecuda.so";
+        lib = dlopen(path.c_str(), RTLD_NOW | RTLD_LOCAL);
+        if (lib == nullptr)
+        {
+            path = "librivecuda.so";
+            lib = dlopen(path.c_str(), RTLD_NOW | RTLD_LOCAL);
+        }
+    }
+    if (lib == nullptr)
+        abi_fatal("cannot load the rivecuda ABI library", dlerror());
+
+#define RIVECUDA_FN(NAME)                                                      \
+    s_abi.NAME = reinterpret_cast<decltype(s_abi.NAME)>(                       \
+        dlsym(lib, "rivecuda_" #NAME));                                        \
+    if (s_abi.NAME == nullptr)                                                 \
+        abi_fatal("missing ABI symbol", "rivecuda_" #NAME);
+#include "rivecuda_fns.inc"
+#undef RIVECUDA_FN
+
+    if (s_abi.abi_version() != RIVECUDA_ABI_VERSION)
+        abi_fatal("ABI version mismatch", path.c_str());
+    s_loaded = true;
+    return s_abi;
+}
+
+#define ABI_CHECK(CALL)                                                        \
+    do                                                                         \
+    {                                                                          \
+        if ((CALL) != 0)                                                       \
+        {                                                                      \
+            fprintf(stderr,                                                    \
+                    "RenderContextCUDAImpl: %s failed: %s\n",                  \
+                    #CALL,                                                     \
+                    m_abi.last_error());                                       \
+            abort();                                                           \
+        }                                                                      \
+    } while (0)
+
+// ---------------------------------------------------------------------------
+// RenderTargetCUDA / TextureCUDA / RenderBufferCUDA
+
+RenderTargetCUDA::RenderTargetCUDA(const RiveCudaABI& abi,
+                                   rivecuda_ctx* ctx,
+                                   uint32_t width,
+                                   uint32_t height) :
+    RenderTarget(width, height), m_abi(abi), m_ctx(ctx)
+{
+    ABI_CHECK(m_abi.target_create(m_ctx, width, height, &m_handle));
+}
+
+RenderTargetCUDA::~RenderTargetCUDA()
+{
+    if (m_handle != nullptr)
+        m_abi.target_destroy(m_ctx, m_handle);
+}
+
+bool RenderTargetCUDA::readPixels(std::vector<uint8_t>* rgba8) const
+{
+    rgba8->resize(static_cast<size_t>(width()) * height() * 4);
+    return m_abi.target_read_pixels(m_ctx,
+                                    m_handle,
+                                    rgba8->data(),
+                                    rgba8->size()) == 0;
+}
+
+bool RenderTargetCUDA::writePixels(const uint8_t* rgba8, size_t sizeInBytes)
+{
+    return m_abi.target_write_pixels(m_ctx, m_handle, rgba8, sizeInBytes) == 0;
+}
+
+TextureCUDA::TextureCUDA(const RiveCudaABI& abi,
+                         rivecuda_ctx* ctx,
+                         uint32_t width,
+                         uint32_t height,
+                         uint32_t mipLevelCount,
+                         const uint8_t rgba8Premul[],
+                         bool generateRemainingMips) :
+    Texture(width, height), m_abi(abi), m_ctx(ctx)
+{
+    ABI_CHECK(m_abi.texture_create(m_ctx,
+                                   width,
+                                   height,
+                                   mipLevelCount,
+                                   rgba8Premul,
+                                   generateRemainingMips ? 1 : 0,
+                                   &m_handle));
+}
+
+TextureCUDA::~TextureCUDA()
+{
+    if (m_handle != nullptr)
+        m_abi.texture_destroy(m_ctx, m_handle);
+}
+
+// Mesh vertex/uv/index storage. map() hands out the ABI's host staging memory;
+// unmap() enqueues the upload.
+class RenderBufferCUDA
+    : public LITE_RTTI_OVERRIDE(RenderBuffer, RenderBufferCUDA)
+{
+public:
+    RenderBufferCUDA(const RiveCudaABI& abi,
+                     rivecuda_ctx* ctx,
+                     RenderBufferType type,
+                     RenderBufferFlags flags,
+                     size_t sizeInBytes) :
+        lite_rtti_override(type, flags, sizeInBytes), m_abi(abi), m_ctx(ctx)
+    {
+        ABI_CHECK(m_abi.renderbuffer_create(
+            m_ctx,
+            type == RenderBufferType::vertex ? 1u : 0u,
+            static_cast<uint32_t>(flags),
+            sizeInBytes,
+            &m_handle));
+    }
+
+    ~RenderBufferCUDA() override
+    {
+        if (m_handle != nullptr)
+            m_abi.renderbuffer_destroy(m_ctx, m_handle);
+    }
+
+    rivecuda_renderbuffer* handle() const { return m_handle; }
+
+protected:
+    void* onMap() override
+    {
+        void* ptr = nullptr;
+        ABI_CHECK(m_abi.renderbuffer_map(m_ctx, m_handle, &ptr));
+        return ptr;
+    }
+
+    void onUnmap() override
+    {
+        ABI_CHECK(m_abi.renderbuffer_unmap(m_ctx, m_handle));
+    }
+
+private:
+    const RiveCudaABI& m_abi;
+    rivecuda_ctx* m_ctx;
+    rivecuda_renderbuffer* m_handle = nullptr;
+};
+
+// ---------------------------------------------------------------------------
+// RenderContextCUDAImpl
+
+std::unique_ptr<RenderContext> RenderContextCUDAImpl::MakeContext(
+    const ContextOptions& options)
+{
+    const RiveCudaABI& abi = RiveCudaABI::Load(options.abiLibraryPath);
+    rivecuda_ctx* ctx = nullptr;
+    if (abi.create(options.device, &ctx) != 0 || ctx == nullptr)
+    {
+        fprintf(stderr,
+                "RenderContextCUDAImpl: rivecuda_create(%d) failed: %s\n",
+                options.device,
+                abi.last_error());
+        return nullptr;
+    }
+    std::unique_ptr<RenderContextCUDAImpl> impl(
+        new RenderContextCUDAImpl(abi, ctx));
+    return std::make_unique<RenderContext>(std::move(impl));
+}
+
+RenderContextCUDAImpl::RenderContextCUDAImpl(const RiveCudaABI& abi,
+                                             rivecuda_ctx* ctx) :
+    m_abi(abi), m_ctx(ctx)
+{
+    // The tile rasteriser composites paths strictly in draw order inside each
+    // tile, which is exactly the guarantee of InterlockMode::rasterOrdering,
+    // so that is the only mode advertised (select_interlock_mode,
+    // render_context.cpp:381-415, then never picks atomics/clockwise/msaa
+    // unless a frame forces msaaSampleCount or clockwiseFillOverride).
+    m_platformFeatures.supportsRasterOrderingMode = true;
+    // Vulkan conventions, so FlushUniforms and paint matrices are what the
+    // oracle backend sees (render_context_vulkan_impl.cpp:1167-1168).
+    m_platformFeatures.clipSpaceBottomUp = false;
+    m_platformFeatures.framebufferBottomUp = false;
+    // Keep draws in submission order with no per-batch scissors
+    // (render_context.cpp:1572-1588).
+    m_platformFeatures.supportsClipScissor = false;
+    m_platformFeatures.pathIDGranularity = 1;
+    m_platformFeatures.maxTextureSize = 32768;
+}
+
+RenderContextCUDAImpl::~RenderContextCUDAImpl()
+{
+    if (m_ctx != nullptr)
+    {
+        m_abi.sync(m_ctx);
+        m_abi.destroy(m_ctx);
+    }
+}
+
+rcp<RenderTargetCUDA> RenderContextCUDAImpl::makeRenderTarget(uint32_t width,
+                                                              uint32_t height)
+{
+    return rcp<RenderTargetCUDA>(
+        new RenderTargetCUDA(m_abi, m_ctx, width, height));
+}
+
+void RenderContextCUDAImpl::sync() { ABI_CHECK(m_abi.sync(m_ctx)); }
+
+rcp<RenderBuffer> RenderContextCUDAImpl::makeRenderBuffer(
+    RenderBufferType type,
+    RenderBufferFlags flags,
+    size_t sizeInBytes)
+{
+    return make_rcp<RenderBufferCUDA>(m_abi, m_ctx, type, flags, sizeInBytes);
+}
+
+rcp<Texture> RenderContextCUDAImpl::makeImageTexture(
+    uint32_t width,
+    uint32_t height,
+    uint32_t mipLevelCount,
+    GPUTextureFormat format,
+    const uint8_t imageData[],
+    uint8_t blockWidth,
+    uint8_t blockHeight,
+    bool srgb,
+    bool generateRemainingMips)
+{
+    if (format != GPUTextureFormat::rgba32)
+    {
+        // platformFeatures().supportsTextureCompression* are all false, so the
+        // front end never hands us block-compressed data.
+        fprintf(stderr,
+                "RenderContextCUDAImpl: only rgba32 image textures are "
+                "supported\n");
+        return nullptr;
+    }
+    return make_rcp<TextureCUDA>(m_abi,
+                                 m_ctx,
+                                 width,
+                                 height,
+                                 mipLevelCount,
+                                 imageData,
+                                 generateRemainingMips);
+}
+
+void RenderContextCUDAImpl::resizeBuffer(rivecuda_buffer_kind kind,
+                                         size_t sizeInBytes)
+{
+    ABI_CHECK(m_abi.buffer_resize(m_ctx, kind, sizeInBytes));
+}
+
+void* RenderContextCUDAImpl::mapBuffer(rivecuda_buffer_kind kind,
+                                       size_t mapSizeInBytes)
+{
+    void* ptr = nullptr;
+    if (m_abi.buffer_map(m_ctx, kind, mapSizeInBytes, &ptr) != 0)
+    {
+        // A null map makes RenderContext skip the frame
+        // (render_context.cpp:1012-1016).
+        fprintf(stderr,
+                "RenderContextCUDAImpl: buffer_map(%d) failed: %s\n",
+                static_cast<int>(kind),
+                m_abi.last_error());
+        return nullptr;
+    }
+    return ptr;
+}
+
+void RenderContextCUDAImpl::unmapBuffer(rivecuda_buffer_kind kind,
+                                        size_t mapSizeInBytes)
+{
+    ABI_CHECK(m_abi.buffer_unmap(m_ctx, kind, mapSizeInBytes));
+}
+
+#define IMPLEMENT_BUFFER(NAME, KIND, ...)                                      \
+    void RenderContextCUDAImpl::resize##NAME(size_t sizeInBytes __VA_ARGS__)   \
+    {                                                                          \
+        resizeBuffer(KIND, sizeInBytes);                                       \
+    }                                                                          \
+    void* RenderContextCUDAImpl::map##NAME(size_t mapSizeInBytes)              \
+    {                                                                          \
+        return mapBuffer(KIND, mapSizeInBytes);                                \
+    }                                                                          \
+    void RenderContextCUDAImpl::unmap##NAME(size_t mapSizeInBytes)             \
+    {                                                                          \
+        unmapBuffer(KIND, mapSizeInBytes);                                     \
+    }
+
+#define COMMA_STRUCTURE , gpu::StorageBufferStructure
+IMPLEMENT_BUFFER(FlushUniformBuffer, RIVECUDA_BUFFER_FLUSH_UNIFORM)
+IMPLEMENT_BUFFER(PathBuffer, RIVECUDA_BUFFER_PATH, COMMA_STRUCTURE)
+IMPLEMENT_BUFFER(PaintBuffer, RIVECUDA_BUFFER_PAINT, COMMA_STRUCTURE)
+IMPLEMENT_BUFFER(PaintAuxBuffer, RIVECUDA_BUFFER_PAINT_AUX, COMMA_STRUCTURE)
+IMPLEMENT_BUFFER(ContourBuffer, RIVECUDA_BUFFER_CONTOUR, COMMA_STRUCTURE)
+IMPLEMENT_BUFFER(GradSpanBuffer, RIVECUDA_BUFFER_GRAD_SPAN)
+IMPLEMENT_BUFFER(TessVertexSpanBuffer, RIVECUDA_BUFFER_TESS_SPAN)
+IMPLEMENT_BUFFER(TriangleVertexBuffer, RIVECUDA_BUFFER_TRIANGLE)
+IMPLEMENT_BUFFER(ImageDrawInstanceBuffer, RIVECUDA_BUFFER_IMAGE_DRAW)
+#undef COMMA_STRUCTURE
+#undef IMPLEMENT_BUFFER
+
+void RenderContextCUDAImpl::resizeGradientTexture(uint32_t width,
+                                                  uint32_t height)
+{
+    ABI_CHECK(m_abi.resize_gradient_texture(m_ctx, width, height));
+}
+
+void RenderContextCUDAImpl::resizeTessellationTexture(uint32_t width,
+                                                      uint32_t height)
+{
+    ABI_CHECK(m_abi.resize_tessellation_texture(m_ctx, width, height));
+}
+
+void RenderContextCUDAImpl::resizeFeatherAtlasTexture(uint32_t width,
+                                                      uint32_t height)
+{
+    ABI_CHECK(m_abi.resize_feather_atlas_texture(m_ctx, width, height));
+}
+
+void RenderContextCUDAImpl::prepareToFlush(uint64_t nextFrameNumber,
+                                           uint64_t safeFrameNumber)
+{
+    ABI_CHECK(m_abi.prepare_to_flush(m_ctx, nextFrameNumber, safeFrameNumber));
+}
+
+static void convert_atlas_batches(const AtlasDrawBatch* batches,
+                                  size_t count,
+                                  std::vector<rivecuda_atlas_batch>* out)
+{
+    for (size_t i = 0; i < count; ++i)
+    {
+        const AtlasDrawBatch& b = batches[i];
+        out->push_back({b.scissor.left,
+                        b.scissor.top,
+                        b.scissor.right,
+                        b.scissor.bottom,
+                        b.patchCount,
+                        b.basePatch});
+    }
+}
+
+void RenderContextCUDAImpl::flush(const FlushDescriptor& desc)
+{
+    if (desc.interlockMode != InterlockMode::rasterOrdering)
+    {
+        fprintf(stderr,
+                "RenderContextCUDAImpl: InterlockMode %d is not supported "
+                "(only rasterOrdering is advertised)\n",
+                static_cast<int>(desc.interlockMode));
+        abort();
+    }
+
+    rivecuda_flush_desc d;
+    memset(&d, 0, sizeof(d));
+    d.abi_version = RIVECUDA_ABI_VERSION;
+    d.interlock_mode = static_cast<uint32_t>(desc.interlockMode);
+    d.render_target =
+        static_cast<RenderTargetCUDA*>(desc.renderTarget)->handle();
+    d.combined_shader_features =
+        static_cast<uint32_t>(desc.combinedShaderFeatures);
+    d.color_load_action = static_cast<uint32_t>(desc.colorLoadAction);
+    d.color_clear_value = desc.colorClearValue;
+    d.coverage_clear_value = desc.coverageClearValue;
+    d.update_bounds[0] = desc.renderTargetUpdateBounds.left;
+    d.update_bounds[1] = desc.renderTargetUpdateBounds.top;
+    d.update_bounds[2] = desc.renderTargetUpdateBounds.right;
+    d.update_bounds[3] = desc.renderTargetUpdateBounds.bottom;
+    d.feather_atlas_texture_width = desc.featherAtlasTextureWidth;
+    d.feather_atlas_texture_height = desc.featherAtlasTextureHeight;
+    d.feather_atlas_content_width = desc.featherAtlasContentWidth;
+    d.feather_atlas_content_height = desc.featherAtlasContentHeight;
+    d.flush_uniform_data_offset_in_bytes = desc.flushUniformDataOffsetInBytes;
+    d.path_count = desc.pathCount;
+    d.contour_count = desc.contourCount;
+    d.grad_span_count = desc.gradSpanCount;
+    d.tess_vertex_span_count = desc.tessVertexSpanCount;
+    d.first_path = desc.firstPath;
+    d.first_paint = desc.firstPaint;
+    d.first_paint_aux = desc.firstPaintAux;
+    d.first_contour = desc.firstContour;
+    d.first_grad_span = desc.firstGradSpan;
+    d.first_tess_vertex_span = desc.firstTessVertexSpan;
+    d.grad_data_height = desc.gradDataHeight;
+    d.tess_data_height = desc.tessDataHeight;
+    d.clockwise_fill_override = desc.clockwiseFillOverride;
+    d.has_triangle_vertices = desc.hasTriangleVertices;
+    d.wireframe = desc.wireframe;
+    d.dither_mode = static_cast<uint8_t>(desc.ditherMode);
+
+    m_batchScratch.clear();
+    if (desc.drawList != nullptr)
+    {
+        for (const DrawBatch& batch : *desc.drawList)
+        {
+            rivecuda_draw_batch b;
+            memset(&b, 0, sizeof(b));
+            b.draw_type = static_cast<uint32_t>(batch.drawType);
+            b.shader_misc_flags = static_cast<uint32_t>(batch.shaderMiscFlags);
+            b.draw_contents = static_cast<uint32_t>(batch.drawContents);
+            b.shader_features = static_cast<uint32_t>(batch.shaderFeatures);
+            b.element_count = batch.elementCount;
+            b.base_element = batch.baseElement;
+            b.index_count_per_instance = batch.indexCountPerInstance;
+            b.base_index = batch.baseIndex;
+            b.first_blend_mode = static_cast<uint32_t>(batch.firstBlendMode);
+            b.barriers = static_cast<uint32_t>(batch.barriers);
+            b.image_sampler = batch.imageSampler.asKey();
+            if (batch.imageTexture != nullptr)
+            {
+                b.image_texture =
+                    static_cast<const TextureCUDA*>(batch.imageTexture)
+                        ->handle();
+            }
+            if (batch.drawType == DrawType::imageMesh)
+            {
+                auto vb = lite_rtti_cast<RenderBufferCUDA*>(batch.vertexBuffer);
+                auto uv = lite_rtti_cast<RenderBufferCUDA*>(batch.uvBuffer);
+                auto ib = lite_rtti_cast<RenderBufferCUDA*>(batch.indexBuffer);
+                if (vb == nullptr || uv == nullptr || ib == nullptr)
+                    continue; // Foreign buffers: skip, like LITE_RTTI_CAST_OR_BREAK.
+                b.vertex_buffer = vb->handle();
+                b.uv_buffer = uv->handle();
+                b.index_buffer = ib->handle();
+            }
+            m_batchScratch.push_back(b);
+        }
+    }
+
+    m_atlasScratch.clear();
+    convert_atlas_batches(desc.featherAtlasFillBatches,
+                          desc.featherAtlasFillBatchCount,
+                          &m_atlasScratch);
+    convert_atlas_batches(desc.featherAtlasStrokeBatches,
+                          desc.featherAtlasStrokeBatchCount,
+                          &m_atlasScratch);
+    const rivecuda_atlas_batch* fills = m_atlasScratch.data();
+    const rivecuda_atlas_batch* strokes =
+        m_atlasScratch.data() + desc.featherAtlasFillBatchCount;
+
+    ABI_CHECK(m_abi.flush(
+        m_ctx,
+        &d,
+        m_batchScratch.data(),
+        static_cast<uint32_t>(m_batchScratch.size()),
+        fills,
+        static_cast<uint32_t>(desc.featherAtlasFillBatchCount),
+        strokes,
+        static_cast<uint32_t>(desc.featherAtlasStrokeBatchCount)));
+}
+
+void RenderContextCUDAImpl::postFlush(const RenderContext::FlushResources&)
+{
+    ABI_CHECK(m_abi.post_flush(m_ctx));
+}
+} // namespace rive::gpu

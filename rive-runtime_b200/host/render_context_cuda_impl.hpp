@@ -1,0 +1,199 @@
+/*
+ * rive::gpu::RenderContextCUDAImpl -- the B200-native backend for Rive's GPU
+ * vector renderer, behind the reference's unchanged RenderContextImpl
+ * interface (reference: renderer/include/rive/renderer/render_context_impl.hpp
+ * :26-243). It is to CUDA what RenderContextVulkanImpl
+ * (renderer/src/vulkan/render_context_vulkan_impl.cpp) is to Vulkan, except
+ * that all device work happens behind the C ABI in include/rivecuda.h: this
+ * class only translates the reference's C++ objects (FlushDescriptor, DrawBatch
+ * list, Texture / RenderBuffer / RenderTarget pointers) into the ABI's PODs.
+ *
+ * Usage (identical to any other backend):
+ *
+ *   auto ctx = RenderContextCUDAImpl::MakeContext({.device = 0});
+ *   auto target = ctx->static_impl_cast<RenderContextCUDAImpl>()
+ *                     ->makeRenderTarget(w, h);
+ *   ctx->beginFrame({...});  RiveRenderer r(ctx.get());  artboard->draw(&r);
+ *   ctx->flush({.renderTarget = target.get()});
+ *   target->readPixels(rgba);   // optional
+ */
+#pragma once
+
+#include "rive/renderer/render_context_impl.hpp"
+#include "rive/renderer/render_target.hpp"
+#include "rive/renderer/texture.hpp"
+#include "rivecuda.h"
+
+#include <chrono>
+#include <memory>
+#include <vector>
+
+namespace rive::gpu
+{
+// Table of the C ABI's entry points, resolved at runtime with dlopen() so the
+// same host binary can run against librivecuda.so (the device) or
+// librivecuda_trace.so (the call recorder used to make flush traces on boxes
+// without a GPU).
+struct RiveCudaABI
+{
+#define RIVECUDA_FN(NAME) decltype(&::rivecuda_##NAME) NAME = nullptr;
+#include "rivecuda_fns.inc"
+#undef RIVECUDA_FN
+
+    // Loads `libraryPath` (or $RIVECUDA_LIB, or "librivecuda.so" next to this
+    // binary). Aborts with a message if the library or any symbol is missing:
+    // there is no CPU fallback.
+    static const RiveCudaABI& Load(const char* libraryPath = nullptr);
+};
+
+class RenderTargetCUDA : public RenderTarget
+{
+public:
+    ~RenderTargetCUDA() override;
+
+    rivecuda_target* handle() const { return m_handle; }
+
+    // Synchronising read-back of the premultiplied RGBA8 framebuffer
+    // (row-major, top-down, width*height*4 bytes).
+    bool readPixels(std::vector<uint8_t>* rgba8) const;
+    bool writePixels(const uint8_t* rgba8, size_t sizeInBytes);
+
+private:
+    friend class RenderContextCUDAImpl;
+    RenderTargetCUDA(const RiveCudaABI& abi,
+                     rivecuda_ctx* ctx,
+                     uint32_t width,
+                     uint32_t height);
+
+    const RiveCudaABI& m_abi;
+    rivecuda_ctx* m_ctx;
+    rivecuda_target* m_handle = nullptr;
+};
+
+class TextureCUDA : public Texture
+{
+public:
+    TextureCUDA(const RiveCudaABI& abi,
+                rivecuda_ctx* ctx,
+                uint32_t width,
+                uint32_t height,
+                uint32_t mipLevelCount,
+                const uint8_t rgba8Premul[],
+                bool generateRemainingMips);
+    ~TextureCUDA() override;
+
+    rivecuda_texture* handle() const { return m_handle; }
+    void* nativeHandle() const override { return m_handle; }
+
+private:
+    const RiveCudaABI& m_abi;
+    rivecuda_ctx* m_ctx;
+    rivecuda_texture* m_handle = nullptr;
+};
+
+class RenderContextCUDAImpl : public RenderContextImpl
+{
+public:
+    struct ContextOptions
+    {
+        int device = 0;
+        // Path of the shared library that implements include/rivecuda.h.
+        // nullptr => $RIVECUDA_LIB, else "librivecuda.so".
+        const char* abiLibraryPath = nullptr;
+    };
+
+    static std::unique_ptr<RenderContext> MakeContext(const ContextOptions&);
+    static std::unique_ptr<RenderContext> MakeContext()
+    {
+        return MakeContext(ContextOptions());
+    }
+
+    ~RenderContextCUDAImpl() override;
+
+    rcp<RenderTargetCUDA> makeRenderTarget(uint32_t width, uint32_t height);
+
+    rivecuda_ctx* abiContext() const { return m_ctx; }
+    const RiveCudaABI& abi() const { return m_abi; }
+
+    // Blocks until the device has finished everything flushed so far.
+    void sync();
+
+    // RenderContextImpl overrides.
+    rcp<RenderBuffer> makeRenderBuffer(RenderBufferType,
+                                       RenderBufferFlags,
+                                       size_t) override;
+
+    rcp<Texture> makeImageTexture(uint32_t width,
+                                  uint32_t height,
+                                  uint32_t mipLevelCount,
+                                  GPUTextureFormat format,
+                                  const uint8_t imageData[],
+                                  uint8_t blockWidth = 1,
+                                  uint8_t blockHeight = 1,
+                                  bool srgb = false,
+                                  bool generateRemainingMips = false) override;
+
+    void resizeFlushUniformBuffer(size_t sizeInBytes) override;
+    void resizePathBuffer(size_t sizeInBytes,
+                          gpu::StorageBufferStructure) override;
+    void resizePaintBuffer(size_t sizeInBytes,
+                           gpu::StorageBufferStructure) override;
+    void resizePaintAuxBuffer(size_t sizeInBytes,
+                              gpu::StorageBufferStructure) override;
+    void resizeContourBuffer(size_t sizeInBytes,
+                             gpu::StorageBufferStructure) override;
+    void resizeGradSpanBuffer(size_t sizeInBytes) override;
+    void resizeTessVertexSpanBuffer(size_t sizeInBytes) override;
+    void resizeTriangleVertexBuffer(size_t sizeInBytes) override;
+    void resizeImageDrawInstanceBuffer(size_t sizeInBytes) override;
+
+    void* mapFlushUniformBuffer(size_t mapSizeInBytes) override;
+    void* mapPathBuffer(size_t mapSizeInBytes) override;
+    void* mapPaintBuffer(size_t mapSizeInBytes) override;
+    void* mapPaintAuxBuffer(size_t mapSizeInBytes) override;
+    void* mapContourBuffer(size_t mapSizeInBytes) override;
+    void* mapGradSpanBuffer(size_t mapSizeInBytes) override;
+    void* mapTessVertexSpanBuffer(size_t mapSizeInBytes) override;
+    void* mapTriangleVertexBuffer(size_t mapSizeInBytes) override;
+    void* mapImageDrawInstanceBuffer(size_t mapSizeInBytes) override;
+
+    void unmapFlushUniformBuffer(size_t mapSizeInBytes) override;
+    void unmapPathBuffer(size_t mapSizeInBytes) override;
+    void unmapPaintBuffer(size_t mapSizeInBytes) override;
+    void unmapPaintAuxBuffer(size_t mapSizeInBytes) override;
+    void unmapContourBuffer(size_t mapSizeInBytes) override;
+    void unmapGradSpanBuffer(size_t mapSizeInBytes) override;
+    void unmapTessVertexSpanBuffer(size_t mapSizeInBytes) override;
+    void unmapTriangleVertexBuffer(size_t mapSizeInBytes) override;
+    void unmapImageDrawInstanceBuffer(size_t mapSizeInBytes) override;
+
+    void resizeGradientTexture(uint32_t width, uint32_t height) override;
+    void resizeTessellationTexture(uint32_t width, uint32_t height) override;
+    void resizeFeatherAtlasTexture(uint32_t width, uint32_t height) override;
+
+    void prepareToFlush(uint64_t nextFrameNumber,
+                        uint64_t safeFrameNumber) override;
+    void flush(const gpu::FlushDescriptor&) override;
+    void postFlush(const RenderContext::FlushResources&) override;
+
+    double secondsNow() const override
+    {
+        auto elapsed = std::chrono::steady_clock::now() - m_localEpoch;
+        return std::chrono::duration<double>(elapsed).count();
+    }
+
+private:
+    RenderContextCUDAImpl(const RiveCudaABI&, rivecuda_ctx*);
+
+    void resizeBuffer(rivecuda_buffer_kind, size_t sizeInBytes);
+    void* mapBuffer(rivecuda_buffer_kind, size_t mapSizeInBytes);
+    void unmapBuffer(rivecuda_buffer_kind, size_t mapSizeInBytes);
+
+    const RiveCudaABI& m_abi;
+    rivecuda_ctx* m_ctx;
+    std::vector<rivecuda_draw_batch> m_batchScratch;
+    std::vector<rivecuda_atlas_batch> m_atlasScratch;
+    std::chrono::steady_clock::time_point m_localEpoch =
+        std::chrono::steady_clock::now();
+};
+} // namespace rive::gpu
