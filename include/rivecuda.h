@@ -57,8 +57,7 @@ typedef enum rivecuda_buffer_kind
     RIVECUDA_BUFFER_GRAD_SPAN = 5,     /* GradientSpan, 16 B                 */
     RIVECUDA_BUFFER_TESS_SPAN = 6,     /* TessVertexSpan, 64 B               */
     RIVECUDA_BUFFER_TRIANGLE = 7,      /* TriangleVertex, 12 B               */
-    RIVECUDA_BUFFER_IMAGE_DRAW = 8,    /* ImageDrawInstance, 64 B (256 B     */
-                                       /* stride, see render_context.cpp)    */
+    RIVECUDA_BUFFER_IMAGE_DRAW = 8,    /* ImageDrawInstance, 64 B            */
     RIVECUDA_BUFFER_KIND_COUNT = 9
 } rivecuda_buffer_kind;
 
@@ -105,9 +104,9 @@ enum
     RIVECUDA_MISC_CLOCKWISE_FILL = 1 << 1
 };
 
-/* rive::ImageSampler key (include/rive/shapes/paint/image_sampler.hpp:8-27):
- * wrapX | wrapY<<2 | filter<<4; wrap: 0 clamp, 1 repeat, 2 mirror; filter: 0
- * bilinear, 1 nearest. */
+/* rive::ImageSampler::asKey() (include/rive/shapes/paint/image_sampler.hpp:
+ * 60-65): wrapX + 3*wrapY + 9*filter; wrap: 0 clamp, 1 repeat, 2 mirror;
+ * filter: 0 bilinear, 1 nearest. */
 typedef uint8_t rivecuda_sampler_key;
 
 /* POD mirror of gpu::DrawBatch (gpu.hpp:1219-1282), one per node of
@@ -188,13 +187,26 @@ typedef struct rivecuda_flush_timings
 
 /* ---- context ----------------------------------------------------------- */
 
-/* Create a context on CUDA device `device`. Uploads the static patch vertex /
- * index buffers (gpu.cpp:669 GeneratePatchBufferData, rebuilt natively) and the
- * two Gaussian-integral tables (gpu.hpp:2088-2090). */
+/* Create a context on CUDA device `device`. */
 int rivecuda_create(int device, rivecuda_ctx** out_ctx);
 void rivecuda_destroy(rivecuda_ctx* ctx);
 const char* rivecuda_last_error(void);
 uint32_t rivecuda_abi_version(void);
+
+/* Upload the constant tables every backend of the reference uploads once at
+ * start-up: the static patch vertex / index buffers produced by
+ * gpu::GeneratePatchBufferData (gpu.cpp:669; 269 PatchVertex of 32 B, 441 u16
+ * indices, gpu.hpp:547-655) and the two 512-entry fp16 Gaussian-integral
+ * tables g_gaussianIntegralTableF16 / g_inverseGaussianIntegralTableF16
+ * (gpu.hpp:2088-2090). Must be called before the first rivecuda_flush(). */
+int rivecuda_set_static_tables(rivecuda_ctx* ctx,
+                               const void* patch_vertices,
+                               uint32_t patch_vertex_count,
+                               const uint16_t* patch_indices,
+                               uint32_t patch_index_count,
+                               const uint16_t* gaussian_integral_f16,
+                               const uint16_t* inverse_gaussian_integral_f16,
+                               uint32_t gaussian_table_size);
 
 /* ---- mapped resource buffers (rings of 3, pinned host + device copy) ---- */
 
@@ -291,8 +303,6 @@ int rivecuda_debug_read_tessellation(rivecuda_ctx* ctx, void* host_dst, size_t f
 int rivecuda_debug_read_gradient(rivecuda_ctx* ctx, void* host_dst, uint32_t height);
 /* Copy the feather atlas (float32 coverage, atlas width x height). */
 int rivecuda_debug_read_atlas(rivecuda_ctx* ctx, void* host_dst, uint32_t width, uint32_t height);
-/* The static patch vertex (269 x 32 B) and index (441 x u16) buffers. */
-int rivecuda_debug_read_patch_buffers(rivecuda_ctx* ctx, void* host_vertices, size_t vertices_size, void* host_indices, size_t indices_size);
 
 #ifdef __cplusplus
 }

@@ -120,6 +120,33 @@ void rivecuda_destroy(rivecuda_ctx* ctx)
     delete ctx;
 }
 
+int rivecuda_set_static_tables(rivecuda_ctx* ctx,
+                               const void* patchVertices,
+                               uint32_t nVerts,
+                               const uint16_t* patchIndices,
+                               uint32_t nIndices,
+                               const uint16_t* gauss,
+                               const uint16_t* inverseGauss,
+                               uint32_t nGauss)
+{
+    Record r;
+    r.u32(nVerts);
+    r.u32(nIndices);
+    r.u32(nGauss);
+    r.u32(0);
+    r.blob(patchVertices, static_cast<size_t>(nVerts) * 32);
+    r.blob(patchIndices, static_cast<size_t>(nIndices) * 2);
+    if (nIndices & 1)
+    {
+        uint16_t pad = 0;
+        r.put(pad);
+    }
+    r.blob(gauss, static_cast<size_t>(nGauss) * 2);
+    r.blob(inverseGauss, static_cast<size_t>(nGauss) * 2);
+    write_record(ctx, RVCT_STATIC_TABLES, r);
+    return 0;
+}
+
 int rivecuda_buffer_resize(rivecuda_ctx* ctx, uint32_t kind, size_t size)
 {
     if (kind >= RIVECUDA_BUFFER_KIND_COUNT)
@@ -397,10 +424,6 @@ int rivecuda_debug_read_gradient(rivecuda_ctx*, void*, uint32_t)
     return fail("rivecuda_trace: the recorder computes nothing");
 }
 int rivecuda_debug_read_atlas(rivecuda_ctx*, void*, uint32_t, uint32_t)
-{
-    return fail("rivecuda_trace: the recorder computes nothing");
-}
-int rivecuda_debug_read_patch_buffers(rivecuda_ctx*, void*, size_t, void*, size_t)
 {
     return fail("rivecuda_trace: the recorder computes nothing");
 }

@@ -42,7 +42,10 @@ enum rvct_tag
                                   /* rivecuda_draw_batch[n] (pointers := ids),  */
                                   /* rivecuda_atlas_batch[nFill+nStroke]        */
     RVCT_POST_FLUSH = 18,         /* (empty)                                    */
-    RVCT_DESTROY = 19             /* (empty)                                    */
+    RVCT_DESTROY = 19,            /* (empty)                                    */
+    RVCT_STATIC_TABLES = 20       /* u32 nPatchVerts, nPatchIdx, nGauss, u32 0, */
+                                  /* PatchVertex[nV](32 B), u16[nI] pad to 4,   */
+                                  /* u16 gauss[n], u16 inverseGauss[n]          */
 };
 
 #endif

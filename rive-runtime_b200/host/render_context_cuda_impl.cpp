@@ -244,6 +244,21 @@ RenderContextCUDAImpl::RenderContextCUDAImpl(const RiveCudaABI& abi,
     m_platformFeatures.supportsClipScissor = false;
     m_platformFeatures.pathIDGranularity = 1;
     m_platformFeatures.maxTextureSize = 32768;
+
+    // Upload the constant tables every backend uploads at start-up (compare
+    // RenderContextVulkanImpl::initGPUObjects): patch geometry and the feather
+    // LUTs, both taken from the reference's own public symbols.
+    std::vector<PatchVertex> patchVertices(kPatchVertexBufferCount);
+    std::vector<uint16_t> patchIndices(kPatchIndexBufferCount);
+    GeneratePatchBufferData(patchVertices.data(), patchIndices.data());
+    ABI_CHECK(m_abi.set_static_tables(m_ctx,
+                                      patchVertices.data(),
+                                      kPatchVertexBufferCount,
+                                      patchIndices.data(),
+                                      kPatchIndexBufferCount,
+                                      g_gaussianIntegralTableF16,
+                                      g_inverseGaussianIntegralTableF16,
+                                      GAUSSIAN_TABLE_SIZE));
 }
 
 RenderContextCUDAImpl::~RenderContextCUDAImpl()
