@@ -1,0 +1,1935 @@
+/*
+ * K4/K5: the draw list for sm_100a -- patch vertex expansion, triangle setup,
+ * tile binning, and the tile rasteriser with fused coverage / clip / paint /
+ * blend resolve.
+ *
+ * Replaces, for InterlockMode::rasterOrdering, the reference's draw pipelines:
+ *   vertex stage   draw_path_common.glsl:275-789 unpack_tessellated_path_vertex,
+ *                  draw_path.vert:96-408, :793-844 (interior triangles, atlas)
+ *   fixed function instanced indexed draws of the static patch buffers
+ *                  (render_context_vulkan_impl.cpp:3950-4084), back-face
+ *                  culling (gpu.cpp:1552 get_cull_face), top-left rasterisation
+ *   fragment stage draw_raster_order_path.frag:14-238, draw_path.vert:431-547,
+ *                  advanced_blend.glsl, common.glsl:269-336 (dither)
+ *
+ * Design (not a port of the raster pipeline):
+ *   setup_patches_kernel   one warp per patch instance: lanes shade the patch's
+ *                          42/74/153 vertices into shared memory, then lanes
+ *                          assemble, snap (8 sub-pixel bits), cull and store
+ *                          the instance's triangles and count the 16x16 tiles
+ *                          each one overlaps (exact integer edge/tile tests).
+ *   scan + scatter         exclusive scan of the per-tile counts, then each
+ *                          triangle's id is appended to its tiles' lists.
+ *   sort_tiles_kernel      one CTA per tile sorts its list by triangle id,
+ *                          which restores API (draw) order inside the tile.
+ *   raster_tiles_kernel    one CTA (256 threads, one pixel per thread) per
+ *                          tile. Colour, clip and coverage planes live in
+ *                          REGISTERS for the whole flush; triangles are
+ *                          prepared 256 at a time into shared memory (exact
+ *                          int32 tile-local edge functions + coverage planes)
+ *                          and broadcast to all pixels. A path's coverage is
+ *                          accumulated over all its triangles and resolved
+ *                          ONCE per pixel when the path id changes -- in-order
+ *                          compositing without any interlock or atomics -- and
+ *                          the framebuffer is written exactly once, coalesced.
+ */
+#include "rivecuda_internal.h"
+#include "device_math.cuh"
+
+#include <cuda_fp16.h>
+
+#include <algorithm>
+
+namespace rivecuda
+{
+// ---------------------------------------------------------------------------
+// Records
+
+enum TriKind : uint32_t
+{
+    kKindFill = 0,          // coverage += plane0 (also interior triangles)
+    kKindStroke = 1,        // coverage = max(coverage, min(plane0, plane1))
+    kKindFeatherFill = 2,   // coverage += eval_feathered_fill(4 planes)
+    kKindFeatherStroke = 3, // coverage = max(coverage, eval_feathered_stroke)
+    kKindAtlasBlit = 4,     // immediate blend, coverage from the atlas
+    kKindImageMesh = 5,     // immediate blend, colour from an image
+};
+
+constexpr uint32_t kMetaValid = 1u << 31;
+constexpr uint32_t kMetaClockwiseFill = 1u << 30;
+constexpr uint32_t kMetaKindShift = 16;
+
+struct TriGeom // 32 B
+{
+    int32_t x0, y0, x1, y1, x2, y2; // snapped, clockwise
+    uint32_t meta;                  // pathID | kind << 16 | flags
+    uint32_t aux;                   // image mesh: batch index; else 0
+};
+static_assert(sizeof(TriGeom) == 32, "TriGeom");
+
+struct TriAttr // 48 B: attr[c*3 + k] = component c at vertex k
+{
+    float attr[12];
+};
+
+struct FlushParams
+{
+    const uint4* pathBuffer;
+    const uint2* paintBuffer;
+    const float4* paintAuxBuffer;
+    const uint4* contourBuffer;
+    const float* triangleVertices;     // frame-wide, 3 floats per vertex
+    const uint8_t* imageDrawInstances; // frame-wide, 64 B each
+    const uint4* tess;
+    uint32_t tessVertexCount;
+    const float* patchVertices; // 8 floats per PatchVertex
+    const uint16_t* patchIndices;
+    const float* featherLUT;
+    const uint32_t* gradTexture;
+    uint32_t gradHeight;
+    const float* atlas;
+    uint32_t atlasWidth, atlasHeight;
+    float atlasInvWidth, atlasInvHeight;
+    uint32_t wireframe;
+    // Raster target / tiling.
+    uint32_t* target;
+    uint32_t targetWidth, targetHeight;
+    int32_t boundsL, boundsT, boundsR, boundsB;
+    int32_t tileX0, tileY0; // first tile (in tile units)
+    uint32_t tilesX, tilesY;
+    uint32_t loadAction;
+    uint32_t clearColorPremulRGBA;
+    float ditherScale, ditherBias;
+};
+
+// ---------------------------------------------------------------------------
+// Patch vertex shading (draw_path_common.glsl:275-789)
+
+struct ShadedVertex
+{
+    float x, y;
+    float c0, c1, c2, c3;
+    uint32_t pathID_ok; // pathID | ok << 16
+};
+
+__device__ __forceinline__ uint4 tess_fetch(const FlushParams& P, int idx)
+{
+    if (idx < 0 || static_cast<uint32_t>(idx) >= P.tessVertexCount)
+        return make_uint4(0, 0, 0, 0);
+    return __ldg(P.tess + idx);
+}
+
+__device__ __forceinline__ float manhattan_pixel_width(m22 M, f2 n)
+{
+    f2 v = mul(M, n);
+    return (fabsf(v.x) + fabsf(v.y)) * (1.f / dot2(v, v));
+}
+
+__device__ float4 pack_feathered_fill_coverages(float cornerTheta, f2 spokeNorm, float outset)
+{
+    f2 corner = mk2((1.f - spokeNorm.x * fabsf(outset)) * .5f, (1.f - spokeNorm.y * fabsf(outset)) * .5f);
+    float cotTheta, y0;
+    if (fabsf(cornerTheta - kPI_2) < 1.f / kHorizontalCotangentThreshold)
+    {
+        cotTheta = 0.f;
+        y0 = 0.f;
+    }
+    else
+    {
+        float tanTheta = tanf(cornerTheta);
+        cotTheta = signf(kPI_2 - cornerTheta) / fmaxf(fabsf(tanTheta), 1.f / kHorizontalCotangentValue);
+        y0 = cotTheta >= 0.f ? corner.y - (1.f - corner.x) * tanTheta : corner.y + corner.x * tanTheta;
+    }
+    return make_float4(fmaxf(corner.x, 0.f) + kFeatherXCoordBias, -corner.y + kFeatherCoverageBias, cotTheta, y0);
+}
+
+__device__ ShadedVertex shade_patch_vertex(const FlushParams& P, const float* __restrict__ pv, int instanceID, bool enableFeather)
+{
+    ShadedVertex out;
+    int localVertexID = static_cast<int>(__ldg(pv + 0));
+    float outset = __ldg(pv + 1);
+    float fillCoverage = __ldg(pv + 2);
+    const int params = __float_as_int(__ldg(pv + 3));
+    const int patchSegmentSpan = params >> 2;
+    const int vertexType = params & 3;
+
+    const int vertexIDOnContour = min(localVertexID, patchSegmentSpan - 1);
+    int tessVertexIdx = instanceID * patchSegmentSpan + vertexIDOnContour;
+    uint4 tv = tess_fetch(P, tessVertexIdx);
+    uint32_t flags = tv.w;
+
+    const uint32_t contourID = max(flags & kContourIDMask, 1u);
+    const uint4 contourData = __ldg(P.contourBuffer + (contourID - 1u));
+    const f2 midpoint = mk2(__uint_as_float(contourData.x), __uint_as_float(contourData.y));
+    const uint32_t pathID = contourData.z & 0xffffu;
+    const uint32_t vertexIndex0 = contourData.w;
+
+    const uint4 m4 = __ldg(P.pathBuffer + pathID * 4u);
+    const m22 M = {__uint_as_float(m4.x), __uint_as_float(m4.y), __uint_as_float(m4.z), __uint_as_float(m4.w)};
+    const uint4 pd = __ldg(P.pathBuffer + pathID * 4u + 1u);
+    const f2 translate = mk2(__uint_as_float(pd.x), __uint_as_float(pd.y));
+    float strokeRadius = __uint_as_float(pd.z);
+    float featherRadius = __uint_as_float(pd.w);
+
+    const uint32_t mirroredFlag = flags & kMirroredContourFlag;
+    if (mirroredFlag != 0u)
+    {
+        localVertexID = static_cast<int>(__ldg(pv + 4));
+        outset = __ldg(pv + 5);
+        fillCoverage = __ldg(pv + 6);
+    }
+    if (localVertexID != vertexIDOnContour)
+    {
+        const int replacementIdx = tessVertexIdx + localVertexID - vertexIDOnContour;
+        const uint4 rv = tess_fetch(P, replacementIdx);
+        if ((rv.w & (kMirroredContourFlag | 0xffffu)) != (flags & (kMirroredContourFlag | 0xffffu)))
+        {
+            const bool isClosed = strokeRadius == 0.f || midpoint.x != 0.f;
+            if (isClosed)
+            {
+                tessVertexIdx = static_cast<int>(vertexIndex0);
+                tv = tess_fetch(P, tessVertexIdx);
+            }
+        }
+        else
+        {
+            tessVertexIdx = replacementIdx;
+            tv = rv;
+        }
+        flags = (tv.w & ~kMirroredContourFlag) | mirroredFlag;
+    }
+
+    float theta;
+    float featherJoinEdge0Theta = 0.f, featherJoinCornerTheta = 0.f;
+    const bool isFeatherJoinVertex = enableFeather && (flags & kJoinTypeMask) == kFeatherJoin && vertexType == kStrokeVertex;
+    if (isFeatherJoinVertex)
+    {
+        const uint32_t packed = tv.z;
+        float joinVertexID = static_cast<float>(packed & 0xffffu);
+        float joinSegmentCount = static_cast<float>(packed >> 16);
+        int off0 = static_cast<int>(-joinVertexID - 1.f);
+        int off1 = static_cast<int>(joinSegmentCount - joinVertexID + 1.f);
+        if ((flags & kMirroredContourFlag) != 0u)
+        {
+            off0 = -off0;
+            off1 = -off1;
+        }
+        const uint4 before = tess_fetch(P, tessVertexIdx + off0);
+        uint4 after = tess_fetch(P, tessVertexIdx + off1);
+        if ((after.w & (kMirroredContourFlag | 0xffffu)) != (before.w & (kMirroredContourFlag | 0xffffu)))
+            after = tess_fetch(P, static_cast<int>(vertexIndex0));
+        featherJoinEdge0Theta = __uint_as_float(before.z);
+        const float edge1Theta = __uint_as_float(after.z);
+        featherJoinCornerTheta = edge1Theta - featherJoinEdge0Theta;
+        if (fabsf(featherJoinCornerTheta) > kPI)
+            featherJoinCornerTheta -= k2PI * signf(featherJoinCornerTheta);
+        const float nonHelper = joinSegmentCount + 1.f - 3.f;
+        const float forwardCount = clampf(roundf(fabsf(featherJoinCornerTheta) / kPI * nonHelper), 1.f, nonHelper - 1.f);
+        const float backwardCount = nonHelper - forwardCount;
+        if (joinVertexID <= backwardCount)
+        {
+            featherJoinCornerTheta = -(kPI * signf(featherJoinCornerTheta) - featherJoinCornerTheta);
+            joinSegmentCount = backwardCount;
+            if (joinVertexID == backwardCount)
+                outset = -outset;
+        }
+        else if (joinVertexID == backwardCount + 1.f)
+        {
+            joinVertexID = 0.f;
+            joinSegmentCount = 0.f;
+            outset = 0.f;
+        }
+        else
+        {
+            joinVertexID -= backwardCount + 2.f;
+            joinSegmentCount = forwardCount;
+        }
+        if (joinVertexID == joinSegmentCount)
+            theta = edge1Theta;
+        else
+            theta = featherJoinEdge0Theta + featherJoinCornerTheta * (joinVertexID / joinSegmentCount);
+    }
+    else
+    {
+        theta = __uint_as_float(tv.z);
+    }
+    const f2 nrm = mk2(sinf(theta), -cosf(theta));
+    f2 origin = mk2(__uint_as_float(tv.x), __uint_as_float(tv.y));
+    f2 postTransformOffset = mk2(0.f, 0.f);
+    float4 cov;
+    bool ok = true;
+
+    if (featherRadius != 0.f)
+        featherRadius = fmaxf(featherRadius, (kGaussianStddevs / 3.f) / len2(mul(M, nrm)));
+
+    if (strokeRadius != 0.f)
+    {
+        outset *= signf(det(M));
+        if ((flags & kLeftJoinFlag) != 0u)
+            outset = fminf(outset, 0.f);
+        if ((flags & kRightJoinFlag) != 0u)
+            outset = fmaxf(outset, 0.f);
+        const float aaRadius = featherRadius != 0.f ? featherRadius : manhattan_pixel_width(M, nrm) * .5f;
+        float globalCoverage = 1.f;
+        if (aaRadius > strokeRadius && featherRadius == 0.f)
+        {
+            globalCoverage = strokeRadius / aaRadius;
+            strokeRadius = aaRadius;
+        }
+        f2 vertexOffset = nrm * (strokeRadius + aaRadius);
+        const float x = outset * (strokeRadius + aaRadius);
+        cov.x = (1.f / (aaRadius * 2.f)) * (x + strokeRadius) + .5f;
+        cov.y = (1.f / (aaRadius * 2.f)) * (-x + strokeRadius) + .5f;
+        cov.z = 0.f;
+        cov.w = 0.f;
+        const uint32_t joinType = flags & kJoinTypeMask;
+        if (joinType > kRoundJoin)
+        {
+            int peekDir = 2;
+            if ((flags & kJoinTangent0Flag) == 0u)
+                peekDir = -peekDir;
+            if ((flags & kMirroredContourFlag) != 0u)
+                peekDir = -peekDir;
+            const uint4 other = tess_fetch(P, tessVertexIdx + peekDir);
+            const float otherTheta = __uint_as_float(other.z);
+            float joinAngle = fabsf(otherTheta - theta);
+            if (joinAngle > kPI)
+                joinAngle = k2PI - joinAngle;
+            const bool isTan0 = (flags & kJoinTangent0Flag) != 0u;
+            const bool isLeftJoin = (flags & kLeftJoinFlag) != 0u;
+            const float bisectTheta = joinAngle * (isTan0 == isLeftJoin ? -.5f : .5f) + theta;
+            const f2 bisector = mk2(sinf(bisectTheta), -cosf(bisectTheta));
+            const float bisectPixelWidth = manhattan_pixel_width(M, bisector);
+            const float miterRatio = cosf(joinAngle * .5f);
+            float clipRadius;
+            if (joinType == kMiterClipJoin || (joinType == kMiterRevertJoin && miterRatio >= .25f))
+            {
+                const float miterInverseLimit = (flags & kEmulatedStrokeCapFlag) != 0u ? 1.f : .25f;
+                clipRadius = strokeRadius * (1.f / fmaxf(miterRatio, miterInverseLimit));
+            }
+            else
+            {
+                clipRadius = strokeRadius * miterRatio + bisectPixelWidth * .5f;
+            }
+            const float clipAARadius = clipRadius + bisectPixelWidth * .5f;
+            if ((flags & kJoinTangentInnerFlag) != 0u)
+            {
+                const float strokeAARadius = strokeRadius + aaRadius;
+                const float slop = aaRadius * .125f;
+                if (strokeAARadius <= clipAARadius * miterRatio + slop)
+                {
+                    vertexOffset = bisector * (strokeAARadius * (1.f / miterRatio));
+                }
+                else
+                {
+                    const f2 bisectAAOffset = bisector * clipAARadius;
+                    const f2 k = mk2(dot2(vertexOffset, vertexOffset), dot2(bisectAAOffset, bisectAAOffset));
+                    // MUL(k, inverse(float2x2(vertexOffset, bisectAAOffset)))
+                    const m22 mm = {vertexOffset.x, vertexOffset.y, bisectAAOffset.x, bisectAAOffset.y};
+                    vertexOffset = mulT(k, inverse(mm));
+                }
+            }
+            const f2 pt = vertexOffset * fabsf(outset);
+            const float clipDistance = (clipAARadius - dot2(pt, bisector)) / (bisectPixelWidth * 1.f);
+            if ((flags & kLeftJoinFlag) != 0u)
+                cov.y = clipDistance;
+            else
+                cov.x = clipDistance;
+        }
+        cov.x *= globalCoverage;
+        cov.y *= globalCoverage;
+        cov.y = fmaxf(cov.y, 1e-4f);
+        if (featherRadius != 0.f)
+            cov.x = kFeatherCoverageBias - cov.x;
+        postTransformOffset = mul(M, vertexOffset * outset);
+        if (vertexType != kStrokeVertex)
+            ok = false;
+    }
+    else
+    {
+        cov = make_float4(fillCoverage, -1.f, 0.f, 0.f);
+        if (enableFeather && featherRadius != 0.f)
+        {
+            cov.y = kFeatherCoverageBias;
+            cov.z = kHorizontalCotangentValue;
+            cov.w = fillCoverage;
+            if (isFeatherJoinVertex)
+            {
+                if (featherJoinCornerTheta < 0.f)
+                {
+                    featherJoinEdge0Theta += featherJoinCornerTheta;
+                    featherJoinCornerTheta = -featherJoinCornerTheta;
+                }
+                float spokeTheta = theta - featherJoinEdge0Theta;
+                spokeTheta = modglsl(spokeTheta + kPI_2, k2PI) - kPI_2;
+                spokeTheta = clampf(spokeTheta, 0.f, featherJoinCornerTheta);
+                if (spokeTheta > featherJoinCornerTheta * .5f)
+                    spokeTheta = featherJoinCornerTheta - spokeTheta;
+                cov = pack_feathered_fill_coverages(featherJoinCornerTheta, mk2(sinf(spokeTheta), cosf(spokeTheta)), outset);
+            }
+            postTransformOffset = mul(M, nrm * (outset * featherRadius));
+        }
+        else
+        {
+            const f2 v = mulT(nrm * outset, inverse(M));
+            postTransformOffset = mk2(signf(v.x) * .5f, signf(v.y) * .5f);
+        }
+        if (((flags & kMirroredContourFlag) != 0u) != ((flags & kNegateFillCoverageFlag) != 0u))
+            cov.x = -cov.x;
+        if (vertexType == kFanMidpointVertex)
+            origin = midpoint;
+        if ((flags & kRetrofitTriStripFlag) != 0u && vertexType != kFanVertex)
+            ok = false;
+    }
+    const f2 pos = mul(M, origin) + postTransformOffset + translate;
+    if (P.wireframe != 0u)
+    {
+        cov.x = 1.f;
+        cov.y = -1.f;
+    }
+    out.x = pos.x;
+    out.y = pos.y;
+    out.c0 = cov.x;
+    out.c1 = cov.y;
+    out.c2 = cov.z;
+    out.c3 = cov.w;
+    out.pathID_ok = pathID | (ok ? 0x10000u : 0u);
+    return out;
+}
+
+// ---------------------------------------------------------------------------
+// Snapping, tile overlap
+
+__device__ __forceinline__ bool snap_coord(float v, int32_t& out)
+{
+    if (!(v == v))
+        return false;
+    v = fminf(fmaxf(v, -4194304.f), 4194304.f);
+    out = static_cast<int32_t>(__float2ll_rn(v * 256.f));
+    return true;
+}
+
+struct TileRange
+{
+    int tx0, ty0, tx1, ty1; // inclusive, in tile units relative to the grid; empty if tx0 > tx1
+};
+
+// Pixel bounds of the pixel centres a snapped triangle can cover, clipped to the
+// render bounds, as a tile range.
+__device__ __forceinline__ TileRange triangle_tile_range(const FlushParams& P, const int32_t X[3], const int32_t Y[3])
+{
+    const int32_t minX = min(X[0], min(X[1], X[2])), maxX = max(X[0], max(X[1], X[2]));
+    const int32_t minY = min(Y[0], min(Y[1], Y[2])), maxY = max(Y[0], max(Y[1], Y[2]));
+    // Pixel p has its centre at 256*p + 128: p >= ceil((min-128)/256), p <= floor((max-128)/256).
+    int px0 = (minX - 128 + 255) >> 8, px1 = (maxX - 128) >> 8;
+    int py0 = (minY - 128 + 255) >> 8, py1 = (maxY - 128) >> 8;
+    px0 = max(px0, P.boundsL);
+    py0 = max(py0, P.boundsT);
+    px1 = min(px1, P.boundsR - 1);
+    py1 = min(py1, P.boundsB - 1);
+    TileRange r;
+    if (px0 > px1 || py0 > py1)
+    {
+        r.tx0 = 1;
+        r.tx1 = 0;
+        r.ty0 = 1;
+        r.ty1 = 0;
+        return r;
+    }
+    r.tx0 = (px0 >> kTileSizeLog2) - P.tileX0;
+    r.tx1 = (px1 >> kTileSizeLog2) - P.tileX0;
+    r.ty0 = (py0 >> kTileSizeLog2) - P.tileY0;
+    r.ty1 = (py1 >> kTileSizeLog2) - P.tileY0;
+    return r;
+}
+
+struct EdgeEq
+{
+    int64_t A, B, C; // E(px,py) = A*px + B*py + C - bias >= 0 inside (sub-pixel units)
+};
+
+__device__ __forceinline__ void edge_equations(const int32_t X[3], const int32_t Y[3], EdgeEq E[3])
+{
+#pragma unroll
+    for (int e = 0; e < 3; ++e)
+    {
+        const int a = (e + 1) % 3, b = (e + 2) % 3;
+        const int64_t dx = static_cast<int64_t>(X[b]) - X[a], dy = static_cast<int64_t>(Y[b]) - Y[a];
+        const bool topLeft = (dy == 0 && dx > 0) || (dy < 0);
+        E[e].A = -dy;
+        E[e].B = dx;
+        E[e].C = dy * X[a] - dx * Y[a] - (topLeft ? 0 : 1);
+    }
+}
+
+// Does any pixel centre of tile (absolute tile coords) possibly lie inside?
+// Exact: evaluates each edge at the tile's most-inside pixel centre.
+__device__ __forceinline__ bool tile_overlaps(const EdgeEq E[3], int tileX, int tileY)
+{
+    const int64_t px0 = (static_cast<int64_t>(tileX) << (kTileSizeLog2 + 8)) + 128;
+    const int64_t py0 = (static_cast<int64_t>(tileY) << (kTileSizeLog2 + 8)) + 128;
+    const int64_t span = static_cast<int64_t>(kTileSize - 1) << 8;
+#pragma unroll
+    for (int e = 0; e < 3; ++e)
+    {
+        const int64_t px = E[e].A > 0 ? px0 + span : px0;
+        const int64_t py = E[e].B > 0 ? py0 + span : py0;
+        if (E[e].A * px + E[e].B * py + E[e].C < 0)
+            return false;
+    }
+    return true;
+}
+
+// Visits the tiles a triangle overlaps (absolute tile index = ty*tilesX+tx in
+// the flush's tile grid).
+template <typename Fn> __device__ __forceinline__ void for_each_tile(const FlushParams& P, const int32_t X[3], const int32_t Y[3], Fn&& fn)
+{
+    const TileRange r = triangle_tile_range(P, X, Y);
+    if (r.tx0 > r.tx1)
+        return;
+    const bool single = (r.tx0 == r.tx1) && (r.ty0 == r.ty1);
+    EdgeEq E[3];
+    edge_equations(X, Y, E);
+    for (int ty = r.ty0; ty <= r.ty1; ++ty)
+    {
+        for (int tx = r.tx0; tx <= r.tx1; ++tx)
+        {
+            if (single || tile_overlaps(E, tx + P.tileX0, ty + P.tileY0))
+                fn(static_cast<uint32_t>(ty) * P.tilesX + static_cast<uint32_t>(tx));
+        }
+    }
+}
+
+// Snap, orient, cull and store one triangle; returns true if stored.
+// attr[c*3+k]. cullCCW false => counter-clockwise triangles are re-wound.
+__device__ __forceinline__ bool store_triangle(const FlushParams& P,
+                                               TriGeom* __restrict__ triGeom,
+                                               TriAttr* __restrict__ triAttr,
+                                               uint32_t* __restrict__ tileCounts,
+                                               uint32_t rawTri,
+                                               const float xs[3],
+                                               const float ys[3],
+                                               float attr[12],
+                                               int attrComponents,
+                                               uint32_t meta,
+                                               uint32_t aux,
+                                               bool cullCCW)
+{
+    int32_t X[3], Y[3];
+    bool ok = true;
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+        ok = ok && snap_coord(xs[k], X[k]) && snap_coord(ys[k], Y[k]);
+    int64_t area2 = 0;
+    if (ok)
+    {
+        area2 = (static_cast<int64_t>(X[1]) - X[0]) * (static_cast<int64_t>(Y[2]) - Y[0]) -
+                (static_cast<int64_t>(X[2]) - X[0]) * (static_cast<int64_t>(Y[1]) - Y[0]);
+        if (area2 == 0 || (area2 < 0 && cullCCW))
+            ok = false;
+    }
+    if (ok && area2 < 0)
+    {
+        int32_t t = X[1];
+        X[1] = X[2];
+        X[2] = t;
+        t = Y[1];
+        Y[1] = Y[2];
+        Y[2] = t;
+        for (int c = 0; c < attrComponents; ++c)
+        {
+            float f = attr[c * 3 + 1];
+            attr[c * 3 + 1] = attr[c * 3 + 2];
+            attr[c * 3 + 2] = f;
+        }
+        if (((meta >> kMetaKindShift) & 0xf) == kKindFeatherFill)
+        {
+            // Back-facing feathered fills (atlas) subtract; the sign lives in
+            // component 0's sign, which the caller has already applied.
+        }
+    }
+    if (ok)
+    {
+        const TileRange r = triangle_tile_range(P, X, Y);
+        if (r.tx0 > r.tx1)
+            ok = false;
+    }
+    TriGeom g;
+    if (!ok)
+    {
+        g.x0 = g.y0 = g.x1 = g.y1 = g.x2 = g.y2 = 0;
+        g.meta = 0;
+        g.aux = 0;
+        triGeom[rawTri] = g;
+        return false;
+    }
+    g.x0 = X[0];
+    g.y0 = Y[0];
+    g.x1 = X[1];
+    g.y1 = Y[1];
+    g.x2 = X[2];
+    g.y2 = Y[2];
+    g.meta = meta | kMetaValid;
+    g.aux = aux;
+    triGeom[rawTri] = g;
+    float4* dst = reinterpret_cast<float4*>(triAttr + rawTri);
+    dst[0] = make_float4(attr[0], attr[1], attr[2], attr[3]);
+    if (attrComponents > 1)
+        dst[1] = make_float4(attr[4], attr[5], attr[6], attr[7]);
+    if (attrComponents > 2)
+        dst[2] = make_float4(attr[8], attr[9], attr[10], attr[11]);
+    for_each_tile(P, X, Y, [&](uint32_t tile) { atomicAdd(tileCounts + tile, 1u); });
+    return true;
+}
+
+// ---------------------------------------------------------------------------
+// Setup kernels
+
+constexpr int kSetupWarpsPerBlock = 4;
+constexpr int kMaxPatchVertices = 153;
+
+__device__ __forceinline__ uint32_t find_batch(const DeviceBatch* __restrict__ batches, uint32_t batchCount, uint32_t workItem)
+{
+    uint32_t lo = 0, hi = batchCount;
+    while (hi - lo > 1)
+    {
+        uint32_t mid = (lo + hi) >> 1;
+        if (__ldg(&batches[mid].firstWorkItem) <= workItem)
+            lo = mid;
+        else
+            hi = mid;
+    }
+    return lo;
+}
+
+// One warp per patch instance.
+__global__ void __launch_bounds__(kSetupWarpsPerBlock * 32) setup_patches_kernel(FlushParams P,
+                                                                                const DeviceBatch* __restrict__ batches,
+                                                                                uint32_t batchCount,
+                                                                                uint32_t totalInstances,
+                                                                                TriGeom* __restrict__ triGeom,
+                                                                                TriAttr* __restrict__ triAttr,
+                                                                                uint32_t* __restrict__ tileCounts)
+{
+    __shared__ ShadedVertex s_verts[kSetupWarpsPerBlock][kMaxPatchVertices];
+    const int lane = threadIdx.x & 31;
+    const int warpInBlock = threadIdx.x >> 5;
+    ShadedVertex* verts = s_verts[warpInBlock];
+    const uint32_t warpsPerGrid = gridDim.x * kSetupWarpsPerBlock;
+    for (uint32_t item = blockIdx.x * kSetupWarpsPerBlock + warpInBlock; item < totalInstances; item += warpsPerGrid)
+    {
+        const uint32_t bi = find_batch(batches, batchCount, item);
+        const DeviceBatch b = batches[bi];
+        const uint32_t inst = item - b.firstWorkItem;
+        const int instanceID = static_cast<int>(b.baseElement + inst);
+        const bool enableFeather = (b.flags & RIVECUDA_FEATURE_FEATHER) != 0u;
+        // Patch type => vertex range of the static patch vertex buffer.
+        uint32_t vmin, vcount;
+        if (b.drawType == RIVECUDA_DRAW_MIDPOINT_FAN_PATCHES)
+        {
+            vmin = 0;
+            vcount = 42;
+        }
+        else if (b.drawType == RIVECUDA_DRAW_MIDPOINT_FAN_CENTER_AA_PATCHES)
+        {
+            vmin = 42;
+            vcount = 74;
+        }
+        else
+        {
+            vmin = 116;
+            vcount = 153;
+        }
+        __syncwarp();
+        for (uint32_t v = lane; v < vcount; v += 32)
+            verts[v] = shade_patch_vertex(P, P.patchVertices + (vmin + v) * 8, instanceID, enableFeather);
+        __syncwarp();
+        const uint32_t tris = b.trisPerElement;
+        for (uint32_t t = lane; t < tris; t += 32)
+        {
+            const uint32_t rawTri = b.firstTriangle + inst * tris + t;
+            const uint32_t i0 = __ldg(P.patchIndices + b.baseIndex + t * 3 + 0) - vmin;
+            const uint32_t i1 = __ldg(P.patchIndices + b.baseIndex + t * 3 + 1) - vmin;
+            const uint32_t i2 = __ldg(P.patchIndices + b.baseIndex + t * 3 + 2) - vmin;
+            const ShadedVertex a = verts[i0], c = verts[i1], d = verts[i2];
+            const uint32_t pathID = a.pathID_ok & 0xffffu; // flat varying: provoking vertex
+            const bool ok = (a.pathID_ok & c.pathID_ok & d.pathID_ok & 0x10000u) != 0u;
+            float xs[3] = {a.x, c.x, d.x}, ys[3] = {a.y, c.y, d.y};
+            if (!ok)
+                xs[0] = __int_as_float(0x7fc00000); // vertexDiscardValue = NaN
+            // Classify the path.
+            const uint4 pd = __ldg(P.pathBuffer + pathID * 4u + 1u);
+            const bool isStroke = __uint_as_float(pd.z) != 0.f;
+            const bool isFeathered = enableFeather && __uint_as_float(pd.w) != 0.f;
+            uint32_t kind = isStroke ? (isFeathered ? kKindFeatherStroke : kKindStroke) : (isFeathered ? kKindFeatherFill : kKindFill);
+            float attr[12] = {a.c0, c.c0, d.c0, a.c1, c.c1, d.c1, a.c2, c.c2, d.c2, a.c3, c.c3, d.c3};
+            const int comps = kind == kKindFill ? 1 : (kind == kKindFeatherFill ? 4 : 2);
+            uint32_t meta = pathID | (kind << kMetaKindShift);
+            if ((b.miscFlags & RIVECUDA_MISC_CLOCKWISE_FILL) != 0u)
+                meta |= kMetaClockwiseFill;
+            store_triangle(P, triGeom, triAttr, tileCounts, rawTri, xs, ys, attr, comps, meta, 0u, /*cullCCW=*/true);
+        }
+    }
+}
+
+// Interior triangulation / atlas blit: one thread per triangle of a triangle run
+// (draw_path_common.glsl:793-844).
+__global__ void __launch_bounds__(256) setup_triangle_runs_kernel(FlushParams P,
+                                                                 const DeviceBatch* __restrict__ batches,
+                                                                 uint32_t batchCount,
+                                                                 uint32_t totalTriangles,
+                                                                 TriGeom* __restrict__ triGeom,
+                                                                 TriAttr* __restrict__ triAttr,
+                                                                 uint32_t* __restrict__ tileCounts)
+{
+    for (uint32_t item = blockIdx.x * blockDim.x + threadIdx.x; item < totalTriangles; item += gridDim.x * blockDim.x)
+    {
+        const uint32_t bi = find_batch(batches, batchCount, item);
+        const DeviceBatch b = batches[bi];
+        const uint32_t t = item - b.firstWorkItem;
+        const uint32_t rawTri = b.firstTriangle + t;
+        const bool atlasBlit = b.drawType == RIVECUDA_DRAW_FEATHER_ATLAS_BLIT;
+        float xs[3], ys[3];
+        float attr[12];
+        uint32_t pathID = 0;
+        float weight = 0.f;
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+        {
+            const float* tv = P.triangleVertices + static_cast<size_t>(b.baseElement + t * 3 + k) * 3;
+            const float vx = __ldg(tv), vy = __ldg(tv + 1);
+            const uint32_t zbits = __float_as_uint(__ldg(tv + 2));
+            const uint32_t vPathID = zbits & 0xffffu;
+            if (k == 0)
+            {
+                pathID = vPathID;
+                weight = static_cast<float>(static_cast<int32_t>(zbits) >> 16);
+            }
+            if (atlasBlit)
+            {
+                const uint4 pd2 = __ldg(P.pathBuffer + vPathID * 4u + 2u);
+                const float s = __uint_as_float(pd2.y), tx = __uint_as_float(pd2.z), ty = __uint_as_float(pd2.w);
+                xs[k] = vx;
+                ys[k] = vy;
+                attr[0 * 3 + k] = (vx * s + tx) * P.atlasInvWidth;
+                attr[1 * 3 + k] = (vy * s + ty) * P.atlasInvHeight;
+            }
+            else
+            {
+                const uint4 m4 = __ldg(P.pathBuffer + vPathID * 4u);
+                const m22 M = {__uint_as_float(m4.x), __uint_as_float(m4.y), __uint_as_float(m4.z), __uint_as_float(m4.w)};
+                const uint4 pd = __ldg(P.pathBuffer + vPathID * 4u + 1u);
+                const f2 pos = mul(M, mk2(vx, vy)) + mk2(__uint_as_float(pd.x), __uint_as_float(pd.y));
+                xs[k] = pos.x;
+                ys[k] = pos.y;
+            }
+        }
+        uint32_t meta;
+        int comps;
+        if (atlasBlit)
+        {
+            meta = pathID | (kKindAtlasBlit << kMetaKindShift);
+            comps = 2;
+        }
+        else
+        {
+            attr[0] = attr[1] = attr[2] = weight; // flat v_windingWeight
+            meta = pathID | (kKindFill << kMetaKindShift);
+            comps = 1;
+        }
+        if ((b.miscFlags & RIVECUDA_MISC_CLOCKWISE_FILL) != 0u)
+            meta |= kMetaClockwiseFill;
+        store_triangle(P, triGeom, triAttr, tileCounts, rawTri, xs, ys, attr, comps, meta, 0u, /*cullCCW=*/true);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// Scan of the per-tile counts (exclusive), three small kernels.
+
+constexpr int kScanBlock = 1024;
+
+__global__ void __launch_bounds__(kScanBlock) scan_reduce_kernel(const uint32_t* __restrict__ counts, uint32_t n, uint32_t* __restrict__ blockSums)
+{
+    __shared__ uint32_t s[32];
+    const uint32_t i = blockIdx.x * kScanBlock + threadIdx.x;
+    uint32_t v = i < n ? counts[i] : 0u;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+        v += __shfl_down_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0)
+        s[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x < 32)
+    {
+        v = s[threadIdx.x];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1)
+            v += __shfl_down_sync(0xffffffffu, v, o);
+        if (threadIdx.x == 0)
+            blockSums[blockIdx.x] = v;
+    }
+}
+
+// Single block: exclusive scan of up to kScanBlock block sums; writes the grand
+// total to total[0].
+__global__ void __launch_bounds__(kScanBlock) scan_block_sums_kernel(uint32_t* __restrict__ blockSums, uint32_t n, uint32_t* __restrict__ total)
+{
+    __shared__ uint32_t s[32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t v = threadIdx.x < n ? blockSums[threadIdx.x] : 0u;
+    uint32_t incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1)
+    {
+        uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o)
+            incl += t;
+    }
+    if (lane == 31)
+        s[warp] = incl;
+    __syncthreads();
+    if (warp == 0)
+    {
+        uint32_t w = s[lane];
+        uint32_t wi = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1)
+        {
+            uint32_t t = __shfl_up_sync(0xffffffffu, wi, o);
+            if (lane >= o)
+                wi += t;
+        }
+        s[lane] = wi - w; // exclusive warp offsets
+        if (lane == 31)
+            total[0] = wi;
+    }
+    __syncthreads();
+    if (threadIdx.x < n)
+        blockSums[threadIdx.x] = s[warp] + incl - v;
+}
+
+__global__ void __launch_bounds__(kScanBlock) scan_apply_kernel(const uint32_t* __restrict__ counts,
+                                                               uint32_t n,
+                                                               const uint32_t* __restrict__ blockOffsets,
+                                                               uint32_t* __restrict__ offsets)
+{
+    __shared__ uint32_t s[32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t i = blockIdx.x * kScanBlock + threadIdx.x;
+    const uint32_t v = i < n ? counts[i] : 0u;
+    uint32_t incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1)
+    {
+        uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o)
+            incl += t;
+    }
+    if (lane == 31)
+        s[warp] = incl;
+    __syncthreads();
+    if (warp == 0)
+    {
+        uint32_t w = s[lane];
+        uint32_t wi = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1)
+        {
+            uint32_t t = __shfl_up_sync(0xffffffffu, wi, o);
+            if (lane >= o)
+                wi += t;
+        }
+        s[lane] = wi - w;
+    }
+    __syncthreads();
+    if (i < n)
+        offsets[i] = blockOffsets[blockIdx.x] + s[warp] + incl - v;
+}
+
+// ---------------------------------------------------------------------------
+// Scatter: append each valid triangle's id to the lists of the tiles it overlaps.
+
+__global__ void __launch_bounds__(256) scatter_kernel(FlushParams P,
+                                                      const TriGeom* __restrict__ triGeom,
+                                                      uint32_t triCount,
+                                                      const uint32_t* __restrict__ tileOffsets,
+                                                      uint32_t* __restrict__ tileCursors,
+                                                      uint32_t* __restrict__ entries,
+                                                      uint32_t entryCapacity)
+{
+    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < triCount; t += gridDim.x * blockDim.x)
+    {
+        const uint4 lo = __ldg(reinterpret_cast<const uint4*>(triGeom + t));
+        const uint4 hi = __ldg(reinterpret_cast<const uint4*>(triGeom + t) + 1);
+        if ((hi.z & kMetaValid) == 0u)
+            continue;
+        const int32_t X[3] = {static_cast<int32_t>(lo.x), static_cast<int32_t>(lo.z), static_cast<int32_t>(hi.x)};
+        const int32_t Y[3] = {static_cast<int32_t>(lo.y), static_cast<int32_t>(lo.w), static_cast<int32_t>(hi.y)};
+        for_each_tile(P, X, Y, [&](uint32_t tile) {
+            const uint32_t pos = __ldg(tileOffsets + tile) + atomicAdd(tileCursors + tile, 1u);
+            if (pos < entryCapacity)
+                entries[pos] = t;
+        });
+    }
+}
+
+// ---------------------------------------------------------------------------
+// Per-tile sort by triangle id (= API order). Bitonic network in the
+// "all-ascending" form, so arbitrary n works without padding.
+
+constexpr int kSortSmemEntries = 4096;
+
+template <typename Ptr> __device__ __forceinline__ void bitonic_sort(Ptr data, uint32_t n)
+{
+    for (uint32_t k = 2; (k >> 1) < n; k <<= 1)
+    {
+        // First step of each stage mirrors within blocks of k.
+        for (uint32_t i = threadIdx.x; i < n; i += blockDim.x)
+        {
+            const uint32_t j = i ^ (k - 1);
+            if (j > i && j < n)
+            {
+                const uint32_t a = data[i], b = data[j];
+                if (a > b)
+                {
+                    data[i] = b;
+                    data[j] = a;
+                }
+            }
+        }
+        __syncthreads();
+        for (uint32_t j2 = k >> 2; j2 > 0; j2 >>= 1)
+        {
+            for (uint32_t i = threadIdx.x; i < n; i += blockDim.x)
+            {
+                const uint32_t j = i ^ j2;
+                if (j > i && j < n)
+                {
+                    const uint32_t a = data[i], b = data[j];
+                    if (a > b)
+                    {
+                        data[i] = b;
+                        data[j] = a;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) sort_tiles_kernel(const uint32_t* __restrict__ tileOffsets,
+                                                         const uint32_t* __restrict__ tileCounts,
+                                                         uint32_t* __restrict__ entries)
+{
+    __shared__ uint32_t s_data[kSortSmemEntries];
+    const uint32_t tile = blockIdx.x;
+    const uint32_t n = tileCounts[tile];
+    if (n < 2)
+        return;
+    uint32_t* list = entries + tileOffsets[tile];
+    if (n <= kSortSmemEntries)
+    {
+        for (uint32_t i = threadIdx.x; i < n; i += blockDim.x)
+            s_data[i] = list[i];
+        __syncthreads();
+        bitonic_sort(s_data, n);
+        for (uint32_t i = threadIdx.x; i < n; i += blockDim.x)
+            list[i] = s_data[i];
+    }
+    else
+    {
+        bitonic_sort(list, n);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// Raster
+
+struct Prepared // 24 words, one per (triangle, tile), in shared memory
+{
+    int32_t A0, B0, q0, A1, B1, q1, A2, B2, q2;
+    float plane[4][3]; // P0, Px, Py per attribute component
+    uint32_t meta;     // TriGeom::meta (0 => skip)
+    uint32_t bbox;     // xmin | xmax<<4 | ymin<<8 | ymax<<12, tile-local
+    uint32_t aux;
+};
+static_assert(sizeof(Prepared) == 96, "Prepared");
+
+constexpr int kRasterChunk = 256;
+
+__device__ __forceinline__ int64_t floor_shift8(int64_t v) { return v >> 8; }
+
+// Builds the tile-local form of one triangle. Exact for edges whose Manhattan
+// length is below ~2^18 px; longer edges are scaled (approximate).
+__device__ void prepare_triangle(const TriGeom& g, const TriAttr* __restrict__ attrPtr, int originX, int originY, Prepared& out)
+{
+    out.meta = 0;
+    out.bbox = 0;
+    out.aux = g.aux;
+    if ((g.meta & kMetaValid) == 0u)
+        return;
+    const int32_t X[3] = {g.x0, g.x1, g.x2}, Y[3] = {g.y0, g.y1, g.y2};
+    const int64_t px0 = (static_cast<int64_t>(originX) << 8) + 128, py0 = (static_cast<int64_t>(originY) << 8) + 128;
+    int64_t A[3], B[3], E0u[3];
+    int32_t Ai[3], Bi[3], qi[3];
+    bool reject = false;
+#pragma unroll
+    for (int e = 0; e < 3; ++e)
+    {
+        const int a = (e + 1) % 3, b = (e + 2) % 3;
+        const int64_t dx = static_cast<int64_t>(X[b]) - X[a], dy = static_cast<int64_t>(Y[b]) - Y[a];
+        const bool topLeft = (dy == 0 && dx > 0) || (dy < 0);
+        A[e] = -dy;
+        B[e] = dx;
+        const int64_t C = dy * X[a] - dx * Y[a];
+        E0u[e] = A[e] * px0 + B[e] * py0 + C;
+        // E(i,j) - bias = E0u - bias + 256*(A*i + B*j) >= 0  <=>  q + A*i + B*j >= 0
+        const int64_t q = floor_shift8(E0u[e] - (topLeft ? 0 : 1));
+        const int64_t n = kTileSize - 1;
+        const int64_t emin = q + n * (A[e] < 0 ? A[e] : 0) + n * (B[e] < 0 ? B[e] : 0);
+        const int64_t emax = q + n * (A[e] > 0 ? A[e] : 0) + n * (B[e] > 0 ? B[e] : 0);
+        if (emax < 0)
+            reject = true;
+        if (emin >= 0)
+        {
+            Ai[e] = Bi[e] = qi[e] = 0; // trivially inside for the whole tile
+        }
+        else
+        {
+            int64_t a64 = A[e], b64 = B[e], q64 = q;
+            // Keep |q| + 15|A| + 15|B| inside int32.
+            while ((a64 < 0 ? -a64 : a64) + (b64 < 0 ? -b64 : b64) >= (1ll << 25))
+            {
+                a64 >>= 1;
+                b64 >>= 1;
+                q64 >>= 1;
+            }
+            Ai[e] = static_cast<int32_t>(a64);
+            Bi[e] = static_cast<int32_t>(b64);
+            qi[e] = static_cast<int32_t>(q64);
+        }
+    }
+    if (reject)
+        return;
+    // Tile-local pixel bounds of candidate pixels.
+    const int32_t minX = min(X[0], min(X[1], X[2])), maxX = max(X[0], max(X[1], X[2]));
+    const int32_t minY = min(Y[0], min(Y[1], Y[2])), maxY = max(Y[0], max(Y[1], Y[2]));
+    const int bx0 = max(((minX - 128 + 255) >> 8) - originX, 0), bx1 = min(((maxX - 128) >> 8) - originX, kTileSize - 1);
+    const int by0 = max(((minY - 128 + 255) >> 8) - originY, 0), by1 = min(((maxY - 128) >> 8) - originY, kTileSize - 1);
+    if (bx0 > bx1 || by0 > by1)
+        return;
+    out.A0 = Ai[0];
+    out.B0 = Bi[0];
+    out.q0 = qi[0];
+    out.A1 = Ai[1];
+    out.B1 = Bi[1];
+    out.q1 = qi[1];
+    out.A2 = Ai[2];
+    out.B2 = Bi[2];
+    out.q2 = qi[2];
+    out.bbox = static_cast<uint32_t>(bx0) | (static_cast<uint32_t>(bx1) << 4) | (static_cast<uint32_t>(by0) << 8) | (static_cast<uint32_t>(by1) << 12);
+    out.meta = g.meta;
+    // Attribute planes from exact barycentrics at tile pixel (0,0):
+    //   attr(i,j) = sum_k c_k * (E0u_k + 256*(A_k*i + B_k*j)) / area2
+    const double area2 = static_cast<double>(E0u[0] + E0u[1] + E0u[2]);
+    const double inv = 1.0 / area2;
+    const uint32_t kind = (g.meta >> kMetaKindShift) & 0xf;
+    const int comps = kind == kKindFill ? 1 : (kind == kKindFeatherFill ? 4 : 2);
+    const float* attr = attrPtr->attr;
+    for (int c = 0; c < comps; ++c)
+    {
+        const double c0 = attr[c * 3 + 0], c1 = attr[c * 3 + 1], c2 = attr[c * 3 + 2];
+        out.plane[c][0] = static_cast<float>((c0 * static_cast<double>(E0u[0]) + c1 * static_cast<double>(E0u[1]) + c2 * static_cast<double>(E0u[2])) * inv);
+        out.plane[c][1] = static_cast<float>((c0 * static_cast<double>(A[0]) + c1 * static_cast<double>(A[1]) + c2 * static_cast<double>(A[2])) * 256.0 * inv);
+        out.plane[c][2] = static_cast<float>((c0 * static_cast<double>(B[0]) + c1 * static_cast<double>(B[1]) + c2 * static_cast<double>(B[2])) * 256.0 * inv);
+    }
+}
+
+// draw_path_common.glsl:153-258
+__device__ float eval_feathered_fill(const float* __restrict__ lut, float4 cov)
+{
+    const float cotTheta = cov.z;
+    const float y0 = fmaxf(cov.w, 0.f);
+    float featherCoverage = cotTheta >= 0.f ? feather_lut(lut, y0) : 0.f;
+    if (fabsf(cotTheta) < kHorizontalCotangentThreshold)
+    {
+        const float x = fabsf(cov.x) - kFeatherXCoordBias;
+        const float y = -cov.y + kFeatherCoverageBias;
+        const float dt = (y - y0) * 0.5984134206f;
+        const float k[4] = {0.20888568955f, 0.62665706865f, 1.04442844776f, 1.46219982687f};
+        float sum = 0.f;
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+        {
+            const float t = y0 + dt * k[i];
+            const float u = t * -cotTheta + (y * cotTheta + x);
+            const float t_ = t * 5.09593080173f + -2.54796540086f;
+            sum += feather_lut(lut, u) * exp2f(-t_ * t_);
+        }
+        featherCoverage += sum * dt;
+    }
+    return featherCoverage * signf(cov.x);
+}
+
+__device__ __forceinline__ float eval_feathered_stroke(const float* __restrict__ lut, float cx, float cy)
+{
+    float c = 1.f;
+    c -= feather_lut(lut, (1.f - kFeatherCoverageBias) + cx);
+    c -= feather_lut(lut, 1.f - cy);
+    return c;
+}
+
+// ---- advanced_blend.glsl:91-330 ----
+
+__device__ __forceinline__ float lum(float3 c) { return c.x * .30f + c.y * .59f + c.z * .11f; }
+__device__ __forceinline__ float min3f(float3 c) { return fminf(fminf(c.x, c.y), c.z); }
+__device__ __forceinline__ float max3f(float3 c) { return fmaxf(fmaxf(c.x, c.y), c.z); }
+
+__device__ float3 set_lum(float3 base, float3 lumColor)
+{
+    const float lumTarget = lum(lumColor);
+    const float lb = lum(base);
+    const float3 biased = make_float3(base.x - lb, base.y - lb, base.z - lb);
+    const float s0 = lumTarget / fmaxf(kEpsilonFP16, -min3f(biased));
+    const float s1 = (1.f - lumTarget) / fmaxf(kEpsilonFP16, max3f(biased));
+    const float satScale = fminf(1.f, fminf(s0, s1));
+    return make_float3(biased.x * satScale + lumTarget, biased.y * satScale + lumTarget, biased.z * satScale + lumTarget);
+}
+
+__device__ float3 set_lum_sat(float3 hueColor, float3 satColor, float3 lumColor)
+{
+    const float satTarget = max3f(satColor) - min3f(satColor);
+    const float mn = min3f(hueColor);
+    hueColor = make_float3(hueColor.x - mn, hueColor.y - mn, hueColor.z - mn);
+    const float scale = satTarget / fmaxf(kEpsilonFP16, max3f(hueColor));
+    return set_lum(make_float3(hueColor.x * scale, hueColor.y * scale, hueColor.z * scale), lumColor);
+}
+
+__device__ __forceinline__ float clamp01(float v) { return clampf(v, 0.f, 1.f); }
+
+__device__ float blend_channel(uint32_t mode, float s, float d, float dPremul, float dA)
+{
+    switch (mode)
+    {
+        case 11: // multiply
+            return s * d;
+        case 1: // screen
+            return s + d - s * d;
+        case 2: // overlay
+        {
+            const float sd = s * d;
+            return 2.f * (d > .5f ? s + d - sd - .5f : sd);
+        }
+        case 3:
+            return fminf(s, d);
+        case 4:
+            return fmaxf(s, d);
+        case 5: // colordodge
+        {
+            const float dp = clampf(dPremul, 0.f, dA);
+            const float denom = clamp01(1.f - s) * dA;
+            return denom == 0.f ? signf(dp) : fminf(1.f, dp / denom);
+        }
+        case 6: // colorburn
+        {
+            const float sc = clamp01(s);
+            const float dp = clampf(dPremul, 0.f, dA);
+            const float da = dA == 0.f ? 1.f : dA;
+            const float numer = da - dp;
+            return 1.f - (sc == 0.f ? signf(numer) : fminf(1.f, numer / (sc * da)));
+        }
+        case 7: // hardlight
+        {
+            const float sd = s * d;
+            return 2.f * (s > .5f ? s + d - sd - .5f : sd);
+        }
+        case 8: // softlight
+        {
+            float k;
+            if (s <= .5f)
+                k = 1.f - d;
+            else if (d <= .25f)
+                k = (16.f * d - 12.f) * d + 3.f;
+            else
+                k = 1.f / sqrtf(d) - 1.f;
+            return d + d * (2.f * s - 1.f) * k;
+        }
+        case 9:
+            return fabsf(d - s);
+        case 10:
+            return s + d - 2.f * s * d;
+        default:
+            return 0.f;
+    }
+}
+
+__device__ float3 advanced_color_blend(float3 src, float4 dstPremul, uint32_t mode)
+{
+    const float invA = dstPremul.w != 0.f ? 1.f / dstPremul.w : 0.f;
+    const float3 dst = make_float3(dstPremul.x * invA, dstPremul.y * invA, dstPremul.z * invA);
+    float3 coeffs;
+    if (mode >= 12)
+    {
+        const float3 sc = make_float3(clamp01(src.x), clamp01(src.y), clamp01(src.z));
+        switch (mode)
+        {
+            case 12:
+                coeffs = set_lum_sat(sc, dst, dst);
+                break;
+            case 13:
+                coeffs = set_lum_sat(dst, sc, dst);
+                break;
+            case 14:
+                coeffs = set_lum(sc, dst);
+                break;
+            default:
+                coeffs = set_lum(dst, sc);
+                break;
+        }
+    }
+    else
+    {
+        coeffs.x = blend_channel(mode, src.x, dst.x, dstPremul.x, dstPremul.w);
+        coeffs.y = blend_channel(mode, src.y, dst.y, dstPremul.y, dstPremul.w);
+        coeffs.z = blend_channel(mode, src.z, dst.z, dstPremul.z, dstPremul.w);
+    }
+    const float a = dstPremul.w;
+    return make_float3(src.x * (1.f - a) + coeffs.x * a, src.y * (1.f - a) + coeffs.y * a, src.z * (1.f - a) + coeffs.z * a);
+}
+
+__device__ __forceinline__ float4 fetch_grad(const FlushParams& P, int x, int y)
+{
+    x = min(max(x, 0), kGradWidth - 1);
+    y = min(max(y, 0), static_cast<int>(P.gradHeight) - 1);
+    return unpack_rgba8(__ldg(P.gradTexture + y * kGradWidth + x));
+}
+
+__device__ float4 sample_grad(const FlushParams& P, float u, float v)
+{
+    const float x = u * 512.f - .5f, y = v * static_cast<float>(P.gradHeight) - .5f;
+    const float fx = floorf(x), fy = floorf(y);
+    const float tx = x - fx, ty = y - fy;
+    const int ix = static_cast<int>(clampf(fx, -1.f, 512.f)), iy = static_cast<int>(clampf(fy, -1.f, 65536.f));
+    const float4 c00 = fetch_grad(P, ix, iy), c10 = fetch_grad(P, ix + 1, iy);
+    const float4 c01 = fetch_grad(P, ix, iy + 1), c11 = fetch_grad(P, ix + 1, iy + 1);
+    float4 top = make_float4(c00.x + (c10.x - c00.x) * tx, c00.y + (c10.y - c00.y) * tx, c00.z + (c10.z - c00.z) * tx, c00.w + (c10.w - c00.w) * tx);
+    float4 bot = make_float4(c01.x + (c11.x - c01.x) * tx, c01.y + (c11.y - c01.y) * tx, c01.z + (c11.z - c01.z) * tx, c01.w + (c11.w - c01.w) * tx);
+    return make_float4(top.x + (bot.x - top.x) * ty, top.y + (bot.y - top.y) * ty, top.z + (bot.z - top.z) * ty, top.w + (bot.w - top.w) * ty);
+}
+
+__device__ float sample_atlas(const FlushParams& P, float u, float v)
+{
+    const float x = u * P.atlasWidth - .5f, y = v * P.atlasHeight - .5f;
+    const float fx = floorf(x), fy = floorf(y);
+    const float tx = x - fx, ty = y - fy;
+    const int ix = static_cast<int>(clampf(fx, -1.f, 65536.f)), iy = static_cast<int>(clampf(fy, -1.f, 65536.f));
+    auto fetch = [&](int xx, int yy) {
+        xx = min(max(xx, 0), static_cast<int>(P.atlasWidth) - 1);
+        yy = min(max(yy, 0), static_cast<int>(P.atlasHeight) - 1);
+        return __ldg(P.atlas + static_cast<size_t>(yy) * P.atlasWidth + xx);
+    };
+    const float a = fetch(ix, iy) + (fetch(ix + 1, iy) - fetch(ix, iy)) * tx;
+    const float b = fetch(ix, iy + 1) + (fetch(ix + 1, iy + 1) - fetch(ix, iy + 1)) * tx;
+    return a + (b - a) * ty;
+}
+
+__device__ __forceinline__ float round_to_half(float v) { return __half2float(__float2half_rn(v)); }
+
+struct PixelState
+{
+    uint32_t color;    // RGBA8 premultiplied: the colour plane IS 8-bit in the reference
+    float clipCoverage;
+    uint32_t clipID;
+};
+
+// Paint lookup (draw_path.vert:188-362 + find_paint_color :431-506), evaluated
+// at the pixel centre instead of interpolated from vertices (the varyings are
+// affine in position, so this is the same function).
+__device__ float4 paint_color(const FlushParams& P, uint32_t pathID, uint2 paint, float fragX, float fragY)
+{
+    const uint32_t paintType = paint.x & 0xfu;
+    float4 color;
+    if (paintType == kPaintTypeSolid)
+    {
+        color = unpack_rgba8(paint.y);
+    }
+    else
+    {
+        const float4 pm = __ldg(P.paintAuxBuffer + pathID * 8u);
+        const float4 pt = __ldg(P.paintAuxBuffer + pathID * 8u + 1u);
+        const float cx = pm.x * fragX + pm.z * fragY + pt.x;
+        const float cy = pm.y * fragX + pm.w * fragY + pt.y;
+        float t = paintType == kPaintTypeLinear ? cx : sqrtf(cx * cx + cy * cy);
+        t = clamp01(t);
+        const float x = pt.z > .9f ? (1.f - 1.f / 512.f) * t + (.5f / 512.f) : (1.f / 512.f) * t + pt.w;
+        color = sample_grad(P, x, __uint_as_float(paint.y));
+    }
+    return color; // unpremultiplied
+}
+
+// Resolve one path at one pixel (draw_raster_order_path.frag:61-232).
+__device__ void resolve_path(const FlushParams& P, uint32_t meta, float coverageCount, int px, int py, PixelState& s)
+{
+    const uint32_t pathID = meta & 0xffffu;
+    const uint2 paint = __ldg(P.paintBuffer + pathID);
+    float coverage;
+    if ((meta & kMetaClockwiseFill) != 0u)
+    {
+        coverage = clamp01(coverageCount);
+    }
+    else
+    {
+        coverage = fabsf(coverageCount);
+        if ((paint.x & kPaintFlagEvenOdd) != 0u)
+            coverage = 1.f - fabsf(fractf(coverage * .5f) * 2.f + -1.f);
+        coverage = fminf(coverage, 1.f);
+    }
+    const uint32_t paintType = paint.x & 0xfu;
+    if (paintType == kPaintTypeClipUpdate)
+    {
+        const uint32_t clipID = paint.y >> 16;
+        const uint32_t outerClipID = paint.x >> 16;
+        if (outerClipID != 0u)
+        {
+            const float outerCoverage = s.clipID == outerClipID ? s.clipCoverage : 0.f;
+            coverage = fminf(coverage, outerCoverage);
+        }
+        s.clipCoverage = round_to_half(coverage); // the clip plane stores fp16
+        s.clipID = clipID;
+        return;
+    }
+    const uint32_t clipID = paint.x >> 16;
+    if (clipID != 0u)
+        coverage = s.clipID == clipID ? fminf(s.clipCoverage, coverage) : 0.f;
+    const float fragX = px + .5f, fragY = py + .5f;
+    if ((paint.x & kPaintFlagClipRect) != 0u)
+    {
+        const float4 m = __ldg(P.paintAuxBuffer + pathID * 8u + 2u);
+        const float4 tr = __ldg(P.paintAuxBuffer + pathID * 8u + 3u);
+        const float wx = fabsf(m.x) + fabsf(m.z), wy = fabsf(m.y) + fabsf(m.w);
+        float d;
+        if (wx != 0.f && wy != 0.f)
+        {
+            const float rx = 1.f / wx, ry = 1.f / wy;
+            const float cx = m.x * fragX + m.z * fragY + tr.x, cy = m.y * fragX + m.w * fragY + tr.y;
+            d = fminf(fminf(cx * rx + rx + .5f, cy * ry + ry + .5f), fminf(-cx * rx + rx + .5f, -cy * ry + ry + .5f));
+        }
+        else
+        {
+            d = fminf(tr.x, tr.y);
+        }
+        coverage = clampf(d, 0.f, coverage);
+    }
+    float4 color = paint_color(P, pathID, paint, fragX, fragY);
+    const float4 dst = unpack_rgba8(s.color);
+    const uint32_t blendMode = (paint.x >> 4) & 0xfu;
+    float3 rgb = make_float3(color.x, color.y, color.z);
+    if (blendMode != 0u)
+        rgb = advanced_color_blend(rgb, dst, blendMode);
+    const float a = color.w * coverage;
+    const float oneMinusA = 1.f - a;
+    float r = rgb.x * a + dst.x * oneMinusA;
+    float g = rgb.y * a + dst.y * oneMinusA;
+    float b = rgb.z * a + dst.z * oneMinusA;
+    const float outA = a + dst.w * oneMinusA;
+    if (a != 0.f && P.ditherScale != 0.f)
+    {
+        const float v1 = fractf(0.06711056f * fragX + 0.00583715f * fragY);
+        const float dither = fractf(52.9829189f * v1) * P.ditherScale + P.ditherBias;
+        r += dither;
+        g += dither;
+        b += dither;
+    }
+    s.color = pack_rgba8(r, g, b, outA);
+}
+
+// Immediate-mode blend for atlas blits (draw_mesh.frag, @FEATHER_ATLAS_BLIT).
+__device__ void resolve_atlas_blit(const FlushParams& P, uint32_t meta, float u, float v, int px, int py, PixelState& s)
+{
+    const uint32_t pathID = meta & 0xffffu;
+    const uint2 paint = __ldg(P.paintBuffer + pathID);
+    float coverage = clamp01(sample_atlas(P, u, v));
+    const float fragX = px + .5f, fragY = py + .5f;
+    if ((paint.x & kPaintFlagClipRect) != 0u)
+    {
+        const float4 m = __ldg(P.paintAuxBuffer + pathID * 8u + 2u);
+        const float4 tr = __ldg(P.paintAuxBuffer + pathID * 8u + 3u);
+        const float wx = fabsf(m.x) + fabsf(m.z), wy = fabsf(m.y) + fabsf(m.w);
+        float d;
+        if (wx != 0.f && wy != 0.f)
+        {
+            const float rx = 1.f / wx, ry = 1.f / wy;
+            const float cx = m.x * fragX + m.z * fragY + tr.x, cy = m.y * fragX + m.w * fragY + tr.y;
+            d = fminf(fminf(cx * rx + rx + .5f, cy * ry + ry + .5f), fminf(-cx * rx + rx + .5f, -cy * ry + ry + .5f));
+        }
+        else
+        {
+            d = fminf(tr.x, tr.y);
+        }
+        coverage = fminf(fmaxf(d, 0.f), coverage);
+    }
+    const uint32_t clipID = paint.x >> 16;
+    if (clipID != 0u)
+        coverage = fminf(coverage, fmaxf(s.clipID == clipID ? s.clipCoverage : 0.f, 0.f));
+    float4 color = paint_color(P, pathID, paint, fragX, fragY);
+    const float4 dst = unpack_rgba8(s.color);
+    const uint32_t blendMode = (paint.x >> 4) & 0xfu;
+    float3 rgb = make_float3(color.x, color.y, color.z);
+    if (blendMode != 0u)
+        rgb = advanced_color_blend(rgb, dst, blendMode);
+    const float a = color.w * coverage;
+    float r = rgb.x * a, g = rgb.y * a, b = rgb.z * a;
+    if (a != 0.f && P.ditherScale != 0.f)
+    {
+        const float v1 = fractf(0.06711056f * fragX + 0.00583715f * fragY);
+        const float dither = fractf(52.9829189f * v1) * P.ditherScale + P.ditherBias;
+        r += dither;
+        g += dither;
+        b += dither;
+    }
+    const float oneMinusA = 1.f - a;
+    s.color = pack_rgba8(dst.x * oneMinusA + r, dst.y * oneMinusA + g, dst.z * oneMinusA + b, dst.w * oneMinusA + a);
+}
+
+__global__ void __launch_bounds__(256) raster_tiles_kernel(FlushParams P,
+                                                           const TriGeom* __restrict__ triGeom,
+                                                           const TriAttr* __restrict__ triAttr,
+                                                           const uint32_t* __restrict__ tileOffsets,
+                                                           const uint32_t* __restrict__ tileCounts,
+                                                           const uint32_t* __restrict__ entries)
+{
+    __shared__ __align__(16) Prepared s_prep[kRasterChunk];
+    const uint32_t tile = blockIdx.x;
+    const int tileX = static_cast<int>(tile % P.tilesX) + P.tileX0, tileY = static_cast<int>(tile / P.tilesX) + P.tileY0;
+    const int originX = tileX << kTileSizeLog2, originY = tileY << kTileSizeLog2;
+    // Each warp owns an 8x4 pixel block of the 16x16 tile.
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int wx0 = (warp & 1) * 8, wy0 = (warp >> 1) * 4;
+    const int i = wx0 + (lane & 7), j = wy0 + (lane >> 3);
+    const int px = originX + i, py = originY + j;
+    const bool inBounds = px >= P.boundsL && px < P.boundsR && py >= P.boundsT && py < P.boundsB;
+
+    PixelState s;
+    s.clipCoverage = 0.f;
+    s.clipID = 0u;
+    if (P.loadAction == RIVECUDA_LOAD_CLEAR)
+        s.color = P.clearColorPremulRGBA;
+    else
+        s.color = inBounds ? P.target[static_cast<size_t>(py) * P.targetWidth + px] : 0u;
+
+    const uint32_t n = tileCounts[tile];
+    const uint32_t* list = entries + tileOffsets[tile];
+
+    uint32_t curMeta = 0u; // meta of the path being accumulated (0 = none)
+    float coverageCount = 0.f;
+    bool touched = false;
+
+    for (uint32_t base = 0; base < n; base += kRasterChunk)
+    {
+        const uint32_t chunk = min(static_cast<uint32_t>(kRasterChunk), n - base);
+        __syncthreads(); // previous chunk fully consumed
+        if (threadIdx.x < chunk)
+        {
+            const uint32_t t = __ldg(list + base + threadIdx.x);
+            TriGeom g;
+            const uint4* src = reinterpret_cast<const uint4*>(triGeom + t);
+            *reinterpret_cast<uint4*>(&g) = __ldg(src);
+            *(reinterpret_cast<uint4*>(&g) + 1) = __ldg(src + 1);
+            prepare_triangle(g, triAttr + t, originX, originY, s_prep[threadIdx.x]);
+        }
+        __syncthreads();
+        for (uint32_t k = 0; k < chunk; ++k)
+        {
+            const Prepared& T = s_prep[k];
+            const uint32_t meta = T.meta;
+            if (meta == 0u)
+                continue;
+            const uint32_t kind = (meta >> kMetaKindShift) & 0xf;
+            // Path boundary: resolve what has been accumulated.
+            if ((meta & 0xffffu) != (curMeta & 0xffffu) || kind >= kKindAtlasBlit)
+            {
+                if (touched)
+                    resolve_path(P, curMeta, coverageCount, px, py, s);
+                curMeta = kind >= kKindAtlasBlit ? 0u : meta;
+                coverageCount = 0.f;
+                touched = false;
+            }
+            // Warp-level reject against the triangle's tile-local bounds.
+            const uint32_t bb = T.bbox;
+            const int bx0 = bb & 15, bx1 = (bb >> 4) & 15, by0 = (bb >> 8) & 15, by1 = (bb >> 12) & 15;
+            if (bx0 > wx0 + 7 || bx1 < wx0 || by0 > wy0 + 3 || by1 < wy0)
+                continue;
+            const int e0 = T.q0 + T.A0 * i + T.B0 * j;
+            const int e1 = T.q1 + T.A1 * i + T.B1 * j;
+            const int e2 = T.q2 + T.A2 * i + T.B2 * j;
+            if ((e0 | e1 | e2) < 0)
+                continue;
+            const float fi = static_cast<float>(i), fj = static_cast<float>(j);
+            const float c0 = T.plane[0][0] + T.plane[0][1] * fi + T.plane[0][2] * fj;
+            switch (kind)
+            {
+                case kKindFill:
+                    coverageCount += c0;
+                    touched = true;
+                    break;
+                case kKindStroke:
+                {
+                    const float c1 = T.plane[1][0] + T.plane[1][1] * fi + T.plane[1][2] * fj;
+                    coverageCount = fmaxf(coverageCount, fminf(c0, c1));
+                    touched = true;
+                    break;
+                }
+                case kKindFeatherFill:
+                {
+                    const float c1 = T.plane[1][0] + T.plane[1][1] * fi + T.plane[1][2] * fj;
+                    const float c2 = T.plane[2][0] + T.plane[2][1] * fi + T.plane[2][2] * fj;
+                    const float c3 = T.plane[3][0] + T.plane[3][1] * fi + T.plane[3][2] * fj;
+                    coverageCount += eval_feathered_fill(P.featherLUT, make_float4(c0, c1, c2, c3));
+                    touched = true;
+                    break;
+                }
+                case kKindFeatherStroke:
+                {
+                    const float c1 = T.plane[1][0] + T.plane[1][1] * fi + T.plane[1][2] * fj;
+                    coverageCount = fmaxf(coverageCount, eval_feathered_stroke(P.featherLUT, c0, c1));
+                    touched = true;
+                    break;
+                }
+                case kKindAtlasBlit:
+                {
+                    const float c1 = T.plane[1][0] + T.plane[1][1] * fi + T.plane[1][2] * fj;
+                    resolve_atlas_blit(P, meta, c0, c1, px, py, s);
+                    break;
+                }
+                default:
+                    break;
+            }
+        }
+    }
+    if (touched)
+        resolve_path(P, curMeta, coverageCount, px, py, s);
+    if (inBounds)
+        P.target[static_cast<size_t>(py) * P.targetWidth + px] = s.color;
+}
+
+// Tiles with no triangles only need the clear colour.
+// (Handled by raster_tiles_kernel itself: n == 0 => store of the clear colour.)
+
+// ---------------------------------------------------------------------------
+// Host orchestration
+
+static uint32_t premul_clear_color(uint32_t argb)
+{
+    // vkutil::color_clear_rgba32f -> UnpackColorToRGBA32FPremul, then the UNORM8
+    // attachment rounds to nearest.
+    const float a = static_cast<float>(argb >> 24) / 255.f;
+    const float r = static_cast<float>((argb >> 16) & 0xff) / 255.f * a;
+    const float g = static_cast<float>((argb >> 8) & 0xff) / 255.f * a;
+    const float b = static_cast<float>(argb & 0xff) / 255.f * a;
+    auto q = [](float v) -> uint32_t {
+        if (!(v > 0.f))
+            return 0u;
+        if (v >= 1.f)
+            return 255u;
+        return static_cast<uint32_t>(v * 255.f + .5f);
+    };
+    return q(r) | (q(g) << 8) | (q(b) << 16) | (q(a) << 24);
+}
+
+int launch_draw_list(rivecuda_ctx* ctx, const rivecuda_flush_desc& desc, const rivecuda_draw_batch* batches, uint32_t batchCount)
+{
+    rivecuda_target* target = desc.render_target;
+    cudaStream_t stream = ctx->stream;
+
+    FlushParams P = {};
+    auto ringPtr = [&](int kind, size_t elementSize, uint64_t first) -> const uint8_t* {
+        const BufferRing& ring = ctx->rings[kind];
+        if (ring.device[ring.current] == nullptr)
+            return nullptr;
+        return static_cast<const uint8_t*>(ring.device[ring.current]) + first * elementSize;
+    };
+    P.pathBuffer = reinterpret_cast<const uint4*>(ringPtr(RIVECUDA_BUFFER_PATH, 64, desc.first_path));
+    P.paintBuffer = reinterpret_cast<const uint2*>(ringPtr(RIVECUDA_BUFFER_PAINT, 8, desc.first_paint));
+    P.paintAuxBuffer = reinterpret_cast<const float4*>(ringPtr(RIVECUDA_BUFFER_PAINT_AUX, 128, desc.first_paint_aux));
+    P.contourBuffer = reinterpret_cast<const uint4*>(ringPtr(RIVECUDA_BUFFER_CONTOUR, 16, desc.first_contour));
+    P.triangleVertices = reinterpret_cast<const float*>(ringPtr(RIVECUDA_BUFFER_TRIANGLE, 12, 0));
+    P.imageDrawInstances = ringPtr(RIVECUDA_BUFFER_IMAGE_DRAW, 64, 0);
+    P.tess = ctx->tessTexture;
+    P.tessVertexCount = ctx->tessHeight * kTessWidth;
+    P.patchVertices = static_cast<const float*>(ctx->patchVertices);
+    P.patchIndices = ctx->patchIndices;
+    P.featherLUT = ctx->featherLUT;
+    P.gradTexture = ctx->gradTexture;
+    P.gradHeight = std::max<uint32_t>(desc.grad_data_height, 1u);
+    P.atlas = ctx->atlas;
+    P.atlasWidth = std::max<uint32_t>(ctx->atlasWidth, 1u);
+    P.atlasHeight = std::max<uint32_t>(ctx->atlasHeight, 1u);
+    P.atlasInvWidth = 1.f / static_cast<float>(desc.feather_atlas_texture_width ? desc.feather_atlas_texture_width : 1u);
+    P.atlasInvHeight = 1.f / static_cast<float>(desc.feather_atlas_texture_height ? desc.feather_atlas_texture_height : 1u);
+    P.wireframe = desc.wireframe;
+    P.target = target->pixels;
+    P.targetWidth = target->width;
+    P.targetHeight = target->height;
+    P.boundsL = std::max(desc.update_bounds[0], 0);
+    P.boundsT = std::max(desc.update_bounds[1], 0);
+    P.boundsR = std::min<int32_t>(desc.update_bounds[2], target->width);
+    P.boundsB = std::min<int32_t>(desc.update_bounds[3], target->height);
+    P.loadAction = desc.color_load_action;
+    P.clearColorPremulRGBA = premul_clear_color(desc.color_clear_value);
+    P.ditherScale = desc.dither_mode == 0 ? 0.f : 1.f / 256.f;
+    P.ditherBias = P.ditherScale * -.5f;
+    if (P.boundsL >= P.boundsR || P.boundsT >= P.boundsB)
+    {
+        if (ctx->profiling)
+            RC_CUDA(cudaEventRecord(ctx->events[5], stream));
+        return 0;
+    }
+    P.tileX0 = P.boundsL >> kTileSizeLog2;
+    P.tileY0 = P.boundsT >> kTileSizeLog2;
+    P.tilesX = static_cast<uint32_t>(((P.boundsR - 1) >> kTileSizeLog2) - P.tileX0 + 1);
+    P.tilesY = static_cast<uint32_t>(((P.boundsB - 1) >> kTileSizeLog2) - P.tileY0 + 1);
+    const uint32_t tileCount = P.tilesX * P.tilesY;
+
+    // Flatten the draw list into device batch tables: one for patch batches
+    // (work item = instance) and one for triangle runs (work item = triangle).
+    std::vector<DeviceBatch> patchBatches, runBatches;
+    uint32_t rawTriangles = 0, patchInstances = 0, runTriangles = 0;
+    for (uint32_t i = 0; i < batchCount; ++i)
+    {
+        const rivecuda_draw_batch& b = batches[i];
+        DeviceBatch d = {};
+        d.drawType = b.draw_type;
+        d.flags = b.shader_features;
+        d.miscFlags = b.shader_misc_flags;
+        d.elementCount = b.element_count;
+        d.baseElement = b.base_element;
+        d.baseIndex = b.base_index;
+        d.firstTriangle = rawTriangles;
+        d.imageSlot = ~0u;
+        d.samplerKey = b.image_sampler;
+        switch (b.draw_type)
+        {
+            case RIVECUDA_DRAW_MIDPOINT_FAN_PATCHES:
+            case RIVECUDA_DRAW_MIDPOINT_FAN_CENTER_AA_PATCHES:
+            case RIVECUDA_DRAW_OUTER_CURVE_PATCHES:
+                d.trisPerElement = b.index_count_per_instance / 3;
+                d.firstWorkItem = patchInstances;
+                patchInstances += b.element_count;
+                rawTriangles += b.element_count * d.trisPerElement;
+                patchBatches.push_back(d);
+                break;
+            case RIVECUDA_DRAW_INTERIOR_TRIANGULATION:
+            case RIVECUDA_DRAW_FEATHER_ATLAS_BLIT:
+                d.trisPerElement = 0;
+                d.firstWorkItem = runTriangles;
+                runTriangles += b.element_count / 3;
+                rawTriangles += b.element_count / 3;
+                runBatches.push_back(d);
+                break;
+            case RIVECUDA_DRAW_IMAGE_MESH:
+                return set_error("rivecuda_flush: imageMesh draws are not implemented yet");
+            default:
+                return set_error("rivecuda_flush: draw type %u is not valid in rasterOrdering mode", b.draw_type);
+        }
+    }
+
+    if (int s = ctx->tileCounts.reserve(static_cast<size_t>(tileCount) * 2 * sizeof(uint32_t)))
+        return s;
+    if (int s = ctx->tileOffsets.reserve(static_cast<size_t>(tileCount) * sizeof(uint32_t)))
+        return s;
+    uint32_t* tileCounts = ctx->tileCounts.as<uint32_t>();
+    uint32_t* tileCursors = tileCounts + tileCount;
+    uint32_t* tileOffsets = ctx->tileOffsets.as<uint32_t>();
+    RC_CUDA(cudaMemsetAsync(tileCounts, 0, static_cast<size_t>(tileCount) * 2 * sizeof(uint32_t), stream));
+
+    TriGeom* triGeom = nullptr;
+    TriAttr* triAttr = nullptr;
+    if (rawTriangles > 0)
+    {
+        if (int s = ctx->triGeom.reserve(static_cast<size_t>(rawTriangles) * sizeof(TriGeom)))
+            return s;
+        if (int s = ctx->triAttr.reserve(static_cast<size_t>(rawTriangles) * sizeof(TriAttr)))
+            return s;
+        triGeom = ctx->triGeom.as<TriGeom>();
+        triAttr = ctx->triAttr.as<TriAttr>();
+        const size_t tableBytes = (patchBatches.size() + runBatches.size()) * sizeof(DeviceBatch);
+        if (int s = ctx->batchTable.reserve(tableBytes))
+            return s;
+        DeviceBatch* devPatch = ctx->batchTable.as<DeviceBatch>();
+        DeviceBatch* devRuns = devPatch + patchBatches.size();
+        if (!patchBatches.empty())
+            RC_CUDA(cudaMemcpyAsync(devPatch, patchBatches.data(), patchBatches.size() * sizeof(DeviceBatch), cudaMemcpyHostToDevice, stream));
+        if (!runBatches.empty())
+            RC_CUDA(cudaMemcpyAsync(devRuns, runBatches.data(), runBatches.size() * sizeof(DeviceBatch), cudaMemcpyHostToDevice, stream));
+        // The batch vectors are pageable host memory: the copies above are
+        // staged by the runtime before returning, so the vectors may die.
+
+        if (patchInstances > 0)
+        {
+            const uint32_t blocks = std::min<uint32_t>((patchInstances + kSetupWarpsPerBlock - 1) / kSetupWarpsPerBlock, ctx->smCount * 16);
+            setup_patches_kernel<<<blocks, kSetupWarpsPerBlock * 32, 0, stream>>>(P, devPatch, static_cast<uint32_t>(patchBatches.size()), patchInstances, triGeom, triAttr, tileCounts);
+            ctx->lastLaunches += 1;
+            RC_CUDA(cudaGetLastError());
+        }
+        if (runTriangles > 0)
+        {
+            const uint32_t blocks = std::min<uint32_t>((runTriangles + 255) / 256, ctx->smCount * 8);
+            setup_triangle_runs_kernel<<<blocks, 256, 0, stream>>>(P, devRuns, static_cast<uint32_t>(runBatches.size()), runTriangles, triGeom, triAttr, tileCounts);
+            ctx->lastLaunches += 1;
+            RC_CUDA(cudaGetLastError());
+        }
+    }
+
+    // Exclusive scan of tile counts -> offsets, total -> pinned host word.
+    const uint32_t scanBlocks = (tileCount + kScanBlock - 1) / kScanBlock;
+    if (scanBlocks > kScanBlock)
+        return set_error("rivecuda_flush: render target too large for the tile scan (%u tiles)", tileCount);
+    if (int s = ctx->scanScratch.reserve((static_cast<size_t>(scanBlocks) + 4) * sizeof(uint32_t)))
+        return s;
+    uint32_t* blockSums = ctx->scanScratch.as<uint32_t>();
+    uint32_t* total = blockSums + scanBlocks;
+    scan_reduce_kernel<<<scanBlocks, kScanBlock, 0, stream>>>(tileCounts, tileCount, blockSums);
+    scan_block_sums_kernel<<<1, kScanBlock, 0, stream>>>(blockSums, scanBlocks, total);
+    scan_apply_kernel<<<scanBlocks, kScanBlock, 0, stream>>>(tileCounts, tileCount, blockSums, tileOffsets);
+    ctx->lastLaunches += 3;
+    RC_CUDA(cudaGetLastError());
+    RC_CUDA(cudaMemcpyAsync(ctx->pinnedTotals, total, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+    RC_CUDA(cudaStreamSynchronize(stream));
+    const uint32_t entryCount = ctx->pinnedTotals[0];
+    ctx->lastTimings.triangle_count = rawTriangles;
+    ctx->lastTimings.tile_entry_count = entryCount;
+
+    if (int s = ctx->tileEntries.reserve((static_cast<size_t>(entryCount) + 1) * sizeof(uint32_t)))
+        return s;
+    uint32_t* entries = ctx->tileEntries.as<uint32_t>();
+    if (entryCount > 0)
+    {
+        const uint32_t blocks = std::min<uint32_t>((rawTriangles + 255) / 256, ctx->smCount * 16);
+        scatter_kernel<<<blocks, 256, 0, stream>>>(P, triGeom, rawTriangles, tileOffsets, tileCursors, entries, entryCount);
+        sort_tiles_kernel<<<tileCount, 256, 0, stream>>>(tileOffsets, tileCounts, entries);
+        ctx->lastLaunches += 2;
+        RC_CUDA(cudaGetLastError());
+    }
+    if (ctx->profiling)
+        RC_CUDA(cudaEventRecord(ctx->events[5], stream));
+    raster_tiles_kernel<<<tileCount, 256, 0, stream>>>(P, triGeom, triAttr, tileOffsets, tileCounts, entries);
+    ctx->lastLaunches += 1;
+    return check_cuda(cudaGetLastError(), "raster_tiles_kernel");
+}
+} // namespace rivecuda
+
+// ---------------------------------------------------------------------------
+// K3: feather atlas (render_atlas.glsl; FEATHER_ATLAS_*_PIPELINE_STATE,
+// gpu.hpp:2076-2080; driver render_context_vulkan_impl.cpp:2861-2990).
+// Fills: midpointFanCenterAA patches, no culling, additive, sign by facing.
+// Strokes: the border triangles of midpointFan patches, CCW culled, max blend.
+// One thread per (patch instance, triangle); each thread walks its triangle's
+// pixels with exact integer edge tests and accumulates with float atomics.
+
+namespace rivecuda
+{
+struct AtlasBatchDev
+{
+    uint32_t scissorL, scissorT, scissorR, scissorB;
+    uint32_t patchCount, basePatch;
+    uint32_t firstWorkItem; // in triangles
+    uint32_t isStroke;
+};
+
+__global__ void __launch_bounds__(128) atlas_kernel(FlushParams P,
+                                                    const AtlasBatchDev* __restrict__ batches,
+                                                    uint32_t batchCount,
+                                                    uint32_t totalTriangles,
+                                                    float* __restrict__ atlas,
+                                                    uint32_t atlasWidth,
+                                                    uint32_t atlasHeight)
+{
+    for (uint32_t item = blockIdx.x * blockDim.x + threadIdx.x; item < totalTriangles; item += gridDim.x * blockDim.x)
+    {
+        uint32_t lo = 0, hi = batchCount;
+        while (hi - lo > 1)
+        {
+            uint32_t mid = (lo + hi) >> 1;
+            if (__ldg(&batches[mid].firstWorkItem) <= item)
+                lo = mid;
+            else
+                hi = mid;
+        }
+        const AtlasBatchDev b = batches[lo];
+        const bool isStroke = b.isStroke != 0u;
+        const uint32_t trisPerPatch = isStroke ? 16u : 40u;
+        const uint32_t baseIndex = isStroke ? 0u : 72u;
+        const uint32_t local = item - b.firstWorkItem;
+        const uint32_t inst = local / trisPerPatch, t = local % trisPerPatch;
+        float xs[3], ys[3];
+        float4 cov[3];
+        bool ok = true;
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+        {
+            const uint32_t vi = __ldg(P.patchIndices + baseIndex + t * 3 + k);
+            const ShadedVertex sv = shade_patch_vertex(P, P.patchVertices + vi * 8, static_cast<int>(b.basePatch + inst), true);
+            ok = ok && (sv.pathID_ok & 0x10000u) != 0u;
+            const uint32_t pathID = sv.pathID_ok & 0xffffu;
+            const uint4 pd2 = __ldg(P.pathBuffer + pathID * 4u + 2u);
+            const float s = __uint_as_float(pd2.y), tx = __uint_as_float(pd2.z), ty = __uint_as_float(pd2.w);
+            xs[k] = sv.x * s + tx;
+            ys[k] = sv.y * s + ty;
+            cov[k] = make_float4(sv.c0, sv.c1, sv.c2, sv.c3);
+        }
+        if (!ok)
+            continue;
+        int32_t X[3], Y[3];
+        if (!(snap_coord(xs[0], X[0]) && snap_coord(ys[0], Y[0]) && snap_coord(xs[1], X[1]) && snap_coord(ys[1], Y[1]) &&
+              snap_coord(xs[2], X[2]) && snap_coord(ys[2], Y[2])))
+            continue;
+        int64_t area2 = (static_cast<int64_t>(X[1]) - X[0]) * (static_cast<int64_t>(Y[2]) - Y[0]) -
+                        (static_cast<int64_t>(X[2]) - X[0]) * (static_cast<int64_t>(Y[1]) - Y[0]);
+        if (area2 == 0)
+            continue;
+        const bool frontFacing = area2 > 0;
+        if (!frontFacing)
+        {
+            if (isStroke)
+                continue;
+            int32_t tmp = X[1];
+            X[1] = X[2];
+            X[2] = tmp;
+            tmp = Y[1];
+            Y[1] = Y[2];
+            Y[2] = tmp;
+            float4 tc = cov[1];
+            cov[1] = cov[2];
+            cov[2] = tc;
+            area2 = -area2;
+        }
+        EdgeEq E[3];
+        edge_equations(X, Y, E);
+        const int32_t minX = min(X[0], min(X[1], X[2])), maxX = max(X[0], max(X[1], X[2]));
+        const int32_t minY = min(Y[0], min(Y[1], Y[2])), maxY = max(Y[0], max(Y[1], Y[2]));
+        const int sx1 = min(static_cast<int>(b.scissorR), static_cast<int>(atlasWidth));
+        const int sy1 = min(static_cast<int>(b.scissorB), static_cast<int>(atlasHeight));
+        const int px0 = max((minX - 128 + 255) >> 8, static_cast<int>(b.scissorL)), px1 = min((maxX - 128) >> 8, sx1 - 1);
+        const int py0 = max((minY - 128 + 255) >> 8, static_cast<int>(b.scissorT)), py1 = min((maxY - 128) >> 8, sy1 - 1);
+        const double inv = 1.0 / static_cast<double>(area2);
+        for (int y = py0; y <= py1; ++y)
+        {
+            const int64_t py = (static_cast<int64_t>(y) << 8) + 128;
+            for (int x = px0; x <= px1; ++x)
+            {
+                const int64_t px = (static_cast<int64_t>(x) << 8) + 128;
+                const int64_t e0 = E[0].A * px + E[0].B * py + E[0].C;
+                const int64_t e1 = E[1].A * px + E[1].B * py + E[1].C;
+                const int64_t e2 = E[2].A * px + E[2].B * py + E[2].C;
+                if ((e0 | e1 | e2) < 0)
+                    continue;
+                // Barycentrics (the top-left bias of at most one unit is far
+                // below fp32 resolution here).
+                const float b0 = static_cast<float>(static_cast<double>(e0) * inv);
+                const float b1 = static_cast<float>(static_cast<double>(e1) * inv);
+                const float b2 = static_cast<float>(static_cast<double>(e2) * inv);
+                const float4 c = make_float4(cov[0].x * b0 + cov[1].x * b1 + cov[2].x * b2,
+                                             cov[0].y * b0 + cov[1].y * b1 + cov[2].y * b2,
+                                             cov[0].z * b0 + cov[1].z * b1 + cov[2].z * b2,
+                                             cov[0].w * b0 + cov[1].w * b1 + cov[2].w * b2);
+                float* texel = atlas + static_cast<size_t>(y) * atlasWidth + x;
+                if (isStroke)
+                {
+                    const float v = eval_feathered_stroke(P.featherLUT, c.x, c.y);
+                    if (v > 0.f)
+                        atomicMax(reinterpret_cast<int*>(texel), __float_as_int(v));
+                }
+                else
+                {
+                    float v = eval_feathered_fill(P.featherLUT, c);
+                    if (!frontFacing)
+                        v = -v;
+                    atomicAdd(texel, v);
+                }
+            }
+        }
+    }
+}
+
+__global__ void clear_atlas_kernel(float* __restrict__ atlas, uint32_t atlasWidth, uint32_t w, uint32_t h)
+{
+    const uint32_t x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x < w && y < h)
+        atlas[static_cast<size_t>(y) * atlasWidth + x] = 0.f;
+}
+
+int launch_atlas(rivecuda_ctx* ctx,
+                 const rivecuda_flush_desc& desc,
+                 const rivecuda_atlas_batch* fills,
+                 uint32_t fillCount,
+                 const rivecuda_atlas_batch* strokes,
+                 uint32_t strokeCount)
+{
+    if (ctx->atlas == nullptr)
+        return set_error("rivecuda_flush: feather atlas batches present but no atlas texture");
+    cudaStream_t stream = ctx->stream;
+    FlushParams P = {};
+    auto ringPtr = [&](int kind, size_t elementSize, uint64_t first) -> const uint8_t* {
+        const BufferRing& ring = ctx->rings[kind];
+        if (ring.device[ring.current] == nullptr)
+            return nullptr;
+        return static_cast<const uint8_t*>(ring.device[ring.current]) + first * elementSize;
+    };
+    P.pathBuffer = reinterpret_cast<const uint4*>(ringPtr(RIVECUDA_BUFFER_PATH, 64, desc.first_path));
+    P.contourBuffer = reinterpret_cast<const uint4*>(ringPtr(RIVECUDA_BUFFER_CONTOUR, 16, desc.first_contour));
+    P.tess = ctx->tessTexture;
+    P.tessVertexCount = ctx->tessHeight * kTessWidth;
+    P.patchVertices = static_cast<const float*>(ctx->patchVertices);
+    P.patchIndices = ctx->patchIndices;
+    P.featherLUT = ctx->featherLUT;
+    P.wireframe = desc.wireframe;
+
+    const uint32_t cw = std::min(desc.feather_atlas_content_width, ctx->atlasWidth);
+    const uint32_t ch = std::min(desc.feather_atlas_content_height, ctx->atlasHeight);
+    if (cw > 0 && ch > 0)
+    {
+        dim3 block(32, 8), grid((cw + 31) / 32, (ch + 7) / 8);
+        clear_atlas_kernel<<<grid, block, 0, stream>>>(ctx->atlas, ctx->atlasWidth, cw, ch);
+        ctx->lastLaunches += 1;
+    }
+    // Fills then strokes, like the reference's atlas render pass. They write
+    // disjoint atlas regions, so two launches keep the add/max ops separate.
+    for (int pass = 0; pass < 2; ++pass)
+    {
+        const rivecuda_atlas_batch* src = pass == 0 ? fills : strokes;
+        const uint32_t count = pass == 0 ? fillCount : strokeCount;
+        if (count == 0)
+            continue;
+        std::vector<AtlasBatchDev> host(count);
+        uint32_t totalTriangles = 0;
+        for (uint32_t i = 0; i < count; ++i)
+        {
+            host[i] = {src[i].scissor_left, src[i].scissor_top, src[i].scissor_right, src[i].scissor_bottom,
+                       src[i].patch_count, src[i].base_patch, totalTriangles, static_cast<uint32_t>(pass)};
+            totalTriangles += src[i].patch_count * (pass == 0 ? 40u : 16u);
+        }
+        if (totalTriangles == 0)
+            continue;
+        DeviceBuffer& table = ctx->imageTable; // reused as scratch for the atlas batch table
+        if (int s = table.reserve(static_cast<size_t>(count) * sizeof(AtlasBatchDev) * 2))
+            return s;
+        AtlasBatchDev* dev = table.as<AtlasBatchDev>() + (pass == 0 ? 0 : count);
+        // Separate halves per pass would alias when counts differ; use a fresh
+        // offset computed from the fill count instead.
+        dev = table.as<AtlasBatchDev>();
+        if (pass == 1)
+        {
+            if (int s = ctx->scanScratch.reserve(static_cast<size_t>(count) * sizeof(AtlasBatchDev)))
+                return s;
+            dev = ctx->scanScratch.as<AtlasBatchDev>();
+        }
+        RC_CUDA(cudaMemcpyAsync(dev, host.data(), static_cast<size_t>(count) * sizeof(AtlasBatchDev), cudaMemcpyHostToDevice, stream));
+        const uint32_t blocks = std::min<uint32_t>((totalTriangles + 127) / 128, ctx->smCount * 16);
+        atlas_kernel<<<blocks, 128, 0, stream>>>(P, dev, count, totalTriangles, ctx->atlas, ctx->atlasWidth, ctx->atlasHeight);
+        ctx->lastLaunches += 1;
+        RC_CUDA(cudaGetLastError());
+    }
+    return 0;
+}
+} // namespace rivecuda

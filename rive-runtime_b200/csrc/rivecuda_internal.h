@@ -1,0 +1,158 @@
+/*
+ * Internal state of librivecuda.so (the sm_100a implementation of
+ * include/rivecuda.h). Not part of the ABI.
+ */
+#pragma once
+
+#include "rivecuda.h"
+
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+namespace rivecuda
+{
+constexpr int kRingSize = 3;         // gpu::kBufferRingSize (gpu.hpp:77)
+constexpr int kTessWidth = 2048;     // gpu::kTessTextureWidth
+constexpr int kTessWidthLog2 = 11;
+constexpr int kGradWidth = 512;      // gpu::kGradTextureWidth
+constexpr int kTileSize = 16;        // raster tile edge, pixels
+constexpr int kTileSizeLog2 = 4;
+constexpr int kSubpixelBits = 8;     // vertex snapping, like the oracle
+
+// Sets the thread-local error string returned by rivecuda_last_error().
+int set_error(const char* fmt, ...);
+int check_cuda(cudaError_t err, const char* what);
+
+#define RC_CUDA(CALL)                                                          \
+    do                                                                         \
+    {                                                                          \
+        int rc_status_ = ::rivecuda::check_cuda((CALL), #CALL);                \
+        if (rc_status_ != 0)                                                   \
+            return rc_status_;                                                 \
+    } while (0)
+
+// A device allocation that only ever grows.
+struct DeviceBuffer
+{
+    void* ptr = nullptr;
+    size_t capacity = 0;
+    int reserve(size_t bytes);
+    void release();
+    template <typename T> T* as() const { return static_cast<T*>(ptr); }
+};
+
+struct BufferRing
+{
+    void* host[kRingSize] = {};   // pinned, write-combined-friendly host memory
+    void* device[kRingSize] = {}; // device copies
+    size_t capacity = 0;
+    int current = 0;              // ring slot mapped / last submitted
+    size_t submittedBytes = 0;
+};
+
+// One record per logical batch after flattening the draw list for the device.
+struct DeviceBatch
+{
+    uint32_t drawType;
+    uint32_t flags;           // RIVECUDA_FEATURE_* of the batch
+    uint32_t miscFlags;       // RIVECUDA_MISC_*
+    uint32_t elementCount;    // instances (patches) or vertices (triangle runs)
+    uint32_t baseElement;
+    uint32_t baseIndex;       // first patch index
+    uint32_t trisPerElement;  // patches: triangles per instance; tri runs: 0
+    uint32_t firstTriangle;   // raw triangle id of this batch's first triangle
+    uint32_t firstWorkItem;   // exclusive prefix of work items (instances / triangles)
+    uint32_t imageSlot;       // index into the flush's image table, or ~0u
+    uint32_t samplerKey;
+    uint32_t reserved;
+};
+
+struct DeviceTexture
+{
+    const uint8_t* levels[16];
+    uint32_t width, height, levelCount, pad;
+};
+} // namespace rivecuda
+
+struct rivecuda_target
+{
+    uint32_t width = 0, height = 0;
+    uint32_t* pixels = nullptr; // device RGBA8 premultiplied, row-major
+};
+
+struct rivecuda_texture
+{
+    rivecuda::DeviceTexture dev{};
+    std::vector<void*> allocations;
+};
+
+struct rivecuda_renderbuffer
+{
+    uint32_t type = 0, flags = 0;
+    size_t size = 0;
+    void* host = nullptr;   // pinned staging
+    void* device = nullptr;
+};
+
+struct rivecuda_ctx
+{
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    int smCount = 148;
+
+    rivecuda::BufferRing rings[RIVECUDA_BUFFER_KIND_COUNT];
+
+    // Static tables (rivecuda_set_static_tables).
+    void* patchVertices = nullptr;   // 269 x 32 B
+    uint16_t* patchIndices = nullptr; // 441
+    uint32_t patchVertexCount = 0, patchIndexCount = 0;
+    float* featherLUT = nullptr;     // [2][512] fp32 (expanded from fp16)
+    bool haveTables = false;
+
+    // Per-flush textures.
+    uint32_t* gradTexture = nullptr; // 512 x gradHeight RGBA8
+    uint32_t gradHeight = 0;
+    uint4* tessTexture = nullptr;    // 2048 x tessHeight
+    uint32_t tessHeight = 0;
+    float* atlas = nullptr;          // atlasWidth x atlasHeight fp32 coverage
+    uint32_t atlasWidth = 0, atlasHeight = 0;
+
+    // Raster work buffers (grow-only).
+    rivecuda::DeviceBuffer triGeom, triAttr, tileCounts, tileOffsets, tileEntries, batchTable, imageTable,
+        scanScratch, clipPlane;
+    uint32_t* pinnedTotals = nullptr; // pinned host words for small D2H results
+
+    // Profiling.
+    bool profiling = false;
+    cudaEvent_t events[8] = {};
+    rivecuda_flush_timings lastTimings{};
+    bool timingsPending = false;
+    uint32_t lastLaunches = 0;
+};
+
+namespace rivecuda
+{
+// kernels_ramp_tess.cu
+int launch_color_ramps(rivecuda_ctx* ctx, const rivecuda_flush_desc& desc, const void* gradSpans);
+int launch_tessellate(rivecuda_ctx* ctx,
+                      const rivecuda_flush_desc& desc,
+                      const void* tessSpans,
+                      const void* pathBuffer,
+                      const void* contourBuffer);
+// kernels_atlas.cu
+int launch_atlas(rivecuda_ctx* ctx,
+                 const rivecuda_flush_desc& desc,
+                 const rivecuda_atlas_batch* fills,
+                 uint32_t fillCount,
+                 const rivecuda_atlas_batch* strokes,
+                 uint32_t strokeCount);
+// kernels_draw.cu
+int launch_draw_list(rivecuda_ctx* ctx,
+                     const rivecuda_flush_desc& desc,
+                     const rivecuda_draw_batch* batches,
+                     uint32_t batchCount);
+} // namespace rivecuda
