@@ -232,6 +232,10 @@ int rivecuda_resize_feather_atlas_texture(rivecuda_ctx* ctx, uint32_t width, uin
 /* A device-resident premultiplied RGBA8 framebuffer (row-major, top-down;
  * what RenderTargetVulkan is to the Vulkan backend). */
 int rivecuda_target_create(rivecuda_ctx* ctx, uint32_t width, uint32_t height, rivecuda_target** out);
+/* Same, over caller-owned device memory (width*height*4 bytes on this
+ * context's device), e.g. a torch tensor that is later handed to NCCL. The
+ * memory is not freed by rivecuda_target_destroy(). */
+int rivecuda_target_wrap(rivecuda_ctx* ctx, uint32_t width, uint32_t height, void* device_rgba8, rivecuda_target** out);
 void rivecuda_target_destroy(rivecuda_ctx* ctx, rivecuda_target* target);
 /* Synchronising D2H read / H2D write of the whole target (RGBA8, w*h*4 bytes). */
 int rivecuda_target_read_pixels(rivecuda_ctx* ctx, const rivecuda_target* target, void* host_rgba8, size_t size_in_bytes);

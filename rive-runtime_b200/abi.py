@@ -33,6 +33,7 @@ SIGNATURES = {
     "rivecuda_resize_tessellation_texture": (_int, [_vp, _u32, _u32]),
     "rivecuda_resize_feather_atlas_texture": (_int, [_vp, _u32, _u32]),
     "rivecuda_target_create": (_int, [_vp, _u32, _u32, ctypes.POINTER(_vp)]),
+    "rivecuda_target_wrap": (_int, [_vp, _u32, _u32, _vp, ctypes.POINTER(_vp)]),
     "rivecuda_target_destroy": (None, [_vp, _vp]),
     "rivecuda_target_read_pixels": (_int, [_vp, _vp, _vp, _sz]),
     "rivecuda_target_write_pixels": (_int, [_vp, _vp, _vp, _sz]),

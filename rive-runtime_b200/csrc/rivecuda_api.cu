@@ -326,13 +326,27 @@ int rivecuda_target_create(rivecuda_ctx* ctx, uint32_t width, uint32_t height, r
     return 0;
 }
 
+int rivecuda_target_wrap(rivecuda_ctx*, uint32_t width, uint32_t height, void* device_rgba8, rivecuda_target** out)
+{
+    if (out == nullptr || device_rgba8 == nullptr || width == 0 || height == 0)
+        return set_error("rivecuda_target_wrap: bad arguments");
+    auto* t = new rivecuda_target;
+    t->width = width;
+    t->height = height;
+    t->pixels = static_cast<uint32_t*>(device_rgba8);
+    t->owned = false;
+    *out = t;
+    return 0;
+}
+
 void rivecuda_target_destroy(rivecuda_ctx* ctx, rivecuda_target* target)
 {
     if (target == nullptr)
         return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    cudaFree(target->pixels);
+    if (target->owned)
+        cudaFree(target->pixels);
     delete target;
 }
 

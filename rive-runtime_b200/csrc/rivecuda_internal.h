@@ -82,6 +82,7 @@ struct rivecuda_target
 {
     uint32_t width = 0, height = 0;
     uint32_t* pixels = nullptr; // device RGBA8 premultiplied, row-major
+    bool owned = true;
 };
 
 struct rivecuda_texture

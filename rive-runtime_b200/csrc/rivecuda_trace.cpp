@@ -217,6 +217,11 @@ int rivecuda_target_create(rivecuda_ctx* ctx, uint32_t w, uint32_t h, rivecuda_t
     return 0;
 }
 
+int rivecuda_target_wrap(rivecuda_ctx* ctx, uint32_t w, uint32_t h, void*, rivecuda_target** out)
+{
+    return rivecuda_target_create(ctx, w, h, out);
+}
+
 void rivecuda_target_destroy(rivecuda_ctx* ctx, rivecuda_target* t)
 {
     Record r;

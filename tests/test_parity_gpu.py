@@ -1,0 +1,121 @@
+"""Parity tests proper: the CUDA path, called through the C ABI with the host
+buffers the reference front end produced, against the CPU oracle on the same
+inputs. Tolerance (north_star): max per-channel delta <= 2/255 and PSNR >= 45 dB.
+Tessellation flags / ids are bit-exact; positions and angles within float
+tolerance; gradient ramps bit-exact."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, golden_traces
+
+pytestmark = pytest.mark.gpu
+
+MAX_DELTA = 2          # /255, per channel
+MIN_PSNR = 45.0        # dB
+
+
+def psnr(a, b):
+    mse = np.mean((a.astype(np.float64) - b.astype(np.float64)) ** 2)
+    return 99.0 if mse == 0 else 10 * np.log10(255.0 ** 2 / mse)
+
+
+@pytest.fixture(scope="module")
+def libs(built):
+    from rive_runtime_b200 import replay, trace, abi
+    from oracle import refcpu
+    abi.load()  # fail loudly if the CUDA extension is missing
+    return replay, trace, refcpu
+
+
+@pytest.mark.parametrize("name", golden_traces())
+def test_scene_parity(libs, name):
+    replay, T, refcpu = libs
+    recs = T.parse(os.path.join(GOLDEN, name))
+    ref = refcpu.replay(recs, threads=os.cpu_count() or 1)
+    got = replay.replay(recs, keep_intermediates=True)
+    assert len(got.frames) == len(ref.frames) >= 1
+    for fr, fg in zip(ref.flushes, got.flushes):
+        n = fr.desc.tess_data_height * 2048
+        if n:
+            rt, gt = fr.tess[:n], fg.tess[:n]
+            assert np.array_equal(rt[:, 3], gt[:, 3]), "contourIDWithFlags must be bit-exact"
+            packed = ((rt[:, 3] >> 26) & 7) == 1  # feather joins pack (segmentCount<<16 | vertexID)
+            assert np.array_equal(rt[packed, 2], gt[packed, 2])
+            rxy, gxy = rt[:, :2].view(np.float32), gt[:, :2].view(np.float32)
+            scale = max(1.0, float(np.nanmax(np.abs(rxy))))
+            assert np.nanmax(np.abs(rxy - gxy)) <= 2e-6 * scale + 1e-4
+            dth = np.abs(rt[~packed, 2].view(np.float32) - gt[~packed, 2].view(np.float32))
+            dth = np.minimum(dth, np.abs(dth - 2 * np.pi))
+            assert dth.size == 0 or np.nanmax(dth) <= 1e-4
+        if fr.desc.grad_data_height:
+            assert np.array_equal(fr.grad[:fr.desc.grad_data_height], fg.grad), "colour ramps must be bit-exact"
+    for a, b in zip(ref.frames, got.frames):
+        delta = int(np.abs(a.astype(int) - b.astype(int)).max())
+        assert delta <= MAX_DELTA, f"{name}: max channel delta {delta}/255"
+        assert psnr(a, b) >= MIN_PSNR, f"{name}: PSNR {psnr(a, b):.1f} dB"
+
+
+def test_c2_full_size_parity_and_properties(libs):
+    """BASELINE.json configs[1] at full size (10k paths, 3840x2160): parity with the
+    oracle, idempotence, and band decomposition (size-independent properties)."""
+    replay, T, refcpu = libs
+    from rive_runtime_b200 import sharding
+    recs = T.parse(os.path.join(GOLDEN, "c2_4k.rvct.xz"))
+    got = replay.replay(recs)
+    again = replay.replay(recs)
+    assert np.array_equal(got.frames[0], again.frames[0]), "rendering must be deterministic"
+    ref = refcpu.replay(recs, threads=os.cpu_count() or 1, keep_intermediates=False)
+    delta = int(np.abs(ref.frames[0].astype(int) - got.frames[0].astype(int)).max())
+    assert delta <= MAX_DELTA and psnr(ref.frames[0], got.frames[0]) >= MIN_PSNR
+    # Render the frame as 4 screen bands (what tile-band sharding does) into one target:
+    # the composite must be bit-identical to the single-pass render.
+    result = replay.ReplayResult()
+    with replay.Replayer(0) as rp:
+        for r in recs:
+            if r.tag in (T.CREATE, T.DESTROY, T.TARGET_READ):
+                continue
+            if r.tag == T.FLUSH:
+                fr = r.fields["flush"]
+                pf = rp.prepare_flush(fr)
+                h = rp.target_shapes[fr.target_id][0]
+                for band_rank in range(4):
+                    band = sharding.band_for_rank(h, band_rank, 4)
+                    pf.desc = sharding.restrict_to_band(rp.prepare_flush(fr).desc, band)
+                    rp.flush(pf)
+                continue
+            rp.apply(r, result)
+        banded = rp.read_target(1)
+    assert np.array_equal(banded, got.frames[0])
+
+
+def test_clear_only_and_preserve(libs):
+    """Empty draw list: clear fills exactly the premultiplied clear colour inside the
+    update bounds; preserveRenderTarget leaves pixels untouched."""
+    import ctypes
+    replay, T, _ = libs
+    recs = T.parse(os.path.join(GOLDEN, "beziers.rvct.xz"))
+    with replay.Replayer(0) as rp:
+        result = replay.ReplayResult()
+        for r in recs:
+            if r.tag in (T.STATIC_TABLES, T.BUFFER_RESIZE, T.BUFFER_UNMAP, T.RESIZE_GRADIENT, T.RESIZE_TESSELLATION,
+                         T.TARGET_CREATE):
+                rp.apply(r, result)
+        fr = next(r.fields["flush"] for r in recs if r.tag == T.FLUSH)
+        pf = rp.prepare_flush(fr)
+        pf.batch_count = 0
+        pf.desc.color_clear_value = 0x80ff8040  # a=128 r=255 g=128 b=64
+        pf.desc.update_bounds[:] = [16, 32, 200, 300]
+        rp.flush(pf)
+        px = rp.read_target(1)
+        inside = px[32:300, 16:200].reshape(-1, 4)
+        a = 128 / 255
+        want = [int(255 / 255 * a * 255 + .5), int(128 / 255 * a * 255 + .5), int(64 / 255 * a * 255 + .5), 128]
+        assert (inside == np.array(want, np.uint8)).all()
+        assert px[:32].max() == 0 and px[:, :16].max() == 0 and px[300:].max() == 0 and px[:, 200:].max() == 0
+        before = px.copy()
+        pf.desc.color_load_action = 1  # preserveRenderTarget
+        pf.desc.update_bounds[:] = [0, 0, 400, 800]
+        rp.flush(pf)
+        assert np.array_equal(rp.read_target(1), before)
