@@ -500,12 +500,68 @@ template <typename Fn> __device__ __forceinline__ void for_each_tile(const Flush
     }
 }
 
+// Warp-cooperative version: every lane of the warp calls this (valid = lane has
+// a triangle). Triangles that overlap only a few tiles are walked by their own
+// lane; larger ones are broadcast one at a time and their tile range is tested
+// by all 32 lanes in parallel, so a full-screen triangle costs tiles/32
+// iterations instead of stalling one lane. fn(tile, ownerLane) is invoked by
+// whichever lane found the overlap; ownerLane says whose triangle it is.
+constexpr int kSmallTileCount = 4;
+
+template <typename Fn>
+__device__ __forceinline__ void warp_for_each_tile(const FlushParams& P, const int32_t X[3], const int32_t Y[3], bool valid, Fn&& fn)
+{
+    const int lane = threadIdx.x & 31;
+    TileRange r;
+    r.tx0 = 1;
+    r.tx1 = 0;
+    r.ty0 = 1;
+    r.ty1 = 0;
+    if (valid)
+        r = triangle_tile_range(P, X, Y);
+    const int w = r.tx1 - r.tx0 + 1, h = r.ty1 - r.ty0 + 1;
+    const int count = (r.tx0 > r.tx1) ? 0 : w * h;
+    if (count > 0 && count <= kSmallTileCount)
+    {
+        EdgeEq E[3];
+        edge_equations(X, Y, E);
+        for (int ty = r.ty0; ty <= r.ty1; ++ty)
+            for (int tx = r.tx0; tx <= r.tx1; ++tx)
+                if (count == 1 || tile_overlaps(E, tx + P.tileX0, ty + P.tileY0))
+                    fn(static_cast<uint32_t>(ty) * P.tilesX + static_cast<uint32_t>(tx), lane);
+    }
+    uint32_t big = __ballot_sync(0xffffffffu, count > kSmallTileCount);
+    while (big != 0u)
+    {
+        const int src = __ffs(big) - 1;
+        big &= big - 1;
+        int32_t BX[3], BY[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+        {
+            BX[k] = __shfl_sync(0xffffffffu, X[k], src);
+            BY[k] = __shfl_sync(0xffffffffu, Y[k], src);
+        }
+        const int tx0 = __shfl_sync(0xffffffffu, r.tx0, src), ty0 = __shfl_sync(0xffffffffu, r.ty0, src);
+        const int bw = __shfl_sync(0xffffffffu, w, src), bcount = __shfl_sync(0xffffffffu, count, src);
+        EdgeEq E[3];
+        edge_equations(BX, BY, E);
+        for (int idx = lane; idx < bcount; idx += 32)
+        {
+            const int ty = ty0 + idx / bw, tx = tx0 + idx % bw;
+            if (tile_overlaps(E, tx + P.tileX0, ty + P.tileY0))
+                fn(static_cast<uint32_t>(ty) * P.tilesX + static_cast<uint32_t>(tx), src);
+        }
+    }
+}
+
 // Snap, orient, cull and store one triangle; returns true if stored.
 // attr[c*3+k]. cullCCW false => counter-clockwise triangles are re-wound.
 __device__ __forceinline__ bool store_triangle(const FlushParams& P,
                                                TriGeom* __restrict__ triGeom,
                                                TriAttr* __restrict__ triAttr,
-                                               uint32_t* __restrict__ tileCounts,
+                                               int32_t X[3],
+                                               int32_t Y[3],
                                                uint32_t rawTri,
                                                const float xs[3],
                                                const float ys[3],
@@ -515,11 +571,13 @@ __device__ __forceinline__ bool store_triangle(const FlushParams& P,
                                                uint32_t aux,
                                                bool cullCCW)
 {
-    int32_t X[3], Y[3];
     bool ok = true;
 #pragma unroll
     for (int k = 0; k < 3; ++k)
+    {
+        X[k] = Y[k] = 0;
         ok = ok && snap_coord(xs[k], X[k]) && snap_coord(ys[k], Y[k]);
+    }
     int64_t area2 = 0;
     if (ok)
     {
@@ -578,7 +636,6 @@ __device__ __forceinline__ bool store_triangle(const FlushParams& P,
         dst[1] = make_float4(attr[4], attr[5], attr[6], attr[7]);
     if (attrComponents > 2)
         dst[2] = make_float4(attr[8], attr[9], attr[10], attr[11]);
-    for_each_tile(P, X, Y, [&](uint32_t tile) { atomicAdd(tileCounts + tile, 1u); });
     return true;
 }
 
@@ -645,29 +702,36 @@ __global__ void __launch_bounds__(kSetupWarpsPerBlock * 32) setup_patches_kernel
             verts[v] = shade_patch_vertex(P, P.patchVertices + (vmin + v) * 8, instanceID, enableFeather);
         __syncwarp();
         const uint32_t tris = b.trisPerElement;
-        for (uint32_t t = lane; t < tris; t += 32)
+        for (uint32_t tbase = 0; tbase < tris; tbase += 32)
         {
-            const uint32_t rawTri = b.firstTriangle + inst * tris + t;
-            const uint32_t i0 = __ldg(P.patchIndices + b.baseIndex + t * 3 + 0) - vmin;
-            const uint32_t i1 = __ldg(P.patchIndices + b.baseIndex + t * 3 + 1) - vmin;
-            const uint32_t i2 = __ldg(P.patchIndices + b.baseIndex + t * 3 + 2) - vmin;
-            const ShadedVertex a = verts[i0], c = verts[i1], d = verts[i2];
-            const uint32_t pathID = a.pathID_ok & 0xffffu; // flat varying: provoking vertex
-            const bool ok = (a.pathID_ok & c.pathID_ok & d.pathID_ok & 0x10000u) != 0u;
-            float xs[3] = {a.x, c.x, d.x}, ys[3] = {a.y, c.y, d.y};
-            if (!ok)
-                xs[0] = __int_as_float(0x7fc00000); // vertexDiscardValue = NaN
-            // Classify the path.
-            const uint4 pd = __ldg(P.pathBuffer + pathID * 4u + 1u);
-            const bool isStroke = __uint_as_float(pd.z) != 0.f;
-            const bool isFeathered = enableFeather && __uint_as_float(pd.w) != 0.f;
-            uint32_t kind = isStroke ? (isFeathered ? kKindFeatherStroke : kKindStroke) : (isFeathered ? kKindFeatherFill : kKindFill);
-            float attr[12] = {a.c0, c.c0, d.c0, a.c1, c.c1, d.c1, a.c2, c.c2, d.c2, a.c3, c.c3, d.c3};
-            const int comps = kind == kKindFill ? 1 : (kind == kKindFeatherFill ? 4 : 2);
-            uint32_t meta = pathID | (kind << kMetaKindShift);
-            if ((b.miscFlags & RIVECUDA_MISC_CLOCKWISE_FILL) != 0u)
-                meta |= kMetaClockwiseFill;
-            store_triangle(P, triGeom, triAttr, tileCounts, rawTri, xs, ys, attr, comps, meta, 0u, /*cullCCW=*/true);
+            const uint32_t t = tbase + lane;
+            int32_t X[3] = {0, 0, 0}, Y[3] = {0, 0, 0};
+            bool stored = false;
+            if (t < tris)
+            {
+                const uint32_t rawTri = b.firstTriangle + inst * tris + t;
+                const uint32_t i0 = __ldg(P.patchIndices + b.baseIndex + t * 3 + 0) - vmin;
+                const uint32_t i1 = __ldg(P.patchIndices + b.baseIndex + t * 3 + 1) - vmin;
+                const uint32_t i2 = __ldg(P.patchIndices + b.baseIndex + t * 3 + 2) - vmin;
+                const ShadedVertex a = verts[i0], c = verts[i1], d = verts[i2];
+                const uint32_t pathID = a.pathID_ok & 0xffffu; // flat varying: provoking vertex
+                const bool ok = (a.pathID_ok & c.pathID_ok & d.pathID_ok & 0x10000u) != 0u;
+                float xs[3] = {a.x, c.x, d.x}, ys[3] = {a.y, c.y, d.y};
+                if (!ok)
+                    xs[0] = __int_as_float(0x7fc00000); // vertexDiscardValue = NaN
+                // Classify the path.
+                const uint4 pd = __ldg(P.pathBuffer + pathID * 4u + 1u);
+                const bool isStroke = __uint_as_float(pd.z) != 0.f;
+                const bool isFeathered = enableFeather && __uint_as_float(pd.w) != 0.f;
+                const uint32_t kind = isStroke ? (isFeathered ? kKindFeatherStroke : kKindStroke) : (isFeathered ? kKindFeatherFill : kKindFill);
+                float attr[12] = {a.c0, c.c0, d.c0, a.c1, c.c1, d.c1, a.c2, c.c2, d.c2, a.c3, c.c3, d.c3};
+                const int comps = kind == kKindFill ? 1 : (kind == kKindFeatherFill ? 4 : 2);
+                uint32_t meta = pathID | (kind << kMetaKindShift);
+                if ((b.miscFlags & RIVECUDA_MISC_CLOCKWISE_FILL) != 0u)
+                    meta |= kMetaClockwiseFill;
+                stored = store_triangle(P, triGeom, triAttr, X, Y, rawTri, xs, ys, attr, comps, meta, 0u, /*cullCCW=*/true);
+            }
+            warp_for_each_tile(P, X, Y, stored, [&](uint32_t tile, int) { atomicAdd(tileCounts + tile, 1u); });
         }
     }
 }
@@ -682,8 +746,13 @@ __global__ void __launch_bounds__(256) setup_triangle_runs_kernel(FlushParams P,
                                                                  TriAttr* __restrict__ triAttr,
                                                                  uint32_t* __restrict__ tileCounts)
 {
-    for (uint32_t item = blockIdx.x * blockDim.x + threadIdx.x; item < totalTriangles; item += gridDim.x * blockDim.x)
+    for (uint32_t itemBase = blockIdx.x * blockDim.x; itemBase < totalTriangles; itemBase += gridDim.x * blockDim.x)
     {
+        const uint32_t item = itemBase + threadIdx.x;
+        int32_t X[3] = {0, 0, 0}, Y[3] = {0, 0, 0};
+        bool stored = false;
+        if (item < totalTriangles)
+        {
         const uint32_t bi = find_batch(batches, batchCount, item);
         const DeviceBatch b = batches[bi];
         const uint32_t t = item - b.firstWorkItem;
@@ -739,7 +808,9 @@ __global__ void __launch_bounds__(256) setup_triangle_runs_kernel(FlushParams P,
         }
         if ((b.miscFlags & RIVECUDA_MISC_CLOCKWISE_FILL) != 0u)
             meta |= kMetaClockwiseFill;
-        store_triangle(P, triGeom, triAttr, tileCounts, rawTri, xs, ys, attr, comps, meta, 0u, /*cullCCW=*/true);
+        stored = store_triangle(P, triGeom, triAttr, X, Y, rawTri, xs, ys, attr, comps, meta, 0u, /*cullCCW=*/true);
+        }
+        warp_for_each_tile(P, X, Y, stored, [&](uint32_t tile, int) { atomicAdd(tileCounts + tile, 1u); });
     }
 }
 
@@ -857,18 +928,28 @@ __global__ void __launch_bounds__(256) scatter_kernel(FlushParams P,
                                                       uint32_t* __restrict__ entries,
                                                       uint32_t entryCapacity)
 {
-    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < triCount; t += gridDim.x * blockDim.x)
+    for (uint32_t tBase = blockIdx.x * blockDim.x; tBase < triCount; tBase += gridDim.x * blockDim.x)
     {
-        const uint4 lo = __ldg(reinterpret_cast<const uint4*>(triGeom + t));
-        const uint4 hi = __ldg(reinterpret_cast<const uint4*>(triGeom + t) + 1);
-        if ((hi.z & kMetaValid) == 0u)
-            continue;
-        const int32_t X[3] = {static_cast<int32_t>(lo.x), static_cast<int32_t>(lo.z), static_cast<int32_t>(hi.x)};
-        const int32_t Y[3] = {static_cast<int32_t>(lo.y), static_cast<int32_t>(lo.w), static_cast<int32_t>(hi.y)};
-        for_each_tile(P, X, Y, [&](uint32_t tile) {
+        const uint32_t t = tBase + threadIdx.x;
+        int32_t X[3] = {0, 0, 0}, Y[3] = {0, 0, 0};
+        bool valid = false;
+        if (t < triCount)
+        {
+            const uint4 lo = __ldg(reinterpret_cast<const uint4*>(triGeom + t));
+            const uint4 hi = __ldg(reinterpret_cast<const uint4*>(triGeom + t) + 1);
+            valid = (hi.z & kMetaValid) != 0u;
+            X[0] = static_cast<int32_t>(lo.x);
+            Y[0] = static_cast<int32_t>(lo.y);
+            X[1] = static_cast<int32_t>(lo.z);
+            Y[1] = static_cast<int32_t>(lo.w);
+            X[2] = static_cast<int32_t>(hi.x);
+            Y[2] = static_cast<int32_t>(hi.y);
+        }
+        const uint32_t warpBase = t - (threadIdx.x & 31);
+        warp_for_each_tile(P, X, Y, valid, [&](uint32_t tile, int ownerLane) {
             const uint32_t pos = __ldg(tileOffsets + tile) + atomicAdd(tileCursors + tile, 1u);
             if (pos < entryCapacity)
-                entries[pos] = t;
+                entries[pos] = warpBase + static_cast<uint32_t>(ownerLane);
         });
     }
 }
@@ -943,578 +1024,7 @@ __global__ void __launch_bounds__(256) sort_tiles_kernel(const uint32_t* __restr
     }
 }
 
-// ---------------------------------------------------------------------------
-// Raster
-
-struct Prepared // 24 words, one per (triangle, tile), in shared memory
-{
-    int32_t A0, B0, q0, A1, B1, q1, A2, B2, q2;
-    float plane[4][3]; // P0, Px, Py per attribute component
-    uint32_t meta;     // TriGeom::meta (0 => skip)
-    uint32_t bbox;     // xmin | xmax<<4 | ymin<<8 | ymax<<12, tile-local
-    uint32_t aux;
-};
-static_assert(sizeof(Prepared) == 96, "Prepared");
-
-constexpr int kRasterChunk = 256;
-
-__device__ __forceinline__ int64_t floor_shift8(int64_t v) { return v >> 8; }
-
-// Builds the tile-local form of one triangle. Exact for edges whose Manhattan
-// length is below ~2^18 px; longer edges are scaled (approximate).
-__device__ void prepare_triangle(const TriGeom& g, const TriAttr* __restrict__ attrPtr, int originX, int originY, Prepared& out)
-{
-    out.meta = 0;
-    out.bbox = 0;
-    out.aux = g.aux;
-    if ((g.meta & kMetaValid) == 0u)
-        return;
-    const int32_t X[3] = {g.x0, g.x1, g.x2}, Y[3] = {g.y0, g.y1, g.y2};
-    const int64_t px0 = (static_cast<int64_t>(originX) << 8) + 128, py0 = (static_cast<int64_t>(originY) << 8) + 128;
-    int64_t A[3], B[3], E0u[3];
-    int32_t Ai[3], Bi[3], qi[3];
-    bool reject = false;
-#pragma unroll
-    for (int e = 0; e < 3; ++e)
-    {
-        const int a = (e + 1) % 3, b = (e + 2) % 3;
-        const int64_t dx = static_cast<int64_t>(X[b]) - X[a], dy = static_cast<int64_t>(Y[b]) - Y[a];
-        const bool topLeft = (dy == 0 && dx > 0) || (dy < 0);
-        A[e] = -dy;
-        B[e] = dx;
-        const int64_t C = dy * X[a] - dx * Y[a];
-        E0u[e] = A[e] * px0 + B[e] * py0 + C;
-        // E(i,j) - bias = E0u - bias + 256*(A*i + B*j) >= 0  <=>  q + A*i + B*j >= 0
-        const int64_t q = floor_shift8(E0u[e] - (topLeft ? 0 : 1));
-        const int64_t n = kTileSize - 1;
-        const int64_t emin = q + n * (A[e] < 0 ? A[e] : 0) + n * (B[e] < 0 ? B[e] : 0);
-        const int64_t emax = q + n * (A[e] > 0 ? A[e] : 0) + n * (B[e] > 0 ? B[e] : 0);
-        if (emax < 0)
-            reject = true;
-        if (emin >= 0)
-        {
-            Ai[e] = Bi[e] = qi[e] = 0; // trivially inside for the whole tile
-        }
-        else
-        {
-            int64_t a64 = A[e], b64 = B[e], q64 = q;
-            // Keep |q| + 15|A| + 15|B| inside int32.
-            while ((a64 < 0 ? -a64 : a64) + (b64 < 0 ? -b64 : b64) >= (1ll << 25))
-            {
-                a64 >>= 1;
-                b64 >>= 1;
-                q64 >>= 1;
-            }
-            Ai[e] = static_cast<int32_t>(a64);
-            Bi[e] = static_cast<int32_t>(b64);
-            qi[e] = static_cast<int32_t>(q64);
-        }
-    }
-    if (reject)
-        return;
-    // Tile-local pixel bounds of candidate pixels.
-    const int32_t minX = min(X[0], min(X[1], X[2])), maxX = max(X[0], max(X[1], X[2]));
-    const int32_t minY = min(Y[0], min(Y[1], Y[2])), maxY = max(Y[0], max(Y[1], Y[2]));
-    const int bx0 = max(((minX - 128 + 255) >> 8) - originX, 0), bx1 = min(((maxX - 128) >> 8) - originX, kTileSize - 1);
-    const int by0 = max(((minY - 128 + 255) >> 8) - originY, 0), by1 = min(((maxY - 128) >> 8) - originY, kTileSize - 1);
-    if (bx0 > bx1 || by0 > by1)
-        return;
-    out.A0 = Ai[0];
-    out.B0 = Bi[0];
-    out.q0 = qi[0];
-    out.A1 = Ai[1];
-    out.B1 = Bi[1];
-    out.q1 = qi[1];
-    out.A2 = Ai[2];
-    out.B2 = Bi[2];
-    out.q2 = qi[2];
-    out.bbox = static_cast<uint32_t>(bx0) | (static_cast<uint32_t>(bx1) << 4) | (static_cast<uint32_t>(by0) << 8) | (static_cast<uint32_t>(by1) << 12);
-    out.meta = g.meta;
-    // Attribute planes from exact barycentrics at tile pixel (0,0):
-    //   attr(i,j) = sum_k c_k * (E0u_k + 256*(A_k*i + B_k*j)) / area2
-    const double area2 = static_cast<double>(E0u[0] + E0u[1] + E0u[2]);
-    const double inv = 1.0 / area2;
-    const uint32_t kind = (g.meta >> kMetaKindShift) & 0xf;
-    const int comps = kind == kKindFill ? 1 : (kind == kKindFeatherFill ? 4 : 2);
-    const float* attr = attrPtr->attr;
-    for (int c = 0; c < comps; ++c)
-    {
-        const double c0 = attr[c * 3 + 0], c1 = attr[c * 3 + 1], c2 = attr[c * 3 + 2];
-        out.plane[c][0] = static_cast<float>((c0 * static_cast<double>(E0u[0]) + c1 * static_cast<double>(E0u[1]) + c2 * static_cast<double>(E0u[2])) * inv);
-        out.plane[c][1] = static_cast<float>((c0 * static_cast<double>(A[0]) + c1 * static_cast<double>(A[1]) + c2 * static_cast<double>(A[2])) * 256.0 * inv);
-        out.plane[c][2] = static_cast<float>((c0 * static_cast<double>(B[0]) + c1 * static_cast<double>(B[1]) + c2 * static_cast<double>(B[2])) * 256.0 * inv);
-    }
-}
-
-// draw_path_common.glsl:153-258
-__device__ float eval_feathered_fill(const float* __restrict__ lut, float4 cov)
-{
-    const float cotTheta = cov.z;
-    const float y0 = fmaxf(cov.w, 0.f);
-    float featherCoverage = cotTheta >= 0.f ? feather_lut(lut, y0) : 0.f;
-    if (fabsf(cotTheta) < kHorizontalCotangentThreshold)
-    {
-        const float x = fabsf(cov.x) - kFeatherXCoordBias;
-        const float y = -cov.y + kFeatherCoverageBias;
-        const float dt = (y - y0) * 0.5984134206f;
-        const float k[4] = {0.20888568955f, 0.62665706865f, 1.04442844776f, 1.46219982687f};
-        float sum = 0.f;
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-        {
-            const float t = y0 + dt * k[i];
-            const float u = t * -cotTheta + (y * cotTheta + x);
-            const float t_ = t * 5.09593080173f + -2.54796540086f;
-            sum += feather_lut(lut, u) * exp2f(-t_ * t_);
-        }
-        featherCoverage += sum * dt;
-    }
-    return featherCoverage * signf(cov.x);
-}
-
-__device__ __forceinline__ float eval_feathered_stroke(const float* __restrict__ lut, float cx, float cy)
-{
-    float c = 1.f;
-    c -= feather_lut(lut, (1.f - kFeatherCoverageBias) + cx);
-    c -= feather_lut(lut, 1.f - cy);
-    return c;
-}
-
-// ---- advanced_blend.glsl:91-330 ----
-
-__device__ __forceinline__ float lum(float3 c) { return c.x * .30f + c.y * .59f + c.z * .11f; }
-__device__ __forceinline__ float min3f(float3 c) { return fminf(fminf(c.x, c.y), c.z); }
-__device__ __forceinline__ float max3f(float3 c) { return fmaxf(fmaxf(c.x, c.y), c.z); }
-
-__device__ float3 set_lum(float3 base, float3 lumColor)
-{
-    const float lumTarget = lum(lumColor);
-    const float lb = lum(base);
-    const float3 biased = make_float3(base.x - lb, base.y - lb, base.z - lb);
-    const float s0 = lumTarget / fmaxf(kEpsilonFP16, -min3f(biased));
-    const float s1 = (1.f - lumTarget) / fmaxf(kEpsilonFP16, max3f(biased));
-    const float satScale = fminf(1.f, fminf(s0, s1));
-    return make_float3(biased.x * satScale + lumTarget, biased.y * satScale + lumTarget, biased.z * satScale + lumTarget);
-}
-
-__device__ float3 set_lum_sat(float3 hueColor, float3 satColor, float3 lumColor)
-{
-    const float satTarget = max3f(satColor) - min3f(satColor);
-    const float mn = min3f(hueColor);
-    hueColor = make_float3(hueColor.x - mn, hueColor.y - mn, hueColor.z - mn);
-    const float scale = satTarget / fmaxf(kEpsilonFP16, max3f(hueColor));
-    return set_lum(make_float3(hueColor.x * scale, hueColor.y * scale, hueColor.z * scale), lumColor);
-}
-
-__device__ __forceinline__ float clamp01(float v) { return clampf(v, 0.f, 1.f); }
-
-__device__ float blend_channel(uint32_t mode, float s, float d, float dPremul, float dA)
-{
-    switch (mode)
-    {
-        case 11: // multiply
-            return s * d;
-        case 1: // screen
-            return s + d - s * d;
-        case 2: // overlay
-        {
-            const float sd = s * d;
-            return 2.f * (d > .5f ? s + d - sd - .5f : sd);
-        }
-        case 3:
-            return fminf(s, d);
-        case 4:
-            return fmaxf(s, d);
-        case 5: // colordodge
-        {
-            const float dp = clampf(dPremul, 0.f, dA);
-            const float denom = clamp01(1.f - s) * dA;
-            return denom == 0.f ? signf(dp) : fminf(1.f, dp / denom);
-        }
-        case 6: // colorburn
-        {
-            const float sc = clamp01(s);
-            const float dp = clampf(dPremul, 0.f, dA);
-            const float da = dA == 0.f ? 1.f : dA;
-            const float numer = da - dp;
-            return 1.f - (sc == 0.f ? signf(numer) : fminf(1.f, numer / (sc * da)));
-        }
-        case 7: // hardlight
-        {
-            const float sd = s * d;
-            return 2.f * (s > .5f ? s + d - sd - .5f : sd);
-        }
-        case 8: // softlight
-        {
-            float k;
-            if (s <= .5f)
-                k = 1.f - d;
-            else if (d <= .25f)
-                k = (16.f * d - 12.f) * d + 3.f;
-            else
-                k = 1.f / sqrtf(d) - 1.f;
-            return d + d * (2.f * s - 1.f) * k;
-        }
-        case 9:
-            return fabsf(d - s);
-        case 10:
-            return s + d - 2.f * s * d;
-        default:
-            return 0.f;
-    }
-}
-
-__device__ float3 advanced_color_blend(float3 src, float4 dstPremul, uint32_t mode)
-{
-    const float invA = dstPremul.w != 0.f ? 1.f / dstPremul.w : 0.f;
-    const float3 dst = make_float3(dstPremul.x * invA, dstPremul.y * invA, dstPremul.z * invA);
-    float3 coeffs;
-    if (mode >= 12)
-    {
-        const float3 sc = make_float3(clamp01(src.x), clamp01(src.y), clamp01(src.z));
-        switch (mode)
-        {
-            case 12:
-                coeffs = set_lum_sat(sc, dst, dst);
-                break;
-            case 13:
-                coeffs = set_lum_sat(dst, sc, dst);
-                break;
-            case 14:
-                coeffs = set_lum(sc, dst);
-                break;
-            default:
-                coeffs = set_lum(dst, sc);
-                break;
-        }
-    }
-    else
-    {
-        coeffs.x = blend_channel(mode, src.x, dst.x, dstPremul.x, dstPremul.w);
-        coeffs.y = blend_channel(mode, src.y, dst.y, dstPremul.y, dstPremul.w);
-        coeffs.z = blend_channel(mode, src.z, dst.z, dstPremul.z, dstPremul.w);
-    }
-    const float a = dstPremul.w;
-    return make_float3(src.x * (1.f - a) + coeffs.x * a, src.y * (1.f - a) + coeffs.y * a, src.z * (1.f - a) + coeffs.z * a);
-}
-
-__device__ __forceinline__ float4 fetch_grad(const FlushParams& P, int x, int y)
-{
-    x = min(max(x, 0), kGradWidth - 1);
-    y = min(max(y, 0), static_cast<int>(P.gradHeight) - 1);
-    return unpack_rgba8(__ldg(P.gradTexture + y * kGradWidth + x));
-}
-
-__device__ float4 sample_grad(const FlushParams& P, float u, float v)
-{
-    const float x = u * 512.f - .5f, y = v * static_cast<float>(P.gradHeight) - .5f;
-    const float fx = floorf(x), fy = floorf(y);
-    const float tx = x - fx, ty = y - fy;
-    const int ix = static_cast<int>(clampf(fx, -1.f, 512.f)), iy = static_cast<int>(clampf(fy, -1.f, 65536.f));
-    const float4 c00 = fetch_grad(P, ix, iy), c10 = fetch_grad(P, ix + 1, iy);
-    const float4 c01 = fetch_grad(P, ix, iy + 1), c11 = fetch_grad(P, ix + 1, iy + 1);
-    float4 top = make_float4(c00.x + (c10.x - c00.x) * tx, c00.y + (c10.y - c00.y) * tx, c00.z + (c10.z - c00.z) * tx, c00.w + (c10.w - c00.w) * tx);
-    float4 bot = make_float4(c01.x + (c11.x - c01.x) * tx, c01.y + (c11.y - c01.y) * tx, c01.z + (c11.z - c01.z) * tx, c01.w + (c11.w - c01.w) * tx);
-    return make_float4(top.x + (bot.x - top.x) * ty, top.y + (bot.y - top.y) * ty, top.z + (bot.z - top.z) * ty, top.w + (bot.w - top.w) * ty);
-}
-
-__device__ float sample_atlas(const FlushParams& P, float u, float v)
-{
-    const float x = u * P.atlasWidth - .5f, y = v * P.atlasHeight - .5f;
-    const float fx = floorf(x), fy = floorf(y);
-    const float tx = x - fx, ty = y - fy;
-    const int ix = static_cast<int>(clampf(fx, -1.f, 65536.f)), iy = static_cast<int>(clampf(fy, -1.f, 65536.f));
-    auto fetch = [&](int xx, int yy) {
-        xx = min(max(xx, 0), static_cast<int>(P.atlasWidth) - 1);
-        yy = min(max(yy, 0), static_cast<int>(P.atlasHeight) - 1);
-        return __ldg(P.atlas + static_cast<size_t>(yy) * P.atlasWidth + xx);
-    };
-    const float a = fetch(ix, iy) + (fetch(ix + 1, iy) - fetch(ix, iy)) * tx;
-    const float b = fetch(ix, iy + 1) + (fetch(ix + 1, iy + 1) - fetch(ix, iy + 1)) * tx;
-    return a + (b - a) * ty;
-}
-
-__device__ __forceinline__ float round_to_half(float v) { return __half2float(__float2half_rn(v)); }
-
-struct PixelState
-{
-    uint32_t color;    // RGBA8 premultiplied: the colour plane IS 8-bit in the reference
-    float clipCoverage;
-    uint32_t clipID;
-};
-
-// Paint lookup (draw_path.vert:188-362 + find_paint_color :431-506), evaluated
-// at the pixel centre instead of interpolated from vertices (the varyings are
-// affine in position, so this is the same function).
-__device__ float4 paint_color(const FlushParams& P, uint32_t pathID, uint2 paint, float fragX, float fragY)
-{
-    const uint32_t paintType = paint.x & 0xfu;
-    float4 color;
-    if (paintType == kPaintTypeSolid)
-    {
-        color = unpack_rgba8(paint.y);
-    }
-    else
-    {
-        const float4 pm = __ldg(P.paintAuxBuffer + pathID * 8u);
-        const float4 pt = __ldg(P.paintAuxBuffer + pathID * 8u + 1u);
-        const float cx = pm.x * fragX + pm.z * fragY + pt.x;
-        const float cy = pm.y * fragX + pm.w * fragY + pt.y;
-        float t = paintType == kPaintTypeLinear ? cx : sqrtf(cx * cx + cy * cy);
-        t = clamp01(t);
-        const float x = pt.z > .9f ? (1.f - 1.f / 512.f) * t + (.5f / 512.f) : (1.f / 512.f) * t + pt.w;
-        color = sample_grad(P, x, __uint_as_float(paint.y));
-    }
-    return color; // unpremultiplied
-}
-
-// Resolve one path at one pixel (draw_raster_order_path.frag:61-232).
-__device__ void resolve_path(const FlushParams& P, uint32_t meta, float coverageCount, int px, int py, PixelState& s)
-{
-    const uint32_t pathID = meta & 0xffffu;
-    const uint2 paint = __ldg(P.paintBuffer + pathID);
-    float coverage;
-    if ((meta & kMetaClockwiseFill) != 0u)
-    {
-        coverage = clamp01(coverageCount);
-    }
-    else
-    {
-        coverage = fabsf(coverageCount);
-        if ((paint.x & kPaintFlagEvenOdd) != 0u)
-            coverage = 1.f - fabsf(fractf(coverage * .5f) * 2.f + -1.f);
-        coverage = fminf(coverage, 1.f);
-    }
-    const uint32_t paintType = paint.x & 0xfu;
-    if (paintType == kPaintTypeClipUpdate)
-    {
-        const uint32_t clipID = paint.y >> 16;
-        const uint32_t outerClipID = paint.x >> 16;
-        if (outerClipID != 0u)
-        {
-            const float outerCoverage = s.clipID == outerClipID ? s.clipCoverage : 0.f;
-            coverage = fminf(coverage, outerCoverage);
-        }
-        s.clipCoverage = round_to_half(coverage); // the clip plane stores fp16
-        s.clipID = clipID;
-        return;
-    }
-    const uint32_t clipID = paint.x >> 16;
-    if (clipID != 0u)
-        coverage = s.clipID == clipID ? fminf(s.clipCoverage, coverage) : 0.f;
-    const float fragX = px + .5f, fragY = py + .5f;
-    if ((paint.x & kPaintFlagClipRect) != 0u)
-    {
-        const float4 m = __ldg(P.paintAuxBuffer + pathID * 8u + 2u);
-        const float4 tr = __ldg(P.paintAuxBuffer + pathID * 8u + 3u);
-        const float wx = fabsf(m.x) + fabsf(m.z), wy = fabsf(m.y) + fabsf(m.w);
-        float d;
-        if (wx != 0.f && wy != 0.f)
-        {
-            const float rx = 1.f / wx, ry = 1.f / wy;
-            const float cx = m.x * fragX + m.z * fragY + tr.x, cy = m.y * fragX + m.w * fragY + tr.y;
-            d = fminf(fminf(cx * rx + rx + .5f, cy * ry + ry + .5f), fminf(-cx * rx + rx + .5f, -cy * ry + ry + .5f));
-        }
-        else
-        {
-            d = fminf(tr.x, tr.y);
-        }
-        coverage = clampf(d, 0.f, coverage);
-    }
-    float4 color = paint_color(P, pathID, paint, fragX, fragY);
-    const float4 dst = unpack_rgba8(s.color);
-    const uint32_t blendMode = (paint.x >> 4) & 0xfu;
-    float3 rgb = make_float3(color.x, color.y, color.z);
-    if (blendMode != 0u)
-        rgb = advanced_color_blend(rgb, dst, blendMode);
-    const float a = color.w * coverage;
-    const float oneMinusA = 1.f - a;
-    float r = rgb.x * a + dst.x * oneMinusA;
-    float g = rgb.y * a + dst.y * oneMinusA;
-    float b = rgb.z * a + dst.z * oneMinusA;
-    const float outA = a + dst.w * oneMinusA;
-    if (a != 0.f && P.ditherScale != 0.f)
-    {
-        const float v1 = fractf(0.06711056f * fragX + 0.00583715f * fragY);
-        const float dither = fractf(52.9829189f * v1) * P.ditherScale + P.ditherBias;
-        r += dither;
-        g += dither;
-        b += dither;
-    }
-    s.color = pack_rgba8(r, g, b, outA);
-}
-
-// Immediate-mode blend for atlas blits (draw_mesh.frag, @FEATHER_ATLAS_BLIT).
-__device__ void resolve_atlas_blit(const FlushParams& P, uint32_t meta, float u, float v, int px, int py, PixelState& s)
-{
-    const uint32_t pathID = meta & 0xffffu;
-    const uint2 paint = __ldg(P.paintBuffer + pathID);
-    float coverage = clamp01(sample_atlas(P, u, v));
-    const float fragX = px + .5f, fragY = py + .5f;
-    if ((paint.x & kPaintFlagClipRect) != 0u)
-    {
-        const float4 m = __ldg(P.paintAuxBuffer + pathID * 8u + 2u);
-        const float4 tr = __ldg(P.paintAuxBuffer + pathID * 8u + 3u);
-        const float wx = fabsf(m.x) + fabsf(m.z), wy = fabsf(m.y) + fabsf(m.w);
-        float d;
-        if (wx != 0.f && wy != 0.f)
-        {
-            const float rx = 1.f / wx, ry = 1.f / wy;
-            const float cx = m.x * fragX + m.z * fragY + tr.x, cy = m.y * fragX + m.w * fragY + tr.y;
-            d = fminf(fminf(cx * rx + rx + .5f, cy * ry + ry + .5f), fminf(-cx * rx + rx + .5f, -cy * ry + ry + .5f));
-        }
-        else
-        {
-            d = fminf(tr.x, tr.y);
-        }
-        coverage = fminf(fmaxf(d, 0.f), coverage);
-    }
-    const uint32_t clipID = paint.x >> 16;
-    if (clipID != 0u)
-        coverage = fminf(coverage, fmaxf(s.clipID == clipID ? s.clipCoverage : 0.f, 0.f));
-    float4 color = paint_color(P, pathID, paint, fragX, fragY);
-    const float4 dst = unpack_rgba8(s.color);
-    const uint32_t blendMode = (paint.x >> 4) & 0xfu;
-    float3 rgb = make_float3(color.x, color.y, color.z);
-    if (blendMode != 0u)
-        rgb = advanced_color_blend(rgb, dst, blendMode);
-    const float a = color.w * coverage;
-    float r = rgb.x * a, g = rgb.y * a, b = rgb.z * a;
-    if (a != 0.f && P.ditherScale != 0.f)
-    {
-        const float v1 = fractf(0.06711056f * fragX + 0.00583715f * fragY);
-        const float dither = fractf(52.9829189f * v1) * P.ditherScale + P.ditherBias;
-        r += dither;
-        g += dither;
-        b += dither;
-    }
-    const float oneMinusA = 1.f - a;
-    s.color = pack_rgba8(dst.x * oneMinusA + r, dst.y * oneMinusA + g, dst.z * oneMinusA + b, dst.w * oneMinusA + a);
-}
-
-__global__ void __launch_bounds__(256) raster_tiles_kernel(FlushParams P,
-                                                           const TriGeom* __restrict__ triGeom,
-                                                           const TriAttr* __restrict__ triAttr,
-                                                           const uint32_t* __restrict__ tileOffsets,
-                                                           const uint32_t* __restrict__ tileCounts,
-                                                           const uint32_t* __restrict__ entries)
-{
-    __shared__ __align__(16) Prepared s_prep[kRasterChunk];
-    const uint32_t tile = blockIdx.x;
-    const int tileX = static_cast<int>(tile % P.tilesX) + P.tileX0, tileY = static_cast<int>(tile / P.tilesX) + P.tileY0;
-    const int originX = tileX << kTileSizeLog2, originY = tileY << kTileSizeLog2;
-    // Each warp owns an 8x4 pixel block of the 16x16 tile.
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int wx0 = (warp & 1) * 8, wy0 = (warp >> 1) * 4;
-    const int i = wx0 + (lane & 7), j = wy0 + (lane >> 3);
-    const int px = originX + i, py = originY + j;
-    const bool inBounds = px >= P.boundsL && px < P.boundsR && py >= P.boundsT && py < P.boundsB;
-
-    PixelState s;
-    s.clipCoverage = 0.f;
-    s.clipID = 0u;
-    if (P.loadAction == RIVECUDA_LOAD_CLEAR)
-        s.color = P.clearColorPremulRGBA;
-    else
-        s.color = inBounds ? P.target[static_cast<size_t>(py) * P.targetWidth + px] : 0u;
-
-    const uint32_t n = tileCounts[tile];
-    const uint32_t* list = entries + tileOffsets[tile];
-
-    uint32_t curMeta = 0u; // meta of the path being accumulated (0 = none)
-    float coverageCount = 0.f;
-    bool touched = false;
-
-    for (uint32_t base = 0; base < n; base += kRasterChunk)
-    {
-        const uint32_t chunk = min(static_cast<uint32_t>(kRasterChunk), n - base);
-        __syncthreads(); // previous chunk fully consumed
-        if (threadIdx.x < chunk)
-        {
-            const uint32_t t = __ldg(list + base + threadIdx.x);
-            TriGeom g;
-            const uint4* src = reinterpret_cast<const uint4*>(triGeom + t);
-            *reinterpret_cast<uint4*>(&g) = __ldg(src);
-            *(reinterpret_cast<uint4*>(&g) + 1) = __ldg(src + 1);
-            prepare_triangle(g, triAttr + t, originX, originY, s_prep[threadIdx.x]);
-        }
-        __syncthreads();
-        for (uint32_t k = 0; k < chunk; ++k)
-        {
-            const Prepared& T = s_prep[k];
-            const uint32_t meta = T.meta;
-            if (meta == 0u)
-                continue;
-            const uint32_t kind = (meta >> kMetaKindShift) & 0xf;
-            // Path boundary: resolve what has been accumulated.
-            if ((meta & 0xffffu) != (curMeta & 0xffffu) || kind >= kKindAtlasBlit)
-            {
-                if (touched)
-                    resolve_path(P, curMeta, coverageCount, px, py, s);
-                curMeta = kind >= kKindAtlasBlit ? 0u : meta;
-                coverageCount = 0.f;
-                touched = false;
-            }
-            // Warp-level reject against the triangle's tile-local bounds.
-            const uint32_t bb = T.bbox;
-            const int bx0 = bb & 15, bx1 = (bb >> 4) & 15, by0 = (bb >> 8) & 15, by1 = (bb >> 12) & 15;
-            if (bx0 > wx0 + 7 || bx1 < wx0 || by0 > wy0 + 3 || by1 < wy0)
-                continue;
-            const int e0 = T.q0 + T.A0 * i + T.B0 * j;
-            const int e1 = T.q1 + T.A1 * i + T.B1 * j;
-            const int e2 = T.q2 + T.A2 * i + T.B2 * j;
-            if ((e0 | e1 | e2) < 0)
-                continue;
-            const float fi = static_cast<float>(i), fj = static_cast<float>(j);
-            const float c0 = T.plane[0][0] + T.plane[0][1] * fi + T.plane[0][2] * fj;
-            switch (kind)
-            {
-                case kKindFill:
-                    coverageCount += c0;
-                    touched = true;
-                    break;
-                case kKindStroke:
-                {
-                    const float c1 = T.plane[1][0] + T.plane[1][1] * fi + T.plane[1][2] * fj;
-                    coverageCount = fmaxf(coverageCount, fminf(c0, c1));
-                    touched = true;
-                    break;
-                }
-                case kKindFeatherFill:
-                {
-                    const float c1 = T.plane[1][0] + T.plane[1][1] * fi + T.plane[1][2] * fj;
-                    const float c2 = T.plane[2][0] + T.plane[2][1] * fi + T.plane[2][2] * fj;
-                    const float c3 = T.plane[3][0] + T.plane[3][1] * fi + T.plane[3][2] * fj;
-                    coverageCount += eval_feathered_fill(P.featherLUT, make_float4(c0, c1, c2, c3));
-                    touched = true;
-                    break;
-                }
-                case kKindFeatherStroke:
-                {
-                    const float c1 = T.plane[1][0] + T.plane[1][1] * fi + T.plane[1][2] * fj;
-                    coverageCount = fmaxf(coverageCount, eval_feathered_stroke(P.featherLUT, c0, c1));
-                    touched = true;
-                    break;
-                }
-                case kKindAtlasBlit:
-                {
-                    const float c1 = T.plane[1][0] + T.plane[1][1] * fi + T.plane[1][2] * fj;
-                    resolve_atlas_blit(P, meta, c0, c1, px, py, s);
-                    break;
-                }
-                default:
-                    break;
-            }
-        }
-    }
-    if (touched)
-        resolve_path(P, curMeta, coverageCount, px, py, s);
-    if (inBounds)
-        P.target[static_cast<size_t>(py) * P.targetWidth + px] = s.color;
-}
-
-// Tiles with no triangles only need the clear colour.
-// (Handled by raster_tiles_kernel itself: n == 0 => store of the clear colour.)
+#include "raster_tiles.cuh"
 
 // ---------------------------------------------------------------------------
 // Host orchestration

@@ -1,0 +1,629 @@
+/*
+ * raster_tiles.cuh -- K5, the tile rasteriser (included by kernels_draw.cu).
+ *
+ * One CTA (8 warps) per 16x16 tile; each warp owns an 8x4 pixel block and each
+ * lane one pixel, whose colour (RGBA8, as in the reference's colour plane),
+ * clip and coverage state stay in registers for the whole flush.
+ *
+ * The tile's triangle list (sorted into API order) is consumed in chunks of 256:
+ *   prepare   thread k turns triangle k into its exact tile-local form in shared
+ *             memory: three int32 edge functions q + A*i + B*j >= 0 (derived in
+ *             int64 from the 8-bit sub-pixel snapped vertices, top-left rule
+ *             folded into q), attribute planes from exact barycentrics, the
+ *             path's paint record, and two 8-bit masks saying which of the eight
+ *             warp blocks the triangle can touch / fully covers.
+ *   raster    each warp walks ONLY the triangles whose mask names its block
+ *             (warp ballot + find-first-set over the masks), independently of
+ *             the other warps: a path boundary is a per-warp event. Fully
+ *             covered blocks skip the edge tests; partially covered ones
+ *             evaluate the three edge functions per lane with integer FMAs.
+ * A path's coverage is accumulated over all of its triangles and resolved once
+ * per pixel when the warp meets the next path (draw_raster_order_path.frag's
+ * per-fragment read-modify-write collapses to one blend per path per pixel).
+ */
+#pragma once
+
+struct Prepared // 28 words (112 B), one per (triangle, tile), in shared memory
+{
+    int32_t A0, B0, q0, A1, B1, q1, A2, B2, q2; // words 0-8
+    float plane[4][3];                            // words 9-20: P0, Px, Py per component
+    uint32_t meta;                                // word 21: TriGeom::meta (0 => skip)
+    uint32_t masks;                               // word 22: blockMask | fullMask << 8 | flat << 16
+    uint32_t aux;                                 // word 23
+    uint32_t paintX, paintY;                      // words 24-25: PaintData of the path
+    uint32_t pad0, pad1;
+};
+static_assert(sizeof(Prepared) == 112, "Prepared");
+
+constexpr int kRasterChunk = 256;
+constexpr uint32_t kMaskFlat = 1u << 16;
+
+// Builds the tile-local form of one triangle. Exact for edges whose Manhattan
+// length is below 2^17 px; longer edges are scaled (approximate).
+__device__ void prepare_triangle(const FlushParams& P,
+                                 const TriGeom& g,
+                                 const TriAttr* __restrict__ attrPtr,
+                                 int originX,
+                                 int originY,
+                                 Prepared& out)
+{
+    out.meta = 0;
+    out.masks = 0;
+    out.aux = g.aux;
+    if ((g.meta & kMetaValid) == 0u)
+        return;
+    const int32_t X[3] = {g.x0, g.x1, g.x2}, Y[3] = {g.y0, g.y1, g.y2};
+    const int64_t px0 = (static_cast<int64_t>(originX) << 8) + 128, py0 = (static_cast<int64_t>(originY) << 8) + 128;
+    int64_t A[3], B[3], E0u[3];
+    int32_t Ai[3], Bi[3], qi[3];
+    bool reject = false;
+#pragma unroll
+    for (int e = 0; e < 3; ++e)
+    {
+        const int a = (e + 1) % 3, b = (e + 2) % 3;
+        const int64_t dx = static_cast<int64_t>(X[b]) - X[a], dy = static_cast<int64_t>(Y[b]) - Y[a];
+        const bool topLeft = (dy == 0 && dx > 0) || (dy < 0);
+        A[e] = -dy;
+        B[e] = dx;
+        const int64_t C = dy * X[a] - dx * Y[a];
+        E0u[e] = A[e] * px0 + B[e] * py0 + C;
+        // E(i,j) - bias = E0u - bias + 256*(A*i + B*j) >= 0  <=>  q + A*i + B*j >= 0
+        const int64_t q = (E0u[e] - (topLeft ? 0 : 1)) >> 8;
+        const int64_t n = kTileSize - 1;
+        const int64_t emin = q + n * (A[e] < 0 ? A[e] : 0) + n * (B[e] < 0 ? B[e] : 0);
+        const int64_t emax = q + n * (A[e] > 0 ? A[e] : 0) + n * (B[e] > 0 ? B[e] : 0);
+        if (emax < 0)
+            reject = true;
+        if (emin >= 0)
+        {
+            Ai[e] = Bi[e] = qi[e] = 0; // true for every pixel of the tile
+        }
+        else
+        {
+            int64_t a64 = A[e], b64 = B[e], q64 = q;
+            while ((a64 < 0 ? -a64 : a64) + (b64 < 0 ? -b64 : b64) >= (1ll << 25))
+            {
+                a64 >>= 1;
+                b64 >>= 1;
+                q64 >>= 1;
+            }
+            Ai[e] = static_cast<int32_t>(a64);
+            Bi[e] = static_cast<int32_t>(b64);
+            qi[e] = static_cast<int32_t>(q64);
+        }
+    }
+    if (reject)
+        return;
+    // Tile-local bounds of the pixel centres the triangle's bbox can cover.
+    const int32_t minX = min(X[0], min(X[1], X[2])), maxX = max(X[0], max(X[1], X[2]));
+    const int32_t minY = min(Y[0], min(Y[1], Y[2])), maxY = max(Y[0], max(Y[1], Y[2]));
+    const int bx0 = max(((minX - 128 + 255) >> 8) - originX, 0), bx1 = min(((maxX - 128) >> 8) - originX, kTileSize - 1);
+    const int by0 = max(((minY - 128 + 255) >> 8) - originY, 0), by1 = min(((maxY - 128) >> 8) - originY, kTileSize - 1);
+    if (bx0 > bx1 || by0 > by1)
+        return;
+    // Classify the eight 8x4 warp blocks (block w: x0 = (w&1)*8, y0 = (w>>1)*4).
+    uint32_t blockMask = 0, fullMask = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w)
+    {
+        const int x0 = (w & 1) * 8, y0 = (w >> 1) * 4;
+        if (bx0 > x0 + 7 || bx1 < x0 || by0 > y0 + 3 || by1 < y0)
+            continue;
+        bool any = true, all = true;
+#pragma unroll
+        for (int e = 0; e < 3; ++e)
+        {
+            const int lo = qi[e] + Ai[e] * (Ai[e] < 0 ? x0 + 7 : x0) + Bi[e] * (Bi[e] < 0 ? y0 + 3 : y0);
+            const int hi = qi[e] + Ai[e] * (Ai[e] < 0 ? x0 : x0 + 7) + Bi[e] * (Bi[e] < 0 ? y0 : y0 + 3);
+            any = any && hi >= 0;
+            all = all && lo >= 0;
+        }
+        if (any)
+            blockMask |= 1u << w;
+        if (all)
+            fullMask |= 1u << w;
+    }
+    if (blockMask == 0u)
+        return;
+    out.A0 = Ai[0];
+    out.B0 = Bi[0];
+    out.q0 = qi[0];
+    out.A1 = Ai[1];
+    out.B1 = Bi[1];
+    out.q1 = qi[1];
+    out.A2 = Ai[2];
+    out.B2 = Bi[2];
+    out.q2 = qi[2];
+    out.meta = g.meta;
+    // Attribute planes from exact barycentrics at tile pixel (0,0):
+    //   attr(i,j) = sum_k c_k * (E0u_k + 256*(A_k*i + B_k*j)) / area2
+    const double area2 = static_cast<double>(E0u[0] + E0u[1] + E0u[2]);
+    const double inv = 1.0 / area2;
+    const uint32_t kind = (g.meta >> kMetaKindShift) & 0xf;
+    const int comps = kind == kKindFill ? 1 : (kind == kKindFeatherFill ? 4 : 2);
+    const float* attr = attrPtr->attr;
+    bool flat = kind == kKindFill;
+    for (int c = 0; c < comps; ++c)
+    {
+        const float f0 = attr[c * 3 + 0], f1 = attr[c * 3 + 1], f2 = attr[c * 3 + 2];
+        if (c == 0 && flat && f0 == f1 && f1 == f2)
+        {
+            // Constant coverage (fan / interior triangles): exact, no gradient.
+            out.plane[0][0] = f0;
+            out.plane[0][1] = 0.f;
+            out.plane[0][2] = 0.f;
+            continue;
+        }
+        flat = false;
+        const double c0 = f0, c1 = f1, c2 = f2;
+        out.plane[c][0] = static_cast<float>((c0 * static_cast<double>(E0u[0]) + c1 * static_cast<double>(E0u[1]) + c2 * static_cast<double>(E0u[2])) * inv);
+        out.plane[c][1] = static_cast<float>((c0 * static_cast<double>(A[0]) + c1 * static_cast<double>(A[1]) + c2 * static_cast<double>(A[2])) * 256.0 * inv);
+        out.plane[c][2] = static_cast<float>((c0 * static_cast<double>(B[0]) + c1 * static_cast<double>(B[1]) + c2 * static_cast<double>(B[2])) * 256.0 * inv);
+    }
+    out.masks = blockMask | (fullMask << 8) | (flat ? kMaskFlat : 0u);
+    const uint2 paint = __ldg(P.paintBuffer + (g.meta & 0xffffu));
+    out.paintX = paint.x;
+    out.paintY = paint.y;
+}
+
+// draw_path_common.glsl:153-258
+__device__ float eval_feathered_fill(const float* __restrict__ lut, float4 cov)
+{
+    const float cotTheta = cov.z;
+    const float y0 = fmaxf(cov.w, 0.f);
+    float featherCoverage = cotTheta >= 0.f ? feather_lut(lut, y0) : 0.f;
+    if (fabsf(cotTheta) < kHorizontalCotangentThreshold)
+    {
+        const float x = fabsf(cov.x) - kFeatherXCoordBias;
+        const float y = -cov.y + kFeatherCoverageBias;
+        const float dt = (y - y0) * 0.5984134206f;
+        const float k[4] = {0.20888568955f, 0.62665706865f, 1.04442844776f, 1.46219982687f};
+        float sum = 0.f;
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+        {
+            const float t = y0 + dt * k[i];
+            const float u = t * -cotTheta + (y * cotTheta + x);
+            const float t_ = t * 5.09593080173f + -2.54796540086f;
+            sum += feather_lut(lut, u) * exp2f(-t_ * t_);
+        }
+        featherCoverage += sum * dt;
+    }
+    return featherCoverage * signf(cov.x);
+}
+
+__device__ __forceinline__ float eval_feathered_stroke(const float* __restrict__ lut, float cx, float cy)
+{
+    float c = 1.f;
+    c -= feather_lut(lut, (1.f - kFeatherCoverageBias) + cx);
+    c -= feather_lut(lut, 1.f - cy);
+    return c;
+}
+
+// ---- advanced_blend.glsl:91-330 ----
+
+__device__ __forceinline__ float lum(float3 c) { return c.x * .30f + c.y * .59f + c.z * .11f; }
+__device__ __forceinline__ float min3f(float3 c) { return fminf(fminf(c.x, c.y), c.z); }
+__device__ __forceinline__ float max3f(float3 c) { return fmaxf(fmaxf(c.x, c.y), c.z); }
+
+__device__ float3 set_lum(float3 base, float3 lumColor)
+{
+    const float lumTarget = lum(lumColor);
+    const float lb = lum(base);
+    const float3 biased = make_float3(base.x - lb, base.y - lb, base.z - lb);
+    const float s0 = lumTarget / fmaxf(kEpsilonFP16, -min3f(biased));
+    const float s1 = (1.f - lumTarget) / fmaxf(kEpsilonFP16, max3f(biased));
+    const float satScale = fminf(1.f, fminf(s0, s1));
+    return make_float3(biased.x * satScale + lumTarget, biased.y * satScale + lumTarget, biased.z * satScale + lumTarget);
+}
+
+__device__ float3 set_lum_sat(float3 hueColor, float3 satColor, float3 lumColor)
+{
+    const float satTarget = max3f(satColor) - min3f(satColor);
+    const float mn = min3f(hueColor);
+    hueColor = make_float3(hueColor.x - mn, hueColor.y - mn, hueColor.z - mn);
+    const float scale = satTarget / fmaxf(kEpsilonFP16, max3f(hueColor));
+    return set_lum(make_float3(hueColor.x * scale, hueColor.y * scale, hueColor.z * scale), lumColor);
+}
+
+__device__ __forceinline__ float clamp01(float v) { return clampf(v, 0.f, 1.f); }
+
+__device__ float blend_channel(uint32_t mode, float s, float d, float dPremul, float dA)
+{
+    switch (mode)
+    {
+        case 11: // multiply
+            return s * d;
+        case 1: // screen
+            return s + d - s * d;
+        case 2: // overlay
+        {
+            const float sd = s * d;
+            return 2.f * (d > .5f ? s + d - sd - .5f : sd);
+        }
+        case 3:
+            return fminf(s, d);
+        case 4:
+            return fmaxf(s, d);
+        case 5: // colordodge
+        {
+            const float dp = clampf(dPremul, 0.f, dA);
+            const float denom = clamp01(1.f - s) * dA;
+            return denom == 0.f ? signf(dp) : fminf(1.f, dp / denom);
+        }
+        case 6: // colorburn
+        {
+            const float sc = clamp01(s);
+            const float dp = clampf(dPremul, 0.f, dA);
+            const float da = dA == 0.f ? 1.f : dA;
+            const float numer = da - dp;
+            return 1.f - (sc == 0.f ? signf(numer) : fminf(1.f, numer / (sc * da)));
+        }
+        case 7: // hardlight
+        {
+            const float sd = s * d;
+            return 2.f * (s > .5f ? s + d - sd - .5f : sd);
+        }
+        case 8: // softlight
+        {
+            float k;
+            if (s <= .5f)
+                k = 1.f - d;
+            else if (d <= .25f)
+                k = (16.f * d - 12.f) * d + 3.f;
+            else
+                k = 1.f / sqrtf(d) - 1.f;
+            return d + d * (2.f * s - 1.f) * k;
+        }
+        case 9:
+            return fabsf(d - s);
+        case 10:
+            return s + d - 2.f * s * d;
+        default:
+            return 0.f;
+    }
+}
+
+__device__ float3 advanced_color_blend(float3 src, float4 dstPremul, uint32_t mode)
+{
+    const float invA = dstPremul.w != 0.f ? 1.f / dstPremul.w : 0.f;
+    const float3 dst = make_float3(dstPremul.x * invA, dstPremul.y * invA, dstPremul.z * invA);
+    float3 coeffs;
+    if (mode >= 12)
+    {
+        const float3 sc = make_float3(clamp01(src.x), clamp01(src.y), clamp01(src.z));
+        switch (mode)
+        {
+            case 12:
+                coeffs = set_lum_sat(sc, dst, dst);
+                break;
+            case 13:
+                coeffs = set_lum_sat(dst, sc, dst);
+                break;
+            case 14:
+                coeffs = set_lum(sc, dst);
+                break;
+            default:
+                coeffs = set_lum(dst, sc);
+                break;
+        }
+    }
+    else
+    {
+        coeffs.x = blend_channel(mode, src.x, dst.x, dstPremul.x, dstPremul.w);
+        coeffs.y = blend_channel(mode, src.y, dst.y, dstPremul.y, dstPremul.w);
+        coeffs.z = blend_channel(mode, src.z, dst.z, dstPremul.z, dstPremul.w);
+    }
+    const float a = dstPremul.w;
+    return make_float3(src.x * (1.f - a) + coeffs.x * a, src.y * (1.f - a) + coeffs.y * a, src.z * (1.f - a) + coeffs.z * a);
+}
+
+__device__ __forceinline__ float4 fetch_grad(const FlushParams& P, int x, int y)
+{
+    x = min(max(x, 0), kGradWidth - 1);
+    y = min(max(y, 0), static_cast<int>(P.gradHeight) - 1);
+    return unpack_rgba8(__ldg(P.gradTexture + y * kGradWidth + x));
+}
+
+__device__ float4 sample_grad(const FlushParams& P, float u, float v)
+{
+    const float x = u * 512.f - .5f, y = v * static_cast<float>(P.gradHeight) - .5f;
+    const float fx = floorf(x), fy = floorf(y);
+    const float tx = x - fx, ty = y - fy;
+    const int ix = static_cast<int>(clampf(fx, -1.f, 512.f)), iy = static_cast<int>(clampf(fy, -1.f, 65536.f));
+    const float4 c00 = fetch_grad(P, ix, iy), c10 = fetch_grad(P, ix + 1, iy);
+    const float4 c01 = fetch_grad(P, ix, iy + 1), c11 = fetch_grad(P, ix + 1, iy + 1);
+    float4 top = make_float4(c00.x + (c10.x - c00.x) * tx, c00.y + (c10.y - c00.y) * tx, c00.z + (c10.z - c00.z) * tx, c00.w + (c10.w - c00.w) * tx);
+    float4 bot = make_float4(c01.x + (c11.x - c01.x) * tx, c01.y + (c11.y - c01.y) * tx, c01.z + (c11.z - c01.z) * tx, c01.w + (c11.w - c01.w) * tx);
+    return make_float4(top.x + (bot.x - top.x) * ty, top.y + (bot.y - top.y) * ty, top.z + (bot.z - top.z) * ty, top.w + (bot.w - top.w) * ty);
+}
+
+__device__ float sample_atlas(const FlushParams& P, float u, float v)
+{
+    const float x = u * P.atlasWidth - .5f, y = v * P.atlasHeight - .5f;
+    const float fx = floorf(x), fy = floorf(y);
+    const float tx = x - fx, ty = y - fy;
+    const int ix = static_cast<int>(clampf(fx, -1.f, 65536.f)), iy = static_cast<int>(clampf(fy, -1.f, 65536.f));
+    auto fetch = [&](int xx, int yy) {
+        xx = min(max(xx, 0), static_cast<int>(P.atlasWidth) - 1);
+        yy = min(max(yy, 0), static_cast<int>(P.atlasHeight) - 1);
+        return __ldg(P.atlas + static_cast<size_t>(yy) * P.atlasWidth + xx);
+    };
+    const float a = fetch(ix, iy) + (fetch(ix + 1, iy) - fetch(ix, iy)) * tx;
+    const float b = fetch(ix, iy + 1) + (fetch(ix + 1, iy + 1) - fetch(ix, iy + 1)) * tx;
+    return a + (b - a) * ty;
+}
+
+__device__ __forceinline__ float round_to_half(float v) { return __half2float(__float2half_rn(v)); }
+
+struct PixelState
+{
+    uint32_t color; // RGBA8 premultiplied: the colour plane IS 8-bit in the reference
+    float clipCoverage;
+    uint32_t clipID;
+    float dither;   // interleaved gradient noise at this pixel (common.glsl:269-275), 0 if off
+};
+
+__device__ __forceinline__ uint32_t pack_rgba8_fast(float r, float g, float b, float a)
+{
+    // floor(sat(v)*255 + .5), as a UNORM8 store does.
+    const uint32_t ur = static_cast<uint32_t>(__saturatef(r) * 255.f + .5f);
+    const uint32_t ug = static_cast<uint32_t>(__saturatef(g) * 255.f + .5f);
+    const uint32_t ub = static_cast<uint32_t>(__saturatef(b) * 255.f + .5f);
+    const uint32_t ua = static_cast<uint32_t>(__saturatef(a) * 255.f + .5f);
+    return ur | (ug << 8) | (ub << 16) | (ua << 24);
+}
+
+// clip-rect coverage (common.glsl:376-400 + draw_raster_order_path.frag:149-156)
+__device__ float clip_rect_coverage(const FlushParams& P, uint32_t pathID, float fragX, float fragY)
+{
+    const float4 m = __ldg(P.paintAuxBuffer + pathID * 8u + 2u);
+    const float4 tr = __ldg(P.paintAuxBuffer + pathID * 8u + 3u);
+    const float wx = fabsf(m.x) + fabsf(m.z), wy = fabsf(m.y) + fabsf(m.w);
+    if (wx != 0.f && wy != 0.f)
+    {
+        const float rx = 1.f / wx, ry = 1.f / wy;
+        const float cx = m.x * fragX + m.z * fragY + tr.x, cy = m.y * fragX + m.w * fragY + tr.y;
+        return fminf(fminf(cx * rx + rx + .5f, cy * ry + ry + .5f), fminf(-cx * rx + rx + .5f, -cy * ry + ry + .5f));
+    }
+    return fminf(tr.x, tr.y);
+}
+
+// Unpremultiplied paint colour at the pixel centre (draw_path.vert:188-362 +
+// find_paint_color :431-506; the varyings are affine in position, so evaluating
+// at the pixel is the same function as interpolating them).
+__device__ __forceinline__ float4 paint_color(const FlushParams& P, uint32_t pathID, uint32_t paintX, uint32_t paintY, float fragX, float fragY)
+{
+    const uint32_t paintType = paintX & 0xfu;
+    if (paintType == kPaintTypeSolid)
+        return unpack_rgba8(paintY);
+    const float4 pm = __ldg(P.paintAuxBuffer + pathID * 8u);
+    const float4 pt = __ldg(P.paintAuxBuffer + pathID * 8u + 1u);
+    const float cx = pm.x * fragX + pm.z * fragY + pt.x;
+    const float cy = pm.y * fragX + pm.w * fragY + pt.y;
+    float t = paintType == kPaintTypeLinear ? cx : sqrtf(cx * cx + cy * cy);
+    t = clamp01(t);
+    const float x = pt.z > .9f ? (1.f - 1.f / 512.f) * t + (.5f / 512.f) : (1.f / 512.f) * t + pt.w;
+    return sample_grad(P, x, __uint_as_float(paintY));
+}
+
+// Resolve one path at one pixel (draw_raster_order_path.frag:61-232).
+__device__ __forceinline__ void resolve_path(const FlushParams& P,
+                                             uint32_t meta,
+                                             uint32_t paintX,
+                                             uint32_t paintY,
+                                             float coverageCount,
+                                             int px,
+                                             int py,
+                                             PixelState& s)
+{
+    const uint32_t pathID = meta & 0xffffu;
+    float coverage;
+    if ((meta & kMetaClockwiseFill) != 0u)
+    {
+        coverage = clamp01(coverageCount);
+    }
+    else
+    {
+        coverage = fabsf(coverageCount);
+        if ((paintX & kPaintFlagEvenOdd) != 0u)
+            coverage = 1.f - fabsf(fractf(coverage * .5f) * 2.f + -1.f);
+        coverage = fminf(coverage, 1.f);
+    }
+    const uint32_t paintType = paintX & 0xfu;
+    if (paintType == kPaintTypeClipUpdate)
+    {
+        const uint32_t clipID = paintY >> 16;
+        const uint32_t outerClipID = paintX >> 16;
+        if (outerClipID != 0u)
+        {
+            const float outerCoverage = s.clipID == outerClipID ? s.clipCoverage : 0.f;
+            coverage = fminf(coverage, outerCoverage);
+        }
+        s.clipCoverage = round_to_half(coverage); // the clip plane stores fp16
+        s.clipID = clipID;
+        return;
+    }
+    const uint32_t clipID = paintX >> 16;
+    if (clipID != 0u)
+        coverage = s.clipID == clipID ? fminf(s.clipCoverage, coverage) : 0.f;
+    const float fragX = px + .5f, fragY = py + .5f;
+    if ((paintX & kPaintFlagClipRect) != 0u)
+        coverage = clampf(clip_rect_coverage(P, pathID, fragX, fragY), 0.f, coverage);
+    const float4 color = paint_color(P, pathID, paintX, paintY, fragX, fragY);
+    const float4 dst = unpack_rgba8(s.color);
+    const uint32_t blendMode = (paintX >> 4) & 0xfu;
+    float3 rgb = make_float3(color.x, color.y, color.z);
+    if (blendMode != 0u)
+        rgb = advanced_color_blend(rgb, dst, blendMode);
+    const float a = color.w * coverage;
+    const float oneMinusA = 1.f - a;
+    const float dither = a != 0.f ? s.dither : 0.f;
+    const float r = rgb.x * a + dst.x * oneMinusA + dither;
+    const float g = rgb.y * a + dst.y * oneMinusA + dither;
+    const float b = rgb.z * a + dst.z * oneMinusA + dither;
+    const float outA = a + dst.w * oneMinusA;
+    s.color = pack_rgba8_fast(r, g, b, outA);
+}
+
+// Immediate-mode blend for atlas blits (draw_mesh.frag, @FEATHER_ATLAS_BLIT).
+__device__ void resolve_atlas_blit(const FlushParams& P, uint32_t meta, uint32_t paintX, uint32_t paintY, float u, float v, int px, int py, PixelState& s)
+{
+    const uint32_t pathID = meta & 0xffffu;
+    float coverage = clamp01(sample_atlas(P, u, v));
+    const float fragX = px + .5f, fragY = py + .5f;
+    if ((paintX & kPaintFlagClipRect) != 0u)
+        coverage = fminf(fmaxf(clip_rect_coverage(P, pathID, fragX, fragY), 0.f), coverage);
+    const uint32_t clipID = paintX >> 16;
+    if (clipID != 0u)
+        coverage = fminf(coverage, fmaxf(s.clipID == clipID ? s.clipCoverage : 0.f, 0.f));
+    const float4 color = paint_color(P, pathID, paintX, paintY, fragX, fragY);
+    const float4 dst = unpack_rgba8(s.color);
+    const uint32_t blendMode = (paintX >> 4) & 0xfu;
+    float3 rgb = make_float3(color.x, color.y, color.z);
+    if (blendMode != 0u)
+        rgb = advanced_color_blend(rgb, dst, blendMode);
+    const float a = color.w * coverage;
+    const float dither = a != 0.f ? s.dither : 0.f;
+    const float oneMinusA = 1.f - a;
+    s.color = pack_rgba8_fast(dst.x * oneMinusA + (rgb.x * a + dither),
+                              dst.y * oneMinusA + (rgb.y * a + dither),
+                              dst.z * oneMinusA + (rgb.z * a + dither),
+                              dst.w * oneMinusA + a);
+}
+
+__global__ void __launch_bounds__(256, 4) raster_tiles_kernel(FlushParams P,
+                                                              const TriGeom* __restrict__ triGeom,
+                                                              const TriAttr* __restrict__ triAttr,
+                                                              const uint32_t* __restrict__ tileOffsets,
+                                                              const uint32_t* __restrict__ tileCounts,
+                                                              const uint32_t* __restrict__ entries)
+{
+    __shared__ __align__(16) Prepared s_prep[kRasterChunk];
+    const uint32_t tile = blockIdx.x;
+    const int tileX = static_cast<int>(tile % P.tilesX) + P.tileX0, tileY = static_cast<int>(tile / P.tilesX) + P.tileY0;
+    const int originX = tileX << kTileSizeLog2, originY = tileY << kTileSizeLog2;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int i = (warp & 1) * 8 + (lane & 7), j = (warp >> 1) * 4 + (lane >> 3);
+    const float fi = static_cast<float>(i), fj = static_cast<float>(j);
+    const int px = originX + i, py = originY + j;
+    const bool inBounds = px >= P.boundsL && px < P.boundsR && py >= P.boundsT && py < P.boundsB;
+
+    PixelState s;
+    s.clipCoverage = 0.f;
+    s.clipID = 0u;
+    s.dither = 0.f;
+    if (P.ditherScale != 0.f)
+    {
+        const float v1 = fractf(0.06711056f * (px + .5f) + 0.00583715f * (py + .5f));
+        s.dither = fractf(52.9829189f * v1) * P.ditherScale + P.ditherBias;
+    }
+    if (P.loadAction == RIVECUDA_LOAD_CLEAR)
+        s.color = P.clearColorPremulRGBA;
+    else
+        s.color = inBounds ? P.target[static_cast<size_t>(py) * P.targetWidth + px] : 0u;
+
+    const uint32_t n = tileCounts[tile];
+    const uint32_t* list = entries + tileOffsets[tile];
+
+    // Per-warp path accumulation state (the warp's pixels only).
+    uint32_t curMeta = 0u, curPaintX = 0u, curPaintY = 0u;
+    float coverageCount = 0.f;
+    bool touched = false;
+
+    for (uint32_t base = 0; base < n; base += kRasterChunk)
+    {
+        const uint32_t chunk = min(static_cast<uint32_t>(kRasterChunk), n - base);
+        __syncthreads(); // every warp is done with the previous chunk
+        uint32_t myMasks = 0u;
+        if (threadIdx.x < chunk)
+        {
+            const uint32_t t = __ldg(list + base + threadIdx.x);
+            TriGeom g;
+            const uint4* src = reinterpret_cast<const uint4*>(triGeom + t);
+            *reinterpret_cast<uint4*>(&g) = __ldg(src);
+            *(reinterpret_cast<uint4*>(&g) + 1) = __ldg(src + 1);
+            prepare_triangle(P, g, triAttr + t, originX, originY, s_prep[threadIdx.x]);
+        }
+        __syncthreads();
+        // Each warp visits only the entries whose block mask names it.
+        for (uint32_t sub = 0; sub < chunk; sub += 32)
+        {
+            const uint32_t idx = sub + lane;
+            myMasks = idx < chunk ? s_prep[idx].masks : 0u;
+            uint32_t bits = __ballot_sync(0xffffffffu, ((myMasks >> warp) & 1u) != 0u);
+            while (bits != 0u)
+            {
+                const int bit = __ffs(bits) - 1;
+                bits &= bits - 1;
+                const Prepared& T = s_prep[sub + bit];
+                const uint32_t masks = __shfl_sync(0xffffffffu, myMasks, bit);
+                const uint32_t meta = T.meta;
+                const uint32_t kind = (meta >> kMetaKindShift) & 0xf;
+                // Path boundary (per warp): resolve what has been accumulated.
+                if ((meta & 0xffffu) != (curMeta & 0xffffu) || kind >= kKindAtlasBlit)
+                {
+                    if (touched)
+                        resolve_path(P, curMeta, curPaintX, curPaintY, coverageCount, px, py, s);
+                    curMeta = kind >= kKindAtlasBlit ? 0u : meta;
+                    curPaintX = T.paintX;
+                    curPaintY = T.paintY;
+                    coverageCount = 0.f;
+                    touched = false;
+                }
+                const bool full = ((masks >> (8 + warp)) & 1u) != 0u;
+                if (full && (masks & kMaskFlat) != 0u)
+                {
+                    // Whole block inside a constant-coverage triangle.
+                    coverageCount += T.plane[0][0];
+                    touched = true;
+                    continue;
+                }
+                if (!full)
+                {
+                    const int e0 = T.q0 + T.A0 * i + T.B0 * j;
+                    const int e1 = T.q1 + T.A1 * i + T.B1 * j;
+                    const int e2 = T.q2 + T.A2 * i + T.B2 * j;
+                    if ((e0 | e1 | e2) < 0)
+                        continue;
+                }
+                const float c0 = T.plane[0][0] + T.plane[0][1] * fi + T.plane[0][2] * fj;
+                if (kind == kKindFill)
+                {
+                    coverageCount += c0;
+                    touched = true;
+                    continue;
+                }
+                const float c1 = T.plane[1][0] + T.plane[1][1] * fi + T.plane[1][2] * fj;
+                switch (kind)
+                {
+                    case kKindStroke:
+                        coverageCount = fmaxf(coverageCount, fminf(c0, c1));
+                        touched = true;
+                        break;
+                    case kKindFeatherFill:
+                    {
+                        const float c2 = T.plane[2][0] + T.plane[2][1] * fi + T.plane[2][2] * fj;
+                        const float c3 = T.plane[3][0] + T.plane[3][1] * fi + T.plane[3][2] * fj;
+                        coverageCount += eval_feathered_fill(P.featherLUT, make_float4(c0, c1, c2, c3));
+                        touched = true;
+                        break;
+                    }
+                    case kKindFeatherStroke:
+                        coverageCount = fmaxf(coverageCount, eval_feathered_stroke(P.featherLUT, c0, c1));
+                        touched = true;
+                        break;
+                    case kKindAtlasBlit:
+                        resolve_atlas_blit(P, meta, T.paintX, T.paintY, c0, c1, px, py, s);
+                        break;
+                    default:
+                        break;
+                }
+            }
+        }
+    }
+    if (touched)
+        resolve_path(P, curMeta, curPaintX, curPaintY, coverageCount, px, py, s);
+    if (inBounds)
+        P.target[static_cast<size_t>(py) * P.targetWidth + px] = s.color;
+}

@@ -74,7 +74,7 @@ def test_c2_full_size_parity_and_properties(libs):
     result = replay.ReplayResult()
     with replay.Replayer(0) as rp:
         for r in recs:
-            if r.tag in (T.CREATE, T.DESTROY, T.TARGET_READ):
+            if r.tag in (T.CREATE, T.DESTROY, T.TARGET_READ, T.TARGET_DESTROY):
                 continue
             if r.tag == T.FLUSH:
                 fr = r.fields["flush"]
