@@ -23,20 +23,25 @@
  */
 #pragma once
 
-struct Prepared // 28 words (112 B), one per (triangle, tile), in shared memory
+struct Prepared // 32 words (128 B), one per (triangle, tile), in shared memory
 {
-    int32_t A0, B0, q0, A1, B1, q1, A2, B2, q2; // words 0-8
-    float plane[4][3];                            // words 9-20: P0, Px, Py per component
-    uint32_t meta;                                // word 21: TriGeom::meta (0 => skip)
-    uint32_t masks;                               // word 22: blockMask | fullMask << 8 | flat << 16
-    uint32_t aux;                                 // word 23
-    uint32_t paintX, paintY;                      // words 24-25: PaintData of the path
+    int32_t A0, B0, q0, A1;  // words 0-3   } three int32 edge functions
+    int32_t B1, q1, A2, B2;  // words 4-7   }   e = q + A*i + B*j >= 0
+    int32_t q2;              // word 8      }
+    float plane0[3];         // words 9-11: component 0 as P0 + Px*i + Py*j
+    float plane1[3];         // words 12-14
+    uint32_t meta;           // word 15: TriGeom::meta (0 => skip)
+    float plane2[3];         // words 16-18 (feathered fills only)
+    float plane3[3];         // words 19-21
+    uint32_t aux;            // word 22
+    uint32_t masks;          // word 23: blockMask | fastMask << 8 | pathID << 16
+    float paintColor[4];     // words 24-27: solid paint colour, unpacked (unpremultiplied)
+    uint32_t paintX, paintY; // words 28-29: PaintData of the path
     uint32_t pad0, pad1;
 };
-static_assert(sizeof(Prepared) == 112, "Prepared");
+static_assert(sizeof(Prepared) == 128, "Prepared");
 
 constexpr int kRasterChunk = 256;
-constexpr uint32_t kMaskFlat = 1u << 16;
 
 // Builds the tile-local form of one triangle. Exact for edges whose Manhattan
 // length is below 2^17 px; longer edges are scaled (approximate).
@@ -145,25 +150,32 @@ __device__ void prepare_triangle(const FlushParams& P,
     bool flat = kind == kKindFill;
     for (int c = 0; c < comps; ++c)
     {
+        float* plane = c == 0 ? out.plane0 : (c == 1 ? out.plane1 : (c == 2 ? out.plane2 : out.plane3));
         const float f0 = attr[c * 3 + 0], f1 = attr[c * 3 + 1], f2 = attr[c * 3 + 2];
         if (c == 0 && flat && f0 == f1 && f1 == f2)
         {
             // Constant coverage (fan / interior triangles): exact, no gradient.
-            out.plane[0][0] = f0;
-            out.plane[0][1] = 0.f;
-            out.plane[0][2] = 0.f;
+            plane[0] = f0;
+            plane[1] = 0.f;
+            plane[2] = 0.f;
             continue;
         }
         flat = false;
         const double c0 = f0, c1 = f1, c2 = f2;
-        out.plane[c][0] = static_cast<float>((c0 * static_cast<double>(E0u[0]) + c1 * static_cast<double>(E0u[1]) + c2 * static_cast<double>(E0u[2])) * inv);
-        out.plane[c][1] = static_cast<float>((c0 * static_cast<double>(A[0]) + c1 * static_cast<double>(A[1]) + c2 * static_cast<double>(A[2])) * 256.0 * inv);
-        out.plane[c][2] = static_cast<float>((c0 * static_cast<double>(B[0]) + c1 * static_cast<double>(B[1]) + c2 * static_cast<double>(B[2])) * 256.0 * inv);
+        plane[0] = static_cast<float>((c0 * static_cast<double>(E0u[0]) + c1 * static_cast<double>(E0u[1]) + c2 * static_cast<double>(E0u[2])) * inv);
+        plane[1] = static_cast<float>((c0 * static_cast<double>(A[0]) + c1 * static_cast<double>(A[1]) + c2 * static_cast<double>(A[2])) * 256.0 * inv);
+        plane[2] = static_cast<float>((c0 * static_cast<double>(B[0]) + c1 * static_cast<double>(B[1]) + c2 * static_cast<double>(B[2])) * 256.0 * inv);
     }
-    out.masks = blockMask | (fullMask << 8) | (flat ? kMaskFlat : 0u);
+    // Blocks that are fully inside a constant-coverage triangle take the fast path.
+    out.masks = blockMask | ((flat ? fullMask : 0u) << 8) | ((g.meta & 0xffffu) << 16);
     const uint2 paint = __ldg(P.paintBuffer + (g.meta & 0xffffu));
     out.paintX = paint.x;
     out.paintY = paint.y;
+    const float4 pc = unpack_rgba8(paint.y);
+    out.paintColor[0] = pc.x;
+    out.paintColor[1] = pc.y;
+    out.paintColor[2] = pc.z;
+    out.paintColor[3] = pc.w;
 }
 
 // draw_path_common.glsl:153-258
@@ -392,11 +404,11 @@ __device__ float clip_rect_coverage(const FlushParams& P, uint32_t pathID, float
 // Unpremultiplied paint colour at the pixel centre (draw_path.vert:188-362 +
 // find_paint_color :431-506; the varyings are affine in position, so evaluating
 // at the pixel is the same function as interpolating them).
-__device__ __forceinline__ float4 paint_color(const FlushParams& P, uint32_t pathID, uint32_t paintX, uint32_t paintY, float fragX, float fragY)
+__device__ __forceinline__ float4 paint_color(const FlushParams& P, uint32_t pathID, uint32_t paintX, uint32_t paintY, float4 solid, float fragX, float fragY)
 {
     const uint32_t paintType = paintX & 0xfu;
     if (paintType == kPaintTypeSolid)
-        return unpack_rgba8(paintY);
+        return solid;
     const float4 pm = __ldg(P.paintAuxBuffer + pathID * 8u);
     const float4 pt = __ldg(P.paintAuxBuffer + pathID * 8u + 1u);
     const float cx = pm.x * fragX + pm.z * fragY + pt.x;
@@ -412,6 +424,7 @@ __device__ __forceinline__ void resolve_path(const FlushParams& P,
                                              uint32_t meta,
                                              uint32_t paintX,
                                              uint32_t paintY,
+                                             float4 solid,
                                              float coverageCount,
                                              int px,
                                              int py,
@@ -450,7 +463,7 @@ __device__ __forceinline__ void resolve_path(const FlushParams& P,
     const float fragX = px + .5f, fragY = py + .5f;
     if ((paintX & kPaintFlagClipRect) != 0u)
         coverage = clampf(clip_rect_coverage(P, pathID, fragX, fragY), 0.f, coverage);
-    const float4 color = paint_color(P, pathID, paintX, paintY, fragX, fragY);
+    const float4 color = paint_color(P, pathID, paintX, paintY, solid, fragX, fragY);
     const float4 dst = unpack_rgba8(s.color);
     const uint32_t blendMode = (paintX >> 4) & 0xfu;
     float3 rgb = make_float3(color.x, color.y, color.z);
@@ -467,7 +480,7 @@ __device__ __forceinline__ void resolve_path(const FlushParams& P,
 }
 
 // Immediate-mode blend for atlas blits (draw_mesh.frag, @FEATHER_ATLAS_BLIT).
-__device__ void resolve_atlas_blit(const FlushParams& P, uint32_t meta, uint32_t paintX, uint32_t paintY, float u, float v, int px, int py, PixelState& s)
+__device__ void resolve_atlas_blit(const FlushParams& P, uint32_t meta, uint32_t paintX, uint32_t paintY, float4 solid, float u, float v, int px, int py, PixelState& s)
 {
     const uint32_t pathID = meta & 0xffffu;
     float coverage = clamp01(sample_atlas(P, u, v));
@@ -477,7 +490,7 @@ __device__ void resolve_atlas_blit(const FlushParams& P, uint32_t meta, uint32_t
     const uint32_t clipID = paintX >> 16;
     if (clipID != 0u)
         coverage = fminf(coverage, fmaxf(s.clipID == clipID ? s.clipCoverage : 0.f, 0.f));
-    const float4 color = paint_color(P, pathID, paintX, paintY, fragX, fragY);
+    const float4 color = paint_color(P, pathID, paintX, paintY, solid, fragX, fragY);
     const float4 dst = unpack_rgba8(s.color);
     const uint32_t blendMode = (paintX >> 4) & 0xfu;
     float3 rgb = make_float3(color.x, color.y, color.z);
@@ -527,15 +540,16 @@ __global__ void __launch_bounds__(256, 4) raster_tiles_kernel(FlushParams P,
     const uint32_t* list = entries + tileOffsets[tile];
 
     // Per-warp path accumulation state (the warp's pixels only).
-    uint32_t curMeta = 0u, curPaintX = 0u, curPaintY = 0u;
+    uint32_t curPath = 0u, curMeta = 0u, curPaintX = 0u, curPaintY = 0u;
+    float4 curSolid = make_float4(0.f, 0.f, 0.f, 0.f);
     float coverageCount = 0.f;
     bool touched = false;
+    const uint32_t blockBit = 1u << warp, fastBit = 0x100u << warp;
 
     for (uint32_t base = 0; base < n; base += kRasterChunk)
     {
         const uint32_t chunk = min(static_cast<uint32_t>(kRasterChunk), n - base);
         __syncthreads(); // every warp is done with the previous chunk
-        uint32_t myMasks = 0u;
         if (threadIdx.x < chunk)
         {
             const uint32_t t = __ldg(list + base + threadIdx.x);
@@ -550,51 +564,52 @@ __global__ void __launch_bounds__(256, 4) raster_tiles_kernel(FlushParams P,
         for (uint32_t sub = 0; sub < chunk; sub += 32)
         {
             const uint32_t idx = sub + lane;
-            myMasks = idx < chunk ? s_prep[idx].masks : 0u;
-            uint32_t bits = __ballot_sync(0xffffffffu, ((myMasks >> warp) & 1u) != 0u);
+            const uint32_t myMasks = idx < chunk ? s_prep[idx].masks : 0u;
+            uint32_t bits = __ballot_sync(0xffffffffu, (myMasks & blockBit) != 0u);
             while (bits != 0u)
             {
                 const int bit = __ffs(bits) - 1;
                 bits &= bits - 1;
-                const Prepared& T = s_prep[sub + bit];
                 const uint32_t masks = __shfl_sync(0xffffffffu, myMasks, bit);
-                const uint32_t meta = T.meta;
-                const uint32_t kind = (meta >> kMetaKindShift) & 0xf;
+                const Prepared& T = s_prep[sub + bit];
                 // Path boundary (per warp): resolve what has been accumulated.
-                if ((meta & 0xffffu) != (curMeta & 0xffffu) || kind >= kKindAtlasBlit)
+                if ((masks >> 16) != curPath)
                 {
                     if (touched)
-                        resolve_path(P, curMeta, curPaintX, curPaintY, coverageCount, px, py, s);
-                    curMeta = kind >= kKindAtlasBlit ? 0u : meta;
-                    curPaintX = T.paintX;
-                    curPaintY = T.paintY;
+                        resolve_path(P, curMeta, curPaintX, curPaintY, curSolid, coverageCount, px, py, s);
+                    curPath = masks >> 16;
+                    curMeta = T.meta;
+                    const uint2 pxy = *reinterpret_cast<const uint2*>(&T.paintX);
+                    curPaintX = pxy.x;
+                    curPaintY = pxy.y;
+                    curSolid = *reinterpret_cast<const float4*>(T.paintColor);
                     coverageCount = 0.f;
                     touched = false;
                 }
-                const bool full = ((masks >> (8 + warp)) & 1u) != 0u;
-                if (full && (masks & kMaskFlat) != 0u)
+                if ((masks & fastBit) != 0u)
                 {
                     // Whole block inside a constant-coverage triangle.
-                    coverageCount += T.plane[0][0];
+                    coverageCount += T.plane0[0];
                     touched = true;
                     continue;
                 }
-                if (!full)
-                {
-                    const int e0 = T.q0 + T.A0 * i + T.B0 * j;
-                    const int e1 = T.q1 + T.A1 * i + T.B1 * j;
-                    const int e2 = T.q2 + T.A2 * i + T.B2 * j;
-                    if ((e0 | e1 | e2) < 0)
-                        continue;
-                }
-                const float c0 = T.plane[0][0] + T.plane[0][1] * fi + T.plane[0][2] * fj;
+                const int4 w0 = *reinterpret_cast<const int4*>(&T.A0);
+                const int4 w1 = *reinterpret_cast<const int4*>(&T.B1);
+                const int4 w2 = *reinterpret_cast<const int4*>(&T.q2);
+                const int e0 = w0.z + w0.x * i + w0.y * j;
+                const int e1 = w1.y + w0.w * i + w1.x * j;
+                const int e2 = w2.x + w1.z * i + w1.w * j;
+                if ((e0 | e1 | e2) < 0)
+                    continue;
+                const float c0 = __int_as_float(w2.y) + __int_as_float(w2.z) * fi + __int_as_float(w2.w) * fj;
+                const uint32_t kind = (curMeta >> kMetaKindShift) & 0xf;
                 if (kind == kKindFill)
                 {
                     coverageCount += c0;
                     touched = true;
                     continue;
                 }
-                const float c1 = T.plane[1][0] + T.plane[1][1] * fi + T.plane[1][2] * fj;
+                const float c1 = T.plane1[0] + T.plane1[1] * fi + T.plane1[2] * fj;
                 switch (kind)
                 {
                     case kKindStroke:
@@ -603,8 +618,8 @@ __global__ void __launch_bounds__(256, 4) raster_tiles_kernel(FlushParams P,
                         break;
                     case kKindFeatherFill:
                     {
-                        const float c2 = T.plane[2][0] + T.plane[2][1] * fi + T.plane[2][2] * fj;
-                        const float c3 = T.plane[3][0] + T.plane[3][1] * fi + T.plane[3][2] * fj;
+                        const float c2 = T.plane2[0] + T.plane2[1] * fi + T.plane2[2] * fj;
+                        const float c3 = T.plane3[0] + T.plane3[1] * fi + T.plane3[2] * fj;
                         coverageCount += eval_feathered_fill(P.featherLUT, make_float4(c0, c1, c2, c3));
                         touched = true;
                         break;
@@ -614,7 +629,7 @@ __global__ void __launch_bounds__(256, 4) raster_tiles_kernel(FlushParams P,
                         touched = true;
                         break;
                     case kKindAtlasBlit:
-                        resolve_atlas_blit(P, meta, T.paintX, T.paintY, c0, c1, px, py, s);
+                        resolve_atlas_blit(P, curMeta, curPaintX, curPaintY, curSolid, c0, c1, px, py, s);
                         break;
                     default:
                         break;
@@ -623,7 +638,7 @@ __global__ void __launch_bounds__(256, 4) raster_tiles_kernel(FlushParams P,
         }
     }
     if (touched)
-        resolve_path(P, curMeta, curPaintX, curPaintY, coverageCount, px, py, s);
+        resolve_path(P, curMeta, curPaintX, curPaintY, curSolid, coverageCount, px, py, s);
     if (inBounds)
         P.target[static_cast<size_t>(py) * P.targetWidth + px] = s.color;
 }
