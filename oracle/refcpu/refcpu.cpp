@@ -33,6 +33,8 @@
 using namespace refcpu;
 
 static thread_local std::string t_error;
+// Debug aid: REFCPU_DEBUG_PIXEL="x,y" prints every fragment that hits the pixel.
+static int g_debugX = -1, g_debugY = -1;
 static int fail(const char* msg)
 {
     t_error = msg;
@@ -1240,6 +1242,8 @@ void path_fragment_main(const Context& c, const BatchState& bs, const FragIn& in
         pls.coverage[idx] = packHalf2x16(coverageCount, in.pathID);
     }
 
+    if (px == g_debugX && py == g_debugY)
+        fprintf(stderr, "[refcpu] px(%d,%d) pathID=%g interior=%d count=%.9g cov=(%.9g,%.9g,%.9g,%.9g) w=%g color=%08x\n", px, py, in.pathID, int(interiorTriangles), coverageCount, in.coverages.x, in.coverages.y, in.coverages.z, in.coverages.w, in.windingWeight, pls.color[idx]);
     float coverage;
     if (bs.clockwiseFill)
     {
@@ -1415,8 +1419,11 @@ void mesh_fragment_main(const Context& c,
     pls.color[idx] = packUnorm4x8(color);
 }
 
-inline float interp(float a0, float a1, float a2, float b0, float b1, float b2) { return a0 * b0 + a1 * b1 + a2 * b2; }
-inline float4 interp4(const float4& a0, const float4& a1, const float4& a2, float b0, float b1, float b2)
+inline float interp(float a0, float a1, float a2, double b0, double b1, double b2)
+{
+    return static_cast<float>(a0 * b0 + a1 * b1 + a2 * b2);
+}
+inline float4 interp4(const float4& a0, const float4& a1, const float4& a2, double b0, double b1, double b2)
 {
     return {interp(a0.x, a1.x, a2.x, b0, b1, b2), interp(a0.y, a1.y, a2.y, b0, b1, b2), interp(a0.z, a1.z, a2.z, b0, b1, b2), interp(a0.w, a1.w, a2.w, b0, b1, b2)};
 }
@@ -1564,7 +1571,7 @@ int draw_list(Context& c)
                             if (tri.setup.ymax < r0 || tri.setup.ymin >= r1)
                                 continue;
                             const VSOut &v0 = verts[tri.v[0]], &v1 = verts[tri.v[1]], &v2 = verts[tri.v[2]];
-                            raster_triangle(tri.setup, r0, r1, [&](int x, int y, float b0, float b1, float b2) {
+                            raster_triangle(tri.setup, r0, r1, [&](int x, int y, double b0, double b1, double b2) {
                                 FragIn in;
                                 in.paint = interp4(v0.paint, v1.paint, v2.paint, b0, b1, b2);
                                 in.image = {interp(v0.image.x, v1.image.x, v2.image.x, b0, b1, b2),
@@ -1645,7 +1652,7 @@ int draw_list(Context& c)
                         if (tri.setup.ymax < r0 || tri.setup.ymin >= r1)
                             continue;
                         const VSOut &v0 = verts[tri.v[0]], &v1 = verts[tri.v[1]], &v2 = verts[tri.v[2]];
-                        raster_triangle(tri.setup, r0, r1, [&](int x, int y, float b0, float b1, float b2) {
+                        raster_triangle(tri.setup, r0, r1, [&](int x, int y, double b0, double b1, double b2) {
                             size_t idx = static_cast<size_t>(y) * W + x;
                             float4 paint = interp4(v0.paint, v1.paint, v2.paint, b0, b1, b2);
                             float3 image = {interp(v0.image.x, v1.image.x, v2.image.x, b0, b1, b2), interp(v0.image.y, v1.image.y, v2.image.y, b0, b1, b2), interp(v0.image.z, v1.image.z, v2.image.z, b0, b1, b2)};
@@ -1757,7 +1764,7 @@ int draw_list(Context& c)
                             }
                             lod += c.uniforms.mipMapLODBias;
                         }
-                        raster_triangle(tri.setup, r0, r1, [&](int x, int y, float b0, float b1, float b2) {
+                        raster_triangle(tri.setup, r0, r1, [&](int x, int y, double b0, double b1, double b2) {
                             float u = interp(v0.uv.x, v1.uv.x, v2.uv.x, b0, b1, b2), v = interp(v0.uv.y, v1.uv.y, v2.uv.y, b0, b1, b2);
                             float4 color = sample_image(tex, bs.samplerKey, u, v, lod);
                             float4 clipRect = interp4(v0.clipRect, v1.clipRect, v2.clipRect, b0, b1, b2);
@@ -1826,7 +1833,7 @@ void render_atlas(Context& c)
                 if (anyDiscard)
                     continue;
                 TriSetup setup = setup_triangle(xs, ys, /*cullCCW=*/isStroke, sx0, sy0, sx1, sy1);
-                raster_triangle(setup, sy0, sy1, [&](int x, int y, float b0, float b1, float b2) {
+                raster_triangle(setup, sy0, sy1, [&](int x, int y, double b0, double b1, double b2) {
                     float4 coverages = interp4(cov[0], cov[1], cov[2], b0, b1, b2);
                     float& texel = c.atlas[static_cast<size_t>(y) * AW + x];
                     float result;
@@ -1865,6 +1872,8 @@ static int with_context(const refcpu_flush* f, int (*fn)(Context&))
 {
     if (f == nullptr || f->desc == nullptr || f->tables == nullptr)
         return fail("refcpu: null flush / desc / tables");
+    if (const char* dbg = getenv("REFCPU_DEBUG_PIXEL"))
+        sscanf(dbg, "%d,%d", &g_debugX, &g_debugY);
     Context c;
     if (!init_context(c, f))
         return fail("refcpu: unsupported flush (interlock mode must be rasterOrdering; flush uniforms required)");
@@ -1948,7 +1957,7 @@ int refcpu_raster_mask(const float xy[6], int cull_ccw, uint32_t w, uint32_t h, 
     float xs[3] = {xy[0], xy[2], xy[4]}, ys[3] = {xy[1], xy[3], xy[5]};
     TriSetup setup = setup_triangle(xs, ys, cull_ccw != 0, 0, 0, static_cast<int>(w), static_cast<int>(h));
     int count = 0;
-    raster_triangle(setup, 0, static_cast<int>(h), [&](int x, int y, float, float, float) {
+    raster_triangle(setup, 0, static_cast<int>(h), [&](int x, int y, double, double, double) {
         mask[static_cast<size_t>(y) * w + x] = 1;
         ++count;
     });

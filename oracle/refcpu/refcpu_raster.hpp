@@ -162,10 +162,12 @@ template <typename Fn> inline void raster_triangle(const TriSetup& t, int rowBeg
             double e0 = static_cast<double>(t.A[0] * px + K[0]);
             double e1 = static_cast<double>(t.A[1] * px + K[1]);
             double e2 = static_cast<double>(t.A[2] * px + K[2]);
-            float b0 = static_cast<float>(e0 * invArea);
-            float b1 = static_cast<float>(e1 * invArea);
-            float b2 = static_cast<float>(e2 * invArea);
-            fn(static_cast<int>(x), y, b0, b1, b2);
+            // Barycentrics stay in double: varyings such as clip-rect distances
+            // and gradient coordinates are affine functions that reach ~1e7 at
+            // the vertices of screen-filling triangles, where fp32 weights
+            // would lose the fractional part a real pipeline keeps (hardware
+            // clips such triangles to the guard band before interpolating).
+            fn(static_cast<int>(x), y, e0 * invArea, e1 * invArea, e2 * invArea);
         }
     }
 }

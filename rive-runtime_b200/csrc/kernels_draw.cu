@@ -57,6 +57,7 @@ enum TriKind : uint32_t
 
 constexpr uint32_t kMetaValid = 1u << 31;
 constexpr uint32_t kMetaClockwiseFill = 1u << 30;
+constexpr uint32_t kMetaUnmultiplied = 1u << 29; // batch has ENABLE_ADVANCED_BLEND (GENERATE_UNMULTIPLIED_PAINT_COLORS)
 constexpr uint32_t kMetaKindShift = 16;
 
 struct TriGeom // 32 B
@@ -100,6 +101,7 @@ struct FlushParams
     uint32_t loadAction;
     uint32_t clearColorPremulRGBA;
     float ditherScale, ditherBias;
+    int32_t debugX, debugY; // RIVECUDA_DEBUG_PIXEL="x,y": printf every accumulate/resolve at this pixel
 };
 
 // ---------------------------------------------------------------------------
@@ -729,6 +731,8 @@ __global__ void __launch_bounds__(kSetupWarpsPerBlock * 32) setup_patches_kernel
                 uint32_t meta = pathID | (kind << kMetaKindShift);
                 if ((b.miscFlags & RIVECUDA_MISC_CLOCKWISE_FILL) != 0u)
                     meta |= kMetaClockwiseFill;
+                if ((b.flags & RIVECUDA_FEATURE_ADVANCED_BLEND) != 0u)
+                    meta |= kMetaUnmultiplied;
                 stored = store_triangle(P, triGeom, triAttr, X, Y, rawTri, xs, ys, attr, comps, meta, 0u, /*cullCCW=*/true);
             }
             warp_for_each_tile(P, X, Y, stored, [&](uint32_t tile, int) { atomicAdd(tileCounts + tile, 1u); });
@@ -808,6 +812,8 @@ __global__ void __launch_bounds__(256) setup_triangle_runs_kernel(FlushParams P,
         }
         if ((b.miscFlags & RIVECUDA_MISC_CLOCKWISE_FILL) != 0u)
             meta |= kMetaClockwiseFill;
+        if ((b.flags & RIVECUDA_FEATURE_ADVANCED_BLEND) != 0u)
+            meta |= kMetaUnmultiplied;
         stored = store_triangle(P, triGeom, triAttr, X, Y, rawTri, xs, ys, attr, comps, meta, 0u, /*cullCCW=*/true);
         }
         warp_for_each_tile(P, X, Y, stored, [&](uint32_t tile, int) { atomicAdd(tileCounts + tile, 1u); });
@@ -1089,6 +1095,9 @@ int launch_draw_list(rivecuda_ctx* ctx, const rivecuda_flush_desc& desc, const r
     P.clearColorPremulRGBA = premul_clear_color(desc.color_clear_value);
     P.ditherScale = desc.dither_mode == 0 ? 0.f : 1.f / 256.f;
     P.ditherBias = P.ditherScale * -.5f;
+    P.debugX = P.debugY = -1;
+    if (const char* dbg = getenv("RIVECUDA_DEBUG_PIXEL"))
+        sscanf(dbg, "%d,%d", &P.debugX, &P.debugY);
     if (P.boundsL >= P.boundsR || P.boundsT >= P.boundsB)
     {
         if (ctx->profiling)

@@ -171,7 +171,15 @@ __device__ void prepare_triangle(const FlushParams& P,
     const uint2 paint = __ldg(P.paintBuffer + (g.meta & 0xffffu));
     out.paintX = paint.x;
     out.paintY = paint.y;
-    const float4 pc = unpack_rgba8(paint.y);
+    // draw_path.vert:298-312: solid colours are premultiplied in the vertex stage
+    // unless the batch runs with advanced blend.
+    float4 pc = unpack_rgba8(paint.y);
+    if ((g.meta & kMetaUnmultiplied) == 0u)
+    {
+        pc.x *= pc.w;
+        pc.y *= pc.w;
+        pc.z *= pc.w;
+    }
     out.paintColor[0] = pc.x;
     out.paintColor[1] = pc.y;
     out.paintColor[2] = pc.z;
@@ -401,14 +409,39 @@ __device__ float clip_rect_coverage(const FlushParams& P, uint32_t pathID, float
     return fminf(tr.x, tr.y);
 }
 
-// Unpremultiplied paint colour at the pixel centre (draw_path.vert:188-362 +
-// find_paint_color :431-506; the varyings are affine in position, so evaluating
-// at the pixel is the same function as interpolating them).
-__device__ __forceinline__ float4 paint_color(const FlushParams& P, uint32_t pathID, uint32_t paintX, uint32_t paintY, float4 solid, float fragX, float fragY)
+// find_paint_color (draw_path.vert:431-506) with the same operation order as the
+// shader, evaluated at the pixel centre (the varyings are affine in position, so
+// this is the same function as interpolating them). `solid` is the vertex
+// stage's v_paint for solid colours. Returns colour with coverage applied:
+// premultiplied unless the batch generates unmultiplied paints.
+__device__ __forceinline__ float4 paint_color(const FlushParams& P,
+                                              uint32_t pathID,
+                                              uint32_t paintX,
+                                              uint32_t paintY,
+                                              float4 solid,
+                                              bool unmultiplied,
+                                              float coverage,
+                                              float fragX,
+                                              float fragY)
 {
     const uint32_t paintType = paintX & 0xfu;
+    float4 color;
     if (paintType == kPaintTypeSolid)
-        return solid;
+    {
+        color = solid;
+        if (unmultiplied)
+        {
+            color.w *= coverage;
+        }
+        else
+        {
+            color.x *= coverage;
+            color.y *= coverage;
+            color.z *= coverage;
+            color.w *= coverage;
+        }
+        return color;
+    }
     const float4 pm = __ldg(P.paintAuxBuffer + pathID * 8u);
     const float4 pt = __ldg(P.paintAuxBuffer + pathID * 8u + 1u);
     const float cx = pm.x * fragX + pm.z * fragY + pt.x;
@@ -416,7 +449,15 @@ __device__ __forceinline__ float4 paint_color(const FlushParams& P, uint32_t pat
     float t = paintType == kPaintTypeLinear ? cx : sqrtf(cx * cx + cy * cy);
     t = clamp01(t);
     const float x = pt.z > .9f ? (1.f - 1.f / 512.f) * t + (.5f / 512.f) : (1.f / 512.f) * t + pt.w;
-    return sample_grad(P, x, __uint_as_float(paintY));
+    color = sample_grad(P, x, __uint_as_float(paintY));
+    color.w *= coverage;
+    if (!unmultiplied)
+    {
+        color.x *= color.w;
+        color.y *= color.w;
+        color.z *= color.w;
+    }
+    return color;
 }
 
 // Resolve one path at one pixel (draw_raster_order_path.frag:61-232).
@@ -431,6 +472,10 @@ __device__ __forceinline__ void resolve_path(const FlushParams& P,
                                              PixelState& s)
 {
     const uint32_t pathID = meta & 0xffffu;
+#ifdef RIVECUDA_DEBUG
+    if (px == P.debugX && py == P.debugY)
+        printf("[cuda] px(%d,%d) resolve pathID=%u count=%.9g color=%08x paint=%08x,%08x\n", px, py, pathID, coverageCount, s.color, paintX, paintY);
+#endif
     float coverage;
     if ((meta & kMetaClockwiseFill) != 0u)
     {
@@ -463,18 +508,29 @@ __device__ __forceinline__ void resolve_path(const FlushParams& P,
     const float fragX = px + .5f, fragY = py + .5f;
     if ((paintX & kPaintFlagClipRect) != 0u)
         coverage = clampf(clip_rect_coverage(P, pathID, fragX, fragY), 0.f, coverage);
-    const float4 color = paint_color(P, pathID, paintX, paintY, solid, fragX, fragY);
+    const bool unmultiplied = (meta & kMetaUnmultiplied) != 0u;
+    float4 color = paint_color(P, pathID, paintX, paintY, solid, unmultiplied, coverage, fragX, fragY);
     const float4 dst = unpack_rgba8(s.color);
-    const uint32_t blendMode = (paintX >> 4) & 0xfu;
-    float3 rgb = make_float3(color.x, color.y, color.z);
-    if (blendMode != 0u)
-        rgb = advanced_color_blend(rgb, dst, blendMode);
-    const float a = color.w * coverage;
+    if (unmultiplied)
+    {
+        const uint32_t blendMode = (paintX >> 4) & 0xfu;
+        if (blendMode != 0u)
+        {
+            const float3 rgb = advanced_color_blend(make_float3(color.x, color.y, color.z), dst, blendMode);
+            color.x = rgb.x;
+            color.y = rgb.y;
+            color.z = rgb.z;
+        }
+        color.x *= color.w;
+        color.y *= color.w;
+        color.z *= color.w;
+    }
+    const float a = color.w;
     const float oneMinusA = 1.f - a;
     const float dither = a != 0.f ? s.dither : 0.f;
-    const float r = rgb.x * a + dst.x * oneMinusA + dither;
-    const float g = rgb.y * a + dst.y * oneMinusA + dither;
-    const float b = rgb.z * a + dst.z * oneMinusA + dither;
+    const float r = (color.x + dst.x * oneMinusA) + dither;
+    const float g = (color.y + dst.y * oneMinusA) + dither;
+    const float b = (color.z + dst.z * oneMinusA) + dither;
     const float outA = a + dst.w * oneMinusA;
     s.color = pack_rgba8_fast(r, g, b, outA);
 }
@@ -490,19 +546,38 @@ __device__ void resolve_atlas_blit(const FlushParams& P, uint32_t meta, uint32_t
     const uint32_t clipID = paintX >> 16;
     if (clipID != 0u)
         coverage = fminf(coverage, fmaxf(s.clipID == clipID ? s.clipCoverage : 0.f, 0.f));
-    const float4 color = paint_color(P, pathID, paintX, paintY, solid, fragX, fragY);
+    // draw_mesh.frag: find_paint_color(v_paint, 1.) then blend with `coverage`.
+    const bool unmultiplied = (meta & kMetaUnmultiplied) != 0u;
+    float4 color = paint_color(P, pathID, paintX, paintY, solid, unmultiplied, 1.f, fragX, fragY);
     const float4 dst = unpack_rgba8(s.color);
-    const uint32_t blendMode = (paintX >> 4) & 0xfu;
-    float3 rgb = make_float3(color.x, color.y, color.z);
-    if (blendMode != 0u)
-        rgb = advanced_color_blend(rgb, dst, blendMode);
-    const float a = color.w * coverage;
-    const float dither = a != 0.f ? s.dither : 0.f;
-    const float oneMinusA = 1.f - a;
-    s.color = pack_rgba8_fast(dst.x * oneMinusA + (rgb.x * a + dither),
-                              dst.y * oneMinusA + (rgb.y * a + dither),
-                              dst.z * oneMinusA + (rgb.z * a + dither),
-                              dst.w * oneMinusA + a);
+    if (unmultiplied)
+    {
+        const uint32_t blendMode = (paintX >> 4) & 0xfu;
+        if (blendMode != 0u)
+        {
+            const float3 rgb = advanced_color_blend(make_float3(color.x, color.y, color.z), dst, blendMode);
+            color.x = rgb.x;
+            color.y = rgb.y;
+            color.z = rgb.z;
+        }
+        color.w *= coverage;
+        color.x *= color.w;
+        color.y *= color.w;
+        color.z *= color.w;
+    }
+    else
+    {
+        color.x *= coverage;
+        color.y *= coverage;
+        color.z *= coverage;
+        color.w *= coverage;
+    }
+    const float dither = color.w != 0.f ? s.dither : 0.f;
+    const float oneMinusA = 1.f - color.w;
+    s.color = pack_rgba8_fast(dst.x * oneMinusA + (color.x + dither),
+                              dst.y * oneMinusA + (color.y + dither),
+                              dst.z * oneMinusA + (color.z + dither),
+                              dst.w * oneMinusA + color.w);
 }
 
 __global__ void __launch_bounds__(256, 4) raster_tiles_kernel(FlushParams P,
@@ -542,7 +617,8 @@ __global__ void __launch_bounds__(256, 4) raster_tiles_kernel(FlushParams P,
     // Per-warp path accumulation state (the warp's pixels only).
     uint32_t curPath = 0u, curMeta = 0u, curPaintX = 0u, curPaintY = 0u;
     float4 curSolid = make_float4(0.f, 0.f, 0.f, 0.f);
-    float coverageCount = 0.f;
+    float coverageCount = 0.f; // what the last fragment computed (fp32, as the shader sees it)
+    float coverageStored = 0.f; // what it wrote back to the fp16 coverage plane
     bool touched = false;
     const uint32_t blockBit = 1u << warp, fastBit = 0x100u << warp;
 
@@ -584,12 +660,22 @@ __global__ void __launch_bounds__(256, 4) raster_tiles_kernel(FlushParams P,
                     curPaintY = pxy.y;
                     curSolid = *reinterpret_cast<const float4*>(T.paintColor);
                     coverageCount = 0.f;
+                    coverageStored = 0.f;
                     touched = false;
                 }
                 if ((masks & fastBit) != 0u)
                 {
                     // Whole block inside a constant-coverage triangle.
-                    coverageCount += T.plane0[0];
+                    // (The reference's coverage plane is fp16: every
+                    // fragment's read-modify-write rounds to half, and deep
+                    // feather overlap makes that rounding visible, so we
+                    // round after every accumulate, in the same order.)
+#ifdef RIVECUDA_DEBUG
+                    if (px == P.debugX && py == P.debugY)
+                        printf("[cuda] px(%d,%d) fast pathID=%u c0=%.9g count=%.9g\n", px, py, curPath, T.plane0[0], coverageCount);
+#endif
+                    coverageCount = coverageStored + T.plane0[0];
+                    coverageStored = round_to_half(coverageCount);
                     touched = true;
                     continue;
                 }
@@ -603,9 +689,14 @@ __global__ void __launch_bounds__(256, 4) raster_tiles_kernel(FlushParams P,
                     continue;
                 const float c0 = __int_as_float(w2.y) + __int_as_float(w2.z) * fi + __int_as_float(w2.w) * fj;
                 const uint32_t kind = (curMeta >> kMetaKindShift) & 0xf;
+#ifdef RIVECUDA_DEBUG
+                if (px == P.debugX && py == P.debugY)
+                    printf("[cuda] px(%d,%d) frag pathID=%u kind=%u c0=%.9g count=%.9g\n", px, py, curPath, kind, c0, coverageCount);
+#endif
                 if (kind == kKindFill)
                 {
-                    coverageCount += c0;
+                    coverageCount = coverageStored + c0;
+                    coverageStored = round_to_half(coverageCount);
                     touched = true;
                     continue;
                 }
@@ -613,19 +704,22 @@ __global__ void __launch_bounds__(256, 4) raster_tiles_kernel(FlushParams P,
                 switch (kind)
                 {
                     case kKindStroke:
-                        coverageCount = fmaxf(coverageCount, fminf(c0, c1));
+                        coverageCount = fmaxf(fminf(c0, c1), coverageStored);
+                        coverageStored = round_to_half(coverageCount);
                         touched = true;
                         break;
                     case kKindFeatherFill:
                     {
                         const float c2 = T.plane2[0] + T.plane2[1] * fi + T.plane2[2] * fj;
                         const float c3 = T.plane3[0] + T.plane3[1] * fi + T.plane3[2] * fj;
-                        coverageCount += eval_feathered_fill(P.featherLUT, make_float4(c0, c1, c2, c3));
+                        coverageCount = coverageStored + eval_feathered_fill(P.featherLUT, make_float4(c0, c1, c2, c3));
+                        coverageStored = round_to_half(coverageCount);
                         touched = true;
                         break;
                     }
                     case kKindFeatherStroke:
-                        coverageCount = fmaxf(coverageCount, eval_feathered_stroke(P.featherLUT, c0, c1));
+                        coverageCount = fmaxf(eval_feathered_stroke(P.featherLUT, c0, c1), coverageStored);
+                        coverageStored = round_to_half(coverageCount);
                         touched = true;
                         break;
                     case kKindAtlasBlit:
