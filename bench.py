@@ -223,6 +223,12 @@ def main() -> None:
     rp.lib.rivecuda_set_profiling(rp.ctx, 0)
     raster = float(np.mean(raster_ms))
     peak, peak_src = measured_peak_gbs()
+    traffic = None
+    try:  # dram__bytes_read+write of the same kernel on the same workload, from the committed ncu capture
+        tj = json.load(open(os.path.join(ROOT, "profiles", "raster_traffic.json")))
+        traffic = int(tj["dram_bytes_read"]) + int(tj["dram_bytes_write"])
+    except Exception:  # noqa: BLE001
+        pass
     achieved = alg_bytes / (raster / 1e3) / 1e9
 
     # ---- e2e: host buffers in, host frame out, through the C ABI --------------
@@ -274,7 +280,7 @@ def main() -> None:
             "e2e": {"value": e2e_fps, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes},
             "gpu_launches": int(launches) * args.steps,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": "raster_tiles_kernel", "kernel_ms": raster,
+                         "traffic": traffic, "kernel": "raster_tiles_kernel", "kernel_ms": raster,
                          "algorithmic_bytes": alg_bytes, "peak_source": peak_src,
                          "other_kernels_ms": {"tessellate": float(np.mean(tess_ms)), "setup_bin_sort": float(np.mean(setup_ms))}},
             "cpu_baseline": cpu,
