@@ -35,6 +35,7 @@ using namespace refcpu;
 static thread_local std::string t_error;
 // Debug aid: REFCPU_DEBUG_PIXEL="x,y" prints every fragment that hits the pixel.
 static int g_debugX = -1, g_debugY = -1;
+static thread_local bool g_debugTrace = false; // the fragment being shaded is REFCPU_DEBUG_PIXEL
 static int fail(const char* msg)
 {
     t_error = msg;
@@ -1174,6 +1175,8 @@ float4 find_paint_color(const Context& c, const BatchState& bs, float4 paint, fl
     {
         float lod = image.z - 1.f;
         float4 imageColor = sample_image(bs.imageTexture, bs.samplerKey, image.x, image.y, lod);
+        if (g_debugTrace)
+            fprintf(stderr, "[refcpu] image uv=(%.9g,%.9g) lod=%.9g -> (%.9g,%.9g,%.9g,%.9g) coverage=%.9g\n", image.x, image.y, lod, imageColor.x, imageColor.y, imageColor.z, imageColor.w, coverage);
         if (unmultiplied)
         {
             half3 u = unmultiply_rgb(imageColor);
@@ -1226,6 +1229,7 @@ struct FragIn
 // @DRAW_INTERIOR_TRIANGLES variant.
 void path_fragment_main(const Context& c, const BatchState& bs, const FragIn& in, bool interiorTriangles, int px, int py, size_t idx, const PLS& pls)
 {
+    g_debugTrace = px == g_debugX && py == g_debugY;
     float2 coverageData = unpackHalf2x16(pls.coverage[idx]);
     float coverageBufferID = coverageData.y;
     float coverageCount = coverageBufferID == in.pathID ? coverageData.x : 0.f;
@@ -1659,6 +1663,7 @@ int draw_list(Context& c)
                             float4 clipRect = interp4(v0.clipRect, v1.clipRect, v2.clipRect, b0, b1, b2);
                             if (atlasBlit)
                             {
+                                g_debugTrace = x == g_debugX && y == g_debugY;
                                 float4 color = find_paint_color(c, bs, paint, image, 1.f);
                                 float u = interp(v0.atlasCoord.x, v1.atlasCoord.x, v2.atlasCoord.x, b0, b1, b2);
                                 float v = interp(v0.atlasCoord.y, v1.atlasCoord.y, v2.atlasCoord.y, b0, b1, b2);

@@ -39,6 +39,7 @@
 #include <cuda_fp16.h>
 
 #include <algorithm>
+#include <cstring>
 
 namespace rivecuda
 {
@@ -55,9 +56,14 @@ enum TriKind : uint32_t
     kKindImageMesh = 5,     // immediate blend, colour from an image
 };
 
+constexpr uint32_t kAuxNoImage = 0xfffu; // TriGeom::aux = imageSlot (12 bits) | imageDrawInstance << 12
+
 constexpr uint32_t kMetaValid = 1u << 31;
 constexpr uint32_t kMetaClockwiseFill = 1u << 30;
 constexpr uint32_t kMetaUnmultiplied = 1u << 29; // batch has ENABLE_ADVANCED_BLEND (GENERATE_UNMULTIPLIED_PAINT_COLORS)
+constexpr uint32_t kMetaModulatedImage = 1u << 28; // batch has ENABLE_MODULATED_IMAGE and binds a texture
+constexpr uint32_t kMetaClipRect = 1u << 27;       // image meshes: batch has ENABLE_CLIP_RECT
+constexpr uint32_t kMetaClipping = 1u << 26;       // image meshes: batch has ENABLE_CLIPPING
 constexpr uint32_t kMetaKindShift = 16;
 
 struct TriGeom // 32 B
@@ -102,6 +108,33 @@ struct FlushParams
     uint32_t clearColorPremulRGBA;
     float ditherScale, ditherBias;
     int32_t debugX, debugY; // RIVECUDA_DEBUG_PIXEL="x,y": printf every accumulate/resolve at this pixel
+    const struct ImageSlot* images; // per-flush table of (texture, sampler) for batches that bind one
+    uint16_t* pathImageSlots;       // pathID -> index into `images` (written by setup for image paints)
+};
+
+// A bound image: rivecuda_draw_batch::image_texture + image_sampler.
+struct ImageSlot
+{
+    DeviceTexture texture;
+    uint32_t samplerKey; // ImageSampler::asKey(): wrapX + 3*wrapY + 9*filter
+    uint32_t pad[3];
+};
+
+struct MeshBatchDev
+{
+    const float* positions; // float2 per vertex
+    const float* uvs;       // float2 per vertex
+    const uint16_t* indices;
+    uint32_t vertexCount;
+    uint32_t indexCount;
+    uint32_t baseIndex;
+    uint32_t instanceIndex; // ImageDrawInstance index (frame-wide)
+    uint32_t firstTriangle; // raw triangle id
+    uint32_t firstWorkItem; // in triangles
+    uint32_t imageSlot;
+    uint32_t flags;         // RIVECUDA_FEATURE_*
+    uint32_t texWidth, texHeight, texLevels;
+    float mipBias;          // FlushUniforms::mipMapLODBias
 };
 
 // ---------------------------------------------------------------------------
@@ -557,6 +590,19 @@ __device__ __forceinline__ void warp_for_each_tile(const FlushParams& P, const i
     }
 }
 
+// Per-batch bits of TriGeom::meta.
+__device__ __forceinline__ uint32_t batch_meta_bits(const DeviceBatch& b)
+{
+    uint32_t meta = 0u;
+    if ((b.miscFlags & RIVECUDA_MISC_CLOCKWISE_FILL) != 0u)
+        meta |= kMetaClockwiseFill;
+    if ((b.flags & RIVECUDA_FEATURE_ADVANCED_BLEND) != 0u)
+        meta |= kMetaUnmultiplied;
+    if ((b.flags & RIVECUDA_FEATURE_MODULATED_IMAGE) != 0u && b.imageSlot != kAuxNoImage)
+        meta |= kMetaModulatedImage;
+    return meta;
+}
+
 // Snap, orient, cull and store one triangle; returns true if stored.
 // attr[c*3+k]. cullCCW false => counter-clockwise triangles are re-wound.
 __device__ __forceinline__ bool store_triangle(const FlushParams& P,
@@ -728,12 +774,10 @@ __global__ void __launch_bounds__(kSetupWarpsPerBlock * 32) setup_patches_kernel
                 const uint32_t kind = isStroke ? (isFeathered ? kKindFeatherStroke : kKindStroke) : (isFeathered ? kKindFeatherFill : kKindFill);
                 float attr[12] = {a.c0, c.c0, d.c0, a.c1, c.c1, d.c1, a.c2, c.c2, d.c2, a.c3, c.c3, d.c3};
                 const int comps = kind == kKindFill ? 1 : (kind == kKindFeatherFill ? 4 : 2);
-                uint32_t meta = pathID | (kind << kMetaKindShift);
-                if ((b.miscFlags & RIVECUDA_MISC_CLOCKWISE_FILL) != 0u)
-                    meta |= kMetaClockwiseFill;
-                if ((b.flags & RIVECUDA_FEATURE_ADVANCED_BLEND) != 0u)
-                    meta |= kMetaUnmultiplied;
+                const uint32_t meta = pathID | (kind << kMetaKindShift) | batch_meta_bits(b);
                 stored = store_triangle(P, triGeom, triAttr, X, Y, rawTri, xs, ys, attr, comps, meta, 0u, /*cullCCW=*/true);
+                if (stored && (meta & kMetaModulatedImage) != 0u)
+                    P.pathImageSlots[pathID] = static_cast<uint16_t>(b.imageSlot);
             }
             warp_for_each_tile(P, X, Y, stored, [&](uint32_t tile, int) { atomicAdd(tileCounts + tile, 1u); });
         }
@@ -810,11 +854,94 @@ __global__ void __launch_bounds__(256) setup_triangle_runs_kernel(FlushParams P,
             meta = pathID | (kKindFill << kMetaKindShift);
             comps = 1;
         }
-        if ((b.miscFlags & RIVECUDA_MISC_CLOCKWISE_FILL) != 0u)
-            meta |= kMetaClockwiseFill;
-        if ((b.flags & RIVECUDA_FEATURE_ADVANCED_BLEND) != 0u)
-            meta |= kMetaUnmultiplied;
+        meta |= batch_meta_bits(b);
         stored = store_triangle(P, triGeom, triAttr, X, Y, rawTri, xs, ys, attr, comps, meta, 0u, /*cullCCW=*/true);
+        if (stored && (meta & kMetaModulatedImage) != 0u)
+            P.pathImageSlots[pathID] = static_cast<uint16_t>(b.imageSlot);
+        }
+        warp_for_each_tile(P, X, Y, stored, [&](uint32_t tile, int) { atomicAdd(tileCounts + tile, 1u); });
+    }
+}
+
+// Image meshes (draw_image_mesh.vert): one thread per indexed triangle. No
+// culling (gpu.cpp:1580-1588); overlapping triangles blend in index order.
+__global__ void __launch_bounds__(256) setup_meshes_kernel(FlushParams P,
+                                                          const MeshBatchDev* __restrict__ batches,
+                                                          uint32_t batchCount,
+                                                          uint32_t totalTriangles,
+                                                          TriGeom* __restrict__ triGeom,
+                                                          TriAttr* __restrict__ triAttr,
+                                                          uint32_t* __restrict__ tileCounts)
+{
+    for (uint32_t itemBase = blockIdx.x * blockDim.x; itemBase < totalTriangles; itemBase += gridDim.x * blockDim.x)
+    {
+        const uint32_t item = itemBase + threadIdx.x;
+        int32_t X[3] = {0, 0, 0}, Y[3] = {0, 0, 0};
+        bool stored = false;
+        if (item < totalTriangles)
+        {
+            uint32_t lo = 0, hi = batchCount;
+            while (hi - lo > 1)
+            {
+                uint32_t mid = (lo + hi) >> 1;
+                if (__ldg(&batches[mid].firstWorkItem) <= item)
+                    lo = mid;
+                else
+                    hi = mid;
+            }
+            const MeshBatchDev b = batches[lo];
+            const uint32_t t = item - b.firstWorkItem;
+            const uint8_t* inst = P.imageDrawInstances + static_cast<size_t>(b.instanceIndex) * 64;
+            const float4 view = __ldg(reinterpret_cast<const float4*>(inst));
+            const float4 tr = __ldg(reinterpret_cast<const float4*>(inst + 32));
+            float xs[3], ys[3], attr[12] = {};
+            bool ok = true;
+#pragma unroll
+            for (int k = 0; k < 3; ++k)
+            {
+                const uint32_t vi = __ldg(b.indices + b.baseIndex + t * 3 + k);
+                if (vi >= b.vertexCount)
+                {
+                    ok = false;
+                    xs[k] = ys[k] = 0.f;
+                    continue;
+                }
+                const float px = __ldg(b.positions + vi * 2), py = __ldg(b.positions + vi * 2 + 1);
+                xs[k] = view.x * px + view.z * py + tr.x;
+                ys[k] = view.y * px + view.w * py + tr.y;
+                attr[0 * 3 + k] = __ldg(b.uvs + vi * 2);
+                attr[1 * 3 + k] = __ldg(b.uvs + vi * 2 + 1);
+            }
+            if (!ok)
+                xs[0] = __int_as_float(0x7fc00000);
+            // Implicit LOD: the uv gradients are constant per triangle.
+            float lod = 0.f;
+            if (ok && b.texLevels > 1u)
+            {
+                const float ax = xs[1] - xs[0], ay = ys[1] - ys[0], bx = xs[2] - xs[0], by = ys[2] - ys[0];
+                const float d = ax * by - bx * ay;
+                if (d != 0.f)
+                {
+                    const float tw = static_cast<float>(b.texWidth), th = static_cast<float>(b.texHeight);
+                    const float au = (attr[1] - attr[0]) * tw, av = (attr[4] - attr[3]) * th;
+                    const float bu = (attr[2] - attr[0]) * tw, bv = (attr[5] - attr[3]) * th;
+                    const float dudx = (au * by - bu * ay) / d, dudy = (bu * ax - au * bx) / d;
+                    const float dvdx = (av * by - bv * ay) / d, dvdy = (bv * ax - av * bx) / d;
+                    const float rho = fmaxf(sqrtf(dudx * dudx + dvdx * dvdx), sqrtf(dudy * dudy + dvdy * dvdy));
+                    lod = rho > 0.f ? log2f(rho) : -1000.f;
+                }
+                lod += b.mipBias;
+            }
+            attr[6] = attr[7] = attr[8] = lod;
+            uint32_t meta = (kKindImageMesh << kMetaKindShift); // pathID 0: immediate entry
+            if ((b.flags & RIVECUDA_FEATURE_ADVANCED_BLEND) != 0u)
+                meta |= kMetaUnmultiplied;
+            if ((b.flags & RIVECUDA_FEATURE_CLIP_RECT) != 0u)
+                meta |= kMetaClipRect;
+            if ((b.flags & RIVECUDA_FEATURE_CLIPPING) != 0u)
+                meta |= kMetaClipping;
+            const uint32_t aux = (b.imageSlot & kAuxNoImage) | (b.instanceIndex << 12);
+            stored = store_triangle(P, triGeom, triAttr, X, Y, b.firstTriangle + t, xs, ys, attr, 3, meta, aux, /*cullCCW=*/false);
         }
         warp_for_each_tile(P, X, Y, stored, [&](uint32_t tile, int) { atomicAdd(tileCounts + tile, 1u); });
     }
@@ -1112,8 +1239,17 @@ int launch_draw_list(rivecuda_ctx* ctx, const rivecuda_flush_desc& desc, const r
 
     // Flatten the draw list into device batch tables: one for patch batches
     // (work item = instance) and one for triangle runs (work item = triangle).
+    // FlushUniforms::mipMapLODBias (gpu.hpp:1498-1535, float #20), from the mapped ring slot.
+    float mipBias = -.5f;
+    {
+        const BufferRing& ring = ctx->rings[RIVECUDA_BUFFER_FLUSH_UNIFORM];
+        if (ring.host[ring.current] != nullptr && desc.flush_uniform_data_offset_in_bytes + 84 <= ring.capacity)
+            memcpy(&mipBias, static_cast<const uint8_t*>(ring.host[ring.current]) + desc.flush_uniform_data_offset_in_bytes + 80, sizeof(float));
+    }
     std::vector<DeviceBatch> patchBatches, runBatches;
-    uint32_t rawTriangles = 0, patchInstances = 0, runTriangles = 0;
+    std::vector<MeshBatchDev> meshBatches;
+    std::vector<ImageSlot> imageSlots;
+    uint32_t rawTriangles = 0, patchInstances = 0, runTriangles = 0, meshTriangles = 0;
     for (uint32_t i = 0; i < batchCount; ++i)
     {
         const rivecuda_draw_batch& b = batches[i];
@@ -1125,8 +1261,18 @@ int launch_draw_list(rivecuda_ctx* ctx, const rivecuda_flush_desc& desc, const r
         d.baseElement = b.base_element;
         d.baseIndex = b.base_index;
         d.firstTriangle = rawTriangles;
-        d.imageSlot = ~0u;
+        d.imageSlot = kAuxNoImage;
         d.samplerKey = b.image_sampler;
+        if (b.image_texture != nullptr)
+        {
+            if (imageSlots.size() >= kAuxNoImage)
+                return set_error("rivecuda_flush: too many image bindings in one flush");
+            ImageSlot slot = {};
+            slot.texture = b.image_texture->dev;
+            slot.samplerKey = b.image_sampler;
+            d.imageSlot = static_cast<uint32_t>(imageSlots.size());
+            imageSlots.push_back(slot);
+        }
         switch (b.draw_type)
         {
             case RIVECUDA_DRAW_MIDPOINT_FAN_PATCHES:
@@ -1147,7 +1293,32 @@ int launch_draw_list(rivecuda_ctx* ctx, const rivecuda_flush_desc& desc, const r
                 runBatches.push_back(d);
                 break;
             case RIVECUDA_DRAW_IMAGE_MESH:
-                return set_error("rivecuda_flush: imageMesh draws are not implemented yet");
+            {
+                if (b.vertex_buffer == nullptr || b.uv_buffer == nullptr || b.index_buffer == nullptr || b.image_texture == nullptr)
+                    return set_error("rivecuda_flush: imageMesh batch without buffers / texture");
+                MeshBatchDev m = {};
+                m.positions = static_cast<const float*>(b.vertex_buffer->device);
+                m.uvs = static_cast<const float*>(b.uv_buffer->device);
+                m.indices = static_cast<const uint16_t*>(b.index_buffer->device);
+                m.vertexCount = static_cast<uint32_t>(std::min(b.vertex_buffer->size, b.uv_buffer->size) / 8);
+                m.indexCount = b.index_count_per_instance;
+                m.baseIndex = b.base_index;
+                m.instanceIndex = b.base_element;
+                m.firstTriangle = rawTriangles;
+                m.firstWorkItem = meshTriangles;
+                m.imageSlot = d.imageSlot;
+                m.flags = b.shader_features;
+                m.texWidth = b.image_texture->dev.width;
+                m.texHeight = b.image_texture->dev.height;
+                m.texLevels = b.image_texture->dev.levelCount;
+                m.mipBias = mipBias;
+                if (static_cast<size_t>(m.baseIndex + m.indexCount) * 2 > b.index_buffer->size)
+                    return set_error("rivecuda_flush: imageMesh index range beyond the index buffer");
+                meshTriangles += m.indexCount / 3;
+                rawTriangles += m.indexCount / 3;
+                meshBatches.push_back(m);
+                break;
+            }
             default:
                 return set_error("rivecuda_flush: draw type %u is not valid in rasterOrdering mode", b.draw_type);
         }
@@ -1173,8 +1344,23 @@ int launch_draw_list(rivecuda_ctx* ctx, const rivecuda_flush_desc& desc, const r
         triGeom = ctx->triGeom.as<TriGeom>();
         triAttr = ctx->triAttr.as<TriAttr>();
         const size_t tableBytes = (patchBatches.size() + runBatches.size()) * sizeof(DeviceBatch);
-        if (int s = ctx->batchTable.reserve(tableBytes))
+        if (int s = ctx->batchTable.reserve(tableBytes + 16))
             return s;
+        if (int s = ctx->imageTable.reserve(imageSlots.size() * sizeof(ImageSlot) + meshBatches.size() * sizeof(MeshBatchDev) + 16))
+            return s;
+        ImageSlot* devImages = ctx->imageTable.as<ImageSlot>();
+        MeshBatchDev* devMeshes = reinterpret_cast<MeshBatchDev*>(devImages + imageSlots.size());
+        if (!imageSlots.empty())
+            RC_CUDA(cudaMemcpyAsync(devImages, imageSlots.data(), imageSlots.size() * sizeof(ImageSlot), cudaMemcpyHostToDevice, stream));
+        if (!meshBatches.empty())
+            RC_CUDA(cudaMemcpyAsync(devMeshes, meshBatches.data(), meshBatches.size() * sizeof(MeshBatchDev), cudaMemcpyHostToDevice, stream));
+        P.images = devImages;
+        if (!imageSlots.empty())
+        {
+            if (int s = ctx->pathImageSlots.reserve((static_cast<size_t>(desc.path_count) + 2) * sizeof(uint16_t)))
+                return s;
+            P.pathImageSlots = ctx->pathImageSlots.as<uint16_t>();
+        }
         DeviceBatch* devPatch = ctx->batchTable.as<DeviceBatch>();
         DeviceBatch* devRuns = devPatch + patchBatches.size();
         if (!patchBatches.empty())
@@ -1198,6 +1384,16 @@ int launch_draw_list(rivecuda_ctx* ctx, const rivecuda_flush_desc& desc, const r
             ctx->lastLaunches += 1;
             RC_CUDA(cudaGetLastError());
         }
+    }
+
+    if (meshTriangles > 0)
+    {
+        const ImageSlot* devImages = ctx->imageTable.as<ImageSlot>();
+        const MeshBatchDev* devMeshes = reinterpret_cast<const MeshBatchDev*>(devImages + imageSlots.size());
+        const uint32_t blocks = std::min<uint32_t>((meshTriangles + 255) / 256, ctx->smCount * 8);
+        setup_meshes_kernel<<<blocks, 256, 0, stream>>>(P, devMeshes, static_cast<uint32_t>(meshBatches.size()), meshTriangles, ctx->triGeom.as<TriGeom>(), ctx->triAttr.as<TriAttr>(), tileCounts);
+        ctx->lastLaunches += 1;
+        RC_CUDA(cudaGetLastError());
     }
 
     // Exclusive scan of tile counts -> offsets, total -> pinned host word.
@@ -1430,19 +1626,10 @@ int launch_atlas(rivecuda_ctx* ctx,
         }
         if (totalTriangles == 0)
             continue;
-        DeviceBuffer& table = ctx->imageTable; // reused as scratch for the atlas batch table
-        if (int s = table.reserve(static_cast<size_t>(count) * sizeof(AtlasBatchDev) * 2))
+        // Both passes' tables live in one buffer: fills first, then strokes.
+        if (int s = ctx->atlasTable.reserve(static_cast<size_t>(fillCount + strokeCount) * sizeof(AtlasBatchDev)))
             return s;
-        AtlasBatchDev* dev = table.as<AtlasBatchDev>() + (pass == 0 ? 0 : count);
-        // Separate halves per pass would alias when counts differ; use a fresh
-        // offset computed from the fill count instead.
-        dev = table.as<AtlasBatchDev>();
-        if (pass == 1)
-        {
-            if (int s = ctx->scanScratch.reserve(static_cast<size_t>(count) * sizeof(AtlasBatchDev)))
-                return s;
-            dev = ctx->scanScratch.as<AtlasBatchDev>();
-        }
+        AtlasBatchDev* dev = ctx->atlasTable.as<AtlasBatchDev>() + (pass == 0 ? 0u : fillCount);
         RC_CUDA(cudaMemcpyAsync(dev, host.data(), static_cast<size_t>(count) * sizeof(AtlasBatchDev), cudaMemcpyHostToDevice, stream));
         const uint32_t blocks = std::min<uint32_t>((totalTriangles + 127) / 128, ctx->smCount * 16);
         atlas_kernel<<<blocks, 128, 0, stream>>>(P, dev, count, totalTriangles, ctx->atlas, ctx->atlasWidth, ctx->atlasHeight);

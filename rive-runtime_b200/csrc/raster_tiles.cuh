@@ -145,22 +145,24 @@ __device__ void prepare_triangle(const FlushParams& P,
     const double area2 = static_cast<double>(E0u[0] + E0u[1] + E0u[2]);
     const double inv = 1.0 / area2;
     const uint32_t kind = (g.meta >> kMetaKindShift) & 0xf;
-    const int comps = kind == kKindFill ? 1 : (kind == kKindFeatherFill ? 4 : 2);
+    const int comps = kind == kKindFill ? 1 : (kind == kKindFeatherFill ? 4 : (kind == kKindImageMesh ? 3 : 2));
     const float* attr = attrPtr->attr;
     bool flat = kind == kKindFill;
     for (int c = 0; c < comps; ++c)
     {
         float* plane = c == 0 ? out.plane0 : (c == 1 ? out.plane1 : (c == 2 ? out.plane2 : out.plane3));
         const float f0 = attr[c * 3 + 0], f1 = attr[c * 3 + 1], f2 = attr[c * 3 + 2];
-        if (c == 0 && flat && f0 == f1 && f1 == f2)
+        if (f0 == f1 && f1 == f2)
         {
-            // Constant coverage (fan / interior triangles): exact, no gradient.
+            // Constant attribute (fan / interior triangle coverage, a mesh
+            // triangle's LOD): exact, no gradient.
             plane[0] = f0;
             plane[1] = 0.f;
             plane[2] = 0.f;
             continue;
         }
-        flat = false;
+        if (c == 0)
+            flat = false;
         const double c0 = f0, c1 = f1, c2 = f2;
         plane[0] = static_cast<float>((c0 * static_cast<double>(E0u[0]) + c1 * static_cast<double>(E0u[1]) + c2 * static_cast<double>(E0u[2])) * inv);
         plane[1] = static_cast<float>((c0 * static_cast<double>(A[0]) + c1 * static_cast<double>(A[1]) + c2 * static_cast<double>(A[2])) * 256.0 * inv);
@@ -394,19 +396,86 @@ __device__ __forceinline__ uint32_t pack_rgba8_fast(float r, float g, float b, f
     return ur | (ug << 8) | (ub << 16) | (ua << 24);
 }
 
-// clip-rect coverage (common.glsl:376-400 + draw_raster_order_path.frag:149-156)
-__device__ float clip_rect_coverage(const FlushParams& P, uint32_t pathID, float fragX, float fragY)
+// clip-rect coverage (common.glsl:376-400 + draw_raster_order_path.frag:149-156):
+// the smallest of the four edge distances, for clipRectInverseMatrix m and
+// translate (tx, ty).
+__device__ __forceinline__ float clip_rect_distance(float4 m, float tx, float ty, float fragX, float fragY)
 {
-    const float4 m = __ldg(P.paintAuxBuffer + pathID * 8u + 2u);
-    const float4 tr = __ldg(P.paintAuxBuffer + pathID * 8u + 3u);
     const float wx = fabsf(m.x) + fabsf(m.z), wy = fabsf(m.y) + fabsf(m.w);
     if (wx != 0.f && wy != 0.f)
     {
         const float rx = 1.f / wx, ry = 1.f / wy;
-        const float cx = m.x * fragX + m.z * fragY + tr.x, cy = m.y * fragX + m.w * fragY + tr.y;
+        const float cx = m.x * fragX + m.z * fragY + tx, cy = m.y * fragX + m.w * fragY + ty;
         return fminf(fminf(cx * rx + rx + .5f, cy * ry + ry + .5f), fminf(-cx * rx + rx + .5f, -cy * ry + ry + .5f));
     }
-    return fminf(tr.x, tr.y);
+    return fminf(tx, ty);
+}
+
+__device__ float clip_rect_coverage(const FlushParams& P, uint32_t pathID, float fragX, float fragY)
+{
+    const float4 m = __ldg(P.paintAuxBuffer + pathID * 8u + 2u);
+    const float4 tr = __ldg(P.paintAuxBuffer + pathID * 8u + 3u);
+    return clip_rect_distance(m, tr.x, tr.y, fragX, fragY);
+}
+
+// ---- image sampling (VkSampler: {linear,nearest} x {clamp,repeat,mirror}^2,
+// mipmapMode NEAREST; pipeline_manager_vulkan.cpp:12-21) ----
+
+__device__ __forceinline__ int wrap_coord(int i, int size, uint32_t wrap)
+{
+    if (wrap == 1u) // repeat
+    {
+        const int m = i % size;
+        return m < 0 ? m + size : m;
+    }
+    if (wrap == 2u) // mirrored repeat
+    {
+        const int period = 2 * size;
+        int m = i % period;
+        if (m < 0)
+            m += period;
+        return m < size ? m : period - 1 - m;
+    }
+    return min(max(i, 0), size - 1);
+}
+
+__device__ float4 sample_image(const ImageSlot* __restrict__ img, float u, float v, float lod)
+{
+    const uint32_t levelCount = __ldg(&img->texture.levelCount);
+    if (levelCount == 0u || !(u == u) || !(v == v))
+        return make_float4(0.f, 0.f, 0.f, 0.f);
+    const uint32_t samplerKey = __ldg(&img->samplerKey);
+    const uint32_t wrapX = samplerKey % 3u, wrapY = (samplerKey / 3u) % 3u, filter = samplerKey / 9u;
+    int level = static_cast<int>(floorf(clampf(lod, 0.f, static_cast<float>(levelCount - 1u)) + .5f));
+    level = min(max(level, 0), static_cast<int>(levelCount) - 1);
+    const int w = max(static_cast<int>(__ldg(&img->texture.width) >> level), 1);
+    const int h = max(static_cast<int>(__ldg(&img->texture.height) >> level), 1);
+    const uint32_t* base = reinterpret_cast<const uint32_t*>(img->texture.levels[level]);
+    auto fetch = [&](int x, int y) {
+        x = wrap_coord(x, w, wrapX);
+        y = wrap_coord(y, h, wrapY);
+        return unpack_rgba8(__ldg(base + static_cast<size_t>(y) * w + x));
+    };
+    u = clampf(u, -65536.f, 65536.f);
+    v = clampf(v, -65536.f, 65536.f);
+    const float fw = static_cast<float>(w), fh = static_cast<float>(h);
+    if (filter == 1u)
+        return fetch(static_cast<int>(floorf(u * fw)), static_cast<int>(floorf(v * fh)));
+    const float x = u * fw - .5f, y = v * fh - .5f;
+    const float fx = floorf(x), fy = floorf(y);
+    const float tx = x - fx, ty = y - fy;
+    const int ix = static_cast<int>(fx), iy = static_cast<int>(fy);
+    const float4 c00 = fetch(ix, iy), c10 = fetch(ix + 1, iy), c01 = fetch(ix, iy + 1), c11 = fetch(ix + 1, iy + 1);
+    const float4 top = make_float4(c00.x + (c10.x - c00.x) * tx, c00.y + (c10.y - c00.y) * tx, c00.z + (c10.z - c00.z) * tx, c00.w + (c10.w - c00.w) * tx);
+    const float4 bot = make_float4(c01.x + (c11.x - c01.x) * tx, c01.y + (c11.y - c01.y) * tx, c01.z + (c11.z - c01.z) * tx, c01.w + (c11.w - c01.w) * tx);
+    return make_float4(top.x + (bot.x - top.x) * ty, top.y + (bot.y - top.y) * ty, top.z + (bot.z - top.z) * ty, top.w + (bot.w - top.w) * ty);
+}
+
+// common.glsl:210-216
+__device__ __forceinline__ float4 unmultiply_rgb(float4 premul)
+{
+    const float inv = premul.w != 0.f ? 1.f / premul.w : 0.f;
+    return make_float4(premul.x * inv, premul.y * inv, premul.z * inv, premul.w);
 }
 
 // find_paint_color (draw_path.vert:431-506) with the same operation order as the
@@ -415,15 +484,16 @@ __device__ float clip_rect_coverage(const FlushParams& P, uint32_t pathID, float
 // stage's v_paint for solid colours. Returns colour with coverage applied:
 // premultiplied unless the batch generates unmultiplied paints.
 __device__ __forceinline__ float4 paint_color(const FlushParams& P,
-                                              uint32_t pathID,
+                                              uint32_t meta,
                                               uint32_t paintX,
                                               uint32_t paintY,
                                               float4 solid,
-                                              bool unmultiplied,
                                               float coverage,
                                               float fragX,
                                               float fragY)
 {
+    const uint32_t pathID = meta & 0xffffu;
+    const bool unmultiplied = (meta & kMetaUnmultiplied) != 0u;
     const uint32_t paintType = paintX & 0xfu;
     float4 color;
     if (paintType == kPaintTypeSolid)
@@ -440,22 +510,48 @@ __device__ __forceinline__ float4 paint_color(const FlushParams& P,
             color.z *= coverage;
             color.w *= coverage;
         }
-        return color;
     }
-    const float4 pm = __ldg(P.paintAuxBuffer + pathID * 8u);
-    const float4 pt = __ldg(P.paintAuxBuffer + pathID * 8u + 1u);
-    const float cx = pm.x * fragX + pm.z * fragY + pt.x;
-    const float cy = pm.y * fragX + pm.w * fragY + pt.y;
-    float t = paintType == kPaintTypeLinear ? cx : sqrtf(cx * cx + cy * cy);
-    t = clamp01(t);
-    const float x = pt.z > .9f ? (1.f - 1.f / 512.f) * t + (.5f / 512.f) : (1.f / 512.f) * t + pt.w;
-    color = sample_grad(P, x, __uint_as_float(paintY));
-    color.w *= coverage;
-    if (!unmultiplied)
+    else
     {
-        color.x *= color.w;
-        color.y *= color.w;
-        color.z *= color.w;
+        const float4 pm = __ldg(P.paintAuxBuffer + pathID * 8u);
+        const float4 pt = __ldg(P.paintAuxBuffer + pathID * 8u + 1u);
+        const float cx = pm.x * fragX + pm.z * fragY + pt.x;
+        const float cy = pm.y * fragX + pm.w * fragY + pt.y;
+        float t = paintType == kPaintTypeLinear ? cx : sqrtf(cx * cx + cy * cy);
+        t = clamp01(t);
+        const float x = pt.z > .9f ? (1.f - 1.f / 512.f) * t + (.5f / 512.f) : (1.f / 512.f) * t + pt.w;
+        color = sample_grad(P, x, __uint_as_float(paintY));
+        color.w *= coverage;
+        if (!unmultiplied)
+        {
+            color.x *= color.w;
+            color.y *= color.w;
+            color.z *= color.w;
+        }
+    }
+    // Image paints: the paint colour modulates the image (draw_path.vert:343-357,
+    // 485-502). The LOD is constant per path and comes from the host.
+    if ((meta & kMetaModulatedImage) != 0u && (paintX & kPaintFlagImage) != 0u)
+    {
+        const float4 im = __ldg(P.paintAuxBuffer + pathID * 8u + 4u);
+        const float4 it = __ldg(P.paintAuxBuffer + pathID * 8u + 5u);
+        const float imageZ = 1.f + it.z;
+        if (imageZ > 0.f)
+        {
+            const float u = im.x * fragX + im.z * fragY + it.x;
+            const float v = im.y * fragX + im.w * fragY + it.y;
+            float4 imageColor = sample_image(P.images + __ldg(P.pathImageSlots + pathID), u, v, imageZ - 1.f);
+#ifdef RIVECUDA_DEBUG
+            if (static_cast<int>(fragX) == P.debugX && static_cast<int>(fragY) == P.debugY)
+                printf("[cuda] image pathID=%u slot=%u uv=(%.9g,%.9g) lod=%.9g -> (%.9g,%.9g,%.9g,%.9g) coverage=%.9g\n", pathID, static_cast<uint32_t>(__ldg(P.pathImageSlots + pathID)), u, v, imageZ - 1.f, imageColor.x, imageColor.y, imageColor.z, imageColor.w, coverage);
+#endif
+            if (unmultiplied)
+                imageColor = unmultiply_rgb(imageColor);
+            color.x *= imageColor.x;
+            color.y *= imageColor.y;
+            color.z *= imageColor.z;
+            color.w *= imageColor.w;
+        }
     }
     return color;
 }
@@ -509,7 +605,7 @@ __device__ __forceinline__ void resolve_path(const FlushParams& P,
     if ((paintX & kPaintFlagClipRect) != 0u)
         coverage = clampf(clip_rect_coverage(P, pathID, fragX, fragY), 0.f, coverage);
     const bool unmultiplied = (meta & kMetaUnmultiplied) != 0u;
-    float4 color = paint_color(P, pathID, paintX, paintY, solid, unmultiplied, coverage, fragX, fragY);
+    float4 color = paint_color(P, meta, paintX, paintY, solid, coverage, fragX, fragY);
     const float4 dst = unpack_rgba8(s.color);
     if (unmultiplied)
     {
@@ -535,24 +631,15 @@ __device__ __forceinline__ void resolve_path(const FlushParams& P,
     s.color = pack_rgba8_fast(r, g, b, outA);
 }
 
-// Immediate-mode blend for atlas blits (draw_mesh.frag, @FEATHER_ATLAS_BLIT).
-__device__ void resolve_atlas_blit(const FlushParams& P, uint32_t meta, uint32_t paintX, uint32_t paintY, float4 solid, float u, float v, int px, int py, PixelState& s)
+// draw_mesh.frag:147-234: blend `color` (paint or image colour, before coverage)
+// into the colour plane immediately.
+__device__ __forceinline__ void blend_mesh_fragment(float4 color, float coverage, bool unmultiplied, bool isImageMesh, uint32_t blendMode, PixelState& s)
 {
-    const uint32_t pathID = meta & 0xffffu;
-    float coverage = clamp01(sample_atlas(P, u, v));
-    const float fragX = px + .5f, fragY = py + .5f;
-    if ((paintX & kPaintFlagClipRect) != 0u)
-        coverage = fminf(fmaxf(clip_rect_coverage(P, pathID, fragX, fragY), 0.f), coverage);
-    const uint32_t clipID = paintX >> 16;
-    if (clipID != 0u)
-        coverage = fminf(coverage, fmaxf(s.clipID == clipID ? s.clipCoverage : 0.f, 0.f));
-    // draw_mesh.frag: find_paint_color(v_paint, 1.) then blend with `coverage`.
-    const bool unmultiplied = (meta & kMetaUnmultiplied) != 0u;
-    float4 color = paint_color(P, pathID, paintX, paintY, solid, unmultiplied, 1.f, fragX, fragY);
     const float4 dst = unpack_rgba8(s.color);
     if (unmultiplied)
     {
-        const uint32_t blendMode = (paintX >> 4) & 0xfu;
+        if (isImageMesh)
+            color = unmultiply_rgb(color);
         if (blendMode != 0u)
         {
             const float3 rgb = advanced_color_blend(make_float3(color.x, color.y, color.z), dst, blendMode);
@@ -578,6 +665,44 @@ __device__ void resolve_atlas_blit(const FlushParams& P, uint32_t meta, uint32_t
                               dst.y * oneMinusA + (color.y + dither),
                               dst.z * oneMinusA + (color.z + dither),
                               dst.w * oneMinusA + color.w);
+}
+
+// Immediate-mode blend for atlas blits (draw_mesh.frag, @FEATHER_ATLAS_BLIT).
+__device__ void resolve_atlas_blit(const FlushParams& P, uint32_t meta, uint32_t paintX, uint32_t paintY, float4 solid, float u, float v, int px, int py, PixelState& s)
+{
+    const uint32_t pathID = meta & 0xffffu;
+    float coverage = clamp01(sample_atlas(P, u, v));
+    const float fragX = px + .5f, fragY = py + .5f;
+    if ((paintX & kPaintFlagClipRect) != 0u)
+        coverage = fminf(fmaxf(clip_rect_coverage(P, pathID, fragX, fragY), 0.f), coverage);
+    const uint32_t clipID = paintX >> 16;
+    if (clipID != 0u)
+        coverage = fminf(coverage, fmaxf(s.clipID == clipID ? s.clipCoverage : 0.f, 0.f));
+    // draw_mesh.frag: find_paint_color(v_paint, 1.) then blend with `coverage`.
+    const float4 color = paint_color(P, meta, paintX, paintY, solid, 1.f, fragX, fragY);
+    blend_mesh_fragment(color, coverage, (meta & kMetaUnmultiplied) != 0u, false, (paintX >> 4) & 0xfu, s);
+}
+
+// Image meshes (draw_image_mesh.vert + draw_mesh.frag @DRAW_IMAGE_MESH): every
+// fragment blends immediately, in primitive order.
+__device__ void resolve_image_mesh(const FlushParams& P, uint32_t meta, uint32_t aux, float u, float v, float lod, int px, int py, PixelState& s)
+{
+    const uint8_t* inst = P.imageDrawInstances + static_cast<size_t>(aux >> 12) * 64;
+    const uint4 packed = __ldg(reinterpret_cast<const uint4*>(inst + 48));
+    const float fragX = px + .5f, fragY = py + .5f;
+    float coverage = 1.f;
+    if ((meta & kMetaClipRect) != 0u)
+    {
+        const float4 m = __ldg(reinterpret_cast<const float4*>(inst + 16));
+        const float4 tr = __ldg(reinterpret_cast<const float4*>(inst + 32));
+        coverage = fminf(fmaxf(clip_rect_distance(m, tr.z, tr.w, fragX, fragY), 0.f), coverage);
+    }
+    const uint32_t clipID = packed.y;
+    if ((meta & kMetaClipping) != 0u && clipID != 0u)
+        coverage = fminf(coverage, fmaxf(s.clipID == clipID ? s.clipCoverage : 0.f, 0.f));
+    coverage *= __uint_as_float(packed.x); // opacity
+    const float4 color = sample_image(P.images + (aux & kAuxNoImage), u, v, lod);
+    blend_mesh_fragment(color, coverage, (meta & kMetaUnmultiplied) != 0u, true, packed.z, s);
 }
 
 __global__ void __launch_bounds__(256, 4) raster_tiles_kernel(FlushParams P,
@@ -615,7 +740,7 @@ __global__ void __launch_bounds__(256, 4) raster_tiles_kernel(FlushParams P,
     const uint32_t* list = entries + tileOffsets[tile];
 
     // Per-warp path accumulation state (the warp's pixels only).
-    uint32_t curPath = 0u, curMeta = 0u, curPaintX = 0u, curPaintY = 0u;
+    uint32_t curPath = ~0u, curMeta = 0u, curPaintX = 0u, curPaintY = 0u;
     float4 curSolid = make_float4(0.f, 0.f, 0.f, 0.f);
     float coverageCount = 0.f; // what the last fragment computed (fp32, as the shader sees it)
     float coverageStored = 0.f; // what it wrote back to the fp16 coverage plane
@@ -724,6 +849,11 @@ __global__ void __launch_bounds__(256, 4) raster_tiles_kernel(FlushParams P,
                         break;
                     case kKindAtlasBlit:
                         resolve_atlas_blit(P, curMeta, curPaintX, curPaintY, curSolid, c0, c1, px, py, s);
+                        break;
+                    case kKindImageMesh:
+                        // Consecutive meshes share "path" 0, so the flags come
+                        // from the triangle itself.
+                        resolve_image_mesh(P, T.meta, T.aux, c0, c1, T.plane2[0], px, py, s);
                         break;
                     default:
                         break;
