@@ -64,6 +64,8 @@ constexpr uint32_t kMetaUnmultiplied = 1u << 29; // batch has ENABLE_ADVANCED_BL
 constexpr uint32_t kMetaModulatedImage = 1u << 28; // batch has ENABLE_MODULATED_IMAGE and binds a texture
 constexpr uint32_t kMetaClipRect = 1u << 27;       // image meshes: batch has ENABLE_CLIP_RECT
 constexpr uint32_t kMetaClipping = 1u << 26;       // image meshes: batch has ENABLE_CLIPPING
+constexpr uint32_t kMetaSimplePaint = 1u << 25;    // set by the rasteriser's prepare step, never stored
+constexpr uint32_t kMetaSmallMasks = 1u << 24;     // likewise: the Prepared record holds pixel masks, not edges
 constexpr uint32_t kMetaKindShift = 16;
 
 struct TriGeom // 32 B
@@ -539,12 +541,13 @@ template <typename Fn> __device__ __forceinline__ void for_each_tile(const Flush
 // a triangle). Triangles that overlap only a few tiles are walked by their own
 // lane; larger ones are broadcast one at a time and their tile range is tested
 // by all 32 lanes in parallel, so a full-screen triangle costs tiles/32
-// iterations instead of stalling one lane. fn(tile, ownerLane) is invoked by
-// whichever lane found the overlap; ownerLane says whose triangle it is.
+// iterations instead of stalling one lane. fn(tile, ownerLane, cooperative) is
+// invoked by whichever lane found the overlap; ownerLane says whose triangle it
+// is. Returns whether the calling lane's own triangle took the cooperative route.
 constexpr int kSmallTileCount = 4;
 
 template <typename Fn>
-__device__ __forceinline__ void warp_for_each_tile(const FlushParams& P, const int32_t X[3], const int32_t Y[3], bool valid, Fn&& fn)
+__device__ __forceinline__ bool warp_for_each_tile(const FlushParams& P, const int32_t X[3], const int32_t Y[3], bool valid, Fn&& fn)
 {
     const int lane = threadIdx.x & 31;
     TileRange r;
@@ -563,7 +566,7 @@ __device__ __forceinline__ void warp_for_each_tile(const FlushParams& P, const i
         for (int ty = r.ty0; ty <= r.ty1; ++ty)
             for (int tx = r.tx0; tx <= r.tx1; ++tx)
                 if (count == 1 || tile_overlaps(E, tx + P.tileX0, ty + P.tileY0))
-                    fn(static_cast<uint32_t>(ty) * P.tilesX + static_cast<uint32_t>(tx), lane);
+                    fn(static_cast<uint32_t>(ty) * P.tilesX + static_cast<uint32_t>(tx), lane, false);
     }
     uint32_t big = __ballot_sync(0xffffffffu, count > kSmallTileCount);
     while (big != 0u)
@@ -585,9 +588,44 @@ __device__ __forceinline__ void warp_for_each_tile(const FlushParams& P, const i
         {
             const int ty = ty0 + idx / bw, tx = tx0 + idx % bw;
             if (tile_overlaps(E, tx + P.tileX0, ty + P.tileY0))
-                fn(static_cast<uint32_t>(ty) * P.tilesX + static_cast<uint32_t>(tx), src);
+                fn(static_cast<uint32_t>(ty) * P.tilesX + static_cast<uint32_t>(tx), src, true);
         }
     }
+    return count > kSmallTileCount;
+}
+
+// Tile binning, pass 1 (inside the setup kernels). Every lane calls this with its
+// triangle (stored = it survived). A triangle that overlaps at most
+// kSmallTileCount tiles claims its slot in each tile's list right here -- the
+// atomicAdd that counts the tile also hands out the rank -- and records the
+// (tile, rank) pairs, so pass 2 is a plain copy. Larger triangles only count;
+// pass 2 re-walks their tile range cooperatively.
+struct BinTables
+{
+    uint32_t* smallCounts; // per tile: entries with a pre-assigned rank
+    uint32_t* bigCounts;   // per tile: entries appended after them by pass 2
+    uint8_t* binCount;     // per raw triangle: 0 none, 1..kSmallTileCount inline pairs, kBinBig
+    uint2* binPairs;       // per raw triangle: kSmallTileCount x (tile, rank)
+};
+constexpr uint8_t kBinBig = 0xff;
+
+__device__ __forceinline__ void bin_triangle(const FlushParams& P, const BinTables& B, const int32_t X[3], const int32_t Y[3], bool stored, bool hasSlot, uint32_t rawTri)
+{
+    uint32_t n = 0;
+    const bool big = warp_for_each_tile(P, X, Y, stored, [&](uint32_t tile, int, bool cooperative) {
+        if (cooperative)
+        {
+            atomicAdd(B.bigCounts + tile, 1u);
+        }
+        else
+        {
+            const uint32_t rank = atomicAdd(B.smallCounts + tile, 1u);
+            B.binPairs[static_cast<size_t>(rawTri) * kSmallTileCount + n] = make_uint2(tile, rank);
+            ++n;
+        }
+    });
+    if (hasSlot)
+        B.binCount[rawTri] = big ? kBinBig : static_cast<uint8_t>(n);
 }
 
 // Per-batch bits of TriGeom::meta.
@@ -660,15 +698,11 @@ __device__ __forceinline__ bool store_triangle(const FlushParams& P,
         if (r.tx0 > r.tx1)
             ok = false;
     }
-    TriGeom g;
+    // Culled / discarded triangles leave no record: nothing reads a raw triangle
+    // slot that no tile list references.
     if (!ok)
-    {
-        g.x0 = g.y0 = g.x1 = g.y1 = g.x2 = g.y2 = 0;
-        g.meta = 0;
-        g.aux = 0;
-        triGeom[rawTri] = g;
         return false;
-    }
+    TriGeom g;
     g.x0 = X[0];
     g.y0 = Y[0];
     g.x1 = X[1];
@@ -714,7 +748,7 @@ __global__ void __launch_bounds__(kSetupWarpsPerBlock * 32) setup_patches_kernel
                                                                                 uint32_t totalInstances,
                                                                                 TriGeom* __restrict__ triGeom,
                                                                                 TriAttr* __restrict__ triAttr,
-                                                                                uint32_t* __restrict__ tileCounts)
+                                                                                BinTables bins)
 {
     __shared__ ShadedVertex s_verts[kSetupWarpsPerBlock][kMaxPatchVertices];
     const int lane = threadIdx.x & 31;
@@ -755,9 +789,9 @@ __global__ void __launch_bounds__(kSetupWarpsPerBlock * 32) setup_patches_kernel
             const uint32_t t = tbase + lane;
             int32_t X[3] = {0, 0, 0}, Y[3] = {0, 0, 0};
             bool stored = false;
+            const uint32_t rawTri = b.firstTriangle + inst * tris + t;
             if (t < tris)
             {
-                const uint32_t rawTri = b.firstTriangle + inst * tris + t;
                 const uint32_t i0 = __ldg(P.patchIndices + b.baseIndex + t * 3 + 0) - vmin;
                 const uint32_t i1 = __ldg(P.patchIndices + b.baseIndex + t * 3 + 1) - vmin;
                 const uint32_t i2 = __ldg(P.patchIndices + b.baseIndex + t * 3 + 2) - vmin;
@@ -779,7 +813,7 @@ __global__ void __launch_bounds__(kSetupWarpsPerBlock * 32) setup_patches_kernel
                 if (stored && (meta & kMetaModulatedImage) != 0u)
                     P.pathImageSlots[pathID] = static_cast<uint16_t>(b.imageSlot);
             }
-            warp_for_each_tile(P, X, Y, stored, [&](uint32_t tile, int) { atomicAdd(tileCounts + tile, 1u); });
+            bin_triangle(P, bins, X, Y, stored, t < tris, rawTri);
         }
     }
 }
@@ -792,19 +826,20 @@ __global__ void __launch_bounds__(256) setup_triangle_runs_kernel(FlushParams P,
                                                                  uint32_t totalTriangles,
                                                                  TriGeom* __restrict__ triGeom,
                                                                  TriAttr* __restrict__ triAttr,
-                                                                 uint32_t* __restrict__ tileCounts)
+                                                                 BinTables bins)
 {
     for (uint32_t itemBase = blockIdx.x * blockDim.x; itemBase < totalTriangles; itemBase += gridDim.x * blockDim.x)
     {
         const uint32_t item = itemBase + threadIdx.x;
         int32_t X[3] = {0, 0, 0}, Y[3] = {0, 0, 0};
         bool stored = false;
+        uint32_t rawTri = 0;
         if (item < totalTriangles)
         {
         const uint32_t bi = find_batch(batches, batchCount, item);
         const DeviceBatch b = batches[bi];
         const uint32_t t = item - b.firstWorkItem;
-        const uint32_t rawTri = b.firstTriangle + t;
+        rawTri = b.firstTriangle + t;
         const bool atlasBlit = b.drawType == RIVECUDA_DRAW_FEATHER_ATLAS_BLIT;
         float xs[3], ys[3];
         float attr[12];
@@ -859,7 +894,7 @@ __global__ void __launch_bounds__(256) setup_triangle_runs_kernel(FlushParams P,
         if (stored && (meta & kMetaModulatedImage) != 0u)
             P.pathImageSlots[pathID] = static_cast<uint16_t>(b.imageSlot);
         }
-        warp_for_each_tile(P, X, Y, stored, [&](uint32_t tile, int) { atomicAdd(tileCounts + tile, 1u); });
+        bin_triangle(P, bins, X, Y, stored, item < totalTriangles, rawTri);
     }
 }
 
@@ -871,13 +906,14 @@ __global__ void __launch_bounds__(256) setup_meshes_kernel(FlushParams P,
                                                           uint32_t totalTriangles,
                                                           TriGeom* __restrict__ triGeom,
                                                           TriAttr* __restrict__ triAttr,
-                                                          uint32_t* __restrict__ tileCounts)
+                                                          BinTables bins)
 {
     for (uint32_t itemBase = blockIdx.x * blockDim.x; itemBase < totalTriangles; itemBase += gridDim.x * blockDim.x)
     {
         const uint32_t item = itemBase + threadIdx.x;
         int32_t X[3] = {0, 0, 0}, Y[3] = {0, 0, 0};
         bool stored = false;
+        uint32_t rawTri = 0;
         if (item < totalTriangles)
         {
             uint32_t lo = 0, hi = batchCount;
@@ -941,9 +977,10 @@ __global__ void __launch_bounds__(256) setup_meshes_kernel(FlushParams P,
             if ((b.flags & RIVECUDA_FEATURE_CLIPPING) != 0u)
                 meta |= kMetaClipping;
             const uint32_t aux = (b.imageSlot & kAuxNoImage) | (b.instanceIndex << 12);
-            stored = store_triangle(P, triGeom, triAttr, X, Y, b.firstTriangle + t, xs, ys, attr, 3, meta, aux, /*cullCCW=*/false);
+            rawTri = b.firstTriangle + t;
+            stored = store_triangle(P, triGeom, triAttr, X, Y, rawTri, xs, ys, attr, 3, meta, aux, /*cullCCW=*/false);
         }
-        warp_for_each_tile(P, X, Y, stored, [&](uint32_t tile, int) { atomicAdd(tileCounts + tile, 1u); });
+        bin_triangle(P, bins, X, Y, stored, item < totalTriangles, rawTri);
     }
 }
 
@@ -952,11 +989,11 @@ __global__ void __launch_bounds__(256) setup_meshes_kernel(FlushParams P,
 
 constexpr int kScanBlock = 1024;
 
-__global__ void __launch_bounds__(kScanBlock) scan_reduce_kernel(const uint32_t* __restrict__ counts, uint32_t n, uint32_t* __restrict__ blockSums)
+__global__ void __launch_bounds__(kScanBlock) scan_reduce_kernel(const uint32_t* __restrict__ countsA, const uint32_t* __restrict__ countsB, uint32_t n, uint32_t* __restrict__ blockSums)
 {
     __shared__ uint32_t s[32];
     const uint32_t i = blockIdx.x * kScanBlock + threadIdx.x;
-    uint32_t v = i < n ? counts[i] : 0u;
+    uint32_t v = i < n ? countsA[i] + countsB[i] : 0u;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1)
         v += __shfl_down_sync(0xffffffffu, v, o);
@@ -1012,15 +1049,17 @@ __global__ void __launch_bounds__(kScanBlock) scan_block_sums_kernel(uint32_t* _
         blockSums[threadIdx.x] = s[warp] + incl - v;
 }
 
-__global__ void __launch_bounds__(kScanBlock) scan_apply_kernel(const uint32_t* __restrict__ counts,
+__global__ void __launch_bounds__(kScanBlock) scan_apply_kernel(const uint32_t* __restrict__ countsA,
+                                                               const uint32_t* __restrict__ countsB,
                                                                uint32_t n,
                                                                const uint32_t* __restrict__ blockOffsets,
-                                                               uint32_t* __restrict__ offsets)
+                                                               uint32_t* __restrict__ offsets,
+                                                               uint32_t* __restrict__ totals)
 {
     __shared__ uint32_t s[32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t i = blockIdx.x * kScanBlock + threadIdx.x;
-    const uint32_t v = i < n ? counts[i] : 0u;
+    const uint32_t v = i < n ? countsA[i] + countsB[i] : 0u;
     uint32_t incl = v;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1)
@@ -1047,30 +1086,50 @@ __global__ void __launch_bounds__(kScanBlock) scan_apply_kernel(const uint32_t* 
     }
     __syncthreads();
     if (i < n)
+    {
         offsets[i] = blockOffsets[blockIdx.x] + s[warp] + incl - v;
+        totals[i] = v;
+    }
 }
 
 // ---------------------------------------------------------------------------
-// Scatter: append each valid triangle's id to the lists of the tiles it overlaps.
+// Tile binning, pass 2: write each triangle's id into its tiles' lists. Small
+// triangles copy the (tile, rank) pairs claimed in pass 1; big ones re-walk
+// their tile range (all 32 lanes per triangle) and append after the ranked
+// entries. The order inside a tile's list is arbitrary: it is sorted next.
 
 __global__ void __launch_bounds__(256) scatter_kernel(FlushParams P,
                                                       const TriGeom* __restrict__ triGeom,
                                                       uint32_t triCount,
+                                                      BinTables bins,
                                                       const uint32_t* __restrict__ tileOffsets,
-                                                      uint32_t* __restrict__ tileCursors,
+                                                      uint32_t* __restrict__ bigCursors,
                                                       uint32_t* __restrict__ entries,
                                                       uint32_t entryCapacity)
 {
     for (uint32_t tBase = blockIdx.x * blockDim.x; tBase < triCount; tBase += gridDim.x * blockDim.x)
     {
         const uint32_t t = tBase + threadIdx.x;
+        const uint32_t n = t < triCount ? bins.binCount[t] : 0u;
+        if (n != 0u && n != kBinBig)
+        {
+            const uint2* pairs = bins.binPairs + static_cast<size_t>(t) * kSmallTileCount;
+            for (uint32_t k = 0; k < n; ++k)
+            {
+                const uint2 pr = pairs[k];
+                const uint32_t pos = __ldg(tileOffsets + pr.x) + pr.y;
+                if (pos < entryCapacity)
+                    entries[pos] = t;
+            }
+        }
+        const bool big = n == kBinBig;
+        if (__ballot_sync(0xffffffffu, big) == 0u)
+            continue;
         int32_t X[3] = {0, 0, 0}, Y[3] = {0, 0, 0};
-        bool valid = false;
-        if (t < triCount)
+        if (big)
         {
             const uint4 lo = __ldg(reinterpret_cast<const uint4*>(triGeom + t));
-            const uint4 hi = __ldg(reinterpret_cast<const uint4*>(triGeom + t) + 1);
-            valid = (hi.z & kMetaValid) != 0u;
+            const uint2 hi = __ldg(reinterpret_cast<const uint2*>(triGeom + t) + 2);
             X[0] = static_cast<int32_t>(lo.x);
             Y[0] = static_cast<int32_t>(lo.y);
             X[1] = static_cast<int32_t>(lo.z);
@@ -1079,8 +1138,8 @@ __global__ void __launch_bounds__(256) scatter_kernel(FlushParams P,
             Y[2] = static_cast<int32_t>(hi.y);
         }
         const uint32_t warpBase = t - (threadIdx.x & 31);
-        warp_for_each_tile(P, X, Y, valid, [&](uint32_t tile, int ownerLane) {
-            const uint32_t pos = __ldg(tileOffsets + tile) + atomicAdd(tileCursors + tile, 1u);
+        warp_for_each_tile(P, X, Y, big, [&](uint32_t tile, int ownerLane, bool) {
+            const uint32_t pos = __ldg(tileOffsets + tile) + __ldg(bins.smallCounts + tile) + atomicAdd(bigCursors + tile, 1u);
             if (pos < entryCapacity)
                 entries[pos] = warpBase + static_cast<uint32_t>(ownerLane);
         });
@@ -1324,14 +1383,19 @@ int launch_draw_list(rivecuda_ctx* ctx, const rivecuda_flush_desc& desc, const r
         }
     }
 
-    if (int s = ctx->tileCounts.reserve(static_cast<size_t>(tileCount) * 2 * sizeof(uint32_t)))
+    // Per-tile counters: [0] ranked (small-triangle) entries, [1] big-triangle
+    // entries, [2] pass-2 cursors for the latter, [3] totals (written by the scan).
+    if (int s = ctx->tileCounts.reserve(static_cast<size_t>(tileCount) * 4 * sizeof(uint32_t)))
         return s;
     if (int s = ctx->tileOffsets.reserve(static_cast<size_t>(tileCount) * sizeof(uint32_t)))
         return s;
-    uint32_t* tileCounts = ctx->tileCounts.as<uint32_t>();
-    uint32_t* tileCursors = tileCounts + tileCount;
+    uint32_t* smallCounts = ctx->tileCounts.as<uint32_t>();
+    uint32_t* bigCounts = smallCounts + tileCount;
+    uint32_t* bigCursors = bigCounts + tileCount;
+    uint32_t* tileCounts = bigCursors + tileCount;
     uint32_t* tileOffsets = ctx->tileOffsets.as<uint32_t>();
-    RC_CUDA(cudaMemsetAsync(tileCounts, 0, static_cast<size_t>(tileCount) * 2 * sizeof(uint32_t), stream));
+    RC_CUDA(cudaMemsetAsync(smallCounts, 0, static_cast<size_t>(tileCount) * 3 * sizeof(uint32_t), stream));
+    BinTables bins = {smallCounts, bigCounts, nullptr, nullptr};
 
     TriGeom* triGeom = nullptr;
     TriAttr* triAttr = nullptr;
@@ -1341,8 +1405,14 @@ int launch_draw_list(rivecuda_ctx* ctx, const rivecuda_flush_desc& desc, const r
             return s;
         if (int s = ctx->triAttr.reserve(static_cast<size_t>(rawTriangles) * sizeof(TriAttr)))
             return s;
+        if (int s = ctx->binCount.reserve(static_cast<size_t>(rawTriangles)))
+            return s;
+        if (int s = ctx->binPairs.reserve(static_cast<size_t>(rawTriangles) * kSmallTileCount * sizeof(uint2)))
+            return s;
         triGeom = ctx->triGeom.as<TriGeom>();
         triAttr = ctx->triAttr.as<TriAttr>();
+        bins.binCount = ctx->binCount.as<uint8_t>();
+        bins.binPairs = ctx->binPairs.as<uint2>();
         const size_t tableBytes = (patchBatches.size() + runBatches.size()) * sizeof(DeviceBatch);
         if (int s = ctx->batchTable.reserve(tableBytes + 16))
             return s;
@@ -1373,14 +1443,14 @@ int launch_draw_list(rivecuda_ctx* ctx, const rivecuda_flush_desc& desc, const r
         if (patchInstances > 0)
         {
             const uint32_t blocks = std::min<uint32_t>((patchInstances + kSetupWarpsPerBlock - 1) / kSetupWarpsPerBlock, ctx->smCount * 16);
-            setup_patches_kernel<<<blocks, kSetupWarpsPerBlock * 32, 0, stream>>>(P, devPatch, static_cast<uint32_t>(patchBatches.size()), patchInstances, triGeom, triAttr, tileCounts);
+            setup_patches_kernel<<<blocks, kSetupWarpsPerBlock * 32, 0, stream>>>(P, devPatch, static_cast<uint32_t>(patchBatches.size()), patchInstances, triGeom, triAttr, bins);
             ctx->lastLaunches += 1;
             RC_CUDA(cudaGetLastError());
         }
         if (runTriangles > 0)
         {
             const uint32_t blocks = std::min<uint32_t>((runTriangles + 255) / 256, ctx->smCount * 8);
-            setup_triangle_runs_kernel<<<blocks, 256, 0, stream>>>(P, devRuns, static_cast<uint32_t>(runBatches.size()), runTriangles, triGeom, triAttr, tileCounts);
+            setup_triangle_runs_kernel<<<blocks, 256, 0, stream>>>(P, devRuns, static_cast<uint32_t>(runBatches.size()), runTriangles, triGeom, triAttr, bins);
             ctx->lastLaunches += 1;
             RC_CUDA(cudaGetLastError());
         }
@@ -1391,7 +1461,7 @@ int launch_draw_list(rivecuda_ctx* ctx, const rivecuda_flush_desc& desc, const r
         const ImageSlot* devImages = ctx->imageTable.as<ImageSlot>();
         const MeshBatchDev* devMeshes = reinterpret_cast<const MeshBatchDev*>(devImages + imageSlots.size());
         const uint32_t blocks = std::min<uint32_t>((meshTriangles + 255) / 256, ctx->smCount * 8);
-        setup_meshes_kernel<<<blocks, 256, 0, stream>>>(P, devMeshes, static_cast<uint32_t>(meshBatches.size()), meshTriangles, ctx->triGeom.as<TriGeom>(), ctx->triAttr.as<TriAttr>(), tileCounts);
+        setup_meshes_kernel<<<blocks, 256, 0, stream>>>(P, devMeshes, static_cast<uint32_t>(meshBatches.size()), meshTriangles, ctx->triGeom.as<TriGeom>(), ctx->triAttr.as<TriAttr>(), bins);
         ctx->lastLaunches += 1;
         RC_CUDA(cudaGetLastError());
     }
@@ -1404,9 +1474,9 @@ int launch_draw_list(rivecuda_ctx* ctx, const rivecuda_flush_desc& desc, const r
         return s;
     uint32_t* blockSums = ctx->scanScratch.as<uint32_t>();
     uint32_t* total = blockSums + scanBlocks;
-    scan_reduce_kernel<<<scanBlocks, kScanBlock, 0, stream>>>(tileCounts, tileCount, blockSums);
+    scan_reduce_kernel<<<scanBlocks, kScanBlock, 0, stream>>>(smallCounts, bigCounts, tileCount, blockSums);
     scan_block_sums_kernel<<<1, kScanBlock, 0, stream>>>(blockSums, scanBlocks, total);
-    scan_apply_kernel<<<scanBlocks, kScanBlock, 0, stream>>>(tileCounts, tileCount, blockSums, tileOffsets);
+    scan_apply_kernel<<<scanBlocks, kScanBlock, 0, stream>>>(smallCounts, bigCounts, tileCount, blockSums, tileOffsets, tileCounts);
     ctx->lastLaunches += 3;
     RC_CUDA(cudaGetLastError());
     RC_CUDA(cudaMemcpyAsync(ctx->pinnedTotals, total, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
@@ -1421,15 +1491,32 @@ int launch_draw_list(rivecuda_ctx* ctx, const rivecuda_flush_desc& desc, const r
     if (entryCount > 0)
     {
         const uint32_t blocks = std::min<uint32_t>((rawTriangles + 255) / 256, ctx->smCount * 16);
-        scatter_kernel<<<blocks, 256, 0, stream>>>(P, triGeom, rawTriangles, tileOffsets, tileCursors, entries, entryCount);
+        scatter_kernel<<<blocks, 256, 0, stream>>>(P, triGeom, rawTriangles, bins, tileOffsets, bigCursors, entries, entryCount);
         sort_tiles_kernel<<<tileCount, 256, 0, stream>>>(tileOffsets, tileCounts, entries);
         ctx->lastLaunches += 2;
         RC_CUDA(cudaGetLastError());
     }
     if (ctx->profiling)
         RC_CUDA(cudaEventRecord(ctx->events[5], stream));
+#ifdef RIVECUDA_STATS
+    {
+        unsigned long long zero[32] = {};
+        cudaMemcpyToSymbol(g_rasterStats, zero, sizeof(zero));
+    }
+#endif
     raster_tiles_kernel<<<tileCount, 256, 0, stream>>>(P, triGeom, triAttr, tileOffsets, tileCounts, entries);
     ctx->lastLaunches += 1;
+#ifdef RIVECUDA_STATS
+    {
+        unsigned long long st[32];
+        cudaStreamSynchronize(stream);
+        cudaMemcpyFromSymbol(st, g_rasterStats, sizeof(st));
+        const char* names[3] = {"border", "inner-fan", "midpoint-fan"};
+        for (int c = 0; c < 3; ++c)
+            fprintf(stderr, "[stats] %-12s entries %llu visits %llu fast %llu hit %llu lanes-inside %llu\n", names[c], st[c * 8], st[c * 8 + 1], st[c * 8 + 2], st[c * 8 + 3], st[c * 8 + 4]);
+        fprintf(stderr, "[stats] warp resolves %llu lanes with coverage %llu\n", st[30], st[31]);
+    }
+#endif
     return check_cuda(cudaGetLastError(), "raster_tiles_kernel");
 }
 } // namespace rivecuda

@@ -43,6 +43,23 @@ static_assert(sizeof(Prepared) == 128, "Prepared");
 
 constexpr int kRasterChunk = 256;
 
+#ifdef RIVECUDA_STATS
+// Work counters of the raster kernel (dev tool: `make stats`; printed per flush).
+// [class*8 + k], class = raw triangle id % 24 -> 0 border, 1 inner fan, 2 midpoint fan
+// (valid for midpointFan-only scenes such as C2). k: 0 entries, 1 block visits, 2 fast
+// visits, 3 visits with a lane inside, 4 lanes inside. [30] warp resolves, [31] lanes
+// resolved with nonzero coverage.
+__device__ unsigned long long g_rasterStats[32];
+#define RC_STAT(IDX, N)                                                                                               \
+    do                                                                                                                \
+    {                                                                                                                 \
+        if ((threadIdx.x & 31) == 0)                                                                                  \
+            atomicAdd(&g_rasterStats[IDX], static_cast<unsigned long long>(N));                                       \
+    } while (0)
+#else
+#define RC_STAT(IDX, N)
+#endif
+
 // Builds the tile-local form of one triangle. Exact for edges whose Manhattan
 // length is below 2^17 px; longer edges are scaled (approximate).
 __device__ void prepare_triangle(const FlushParams& P,
@@ -139,7 +156,6 @@ __device__ void prepare_triangle(const FlushParams& P,
     out.A2 = Ai[2];
     out.B2 = Bi[2];
     out.q2 = qi[2];
-    out.meta = g.meta;
     // Attribute planes from exact barycentrics at tile pixel (0,0):
     //   attr(i,j) = sum_k c_k * (E0u_k + 256*(A_k*i + B_k*j)) / area2
     const double area2 = static_cast<double>(E0u[0] + E0u[1] + E0u[2]);
@@ -173,6 +189,12 @@ __device__ void prepare_triangle(const FlushParams& P,
     const uint2 paint = __ldg(P.paintBuffer + (g.meta & 0xffffu));
     out.paintX = paint.x;
     out.paintY = paint.y;
+    // Solid colour, src-over, no clip id / clip rect / image, premultiplied:
+    // resolve_path's straight-line case.
+    uint32_t meta = g.meta;
+    if ((paint.x & 0xffff0cffu) == kPaintTypeSolid && (g.meta & (kMetaUnmultiplied | kMetaModulatedImage)) == 0u)
+        meta |= kMetaSimplePaint;
+    out.meta = meta;
     // draw_path.vert:298-312: solid colours are premultiplied in the vertex stage
     // unless the batch runs with advanced blend.
     float4 pc = unpack_rgba8(paint.y);
@@ -377,6 +399,39 @@ __device__ float sample_atlas(const FlushParams& P, float u, float v)
 }
 
 __device__ __forceinline__ float round_to_half(float v) { return __half2float(__float2half_rn(v)); }
+
+// Shared-memory loads by 32-bit shared address: keeps the walk loop's addressing
+// to one add per triangle (no generic-to-shared conversion per iteration).
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr)
+{
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ float lds_f32(uint32_t addr)
+{
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint2 lds_u32x2(uint32_t addr)
+{
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint4 lds_u32x4(uint32_t addr)
+{
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ float4 lds_f32x4(uint32_t addr)
+{
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
 
 struct PixelState
 {
@@ -584,6 +639,22 @@ __device__ __forceinline__ void resolve_path(const FlushParams& P,
             coverage = 1.f - fabsf(fractf(coverage * .5f) * 2.f + -1.f);
         coverage = fminf(coverage, 1.f);
     }
+    if ((meta & kMetaSimplePaint) != 0u)
+    {
+        // The common case, straight-line: premultiplied solid colour, src-over,
+        // no clip / clip rect / image (same arithmetic as the general path below).
+        const float4 dst = unpack_rgba8(s.color);
+        const float a = solid.w * coverage;
+        const float oneMinusA = 1.f - a;
+        const float dither = a != 0.f ? s.dither : 0.f;
+        s.color = pack_rgba8_fast((solid.x * coverage + dst.x * oneMinusA) + dither,
+                                  (solid.y * coverage + dst.y * oneMinusA) + dither,
+                                  (solid.z * coverage + dst.z * oneMinusA) + dither,
+                                  a + dst.w * oneMinusA);
+        return;
+    }
+    // (Keeps the float pixel centre below from being hoisted into the walk loop.)
+    asm volatile("" : "+r"(px), "+r"(py));
     const uint32_t paintType = paintX & 0xfu;
     if (paintType == kPaintTypeClipUpdate)
     {
@@ -705,7 +776,10 @@ __device__ void resolve_image_mesh(const FlushParams& P, uint32_t meta, uint32_t
     blend_mesh_fragment(color, coverage, (meta & kMetaUnmultiplied) != 0u, true, packed.z, s);
 }
 
-__global__ void __launch_bounds__(256, 4) raster_tiles_kernel(FlushParams P,
+#ifndef RIVECUDA_RASTER_MIN_BLOCKS
+#define RIVECUDA_RASTER_MIN_BLOCKS 4
+#endif
+__global__ void __launch_bounds__(256, RIVECUDA_RASTER_MIN_BLOCKS) raster_tiles_kernel(FlushParams P,
                                                               const TriGeom* __restrict__ triGeom,
                                                               const TriAttr* __restrict__ triAttr,
                                                               const uint32_t* __restrict__ tileOffsets,
@@ -746,6 +820,8 @@ __global__ void __launch_bounds__(256, 4) raster_tiles_kernel(FlushParams P,
     float coverageStored = 0.f; // what it wrote back to the fp16 coverage plane
     bool touched = false;
     const uint32_t blockBit = 1u << warp, fastBit = 0x100u << warp;
+    uint32_t prepAddr = static_cast<uint32_t>(__cvta_generic_to_shared(s_prep));
+    asm volatile("" : "+r"(prepAddr)); // opaque: computed once, not re-derived from %cluster_ctaid per visit
 
     for (uint32_t base = 0; base < n; base += kRasterChunk)
     {
@@ -759,6 +835,12 @@ __global__ void __launch_bounds__(256, 4) raster_tiles_kernel(FlushParams P,
             *reinterpret_cast<uint4*>(&g) = __ldg(src);
             *(reinterpret_cast<uint4*>(&g) + 1) = __ldg(src + 1);
             prepare_triangle(P, g, triAttr + t, originX, originY, s_prep[threadIdx.x]);
+#ifdef RIVECUDA_STATS
+            const uint32_t cls = (t % 24u) < 16u ? 0u : ((t % 24u) < 23u ? 1u : 2u);
+            s_prep[threadIdx.x].pad0 = cls;
+            if (s_prep[threadIdx.x].masks != 0u)
+                atomicAdd(&g_rasterStats[cls * 8], 1ull);
+#endif
         }
         __syncthreads();
         // Each warp visits only the entries whose block mask names it.
@@ -767,52 +849,70 @@ __global__ void __launch_bounds__(256, 4) raster_tiles_kernel(FlushParams P,
             const uint32_t idx = sub + lane;
             const uint32_t myMasks = idx < chunk ? s_prep[idx].masks : 0u;
             uint32_t bits = __ballot_sync(0xffffffffu, (myMasks & blockBit) != 0u);
+            const uint32_t subAddr = prepAddr + sub * static_cast<uint32_t>(sizeof(Prepared));
+#pragma unroll 1
             while (bits != 0u)
             {
-                const int bit = __ffs(bits) - 1;
+                const uint32_t T = subAddr + (__ffs(bits) - 1) * static_cast<uint32_t>(sizeof(Prepared)); // shared address
                 bits &= bits - 1;
-                const uint32_t masks = __shfl_sync(0xffffffffu, myMasks, bit);
-                const Prepared& T = s_prep[sub + bit];
+                const uint32_t masks = lds_u32(T + 92);
+                RC_STAT(lds_u32(T + 120) * 8 + 1, 1);
                 // Path boundary (per warp): resolve what has been accumulated.
                 if ((masks >> 16) != curPath)
                 {
                     if (touched)
+                    {
+#ifdef RIVECUDA_STATS
+                        if (coverageCount != 0.f)
+                            atomicAdd(&g_rasterStats[31], 1ull);
+                        if (__ffs(__activemask()) - 1 == lane)
+                            atomicAdd(&g_rasterStats[30], 1ull);
+#endif
                         resolve_path(P, curMeta, curPaintX, curPaintY, curSolid, coverageCount, px, py, s);
+                    }
                     curPath = masks >> 16;
-                    curMeta = T.meta;
-                    const uint2 pxy = *reinterpret_cast<const uint2*>(&T.paintX);
+                    curMeta = lds_u32(T + 60);
+                    const uint2 pxy = lds_u32x2(T + 112);
                     curPaintX = pxy.x;
                     curPaintY = pxy.y;
-                    curSolid = *reinterpret_cast<const float4*>(T.paintColor);
+                    curSolid = lds_f32x4(T + 96);
                     coverageCount = 0.f;
                     coverageStored = 0.f;
                     touched = false;
                 }
+                // (The reference's coverage plane is fp16: every fragment's
+                // read-modify-write rounds to half, and deep feather overlap makes
+                // that rounding visible, so we round after every accumulate, in
+                // the same order.)
+                const uint4 w2 = lds_u32x4(T + 32); // q2, plane0
                 if ((masks & fastBit) != 0u)
                 {
                     // Whole block inside a constant-coverage triangle.
-                    // (The reference's coverage plane is fp16: every
-                    // fragment's read-modify-write rounds to half, and deep
-                    // feather overlap makes that rounding visible, so we
-                    // round after every accumulate, in the same order.)
 #ifdef RIVECUDA_DEBUG
                     if (px == P.debugX && py == P.debugY)
-                        printf("[cuda] px(%d,%d) fast pathID=%u c0=%.9g count=%.9g\n", px, py, curPath, T.plane0[0], coverageCount);
+                        printf("[cuda] px(%d,%d) fast pathID=%u c0=%.9g count=%.9g\n", px, py, curPath, __uint_as_float(w2.y), coverageCount);
 #endif
-                    coverageCount = coverageStored + T.plane0[0];
+                    RC_STAT(lds_u32(T + 120) * 8 + 2, 1);
+                    coverageCount = coverageStored + __uint_as_float(w2.y);
                     coverageStored = round_to_half(coverageCount);
                     touched = true;
                     continue;
                 }
-                const int4 w0 = *reinterpret_cast<const int4*>(&T.A0);
-                const int4 w1 = *reinterpret_cast<const int4*>(&T.B1);
-                const int4 w2 = *reinterpret_cast<const int4*>(&T.q2);
-                const int e0 = w0.z + w0.x * i + w0.y * j;
-                const int e1 = w1.y + w0.w * i + w1.x * j;
-                const int e2 = w2.x + w1.z * i + w1.w * j;
+                const uint4 w0 = lds_u32x4(T);
+                const uint4 w1 = lds_u32x4(T + 16);
+                const int e0 = static_cast<int>(w0.z) + static_cast<int>(w0.x) * i + static_cast<int>(w0.y) * j;
+                const int e1 = static_cast<int>(w1.y) + static_cast<int>(w0.w) * i + static_cast<int>(w1.x) * j;
+                const int e2 = static_cast<int>(w2.x) + static_cast<int>(w1.z) * i + static_cast<int>(w1.w) * j;
+#ifdef RIVECUDA_STATS
+                {
+                    const uint32_t in = __ballot_sync(0xffffffffu, (e0 | e1 | e2) >= 0);
+                    RC_STAT(lds_u32(T + 120) * 8 + 3, in != 0u ? 1 : 0);
+                    RC_STAT(lds_u32(T + 120) * 8 + 4, __popc(in));
+                }
+#endif
                 if ((e0 | e1 | e2) < 0)
                     continue;
-                const float c0 = __int_as_float(w2.y) + __int_as_float(w2.z) * fi + __int_as_float(w2.w) * fj;
+                const float c0 = __uint_as_float(w2.y) + __uint_as_float(w2.z) * fi + __uint_as_float(w2.w) * fj;
                 const uint32_t kind = (curMeta >> kMetaKindShift) & 0xf;
 #ifdef RIVECUDA_DEBUG
                 if (px == P.debugX && py == P.debugY)
@@ -825,7 +925,8 @@ __global__ void __launch_bounds__(256, 4) raster_tiles_kernel(FlushParams P,
                     touched = true;
                     continue;
                 }
-                const float c1 = T.plane1[0] + T.plane1[1] * fi + T.plane1[2] * fj;
+                const float4 p1 = lds_f32x4(T + 48); // plane1, meta
+                const float c1 = p1.x + p1.y * fi + p1.z * fj;
                 switch (kind)
                 {
                     case kKindStroke:
@@ -835,8 +936,10 @@ __global__ void __launch_bounds__(256, 4) raster_tiles_kernel(FlushParams P,
                         break;
                     case kKindFeatherFill:
                     {
-                        const float c2 = T.plane2[0] + T.plane2[1] * fi + T.plane2[2] * fj;
-                        const float c3 = T.plane3[0] + T.plane3[1] * fi + T.plane3[2] * fj;
+                        const float4 p2 = lds_f32x4(T + 64); // plane2, plane3[0]
+                        const uint2 p3 = lds_u32x2(T + 80);  // plane3[1..2]
+                        const float c2 = p2.x + p2.y * fi + p2.z * fj;
+                        const float c3 = p2.w + __uint_as_float(p3.x) * fi + __uint_as_float(p3.y) * fj;
                         coverageCount = coverageStored + eval_feathered_fill(P.featherLUT, make_float4(c0, c1, c2, c3));
                         coverageStored = round_to_half(coverageCount);
                         touched = true;
@@ -853,7 +956,7 @@ __global__ void __launch_bounds__(256, 4) raster_tiles_kernel(FlushParams P,
                     case kKindImageMesh:
                         // Consecutive meshes share "path" 0, so the flags come
                         // from the triangle itself.
-                        resolve_image_mesh(P, T.meta, T.aux, c0, c1, T.plane2[0], px, py, s);
+                        resolve_image_mesh(P, __float_as_uint(p1.w), lds_u32(T + 88), c0, c1, lds_f32(T + 64), px, py, s);
                         break;
                     default:
                         break;

@@ -124,7 +124,7 @@ struct rivecuda_ctx
 
     // Raster work buffers (grow-only).
     rivecuda::DeviceBuffer triGeom, triAttr, tileCounts, tileOffsets, tileEntries, batchTable, imageTable,
-        scanScratch, clipPlane, pathImageSlots, atlasTable;
+        scanScratch, clipPlane, pathImageSlots, atlasTable, binCount, binPairs;
     uint32_t* pinnedTotals = nullptr; // pinned host words for small D2H results
 
     // Profiling.

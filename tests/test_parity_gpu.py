@@ -66,7 +66,7 @@ def test_scene_parity(libs, name):
             assert np.nanmax(np.abs(rxy - gxy)) <= 2e-6 * scale + 1e-4
             dth = np.abs(rt[~packed, 2].view(np.float32) - gt[~packed, 2].view(np.float32))
             dth = np.minimum(dth, np.abs(dth - 2 * np.pi))
-            assert dth.size == 0 or np.nanmax(dth) <= 1e-4
+            assert dth.size == 0 or np.nanmax(dth) <= 2.5e-4  # acosf/atan2 differ by a few ulp between libm and CUDA; ill-conditioned for tiny tangents
         if fr.desc.grad_data_height:
             assert np.array_equal(fr.grad[:fr.desc.grad_data_height], fg.grad), "colour ramps must be bit-exact"
     max_delta, max_outliers = KNOWN_DEVIATIONS.get(name, (MAX_DELTA, 0))
