@@ -788,6 +788,11 @@ __global__ void __launch_bounds__(256, RIVECUDA_RASTER_MIN_BLOCKS) raster_tiles_
 {
     __shared__ __align__(16) Prepared s_prep[kRasterChunk];
     const uint32_t tile = blockIdx.x;
+    const uint32_t n = tileCounts[tile];
+    // Nothing drawn here and the target is preserved (later logical flushes of a
+    // frame, or a partial update): the tile's pixels are already final.
+    if (n == 0u && P.loadAction != RIVECUDA_LOAD_CLEAR)
+        return;
     const int tileX = static_cast<int>(tile % P.tilesX) + P.tileX0, tileY = static_cast<int>(tile / P.tilesX) + P.tileY0;
     const int originX = tileX << kTileSizeLog2, originY = tileY << kTileSizeLog2;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -810,7 +815,6 @@ __global__ void __launch_bounds__(256, RIVECUDA_RASTER_MIN_BLOCKS) raster_tiles_
     else
         s.color = inBounds ? P.target[static_cast<size_t>(py) * P.targetWidth + px] : 0u;
 
-    const uint32_t n = tileCounts[tile];
     const uint32_t* list = entries + tileOffsets[tile];
 
     // Per-warp path accumulation state (the warp's pixels only).

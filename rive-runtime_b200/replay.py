@@ -48,6 +48,9 @@ class Replayer:
         self.textures: Dict[int, ctypes.c_void_p] = {}
         self.renderbuffers: Dict[int, ctypes.c_void_p] = {}
         self.capacity = [0] * 9
+        # Optional: id -> device pointer of caller-owned RGBA8 memory (e.g. a torch tensor
+        # later handed to NCCL); TARGET_CREATE records then wrap it instead of allocating.
+        self.external_targets: Dict[int, int] = {}
         self.profiling = profiling
         if profiling:
             self.lib.rivecuda_set_profiling(self.ctx, 1)
@@ -154,7 +157,11 @@ class Replayer:
             self._call("rivecuda_resize_feather_atlas_texture", r.fields["width"], r.fields["height"])
         elif tag == T.TARGET_CREATE:
             t = ctypes.c_void_p()
-            self._call("rivecuda_target_create", r.fields["width"], r.fields["height"], ctypes.byref(t))
+            ext = self.external_targets.get(r.fields["id"])
+            if ext is not None:
+                self._call("rivecuda_target_wrap", r.fields["width"], r.fields["height"], ctypes.c_void_p(ext), ctypes.byref(t))
+            else:
+                self._call("rivecuda_target_create", r.fields["width"], r.fields["height"], ctypes.byref(t))
             self.targets[r.fields["id"]] = t
             self.target_shapes[r.fields["id"]] = (r.fields["height"], r.fields["width"])
         elif tag == T.TARGET_DESTROY:

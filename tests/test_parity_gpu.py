@@ -139,3 +139,23 @@ def test_clear_only_and_preserve(libs):
         pf.desc.update_bounds[:] = [0, 0, 400, 800]
         rp.flush(pf)
         assert np.array_equal(rp.read_target(1), before)
+
+
+def test_band_sharding_over_two_gpus_with_nccl_gather():
+    """one frame as screen-tile bands on 2 GPUs, composited by one NCCL gather,
+    must equal the single-GPU render bit for bit (skipped on a 1-GPU box; the CPU/gloo
+    version of the partitioning logic is tests/test_sharding_cpu.py)."""
+    import json
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(GOLDEN.rstrip("/")).rsplit("/tests", 1)[0]
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29533",
+                          os.path.join(root, "tools", "band_shard_check.py"), os.path.join(GOLDEN, "c3.rvct.xz")],
+                         capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])
+    assert line["composite_identical_to_single_pass"] and line["n_gpus"] == 2
