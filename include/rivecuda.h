@@ -240,6 +240,14 @@ void rivecuda_target_destroy(rivecuda_ctx* ctx, rivecuda_target* target);
 /* Synchronising D2H read / H2D write of the whole target (RGBA8, w*h*4 bytes). */
 int rivecuda_target_read_pixels(rivecuda_ctx* ctx, const rivecuda_target* target, void* host_rgba8, size_t size_in_bytes);
 int rivecuda_target_write_pixels(rivecuda_ctx* ctx, rivecuda_target* target, const void* host_rgba8, size_t size_in_bytes);
+/* Asynchronous read-back for pipelined presentation (what a swap chain / staging
+ * ring is to the reference's window back ends): enqueue the D2H copy of the
+ * target, as rendered by everything submitted so far, on the context's copy
+ * stream and return at once; host_rgba8 must be pinned memory and is valid
+ * after rivecuda_target_read_wait(). Later flushes into OTHER targets overlap
+ * the copy; a later flush into this target waits for it. */
+int rivecuda_target_read_pixels_async(rivecuda_ctx* ctx, rivecuda_target* target, void* host_rgba8, size_t size_in_bytes);
+int rivecuda_target_read_wait(rivecuda_ctx* ctx, rivecuda_target* target);
 /* Raw device pointer of the target's RGBA8 pixels (for zero-copy interop and
  * for the NCCL band gather). */
 int rivecuda_target_device_ptr(rivecuda_ctx* ctx, const rivecuda_target* target, void** out_device_ptr);

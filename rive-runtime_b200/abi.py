@@ -37,6 +37,8 @@ SIGNATURES = {
     "rivecuda_target_destroy": (None, [_vp, _vp]),
     "rivecuda_target_read_pixels": (_int, [_vp, _vp, _vp, _sz]),
     "rivecuda_target_write_pixels": (_int, [_vp, _vp, _vp, _sz]),
+    "rivecuda_target_read_pixels_async": (_int, [_vp, _vp, _vp, _sz]),
+    "rivecuda_target_read_wait": (_int, [_vp, _vp]),
     "rivecuda_target_device_ptr": (_int, [_vp, _vp, ctypes.POINTER(_vp)]),
     "rivecuda_texture_create": (_int, [_vp, _u32, _u32, _u32, _vp, _int, ctypes.POINTER(_vp)]),
     "rivecuda_texture_destroy": (None, [_vp, _vp]),

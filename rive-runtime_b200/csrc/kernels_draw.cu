@@ -543,11 +543,20 @@ template <typename Fn> __device__ __forceinline__ void for_each_tile(const Flush
 // by all 32 lanes in parallel, so a full-screen triangle costs tiles/32
 // iterations instead of stalling one lane. fn(tile, ownerLane, cooperative) is
 // invoked by whichever lane found the overlap; ownerLane says whose triangle it
-// is. Returns whether the calling lane's own triangle took the cooperative route.
+// is. Returns how the calling lane's own triangle was handled.
 constexpr int kSmallTileCount = 4;
+constexpr int kHugeTileCount = 512;   // above this a triangle's tile range is walked by bin_huge_kernel,
+constexpr int kHugeChunkTiles = 2048; // one CTA per chunk of this many tiles of the range
+
+enum TileWalk : int
+{
+    kWalkSmall = 0,       // own lane visited <= kSmallTileCount tiles (or none)
+    kWalkCooperative = 1, // all 32 lanes visited the tile range
+    kWalkHuge = 2,        // not visited: > kHugeTileCount tiles, left to bin_huge_kernel
+};
 
 template <typename Fn>
-__device__ __forceinline__ bool warp_for_each_tile(const FlushParams& P, const int32_t X[3], const int32_t Y[3], bool valid, Fn&& fn)
+__device__ __forceinline__ TileWalk warp_for_each_tile(const FlushParams& P, const int32_t X[3], const int32_t Y[3], bool valid, Fn&& fn)
 {
     const int lane = threadIdx.x & 31;
     TileRange r;
@@ -568,7 +577,7 @@ __device__ __forceinline__ bool warp_for_each_tile(const FlushParams& P, const i
                 if (count == 1 || tile_overlaps(E, tx + P.tileX0, ty + P.tileY0))
                     fn(static_cast<uint32_t>(ty) * P.tilesX + static_cast<uint32_t>(tx), lane, false);
     }
-    uint32_t big = __ballot_sync(0xffffffffu, count > kSmallTileCount);
+    uint32_t big = __ballot_sync(0xffffffffu, count > kSmallTileCount && count <= kHugeTileCount);
     while (big != 0u)
     {
         const int src = __ffs(big) - 1;
@@ -591,7 +600,7 @@ __device__ __forceinline__ bool warp_for_each_tile(const FlushParams& P, const i
                 fn(static_cast<uint32_t>(ty) * P.tilesX + static_cast<uint32_t>(tx), src, true);
         }
     }
-    return count > kSmallTileCount;
+    return count > kHugeTileCount ? kWalkHuge : (count > kSmallTileCount ? kWalkCooperative : kWalkSmall);
 }
 
 // Tile binning, pass 1 (inside the setup kernels). Every lane calls this with its
@@ -604,15 +613,18 @@ struct BinTables
 {
     uint32_t* smallCounts; // per tile: entries with a pre-assigned rank
     uint32_t* bigCounts;   // per tile: entries appended after them by pass 2
-    uint8_t* binCount;     // per raw triangle: 0 none, 1..kSmallTileCount inline pairs, kBinBig
+    uint8_t* binCount;     // per raw triangle: 0 none, 1..kSmallTileCount inline pairs, kBinBig, kBinHuge
     uint2* binPairs;       // per raw triangle: kSmallTileCount x (tile, rank)
+    uint32_t* hugeCount;   // [0] chunks queued for bin_huge_kernel, [1] chunks dropped (queue full)
+    uint2* hugeList;       // (raw triangle id, chunk index)
+    uint32_t hugeCapacity;
 };
-constexpr uint8_t kBinBig = 0xff;
+constexpr uint8_t kBinBig = 0xff, kBinHuge = 0xfe;
 
 __device__ __forceinline__ void bin_triangle(const FlushParams& P, const BinTables& B, const int32_t X[3], const int32_t Y[3], bool stored, bool hasSlot, uint32_t rawTri)
 {
     uint32_t n = 0;
-    const bool big = warp_for_each_tile(P, X, Y, stored, [&](uint32_t tile, int, bool cooperative) {
+    const TileWalk walk = warp_for_each_tile(P, X, Y, stored, [&](uint32_t tile, int, bool cooperative) {
         if (cooperative)
         {
             atomicAdd(B.bigCounts + tile, 1u);
@@ -624,9 +636,74 @@ __device__ __forceinline__ void bin_triangle(const FlushParams& P, const BinTabl
             ++n;
         }
     });
+    if (walk == kWalkHuge)
+    {
+        // A few per frame (backgrounds, big interior triangles): queue the tile
+        // range in chunks, one CTA of bin_huge_kernel each.
+        const TileRange r = triangle_tile_range(P, X, Y);
+        const uint32_t total = static_cast<uint32_t>(r.tx1 - r.tx0 + 1) * static_cast<uint32_t>(r.ty1 - r.ty0 + 1);
+        const uint32_t chunks = (total + kHugeChunkTiles - 1) / kHugeChunkTiles;
+        const uint32_t first = atomicAdd(B.hugeCount, chunks);
+        for (uint32_t c = 0; c < chunks; ++c)
+        {
+            if (first + c < B.hugeCapacity)
+                B.hugeList[first + c] = make_uint2(rawTri, c);
+            else
+                atomicAdd(B.hugeCount + 1, 1u);
+        }
+    }
     if (hasSlot)
-        B.binCount[rawTri] = big ? kBinBig : static_cast<uint8_t>(n);
+        B.binCount[rawTri] = walk == kWalkHuge ? kBinHuge : (walk == kWalkCooperative ? kBinBig : static_cast<uint8_t>(n));
 }
+
+// Tile binning of the queued huge triangles: one CTA per queued chunk of a
+// triangle's tile range, a thread per tile. SCATTER false: count
+// (before the scan); true: append the id to the tiles' lists (after it).
+template <bool SCATTER>
+__global__ void __launch_bounds__(256) bin_huge_kernel(FlushParams P,
+                                                       const TriGeom* __restrict__ triGeom,
+                                                       BinTables bins,
+                                                       const uint32_t* __restrict__ tileOffsets,
+                                                       uint32_t* __restrict__ bigCursors,
+                                                       uint32_t* __restrict__ entries,
+                                                       uint32_t entryCapacity)
+{
+    const uint32_t n = min(*bins.hugeCount, bins.hugeCapacity);
+    for (uint32_t item = blockIdx.x; item < n; item += gridDim.x)
+    {
+        const uint2 work = bins.hugeList[item];
+        const uint32_t t = work.x;
+        const uint4 lo = __ldg(reinterpret_cast<const uint4*>(triGeom + t));
+        const uint2 hi = __ldg(reinterpret_cast<const uint2*>(triGeom + t) + 2);
+        const int32_t X[3] = {static_cast<int32_t>(lo.x), static_cast<int32_t>(lo.z), static_cast<int32_t>(hi.x)};
+        const int32_t Y[3] = {static_cast<int32_t>(lo.y), static_cast<int32_t>(lo.w), static_cast<int32_t>(hi.y)};
+        const TileRange r = triangle_tile_range(P, X, Y);
+        if (r.tx0 > r.tx1)
+            continue;
+        const uint32_t w = static_cast<uint32_t>(r.tx1 - r.tx0 + 1), total = w * static_cast<uint32_t>(r.ty1 - r.ty0 + 1);
+        const uint32_t end = min(total, (work.y + 1u) * kHugeChunkTiles);
+        EdgeEq E[3];
+        edge_equations(X, Y, E);
+        for (uint32_t idx = work.y * kHugeChunkTiles + threadIdx.x; idx < end; idx += blockDim.x)
+        {
+            const int ty = r.ty0 + static_cast<int>(idx / w), tx = r.tx0 + static_cast<int>(idx % w);
+            if (!tile_overlaps(E, tx + P.tileX0, ty + P.tileY0))
+                continue;
+            const uint32_t tile = static_cast<uint32_t>(ty) * P.tilesX + static_cast<uint32_t>(tx);
+            if (SCATTER)
+            {
+                const uint32_t pos = __ldg(tileOffsets + tile) + __ldg(bins.smallCounts + tile) + atomicAdd(bigCursors + tile, 1u);
+                if (pos < entryCapacity)
+                    entries[pos] = t;
+            }
+            else
+            {
+                atomicAdd(bins.bigCounts + tile, 1u);
+            }
+        }
+    }
+}
+
 
 // Per-batch bits of TriGeom::meta.
 __device__ __forceinline__ uint32_t batch_meta_bits(const DeviceBatch& b)
@@ -1111,7 +1188,7 @@ __global__ void __launch_bounds__(256) scatter_kernel(FlushParams P,
     {
         const uint32_t t = tBase + threadIdx.x;
         const uint32_t n = t < triCount ? bins.binCount[t] : 0u;
-        if (n != 0u && n != kBinBig)
+        if (n != 0u && n < kBinHuge)
         {
             const uint2* pairs = bins.binPairs + static_cast<size_t>(t) * kSmallTileCount;
             for (uint32_t k = 0; k < n; ++k)
@@ -1385,17 +1462,18 @@ int launch_draw_list(rivecuda_ctx* ctx, const rivecuda_flush_desc& desc, const r
 
     // Per-tile counters: [0] ranked (small-triangle) entries, [1] big-triangle
     // entries, [2] pass-2 cursors for the latter, [3] totals (written by the scan).
-    if (int s = ctx->tileCounts.reserve(static_cast<size_t>(tileCount) * 4 * sizeof(uint32_t)))
+    if (int s = ctx->tileCounts.reserve((static_cast<size_t>(tileCount) * 4 + 4) * sizeof(uint32_t)))
         return s;
     if (int s = ctx->tileOffsets.reserve(static_cast<size_t>(tileCount) * sizeof(uint32_t)))
         return s;
-    uint32_t* smallCounts = ctx->tileCounts.as<uint32_t>();
+    uint32_t* hugeCount = ctx->tileCounts.as<uint32_t>(); // [0]; [1..3] pad
+    uint32_t* smallCounts = hugeCount + 4;
     uint32_t* bigCounts = smallCounts + tileCount;
     uint32_t* bigCursors = bigCounts + tileCount;
     uint32_t* tileCounts = bigCursors + tileCount;
     uint32_t* tileOffsets = ctx->tileOffsets.as<uint32_t>();
-    RC_CUDA(cudaMemsetAsync(smallCounts, 0, static_cast<size_t>(tileCount) * 3 * sizeof(uint32_t), stream));
-    BinTables bins = {smallCounts, bigCounts, nullptr, nullptr};
+    RC_CUDA(cudaMemsetAsync(hugeCount, 0, (static_cast<size_t>(tileCount) * 3 + 4) * sizeof(uint32_t), stream));
+    BinTables bins = {smallCounts, bigCounts, nullptr, nullptr, hugeCount, nullptr, 0u};
 
     TriGeom* triGeom = nullptr;
     TriAttr* triAttr = nullptr;
@@ -1411,8 +1489,12 @@ int launch_draw_list(rivecuda_ctx* ctx, const rivecuda_flush_desc& desc, const r
             return s;
         triGeom = ctx->triGeom.as<TriGeom>();
         triAttr = ctx->triAttr.as<TriAttr>();
+        bins.hugeCapacity = rawTriangles + 65536u;
+        if (int s = ctx->hugeList.reserve(static_cast<size_t>(bins.hugeCapacity) * sizeof(uint2)))
+            return s;
         bins.binCount = ctx->binCount.as<uint8_t>();
         bins.binPairs = ctx->binPairs.as<uint2>();
+        bins.hugeList = ctx->hugeList.as<uint2>();
         const size_t tableBytes = (patchBatches.size() + runBatches.size()) * sizeof(DeviceBatch);
         if (int s = ctx->batchTable.reserve(tableBytes + 16))
             return s;
@@ -1466,6 +1548,14 @@ int launch_draw_list(rivecuda_ctx* ctx, const rivecuda_flush_desc& desc, const r
         RC_CUDA(cudaGetLastError());
     }
 
+    const uint32_t hugeBlocks = static_cast<uint32_t>(ctx->smCount) * 4;
+    if (rawTriangles > 0)
+    {
+        bin_huge_kernel<false><<<hugeBlocks, 256, 0, stream>>>(P, triGeom, bins, nullptr, nullptr, nullptr, 0u);
+        ctx->lastLaunches += 1;
+        RC_CUDA(cudaGetLastError());
+    }
+
     // Exclusive scan of tile counts -> offsets, total -> pinned host word.
     const uint32_t scanBlocks = (tileCount + kScanBlock - 1) / kScanBlock;
     if (scanBlocks > kScanBlock)
@@ -1480,8 +1570,11 @@ int launch_draw_list(rivecuda_ctx* ctx, const rivecuda_flush_desc& desc, const r
     ctx->lastLaunches += 3;
     RC_CUDA(cudaGetLastError());
     RC_CUDA(cudaMemcpyAsync(ctx->pinnedTotals, total, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+    RC_CUDA(cudaMemcpyAsync(ctx->pinnedTotals + 1, hugeCount + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
     RC_CUDA(cudaStreamSynchronize(stream));
     const uint32_t entryCount = ctx->pinnedTotals[0];
+    if (ctx->pinnedTotals[1] != 0u)
+        return set_error("rivecuda_flush: huge-triangle queue overflow (%u chunks dropped)", ctx->pinnedTotals[1]);
     ctx->lastTimings.triangle_count = rawTriangles;
     ctx->lastTimings.tile_entry_count = entryCount;
 
@@ -1492,6 +1585,8 @@ int launch_draw_list(rivecuda_ctx* ctx, const rivecuda_flush_desc& desc, const r
     {
         const uint32_t blocks = std::min<uint32_t>((rawTriangles + 255) / 256, ctx->smCount * 16);
         scatter_kernel<<<blocks, 256, 0, stream>>>(P, triGeom, rawTriangles, bins, tileOffsets, bigCursors, entries, entryCount);
+        bin_huge_kernel<true><<<hugeBlocks, 256, 0, stream>>>(P, triGeom, bins, tileOffsets, bigCursors, entries, entryCount);
+        ctx->lastLaunches += 1;
         sort_tiles_kernel<<<tileCount, 256, 0, stream>>>(tileOffsets, tileCounts, entries);
         ctx->lastLaunches += 2;
         RC_CUDA(cudaGetLastError());

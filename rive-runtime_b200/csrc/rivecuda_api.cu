@@ -137,6 +137,8 @@ int rivecuda_create(int device, rivecuda_ctx** out_ctx)
     ctx->device = device;
     ctx->smCount = prop.multiProcessorCount;
     RC_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    RC_CUDA(cudaStreamCreateWithFlags(&ctx->copyStream, cudaStreamNonBlocking));
+    RC_CUDA(cudaEventCreateWithFlags(&ctx->renderDone, cudaEventDisableTiming));
     for (auto& e : ctx->events)
         RC_CUDA(cudaEventCreate(&e));
     RC_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&ctx->pinnedTotals), 64 * sizeof(uint32_t), cudaHostAllocDefault));
@@ -167,11 +169,14 @@ void rivecuda_destroy(rivecuda_ctx* ctx)
     cudaFree(ctx->tessTexture);
     cudaFree(ctx->atlas);
     for (DeviceBuffer* b : {&ctx->triGeom, &ctx->triAttr, &ctx->tileCounts, &ctx->tileOffsets, &ctx->tileEntries,
-                            &ctx->batchTable, &ctx->imageTable, &ctx->scanScratch, &ctx->clipPlane, &ctx->pathImageSlots, &ctx->atlasTable, &ctx->binCount, &ctx->binPairs})
+                            &ctx->batchTable, &ctx->imageTable, &ctx->scanScratch, &ctx->clipPlane, &ctx->pathImageSlots, &ctx->atlasTable, &ctx->binCount, &ctx->binPairs, &ctx->hugeList})
         b->release();
     cudaFreeHost(ctx->pinnedTotals);
     for (auto& e : ctx->events)
         cudaEventDestroy(e);
+    cudaStreamSynchronize(ctx->copyStream);
+    cudaStreamDestroy(ctx->copyStream);
+    cudaEventDestroy(ctx->renderDone);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -215,6 +220,8 @@ int rivecuda_buffer_resize(rivecuda_ctx* ctx, uint32_t kind, size_t size)
         return set_error("rivecuda_buffer_resize: bad kind %u", kind);
     RC_CUDA(cudaSetDevice(ctx->device));
     BufferRing& ring = ctx->rings[kind];
+    if (size == ring.capacity)
+        return 0;
     // In-flight copies/kernels may still read the old allocations.
     RC_CUDA(cudaStreamSynchronize(ctx->stream));
     for (int i = 0; i < kRingSize; ++i)
@@ -268,6 +275,8 @@ int rivecuda_resize_gradient_texture(rivecuda_ctx* ctx, uint32_t width, uint32_t
     if (width != 0 && width != kGradWidth)
         return set_error("rivecuda_resize_gradient_texture: width must be %d", kGradWidth);
     RC_CUDA(cudaSetDevice(ctx->device));
+    if (height == ctx->gradHeight && (height == 0 || ctx->gradTexture != nullptr))
+        return 0;
     RC_CUDA(cudaStreamSynchronize(ctx->stream));
     cudaFree(ctx->gradTexture);
     ctx->gradTexture = nullptr;
@@ -282,6 +291,8 @@ int rivecuda_resize_tessellation_texture(rivecuda_ctx* ctx, uint32_t width, uint
     if (width != 0 && width != kTessWidth)
         return set_error("rivecuda_resize_tessellation_texture: width must be %d", kTessWidth);
     RC_CUDA(cudaSetDevice(ctx->device));
+    if (height == ctx->tessHeight && (height == 0 || ctx->tessTexture != nullptr))
+        return 0;
     RC_CUDA(cudaStreamSynchronize(ctx->stream));
     cudaFree(ctx->tessTexture);
     ctx->tessTexture = nullptr;
@@ -345,6 +356,9 @@ void rivecuda_target_destroy(rivecuda_ctx* ctx, rivecuda_target* target)
         return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    cudaStreamSynchronize(ctx->copyStream);
+    if (target->readDone != nullptr)
+        cudaEventDestroy(target->readDone);
     if (target->owned)
         cudaFree(target->pixels);
     delete target;
@@ -358,6 +372,32 @@ int rivecuda_target_read_pixels(rivecuda_ctx* ctx, const rivecuda_target* target
     RC_CUDA(cudaSetDevice(ctx->device));
     RC_CUDA(cudaMemcpyAsync(host, target->pixels, bytes, cudaMemcpyDeviceToHost, ctx->stream));
     RC_CUDA(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int rivecuda_target_read_pixels_async(rivecuda_ctx* ctx, rivecuda_target* target, void* host, size_t size)
+{
+    size_t bytes = static_cast<size_t>(target->width) * target->height * 4;
+    if (size < bytes)
+        return set_error("rivecuda_target_read_pixels_async: destination too small");
+    RC_CUDA(cudaSetDevice(ctx->device));
+    if (target->readDone == nullptr)
+        RC_CUDA(cudaEventCreateWithFlags(&target->readDone, cudaEventDisableTiming));
+    // The copy starts when everything submitted so far has rendered, and runs on
+    // the copy stream so that later flushes (into other targets) overlap it.
+    RC_CUDA(cudaEventRecord(ctx->renderDone, ctx->stream));
+    RC_CUDA(cudaStreamWaitEvent(ctx->copyStream, ctx->renderDone, 0));
+    RC_CUDA(cudaMemcpyAsync(host, target->pixels, bytes, cudaMemcpyDeviceToHost, ctx->copyStream));
+    RC_CUDA(cudaEventRecord(target->readDone, ctx->copyStream));
+    target->readPending = true;
+    return 0;
+}
+
+int rivecuda_target_read_wait(rivecuda_ctx* ctx, rivecuda_target* target)
+{
+    RC_CUDA(cudaSetDevice(ctx->device));
+    if (target->readDone != nullptr)
+        RC_CUDA(cudaEventSynchronize(target->readDone));
     return 0;
 }
 
@@ -515,6 +555,12 @@ int rivecuda_flush(rivecuda_ctx* ctx,
     if (desc->tess_data_height > ctx->tessHeight || desc->grad_data_height > ctx->gradHeight)
         return set_error("rivecuda_flush: tessellation/gradient texture smaller than the flush needs");
     RC_CUDA(cudaSetDevice(ctx->device));
+    if (desc->render_target->readPending)
+    {
+        // An asynchronous read-back of this target may still be in flight.
+        RC_CUDA(cudaStreamWaitEvent(ctx->stream, desc->render_target->readDone, 0));
+        desc->render_target->readPending = false;
+    }
 
     auto ringPtr = [&](int kind, size_t elementSize, uint64_t first) -> const uint8_t* {
         const BufferRing& ring = ctx->rings[kind];

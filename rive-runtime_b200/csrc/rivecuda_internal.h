@@ -83,6 +83,8 @@ struct rivecuda_target
     uint32_t width = 0, height = 0;
     uint32_t* pixels = nullptr; // device RGBA8 premultiplied, row-major
     bool owned = true;
+    cudaEvent_t readDone = nullptr; // last asynchronous read-back of this target
+    bool readPending = false;
 };
 
 struct rivecuda_texture
@@ -103,6 +105,8 @@ struct rivecuda_ctx
 {
     int device = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t copyStream = nullptr; // asynchronous target read-backs
+    cudaEvent_t renderDone = nullptr;
     int smCount = 148;
 
     rivecuda::BufferRing rings[RIVECUDA_BUFFER_KIND_COUNT];
@@ -124,7 +128,7 @@ struct rivecuda_ctx
 
     // Raster work buffers (grow-only).
     rivecuda::DeviceBuffer triGeom, triAttr, tileCounts, tileOffsets, tileEntries, batchTable, imageTable,
-        scanScratch, clipPlane, pathImageSlots, atlasTable, binCount, binPairs;
+        scanScratch, clipPlane, pathImageSlots, atlasTable, binCount, binPairs, hugeList;
     uint32_t* pinnedTotals = nullptr; // pinned host words for small D2H results
 
     // Profiling.

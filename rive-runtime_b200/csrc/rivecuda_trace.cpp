@@ -242,6 +242,13 @@ int rivecuda_target_read_pixels(rivecuda_ctx* ctx, const rivecuda_target* t, voi
     return 0;
 }
 
+int rivecuda_target_read_pixels_async(rivecuda_ctx* ctx, rivecuda_target* t, void* host, size_t size)
+{
+    return rivecuda_target_read_pixels(ctx, t, host, size);
+}
+
+int rivecuda_target_read_wait(rivecuda_ctx*, rivecuda_target*) { return 0; }
+
 int rivecuda_target_write_pixels(rivecuda_ctx* ctx, rivecuda_target* t, const void* host, size_t size)
 {
     Record r;

@@ -243,3 +243,42 @@ def replay(records: List[T.Record], device: int = 0, keep_intermediates: bool = 
                 continue
             rp.apply(r, result)
     return result
+
+
+def split_frames(records: List[T.Record]):
+    """Split a trace into (setup records, frames). Setup = what persists across frames
+    (static tables, the render target, textures, mesh buffers) plus ONE resize per buffer
+    kind / per-flush texture at the largest size the trace ever asks for, so that looping
+    over the frames never reallocates. A frame = (buffer uploads, flush records), ended by
+    the trace's TARGET_READ."""
+    setup: List[T.Record] = []
+    frames = []
+    uploads: List[T.Record] = []
+    flushes: List[T.Record] = []
+    buf_max: Dict[int, T.Record] = {}
+    tex_max: Dict[int, T.Record] = {}
+    for r in records:
+        if r.tag in (T.CREATE, T.DESTROY, T.TARGET_DESTROY, T.TEXTURE_DESTROY, T.RENDERBUFFER_DESTROY,
+                     T.PREPARE_TO_FLUSH, T.POST_FLUSH):
+            continue
+        if r.tag == T.BUFFER_RESIZE:
+            k = r.fields["kind"]
+            if k not in buf_max or r.fields["size"] > buf_max[k].fields["size"]:
+                buf_max[k] = r
+        elif r.tag in (T.RESIZE_GRADIENT, T.RESIZE_TESSELLATION, T.RESIZE_ATLAS):
+            m = tex_max.get(r.tag)
+            if m is None or r.fields["height"] * max(r.fields["width"], 1) > m.fields["height"] * max(m.fields["width"], 1):
+                tex_max[r.tag] = r
+        elif r.tag == T.BUFFER_UNMAP:
+            uploads.append(r)
+        elif r.tag == T.FLUSH:
+            flushes.append(r)
+        elif r.tag == T.TARGET_READ:
+            frames.append((uploads, flushes))
+            uploads, flushes = [], []
+        else:
+            setup.append(r)
+    if flushes:
+        frames.append((uploads, flushes))
+    setup = setup + list(buf_max.values()) + list(tex_max.values())
+    return setup, frames
