@@ -56,6 +56,7 @@ enum TriKind : uint32_t
     kKindImageMesh = 5,     // immediate blend, colour from an image
 };
 
+constexpr float kAtlasFixedOne = 65536.f; // the feather atlas holds 16.16 fixed-point coverage
 constexpr uint32_t kAuxNoImage = 0xfffu; // TriGeom::aux = imageSlot (12 bits) | imageDrawInstance << 12
 
 constexpr uint32_t kMetaValid = 1u << 31;
@@ -1730,19 +1731,23 @@ __global__ void __launch_bounds__(128) atlas_kernel(FlushParams P,
                                              cov[0].y * b0 + cov[1].y * b1 + cov[2].y * b2,
                                              cov[0].z * b0 + cov[1].z * b1 + cov[2].z * b2,
                                              cov[0].w * b0 + cov[1].w * b1 + cov[2].w * b2);
-                float* texel = atlas + static_cast<size_t>(y) * atlasWidth + x;
+                // Coverage is accumulated in 16.16 fixed point: integer add / max are
+                // associative, so the atlas is deterministic whatever order the
+                // triangles' threads arrive in (the reference blends in primitive order
+                // into an R16F target; fp32 atomics would depend on scheduling).
+                int* texel = reinterpret_cast<int*>(atlas) + static_cast<size_t>(y) * atlasWidth + x;
                 if (isStroke)
                 {
                     const float v = eval_feathered_stroke(P.featherLUT, c.x, c.y);
                     if (v > 0.f)
-                        atomicMax(reinterpret_cast<int*>(texel), __float_as_int(v));
+                        atomicMax(texel, __float2int_rn(v * kAtlasFixedOne));
                 }
                 else
                 {
                     float v = eval_feathered_fill(P.featherLUT, c);
                     if (!frontFacing)
                         v = -v;
-                    atomicAdd(texel, v);
+                    atomicAdd(texel, __float2int_rn(v * kAtlasFixedOne));
                 }
             }
         }

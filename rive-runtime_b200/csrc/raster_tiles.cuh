@@ -391,7 +391,7 @@ __device__ float sample_atlas(const FlushParams& P, float u, float v)
     auto fetch = [&](int xx, int yy) {
         xx = min(max(xx, 0), static_cast<int>(P.atlasWidth) - 1);
         yy = min(max(yy, 0), static_cast<int>(P.atlasHeight) - 1);
-        return __ldg(P.atlas + static_cast<size_t>(yy) * P.atlasWidth + xx);
+        return static_cast<float>(__ldg(reinterpret_cast<const int*>(P.atlas) + static_cast<size_t>(yy) * P.atlasWidth + xx)) * (1.f / kAtlasFixedOne);
     };
     const float a = fetch(ix, iy) + (fetch(ix + 1, iy) - fetch(ix, iy)) * tx;
     const float b = fetch(ix, iy + 1) + (fetch(ix + 1, iy + 1) - fetch(ix, iy + 1)) * tx;

@@ -680,6 +680,14 @@ int rivecuda_debug_read_atlas(rivecuda_ctx* ctx, void* host, uint32_t width, uin
     RC_CUDA(cudaSetDevice(ctx->device));
     RC_CUDA(cudaStreamSynchronize(ctx->stream));
     RC_CUDA(cudaMemcpy(host, ctx->atlas, static_cast<size_t>(width) * height * sizeof(float), cudaMemcpyDeviceToHost));
+    // Device texels are 16.16 fixed point (kernels_draw.cu, atlas_kernel).
+    for (size_t i = 0; i < static_cast<size_t>(width) * height; ++i)
+    {
+        int32_t fixed;
+        memcpy(&fixed, static_cast<const uint8_t*>(host) + i * 4, 4);
+        const float v = static_cast<float>(fixed) * (1.f / 65536.f);
+        memcpy(static_cast<uint8_t*>(host) + i * 4, &v, 4);
+    }
     return 0;
 }
 

@@ -159,3 +159,28 @@ def test_band_sharding_over_two_gpus_with_nccl_gather():
     assert out.returncode == 0, out.stderr[-2000:]
     line = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])
     assert line["composite_identical_to_single_pass"] and line["n_gpus"] == 2
+
+
+@pytest.mark.parametrize("scene,trace_name,size", [("gm:beziers", "beziers", (800, 400)), ("c1", "c1", (1600, 1600)),
+                                                   ("img", "img", (960, 1280)), ("gm:feather_shapes", "feather_shapes", None)])
+def test_reference_front_end_drives_the_cuda_backend(libs, scene, trace_name, size):
+    """The drop-in boundary end to end, in C++: the reference's own RiveRenderer ->
+    RenderContext (built in place, oracle/_ref) -> RenderContextCUDAImpl -> C ABI ->
+    librivecuda.so on the GPU (host/player). Its pixels must equal the replay of the
+    recorded ABI trace bit for bit (same calls, same kernels) -- i.e. the Python replayer
+    the other tests use is a faithful stand-in for the C++ host layer."""
+    import subprocess
+    import tempfile
+    replay, T, _ = libs
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    player = os.path.join(root, "rive-runtime_b200", "_build", "rive_cuda_player")
+    if not os.path.exists(player):
+        pytest.skip("scene player not built (needs the reference tree at build time)")
+    got = replay.replay(T.parse(os.path.join(GOLDEN, trace_name + ".rvct.xz"))).frames[-1]
+    with tempfile.TemporaryDirectory() as tmp:
+        out = os.path.join(tmp, "frame.rgba")
+        env = dict(os.environ, RIVECUDA_LIB=os.path.join(root, "rive-runtime_b200", "_build", "librivecuda.so"))
+        subprocess.check_call([player, "--scene", scene, "--out", out], env=env, stdout=subprocess.DEVNULL, timeout=300)
+        px = np.fromfile(out, dtype=np.uint8)
+    assert px.size == got.size
+    assert np.array_equal(px.reshape(got.shape), got)
