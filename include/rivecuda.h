@@ -299,7 +299,56 @@ int rivecuda_sync(rivecuda_ctx* ctx);
 /* The context's cudaStream_t, as void*. */
 int rivecuda_stream(rivecuda_ctx* ctx, void** out_stream);
 
+/* ---- GPU path front end -------------------------------- */
+
+/* One filled path: a slice of the caller's verb / point arrays (rive::RawPath layout:
+ * include/rive/math/raw_path.hpp; PathVerb values move 0, line 1, cubic 4, close 5), its
+ * view matrix (Mat2D::values() order xx, xy, yx, yy, tx, ty), fill rule and colour. */
+typedef struct rivecuda_fill_path
+{
+    uint32_t first_verb, verb_count;
+    uint32_t first_point;
+    uint32_t fill_rule; /* 0 nonZero, 1 evenOdd */
+    float matrix[6];
+    uint32_t color;     /* rive::ColorInt, 0xAARRGGBB, unpremultiplied */
+    uint32_t reserved0;
+} rivecuda_fill_path;
+
+/* What the host needs to fill in the FlushDescriptor / the one midpointFanPatches batch. */
+typedef struct rivecuda_front_end_result
+{
+    uint32_t path_count;                     /* incl. the reserved record 0 */
+    uint32_t contour_count;
+    uint32_t tess_vertex_span_count;
+    uint32_t midpoint_fan_tess_vertex_count; /* both directions */
+    uint32_t tess_data_height;
+    uint32_t first_patch, patch_count;       /* DrawBatch::baseElement / elementCount */
+    uint32_t reserved0;
+} rivecuda_front_end_result;
+
+/* Device-side replacement, for non-feathered nonZero / evenOdd solid-colour fills, of the
+ * per-path CPU work the reference does before a flush: PathDraw::initForMidpointFan
+ * (renderer/src/draw.cpp:768-1392; Wang's-formula segment counts, contour padding),
+ * LogicalFlush::allocateMidpointFanTessVertices (render_context.cpp:3019; prefix-summed span
+ * allocation), PathDraw::pushMidpointFanTessellationData + TessellationWriter::pushCubic /
+ * pushContour (draw.cpp:1992-2375, render_context.cpp:3140-3402) and LogicalFlush::pushPath
+ * (render_context.cpp:3037). Writes the TessVertexSpan, ContourData, PathData, PaintData and
+ * PaintAuxData records, in the reference's byte layout, into fresh slots of the context's
+ * buffer rings (as if the host had mapped, written and unmapped them); the caller then
+ * issues rivecuda_flush() with first_* = 0 and the counts returned here. */
+int rivecuda_front_end_fills(rivecuda_ctx* ctx,
+                             const float* points_xy,
+                             uint32_t point_count,
+                             const uint8_t* verbs,
+                             uint32_t verb_count,
+                             const rivecuda_fill_path* paths,
+                             uint32_t path_count,
+                             rivecuda_front_end_result* result);
+
 /* ---- introspection (parity tests, bench) --------------------------------- */
+
+/* Copy bytes [offset, offset + size) of the current device slot of a buffer ring. */
+int rivecuda_debug_read_buffer(rivecuda_ctx* ctx, uint32_t kind, void* host_dst, size_t offset, size_t size);
 
 /* Enable per-kernel CUDA-event timing of subsequent flushes (off by default:
  * the events serialise nothing but cost a few microseconds each). */

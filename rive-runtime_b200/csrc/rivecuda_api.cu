@@ -169,7 +169,7 @@ void rivecuda_destroy(rivecuda_ctx* ctx)
     cudaFree(ctx->tessTexture);
     cudaFree(ctx->atlas);
     for (DeviceBuffer* b : {&ctx->triGeom, &ctx->triAttr, &ctx->tileCounts, &ctx->tileOffsets, &ctx->tileEntries,
-                            &ctx->batchTable, &ctx->imageTable, &ctx->scanScratch, &ctx->clipPlane, &ctx->pathImageSlots, &ctx->atlasTable, &ctx->binCount, &ctx->binPairs, &ctx->hugeList})
+                            &ctx->batchTable, &ctx->imageTable, &ctx->scanScratch, &ctx->clipPlane, &ctx->pathImageSlots, &ctx->atlasTable, &ctx->binCount, &ctx->binPairs, &ctx->hugeList, &ctx->frontEnd})
         b->release();
     cudaFreeHost(ctx->pinnedTotals);
     for (auto& e : ctx->events)

@@ -128,7 +128,7 @@ struct rivecuda_ctx
 
     // Raster work buffers (grow-only).
     rivecuda::DeviceBuffer triGeom, triAttr, tileCounts, tileOffsets, tileEntries, batchTable, imageTable,
-        scanScratch, clipPlane, pathImageSlots, atlasTable, binCount, binPairs, hugeList;
+        scanScratch, clipPlane, pathImageSlots, atlasTable, binCount, binPairs, hugeList, frontEnd;
     uint32_t* pinnedTotals = nullptr; // pinned host words for small D2H results
 
     // Profiling.

@@ -249,6 +249,16 @@ int rivecuda_target_read_pixels_async(rivecuda_ctx* ctx, rivecuda_target* t, voi
 
 int rivecuda_target_read_wait(rivecuda_ctx*, rivecuda_target*) { return 0; }
 
+int rivecuda_front_end_fills(rivecuda_ctx*, const float*, uint32_t, const uint8_t*, uint32_t, const rivecuda_fill_path*, uint32_t, rivecuda_front_end_result*)
+{
+    return fail("rivecuda_trace: the GPU path front end needs a device (the recorder renders nothing)");
+}
+
+int rivecuda_debug_read_buffer(rivecuda_ctx*, uint32_t, void*, size_t, size_t)
+{
+    return fail("rivecuda_trace: no device memory behind the recorder");
+}
+
 int rivecuda_target_write_pixels(rivecuda_ctx* ctx, rivecuda_target* t, const void* host, size_t size)
 {
     Record r;
