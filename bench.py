@@ -320,6 +320,51 @@ def main() -> None:
         pf.desc.render_target = targets[0].value
     e2e_fps = e2e["pipelined"]
 
+    # ---- raw paths in, host frame out: the GPU path front end ------
+    # Same frame, but the host hands over only the RawPaths (verbs + points), matrices
+    # and colours (1.5 MB); segment counts, span allocation and all per-path records are
+    # produced on the device (rivecuda_front_end_fills), then the same flush runs.
+    raw_paths = None
+    dump_path = os.path.join(ROOT, "tests", "golden", "c2_4k.paths.xz")
+    if args.workload == "c2" and os.path.exists(dump_path):
+        from rive_runtime_b200 import front_end as F
+        dump = F.load_paths(dump_path)
+        pf = frames[0][1][0]
+
+        def raw_pass(steps):
+            for n in range(steps):
+                slot = n & 1
+                F.run(rp, dump)
+                pf.desc.render_target = targets[slot].value
+                rp.flush(pf)
+                rp._call("rivecuda_target_read_pixels_async", targets[slot], host_frames[slot].data_ptr(), d2h_bytes)
+                if n > 0:
+                    rp._call("rivecuda_target_read_wait", targets[slot ^ 1])
+            rp._call("rivecuda_target_read_wait", targets[(steps - 1) & 1])
+
+        raw_pass(3)
+        barrier()
+        t0 = time.perf_counter()
+        raw_pass(args.steps)
+        barrier()
+        dt = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            F.run(rp, dump)
+        rp.sync()
+        fe_ms = (time.perf_counter() - t0) / args.steps * 1e3
+        pf.desc.render_target = targets[0].value
+        for kind, data in frames[0][0]:
+            rp.upload_buffer(kind, data)
+        raw_paths = {"value": args.steps / dt, "unit": UNIT, "front_end_ms": fe_ms,
+                     "h2d_bytes_per_step": int(dump.points.nbytes + dump.verbs.nbytes + dump.paths.nbytes),
+                     "d2h_bytes_per_step": d2h_bytes,
+                     "note": "RawPaths + matrices + colours in (host), RGBA8 frame out (host): rivecuda_front_end_fills (Wang's "
+                             "formula counts, warp-scan span allocation, span/contour/path records on the device; byte-identical "
+                             "to the reference front end, tests/test_front_end_gpu.py) + the same flush; front_end_ms includes "
+                             "the H2D of the paths and two stream syncs. The reference's CPU front end alone takes ~16 ms for "
+                             "this frame (host/player, one thread)."}
+
     # ---- CPU baseline (rank 0, N=1 only): bounded sample of the same workload ---
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -355,6 +400,7 @@ def main() -> None:
                     "note": "per frame: H2D of its inputs from pinned rings, flush, D2H of the RGBA8 frame to pinned memory; "
                             "frame k's read-back overlaps frame k+1's rendering (two targets); serial_value waits for each "
                             "read-back before the next frame"},
+            "raw_paths_e2e": raw_paths,
             "gpu_launches": int(launches) * args.steps,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "kernel": "raster_tiles_kernel", "kernel_ms": raster,
