@@ -94,6 +94,7 @@ struct FlushParams
     uint32_t tessVertexCount;
     const float* patchVertices; // 8 floats per PatchVertex
     const uint16_t* patchIndices;
+    const PatchDedup* patchDedup; // [patch type][mirrored]
     const float* featherLUT;
     const uint32_t* gradTexture;
     uint32_t gradHeight;
@@ -840,26 +841,37 @@ __global__ void __launch_bounds__(kSetupWarpsPerBlock * 32) setup_patches_kernel
         const uint32_t inst = item - b.firstWorkItem;
         const int instanceID = static_cast<int>(b.baseElement + inst);
         const bool enableFeather = (b.flags & RIVECUDA_FEATURE_FEATHER) != 0u;
-        // Patch type => vertex range of the static patch vertex buffer.
-        uint32_t vmin, vcount;
+        // Patch type => vertex range of the static patch vertex buffer and tessellation
+        // vertices per instance.
+        uint32_t vmin, patchType, span;
         if (b.drawType == RIVECUDA_DRAW_MIDPOINT_FAN_PATCHES)
         {
             vmin = 0;
-            vcount = 42;
+            patchType = 0;
+            span = 8;
         }
         else if (b.drawType == RIVECUDA_DRAW_MIDPOINT_FAN_CENTER_AA_PATCHES)
         {
             vmin = 42;
-            vcount = 74;
+            patchType = 1;
+            span = 8;
         }
         else
         {
             vmin = 116;
-            vcount = 153;
+            patchType = 2;
+            span = 17;
         }
+        // An instance's tessellation vertices all belong to one contour copy (contours
+        // are padded to whole patches, forward and mirrored copies are allocated apart),
+        // so one flag says which reading of the patch vertex table applies, and with it
+        // which patch vertices shade identically.
+        const bool mirrored = (tess_fetch(P, instanceID * static_cast<int>(span)).w & kMirroredContourFlag) != 0u;
+        const PatchDedup* __restrict__ dedup = P.patchDedup + patchType * 2 + (mirrored ? 1 : 0);
+        const uint32_t uniqueCount = __ldg(&dedup->uniqueCount);
         __syncwarp();
-        for (uint32_t v = lane; v < vcount; v += 32)
-            verts[v] = shade_patch_vertex(P, P.patchVertices + (vmin + v) * 8, instanceID, enableFeather);
+        for (uint32_t u = lane; u < uniqueCount; u += 32)
+            verts[u] = shade_patch_vertex(P, P.patchVertices + __ldg(&dedup->unique[u]) * 8, instanceID, enableFeather);
         __syncwarp();
         const uint32_t tris = b.trisPerElement;
         for (uint32_t tbase = 0; tbase < tris; tbase += 32)
@@ -870,9 +882,9 @@ __global__ void __launch_bounds__(kSetupWarpsPerBlock * 32) setup_patches_kernel
             const uint32_t rawTri = b.firstTriangle + inst * tris + t;
             if (t < tris)
             {
-                const uint32_t i0 = __ldg(P.patchIndices + b.baseIndex + t * 3 + 0) - vmin;
-                const uint32_t i1 = __ldg(P.patchIndices + b.baseIndex + t * 3 + 1) - vmin;
-                const uint32_t i2 = __ldg(P.patchIndices + b.baseIndex + t * 3 + 2) - vmin;
+                const uint32_t i0 = __ldg(&dedup->remap[__ldg(P.patchIndices + b.baseIndex + t * 3 + 0) - vmin]);
+                const uint32_t i1 = __ldg(&dedup->remap[__ldg(P.patchIndices + b.baseIndex + t * 3 + 1) - vmin]);
+                const uint32_t i2 = __ldg(&dedup->remap[__ldg(P.patchIndices + b.baseIndex + t * 3 + 2) - vmin]);
                 const ShadedVertex a = verts[i0], c = verts[i1], d = verts[i2];
                 const uint32_t pathID = a.pathID_ok & 0xffffu; // flat varying: provoking vertex
                 const bool ok = (a.pathID_ok & c.pathID_ok & d.pathID_ok & 0x10000u) != 0u;
@@ -1232,37 +1244,39 @@ constexpr int kSortSmemEntries = 4096;
 
 template <typename Ptr> __device__ __forceinline__ void bitonic_sort(Ptr data, uint32_t n)
 {
-    for (uint32_t k = 2; (k >> 1) < n; k <<= 1)
-    {
-        // First step of each stage mirrors within blocks of k.
-        for (uint32_t i = threadIdx.x; i < n; i += blockDim.x)
+    // One thread per comparator (half as many as elements), n rounded up to a power
+    // of two; comparators whose upper element lies beyond n do nothing.
+    uint32_t padded = 2;
+    while (padded < n)
+        padded <<= 1;
+    const uint32_t comparators = padded >> 1;
+    auto compare_exchange = [&](uint32_t i, uint32_t j) {
+        if (j < n)
         {
-            const uint32_t j = i ^ (k - 1);
-            if (j > i && j < n)
+            const uint32_t a = data[i], b = data[j];
+            if (a > b)
             {
-                const uint32_t a = data[i], b = data[j];
-                if (a > b)
-                {
-                    data[i] = b;
-                    data[j] = a;
-                }
+                data[i] = b;
+                data[j] = a;
             }
         }
-        __syncthreads();
-        for (uint32_t j2 = k >> 2; j2 > 0; j2 >>= 1)
+    };
+    for (uint32_t k = 2; k <= padded; k <<= 1)
+    {
+        // First step of each stage mirrors within blocks of k.
+        const uint32_t half = k >> 1;
+        for (uint32_t c = threadIdx.x; c < comparators; c += blockDim.x)
         {
-            for (uint32_t i = threadIdx.x; i < n; i += blockDim.x)
+            const uint32_t i = ((c & ~(half - 1)) << 1) | (c & (half - 1));
+            compare_exchange(i, i ^ (k - 1));
+        }
+        __syncthreads();
+        for (uint32_t d = k >> 2; d > 0; d >>= 1)
+        {
+            for (uint32_t c = threadIdx.x; c < comparators; c += blockDim.x)
             {
-                const uint32_t j = i ^ j2;
-                if (j > i && j < n)
-                {
-                    const uint32_t a = data[i], b = data[j];
-                    if (a > b)
-                    {
-                        data[i] = b;
-                        data[j] = a;
-                    }
-                }
+                const uint32_t i = ((c & ~(d - 1)) << 1) | (c & (d - 1));
+                compare_exchange(i, i | d);
             }
             __syncthreads();
         }
@@ -1339,6 +1353,7 @@ int launch_draw_list(rivecuda_ctx* ctx, const rivecuda_flush_desc& desc, const r
     P.tessVertexCount = ctx->tessHeight * kTessWidth;
     P.patchVertices = static_cast<const float*>(ctx->patchVertices);
     P.patchIndices = ctx->patchIndices;
+    P.patchDedup = ctx->patchDedup;
     P.featherLUT = ctx->featherLUT;
     P.gradTexture = ctx->gradTexture;
     P.gradHeight = std::max<uint32_t>(desc.grad_data_height, 1u);

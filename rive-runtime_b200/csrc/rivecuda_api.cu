@@ -8,6 +8,7 @@
 #include <cstdarg>
 #include <cstdlib>
 #include <cstring>
+#include <vector>
 
 namespace rivecuda
 {
@@ -164,6 +165,7 @@ void rivecuda_destroy(rivecuda_ctx* ctx)
     }
     cudaFree(ctx->patchVertices);
     cudaFree(ctx->patchIndices);
+    cudaFree(ctx->patchDedup);
     cudaFree(ctx->featherLUT);
     cudaFree(ctx->gradTexture);
     cudaFree(ctx->tessTexture);
@@ -210,6 +212,59 @@ int rivecuda_set_static_tables(rivecuda_ctx* ctx,
     RC_CUDA(cudaMemcpy(ctx->featherLUT, lut, sizeof(lut), cudaMemcpyHostToDevice));
     ctx->patchVertexCount = patch_vertex_count;
     ctx->patchIndexCount = patch_index_count;
+    // De-duplicate each patch type's vertices, for the forward and the mirrored reading of
+    // the table (PatchVertex: localVertexID, outset, fillCoverage, params, then the mirrored
+    // triple; gpu.hpp:547-588). Two vertices shade identically iff they use the same effective
+    // triple and the same params.
+    {
+        const uint32_t firstVertex[3] = {0, 42, 116}, vertexCount[3] = {42, 74, 153};
+        if (patch_vertex_count < 269)
+            return set_error("rivecuda_set_static_tables: expected the 269 patch vertices of gpu::GeneratePatchBufferData");
+        // (Word 0 only chooses which in-patch tessellation vertex the flags are first read
+        // from; the vertex finally used, and so the result, depends on the effective id.
+        // RIVECUDA_DEDUP_STRICT=1 keeps it in the key anyway, for A/B checks.)
+        const bool strictKey = getenv("RIVECUDA_DEDUP_STRICT") != nullptr;
+        std::vector<PatchDedup> dedup(6);
+        const uint32_t* words = static_cast<const uint32_t*>(patch_vertices);
+        for (int type = 0; type < 3; ++type)
+        {
+            for (int mirrored = 0; mirrored < 2; ++mirrored)
+            {
+                PatchDedup& d = dedup[type * 2 + mirrored];
+                memset(&d, 0, sizeof(d));
+                auto key = [&](uint32_t v, uint32_t out[5]) {
+                    const uint32_t* w = words + static_cast<size_t>(firstVertex[type] + v) * 8;
+                    out[0] = strictKey ? w[0] : 0u;
+                    out[1] = w[mirrored ? 4 : 0];
+                    out[2] = w[mirrored ? 5 : 1];
+                    out[3] = w[mirrored ? 6 : 2];
+                    out[4] = w[3];
+                };
+                for (uint32_t v = 0; v < vertexCount[type]; ++v)
+                {
+                    uint32_t kv[5];
+                    key(v, kv);
+                    uint32_t u = 0;
+                    for (; u < d.uniqueCount; ++u)
+                    {
+                        uint32_t ku[5];
+                        key(d.unique[u] - firstVertex[type], ku);
+                        if (memcmp(kv, ku, sizeof(kv)) == 0)
+                            break;
+                    }
+                    if (u == d.uniqueCount)
+                        d.unique[d.uniqueCount++] = static_cast<uint16_t>(firstVertex[type] + v);
+                    d.remap[v] = static_cast<uint8_t>(u);
+                }
+            }
+        }
+        cudaFree(ctx->patchDedup);
+        RC_CUDA(cudaMalloc(reinterpret_cast<void**>(&ctx->patchDedup), dedup.size() * sizeof(PatchDedup)));
+        RC_CUDA(cudaMemcpy(ctx->patchDedup, dedup.data(), dedup.size() * sizeof(PatchDedup), cudaMemcpyHostToDevice));
+        if (getenv("RIVECUDA_VERBOSE"))
+            for (int i = 0; i < 6; ++i)
+                fprintf(stderr, "[rivecuda] patch type %d %s: %u unique of %u vertices\n", i / 2, (i & 1) ? "mirrored" : "forward", dedup[i].uniqueCount, vertexCount[i / 2]);
+    }
     ctx->haveTables = true;
     return 0;
 }

@@ -71,6 +71,19 @@ struct DeviceBatch
     uint32_t reserved;
 };
 
+// Many vertices of a patch are shaded identically (the right edge of one border
+// segment is the left edge of the next): `unique[u]` lists one representative patch
+// vertex per distinct shading input, `remap[v - firstVertex]` maps every patch vertex
+// to its representative's slot. Built on the host from the static patch vertex buffer.
+constexpr int kMaxPatchVertexCount = 153; // gpu::kOuterCurvePatchVertexCount
+struct PatchDedup
+{
+    uint16_t unique[kMaxPatchVertexCount];
+    uint16_t uniqueCount;
+    uint8_t remap[kMaxPatchVertexCount];
+    uint8_t pad;
+};
+
 struct DeviceTexture
 {
     const uint8_t* levels[16];
@@ -115,6 +128,8 @@ struct rivecuda_ctx
     void* patchVertices = nullptr;   // 269 x 32 B
     uint16_t* patchIndices = nullptr; // 441
     uint32_t patchVertexCount = 0, patchIndexCount = 0;
+    // Per (patch type, mirrored?) de-duplication of the patch vertices (see PatchDedup).
+    rivecuda::PatchDedup* patchDedup = nullptr; // device, [3][2]
     float* featherLUT = nullptr;     // [2][512] fp32 (expanded from fp16)
     bool haveTables = false;
 
