@@ -1245,7 +1245,10 @@ constexpr int kSortSmemEntries = 4096;
 template <typename Ptr> __device__ __forceinline__ void bitonic_sort(Ptr data, uint32_t n)
 {
     // One thread per comparator (half as many as elements), n rounded up to a power
-    // of two; comparators whose upper element lies beyond n do nothing.
+    // of two; comparators whose upper element lies beyond n do nothing. Comparator c of
+    // a step at distance d works on element i = c with a 0 inserted at bit log2(d), and
+    // i | d: for d <= 32 the 32 comparators of a warp stay inside that warp's own 64
+    // elements, so those steps (all but a handful) only need a warp-level barrier.
     uint32_t padded = 2;
     while (padded < n)
         padded <<= 1;
@@ -1261,26 +1264,37 @@ template <typename Ptr> __device__ __forceinline__ void bitonic_sort(Ptr data, u
             }
         }
     };
+    // A step that crosses warps must see every warp's previous writes, and so must the
+    // step after it; between two warp-local steps only this warp wrote this warp's data.
+    bool previousCrossed = true;
+    auto barrier = [&](bool crossesWarps) {
+        if (crossesWarps || previousCrossed)
+            __syncthreads();
+        else
+            __syncwarp();
+        previousCrossed = crossesWarps;
+    };
     for (uint32_t k = 2; k <= padded; k <<= 1)
     {
         // First step of each stage mirrors within blocks of k.
         const uint32_t half = k >> 1;
+        barrier(k > 64);
         for (uint32_t c = threadIdx.x; c < comparators; c += blockDim.x)
         {
             const uint32_t i = ((c & ~(half - 1)) << 1) | (c & (half - 1));
             compare_exchange(i, i ^ (k - 1));
         }
-        __syncthreads();
         for (uint32_t d = k >> 2; d > 0; d >>= 1)
         {
+            barrier(d > 32);
             for (uint32_t c = threadIdx.x; c < comparators; c += blockDim.x)
             {
                 const uint32_t i = ((c & ~(d - 1)) << 1) | (c & (d - 1));
                 compare_exchange(i, i | d);
             }
-            __syncthreads();
         }
     }
+    __syncthreads();
 }
 
 __global__ void __launch_bounds__(256) sort_tiles_kernel(const uint32_t* __restrict__ tileOffsets,
