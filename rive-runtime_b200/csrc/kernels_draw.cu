@@ -1664,121 +1664,165 @@ struct AtlasBatchDev
     uint32_t isStroke;
 };
 
-__global__ void __launch_bounds__(128) atlas_kernel(FlushParams P,
-                                                    const AtlasBatchDev* __restrict__ batches,
-                                                    uint32_t batchCount,
-                                                    uint32_t totalTriangles,
-                                                    float* __restrict__ atlas,
-                                                    uint32_t atlasWidth,
-                                                    uint32_t atlasHeight)
+// One atlas triangle, ready to rasterise.
+struct AtlasTriangle
 {
-    for (uint32_t item = blockIdx.x * blockDim.x + threadIdx.x; item < totalTriangles; item += gridDim.x * blockDim.x)
+    EdgeEq E[3];
+    float4 cov[3];
+    double invArea2;
+    int32_t px0, py0, w, h; // pixel bounds (clipped to the batch scissor); w <= 0 => nothing to draw
+    uint32_t isStroke, frontFacing;
+};
+
+__device__ __forceinline__ void atlas_pixel(const FlushParams& P, const AtlasTriangle& T, float* __restrict__ atlas, uint32_t atlasWidth, int x, int y)
+{
+    const int64_t px = (static_cast<int64_t>(x) << 8) + 128, py = (static_cast<int64_t>(y) << 8) + 128;
+    const int64_t e0 = T.E[0].A * px + T.E[0].B * py + T.E[0].C;
+    const int64_t e1 = T.E[1].A * px + T.E[1].B * py + T.E[1].C;
+    const int64_t e2 = T.E[2].A * px + T.E[2].B * py + T.E[2].C;
+    if ((e0 | e1 | e2) < 0)
+        return;
+    // Barycentrics (the top-left bias of at most one unit is far below fp32 resolution here).
+    const float b0 = static_cast<float>(static_cast<double>(e0) * T.invArea2);
+    const float b1 = static_cast<float>(static_cast<double>(e1) * T.invArea2);
+    const float b2 = static_cast<float>(static_cast<double>(e2) * T.invArea2);
+    const float4 c = make_float4(T.cov[0].x * b0 + T.cov[1].x * b1 + T.cov[2].x * b2,
+                                 T.cov[0].y * b0 + T.cov[1].y * b1 + T.cov[2].y * b2,
+                                 T.cov[0].z * b0 + T.cov[1].z * b1 + T.cov[2].z * b2,
+                                 T.cov[0].w * b0 + T.cov[1].w * b1 + T.cov[2].w * b2);
+    // Coverage is accumulated in 16.16 fixed point: integer add / max are associative, so
+    // the atlas is deterministic whatever order the triangles' threads arrive in (the
+    // reference blends in primitive order into an R16F target; fp32 atomics would depend on
+    // scheduling).
+    int* texel = reinterpret_cast<int*>(atlas) + static_cast<size_t>(y) * atlasWidth + x;
+    if (T.isStroke != 0u)
     {
-        uint32_t lo = 0, hi = batchCount;
-        while (hi - lo > 1)
+        const float v = eval_feathered_stroke(P.featherLUT, c.x, c.y);
+        if (v > 0.f)
+            atomicMax(texel, __float2int_rn(v * kAtlasFixedOne));
+    }
+    else
+    {
+        float v = eval_feathered_fill(P.featherLUT, c);
+        if (T.frontFacing == 0u)
+            v = -v;
+        atomicAdd(texel, __float2int_rn(v * kAtlasFixedOne));
+    }
+}
+
+constexpr int kAtlasSerialPixels = 48; // larger bounding boxes are walked by the whole warp
+constexpr int kAtlasWarpsPerBlock = 4;
+
+// One thread per (patch instance, triangle) sets the triangle up; small ones are walked by
+// their own thread, large ones (the fan triangles of big feathered fills) by all 32 lanes.
+__global__ void __launch_bounds__(kAtlasWarpsPerBlock * 32) atlas_kernel(FlushParams P,
+                                                                        const AtlasBatchDev* __restrict__ batches,
+                                                                        uint32_t batchCount,
+                                                                        uint32_t totalTriangles,
+                                                                        float* __restrict__ atlas,
+                                                                        uint32_t atlasWidth,
+                                                                        uint32_t atlasHeight)
+{
+    __shared__ AtlasTriangle s_tri[kAtlasWarpsPerBlock];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (uint32_t base = blockIdx.x * blockDim.x; base < totalTriangles; base += gridDim.x * blockDim.x)
+    {
+        const uint32_t item = base + threadIdx.x;
+        AtlasTriangle T;
+        T.w = 0;
+        T.h = 0;
+        if (item < totalTriangles)
         {
-            uint32_t mid = (lo + hi) >> 1;
-            if (__ldg(&batches[mid].firstWorkItem) <= item)
-                lo = mid;
-            else
-                hi = mid;
-        }
-        const AtlasBatchDev b = batches[lo];
-        const bool isStroke = b.isStroke != 0u;
-        const uint32_t trisPerPatch = isStroke ? 16u : 40u;
-        const uint32_t baseIndex = isStroke ? 0u : 72u;
-        const uint32_t local = item - b.firstWorkItem;
-        const uint32_t inst = local / trisPerPatch, t = local % trisPerPatch;
-        float xs[3], ys[3];
-        float4 cov[3];
-        bool ok = true;
-#pragma unroll
-        for (int k = 0; k < 3; ++k)
-        {
-            const uint32_t vi = __ldg(P.patchIndices + baseIndex + t * 3 + k);
-            const ShadedVertex sv = shade_patch_vertex(P, P.patchVertices + vi * 8, static_cast<int>(b.basePatch + inst), true);
-            ok = ok && (sv.pathID_ok & 0x10000u) != 0u;
-            const uint32_t pathID = sv.pathID_ok & 0xffffu;
-            const uint4 pd2 = __ldg(P.pathBuffer + pathID * 4u + 2u);
-            const float s = __uint_as_float(pd2.y), tx = __uint_as_float(pd2.z), ty = __uint_as_float(pd2.w);
-            xs[k] = sv.x * s + tx;
-            ys[k] = sv.y * s + ty;
-            cov[k] = make_float4(sv.c0, sv.c1, sv.c2, sv.c3);
-        }
-        if (!ok)
-            continue;
-        int32_t X[3], Y[3];
-        if (!(snap_coord(xs[0], X[0]) && snap_coord(ys[0], Y[0]) && snap_coord(xs[1], X[1]) && snap_coord(ys[1], Y[1]) &&
-              snap_coord(xs[2], X[2]) && snap_coord(ys[2], Y[2])))
-            continue;
-        int64_t area2 = (static_cast<int64_t>(X[1]) - X[0]) * (static_cast<int64_t>(Y[2]) - Y[0]) -
-                        (static_cast<int64_t>(X[2]) - X[0]) * (static_cast<int64_t>(Y[1]) - Y[0]);
-        if (area2 == 0)
-            continue;
-        const bool frontFacing = area2 > 0;
-        if (!frontFacing)
-        {
-            if (isStroke)
-                continue;
-            int32_t tmp = X[1];
-            X[1] = X[2];
-            X[2] = tmp;
-            tmp = Y[1];
-            Y[1] = Y[2];
-            Y[2] = tmp;
-            float4 tc = cov[1];
-            cov[1] = cov[2];
-            cov[2] = tc;
-            area2 = -area2;
-        }
-        EdgeEq E[3];
-        edge_equations(X, Y, E);
-        const int32_t minX = min(X[0], min(X[1], X[2])), maxX = max(X[0], max(X[1], X[2]));
-        const int32_t minY = min(Y[0], min(Y[1], Y[2])), maxY = max(Y[0], max(Y[1], Y[2]));
-        const int sx1 = min(static_cast<int>(b.scissorR), static_cast<int>(atlasWidth));
-        const int sy1 = min(static_cast<int>(b.scissorB), static_cast<int>(atlasHeight));
-        const int px0 = max((minX - 128 + 255) >> 8, static_cast<int>(b.scissorL)), px1 = min((maxX - 128) >> 8, sx1 - 1);
-        const int py0 = max((minY - 128 + 255) >> 8, static_cast<int>(b.scissorT)), py1 = min((maxY - 128) >> 8, sy1 - 1);
-        const double inv = 1.0 / static_cast<double>(area2);
-        for (int y = py0; y <= py1; ++y)
-        {
-            const int64_t py = (static_cast<int64_t>(y) << 8) + 128;
-            for (int x = px0; x <= px1; ++x)
+            uint32_t lo = 0, hi = batchCount;
+            while (hi - lo > 1)
             {
-                const int64_t px = (static_cast<int64_t>(x) << 8) + 128;
-                const int64_t e0 = E[0].A * px + E[0].B * py + E[0].C;
-                const int64_t e1 = E[1].A * px + E[1].B * py + E[1].C;
-                const int64_t e2 = E[2].A * px + E[2].B * py + E[2].C;
-                if ((e0 | e1 | e2) < 0)
-                    continue;
-                // Barycentrics (the top-left bias of at most one unit is far
-                // below fp32 resolution here).
-                const float b0 = static_cast<float>(static_cast<double>(e0) * inv);
-                const float b1 = static_cast<float>(static_cast<double>(e1) * inv);
-                const float b2 = static_cast<float>(static_cast<double>(e2) * inv);
-                const float4 c = make_float4(cov[0].x * b0 + cov[1].x * b1 + cov[2].x * b2,
-                                             cov[0].y * b0 + cov[1].y * b1 + cov[2].y * b2,
-                                             cov[0].z * b0 + cov[1].z * b1 + cov[2].z * b2,
-                                             cov[0].w * b0 + cov[1].w * b1 + cov[2].w * b2);
-                // Coverage is accumulated in 16.16 fixed point: integer add / max are
-                // associative, so the atlas is deterministic whatever order the
-                // triangles' threads arrive in (the reference blends in primitive order
-                // into an R16F target; fp32 atomics would depend on scheduling).
-                int* texel = reinterpret_cast<int*>(atlas) + static_cast<size_t>(y) * atlasWidth + x;
-                if (isStroke)
-                {
-                    const float v = eval_feathered_stroke(P.featherLUT, c.x, c.y);
-                    if (v > 0.f)
-                        atomicMax(texel, __float2int_rn(v * kAtlasFixedOne));
-                }
+                uint32_t mid = (lo + hi) >> 1;
+                if (__ldg(&batches[mid].firstWorkItem) <= item)
+                    lo = mid;
                 else
-                {
-                    float v = eval_feathered_fill(P.featherLUT, c);
-                    if (!frontFacing)
-                        v = -v;
-                    atomicAdd(texel, __float2int_rn(v * kAtlasFixedOne));
-                }
+                    hi = mid;
             }
+            const AtlasBatchDev b = batches[lo];
+            const bool isStroke = b.isStroke != 0u;
+            const uint32_t trisPerPatch = isStroke ? 16u : 40u;
+            const uint32_t baseIndex = isStroke ? 0u : 72u;
+            const uint32_t local = item - b.firstWorkItem;
+            const uint32_t inst = local / trisPerPatch, t = local % trisPerPatch;
+            float xs[3], ys[3];
+            bool ok = true;
+#pragma unroll
+            for (int k = 0; k < 3; ++k)
+            {
+                const uint32_t vi = __ldg(P.patchIndices + baseIndex + t * 3 + k);
+                const ShadedVertex sv = shade_patch_vertex(P, P.patchVertices + vi * 8, static_cast<int>(b.basePatch + inst), true);
+                ok = ok && (sv.pathID_ok & 0x10000u) != 0u;
+                const uint32_t pathID = sv.pathID_ok & 0xffffu;
+                const uint4 pd2 = __ldg(P.pathBuffer + pathID * 4u + 2u);
+                const float s = __uint_as_float(pd2.y), tx = __uint_as_float(pd2.z), ty = __uint_as_float(pd2.w);
+                xs[k] = sv.x * s + tx;
+                ys[k] = sv.y * s + ty;
+                T.cov[k] = make_float4(sv.c0, sv.c1, sv.c2, sv.c3);
+            }
+            int32_t X[3], Y[3];
+            ok = ok && snap_coord(xs[0], X[0]) && snap_coord(ys[0], Y[0]) && snap_coord(xs[1], X[1]) && snap_coord(ys[1], Y[1]) &&
+                 snap_coord(xs[2], X[2]) && snap_coord(ys[2], Y[2]);
+            int64_t area2 = 0;
+            if (ok)
+                area2 = (static_cast<int64_t>(X[1]) - X[0]) * (static_cast<int64_t>(Y[2]) - Y[0]) -
+                        (static_cast<int64_t>(X[2]) - X[0]) * (static_cast<int64_t>(Y[1]) - Y[0]);
+            const bool frontFacing = area2 > 0;
+            if (area2 == 0 || (!frontFacing && isStroke))
+                ok = false;
+            if (ok)
+            {
+                if (!frontFacing)
+                {
+                    int32_t tmp = X[1];
+                    X[1] = X[2];
+                    X[2] = tmp;
+                    tmp = Y[1];
+                    Y[1] = Y[2];
+                    Y[2] = tmp;
+                    const float4 tc = T.cov[1];
+                    T.cov[1] = T.cov[2];
+                    T.cov[2] = tc;
+                    area2 = -area2;
+                }
+                edge_equations(X, Y, T.E);
+                const int32_t minX = min(X[0], min(X[1], X[2])), maxX = max(X[0], max(X[1], X[2]));
+                const int32_t minY = min(Y[0], min(Y[1], Y[2])), maxY = max(Y[0], max(Y[1], Y[2]));
+                const int sx1 = min(static_cast<int>(b.scissorR), static_cast<int>(atlasWidth));
+                const int sy1 = min(static_cast<int>(b.scissorB), static_cast<int>(atlasHeight));
+                T.px0 = max((minX - 128 + 255) >> 8, static_cast<int>(b.scissorL));
+                T.py0 = max((minY - 128 + 255) >> 8, static_cast<int>(b.scissorT));
+                T.w = min((maxX - 128) >> 8, sx1 - 1) - T.px0 + 1;
+                T.h = min((maxY - 128) >> 8, sy1 - 1) - T.py0 + 1;
+                T.invArea2 = 1.0 / static_cast<double>(area2);
+                T.isStroke = isStroke ? 1u : 0u;
+                T.frontFacing = frontFacing ? 1u : 0u;
+            }
+        }
+        const bool drawable = T.w > 0 && T.h > 0;
+        const bool large = drawable && T.w * T.h > kAtlasSerialPixels;
+        if (drawable && !large)
+        {
+            for (int y = T.py0; y < T.py0 + T.h; ++y)
+                for (int x = T.px0; x < T.px0 + T.w; ++x)
+                    atlas_pixel(P, T, atlas, atlasWidth, x, y);
+        }
+        uint32_t bigMask = __ballot_sync(0xffffffffu, large);
+        while (bigMask != 0u)
+        {
+            const int src = __ffs(bigMask) - 1;
+            bigMask &= bigMask - 1;
+            __syncwarp();
+            if (lane == src)
+                s_tri[warp] = T;
+            __syncwarp();
+            const AtlasTriangle& B = s_tri[warp];
+            const int total = B.w * B.h;
+            for (int idx = lane; idx < total; idx += 32)
+                atlas_pixel(P, B, atlas, atlasWidth, B.px0 + idx % B.w, B.py0 + idx / B.w);
         }
     }
 }
@@ -1848,7 +1892,7 @@ int launch_atlas(rivecuda_ctx* ctx,
         AtlasBatchDev* dev = ctx->atlasTable.as<AtlasBatchDev>() + (pass == 0 ? 0u : fillCount);
         RC_CUDA(cudaMemcpyAsync(dev, host.data(), static_cast<size_t>(count) * sizeof(AtlasBatchDev), cudaMemcpyHostToDevice, stream));
         const uint32_t blocks = std::min<uint32_t>((totalTriangles + 127) / 128, ctx->smCount * 16);
-        atlas_kernel<<<blocks, 128, 0, stream>>>(P, dev, count, totalTriangles, ctx->atlas, ctx->atlasWidth, ctx->atlasHeight);
+        atlas_kernel<<<blocks, kAtlasWarpsPerBlock * 32, 0, stream>>>(P, dev, count, totalTriangles, ctx->atlas, ctx->atlasWidth, ctx->atlasHeight);
         ctx->lastLaunches += 1;
         RC_CUDA(cudaGetLastError());
     }
