@@ -75,7 +75,10 @@ __device__ void prepare_triangle(const FlushParams& P,
     if ((g.meta & kMetaValid) == 0u)
         return;
     const int32_t X[3] = {g.x0, g.x1, g.x2}, Y[3] = {g.y0, g.y1, g.y2};
-    const int64_t px0 = (static_cast<int64_t>(originX) << 8) + 128, py0 = (static_cast<int64_t>(originY) << 8) + 128;
+    const int32_t px0 = (originX << 8) + 128, py0 = (originY << 8) + 128; // pixel centre of tile pixel (0,0)
+    // Vertices within +-2^29 sub-pixel units (2 M px: everything but pathological input)
+    // keep every difference in int32, so each 64-bit product is ONE widening multiply.
+    const bool narrow = ((abs(X[0]) | abs(X[1]) | abs(X[2]) | abs(Y[0]) | abs(Y[1]) | abs(Y[2])) >> 29) == 0;
     int64_t A[3], B[3], E0u[3];
     int32_t Ai[3], Bi[3], qi[3];
     bool reject = false;
@@ -83,22 +86,56 @@ __device__ void prepare_triangle(const FlushParams& P,
     for (int e = 0; e < 3; ++e)
     {
         const int a = (e + 1) % 3, b = (e + 2) % 3;
-        const int64_t dx = static_cast<int64_t>(X[b]) - X[a], dy = static_cast<int64_t>(Y[b]) - Y[a];
-        const bool topLeft = (dy == 0 && dx > 0) || (dy < 0);
-        A[e] = -dy;
-        B[e] = dx;
-        const int64_t C = dy * X[a] - dx * Y[a];
-        E0u[e] = A[e] * px0 + B[e] * py0 + C;
-        // E(i,j) - bias = E0u - bias + 256*(A*i + B*j) >= 0  <=>  q + A*i + B*j >= 0
-        const int64_t q = (E0u[e] - (topLeft ? 0 : 1)) >> 8;
-        const int64_t n = kTileSize - 1;
-        const int64_t emin = q + n * (A[e] < 0 ? A[e] : 0) + n * (B[e] < 0 ? B[e] : 0);
-        const int64_t emax = q + n * (A[e] > 0 ? A[e] : 0) + n * (B[e] > 0 ? B[e] : 0);
-        if (emax < 0)
-            reject = true;
-        if (emin >= 0)
+        int64_t q;
+        bool fits;
+        if (narrow)
         {
-            Ai[e] = Bi[e] = qi[e] = 0; // true for every pixel of the tile
+            const int32_t dx = X[b] - X[a], dy = Y[b] - Y[a];
+            const bool topLeft = (dy == 0 && dx > 0) || (dy < 0);
+            A[e] = -dy;
+            B[e] = dx;
+            const int64_t C = static_cast<int64_t>(dy) * X[a] - static_cast<int64_t>(dx) * Y[a];
+            E0u[e] = static_cast<int64_t>(-dy) * px0 + static_cast<int64_t>(dx) * py0 + C;
+            q = (E0u[e] - (topLeft ? 0 : 1)) >> 8;
+            const int32_t negSum = min(-dy, 0) + min(dx, 0), posSum = max(-dy, 0) + max(dx, 0); // |.| <= 2^31 - 2
+            const int64_t emin = q + static_cast<int64_t>(negSum) * (kTileSize - 1);
+            const int64_t emax = q + static_cast<int64_t>(posSum) * (kTileSize - 1);
+            if (emax < 0)
+                reject = true;
+            if (emin >= 0)
+            {
+                Ai[e] = Bi[e] = qi[e] = 0; // true for every pixel of the tile
+                continue;
+            }
+            fits = (static_cast<int64_t>(posSum) - negSum) < (1ll << 25);
+        }
+        else
+        {
+            const int64_t dx = static_cast<int64_t>(X[b]) - X[a], dy = static_cast<int64_t>(Y[b]) - Y[a];
+            const bool topLeft = (dy == 0 && dx > 0) || (dy < 0);
+            A[e] = -dy;
+            B[e] = dx;
+            const int64_t C = dy * X[a] - dx * Y[a];
+            E0u[e] = A[e] * px0 + B[e] * py0 + C;
+            // E(i,j) - bias = E0u - bias + 256*(A*i + B*j) >= 0  <=>  q + A*i + B*j >= 0
+            q = (E0u[e] - (topLeft ? 0 : 1)) >> 8;
+            const int64_t n = kTileSize - 1;
+            const int64_t emin = q + n * (A[e] < 0 ? A[e] : 0) + n * (B[e] < 0 ? B[e] : 0);
+            const int64_t emax = q + n * (A[e] > 0 ? A[e] : 0) + n * (B[e] > 0 ? B[e] : 0);
+            if (emax < 0)
+                reject = true;
+            if (emin >= 0)
+            {
+                Ai[e] = Bi[e] = qi[e] = 0;
+                continue;
+            }
+            fits = false;
+        }
+        if (fits)
+        {
+            Ai[e] = static_cast<int32_t>(A[e]);
+            Bi[e] = static_cast<int32_t>(B[e]);
+            qi[e] = static_cast<int32_t>(q);
         }
         else
         {
@@ -123,28 +160,37 @@ __device__ void prepare_triangle(const FlushParams& P,
     const int by0 = max(((minY - 128 + 255) >> 8) - originY, 0), by1 = min(((maxY - 128) >> 8) - originY, kTileSize - 1);
     if (bx0 > bx1 || by0 > by1)
         return;
-    // Classify the eight 8x4 warp blocks (block w: x0 = (w&1)*8, y0 = (w>>1)*4).
-    uint32_t blockMask = 0, fullMask = 0;
-#pragma unroll
-    for (int w = 0; w < 8; ++w)
+    // Classify the eight 8x4 warp blocks (block w: x0 = (w&1)*8, y0 = (w>>1)*4): which ones
+    // the bounding box reaches, which ones every edge reaches (any), which ones lie inside
+    // every edge (all). Per edge, the function's minimum over a block is its value at the
+    // block origin plus a per-edge constant, and the maximum is the minimum plus another.
+    uint32_t bboxMask = (bx0 <= 7 ? 0x55u : 0u) | (bx1 >= 8 ? 0xaau : 0u);
     {
-        const int x0 = (w & 1) * 8, y0 = (w >> 1) * 4;
-        if (bx0 > x0 + 7 || bx1 < x0 || by0 > y0 + 3 || by1 < y0)
-            continue;
-        bool any = true, all = true;
+        uint32_t rows = 0;
 #pragma unroll
-        for (int e = 0; e < 3; ++e)
-        {
-            const int lo = qi[e] + Ai[e] * (Ai[e] < 0 ? x0 + 7 : x0) + Bi[e] * (Bi[e] < 0 ? y0 + 3 : y0);
-            const int hi = qi[e] + Ai[e] * (Ai[e] < 0 ? x0 : x0 + 7) + Bi[e] * (Bi[e] < 0 ? y0 : y0 + 3);
-            any = any && hi >= 0;
-            all = all && lo >= 0;
-        }
-        if (any)
-            blockMask |= 1u << w;
-        if (all)
-            fullMask |= 1u << w;
+        for (int r = 0; r < 4; ++r)
+            if (by0 <= r * 4 + 3 && by1 >= r * 4)
+                rows |= 3u << (r * 2);
+        bboxMask &= rows;
     }
+    uint32_t rejectMask = 0, partialMask = 0; // per block: some edge entirely outside / some edge crossing
+#pragma unroll
+    for (int e = 0; e < 3; ++e)
+    {
+        const int32_t lo0 = qi[e] + min(Ai[e], 0) * 7 + min(Bi[e], 0) * 3; // minimum over block 0
+        const int32_t span = abs(Ai[e]) * 7 + abs(Bi[e]) * 3;             // maximum - minimum
+        const int32_t stepX = Ai[e] * 8, stepY = Bi[e] * 4;
+#pragma unroll
+        for (int w = 0; w < 8; ++w)
+        {
+            const int32_t lo = lo0 + (w & 1) * stepX + (w >> 1) * stepY;
+            if (lo + span < 0)
+                rejectMask |= 1u << w;
+            if (lo < 0)
+                partialMask |= 1u << w;
+        }
+    }
+    const uint32_t blockMask = bboxMask & ~rejectMask, fullMask = blockMask & ~partialMask;
     if (blockMask == 0u)
         return;
     out.A0 = Ai[0];
