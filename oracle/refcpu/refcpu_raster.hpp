@@ -37,7 +37,7 @@ inline bool snap_coord(float v, int64_t* out)
         return false;
     // Clamp far-off vertices (what clipping would bound anyway) so the edge
     // products below stay inside 64 bits.
-    const float lim = 4194304.f; // 2^22 px
+    const float lim = 2097152.f; // 2^21 px: coordinate differences stay inside 31 bits of sub-pixels
     if (v > lim)
         v = lim;
     if (v < -lim)

@@ -443,7 +443,7 @@ __device__ __forceinline__ bool snap_coord(float v, int32_t& out)
 {
     if (!(v == v))
         return false;
-    v = fminf(fmaxf(v, -4194304.f), 4194304.f);
+    v = fminf(fmaxf(v, -2097152.f), 2097152.f); // +-2^21 px: every coordinate difference fits int32 sub-pixels
     out = static_cast<int32_t>(__float2ll_rn(v * 256.f));
     return true;
 }
@@ -484,7 +484,8 @@ __device__ __forceinline__ TileRange triangle_tile_range(const FlushParams& P, c
 
 struct EdgeEq
 {
-    int64_t A, B, C; // E(px,py) = A*px + B*py + C - bias >= 0 inside (sub-pixel units)
+    int32_t A, B; // coordinates are clamped to +-2^29 sub-pixels, so differences fit
+    int64_t C;    // E(px,py) = A*px + B*py + C >= 0 inside (sub-pixel units, top-left bias folded in)
 };
 
 __device__ __forceinline__ void edge_equations(const int32_t X[3], const int32_t Y[3], EdgeEq E[3])
@@ -493,11 +494,11 @@ __device__ __forceinline__ void edge_equations(const int32_t X[3], const int32_t
     for (int e = 0; e < 3; ++e)
     {
         const int a = (e + 1) % 3, b = (e + 2) % 3;
-        const int64_t dx = static_cast<int64_t>(X[b]) - X[a], dy = static_cast<int64_t>(Y[b]) - Y[a];
+        const int32_t dx = X[b] - X[a], dy = Y[b] - Y[a];
         const bool topLeft = (dy == 0 && dx > 0) || (dy < 0);
         E[e].A = -dy;
         E[e].B = dx;
-        E[e].C = dy * X[a] - dx * Y[a] - (topLeft ? 0 : 1);
+        E[e].C = static_cast<int64_t>(dy) * X[a] - static_cast<int64_t>(dx) * Y[a] - (topLeft ? 0 : 1);
     }
 }
 
@@ -505,15 +506,15 @@ __device__ __forceinline__ void edge_equations(const int32_t X[3], const int32_t
 // Exact: evaluates each edge at the tile's most-inside pixel centre.
 __device__ __forceinline__ bool tile_overlaps(const EdgeEq E[3], int tileX, int tileY)
 {
-    const int64_t px0 = (static_cast<int64_t>(tileX) << (kTileSizeLog2 + 8)) + 128;
-    const int64_t py0 = (static_cast<int64_t>(tileY) << (kTileSizeLog2 + 8)) + 128;
-    const int64_t span = static_cast<int64_t>(kTileSize - 1) << 8;
+    const int32_t px0 = (tileX << (kTileSizeLog2 + 8)) + 128;
+    const int32_t py0 = (tileY << (kTileSizeLog2 + 8)) + 128;
+    const int32_t span = (kTileSize - 1) << 8;
 #pragma unroll
     for (int e = 0; e < 3; ++e)
     {
-        const int64_t px = E[e].A > 0 ? px0 + span : px0;
-        const int64_t py = E[e].B > 0 ? py0 + span : py0;
-        if (E[e].A * px + E[e].B * py + E[e].C < 0)
+        const int32_t px = E[e].A > 0 ? px0 + span : px0;
+        const int32_t py = E[e].B > 0 ? py0 + span : py0;
+        if (static_cast<int64_t>(E[e].A) * px + static_cast<int64_t>(E[e].B) * py + E[e].C < 0)
             return false;
     }
     return true;

@@ -76,69 +76,42 @@ __device__ void prepare_triangle(const FlushParams& P,
         return;
     const int32_t X[3] = {g.x0, g.x1, g.x2}, Y[3] = {g.y0, g.y1, g.y2};
     const int32_t px0 = (originX << 8) + 128, py0 = (originY << 8) + 128; // pixel centre of tile pixel (0,0)
-    // Vertices within +-2^29 sub-pixel units (2 M px: everything but pathological input)
-    // keep every difference in int32, so each 64-bit product is ONE widening multiply.
-    const bool narrow = ((abs(X[0]) | abs(X[1]) | abs(X[2]) | abs(Y[0]) | abs(Y[1]) | abs(Y[2])) >> 29) == 0;
-    int64_t A[3], B[3], E0u[3];
+    // Vertices are clamped to +-2^29 sub-pixel units (snap_coord), so every coordinate
+    // difference fits int32 and each 64-bit product below is ONE widening multiply.
+    int32_t A[3], B[3];
+    int64_t E0u[3];
     int32_t Ai[3], Bi[3], qi[3];
     bool reject = false;
 #pragma unroll
     for (int e = 0; e < 3; ++e)
     {
         const int a = (e + 1) % 3, b = (e + 2) % 3;
-        int64_t q;
-        bool fits;
-        if (narrow)
+        const int32_t dx = X[b] - X[a], dy = Y[b] - Y[a];
+        const bool topLeft = (dy == 0 && dx > 0) || (dy < 0);
+        A[e] = -dy;
+        B[e] = dx;
+        const int64_t C = static_cast<int64_t>(dy) * X[a] - static_cast<int64_t>(dx) * Y[a];
+        E0u[e] = static_cast<int64_t>(-dy) * px0 + static_cast<int64_t>(dx) * py0 + C;
+        // E(i,j) - bias = E0u - bias + 256*(A*i + B*j) >= 0  <=>  q + A*i + B*j >= 0
+        const int64_t q = (E0u[e] - (topLeft ? 0 : 1)) >> 8;
+        const int32_t negSum = min(-dy, 0) + min(dx, 0), posSum = max(-dy, 0) + max(dx, 0); // |.| <= 2^31 - 2
+        const int64_t emin = q + static_cast<int64_t>(negSum) * (kTileSize - 1);
+        const int64_t emax = q + static_cast<int64_t>(posSum) * (kTileSize - 1);
+        if (emax < 0)
+            reject = true;
+        if (emin >= 0)
         {
-            const int32_t dx = X[b] - X[a], dy = Y[b] - Y[a];
-            const bool topLeft = (dy == 0 && dx > 0) || (dy < 0);
-            A[e] = -dy;
-            B[e] = dx;
-            const int64_t C = static_cast<int64_t>(dy) * X[a] - static_cast<int64_t>(dx) * Y[a];
-            E0u[e] = static_cast<int64_t>(-dy) * px0 + static_cast<int64_t>(dx) * py0 + C;
-            q = (E0u[e] - (topLeft ? 0 : 1)) >> 8;
-            const int32_t negSum = min(-dy, 0) + min(dx, 0), posSum = max(-dy, 0) + max(dx, 0); // |.| <= 2^31 - 2
-            const int64_t emin = q + static_cast<int64_t>(negSum) * (kTileSize - 1);
-            const int64_t emax = q + static_cast<int64_t>(posSum) * (kTileSize - 1);
-            if (emax < 0)
-                reject = true;
-            if (emin >= 0)
-            {
-                Ai[e] = Bi[e] = qi[e] = 0; // true for every pixel of the tile
-                continue;
-            }
-            fits = (static_cast<int64_t>(posSum) - negSum) < (1ll << 25);
+            Ai[e] = Bi[e] = qi[e] = 0; // true for every pixel of the tile
         }
-        else
+        else if ((static_cast<int64_t>(posSum) - negSum) < (1ll << 25))
         {
-            const int64_t dx = static_cast<int64_t>(X[b]) - X[a], dy = static_cast<int64_t>(Y[b]) - Y[a];
-            const bool topLeft = (dy == 0 && dx > 0) || (dy < 0);
-            A[e] = -dy;
-            B[e] = dx;
-            const int64_t C = dy * X[a] - dx * Y[a];
-            E0u[e] = A[e] * px0 + B[e] * py0 + C;
-            // E(i,j) - bias = E0u - bias + 256*(A*i + B*j) >= 0  <=>  q + A*i + B*j >= 0
-            q = (E0u[e] - (topLeft ? 0 : 1)) >> 8;
-            const int64_t n = kTileSize - 1;
-            const int64_t emin = q + n * (A[e] < 0 ? A[e] : 0) + n * (B[e] < 0 ? B[e] : 0);
-            const int64_t emax = q + n * (A[e] > 0 ? A[e] : 0) + n * (B[e] > 0 ? B[e] : 0);
-            if (emax < 0)
-                reject = true;
-            if (emin >= 0)
-            {
-                Ai[e] = Bi[e] = qi[e] = 0;
-                continue;
-            }
-            fits = false;
-        }
-        if (fits)
-        {
-            Ai[e] = static_cast<int32_t>(A[e]);
-            Bi[e] = static_cast<int32_t>(B[e]);
+            Ai[e] = A[e];
+            Bi[e] = B[e];
             qi[e] = static_cast<int32_t>(q);
         }
         else
         {
+            // Edges longer than 2^17 px: scaled (approximate).
             int64_t a64 = A[e], b64 = B[e], q64 = q;
             while ((a64 < 0 ? -a64 : a64) + (b64 < 0 ? -b64 : b64) >= (1ll << 25))
             {
