@@ -747,8 +747,7 @@ __device__ __forceinline__ bool store_triangle(const FlushParams& P,
     int64_t area2 = 0;
     if (ok)
     {
-        area2 = (static_cast<int64_t>(X[1]) - X[0]) * (static_cast<int64_t>(Y[2]) - Y[0]) -
-                (static_cast<int64_t>(X[2]) - X[0]) * (static_cast<int64_t>(Y[1]) - Y[0]);
+        area2 = static_cast<int64_t>(X[1] - X[0]) * (Y[2] - Y[0]) - static_cast<int64_t>(X[2] - X[0]) * (Y[1] - Y[0]);
         if (area2 == 0 || (area2 < 0 && cullCCW))
             ok = false;
     }

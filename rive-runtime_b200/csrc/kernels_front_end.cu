@@ -570,6 +570,7 @@ int rivecuda_debug_read_buffer(rivecuda_ctx* ctx, uint32_t kind, void* host_dst,
     if (ring.device[ring.current] == nullptr || offset + size > ring.capacity)
         return set_error("rivecuda_debug_read_buffer: range beyond the buffer");
     RC_CUDA(cudaSetDevice(ctx->device));
+    RC_CUDA(cudaStreamSynchronize(ctx->uploadStream));
     RC_CUDA(cudaStreamSynchronize(ctx->stream));
     RC_CUDA(cudaMemcpy(host_dst, static_cast<const uint8_t*>(ring.device[ring.current]) + offset, size, cudaMemcpyDeviceToHost));
     return 0;

@@ -139,7 +139,9 @@ int rivecuda_create(int device, rivecuda_ctx** out_ctx)
     ctx->smCount = prop.multiProcessorCount;
     RC_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     RC_CUDA(cudaStreamCreateWithFlags(&ctx->copyStream, cudaStreamNonBlocking));
+    RC_CUDA(cudaStreamCreateWithFlags(&ctx->uploadStream, cudaStreamNonBlocking));
     RC_CUDA(cudaEventCreateWithFlags(&ctx->renderDone, cudaEventDisableTiming));
+    RC_CUDA(cudaEventCreateWithFlags(&ctx->uploadDone, cudaEventDisableTiming));
     for (auto& e : ctx->events)
         RC_CUDA(cudaEventCreate(&e));
     RC_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&ctx->pinnedTotals), 64 * sizeof(uint32_t), cudaHostAllocDefault));
@@ -178,7 +180,10 @@ void rivecuda_destroy(rivecuda_ctx* ctx)
         cudaEventDestroy(e);
     cudaStreamSynchronize(ctx->copyStream);
     cudaStreamDestroy(ctx->copyStream);
+    cudaStreamSynchronize(ctx->uploadStream);
+    cudaStreamDestroy(ctx->uploadStream);
     cudaEventDestroy(ctx->renderDone);
+    cudaEventDestroy(ctx->uploadDone);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -278,6 +283,7 @@ int rivecuda_buffer_resize(rivecuda_ctx* ctx, uint32_t kind, size_t size)
     if (size == ring.capacity)
         return 0;
     // In-flight copies/kernels may still read the old allocations.
+    RC_CUDA(cudaStreamSynchronize(ctx->uploadStream));
     RC_CUDA(cudaStreamSynchronize(ctx->stream));
     for (int i = 0; i < kRingSize; ++i)
     {
@@ -319,8 +325,15 @@ int rivecuda_buffer_unmap(rivecuda_ctx* ctx, uint32_t kind, size_t size)
     if (size > ring.capacity)
         return set_error("rivecuda_buffer_unmap: size %zu exceeds capacity %zu", size, ring.capacity);
     RC_CUDA(cudaSetDevice(ctx->device));
+    // The H2D goes on the upload stream so that it overlaps the previous frame's kernels; the
+    // next flush waits for it (rivecuda_flush). The ring slot is not in use any more: two
+    // whole flushes, each with a stream synchronisation behind the older work, lie between
+    // two uses of a slot.
     if (size > 0)
-        RC_CUDA(cudaMemcpyAsync(ring.device[ring.current], ring.host[ring.current], size, cudaMemcpyHostToDevice, ctx->stream));
+    {
+        RC_CUDA(cudaMemcpyAsync(ring.device[ring.current], ring.host[ring.current], size, cudaMemcpyHostToDevice, ctx->uploadStream));
+        ctx->uploadsPending = true;
+    }
     ring.submittedBytes = size;
     return 0;
 }
@@ -610,6 +623,12 @@ int rivecuda_flush(rivecuda_ctx* ctx,
     if (desc->tess_data_height > ctx->tessHeight || desc->grad_data_height > ctx->gradHeight)
         return set_error("rivecuda_flush: tessellation/gradient texture smaller than the flush needs");
     RC_CUDA(cudaSetDevice(ctx->device));
+    if (ctx->uploadsPending)
+    {
+        RC_CUDA(cudaEventRecord(ctx->uploadDone, ctx->uploadStream));
+        RC_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->uploadDone, 0));
+        ctx->uploadsPending = false;
+    }
     if (desc->render_target->readPending)
     {
         // An asynchronous read-back of this target may still be in flight.

@@ -118,8 +118,10 @@ struct rivecuda_ctx
 {
     int device = 0;
     cudaStream_t stream = nullptr;
-    cudaStream_t copyStream = nullptr; // asynchronous target read-backs
-    cudaEvent_t renderDone = nullptr;
+    cudaStream_t copyStream = nullptr;   // asynchronous target read-backs (D2H)
+    cudaStream_t uploadStream = nullptr; // buffer ring uploads (H2D), overlapping the previous frame
+    cudaEvent_t renderDone = nullptr, uploadDone = nullptr;
+    bool uploadsPending = false; // buffer uploads enqueued on copyStream since the last flush
     int smCount = 148;
 
     rivecuda::BufferRing rings[RIVECUDA_BUFFER_KIND_COUNT];
