@@ -39,6 +39,7 @@
 #include <cuda_fp16.h>
 
 #include <algorithm>
+#include <memory>
 #include <cstring>
 
 namespace rivecuda
@@ -669,8 +670,11 @@ __global__ void __launch_bounds__(256) bin_huge_kernel(FlushParams P,
                                                        const uint32_t* __restrict__ tileOffsets,
                                                        uint32_t* __restrict__ bigCursors,
                                                        uint32_t* __restrict__ entries,
+                                                       const uint32_t* __restrict__ entryTotal,
                                                        uint32_t entryCapacity)
 {
+    if (SCATTER && __ldg(entryTotal) > entryCapacity)
+        return;
     const uint32_t n = min(*bins.hugeCount, bins.hugeCapacity);
     for (uint32_t item = blockIdx.x; item < n; item += gridDim.x)
     {
@@ -1195,8 +1199,11 @@ __global__ void __launch_bounds__(256) scatter_kernel(FlushParams P,
                                                       const uint32_t* __restrict__ tileOffsets,
                                                       uint32_t* __restrict__ bigCursors,
                                                       uint32_t* __restrict__ entries,
+                                                      const uint32_t* __restrict__ entryTotal,
                                                       uint32_t entryCapacity)
 {
+    if (__ldg(entryTotal) > entryCapacity)
+        return; // the list buffer is too small: the host re-runs this stage (resolve_pending_flush)
     for (uint32_t tBase = blockIdx.x * blockDim.x; tBase < triCount; tBase += gridDim.x * blockDim.x)
     {
         const uint32_t t = tBase + threadIdx.x;
@@ -1299,9 +1306,13 @@ template <typename Ptr> __device__ __forceinline__ void bitonic_sort(Ptr data, u
 
 __global__ void __launch_bounds__(256) sort_tiles_kernel(const uint32_t* __restrict__ tileOffsets,
                                                          const uint32_t* __restrict__ tileCounts,
-                                                         uint32_t* __restrict__ entries)
+                                                         uint32_t* __restrict__ entries,
+                                                         const uint32_t* __restrict__ entryTotal,
+                                                         uint32_t entryCapacity)
 {
     __shared__ uint32_t s_data[kSortSmemEntries];
+    if (__ldg(entryTotal) > entryCapacity)
+        return;
     const uint32_t tile = blockIdx.x;
     const uint32_t n = tileCounts[tile];
     if (n < 2)
@@ -1344,6 +1355,8 @@ static uint32_t premul_clear_color(uint32_t argb)
     };
     return q(r) | (q(g) << 8) | (q(b) << 16) | (q(a) << 24);
 }
+
+int launch_tail(rivecuda_ctx* ctx);
 
 int launch_draw_list(rivecuda_ctx* ctx, const rivecuda_flush_desc& desc, const rivecuda_draw_batch* batches, uint32_t batchCount)
 {
@@ -1394,7 +1407,10 @@ int launch_draw_list(rivecuda_ctx* ctx, const rivecuda_flush_desc& desc, const r
     if (P.boundsL >= P.boundsR || P.boundsT >= P.boundsB)
     {
         if (ctx->profiling)
+        {
             RC_CUDA(cudaEventRecord(ctx->events[5], stream));
+            RC_CUDA(cudaEventRecord(ctx->events[7], stream));
+        }
         return 0;
     }
     P.tileX0 = P.boundsL >> kTileSizeLog2;
@@ -1581,7 +1597,7 @@ int launch_draw_list(rivecuda_ctx* ctx, const rivecuda_flush_desc& desc, const r
     const uint32_t hugeBlocks = static_cast<uint32_t>(ctx->smCount) * 4;
     if (rawTriangles > 0)
     {
-        bin_huge_kernel<false><<<hugeBlocks, 256, 0, stream>>>(P, triGeom, bins, nullptr, nullptr, nullptr, 0u);
+        bin_huge_kernel<false><<<hugeBlocks, 256, 0, stream>>>(P, triGeom, bins, nullptr, nullptr, nullptr, nullptr, 0u);
         ctx->lastLaunches += 1;
         RC_CUDA(cudaGetLastError());
     }
@@ -1599,26 +1615,55 @@ int launch_draw_list(rivecuda_ctx* ctx, const rivecuda_flush_desc& desc, const r
     scan_apply_kernel<<<scanBlocks, kScanBlock, 0, stream>>>(smallCounts, bigCounts, tileCount, blockSums, tileOffsets, tileCounts);
     ctx->lastLaunches += 3;
     RC_CUDA(cudaGetLastError());
+    // The list size (and the huge-queue overflow word) travel to the host asynchronously:
+    // the flush does NOT wait for them. The tail below runs against the buffer we already
+    // have and checks on the device that the lists fit; the host looks at the numbers at its
+    // next synchronisation point and re-runs the tail if they did not (resolve_pending_flush).
     RC_CUDA(cudaMemcpyAsync(ctx->pinnedTotals, total, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
     RC_CUDA(cudaMemcpyAsync(ctx->pinnedTotals + 1, hugeCount + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
-    RC_CUDA(cudaStreamSynchronize(stream));
-    const uint32_t entryCount = ctx->pinnedTotals[0];
-    if (ctx->pinnedTotals[1] != 0u)
-        return set_error("rivecuda_flush: huge-triangle queue overflow (%u chunks dropped)", ctx->pinnedTotals[1]);
+    RC_CUDA(cudaEventRecord(ctx->countsReady, stream));
     ctx->lastTimings.triangle_count = rawTriangles;
-    ctx->lastTimings.tile_entry_count = entryCount;
 
-    if (int s = ctx->tileEntries.reserve((static_cast<size_t>(entryCount) + 1) * sizeof(uint32_t)))
-        return s;
-    uint32_t* entries = ctx->tileEntries.as<uint32_t>();
-    if (entryCount > 0)
+    if (ctx->tileEntries.capacity == 0)
     {
-        const uint32_t blocks = std::min<uint32_t>((rawTriangles + 255) / 256, ctx->smCount * 16);
-        scatter_kernel<<<blocks, 256, 0, stream>>>(P, triGeom, rawTriangles, bins, tileOffsets, bigCursors, entries, entryCount);
-        bin_huge_kernel<true><<<hugeBlocks, 256, 0, stream>>>(P, triGeom, bins, tileOffsets, bigCursors, entries, entryCount);
-        ctx->lastLaunches += 1;
-        sort_tiles_kernel<<<tileCount, 256, 0, stream>>>(tileOffsets, tileCounts, entries);
-        ctx->lastLaunches += 2;
+        // First flush of the context: a guess (grown to the exact need on overflow).
+        if (int s = ctx->tileEntries.reserve((static_cast<size_t>(std::max<uint32_t>(rawTriangles * 2u, 1u << 16)) + 1) * sizeof(uint32_t)))
+            return s;
+    }
+    PendingTail& tail = ctx->pendingTail;
+    tail.params = std::make_shared<FlushParams>(P);
+    tail.triGeom = triGeom;
+    tail.triAttr = triAttr;
+    tail.bins = std::make_shared<BinTables>(bins);
+    tail.tileOffsets = tileOffsets;
+    tail.tileCounts = tileCounts;
+    tail.bigCursors = bigCursors;
+    tail.entryTotal = total;
+    tail.tileCount = tileCount;
+    tail.rawTriangles = rawTriangles;
+    tail.valid = true;
+    return launch_tail(ctx);
+}
+
+// Binning pass 2 + per-tile sort + raster, against the tile-list buffer as it is.
+int launch_tail(rivecuda_ctx* ctx)
+{
+    PendingTail& tail = ctx->pendingTail;
+    cudaStream_t stream = ctx->stream;
+    const FlushParams& P = *static_cast<const FlushParams*>(tail.params.get());
+    const BinTables& bins = *static_cast<const BinTables*>(tail.bins.get());
+    uint32_t* entries = ctx->tileEntries.as<uint32_t>();
+    const uint32_t capacity = static_cast<uint32_t>(std::min<size_t>(ctx->tileEntries.capacity / sizeof(uint32_t), 0xffffffffu)) - 1u;
+    tail.capacity = capacity;
+    const TriGeom* triGeom = static_cast<const TriGeom*>(tail.triGeom);
+    if (tail.rawTriangles > 0)
+    {
+        const uint32_t blocks = std::min<uint32_t>((tail.rawTriangles + 255) / 256, ctx->smCount * 16);
+        const uint32_t hugeBlocks = static_cast<uint32_t>(ctx->smCount) * 4;
+        scatter_kernel<<<blocks, 256, 0, stream>>>(P, triGeom, tail.rawTriangles, bins, tail.tileOffsets, tail.bigCursors, entries, tail.entryTotal, capacity);
+        bin_huge_kernel<true><<<hugeBlocks, 256, 0, stream>>>(P, triGeom, bins, tail.tileOffsets, tail.bigCursors, entries, tail.entryTotal, capacity);
+        sort_tiles_kernel<<<tail.tileCount, 256, 0, stream>>>(tail.tileOffsets, tail.tileCounts, entries, tail.entryTotal, capacity);
+        ctx->lastLaunches += 3;
         RC_CUDA(cudaGetLastError());
     }
     if (ctx->profiling)
@@ -1629,7 +1674,7 @@ int launch_draw_list(rivecuda_ctx* ctx, const rivecuda_flush_desc& desc, const r
         cudaMemcpyToSymbol(g_rasterStats, zero, sizeof(zero));
     }
 #endif
-    raster_tiles_kernel<<<tileCount, 256, 0, stream>>>(P, triGeom, triAttr, tileOffsets, tileCounts, entries);
+    raster_tiles_kernel<<<tail.tileCount, 256, 0, stream>>>(P, triGeom, static_cast<const TriAttr*>(tail.triAttr), tail.tileOffsets, tail.tileCounts, entries, tail.entryTotal, capacity);
     ctx->lastLaunches += 1;
 #ifdef RIVECUDA_STATS
     {
@@ -1642,7 +1687,30 @@ int launch_draw_list(rivecuda_ctx* ctx, const rivecuda_flush_desc& desc, const r
         fprintf(stderr, "[stats] warp resolves %llu lanes with coverage %llu\n", st[30], st[31]);
     }
 #endif
+    if (ctx->profiling)
+        RC_CUDA(cudaEventRecord(ctx->events[7], stream));
     return check_cuda(cudaGetLastError(), "raster_tiles_kernel");
+}
+
+// Called at every host synchronisation point (next flush, sync, read-back, timings, destroy):
+// by now the list size of the last flush has arrived. If the lists did not fit, the tail
+// skipped itself on the device (the target is untouched): grow the buffer and run it again.
+int resolve_pending_flush(rivecuda_ctx* ctx)
+{
+    PendingTail& tail = ctx->pendingTail;
+    if (!tail.valid)
+        return 0;
+    RC_CUDA(cudaEventSynchronize(ctx->countsReady));
+    const uint32_t entryCount = ctx->pinnedTotals[0];
+    ctx->lastTimings.tile_entry_count = entryCount;
+    tail.valid = false;
+    if (ctx->pinnedTotals[1] != 0u)
+        return set_error("rivecuda_flush: huge-triangle queue overflow (%u chunks dropped)", ctx->pinnedTotals[1]);
+    if (entryCount <= tail.capacity)
+        return 0;
+    if (int s = ctx->tileEntries.reserve((static_cast<size_t>(entryCount) + 1) * sizeof(uint32_t)))
+        return s;
+    return launch_tail(ctx);
 }
 } // namespace rivecuda
 

@@ -803,9 +803,16 @@ __global__ void __launch_bounds__(256, RIVECUDA_RASTER_MIN_BLOCKS) raster_tiles_
                                                               const TriAttr* __restrict__ triAttr,
                                                               const uint32_t* __restrict__ tileOffsets,
                                                               const uint32_t* __restrict__ tileCounts,
-                                                              const uint32_t* __restrict__ entries)
+                                                              const uint32_t* __restrict__ entries,
+                                                              const uint32_t* __restrict__ entryTotal,
+                                                              uint32_t entryCapacity)
 {
     __shared__ __align__(16) Prepared s_prep[kRasterChunk];
+    // The tile lists did not fit the buffer they were given: nothing has been written to
+    // them and nothing may be drawn; the host re-runs scatter / sort / raster with a larger
+    // buffer (resolve_pending_flush). The target is untouched.
+    if (__ldg(entryTotal) > entryCapacity)
+        return;
     const uint32_t tile = blockIdx.x;
     const uint32_t n = tileCounts[tile];
     // Nothing drawn here and the target is preserved (later logical flushes of a

@@ -142,6 +142,7 @@ int rivecuda_create(int device, rivecuda_ctx** out_ctx)
     RC_CUDA(cudaStreamCreateWithFlags(&ctx->uploadStream, cudaStreamNonBlocking));
     RC_CUDA(cudaEventCreateWithFlags(&ctx->renderDone, cudaEventDisableTiming));
     RC_CUDA(cudaEventCreateWithFlags(&ctx->uploadDone, cudaEventDisableTiming));
+    RC_CUDA(cudaEventCreateWithFlags(&ctx->countsReady, cudaEventDisableTiming));
     for (auto& e : ctx->events)
         RC_CUDA(cudaEventCreate(&e));
     RC_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&ctx->pinnedTotals), 64 * sizeof(uint32_t), cudaHostAllocDefault));
@@ -151,6 +152,8 @@ int rivecuda_create(int device, rivecuda_ctx** out_ctx)
 
 void rivecuda_destroy(rivecuda_ctx* ctx)
 {
+    if (ctx != nullptr)
+        rivecuda::resolve_pending_flush(ctx);
     if (ctx == nullptr)
         return;
     cudaSetDevice(ctx->device);
@@ -184,6 +187,7 @@ void rivecuda_destroy(rivecuda_ctx* ctx)
     cudaStreamDestroy(ctx->uploadStream);
     cudaEventDestroy(ctx->renderDone);
     cudaEventDestroy(ctx->uploadDone);
+    cudaEventDestroy(ctx->countsReady);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -276,6 +280,8 @@ int rivecuda_set_static_tables(rivecuda_ctx* ctx,
 
 int rivecuda_buffer_resize(rivecuda_ctx* ctx, uint32_t kind, size_t size)
 {
+    if (int pending = rivecuda::resolve_pending_flush(ctx))
+        return pending;
     if (kind >= RIVECUDA_BUFFER_KIND_COUNT)
         return set_error("rivecuda_buffer_resize: bad kind %u", kind);
     RC_CUDA(cudaSetDevice(ctx->device));
@@ -340,6 +346,8 @@ int rivecuda_buffer_unmap(rivecuda_ctx* ctx, uint32_t kind, size_t size)
 
 int rivecuda_resize_gradient_texture(rivecuda_ctx* ctx, uint32_t width, uint32_t height)
 {
+    if (int pending = rivecuda::resolve_pending_flush(ctx))
+        return pending;
     if (width != 0 && width != kGradWidth)
         return set_error("rivecuda_resize_gradient_texture: width must be %d", kGradWidth);
     RC_CUDA(cudaSetDevice(ctx->device));
@@ -356,6 +364,8 @@ int rivecuda_resize_gradient_texture(rivecuda_ctx* ctx, uint32_t width, uint32_t
 
 int rivecuda_resize_tessellation_texture(rivecuda_ctx* ctx, uint32_t width, uint32_t height)
 {
+    if (int pending = rivecuda::resolve_pending_flush(ctx))
+        return pending;
     if (width != 0 && width != kTessWidth)
         return set_error("rivecuda_resize_tessellation_texture: width must be %d", kTessWidth);
     RC_CUDA(cudaSetDevice(ctx->device));
@@ -372,6 +382,8 @@ int rivecuda_resize_tessellation_texture(rivecuda_ctx* ctx, uint32_t width, uint
 
 int rivecuda_resize_feather_atlas_texture(rivecuda_ctx* ctx, uint32_t width, uint32_t height)
 {
+    if (int pending = rivecuda::resolve_pending_flush(ctx))
+        return pending;
     RC_CUDA(cudaSetDevice(ctx->device));
     RC_CUDA(cudaStreamSynchronize(ctx->stream));
     cudaFree(ctx->atlas);
@@ -420,6 +432,8 @@ int rivecuda_target_wrap(rivecuda_ctx*, uint32_t width, uint32_t height, void* d
 
 void rivecuda_target_destroy(rivecuda_ctx* ctx, rivecuda_target* target)
 {
+    if (ctx != nullptr)
+        rivecuda::resolve_pending_flush(ctx);
     if (target == nullptr)
         return;
     cudaSetDevice(ctx->device);
@@ -434,6 +448,8 @@ void rivecuda_target_destroy(rivecuda_ctx* ctx, rivecuda_target* target)
 
 int rivecuda_target_read_pixels(rivecuda_ctx* ctx, const rivecuda_target* target, void* host, size_t size)
 {
+    if (int pending = rivecuda::resolve_pending_flush(ctx))
+        return pending;
     size_t bytes = static_cast<size_t>(target->width) * target->height * 4;
     if (size < bytes)
         return set_error("rivecuda_target_read_pixels: destination too small");
@@ -445,6 +461,8 @@ int rivecuda_target_read_pixels(rivecuda_ctx* ctx, const rivecuda_target* target
 
 int rivecuda_target_read_pixels_async(rivecuda_ctx* ctx, rivecuda_target* target, void* host, size_t size)
 {
+    if (int pending = rivecuda::resolve_pending_flush(ctx))
+        return pending;
     size_t bytes = static_cast<size_t>(target->width) * target->height * 4;
     if (size < bytes)
         return set_error("rivecuda_target_read_pixels_async: destination too small");
@@ -471,6 +489,8 @@ int rivecuda_target_read_wait(rivecuda_ctx* ctx, rivecuda_target* target)
 
 int rivecuda_target_write_pixels(rivecuda_ctx* ctx, rivecuda_target* target, const void* host, size_t size)
 {
+    if (int pending = rivecuda::resolve_pending_flush(ctx))
+        return pending;
     size_t bytes = static_cast<size_t>(target->width) * target->height * 4;
     if (size < bytes)
         return set_error("rivecuda_target_write_pixels: source too small");
@@ -541,6 +561,8 @@ int rivecuda_texture_create(rivecuda_ctx* ctx,
 
 void rivecuda_texture_destroy(rivecuda_ctx* ctx, rivecuda_texture* texture)
 {
+    if (ctx != nullptr)
+        rivecuda::resolve_pending_flush(ctx);
     if (texture == nullptr)
         return;
     cudaSetDevice(ctx->device);
@@ -570,6 +592,8 @@ int rivecuda_renderbuffer_create(rivecuda_ctx* ctx, uint32_t type, uint32_t flag
 
 void rivecuda_renderbuffer_destroy(rivecuda_ctx* ctx, rivecuda_renderbuffer* rb)
 {
+    if (ctx != nullptr)
+        rivecuda::resolve_pending_flush(ctx);
     if (rb == nullptr)
         return;
     cudaSetDevice(ctx->device);
@@ -623,6 +647,10 @@ int rivecuda_flush(rivecuda_ctx* ctx,
     if (desc->tess_data_height > ctx->tessHeight || desc->grad_data_height > ctx->gradHeight)
         return set_error("rivecuda_flush: tessellation/gradient texture smaller than the flush needs");
     RC_CUDA(cudaSetDevice(ctx->device));
+    // The previous flush's list sizes have long arrived: check them (and re-run its raster
+    // stage if its tile lists outgrew the buffer) before this flush reuses the work buffers.
+    if (int pending = rivecuda::resolve_pending_flush(ctx))
+        return pending;
     if (ctx->uploadsPending)
     {
         RC_CUDA(cudaEventRecord(ctx->uploadDone, ctx->uploadStream));
@@ -675,10 +703,7 @@ int rivecuda_flush(rivecuda_ctx* ctx,
     if (int s = launch_draw_list(ctx, *desc, batches, batchCount))
         return s;
     if (prof)
-    {
-        RC_CUDA(cudaEventRecord(ctx->events[6], ctx->stream));
-        ctx->timingsPending = true;
-    }
+        ctx->timingsPending = true; // events[7] was recorded behind the raster kernel
     ctx->lastTimings.kernel_launches = ctx->lastLaunches;
     return 0;
 }
@@ -687,6 +712,8 @@ int rivecuda_post_flush(rivecuda_ctx*) { return 0; }
 
 int rivecuda_sync(rivecuda_ctx* ctx)
 {
+    if (int pending = rivecuda::resolve_pending_flush(ctx))
+        return pending;
     RC_CUDA(cudaSetDevice(ctx->device));
     RC_CUDA(cudaStreamSynchronize(ctx->stream));
     return 0;
@@ -706,6 +733,8 @@ int rivecuda_set_profiling(rivecuda_ctx* ctx, int enabled)
 
 int rivecuda_get_flush_timings(rivecuda_ctx* ctx, rivecuda_flush_timings* out)
 {
+    if (int pending = rivecuda::resolve_pending_flush(ctx))
+        return pending;
     RC_CUDA(cudaSetDevice(ctx->device));
     RC_CUDA(cudaStreamSynchronize(ctx->stream));
     if (ctx->timingsPending)
@@ -719,8 +748,9 @@ int rivecuda_get_flush_timings(rivecuda_ctx* ctx, rivecuda_flush_timings* out)
         ctx->lastTimings.tessellate_ms = ms(1, 2);
         ctx->lastTimings.atlas_ms = ms(2, 3);
         ctx->lastTimings.setup_bin_ms = ms(3, 5);
-        ctx->lastTimings.raster_ms = ms(5, 6);
-        ctx->lastTimings.total_ms = ms(0, 6);
+        ctx->lastTimings.raster_ms = ms(5, 7);
+        ctx->lastTimings.total_ms = ms(0, 7);
+        ctx->lastTimings.kernel_launches = ctx->lastLaunches;
         ctx->timingsPending = false;
     }
     *out = ctx->lastTimings;

@@ -10,6 +10,7 @@
 
 #include <cstdint>
 #include <cstdio>
+#include <memory>
 #include <string>
 #include <vector>
 
@@ -114,13 +115,29 @@ struct rivecuda_renderbuffer
     void* device = nullptr;
 };
 
+// The last flush's binning pass 2 + sort + raster ("tail"), kept so that it can be run
+// again with a larger tile-list buffer if the device found the lists did not fit.
+struct PendingTail
+{
+    bool valid = false;
+    std::shared_ptr<void> params, bins; // FlushParams / BinTables (types private to kernels_draw.cu)
+    const void* triGeom = nullptr;
+    const void* triAttr = nullptr;
+    uint32_t* tileOffsets = nullptr;
+    uint32_t* tileCounts = nullptr;
+    uint32_t* bigCursors = nullptr;
+    const uint32_t* entryTotal = nullptr;
+    uint32_t tileCount = 0, rawTriangles = 0, capacity = 0;
+};
+
 struct rivecuda_ctx
 {
     int device = 0;
     cudaStream_t stream = nullptr;
     cudaStream_t copyStream = nullptr;   // asynchronous target read-backs (D2H)
     cudaStream_t uploadStream = nullptr; // buffer ring uploads (H2D), overlapping the previous frame
-    cudaEvent_t renderDone = nullptr, uploadDone = nullptr;
+    cudaEvent_t renderDone = nullptr, uploadDone = nullptr, countsReady = nullptr;
+    PendingTail pendingTail;
     bool uploadsPending = false; // buffer uploads enqueued on copyStream since the last flush
     int smCount = 148;
 
@@ -177,4 +194,5 @@ int launch_draw_list(rivecuda_ctx* ctx,
                      const rivecuda_flush_desc& desc,
                      const rivecuda_draw_batch* batches,
                      uint32_t batchCount);
+int resolve_pending_flush(rivecuda_ctx* ctx);
 } // namespace rivecuda
