@@ -1304,6 +1304,54 @@ template <typename Ptr> __device__ __forceinline__ void bitonic_sort(Ptr data, u
     __syncthreads();
 }
 
+// The same network for lists that fit one comparator per thread (n <= 512: almost every
+// tile), fully unrolled: distances and barrier kinds are compile-time constants, the list
+// is padded with 0xffffffff so no comparator needs a bounds check.
+template <int PADDED> __device__ __forceinline__ void bitonic_sort_padded(uint32_t* __restrict__ data)
+{
+    const uint32_t c = threadIdx.x;
+    const bool active = c < PADDED / 2;
+    auto compare_exchange = [&](uint32_t i, uint32_t j) {
+        const uint32_t a = data[i], b = data[j];
+        if (a > b)
+        {
+            data[i] = b;
+            data[j] = a;
+        }
+    };
+    bool previousCrossed = true; // folds away: every use is in unrolled code
+#pragma unroll
+    for (int k = 2; k <= PADDED; k <<= 1)
+    {
+        const int half = k >> 1;
+        if (k > 64 || previousCrossed)
+            __syncthreads();
+        else
+            __syncwarp();
+        previousCrossed = k > 64;
+        if (active)
+        {
+            const uint32_t i = ((c & ~static_cast<uint32_t>(half - 1)) << 1) | (c & static_cast<uint32_t>(half - 1));
+            compare_exchange(i, i ^ static_cast<uint32_t>(k - 1));
+        }
+#pragma unroll
+        for (int d = k >> 2; d > 0; d >>= 1)
+        {
+            if (d > 32 || previousCrossed)
+                __syncthreads();
+            else
+                __syncwarp();
+            previousCrossed = d > 32;
+            if (active)
+            {
+                const uint32_t i = ((c & ~static_cast<uint32_t>(d - 1)) << 1) | (c & static_cast<uint32_t>(d - 1));
+                compare_exchange(i, i | static_cast<uint32_t>(d));
+            }
+        }
+    }
+    __syncthreads();
+}
+
 __global__ void __launch_bounds__(256) sort_tiles_kernel(const uint32_t* __restrict__ tileOffsets,
                                                          const uint32_t* __restrict__ tileCounts,
                                                          uint32_t* __restrict__ entries,
@@ -1318,7 +1366,24 @@ __global__ void __launch_bounds__(256) sort_tiles_kernel(const uint32_t* __restr
     if (n < 2)
         return;
     uint32_t* list = entries + tileOffsets[tile];
-    if (n <= kSortSmemEntries)
+    if (n <= 512)
+    {
+        const uint32_t padded = n <= 64 ? 64u : (n <= 128 ? 128u : (n <= 256 ? 256u : 512u));
+        for (uint32_t i = threadIdx.x; i < padded; i += blockDim.x)
+            s_data[i] = i < n ? list[i] : 0xffffffffu;
+        // (bitonic_sort_padded starts with a block barrier)
+        if (padded == 64u)
+            bitonic_sort_padded<64>(s_data);
+        else if (padded == 128u)
+            bitonic_sort_padded<128>(s_data);
+        else if (padded == 256u)
+            bitonic_sort_padded<256>(s_data);
+        else
+            bitonic_sort_padded<512>(s_data);
+        for (uint32_t i = threadIdx.x; i < n; i += blockDim.x)
+            list[i] = s_data[i];
+    }
+    else if (n <= kSortSmemEntries)
     {
         for (uint32_t i = threadIdx.x; i < n; i += blockDim.x)
             s_data[i] = list[i];
