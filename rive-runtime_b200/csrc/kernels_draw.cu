@@ -1692,7 +1692,12 @@ int launch_draw_list(rivecuda_ctx* ctx, const rivecuda_flush_desc& desc, const r
     if (ctx->tileEntries.capacity == 0)
     {
         // First flush of the context: a guess (grown to the exact need on overflow).
-        if (int s = ctx->tileEntries.reserve((static_cast<size_t>(std::max<uint32_t>(rawTriangles * 2u, 1u << 16)) + 1) * sizeof(uint32_t)))
+        // (RIVECUDA_INITIAL_TILE_ENTRIES overrides the guess; tests use it to force the
+        // overflow path.)
+        size_t guess = std::max<uint32_t>(rawTriangles * 2u, 1u << 16);
+        if (const char* env = getenv("RIVECUDA_INITIAL_TILE_ENTRIES"))
+            guess = static_cast<size_t>(strtoull(env, nullptr, 10));
+        if (int s = ctx->tileEntries.reserve((guess + 1) * sizeof(uint32_t)))
             return s;
     }
     PendingTail& tail = ctx->pendingTail;

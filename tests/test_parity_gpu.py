@@ -184,3 +184,20 @@ def test_reference_front_end_drives_the_cuda_backend(libs, scene, trace_name, si
         px = np.fromfile(out, dtype=np.uint8)
     assert px.size == got.size
     assert np.array_equal(px.reshape(got.shape), got)
+
+
+def test_tile_list_overflow_is_rerun_transparently(libs, monkeypatch):
+    """A flush never waits for the size of its tile lists: it runs scatter / sort / raster
+    against the buffer it has, the device checks that the lists fit, and the host re-runs
+    those kernels with a larger buffer at its next synchronisation point if they did not.
+    Forcing a tiny first buffer must not change a single pixel, for a clearing flush, for
+    a preserving multi-flush sequence and for an animation."""
+    replay, T, _ = libs
+    for name in ("beziers", "preserverendertarget", "c1", "anim_juice"):
+        recs = T.parse(os.path.join(GOLDEN, name + ".rvct.xz"))
+        monkeypatch.delenv("RIVECUDA_INITIAL_TILE_ENTRIES", raising=False)
+        want = replay.replay(recs).frames
+        monkeypatch.setenv("RIVECUDA_INITIAL_TILE_ENTRIES", "7")
+        got = replay.replay(recs).frames
+        assert len(got) == len(want)
+        assert all(np.array_equal(a, b) for a, b in zip(got, want)), name
