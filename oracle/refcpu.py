@@ -118,7 +118,7 @@ class ReplayResult:
 
 
 def replay(records: List[T.Record], threads: int = 1, keep_intermediates: bool = True,
-           max_frames: Optional[int] = None) -> ReplayResult:
+           max_frames: Optional[int] = None, only_frames: Optional[set] = None) -> ReplayResult:
     """Run every flush of a trace through the oracle; returns the frames read
     back (one per RVCT_TARGET_READ) and, per flush, the gradient / tessellation /
     atlas textures the oracle produced."""
@@ -169,6 +169,8 @@ def replay(records: List[T.Record], threads: int = 1, keep_intermediates: bool =
         elif r.tag == T.RENDERBUFFER_UNMAP:
             data = np.ascontiguousarray(r.data)
             renderbuffers[r.fields["id"]] = (RefRenderBuffer(data.ctypes.data, data.size), data)
+        elif r.tag == T.FLUSH and only_frames is not None and len(out.frames) not in only_frames:
+            continue  # a frame the caller does not want (frames are independent: each starts with its own load action)
         elif r.tag == T.FLUSH:
             fr: T.FlushRecord = r.fields["flush"]
             d = fr.desc
@@ -222,7 +224,8 @@ def replay(records: List[T.Record], threads: int = 1, keep_intermediates: bool =
             else:
                 out.flushes.append(FlushOutputs(d))
         elif r.tag == T.TARGET_READ:
-            out.frames.append(targets[r.fields["id"]].copy())
+            skipped = only_frames is not None and len(out.frames) not in only_frames
+            out.frames.append(None if skipped else targets[r.fields["id"]].copy())
             if max_frames is not None and len(out.frames) >= max_frames:
                 break
     return out

@@ -1,0 +1,77 @@
+"""The front end's per-curve arithmetic, pinned against the reference's own output: every
+TessVertexSpan in the committed traces carries the curve's control points and the parametric
+segment count PathDraw::initForMidpointFan computed for it; the numpy restatement of Wang's
+formula (oracle/front_end_ref.py) must reproduce all of them bit for bit. Also checks the
+`--dump-paths` reader against the traces' path / contour counts."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN
+from oracle import front_end_ref
+from rive_runtime_b200 import front_end as F, trace as T
+
+
+def spans_and_matrices(name):
+    recs = T.parse(os.path.join(GOLDEN, name))
+    bufs = {}
+    out = []
+    for r in recs:
+        if r.tag == T.BUFFER_UNMAP:
+            bufs[r.fields["kind"]] = r.data
+        elif r.tag == T.FLUSH:
+            d = r.fields["flush"].desc
+            if d.tess_vertex_span_count == 0:
+                continue
+            spans = np.frombuffer(bufs[6].tobytes(), dtype=np.uint32).reshape(-1, 16)[
+                d.first_tess_vertex_span:d.first_tess_vertex_span + d.tess_vertex_span_count]
+            contours = np.frombuffer(bufs[4].tobytes(), dtype=np.uint32).reshape(-1, 4)[d.first_contour:]
+            paths = np.frombuffer(bufs[1].tobytes(), dtype=np.float32).reshape(-1, 16)[d.first_path:]
+            # Outer-curve patches (interior triangulation) always have 16 segments; their spans
+            # live behind the midpoint-fan region of the tessellation buffer.
+            outer = [b.base_element * 17 for b in r.fields["flush"].batches if b.draw_type == 2]
+            out.append((spans, contours, paths, min(outer) if outer else 1 << 30))
+    return out
+
+
+@pytest.mark.parametrize("name", ["c2_4k.rvct.xz", "f1.rvct.xz", "c1.rvct.xz", "beziers.rvct.xz", "strokes_round.rvct.xz",
+                                  "cubicpath.rvct.xz", "anim_db_health_tracker.rvct.xz"])
+def test_wang_segment_counts_match_the_reference(name):
+    checked = 0
+    for spans, contours, paths, outer_start in spans_and_matrices(name):
+        contour_id = spans[:, 15] & 0xffff
+        x0 = ((spans[:, 12].astype(np.int64) & 0xffff) ^ 0x8000) - 0x8000
+        location = spans[:, 10].view(np.float32).astype(np.int64) * 2048 + x0
+        real = spans[(contour_id > 0) & (location < outer_start)]
+        cid = (real[:, 15] & 0xffff).astype(np.int64) - 1
+        path_id = contours[cid, 2] & 0xffff
+        rec = paths[path_id]
+        matrix = rec[:, :6]
+        feather = rec[:, 7]
+        retrofit = (real[:, 15] >> 31) != 0  # retrofitted triangle strips carry no curve
+        keep = (feather == 0) & ~retrofit
+        pts = real[keep][:, :8].view(np.float32).reshape(-1, 4, 2)
+        want = real[keep][:, 14] & 0x3ff
+        # Lines are stored as the cubic convert_line_to_cubic() makes and always get 1 segment;
+        # zero-length "curves" carrying only a cap/join get 0. Everything else is Wang's formula.
+        got = front_end_ref.wang_cubic_segments(pts, matrix[keep])
+        is_curve = want > 1
+        assert np.array_equal(got[is_curve], want[is_curve]), name
+        # where the reference says 0 or 1 the formula may only say 1 (lines) -- never more for
+        # a real cubic that the reference counted as 1
+        assert np.all(got[~is_curve & (want == 1)] >= 1)
+        checked += int(is_curve.sum())
+    assert checked > 0
+
+
+@pytest.mark.parametrize("name", ["c2_4k", "f1"])
+def test_path_dump_reader(name):
+    dump = F.load_paths(os.path.join(GOLDEN, name + ".paths.xz"))
+    recs = T.parse(os.path.join(GOLDEN, name + ".rvct.xz"))
+    d = next(r.fields["flush"].desc for r in recs if r.tag == T.FLUSH)
+    assert dump.complete
+    assert dump.paths.size == d.path_count - 1           # path 0 is the flush's reserved record
+    assert int((dump.verbs == 0).sum()) == d.contour_count  # one contour per moveTo
+    assert int(dump.paths["verb_count"].sum()) == dump.verbs.size
+    assert dump.points.shape[0] >= int((dump.verbs == 4).sum()) * 3
