@@ -401,6 +401,8 @@ __device__ float4 sample_grad(const FlushParams& P, float u, float v)
     return make_float4(top.x + (bot.x - top.x) * ty, top.y + (bot.y - top.y) * ty, top.z + (bot.z - top.z) * ty, top.w + (bot.w - top.w) * ty);
 }
 
+__device__ __forceinline__ float round_to_half(float v) { return __half2float(__float2half_rn(v)); }
+
 __device__ float sample_atlas(const FlushParams& P, float u, float v)
 {
     const float x = u * P.atlasWidth - .5f, y = v * P.atlasHeight - .5f;
@@ -410,14 +412,15 @@ __device__ float sample_atlas(const FlushParams& P, float u, float v)
     auto fetch = [&](int xx, int yy) {
         xx = min(max(xx, 0), static_cast<int>(P.atlasWidth) - 1);
         yy = min(max(yy, 0), static_cast<int>(P.atlasHeight) - 1);
-        return static_cast<float>(__ldg(reinterpret_cast<const int*>(P.atlas) + static_cast<size_t>(yy) * P.atlasWidth + xx)) * (1.f / kAtlasFixedOne);
+        // The reference's atlas is an R16F texture: what the sampler sees is the coverage
+        // sum rounded to half precision.
+        return round_to_half(static_cast<float>(__ldg(reinterpret_cast<const int*>(P.atlas) + static_cast<size_t>(yy) * P.atlasWidth + xx)) * (1.f / kAtlasFixedOne));
     };
     const float a = fetch(ix, iy) + (fetch(ix + 1, iy) - fetch(ix, iy)) * tx;
     const float b = fetch(ix, iy + 1) + (fetch(ix + 1, iy + 1) - fetch(ix, iy + 1)) * tx;
     return a + (b - a) * ty;
 }
 
-__device__ __forceinline__ float round_to_half(float v) { return __half2float(__float2half_rn(v)); }
 
 // Shared-memory loads by 32-bit shared address: keeps the walk loop's addressing
 // to one add per triangle (no generic-to-shared conversion per iteration).
