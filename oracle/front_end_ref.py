@@ -35,3 +35,56 @@ def wang_cubic_segments(pts: np.ndarray, matrix: np.ndarray, precision: float = 
         n = np.ceil(np.sqrt(np.sqrt(n4.astype(F)).astype(F)).astype(F))
         n = np.clip(n, F(1), F(1023))
     return n.astype(np.uint32)
+
+
+def find_max_scale(m: np.ndarray) -> np.ndarray:
+    """Mat2D::findMaxScale (src/math/mat2d_find_max_scale.cpp:24-60), float32, vectorised."""
+    m = m.astype(F)
+    xx, xy, yx, yy = m[:, 0], m[:, 1], m[:, 2], m[:, 3]
+    simple = (xy == 0) & (yx == 0)
+    a = xx * xx + xy * xy
+    b = xx * yx + yy * xy
+    c = yx * yx + yy * yy
+    b2 = b * b
+    eps = F(1.0 / (1 << 12))  # math::EPSILON
+    aminusc = a - c
+    x = np.sqrt(aminusc * aminusc + F(4) * b2).astype(F) * F(.5)
+    result = np.where(b2 <= eps * eps, np.maximum(a, c), (a + c) * F(.5) + x).astype(F)
+    return np.where(simple, np.maximum(np.abs(xx), np.abs(yy)), np.sqrt(result).astype(F)).astype(F)
+
+
+def fast_acos(x: np.ndarray) -> np.ndarray:
+    """simd::fast_acos (include/rive/math/simd.hpp:496-507)."""
+    x = x.astype(F)
+    a, b, c, d = F(-0.939115566365855), F(0.9217841528914573), F(-1.2845906244690837), F(0.295624144969963174)
+    xx = x * x
+    numer = b * xx + a
+    denom = xx * (d * xx + c) + F(1)
+    return x * (numer / denom) + F(1.5707963267948966)
+
+
+def polar_segments(pts: np.ndarray, matrix: np.ndarray, stroke_radius: np.ndarray, precision: int = 8) -> np.ndarray:
+    """Polar segment count of a stroked (already chopped) cubic: the rotation between its end
+    tangents, times calc_polar_segments_per_radian<kPolarPrecision = 8>(strokeRadius * maxScale)
+    (bezier_utils.hpp:108-113; draw.cpp:776-813, 1203-1232), clamped to [1, 1023]."""
+    p = pts.astype(F)
+
+    def first_distinct(a, b, c, d):
+        # (a != b ? b : b != c ? c : d)
+        ne_ab = (a != b).any(axis=1)[:, None]
+        ne_bc = (b != c).any(axis=1)[:, None]
+        return np.where(ne_ab, b, np.where(ne_bc, c, d))
+
+    t0 = first_distinct(p[:, 0], p[:, 1], p[:, 2], p[:, 3]) - p[:, 0]
+    t1 = p[:, 3] - first_distinct(p[:, 3], p[:, 2], p[:, 1], p[:, 0])
+    with np.errstate(invalid="ignore", divide="ignore"):
+        numer = t0[:, 0] * t1[:, 0] + t0[:, 1] * t1[:, 1]
+        denom2 = (t0[:, 0] * t0[:, 0] + t0[:, 1] * t0[:, 1]) * (t1[:, 0] * t1[:, 0] + t1[:, 1] * t1[:, 1])
+        cos_theta = np.clip(numer / np.sqrt(denom2).astype(F), F(-1), F(1))
+        theta = fast_acos(cos_theta)
+        r = stroke_radius.astype(F) * find_max_scale(matrix)
+        cos_step = F(1) - (F(1) / F(precision)) / r
+        per_radian = F(.5) / np.arccos(np.maximum(cos_step, F(-1)).astype(F)).astype(F)
+        n = np.ceil(theta * per_radian)
+        n = np.clip(n, F(1), F(1023))
+    return np.nan_to_num(n, nan=1.0).astype(np.uint32)

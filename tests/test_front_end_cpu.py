@@ -75,3 +75,24 @@ def test_path_dump_reader(name):
     assert int((dump.verbs == 0).sum()) == d.contour_count  # one contour per moveTo
     assert int(dump.paths["verb_count"].sum()) == dump.verbs.size
     assert dump.points.shape[0] >= int((dump.verbs == 4).sum()) * 3
+
+
+@pytest.mark.parametrize("name", ["beziers.rvct.xz", "strokes_round.rvct.xz", "c1.rvct.xz", "strokes_poly.rvct.xz",
+                                  "trickycubicstrokes.rvct.xz", "c3.rvct.xz", "roundjoinstrokes.rvct.xz",
+                                  "anim_db_health_tracker.rvct.xz"])
+def test_polar_segment_counts_match_the_reference(name):
+    """Stroked curves: the polar segment count in every span equals the restatement of
+    fast_acos(rotation between end tangents) * calc_polar_segments_per_radian<8>(radius * maxScale)."""
+    checked = 0
+    for spans, contours, paths, _ in spans_and_matrices(name):
+        real = spans[(spans[:, 15] & 0xffff) > 0]
+        cid = (real[:, 15] & 0xffff).astype(np.int64) - 1
+        rec = paths[contours[cid, 2] & 0xffff]
+        stroke, feather = rec[:, 6], rec[:, 7]
+        keep = (stroke != 0) & (feather == 0) & ((real[:, 14] & 0x3ff) > 0)  # real curves, not cap/join carriers
+        pts = real[keep][:, :8].view(np.float32).reshape(-1, 4, 2)
+        want = (real[keep][:, 14] >> 10) & 0x3ff
+        got = front_end_ref.polar_segments(pts, rec[keep][:, :6], stroke[keep])
+        assert np.array_equal(got, want), name
+        checked += int(keep.sum())
+    assert checked > 0
