@@ -45,7 +45,6 @@ WORKLOADS = {
     "c4": ("c4: db_health_tracker artboard animation, 63 frames per pass at 1920x1080 (BASELINE.json configs[3])",
            os.path.join(ROOT, "tests", "golden", "anim_db_health_tracker.rvct.xz"), "frames/sec at 1080p (device-timed)"),
 }
-WORKLOAD, TRACE, METRIC = WORKLOADS["c2"]
 UNIT = "frames/s"
 
 

@@ -67,7 +67,6 @@ constexpr uint32_t kMetaModulatedImage = 1u << 28; // batch has ENABLE_MODULATED
 constexpr uint32_t kMetaClipRect = 1u << 27;       // image meshes: batch has ENABLE_CLIP_RECT
 constexpr uint32_t kMetaClipping = 1u << 26;       // image meshes: batch has ENABLE_CLIPPING
 constexpr uint32_t kMetaSimplePaint = 1u << 25;    // set by the rasteriser's prepare step, never stored
-constexpr uint32_t kMetaSmallMasks = 1u << 24;     // likewise: the Prepared record holds pixel masks, not edges
 constexpr uint32_t kMetaKindShift = 16;
 
 struct TriGeom // 32 B
@@ -521,28 +520,9 @@ __device__ __forceinline__ bool tile_overlaps(const EdgeEq E[3], int tileX, int 
     return true;
 }
 
-// Visits the tiles a triangle overlaps (absolute tile index = ty*tilesX+tx in
-// the flush's tile grid).
-template <typename Fn> __device__ __forceinline__ void for_each_tile(const FlushParams& P, const int32_t X[3], const int32_t Y[3], Fn&& fn)
-{
-    const TileRange r = triangle_tile_range(P, X, Y);
-    if (r.tx0 > r.tx1)
-        return;
-    const bool single = (r.tx0 == r.tx1) && (r.ty0 == r.ty1);
-    EdgeEq E[3];
-    edge_equations(X, Y, E);
-    for (int ty = r.ty0; ty <= r.ty1; ++ty)
-    {
-        for (int tx = r.tx0; tx <= r.tx1; ++tx)
-        {
-            if (single || tile_overlaps(E, tx + P.tileX0, ty + P.tileY0))
-                fn(static_cast<uint32_t>(ty) * P.tilesX + static_cast<uint32_t>(tx));
-        }
-    }
-}
-
-// Warp-cooperative version: every lane of the warp calls this (valid = lane has
-// a triangle). Triangles that overlap only a few tiles are walked by their own
+// Visits the tiles a triangle overlaps (tile index = ty*tilesX+tx in the flush's tile
+// grid), warp-cooperatively: every lane of the warp calls this (valid = lane has a
+// triangle). Triangles that overlap only a few tiles are walked by their own
 // lane; larger ones are broadcast one at a time and their tile range is tested
 // by all 32 lanes in parallel, so a full-screen triangle costs tiles/32
 // iterations instead of stalling one lane. fn(tile, ownerLane, cooperative) is

@@ -35,7 +35,7 @@ namespace
 constexpr uint32_t kPatchSpan = 8;       // gpu::kMidpointFanPatchSegmentSpan
 constexpr uint32_t kOuterPatchSpan = 17; // gpu::OuterCubicPatchSegmentSpanPlusJoin
 constexpr uint32_t kMaxParametricSegments = 1023;
-constexpr uint8_t kVerbMove = 0, kVerbLine = 1, kVerbQuad = 2, kVerbCubic = 4, kVerbClose = 5; // rive::PathVerb
+constexpr uint8_t kVerbMove = 0, kVerbLine = 1, kVerbCubic = 4; // rive::PathVerb (quad 2 never reaches the renderer; close 5 is implicit for fills)
 
 struct PathTotals // scanned per path
 {

@@ -182,7 +182,7 @@ int launch_tessellate(rivecuda_ctx* ctx,
                       const void* tessSpans,
                       const void* pathBuffer,
                       const void* contourBuffer);
-// kernels_atlas.cu
+// kernels_draw.cu
 int launch_atlas(rivecuda_ctx* ctx,
                  const rivecuda_flush_desc& desc,
                  const rivecuda_atlas_batch* fills,

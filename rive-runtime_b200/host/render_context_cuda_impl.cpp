@@ -127,6 +127,13 @@ bool RenderTargetCUDA::readPixels(std::vector<uint8_t>* rgba8) const
                                     rgba8->size()) == 0;
 }
 
+bool RenderTargetCUDA::readPixelsAsync(uint8_t* pinnedRGBA8, size_t sizeInBytes)
+{
+    return m_abi.target_read_pixels_async(m_ctx, m_handle, pinnedRGBA8, sizeInBytes) == 0;
+}
+
+bool RenderTargetCUDA::waitForRead() { return m_abi.target_read_wait(m_ctx, m_handle) == 0; }
+
 bool RenderTargetCUDA::writePixels(const uint8_t* rgba8, size_t sizeInBytes)
 {
     return m_abi.target_write_pixels(m_ctx, m_handle, rgba8, sizeInBytes) == 0;

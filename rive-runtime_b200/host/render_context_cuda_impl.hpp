@@ -57,6 +57,12 @@ public:
     // (row-major, top-down, width*height*4 bytes).
     bool readPixels(std::vector<uint8_t>* rgba8) const;
     bool writePixels(const uint8_t* rgba8, size_t sizeInBytes);
+    // Pipelined presentation: enqueue the read-back of what has been flushed into this
+    // target so far into `pinnedRGBA8` (cudaHostAlloc'd or otherwise page-locked memory)
+    // and return at once; flushes into other targets overlap the copy.
+    // waitForRead() blocks until the pixels are there.
+    bool readPixelsAsync(uint8_t* pinnedRGBA8, size_t sizeInBytes);
+    bool waitForRead();
 
 private:
     friend class RenderContextCUDAImpl;
