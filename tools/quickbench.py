@@ -18,7 +18,7 @@ for it in range(N + 3):
         rp.flush(pf)
         tm = rp.timings()
         if it >= 3:
-            for k in ("tessellate_ms", "setup_bin_ms", "raster_ms", "total_ms"):
+            for k in ("tessellate_ms", "atlas_ms", "setup_bin_ms", "raster_ms", "total_ms"):
                 acc[k] = acc.get(k, 0) + getattr(tm, k)
 print(os.environ.get("RIVECUDA_LIB", "default"), {k: round(v / N, 4) for k, v in acc.items()})
 rp.close()
