@@ -39,11 +39,16 @@ WORKLOADS = {
     # name -> (description, trace, metric)
     "c2": ("c2: 10k random filled 4-cubic paths, nonZero/evenOdd, 3840x2160 (BASELINE.json configs[1])",
            os.path.join(ROOT, "tests", "golden", "c2_4k.rvct.xz"), "frames/sec at 4K (device-timed)"),
-    # BASELINE.json configs[3]: an artboard animation at 1080p, frames sharded over the GPUs. The stream is
-    # the reference's own 63-frame db_health_tracker.sriv (tests/unit_tests/silvers) replayed through
-    # RiveRenderer; one step = one pass over the 63 frames, frame i -> rank i mod N.
-    "c4": ("c4: db_health_tracker artboard animation, 63 frames per pass at 1920x1080 (BASELINE.json configs[3])",
-           os.path.join(ROOT, "tests", "golden", "anim_db_health_tracker.rvct.xz"), "frames/sec at 1080p (device-timed)"),
+    # BASELINE.json configs[3]: an artboard state-machine animation at 1080p. The frames are what the
+    # reference's unmodified core runtime produced for its own off_road_car.riv test asset (File::import ->
+    # StateMachineInstance::advanceAndApply(1/60) -> Artboard::draw -> RiveRenderer; host/player `riv:`),
+    # 60 frames per pass; every GPU renders its own instance of the animation.
+    "c4": ("c4: off_road_car.riv artboard state-machine animation, 60 frames per pass at 1920x1080 "
+           "(BASELINE.json configs[3])",
+           os.path.join(ROOT, "tests", "golden", "riv_off_road_car.rvct.xz"), "frames/sec at 1080p (device-timed)"),
+    # The same through a recorded renderer-call stream (.sriv silver) of a UI-style artboard with text.
+    "c4sriv": ("c4sriv: db_health_tracker artboard animation (.sriv stream), 63 frames per pass at 1920x1080",
+               os.path.join(ROOT, "tests", "golden", "anim_db_health_tracker.rvct.xz"), "frames/sec at 1080p (device-timed)"),
 }
 UNIT = "frames/s"
 
