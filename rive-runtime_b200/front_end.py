@@ -34,26 +34,33 @@ class PathDump:
     paths: np.ndarray   # structured array with FillPath's layout
     verbs: np.ndarray   # uint8
     points: np.ndarray  # float32 (n, 2)
-    complete: bool      # every draw of the frame was a simple fill
+    complete: bool      # every draw of the frame was a plain fill or stroke
+    strokes: np.ndarray = None  # structured (is_stroke, thickness, join, cap) per path; zeros for "RPTH" dumps
 
 
 PATH_DTYPE = np.dtype([("first_verb", "<u4"), ("verb_count", "<u4"), ("first_point", "<u4"), ("fill_rule", "<u4"),
                        ("matrix", "<f4", (6,)), ("color", "<u4"), ("reserved0", "<u4")])
 assert PATH_DTYPE.itemsize == 48
+STROKE_DTYPE = np.dtype([("is_stroke", "<u4"), ("thickness", "<f4"), ("join", "<u4"), ("cap", "<u4")])
 
 
 def load_paths(path: str) -> PathDump:
     raw = lzma.open(path, "rb").read() if path.endswith(".xz") else open(path, "rb").read()
     magic, count, complete, _ = struct.unpack_from("<4I", raw, 0)
-    if magic != 0x48545052:
+    if magic not in (0x48545052, 0x32545052):  # "RPTH" (fills only), "RPT2" (+ stroke fields)
         raise ValueError("not a path dump")
+    v2 = magic == 0x32545052
     paths = np.zeros(count, dtype=PATH_DTYPE)
+    strokes = np.zeros(count, dtype=STROKE_DTYPE)
     verbs, points = [], []
     pos, nv, npnt = 16, 0, 0
     for i in range(count):
         m = struct.unpack_from("<6f", raw, pos)
         rule, color, n_verbs, n_pts = struct.unpack_from("<4I", raw, pos + 24)
         pos += 40
+        if v2:
+            strokes[i] = struct.unpack_from("<IfII", raw, pos)
+            pos += 16
         verbs.append(np.frombuffer(raw, dtype=np.uint8, count=n_verbs, offset=pos))
         pos += (n_verbs + 3) & ~3
         points.append(np.frombuffer(raw, dtype=np.float32, count=n_pts * 2, offset=pos))
@@ -62,7 +69,7 @@ def load_paths(path: str) -> PathDump:
         nv += n_verbs
         npnt += n_pts
     return PathDump(paths, np.concatenate(verbs) if verbs else np.zeros(0, np.uint8),
-                    (np.concatenate(points) if points else np.zeros(0, np.float32)).reshape(-1, 2), bool(complete))
+                    (np.concatenate(points) if points else np.zeros(0, np.float32)).reshape(-1, 2), bool(complete), strokes)
 
 
 def run(replayer, dump: PathDump) -> FrontEndResult:

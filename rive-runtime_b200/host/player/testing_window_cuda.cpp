@@ -7,6 +7,7 @@
  * compile here because it references every other backend).
  */
 #include "testing_window_cuda.hpp"
+#include "path_dump.hpp"
 
 #include "rive/renderer/rive_renderer.hpp"
 
@@ -86,7 +87,10 @@ std::unique_ptr<rive::Renderer> TestingWindowCUDA::beginFrame(
         .clockwiseFillOverride = false,
     };
     m_renderContext->beginFrame(frameDescriptor);
-    return std::make_unique<RiveRenderer>(m_renderContext.get());
+    std::unique_ptr<rive::Renderer> renderer = std::make_unique<RiveRenderer>(m_renderContext.get());
+    if (m_pathDump != nullptr && m_pathDump->active)
+        renderer = std::make_unique<PathDumpRenderer>(std::move(renderer), m_pathDump);
+    return renderer;
 }
 
 void TestingWindowCUDA::flushPLSContext(RenderTarget* offscreenRenderTarget)
@@ -103,6 +107,8 @@ void TestingWindowCUDA::flushPLSContext(RenderTarget* offscreenRenderTarget)
 void TestingWindowCUDA::endFrame(std::vector<uint8_t>* pixelData)
 {
     flushPLSContext(nullptr);
+    if (m_pathDump != nullptr)
+        m_pathDump->active = false; // only the first frame is dumped
     if (pixelData != nullptr)
     {
         m_renderTarget->readPixels(pixelData);

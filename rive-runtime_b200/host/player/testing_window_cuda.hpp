@@ -24,7 +24,12 @@ public:
     rive::gpu::RenderContext* renderContext() const override;
     rive::gpu::RenderTarget* renderTarget() const override;
 
+    // --dump-paths: renderers handed out by beginFrame() record the plain draws of the first
+    // frame into `sink` (path_dump.hpp).
+    void setPathDump(struct PathDumpSink* sink) { m_pathDump = sink; }
+
 private:
+    struct PathDumpSink* m_pathDump = nullptr;
     std::unique_ptr<rive::gpu::RenderContext> m_renderContext;
     rive::rcp<rive::gpu::RenderTargetCUDA> m_renderTarget;
     uint64_t m_frameNumber = 0;
