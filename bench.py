@@ -327,7 +327,7 @@ def main() -> None:
     # ---- raw paths in, host frame out: the GPU path front end ------
     # Same frame, but the host hands over only the RawPaths (verbs + points), matrices
     # and colours (1.5 MB); segment counts, span allocation and all per-path records are
-    # produced on the device (rivecuda_front_end_fills), then the same flush runs.
+    # produced on the device (rivecuda_front_end_paths), then the same flush runs.
     raw_paths = None
     dump_path = os.path.join(ROOT, "tests", "golden", "c2_4k.paths.xz")
     if args.workload == "c2" and os.path.exists(dump_path):
@@ -338,7 +338,7 @@ def main() -> None:
         def raw_pass(steps):
             for n in range(steps):
                 slot = n & 1
-                F.run(rp, dump)
+                F.run(rp, dump, width, height)
                 pf.desc.render_target = targets[slot].value
                 rp.flush(pf)
                 rp._call("rivecuda_target_read_pixels_async", targets[slot], host_frames[slot].data_ptr(), d2h_bytes)
@@ -354,7 +354,7 @@ def main() -> None:
         dt = time.perf_counter() - t0
         t0 = time.perf_counter()
         for _ in range(args.steps):
-            F.run(rp, dump)
+            F.run(rp, dump, width, height)
         rp.sync()
         fe_ms = (time.perf_counter() - t0) / args.steps * 1e3
         pf.desc.render_target = targets[0].value
@@ -363,7 +363,7 @@ def main() -> None:
         raw_paths = {"value": args.steps / dt, "unit": UNIT, "front_end_ms": fe_ms,
                      "h2d_bytes_per_step": int(dump.points.nbytes + dump.verbs.nbytes + dump.paths.nbytes),
                      "d2h_bytes_per_step": d2h_bytes,
-                     "note": "RawPaths + matrices + colours in (host), RGBA8 frame out (host): rivecuda_front_end_fills (Wang's "
+                     "note": "RawPaths + matrices + colours in (host), RGBA8 frame out (host): rivecuda_front_end_paths (Wang's "
                              "formula counts, warp-scan span allocation, span/contour/path records on the device; byte-identical "
                              "to the reference front end, tests/test_front_end_gpu.py) + the same flush; front_end_ms includes "
                              "the H2D of the paths and two stream syncs. The reference's CPU front end alone takes ~16 ms for "

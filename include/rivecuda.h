@@ -301,18 +301,29 @@ int rivecuda_stream(rivecuda_ctx* ctx, void** out_stream);
 
 /* ---- GPU path front end -------------------------------- */
 
-/* One filled path: a slice of the caller's verb / point arrays (rive::RawPath layout:
- * include/rive/math/raw_path.hpp; PathVerb values move 0, line 1, cubic 4, close 5), its
- * view matrix (Mat2D::values() order xx, xy, yx, yy, tx, ty), fill rule and colour. */
-typedef struct rivecuda_fill_path
+/* One plain path draw (solid colour, src-over, no feather, no clip): a slice of the caller's
+ * verb / point arrays (rive::RawPath layout: include/rive/math/raw_path.hpp; PathVerb values
+ * move 0, line 1, cubic 4, close 5), its view matrix (Mat2D::values() order xx, xy, yx, yy, tx,
+ * ty), colour, and either a fill rule or the stroke parameters. The two derived stroke scalars
+ * are what PathDraw::initForMidpointFan computes once per path with libm (draw.cpp:776-813):
+ *   matrix_max_scale           = Mat2D::findMaxScale()
+ *   polar_segments_per_radian  = math::calc_polar_segments_per_radian<8>(stroke_radius * matrix_max_scale)
+ *                                (include/rive/math/bezier_utils.hpp:108-113) */
+typedef struct rivecuda_path
 {
     uint32_t first_verb, verb_count;
     uint32_t first_point;
-    uint32_t fill_rule; /* 0 nonZero, 1 evenOdd */
+    uint32_t fill_rule; /* fills: 0 nonZero, 1 evenOdd */
     float matrix[6];
     uint32_t color;     /* rive::ColorInt, 0xAARRGGBB, unpremultiplied */
+    uint32_t stroke;    /* 0 fill, 1 stroke */
+    float stroke_radius; /* RenderPaint thickness * .5, at least FLT_MIN (draw.cpp:603-607) */
+    uint32_t join;      /* rive::StrokeJoin: miter 0, round 1, bevel 2 */
+    uint32_t cap;       /* rive::StrokeCap: butt 0, round 1, square 2 */
+    float polar_segments_per_radian;
+    float matrix_max_scale;
     uint32_t reserved0;
-} rivecuda_fill_path;
+} rivecuda_path;
 
 /* What the host needs to fill in the FlushDescriptor / the one midpointFanPatches batch. */
 typedef struct rivecuda_front_end_result
@@ -326,7 +337,7 @@ typedef struct rivecuda_front_end_result
     uint32_t reserved0;
 } rivecuda_front_end_result;
 
-/* Device-side replacement, for non-feathered nonZero / evenOdd solid-colour fills, of the
+/* Device-side replacement, for non-feathered solid-colour nonZero / evenOdd fills and strokes, of the
  * per-path CPU work the reference does before a flush: PathDraw::initForMidpointFan
  * (renderer/src/draw.cpp:768-1392; Wang's-formula segment counts, contour padding),
  * LogicalFlush::allocateMidpointFanTessVertices (render_context.cpp:3019; prefix-summed span
@@ -335,14 +346,20 @@ typedef struct rivecuda_front_end_result
  * (render_context.cpp:3037). Writes the TessVertexSpan, ContourData, PathData, PaintData and
  * PaintAuxData records, in the reference's byte layout, into fresh slots of the context's
  * buffer rings (as if the host had mapped, written and unmapped them); the caller then
- * issues rivecuda_flush() with first_* = 0 and the counts returned here. */
-int rivecuda_front_end_fills(rivecuda_ctx* ctx,
+ * issues rivecuda_flush() with first_* = 0 and the counts returned here.
+ * A non-zero frame size applies PathDraw::Make's frame cull (draw.cpp:439-509): paths whose
+ * pixel bounds (outset for strokes) miss the render target produce no records, as in the
+ * reference. The caller skips what RiveRenderer::drawPath skips before that point (empty
+ * RawPaths, strokes with !(thickness > 0); rive_renderer.cpp:127-145). */
+int rivecuda_front_end_paths(rivecuda_ctx* ctx,
                              const float* points_xy,
                              uint32_t point_count,
                              const uint8_t* verbs,
                              uint32_t verb_count,
-                             const rivecuda_fill_path* paths,
+                             const rivecuda_path* paths,
                              uint32_t path_count,
+                             uint32_t frame_width,
+                             uint32_t frame_height,
                              rivecuda_front_end_result* result);
 
 /* ---- introspection (parity tests, bench) --------------------------------- */

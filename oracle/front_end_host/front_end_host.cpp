@@ -1,0 +1,63 @@
+/*
+ * TEST INFRASTRUCTURE ONLY (see oracle/__init__.py): a host build of the GPU path front end's
+ * per-contour core (rive-runtime_b200/csrc/front_end_core.h, the code the F1 kernels run per
+ * thread), driven by three serial loops in place of the three kernels and two prefix scans.
+ * tests/test_front_end_cpu.py compares its output byte for byte with the spans / contours / path
+ * records the reference front end wrote into the committed flush traces, so the stroke and fill
+ * arithmetic is checked on every CPU run of the suite; tests/test_front_end_gpu.py then checks
+ * that the kernels produce the same bytes on the device. Nothing in the product links this.
+ */
+#include "front_end_core.h"
+
+#include <vector>
+
+using namespace rivecuda::fe;
+
+extern "C" int front_end_host_paths(const float* pointsXY,
+                                    const uint8_t* verbs,
+                                    const rivecuda_path* paths,
+                                    uint32_t pathCount,
+                                    uint32_t frameWidth, // 0: no frame cull
+                                    uint32_t frameHeight,
+                                    uint32_t* spans,     // capacity in 64-byte records
+                                    uint32_t spanCapacity,
+                                    uint32_t* contours,  // 16-byte records
+                                    uint32_t* pathData,  // 64-byte records, record 0 reserved
+                                    uint32_t* paintData, // 8-byte records
+                                    uint32_t* paintAux,  // 128-byte records
+                                    rivecuda_front_end_result* result)
+{
+    const V2* points = reinterpret_cast<const V2*>(pointsXY);
+    std::vector<PathTotals> own(pathCount), prefix(pathCount);
+    PathTotals sum = {0, 0, 0, 0};
+    for (uint32_t i = 0; i < pathCount; ++i)
+    {
+        own[i] = count_path(paths[i], points, verbs, frameWidth, frameHeight);
+        prefix[i] = sum;
+        sum.tessVertices += own[i].tessVertices;
+        sum.contours += own[i].contours;
+        sum.paths += own[i].paths;
+    }
+    FrontEndOut out = {spans, contours, pathData, paintData, paintAux, 0};
+    uint32_t padding[2];
+    emit_padding_spans(spans, sum.tessVertices, padding);
+    out.spanBase = padding[0];
+    for (uint32_t i = 0; i < pathCount; ++i)
+    {
+        prefix[i].spans = sum.spans;
+        sum.spans += place_path<false>(paths[i], points, verbs, prefix[i], own[i].tessVertices, out);
+    }
+    if (out.spanBase + sum.spans > spanCapacity)
+        return 1;
+    for (uint32_t i = 0; i < pathCount; ++i)
+        place_path<true>(paths[i], points, verbs, prefix[i], own[i].tessVertices, out);
+    result->path_count = sum.paths + 1;
+    result->contour_count = sum.contours;
+    result->tess_vertex_span_count = out.spanBase + sum.spans;
+    result->midpoint_fan_tess_vertex_count = sum.tessVertices;
+    result->tess_data_height = (padding[1] + kTessTextureWidth - 1) / kTessTextureWidth;
+    result->first_patch = 1;
+    result->patch_count = sum.tessVertices / kPatchSpan;
+    result->reserved0 = 0;
+    return 0;
+}

@@ -249,7 +249,7 @@ int rivecuda_target_read_pixels_async(rivecuda_ctx* ctx, rivecuda_target* t, voi
 
 int rivecuda_target_read_wait(rivecuda_ctx*, rivecuda_target*) { return 0; }
 
-int rivecuda_front_end_fills(rivecuda_ctx*, const float*, uint32_t, const uint8_t*, uint32_t, const rivecuda_fill_path*, uint32_t, rivecuda_front_end_result*)
+int rivecuda_front_end_paths(rivecuda_ctx*, const float*, uint32_t, const uint8_t*, uint32_t, const rivecuda_path*, uint32_t, uint32_t, uint32_t, rivecuda_front_end_result*)
 {
     return fail("rivecuda_trace: the GPU path front end needs a device (the recorder renders nothing)");
 }

@@ -1,6 +1,6 @@
-"""Python binding of the GPU path front end (rivecuda_front_end_fills) and
-reader of the `--dump-paths` files the scene player writes (host/player/player_main.cpp,
-PathDumpRenderer): the RawPaths + matrices + paints of a frame's fill draws."""
+"""Python binding of the GPU path front end (rivecuda_front_end_paths) and
+reader of the `--dump-paths` files the scene player writes (host/player/path_dump.hpp):
+the RawPaths + matrices + paints of a frame's plain fill and stroke draws."""
 from __future__ import annotations
 
 import ctypes
@@ -11,11 +11,13 @@ from dataclasses import dataclass
 import numpy as np
 
 
-class FillPath(ctypes.Structure):
-    """ctypes mirror of rivecuda_fill_path."""
+class Path(ctypes.Structure):
+    """ctypes mirror of rivecuda_path."""
     _fields_ = [("first_verb", ctypes.c_uint32), ("verb_count", ctypes.c_uint32), ("first_point", ctypes.c_uint32),
                 ("fill_rule", ctypes.c_uint32), ("matrix", ctypes.c_float * 6), ("color", ctypes.c_uint32),
-                ("reserved0", ctypes.c_uint32)]
+                ("stroke", ctypes.c_uint32), ("stroke_radius", ctypes.c_float), ("join", ctypes.c_uint32),
+                ("cap", ctypes.c_uint32), ("polar_segments_per_radian", ctypes.c_float),
+                ("matrix_max_scale", ctypes.c_float), ("reserved0", ctypes.c_uint32)]
 
 
 class FrontEndResult(ctypes.Structure):
@@ -26,22 +28,59 @@ class FrontEndResult(ctypes.Structure):
                 ("reserved0", ctypes.c_uint32)]
 
 
-assert ctypes.sizeof(FillPath) == 48 and ctypes.sizeof(FrontEndResult) == 32
+assert ctypes.sizeof(Path) == 72 and ctypes.sizeof(FrontEndResult) == 32
 
 
 @dataclass
 class PathDump:
-    paths: np.ndarray   # structured array with FillPath's layout
+    paths: np.ndarray   # structured array with rivecuda_path's layout
     verbs: np.ndarray   # uint8
     points: np.ndarray  # float32 (n, 2)
     complete: bool      # every draw of the frame was a plain fill or stroke
-    strokes: np.ndarray = None  # structured (is_stroke, thickness, join, cap) per path; zeros for "RPTH" dumps
 
 
 PATH_DTYPE = np.dtype([("first_verb", "<u4"), ("verb_count", "<u4"), ("first_point", "<u4"), ("fill_rule", "<u4"),
-                       ("matrix", "<f4", (6,)), ("color", "<u4"), ("reserved0", "<u4")])
-assert PATH_DTYPE.itemsize == 48
-STROKE_DTYPE = np.dtype([("is_stroke", "<u4"), ("thickness", "<f4"), ("join", "<u4"), ("cap", "<u4")])
+                       ("matrix", "<f4", (6,)), ("color", "<u4"), ("stroke", "<u4"), ("stroke_radius", "<f4"),
+                       ("join", "<u4"), ("cap", "<u4"), ("polar_segments_per_radian", "<f4"),
+                       ("matrix_max_scale", "<f4"), ("reserved0", "<u4")])
+assert PATH_DTYPE.itemsize == 72
+
+
+def find_max_scale(m) -> np.float32:
+    """Mat2D::findMaxScale (src/math/mat2d_find_max_scale.cpp:24-60) in float32."""
+    f = np.float32
+    xx, xy, yx, yy = (f(v) for v in m[:4])
+    if xy == 0 and yx == 0:
+        return max(abs(xx), abs(yy))
+    a = f(xx * xx + xy * xy)
+    b = f(xx * yx + yy * xy)
+    c = f(yx * yx + yy * yy)
+    b2 = f(b * b)
+    eps = f(1.0 / (1 << 12))
+    if b2 <= f(eps * eps):
+        result = max(a, c)
+    else:
+        amc = f(a - c)
+        x = f(np.sqrt(f(f(amc * amc) + f(f(4) * b2))) * f(.5))
+        result = f(f(f(a + c) * f(.5)) + x)
+    return f(np.sqrt(result))
+
+
+_LIBM = ctypes.CDLL("libm.so.6")
+_LIBM.acosf.restype = ctypes.c_float
+_LIBM.acosf.argtypes = [ctypes.c_float]
+
+
+def stroke_scalars(matrix, thickness: float):
+    """(stroke_radius, matrix_max_scale, polar_segments_per_radian) the way PathDraw does it on
+    the host (draw.cpp:603-607, 776-813; bezier_utils.hpp:108-113), glibc acosf included."""
+    f = np.float32
+    radius = max(f(f(thickness) * f(.5)), np.finfo(np.float32).tiny)
+    max_scale = find_max_scale(matrix)
+    with np.errstate(divide="ignore", invalid="ignore", over="ignore"):
+        cos_theta = f(f(1) - f(f(f(1) / f(8)) / f(radius * max_scale)))
+    psr = f(f(.5) / f(_LIBM.acosf(max(cos_theta, f(-1)))))
+    return radius, max_scale, psr
 
 
 def load_paths(path: str) -> PathDump:
@@ -51,35 +90,40 @@ def load_paths(path: str) -> PathDump:
         raise ValueError("not a path dump")
     v2 = magic == 0x32545052
     paths = np.zeros(count, dtype=PATH_DTYPE)
-    strokes = np.zeros(count, dtype=STROKE_DTYPE)
     verbs, points = [], []
     pos, nv, npnt = 16, 0, 0
     for i in range(count):
         m = struct.unpack_from("<6f", raw, pos)
         rule, color, n_verbs, n_pts = struct.unpack_from("<4I", raw, pos + 24)
         pos += 40
+        stroke = (0, 0.0, 0, 0)
         if v2:
-            strokes[i] = struct.unpack_from("<IfII", raw, pos)
+            stroke = struct.unpack_from("<IfII", raw, pos)
             pos += 16
         verbs.append(np.frombuffer(raw, dtype=np.uint8, count=n_verbs, offset=pos))
         pos += (n_verbs + 3) & ~3
         points.append(np.frombuffer(raw, dtype=np.float32, count=n_pts * 2, offset=pos))
         pos += n_pts * 8
-        paths[i] = (nv, n_verbs, npnt, rule, m, color, 0)
+        if stroke[0]:
+            radius, max_scale, psr = stroke_scalars(m, stroke[1])
+            paths[i] = (nv, n_verbs, npnt, 0, m, color, 1, radius, stroke[2], stroke[3], psr, max_scale, 0)
+        else:
+            paths[i] = (nv, n_verbs, npnt, rule, m, color, 0, 0.0, 0, 0, 0.0, 0.0, 0)
         nv += n_verbs
         npnt += n_pts
     return PathDump(paths, np.concatenate(verbs) if verbs else np.zeros(0, np.uint8),
-                    (np.concatenate(points) if points else np.zeros(0, np.float32)).reshape(-1, 2), bool(complete), strokes)
+                    (np.concatenate(points) if points else np.zeros(0, np.float32)).reshape(-1, 2), bool(complete))
 
 
-def run(replayer, dump: PathDump) -> FrontEndResult:
-    """rivecuda_front_end_fills on a Replayer's context."""
+def run(replayer, dump: PathDump, frame_width: int = 0, frame_height: int = 0) -> FrontEndResult:
+    """rivecuda_front_end_paths on a Replayer's context. A non-zero frame size enables the
+    reference's frame cull (paths outside the render target draw nothing)."""
     res = FrontEndResult()
     pts = np.ascontiguousarray(dump.points, dtype=np.float32)
     verbs = np.ascontiguousarray(dump.verbs, dtype=np.uint8)
     paths = np.ascontiguousarray(dump.paths)
-    replayer._call("rivecuda_front_end_fills", pts.ctypes.data, pts.shape[0], verbs.ctypes.data, verbs.size,
-                   paths.ctypes.data, paths.size, ctypes.byref(res))
+    replayer._call("rivecuda_front_end_paths", pts.ctypes.data, pts.shape[0], verbs.ctypes.data, verbs.size,
+                   paths.ctypes.data, paths.size, frame_width, frame_height, ctypes.byref(res))
     return res
 
 

@@ -68,7 +68,12 @@ public:
         const bool plain = pt->getFeather() == 0 && pt->getType() == gpu::PaintType::solidColor &&
                            pt->getBlendMode() == BlendMode::srcOver && pt->getImageTexture() == nullptr &&
                            (pt->getIsStroked() || rp->getFillRule() != FillRule::clockwise);
-        if (m_sink->active && plain)
+        // RiveRenderer::drawPath drops these before they reach the front end (rive_renderer.cpp:127-145).
+        const bool dropped = rp->getRawPath().empty() || (pt->getIsStroked() && !(pt->getThickness() > 0));
+        if (dropped)
+        {
+        }
+        else if (m_sink->active && plain)
         {
             const RawPath& raw = rp->getRawPath();
             const Mat2D& m = m_stack.back();

@@ -9,7 +9,7 @@ import numpy as np
 import pytest
 
 from conftest import GOLDEN
-from oracle import front_end_ref
+from oracle import front_end_host, front_end_ref
 from rive_runtime_b200 import front_end as F, trace as T
 
 
@@ -96,3 +96,64 @@ def test_polar_segment_counts_match_the_reference(name):
         assert np.array_equal(got, want), name
         checked += int(keep.sum())
     assert checked > 0
+
+
+FRONT_END_SCENES = ["f1", "s1", "c2_4k", "trickycubicstrokes", "trickycubicstrokes_roundcaps", "emptystroke", "strokes3",
+                    "labyrinth_round", "labyrinth_square", "zero_control_stroke", "zerolinestroke", "OverStroke",
+                    "bevel180strokes", "roundjoinstrokes", "widebuttcaps", "beziers", "CubicStroke", "inner_join_geometry",
+                    "teenyStrokes", "quadcap", "strokefill", "zeroPath"]
+
+
+@pytest.mark.parametrize("name", FRONT_END_SCENES)
+def test_front_end_core_matches_the_reference_front_end(name):
+    """The per-contour core the F1 kernels run (csrc/front_end_core.h), built for the host: for
+    the RawPaths of a frame it must produce, byte for byte, the TessVertexSpans / ContourData /
+    PathData / PaintData the reference front end wrote for that frame -- stroke chops at
+    inflections, 180-degree turns and cusps, round / miter / bevel joins, emulated caps, empty
+    contours, the frame cull, padding, row wraps. tests/test_front_end_gpu.py checks the device
+    build of the same code the same way."""
+    recs = T.parse(os.path.join(GOLDEN, name + ".rvct.xz"))
+    dump = F.load_paths(os.path.join(GOLDEN, name + ".paths.xz"))
+    assert dump.complete
+    host = {r.fields["kind"]: r.data for r in recs if r.tag == T.BUFFER_UNMAP}
+    flushes = [r.fields["flush"] for r in recs if r.tag == T.FLUSH]
+    assert len(flushes) == 1
+    d = flushes[0].desc
+    tc = next(r for r in recs if r.tag == T.TARGET_CREATE)
+    out = front_end_host.run(dump, tc.fields["width"], tc.fields["height"])
+    res = out.result
+    assert (res.path_count, res.contour_count, res.tess_vertex_span_count, res.tess_data_height) == (
+        d.path_count, d.contour_count, d.tess_vertex_span_count, d.tess_data_height)
+    batch = flushes[0].batches[0]
+    assert len(flushes[0].batches) == 1 and batch.draw_type == 0
+    assert (res.first_patch, res.patch_count) == (batch.base_element, batch.element_count)
+    n = res.tess_vertex_span_count
+    want = np.frombuffer(host[6].tobytes()[:n * 64], dtype=np.uint32).reshape(-1, 16)
+    bad = np.nonzero((out.spans[:n] != want).any(axis=1))[0]
+    assert bad.size == 0, f"{bad.size} spans differ, first {bad[:5]}"
+    want = np.frombuffer(host[4].tobytes()[:res.contour_count * 16], dtype=np.uint32).reshape(-1, 4)
+    assert np.array_equal(out.contours[:res.contour_count], want)
+    n = res.path_count
+    want = np.frombuffer(host[1].tobytes()[:n * 64], dtype=np.uint32).reshape(-1, 16)
+    assert np.array_equal(out.path_data[1:n, :8], want[1:, :8])
+    want = np.frombuffer(host[2].tobytes()[:n * 8], dtype=np.uint32).reshape(-1, 2)
+    assert np.array_equal(out.paint_data[1:n], want[1:])
+
+
+def test_stroke_scenes_exercise_every_stroke_feature():
+    """The stress scene is only a test if it reaches the hard cases."""
+    recs = T.parse(os.path.join(GOLDEN, "s1.rvct.xz"))
+    host = {r.fields["kind"]: r.data for r in recs if r.tag == T.BUFFER_UNMAP}
+    d = next(r.fields["flush"].desc for r in recs if r.tag == T.FLUSH)
+    w = np.frombuffer(host[6].tobytes()[:d.tess_vertex_span_count * 64], dtype=np.uint32).reshape(-1, 16)
+    seg = w[:, 14]
+    join, polar, parametric = seg >> 20, (seg >> 10) & 1023, seg & 1023
+    flags = w[:, 15] >> 26 & 7
+    assert set(flags.tolist()) >= {2, 3, 4, 5}                      # round, bevel, miter-revert, miter-clip (square caps)
+    assert int(((w[:, 15] >> 25) & 1).sum()) > 1000                 # emulated caps
+    assert int(((parametric == 0) & (polar == 0)).sum()) > 1000     # cap-only spans
+    pivot = (w[:, 0] == w[:, 6]) & (w[:, 1] == w[:, 7]) & (w[:, 2] == w[:, 4]) & (w[:, 3] == w[:, 5]) & (
+        (w[:, 0] != w[:, 2]) | (w[:, 1] != w[:, 3]))
+    assert int(pivot.sum()) > 100                                   # cusp pivots (chop_cubic_around_cusps)
+    assert int(((w[:, 12] >> 16).astype(np.int32) > 2048).sum()) > 100  # spans wrapping a 2048-texel row
+    assert polar.max() > 32 and join.max() > 32

@@ -1,7 +1,8 @@
-"""GPU path front end (rivecuda_front_end_fills) against the reference's own
+"""GPU path front end (rivecuda_front_end_paths) against the reference's own
 front end: for the same RawPaths, the device-generated TessVertexSpan / ContourData / PathData
-/ PaintData buffers -- Wang's-formula segment counts, prefix-summed span offsets, vertex
-counts, row wraps, contour midpoints -- must equal, byte for byte, what
+/ PaintData buffers -- Wang's-formula and polar segment counts, stroke chops (inflections,
+180-degree turns, cusps), joins, emulated caps, the frame cull, prefix-summed span offsets,
+vertex counts, row wraps, contour midpoints -- must equal, byte for byte, what
 PathDraw::initForMidpointFan + pushMidpointFanTessellationData wrote into the mapped buffers
 (recorded in the committed flush traces), and the rendered frame must be identical."""
 import os
@@ -14,7 +15,7 @@ from conftest import GOLDEN
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("name", ["f1", "c2_4k"])
+@pytest.mark.parametrize("name", ["f1", "s1", "c2_4k", "trickycubicstrokes", "emptystroke", "strokes3", "OverStroke", "zero_control_stroke"])
 def test_gpu_front_end_matches_reference_front_end(built, name):
     from rive_runtime_b200 import abi, front_end as F, replay as R, trace as T
     abi.load()
@@ -34,7 +35,8 @@ def test_gpu_front_end_matches_reference_front_end(built, name):
             if r.tag == T.BUFFER_UNMAP and r.fields["kind"] in (1, 2, 3, 4, 6):
                 continue  # path, paint, paintAux, contour, tessSpan: produced on the GPU below
             rp.apply(r, result)
-        res = F.run(rp, dump)
+        tc = next(r for r in recs if r.tag == T.TARGET_CREATE)
+        res = F.run(rp, dump, tc.fields["width"], tc.fields["height"])
         # a1 / a3: counts and allocation
         assert res.path_count == d.path_count
         assert res.contour_count == d.contour_count

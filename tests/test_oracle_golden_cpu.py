@@ -25,7 +25,7 @@ def frame_hash(frame):
 def test_oracle_frames_are_pinned(name):
     pinned = json.load(open(HASHES))
     recs = T.parse(os.path.join(GOLDEN, name))
-    big = name.startswith(("c3", "c1", "anim_", "f1", "riv_"))
+    big = name.startswith(("c3", "c1", "anim_", "f1", "s1", "riv_"))
     res = refcpu.replay(recs, threads=(os.cpu_count() or 2) if big else 2, keep_intermediates=False)
     assert [frame_hash(f) for f in res.frames] == pinned[name]["frames"]
     if not big:
