@@ -338,7 +338,7 @@ TessVaryings tessellate_span_vs(const Context& c, const TessSpanView& span, bool
     uint32_t totalVertexCount = parametricSegmentCount + polarSegmentCount + joinSegmentCount - 1u;
 
     float2x2 tangents = find_cubic_tangents(p0, p1, p2, p3);
-    float theta = acosf(cosine_between_vectors(tangents.c0, tangents.c1));
+    float theta = cr_acos(cosine_between_vectors(tangents.c0, tangents.c1));
     float radsPerPolarSegment = theta / static_cast<float>(polarSegmentCount);
     float turn = determinant(float2x2{p2 - p0, p3 - p1});
     if (turn == 0.f)
@@ -358,7 +358,7 @@ TessVaryings tessellate_span_vs(const Context& c, const TessSpanView& span, bool
     if (joinSegmentCount > 1u)
     {
         float2x2 joinTangents = {tangents.c1, v.joinTangent};
-        float joinTheta = acosf(cosine_between_vectors(joinTangents.c0, joinTangents.c1));
+        float joinTheta = cr_acos(cosine_between_vectors(joinTangents.c0, joinTangents.c1));
         float joinSpan = static_cast<float>(joinSegmentCount);
         if ((contourIDWithFlags & (JOIN_TYPE_MASK | EMULATED_STROKE_CAP_CONTOUR_FLAG)) ==
             (ROUND_JOIN_CONTOUR_FLAG | EMULATED_STROKE_CAP_CONTOUR_FLAG))
@@ -470,17 +470,17 @@ uint4v tessellate_fs(const TessVaryings& v, float vertexIdxInterpolated)
                     float cosRotation = dot(normalize(testTan), tan0norm);
                     float maxRotation = testParametricID * negAbsRadsPerSegment + maxRotation0;
                     maxRotation = fminf(maxRotation, PI);
-                    if (cosRotation >= cosf(maxRotation))
+                    if (cosRotation >= cr_cos(maxRotation))
                         lastParametricVertexID = testParametricID;
                 }
             }
 
             float parametricT = lastParametricVertexID / parametricSegmentCount;
             float lastPolarVertexID = mergedVertexID - lastParametricVertexID;
-            float theta0 = acosf(clampf(tan0norm.x, -1.f, 1.f));
+            float theta0 = cr_acos(clampf(tan0norm.x, -1.f, 1.f));
             theta0 = tan0norm.y >= 0.f ? theta0 : -theta0;
             theta = lastPolarVertexID * radsPerPolarSegment + theta0;
-            float2 norm = {sinf(theta), -cosf(theta)};
+            float2 norm = {cr_sin(theta), -cr_cos(theta)};
             float a = dot(norm, A), b_over_2 = dot(norm, B), cc = dot(norm, C);
             float discr_over_4 = fmaxf(b_over_2 * b_over_2 - a * cc, 0.f);
             float q = sqrtf(discr_over_4);
@@ -774,7 +774,7 @@ bool unpack_tessellated_path_vertex(const Context& c,
     {
         theta = uintBitsToFloat(tessVertexData.z);
     }
-    float2 norm = {sinf(theta), -cosf(theta)};
+    float2 norm = {cr_sin(theta), -cr_cos(theta)};
     float2 origin = {uintBitsToFloat(tessVertexData.x), uintBitsToFloat(tessVertexData.y)};
     float2 postTransformVertexOffset = {0, 0};
 
@@ -821,10 +821,10 @@ bool unpack_tessellated_path_vertex(const Context& c,
             bool isTan0 = (contourIDWithFlags & JOIN_TANGENT_0_CONTOUR_FLAG) != 0u;
             bool isLeftJoin = (contourIDWithFlags & LEFT_JOIN_CONTOUR_FLAG) != 0u;
             float bisectTheta = joinAngle * (isTan0 == isLeftJoin ? -.5f : .5f) + theta;
-            float2 bisector = {sinf(bisectTheta), -cosf(bisectTheta)};
+            float2 bisector = {cr_sin(bisectTheta), -cr_cos(bisectTheta)};
             float bisectPixelWidth = manhattan_pixel_width(M, bisector);
 
-            float miterRatio = cosf(joinAngle * .5f);
+            float miterRatio = cr_cos(joinAngle * .5f);
             float clipRadius;
             if ((joinType == MITER_CLIP_JOIN_CONTOUR_FLAG) || (joinType == MITER_REVERT_JOIN_CONTOUR_FLAG && miterRatio >= .25f))
             {
@@ -890,7 +890,7 @@ bool unpack_tessellated_path_vertex(const Context& c,
                 spokeTheta = clampf(spokeTheta, 0.f, featherJoinCornerTheta);
                 if (spokeTheta > featherJoinCornerTheta * .5f)
                     spokeTheta = featherJoinCornerTheta - spokeTheta;
-                float2 spokeNorm = {sinf(spokeTheta), cosf(spokeTheta)};
+                float2 spokeNorm = {cr_sin(spokeTheta), cr_cos(spokeTheta)};
                 outCoverages = pack_feathered_fill_coverages(featherJoinCornerTheta, spokeNorm, outset);
             }
             postTransformVertexOffset = MUL(M, (outset * featherRadius) * norm);

@@ -44,6 +44,14 @@ inline float length(float2 a) { return sqrtf(dot(a, a)); }
 inline float inversesqrt(float x) { return 1.f / sqrtf(x); }
 inline float2 normalize(float2 a) { return a * inversesqrt(dot(a, a)); }
 inline float clampf(float x, float lo, float hi) { return fminf(fmaxf(x, lo), hi); }
+// GLSL's cos / sin / acos / pow have implementation-defined precision. The oracle defines them
+// as the real function rounded once to float (evaluated in double): the tessellator's binary
+// search compares cos() values that are nearly equal on almost-straight stroke pieces, so a
+// 1-ulp difference between two libm's would move vertices by many pixels.
+inline float cr_cos(float x) { return static_cast<float>(std::cos(static_cast<double>(x))); }
+inline float cr_sin(float x) { return static_cast<float>(std::sin(static_cast<double>(x))); }
+inline float cr_acos(float x) { return static_cast<float>(std::acos(static_cast<double>(x))); }
+inline float cr_pow(float x, float y) { return static_cast<float>(std::pow(static_cast<double>(x), static_cast<double>(y))); }
 inline float mixf(float a, float b, float t) { return a * (1.f - t) + b * t; }
 inline float2 mix2(float2 a, float2 b, float t) { return a * (1.f - t) + b * t; }
 inline float fractf(float x) { return x - floorf(x); }
@@ -169,7 +177,7 @@ inline uint32_t packUnorm4x8(float4 c)
 inline float atan2_glsl(float2 v)
 {
     v = normalize(v);
-    float theta = acosf(clampf(v.x, -1.f, 1.f));
+    float theta = cr_acos(clampf(v.x, -1.f, 1.f));
     return v.y >= 0.f ? theta : -theta;
 }
 } // namespace refcpu

@@ -142,12 +142,12 @@ inline float measure_cubic_local_curvature(float2 p0, float2 p1, float2 p2, floa
         if (discr < 0.f)
         {
             float sqrtQ = sqrtf(Q);
-            float theta = acosf(R / (sqrtQ * sqrtQ * sqrtQ));
-            dt = -2.f * sqrtQ * cosf(theta * (1.f / 3.f) + (-PI * 2.f / 3.f));
+            float theta = cr_acos(R / (sqrtQ * sqrtQ * sqrtQ));
+            dt = -2.f * sqrtQ * cr_cos(theta * (1.f / 3.f) + (-PI * 2.f / 3.f));
         }
         else
         {
-            float A2 = powf(fabsf(R) + sqrtf(discr), 1.f / 3.f);
+            float A2 = cr_pow(fabsf(R) + sqrtf(discr), 1.f / 3.f);
             if (R < 0.f)
                 A2 = -A2;
             dt = A2 != 0.f ? A2 + Q / A2 : 0.f;
@@ -160,7 +160,7 @@ inline float measure_cubic_local_curvature(float2 p0, float2 p1, float2 p2, floa
     float2x2 tangents = find_cubic_tangents(p0, p1, p2, p3);
     float2 tan0 = t0 < 1e-3f ? tangents.c0 : tanDir0;
     float2 tan1 = t1 > 1.f - 1e-3f ? tangents.c1 : tanDir1;
-    return acosf(cosine_between_vectors(tan0, tan1));
+    return cr_acos(cosine_between_vectors(tan0, tan1));
 }
 
 // bezier_utils.glsl:173-245 (the Newton-Raphson branch that is compiled in)

@@ -86,10 +86,31 @@ __device__ __forceinline__ m22 inverse(m22 m)
     return {m.yy * inv, -m.xy * inv, -m.yx * inv, m.xx * inv};
 }
 
+// Transcendentals of the vertex stages are evaluated in double and rounded to float once. The
+// oracle does the same with glibc, so both sides get the correctly rounded float (barring a
+// double-rounding tie, ~1e-8 per call) and the tessellator's discontinuous decisions -- the
+// binary search "cosRotation >= cos(maxRotation)" on nearly straight stroke pieces next to a
+// cusp -- fall the same way. CUDA's float cosf / acosf are 1-2 ulp off glibc's.
+__device__ __forceinline__ float cr_cos(float x) { return static_cast<float>(cos(static_cast<double>(x))); }
+__device__ __forceinline__ float cr_sin(float x) { return static_cast<float>(sin(static_cast<double>(x))); }
+__device__ __forceinline__ void cr_sincos(float x, float* s, float* c)
+{
+    double ds, dc;
+    sincos(static_cast<double>(x), &ds, &dc); // one shared argument reduction
+    *s = static_cast<float>(ds);
+    *c = static_cast<float>(dc);
+}
+__device__ __forceinline__ float cr_acos(float x) { return static_cast<float>(acos(static_cast<double>(x))); }
+// Out-of-line variants for the rarely taken branches of the vertex stage (join bisectors, feather
+// joins): keeps the double-precision code out of the hot path's register budget.
+__device__ __noinline__ static float cr_cos_cold(float x) { return static_cast<float>(cos(static_cast<double>(x))); }
+__device__ __noinline__ static float cr_sin_cold(float x) { return static_cast<float>(sin(static_cast<double>(x))); }
+__device__ __forceinline__ float cr_pow(float x, float y) { return static_cast<float>(pow(static_cast<double>(x), static_cast<double>(y))); }
+
 __device__ __forceinline__ float atan2_rive(f2 v) // common.glsl atan2()
 {
     v = norm2(v);
-    float theta = acosf(clampf(v.x, -1.f, 1.f));
+    float theta = cr_acos(clampf(v.x, -1.f, 1.f));
     return v.y >= 0.f ? theta : -theta;
 }
 

@@ -92,6 +92,7 @@ struct FlushParams
     const uint8_t* imageDrawInstances; // frame-wide, 64 B each
     const uint4* tess;
     uint32_t tessVertexCount;
+    const float2* tessNormals; // (sin theta, -cos theta) per tessellated vertex (K2)
     const float* patchVertices; // 8 floats per PatchVertex
     const uint16_t* patchIndices;
     const PatchDedup* patchDedup; // [patch type][mirrored]
@@ -292,7 +293,20 @@ __device__ ShadedVertex shade_patch_vertex(const FlushParams& P, const float* __
     {
         theta = __uint_as_float(tv.z);
     }
-    const f2 nrm = mk2(sinf(theta), -cosf(theta));
+    f2 nrm;
+    if (isFeatherJoinVertex || (flags & kJoinTypeMask) == kFeatherJoin)
+    {
+        nrm = mk2(cr_sin_cold(theta), -cr_cos_cold(theta));
+    }
+    else if (tv.z == 0u)
+    {
+        nrm = mk2(0.f, -1.f); // sin 0, -cos 0: also every texel K2 did not write this flush
+    }
+    else
+    {
+        const float2 n = __ldg(P.tessNormals + tessVertexIdx); // K2 evaluated it for this vertex
+        nrm = mk2(n.x, n.y);
+    }
     f2 origin = mk2(__uint_as_float(tv.x), __uint_as_float(tv.y));
     f2 postTransformOffset = mk2(0.f, 0.f);
     float4 cov;
@@ -337,9 +351,9 @@ __device__ ShadedVertex shade_patch_vertex(const FlushParams& P, const float* __
             const bool isTan0 = (flags & kJoinTangent0Flag) != 0u;
             const bool isLeftJoin = (flags & kLeftJoinFlag) != 0u;
             const float bisectTheta = joinAngle * (isTan0 == isLeftJoin ? -.5f : .5f) + theta;
-            const f2 bisector = mk2(sinf(bisectTheta), -cosf(bisectTheta));
+            const f2 bisector = mk2(cr_sin_cold(bisectTheta), -cr_cos_cold(bisectTheta));
             const float bisectPixelWidth = manhattan_pixel_width(M, bisector);
-            const float miterRatio = cosf(joinAngle * .5f);
+            const float miterRatio = cr_cos_cold(joinAngle * .5f);
             float clipRadius;
             if (joinType == kMiterClipJoin || (joinType == kMiterRevertJoin && miterRatio >= .25f))
             {
@@ -404,7 +418,7 @@ __device__ ShadedVertex shade_patch_vertex(const FlushParams& P, const float* __
                 spokeTheta = clampf(spokeTheta, 0.f, featherJoinCornerTheta);
                 if (spokeTheta > featherJoinCornerTheta * .5f)
                     spokeTheta = featherJoinCornerTheta - spokeTheta;
-                cov = pack_feathered_fill_coverages(featherJoinCornerTheta, mk2(sinf(spokeTheta), cosf(spokeTheta)), outset);
+                cov = pack_feathered_fill_coverages(featherJoinCornerTheta, mk2(cr_sin_cold(spokeTheta), cr_cos_cold(spokeTheta)), outset);
             }
             postTransformOffset = mul(M, nrm * (outset * featherRadius));
         }
@@ -805,7 +819,7 @@ __device__ __forceinline__ uint32_t find_batch(const DeviceBatch* __restrict__ b
 }
 
 // One warp per patch instance.
-__global__ void __launch_bounds__(kSetupWarpsPerBlock * 32) setup_patches_kernel(FlushParams P,
+__global__ void __launch_bounds__(kSetupWarpsPerBlock * 32, 2048 / (kSetupWarpsPerBlock * 32) / 2) setup_patches_kernel(FlushParams P,
                                                                                 const DeviceBatch* __restrict__ batches,
                                                                                 uint32_t batchCount,
                                                                                 uint32_t totalInstances,
@@ -1422,6 +1436,7 @@ int launch_draw_list(rivecuda_ctx* ctx, const rivecuda_flush_desc& desc, const r
     P.triangleVertices = reinterpret_cast<const float*>(ringPtr(RIVECUDA_BUFFER_TRIANGLE, 12, 0));
     P.imageDrawInstances = ringPtr(RIVECUDA_BUFFER_IMAGE_DRAW, 64, 0);
     P.tess = ctx->tessTexture;
+    P.tessNormals = ctx->tessNormals;
     P.tessVertexCount = ctx->tessHeight * kTessWidth;
     P.patchVertices = static_cast<const float*>(ctx->patchVertices);
     P.patchIndices = ctx->patchIndices;
@@ -1972,6 +1987,7 @@ int launch_atlas(rivecuda_ctx* ctx,
     P.pathBuffer = reinterpret_cast<const uint4*>(ringPtr(RIVECUDA_BUFFER_PATH, 64, desc.first_path));
     P.contourBuffer = reinterpret_cast<const uint4*>(ringPtr(RIVECUDA_BUFFER_CONTOUR, 16, desc.first_contour));
     P.tess = ctx->tessTexture;
+    P.tessNormals = ctx->tessNormals;
     P.tessVertexCount = ctx->tessHeight * kTessWidth;
     P.patchVertices = static_cast<const float*>(ctx->patchVertices);
     P.patchIndices = ctx->patchIndices;

@@ -163,12 +163,12 @@ __device__ float measure_cubic_local_curvature(f2 p0, f2 p1, f2 p2, f2 p3, float
         if (discr < 0.f)
         {
             float sqrtQ = sqrtf(Q);
-            float theta = acosf(R / (sqrtQ * sqrtQ * sqrtQ));
-            dt = -2.f * sqrtQ * cosf(theta * (1.f / 3.f) + (-kPI * 2.f / 3.f));
+            float theta = cr_acos(R / (sqrtQ * sqrtQ * sqrtQ));
+            dt = -2.f * sqrtQ * cr_cos(theta * (1.f / 3.f) + (-kPI * 2.f / 3.f));
         }
         else
         {
-            float A2 = powf(fabsf(R) + sqrtf(discr), 1.f / 3.f);
+            float A2 = cr_pow(fabsf(R) + sqrtf(discr), 1.f / 3.f);
             if (R < 0.f)
                 A2 = -A2;
             dt = A2 != 0.f ? A2 + Q / A2 : 0.f;
@@ -182,7 +182,7 @@ __device__ float measure_cubic_local_curvature(f2 p0, f2 p1, f2 p2, f2 p3, float
     cubic_tangents(p0, p1, p2, p3, tg0, tg1);
     f2 tan0 = t0 < 1e-3f ? tg0 : tanDir0;
     f2 tan1 = t1 > 1.f - 1e-3f ? tg1 : tanDir1;
-    return acosf(cos_between(tan0, tan1));
+    return cr_acos(cos_between(tan0, tan1));
 }
 
 __device__ SpanSetup span_setup(const TessSpan& span,
@@ -238,7 +238,7 @@ __device__ SpanSetup span_setup(const TessSpan& span,
     uint32_t totalVertexCount = parametricSegmentCount + polarSegmentCount + joinSegmentCount - 1u;
     f2 tan0, tan1;
     cubic_tangents(p0, p1, p2, p3, tan0, tan1);
-    float theta = acosf(cos_between(tan0, tan1));
+    float theta = cr_acos(cos_between(tan0, tan1));
     float radsPerPolarSegment = theta / static_cast<float>(polarSegmentCount);
     float turn = cross2(p2 - p0, p3 - p1);
     if (turn == 0.f)
@@ -257,7 +257,7 @@ __device__ SpanSetup span_setup(const TessSpan& span,
     v.radsPerJoinSegment = 0.f;
     if (joinSegmentCount > 1u)
     {
-        float joinTheta = acosf(cos_between(tan1, v.joinTangent));
+        float joinTheta = cr_acos(cos_between(tan1, v.joinTangent));
         float joinSpan = static_cast<float>(joinSegmentCount);
         if ((flags & (kJoinTypeMask | kEmulatedStrokeCapFlag)) == (kRoundJoin | kEmulatedStrokeCapFlag))
             joinSpan -= 2.f;
@@ -361,16 +361,18 @@ __device__ uint4 tessellate_vertex(const SpanSetup& v, float vertexIdx)
                     testTan = testParametricID * testTan + C_;
                     float cosRotation = dot2(norm2(testTan), tan0norm);
                     float maxRotation = fminf(testParametricID * negAbsRadsPerSegment + maxRotation0, kPI);
-                    if (cosRotation >= cosf(maxRotation))
+                    if (cosRotation >= cr_cos(maxRotation))
                         lastParametricVertexID = testParametricID;
                 }
             }
             float parametricT = lastParametricVertexID / parametricSegmentCount;
             float lastPolarVertexID = mergedVertexID - lastParametricVertexID;
-            float theta0 = acosf(clampf(tan0norm.x, -1.f, 1.f));
+            float theta0 = cr_acos(clampf(tan0norm.x, -1.f, 1.f));
             theta0 = tan0norm.y >= 0.f ? theta0 : -theta0;
             theta = lastPolarVertexID * radsPerPolarSegment + theta0;
-            f2 nrm = mk2(sinf(theta), -cosf(theta));
+            float sinTheta, cosTheta;
+            cr_sincos(theta, &sinTheta, &cosTheta);
+            f2 nrm = mk2(sinTheta, -cosTheta);
             float a = dot2(nrm, A), b_over_2 = dot2(nrm, B), c = dot2(nrm, C);
             float discr_over_4 = fmaxf(b_over_2 * b_over_2 - a * c, 0.f);
             float q = sqrtf(discr_over_4);
@@ -412,6 +414,7 @@ __global__ void __launch_bounds__(256) tessellate_kernel(const TessSpan* __restr
                                                          const uint4* __restrict__ contourBuffer,
                                                          const float* __restrict__ featherLUT,
                                                          uint4* __restrict__ tess,
+                                                         float2* __restrict__ tessNormals,
                                                          int tessHeight)
 {
     const int lane = threadIdx.x & 31;
@@ -445,13 +448,25 @@ __global__ void __launch_bounds__(256) tessellate_kernel(const TessSpan* __restr
         const SpanSetup v = span_setup(span, mirrored, pathBuffer, contourBuffer, featherLUT);
         const int lo = max(min(x0, x1), 0), hi = min(max(x0, x1), kTessWidth);
         uint4* rowPtr = tess + static_cast<size_t>(row) * kTessWidth;
+        float2* normalPtr = tessNormals + static_cast<size_t>(row) * kTessWidth;
         for (int x = lo + lane; x < hi; x += 32)
         {
             // v_args.x at this texel centre, floored and clamped at 0
             // (tessellate.glsl:253, 308).
             float vertexIdx = v.totalVertexCount - fabsf(static_cast<float>(x1) - (static_cast<float>(x) + .5f));
             vertexIdx = fmaxf(floorf(vertexIdx), 0.f);
-            rowPtr[x] = tessellate_vertex(v, vertexIdx);
+            const uint4 tv = tessellate_vertex(v, vertexIdx);
+            rowPtr[x] = tv;
+            // The vertex stage offsets every patch vertex along (sin theta, -cos theta)
+            // (draw_path_common.glsl:214); evaluated once per tessellated vertex here instead
+            // of once per patch vertex there. Feather-join vertices pack counts into .z.
+            if ((tv.w & kJoinTypeMask) != kFeatherJoin)
+            {
+                const float theta = __uint_as_float(tv.z);
+                float sinTheta, cosTheta;
+                cr_sincos(theta, &sinTheta, &cosTheta);
+                normalPtr[x] = make_float2(sinTheta, -cosTheta);
+            }
         }
     }
 }
@@ -486,6 +501,7 @@ int launch_tessellate(rivecuda_ctx* ctx,
                                                        static_cast<const uint4*>(contourBuffer),
                                                        ctx->featherLUT,
                                                        ctx->tessTexture,
+                                                       ctx->tessNormals,
                                                        static_cast<int>(desc.tess_data_height));
     ctx->lastLaunches += 1;
     return check_cuda(cudaGetLastError(), "tessellate_kernel");

@@ -174,6 +174,7 @@ void rivecuda_destroy(rivecuda_ctx* ctx)
     cudaFree(ctx->featherLUT);
     cudaFree(ctx->gradTexture);
     cudaFree(ctx->tessTexture);
+    cudaFree(ctx->tessNormals);
     cudaFree(ctx->atlas);
     for (DeviceBuffer* b : {&ctx->triGeom, &ctx->triAttr, &ctx->tileCounts, &ctx->tileOffsets, &ctx->tileEntries,
                             &ctx->batchTable, &ctx->imageTable, &ctx->scanScratch, &ctx->clipPlane, &ctx->pathImageSlots, &ctx->atlasTable, &ctx->binCount, &ctx->binPairs, &ctx->hugeList, &ctx->frontEnd})
@@ -373,10 +374,15 @@ int rivecuda_resize_tessellation_texture(rivecuda_ctx* ctx, uint32_t width, uint
         return 0;
     RC_CUDA(cudaStreamSynchronize(ctx->stream));
     cudaFree(ctx->tessTexture);
+    cudaFree(ctx->tessNormals);
     ctx->tessTexture = nullptr;
+    ctx->tessNormals = nullptr;
     ctx->tessHeight = height;
     if (height > 0)
+    {
         RC_CUDA(cudaMalloc(reinterpret_cast<void**>(&ctx->tessTexture), static_cast<size_t>(kTessWidth) * height * sizeof(uint4)));
+        RC_CUDA(cudaMalloc(reinterpret_cast<void**>(&ctx->tessNormals), static_cast<size_t>(kTessWidth) * height * sizeof(float2)));
+    }
     return 0;
 }
 

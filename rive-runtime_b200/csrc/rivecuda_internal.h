@@ -156,6 +156,7 @@ struct rivecuda_ctx
     uint32_t* gradTexture = nullptr; // 512 x gradHeight RGBA8
     uint32_t gradHeight = 0;
     uint4* tessTexture = nullptr;    // 2048 x tessHeight
+    float2* tessNormals = nullptr;   // (sin theta, -cos theta) of every tessellated vertex, written by K2 for K4a
     uint32_t tessHeight = 0;
     float* atlas = nullptr;          // atlasWidth x atlasHeight fp32 coverage
     uint32_t atlasWidth = 0, atlasHeight = 0;

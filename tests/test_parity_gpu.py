@@ -65,12 +65,22 @@ def test_scene_parity(libs, name):
             assert np.array_equal(rt[:, 3], gt[:, 3]), "contourIDWithFlags must be bit-exact"
             packed = ((rt[:, 3] >> 26) & 7) == 1  # feather joins pack (segmentCount<<16 | vertexID)
             assert np.array_equal(rt[packed, 2], gt[packed, 2])
-            rxy, gxy = rt[:, :2].view(np.float32), gt[:, :2].view(np.float32)
-            scale = max(1.0, float(np.nanmax(np.abs(rxy))))
-            assert np.nanmax(np.abs(rxy - gxy)) <= 2e-6 * scale + 1e-4
-            dth = np.abs(rt[~packed, 2].view(np.float32) - gt[~packed, 2].view(np.float32))
-            dth = np.minimum(dth, np.abs(dth - 2 * np.pi))
-            assert dth.size == 0 or np.nanmax(dth) <= 2.5e-4  # acosf/atan2 differ by a few ulp between libm and CUDA; ill-conditioned for tiny tangents
+            # Positions and angles: the kernels and the oracle run the same float operations
+            # un-contracted and round their transcendentals once from double, so the tessellation
+            # texture is bit-identical (it is on every committed scene). A double-rounding tie in
+            # one of those calls (~1e-8 per call) may move a vertex by an ulp: allow a handful,
+            # within the old tolerances.
+            rf, gf = rt[:, :3].view(np.float32), gt[:, :3].view(np.float32)
+            differs = ((rt[:, :3] != gt[:, :3]) & ~(np.isnan(rf) & np.isnan(gf))).any(axis=1)
+            differs[packed] = (rt[packed, :2] != gt[packed, :2]).any(axis=1)
+            assert int(differs.sum()) <= 4, f"{int(differs.sum())} tessellated vertices differ"
+            if differs.any():
+                rxy, gxy = rf[differs, :2], gf[differs, :2]
+                scale = max(1.0, float(np.nanmax(np.abs(rxy))))
+                assert np.nanmax(np.abs(rxy - gxy)) <= 2e-6 * scale + 1e-4
+                dth = np.abs(rf[differs & ~packed, 2] - gf[differs & ~packed, 2])
+                dth = np.minimum(dth, np.abs(dth - 2 * np.pi))
+                assert dth.size == 0 or np.nanmax(dth) <= 2.5e-4
         if fr.desc.grad_data_height:
             assert np.array_equal(fr.grad[:fr.desc.grad_data_height], fg.grad), "colour ramps must be bit-exact"
     max_delta, max_outliers = KNOWN_DEVIATIONS.get(name, (MAX_DELTA, 0))
