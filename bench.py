@@ -352,6 +352,10 @@ def main() -> None:
         raw_pass(args.steps)
         barrier()
         dt = time.perf_counter() - t0
+        t = torch.tensor([dt], dtype=torch.float64, device=f"cuda:{local_rank}")
+        if distributed:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item()) / world  # whole-job frames/s: every rank rendered args.steps frames
         t0 = time.perf_counter()
         for _ in range(args.steps):
             F.run(rp, dump, width, height)

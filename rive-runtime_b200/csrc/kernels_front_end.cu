@@ -235,6 +235,12 @@ int rivecuda_front_end_paths(rivecuda_ctx* ctx,
     RC_CUDA(cudaMemcpyAsync(ctx->pinnedTotals + 8 + 3, dSums + 3, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
     RC_CUDA(cudaStreamSynchronize(stream));
     const uint32_t* sums = ctx->pinnedTotals + 8;
+    // One flush holds what RenderContext::LogicalFlush::pushDraws admits (render_context.cpp:528-536):
+    // path ids fit the fp16 id encoding, contour ids 16 bits, the tessellation texture 2048 rows.
+    if (sums[2] > 30720u || sums[1] > 0xffffu || sums[5] > static_cast<uint32_t>(kTessWidth) * 2048u)
+        return set_error("rivecuda_front_end_paths: %u paths / %u contours / %u tessellation vertices exceed one flush "
+                         "(30720 / 65535 / 2048 x 2048); split the draw list as the reference starts a new logical flush",
+                         sums[2], sums[1], sums[5]);
     result->midpoint_fan_tess_vertex_count = sums[0];
     result->contour_count = sums[1];
     result->path_count = sums[2] + 1; // + the reserved record 0

@@ -65,3 +65,90 @@ def test_gpu_front_end_matches_reference_front_end(built, name):
         rp.flush(pf)
         frame = rp.read_target(fr.target_id)
     assert np.array_equal(frame, want_frame)
+
+
+def random_paths(seed, n_paths, strokes=True):
+    """Random RawPaths in the dump format: lines, cubics (generic, cusps, loops, degenerate),
+    closed / open / move-only contours, random matrices and stroke styles."""
+    from rive_runtime_b200 import front_end as F
+    rng = np.random.default_rng(seed)
+    verbs, points, paths = [], [], np.zeros(n_paths, dtype=F.PATH_DTYPE)
+    nv = npnt = 0
+    for i in range(n_paths):
+        side = float(rng.choice([1.0, 30.0, 300.0, 1000.0]))
+        pv, pp = [], []
+        for _ in range(int(rng.integers(1, 4))):
+            cur = rng.uniform(-side, side, 2).astype(np.float32)
+            start = cur.copy()
+            pv.append(0)
+            pp.append(cur)
+            for _ in range(int(rng.integers(0, 6))):
+                kind = int(rng.integers(0, 8))
+                end = rng.uniform(-side, side, 2).astype(np.float32)
+                if kind < 2:
+                    pv.append(1)
+                    pp.append(end)
+                else:
+                    c1 = rng.uniform(-side, side, 2).astype(np.float32)
+                    c2 = rng.uniform(-side, side, 2).astype(np.float32)
+                    if kind == 2:      # collinear overshoot: a cusp
+                        d = end - cur
+                        c1, c2 = cur + d * np.float32(1.5), cur - d * np.float32(.5)
+                    elif kind == 3:    # coincident control points
+                        c1, c2 = cur.copy(), end.copy()
+                    elif kind == 4:    # a loop
+                        d = end - cur
+                        perp = np.array([d[1], -d[0]], np.float32)
+                        c1, c2 = end + perp, cur + perp
+                    pv.append(4)
+                    pp.extend([c1.astype(np.float32), c2.astype(np.float32), end])
+                cur = end
+            if rng.integers(0, 4) == 0 and len(pp) > 1:
+                pv.append(1)
+                pp.append(start)
+            if rng.integers(0, 2) == 0:
+                pv.append(5)
+        ang = rng.uniform(-3.2, 3.2)
+        sx, sy = rng.uniform(.1, 4.0, 2)
+        m = np.array([np.cos(ang) * sx, np.sin(ang) * sx, -np.sin(ang) * sy, np.cos(ang) * sy,
+                      rng.uniform(0, 3840), rng.uniform(0, 2160)], np.float32)
+        if rng.integers(0, 3) == 0:
+            m[1] = m[2] = 0
+        color = int(rng.integers(0, 1 << 32))
+        if strokes and rng.integers(0, 2) == 0:
+            radius, max_scale, psr = F.stroke_scalars(m, float(rng.uniform(.2, 60.0)))
+            paths[i] = (nv, len(pv), npnt, 0, m, color, 1, radius, int(rng.integers(0, 3)), int(rng.integers(0, 3)), psr, max_scale, 0)
+        else:
+            paths[i] = (nv, len(pv), npnt, int(rng.integers(0, 2)), m, color, 0, 0.0, 0, 0, 0.0, 0.0, 0)
+        verbs.extend(pv)
+        points.extend(pp)
+        nv += len(pv)
+        npnt += len(pp)
+    return F.PathDump(paths, np.array(verbs, np.uint8), np.array(points, np.float32).reshape(-1, 2), True)
+
+
+@pytest.mark.parametrize("seed,n_paths", [(1, 2000), (2, 12000)])
+def test_device_front_end_equals_its_host_build_on_random_paths(built, seed, n_paths):
+    """Size-independent property: for arbitrary finite RawPaths the kernels and the host build of
+    the same per-contour core (which the CPU suite pins against the reference) write the same
+    bytes -- spans, contours, path and paint records, counts -- including the frame cull."""
+    from oracle import front_end_host
+    from rive_runtime_b200 import abi, front_end as F, replay as R
+    abi.load()
+    dump = random_paths(seed, n_paths)
+    want = front_end_host.run(dump, 3840, 2160)
+    with R.Replayer(0) as rp:
+        res = F.run(rp, dump, 3840, 2160)
+        for field in ("path_count", "contour_count", "tess_vertex_span_count", "midpoint_fan_tess_vertex_count",
+                      "tess_data_height", "first_patch", "patch_count"):
+            assert getattr(res, field) == getattr(want.result, field), field
+        assert res.tess_vertex_span_count > n_paths and res.tess_data_height <= 2048
+        n = res.tess_vertex_span_count
+        got = F.read_buffer(rp, 6, n * 64).view(np.uint32).reshape(-1, 16)
+        bad = np.nonzero((got != want.spans[:n]).any(axis=1))[0]
+        assert bad.size == 0, f"{bad.size} spans differ, first {bad[:5]}: got {got[bad[0]]} want {want.spans[bad[0]]}"
+        n = res.contour_count
+        assert np.array_equal(F.read_buffer(rp, 4, n * 16).view(np.uint32).reshape(-1, 4), want.contours[:n])
+        n = res.path_count
+        assert np.array_equal(F.read_buffer(rp, 1, n * 64).view(np.uint32).reshape(-1, 16)[1:, :8], want.path_data[1:n, :8])
+        assert np.array_equal(F.read_buffer(rp, 2, n * 8).view(np.uint32).reshape(-1, 2)[1:], want.paint_data[1:n])
