@@ -1,0 +1,151 @@
+/*
+ * CudaPathRenderer -- a rive::Renderer for frames made only of plain draws (solid colour,
+ * src-over, unclipped, unfeathered nonZero / evenOdd fills and strokes) that hands the frame's
+ * RawPaths to the device instead of running the reference's per-path CPU front end
+ * (SURVEY.md 8(f1)). It sits where RiveRenderer sits:
+ *
+ *     CudaPathRenderer renderer(impl, target, LoadAction::clear, clearColor);
+ *     artboardOrScene->draw(&renderer);          // save / restore / transform / drawPath
+ *     if (!renderer.flush()) ...                 // rivecuda_front_end_paths + rivecuda_flush
+ *
+ * What RiveRenderer::drawPath checks before building a PathDraw is mirrored here
+ * (rive_renderer.cpp:121-154): empty paths and strokes with !(thickness > 0) are skipped.
+ * Per stroked path the two scalars PathDraw computes with libm are computed here the same way
+ * (draw.cpp:603-607, 776-813). Anything else -- clips, gradients, images, feathers, blend modes,
+ * opacity -- is not handled by the device front end: the renderer records the first such call
+ * and flush() refuses the frame, so the caller can draw it with RiveRenderer (no silent fallback).
+ */
+#pragma once
+
+#include "render_context_cuda_impl.hpp"
+
+#include "rive/math/bezier_utils.hpp"
+#include "rive/math/mat2d.hpp"
+#include "rive/renderer.hpp"
+#include "rive/renderer/gpu.hpp"
+#include "rive_render_paint.hpp"
+#include "rive_render_path.hpp"
+
+#include <cfloat>
+#include <cmath>
+#include <string>
+#include <vector>
+
+namespace rive::gpu
+{
+class CudaPathRenderer : public Renderer
+{
+public:
+    CudaPathRenderer(RenderContextCUDAImpl* impl, RenderTargetCUDA* target, LoadAction loadAction, ColorInt clearColor) :
+        m_impl(impl), m_target(target), m_loadAction(loadAction), m_clearColor(clearColor)
+    {}
+
+    void save() override { m_stack.push_back(m_stack.back()); }
+    void restore() override
+    {
+        if (m_stack.size() > 1)
+            m_stack.pop_back();
+    }
+    void transform(const Mat2D& m) override { m_stack.back() = m_stack.back() * m; }
+
+    void drawPath(RenderPath* renderPath, RenderPaint* renderPaint) override
+    {
+        auto* path = static_cast<RiveRenderPath*>(renderPath);
+        auto* paint = static_cast<RiveRenderPaint*>(renderPaint);
+        const RawPath& raw = path->getRawPath();
+        if (raw.empty() || (paint->getIsStroked() && !(paint->getThickness() > 0)) || !(paint->getFeather() >= 0))
+            return;
+        if (paint->getFeather() != 0 || paint->getType() != PaintType::solidColor || paint->getBlendMode() != BlendMode::srcOver ||
+            paint->getImageTexture() != nullptr || (!paint->getIsStroked() && path->getFillRule() == FillRule::clockwise))
+        {
+            refuse("drawPath with a feather / gradient / image / blend mode / clockwise fill");
+            return;
+        }
+        const Mat2D& m = m_stack.back();
+        rivecuda_path p;
+        memset(&p, 0, sizeof(p));
+        p.first_verb = static_cast<uint32_t>(m_verbs.size());
+        p.verb_count = static_cast<uint32_t>(raw.verbs().size());
+        p.first_point = static_cast<uint32_t>(m_points.size());
+        for (int i = 0; i < 6; ++i)
+            p.matrix[i] = m[i];
+        p.color = paint->getColor();
+        if (paint->getIsStroked())
+        {
+            p.stroke = 1;
+            p.stroke_radius = fmaxf(paint->getThickness() * .5f, FLT_MIN); // draw.cpp:603-607
+            p.join = static_cast<uint32_t>(paint->getJoin());
+            p.cap = static_cast<uint32_t>(paint->getCap());
+            p.matrix_max_scale = m.findMaxScale(); // draw.cpp:778
+            p.polar_segments_per_radian =
+                math::calc_polar_segments_per_radian<kPolarPrecision>(p.stroke_radius * p.matrix_max_scale); // draw.cpp:806-808
+        }
+        else
+        {
+            p.fill_rule = path->getFillRule() == FillRule::evenOdd ? 1 : 0;
+        }
+        for (PathVerb v : raw.verbs())
+            m_verbs.push_back(static_cast<uint8_t>(v));
+        m_points.insert(m_points.end(), raw.points().begin(), raw.points().end());
+        m_paths.push_back(p);
+    }
+
+    void clipPath(RenderPath*) override { refuse("clipPath"); }
+    void drawImage(const RenderImage*, ImageSampler, BlendMode, float) override { refuse("drawImage"); }
+    void drawImageMesh(const RenderImage*,
+                       ImageSampler,
+                       rcp<RenderBuffer>,
+                       rcp<RenderBuffer>,
+                       rcp<RenderBuffer>,
+                       uint32_t,
+                       uint32_t,
+                       BlendMode,
+                       float) override
+    {
+        refuse("drawImageMesh");
+    }
+    void modulateOpacity(float) override { refuse("modulateOpacity"); }
+
+    // The first call this renderer cannot express, or nullptr.
+    const char* refusedCall() const { return m_refused.empty() ? nullptr : m_refused.c_str(); }
+    size_t pathCount() const { return m_paths.size(); }
+
+    // Renders the collected frame. False if a call was refused or the device reports an error.
+    bool flush()
+    {
+        if (!m_refused.empty())
+        {
+            fprintf(stderr, "CudaPathRenderer: the frame contains %s; draw it with RiveRenderer\n", m_refused.c_str());
+            return false;
+        }
+        RenderContextCUDAImpl::PlainPathFrame frame;
+        frame.renderTarget = m_target;
+        frame.loadAction = m_loadAction;
+        frame.clearColor = m_clearColor;
+        frame.points = m_points.data();
+        frame.pointCount = m_points.size();
+        frame.verbs = m_verbs.data();
+        frame.verbCount = m_verbs.size();
+        frame.paths = m_paths.data();
+        frame.pathCount = m_paths.size();
+        return m_impl->flushPlainPaths(frame);
+    }
+
+private:
+    void refuse(const char* what)
+    {
+        if (m_refused.empty())
+            m_refused = what;
+    }
+
+    RenderContextCUDAImpl* m_impl;
+    RenderTargetCUDA* m_target;
+    LoadAction m_loadAction;
+    ColorInt m_clearColor;
+    std::vector<Mat2D> m_stack{Mat2D()};
+    std::vector<Vec2D> m_points;
+    std::vector<uint8_t> m_verbs;
+    std::vector<rivecuda_path> m_paths;
+    std::string m_refused;
+};
+} // namespace rive::gpu

@@ -8,6 +8,7 @@
  */
 #include "testing_window_cuda.hpp"
 #include "path_dump.hpp"
+#include "cuda_path_renderer.hpp"
 
 #include "rive/renderer/rive_renderer.hpp"
 
@@ -86,6 +87,15 @@ std::unique_ptr<rive::Renderer> TestingWindowCUDA::beginFrame(
         .strokesDisabled = options.strokesDisabled,
         .clockwiseFillOverride = false,
     };
+    if (m_gpuFrontEnd)
+    {
+        auto pathRenderer = std::make_unique<CudaPathRenderer>(m_renderContext->static_impl_cast<RenderContextCUDAImpl>(),
+                                                               m_renderTarget.get(),
+                                                               frameDescriptor.loadAction,
+                                                               frameDescriptor.clearColor);
+        m_pathRenderer = pathRenderer.get();
+        return pathRenderer;
+    }
     m_renderContext->beginFrame(frameDescriptor);
     std::unique_ptr<rive::Renderer> renderer = std::make_unique<RiveRenderer>(m_renderContext.get());
     if (m_pathDump != nullptr && m_pathDump->active)
@@ -106,6 +116,18 @@ void TestingWindowCUDA::flushPLSContext(RenderTarget* offscreenRenderTarget)
 
 void TestingWindowCUDA::endFrame(std::vector<uint8_t>* pixelData)
 {
+    if (m_gpuFrontEnd)
+    {
+        if (m_pathRenderer == nullptr || !m_pathRenderer->flush())
+        {
+            fprintf(stderr, "TestingWindowCUDA: --gpu-front-end cannot draw this frame\n");
+            abort();
+        }
+        m_pathRenderer = nullptr;
+        if (pixelData != nullptr)
+            m_renderTarget->readPixels(pixelData);
+        return;
+    }
     flushPLSContext(nullptr);
     if (m_pathDump != nullptr)
         m_pathDump->active = false; // only the first frame is dumped

@@ -7,6 +7,11 @@
 #include "common/testing_window.hpp"
 #include "render_context_cuda_impl.hpp"
 
+namespace rive::gpu
+{
+class CudaPathRenderer;
+}
+
 class TestingWindowCUDA : public TestingWindow
 {
 public:
@@ -28,8 +33,14 @@ public:
     // frame into `sink` (path_dump.hpp).
     void setPathDump(struct PathDumpSink* sink) { m_pathDump = sink; }
 
+    // --gpu-front-end: beginFrame() hands out a CudaPathRenderer; endFrame()
+    // aborts if the frame contained anything but plain fills and strokes.
+    void setGpuFrontEnd(bool enabled) { m_gpuFrontEnd = enabled; }
+
 private:
     struct PathDumpSink* m_pathDump = nullptr;
+    bool m_gpuFrontEnd = false;
+    class rive::gpu::CudaPathRenderer* m_pathRenderer = nullptr; // owned by beginFrame()'s caller
     std::unique_ptr<rive::gpu::RenderContext> m_renderContext;
     rive::rcp<rive::gpu::RenderTargetCUDA> m_renderTarget;
     uint64_t m_frameNumber = 0;

@@ -419,6 +419,86 @@ static void convert_atlas_batches(const AtlasDrawBatch* batches,
     }
 }
 
+bool RenderContextCUDAImpl::flushPlainPaths(const PlainPathFrame& frame)
+{
+    RenderTargetCUDA* target = frame.renderTarget;
+    rivecuda_front_end_result r;
+    memset(&r, 0, sizeof(r));
+    if (m_abi.front_end_paths(m_ctx,
+                              frame.pointCount != 0 ? &frame.points->x : nullptr,
+                              static_cast<uint32_t>(frame.pointCount),
+                              frame.verbs,
+                              static_cast<uint32_t>(frame.verbCount),
+                              frame.paths,
+                              static_cast<uint32_t>(frame.pathCount),
+                              target->width(),
+                              target->height(),
+                              &r) != 0)
+    {
+        fprintf(stderr, "RenderContextCUDAImpl::flushPlainPaths: %s\n", m_abi.last_error());
+        return false;
+    }
+    resizeTessellationTexture(kTessTextureWidth, r.tess_data_height);
+
+    // The descriptor LogicalFlush::layoutResources would have produced for this frame
+    // (render_context.cpp:1240-1392): one logical flush, everything at offset 0.
+    FlushDescriptor desc;
+    desc.renderTarget = target;
+    desc.interlockMode = InterlockMode::rasterOrdering;
+    desc.colorLoadAction = frame.loadAction;
+    desc.colorClearValue = frame.clearColor;
+    desc.coverageClearValue = 0;
+    desc.renderTargetUpdateBounds = {0, 0, static_cast<int32_t>(target->width()), static_cast<int32_t>(target->height())};
+    desc.pathCount = r.path_count;
+    desc.contourCount = r.contour_count;
+    desc.tessVertexSpanCount = r.tess_vertex_span_count;
+    desc.tessDataHeight = r.tess_data_height;
+    desc.ditherMode = DitherMode::interleavedGradientNoise; // FrameDescriptor's default
+    {
+        const size_t size = sizeof(FlushUniforms);
+        resizeFlushUniformBuffer(size);
+        void* mapped = mapFlushUniformBuffer(size);
+        if (mapped == nullptr)
+            return false;
+        new (mapped) FlushUniforms(desc, m_platformFeatures);
+        unmapFlushUniformBuffer(size);
+    }
+
+    rivecuda_flush_desc d;
+    memset(&d, 0, sizeof(d));
+    d.abi_version = RIVECUDA_ABI_VERSION;
+    d.interlock_mode = static_cast<uint32_t>(desc.interlockMode);
+    d.render_target = target->handle();
+    d.color_load_action = static_cast<uint32_t>(desc.colorLoadAction);
+    d.color_clear_value = desc.colorClearValue;
+    d.coverage_clear_value = desc.coverageClearValue;
+    d.update_bounds[2] = static_cast<int32_t>(target->width());
+    d.update_bounds[3] = static_cast<int32_t>(target->height());
+    d.path_count = r.path_count;
+    d.contour_count = r.contour_count;
+    d.tess_vertex_span_count = r.tess_vertex_span_count;
+    d.tess_data_height = r.tess_data_height;
+    d.dither_mode = static_cast<uint8_t>(desc.ditherMode);
+
+    // One midpointFanPatches batch over all patches (LogicalFlush::pushMidpointFanDraw,
+    // render_context.cpp:3426-3450).
+    rivecuda_draw_batch batch;
+    memset(&batch, 0, sizeof(batch));
+    batch.draw_type = RIVECUDA_DRAW_MIDPOINT_FAN_PATCHES;
+    batch.element_count = r.patch_count;
+    batch.base_element = r.first_patch;
+    batch.index_count_per_instance = kMidpointFanPatchIndexCount;
+    batch.base_index = kMidpointFanPatchBaseIndex;
+    batch.first_blend_mode = static_cast<uint32_t>(BlendMode::srcOver);
+    const uint32_t batchCount = r.patch_count != 0 ? 1u : 0u;
+    if (m_abi.flush(m_ctx, &d, &batch, batchCount, nullptr, 0, nullptr, 0) != 0)
+    {
+        fprintf(stderr, "RenderContextCUDAImpl::flushPlainPaths: %s\n", m_abi.last_error());
+        return false;
+    }
+    return true;
+}
+
 void RenderContextCUDAImpl::flush(const FlushDescriptor& desc)
 {
     if (desc.interlockMode != InterlockMode::rasterOrdering)

@@ -124,6 +124,27 @@ public:
     // Blocks until the device has finished everything flushed so far.
     void sync();
 
+    // a frame made only of plain draws (solid colour, src-over, no clip,
+    // no feather; nonZero / evenOdd fills and strokes), handed over as RawPaths. The device does
+    // what PathDraw::initForMidpointFan / pushMidpointFanTessellationData / pushPath and
+    // LogicalFlush::layoutResources do on the CPU (rivecuda_front_end_paths), then the frame is
+    // flushed like any other. See CudaPathRenderer (cuda_path_renderer.hpp) for the
+    // rive::Renderer that collects such a frame. Returns false (with a message on stderr) when
+    // the paths exceed one logical flush or the ABI reports an error.
+    struct PlainPathFrame
+    {
+        RenderTargetCUDA* renderTarget = nullptr;
+        gpu::LoadAction loadAction = gpu::LoadAction::clear;
+        ColorInt clearColor = 0;
+        const Vec2D* points = nullptr;
+        size_t pointCount = 0;
+        const uint8_t* verbs = nullptr; // rive::PathVerb values
+        size_t verbCount = 0;
+        const rivecuda_path* paths = nullptr;
+        size_t pathCount = 0;
+    };
+    bool flushPlainPaths(const PlainPathFrame&);
+
     // RenderContextImpl overrides.
     rcp<RenderBuffer> makeRenderBuffer(RenderBufferType,
                                        RenderBufferFlags,

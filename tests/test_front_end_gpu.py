@@ -152,3 +152,28 @@ def test_device_front_end_equals_its_host_build_on_random_paths(built, seed, n_p
         n = res.path_count
         assert np.array_equal(F.read_buffer(rp, 1, n * 64).view(np.uint32).reshape(-1, 16)[1:, :8], want.path_data[1:n, :8])
         assert np.array_equal(F.read_buffer(rp, 2, n * 8).view(np.uint32).reshape(-1, 2)[1:], want.paint_data[1:n])
+
+
+@pytest.mark.parametrize("scene,golden", [("c2", "c2_4k"), ("f1", "f1"), ("s1", "s1"), ("gm:trickycubicstrokes", "trickycubicstrokes"),
+                                          ("gm:strokes3", "strokes3")])
+def test_cpp_path_renderer_draws_the_same_frame(built, scene, golden):
+    """SURVEY 8 f1 in the compiled host: the scene player with --gpu-front-end draws through
+    CudaPathRenderer (host/cuda_path_renderer.hpp: the RawPaths go to rivecuda_front_end_paths,
+    no PathDraw / LogicalFlush on the CPU). The frame must equal, bit for bit, the replay of the
+    flush trace the reference front end produced for the same scene."""
+    import subprocess
+    import tempfile
+    from rive_runtime_b200 import abi, replay as R, trace as T
+    abi.load()
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    player = os.path.join(root, "rive-runtime_b200", "_build", "rive_cuda_player")
+    if not os.path.exists(player):
+        pytest.skip("scene player not built (needs the reference tree at build time)")
+    want = R.replay(T.parse(os.path.join(GOLDEN, golden + ".rvct.xz"))).frames[-1]
+    with tempfile.TemporaryDirectory() as tmp:
+        out = os.path.join(tmp, "frame.rgba")
+        env = dict(os.environ, RIVECUDA_LIB=os.path.join(root, "rive-runtime_b200", "_build", "librivecuda.so"))
+        subprocess.check_call([player, "--scene", scene, "--gpu-front-end", "--budget-ms", "0", "--out", out], env=env,
+                              stdout=subprocess.DEVNULL, timeout=300)
+        px = np.fromfile(out, dtype=np.uint8)
+    assert px.size == want.size and np.array_equal(px.reshape(want.shape), want)
