@@ -249,9 +249,40 @@ int rivecuda_target_read_pixels_async(rivecuda_ctx* ctx, rivecuda_target* t, voi
 
 int rivecuda_target_read_wait(rivecuda_ctx*, rivecuda_target*) { return 0; }
 
-int rivecuda_front_end_paths(rivecuda_ctx*, const float*, uint32_t, const uint8_t*, uint32_t, const rivecuda_path*, uint32_t, uint32_t, uint32_t, rivecuda_front_end_result*)
+// The recorder has no device to run the front end on. With $RIVECUDA_TRACE_FRONT_END_OUT set it
+// writes the call's inputs there (what the host collected: tests compare them with the
+// --dump-paths file of the same scene) and reports an empty frame; otherwise it fails.
+//   u32 magic "RPF1", pathCount, pointCount, verbCount, frameWidth, frameHeight, 0, 0;
+//   rivecuda_path paths[]; u8 verbs[] (padded to 4); float points[][2]
+int rivecuda_front_end_paths(rivecuda_ctx*,
+                             const float* points,
+                             uint32_t pointCount,
+                             const uint8_t* verbs,
+                             uint32_t verbCount,
+                             const rivecuda_path* paths,
+                             uint32_t pathCount,
+                             uint32_t frameWidth,
+                             uint32_t frameHeight,
+                             rivecuda_front_end_result* result)
 {
-    return fail("rivecuda_trace: the GPU path front end needs a device (the recorder renders nothing)");
+    const char* out = getenv("RIVECUDA_TRACE_FRONT_END_OUT");
+    if (out == nullptr)
+        return fail("rivecuda_trace: the GPU path front end needs a device (the recorder renders nothing)");
+    FILE* f = fopen(out, "wb");
+    if (f == nullptr)
+        return fail("rivecuda_trace: cannot open $RIVECUDA_TRACE_FRONT_END_OUT");
+    const uint32_t header[8] = {0x31465052u, pathCount, pointCount, verbCount, frameWidth, frameHeight, 0u, 0u};
+    const uint8_t pad[4] = {0, 0, 0, 0};
+    fwrite(header, sizeof(header), 1, f);
+    fwrite(paths, sizeof(rivecuda_path), pathCount, f);
+    fwrite(verbs, 1, verbCount, f);
+    fwrite(pad, 1, (4 - verbCount % 4) % 4, f);
+    fwrite(points, 8, pointCount, f);
+    fclose(f);
+    memset(result, 0, sizeof(*result));
+    result->path_count = 1; // the reserved record
+    result->tess_data_height = 1;
+    return 0;
 }
 
 int rivecuda_debug_read_buffer(rivecuda_ctx*, uint32_t, void*, size_t, size_t)

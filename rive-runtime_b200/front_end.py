@@ -115,6 +115,22 @@ def load_paths(path: str) -> PathDump:
                     (np.concatenate(points) if points else np.zeros(0, np.float32)).reshape(-1, 2), bool(complete))
 
 
+def load_front_end_call(path: str):
+    """Reads what the call recorder (librivecuda_trace.so with $RIVECUDA_TRACE_FRONT_END_OUT)
+    saw in rivecuda_front_end_paths: (PathDump, frame_width, frame_height)."""
+    raw = open(path, "rb").read()
+    magic, n_paths, n_points, n_verbs, width, height, _, _ = struct.unpack_from("<8I", raw, 0)
+    if magic != 0x31465052:
+        raise ValueError("not a recorded front-end call")
+    pos = 32
+    paths = np.frombuffer(raw, dtype=PATH_DTYPE, count=n_paths, offset=pos).copy()
+    pos += n_paths * PATH_DTYPE.itemsize
+    verbs = np.frombuffer(raw, dtype=np.uint8, count=n_verbs, offset=pos).copy()
+    pos += (n_verbs + 3) & ~3
+    points = np.frombuffer(raw, dtype=np.float32, count=n_points * 2, offset=pos).reshape(-1, 2).copy()
+    return PathDump(paths, verbs, points, True), width, height
+
+
 def run(replayer, dump: PathDump, frame_width: int = 0, frame_height: int = 0) -> FrontEndResult:
     """rivecuda_front_end_paths on a Replayer's context. A non-zero frame size enables the
     reference's frame cull (paths outside the render target draw nothing)."""

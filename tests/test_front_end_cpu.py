@@ -157,3 +157,35 @@ def test_stroke_scenes_exercise_every_stroke_feature():
     assert int(pivot.sum()) > 100                                   # cusp pivots (chop_cubic_around_cusps)
     assert int(((w[:, 12] >> 16).astype(np.int32) > 2048).sum()) > 100  # spans wrapping a 2048-texel row
     assert polar.max() > 32 and join.max() > 32
+
+
+@pytest.mark.parametrize("scene,golden", [("s1", "s1"), ("f1", "f1"), ("gm:trickycubicstrokes", "trickycubicstrokes"),
+                                          ("gm:strokes3", "strokes3")])
+def test_cpp_path_renderer_hands_over_what_the_reference_front_end_saw(scene, golden, tmp_path):
+    """host/cuda_path_renderer.hpp (the rive::Renderer that feeds the device front end from C++),
+    run on the call recorder: the RawPaths, matrices, paints and the two per-stroke scalars it
+    passes to rivecuda_front_end_paths must equal the --dump-paths record of the same scene (whose
+    scalars come from front_end.stroke_scalars, the Python mirror) -- and therefore produce the
+    reference's buffers through the front-end core, which the test above checks."""
+    import subprocess
+    from conftest import ROOT
+    player = os.path.join(ROOT, "rive-runtime_b200", "_build", "rive_cuda_player")
+    recorder = os.path.join(ROOT, "rive-runtime_b200", "_build", "librivecuda_trace.so")
+    if not os.path.exists(player) or not os.path.exists(recorder):
+        pytest.skip("scene player not built (needs the reference tree at build time)")
+    out = str(tmp_path / "call.rpf")
+    env = dict(os.environ, RIVECUDA_LIB=recorder, RIVECUDA_TRACE_OUT=str(tmp_path / "unused.rvct"), RIVECUDA_TRACE_FRONT_END_OUT=out)
+    subprocess.check_call([player, "--scene", scene, "--gpu-front-end", "--budget-ms", "0"], env=env, stdout=subprocess.DEVNULL, timeout=120)
+    got, width, height = F.load_front_end_call(out)
+    want = F.load_paths(os.path.join(GOLDEN, golden + ".paths.xz"))
+    recs = T.parse(os.path.join(GOLDEN, golden + ".rvct.xz"))
+    tc = next(r for r in recs if r.tag == T.TARGET_CREATE)
+    assert (width, height) == (tc.fields["width"], tc.fields["height"])
+    assert np.array_equal(got.verbs, want.verbs)
+    assert np.array_equal(got.points.view(np.uint32), want.points.view(np.uint32))
+    assert got.paths.size == want.paths.size
+    for field in want.paths.dtype.names:
+        a, b = got.paths[field], want.paths[field]
+        if a.dtype.kind == "f":
+            a, b = a.view(np.uint32), b.view(np.uint32)
+        assert np.array_equal(a, b), field
