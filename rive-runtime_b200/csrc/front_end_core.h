@@ -468,15 +468,12 @@ FE_HD void enumerate_contour(const rivecuda_path& path, const V2* pts, uint32_t 
         sink.span(reversed, cubic_tan0(cubic), 0u, 0u, capSegments, capFlags);
     };
 
-    // The tangent the NEXT verb starts with (round joins measure the rotation up to it).
+    // The tangent the NEXT verb starts with (round joins measure the rotation up to it). Inside a
+    // contour only a close can follow the last line / cubic, so looking one verb ahead is enough.
+    auto has_next_curve = [&](uint32_t v) { return v + 1 < verbCount && (verbs[v + 1] == kVerbLine || verbs[v + 1] == kVerbCubic); };
     auto next_tangent = [&](uint32_t v, uint32_t kNext, V2 lastPt) -> V2 {
-        for (uint32_t w = v + 1; w < verbCount; ++w)
-        {
-            if (verbs[w] == kVerbLine)
-                return pts[kNext] - pts[kNext - 1];
-            if (verbs[w] == kVerbCubic)
-                return cubic_tan0(pts + kNext - 1);
-        }
+        if (has_next_curve(v))
+            return verbs[v + 1] == kVerbLine ? pts[kNext] - pts[kNext - 1] : cubic_tan0(pts + kNext - 1);
         // Last curve of a closed contour: the implicit closing line, else back to the first tangent.
         if (!same_bits(movePt, lastPt))
             return movePt - lastPt;
@@ -516,11 +513,8 @@ FE_HD void enumerate_contour(const rivecuda_path& path, const V2* pts, uint32_t 
         {
             if (roundJoin)
             {
-                bool hasNext = false;
-                for (uint32_t w = v + 1; w < verbCount; ++w)
-                    hasNext = hasNext || verbs[w] == kVerbLine || verbs[w] == kVerbCubic;
                 V2 nt = next_tangent(v, kEnd + 1, pts[kEnd]);
-                if (!hasNext && same_bits(movePt, pts[kEnd]))
+                if (!has_next_curve(v) && same_bits(movePt, pts[kEnd]))
                     nt = firstTangent;
                 thisJoinTangent = nt;
                 thisJoinSegments = polar_segments(tan1, nt, psr);

@@ -101,7 +101,7 @@ def test_polar_segment_counts_match_the_reference(name):
 FRONT_END_SCENES = ["f1", "s1", "c2_4k", "trickycubicstrokes", "trickycubicstrokes_roundcaps", "emptystroke", "strokes3",
                     "labyrinth_round", "labyrinth_square", "zero_control_stroke", "zerolinestroke", "OverStroke",
                     "bevel180strokes", "roundjoinstrokes", "widebuttcaps", "beziers", "CubicStroke", "inner_join_geometry",
-                    "teenyStrokes", "quadcap", "strokefill", "zeroPath"]
+                    "teenyStrokes", "quadcap", "strokefill", "zeroPath", "lots_of_tess_spans_stroke"]
 
 
 @pytest.mark.parametrize("name", FRONT_END_SCENES)

@@ -15,7 +15,7 @@ from conftest import GOLDEN
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("name", ["f1", "s1", "c2_4k", "trickycubicstrokes", "emptystroke", "strokes3", "OverStroke", "zero_control_stroke"])
+@pytest.mark.parametrize("name", ["f1", "s1", "c2_4k", "trickycubicstrokes", "emptystroke", "strokes3", "OverStroke", "zero_control_stroke", "lots_of_tess_spans_stroke"])
 def test_gpu_front_end_matches_reference_front_end(built, name):
     from rive_runtime_b200 import abi, front_end as F, replay as R, trace as T
     abi.load()

@@ -10,7 +10,7 @@ sys.path.insert(0, ROOT)
 from rive_runtime_b200 import abi, front_end as F, replay as R, trace as T  # noqa: E402
 
 abi.load()
-for name in sys.argv[1:] or ["c2_4k", "f1", "s1"]:
+for name in sys.argv[1:] or ["c2_4k", "f1", "s1", "lots_of_tess_spans_stroke"]:
     golden = os.path.join(ROOT, "tests", "golden")
     dump = F.load_paths(os.path.join(golden, name + ".paths.xz"))
     recs = T.parse(os.path.join(golden, name + ".rvct.xz"))

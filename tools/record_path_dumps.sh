@@ -10,7 +10,7 @@ OUT="${1:-$ROOT/tests/golden}"
 TMP="$(mktemp -d)"
 SCENES="f1 s1 gm:trickycubicstrokes gm:trickycubicstrokes_roundcaps gm:emptystroke gm:strokes3 gm:labyrinth_round
 gm:labyrinth_square gm:zero_control_stroke gm:zerolinestroke gm:OverStroke gm:bevel180strokes gm:roundjoinstrokes
-gm:widebuttcaps gm:beziers gm:CubicStroke gm:inner_join_geometry gm:teenyStrokes gm:quadcap gm:strokefill gm:zeroPath"
+gm:widebuttcaps gm:lots_of_tess_spans_stroke gm:beziers gm:CubicStroke gm:inner_join_geometry gm:teenyStrokes gm:quadcap gm:strokefill gm:zeroPath"
 for SCENE in $SCENES; do
   NAME="${SCENE#gm:}"
   RIVECUDA_LIB="$ROOT/rive-runtime_b200/_build/librivecuda_trace.so" RIVECUDA_TRACE_OUT="$TMP/$NAME.rvct" \
