@@ -799,10 +799,11 @@ template <bool EMIT> struct PlaceSink
         nextPadding = 0;
         int32_t y = static_cast<int32_t>(forwardLoc / kTessTextureWidth), x0 = static_cast<int32_t>(forwardLoc % kTessTextureWidth);
         int32_t x1 = x0 + static_cast<int32_t>(total);
-        int32_t ry = 0, rx0 = -1, rx1 = -1;
+        uint32_t ry = 0; // unsigned as in the reference: wraps (to 4294967296.f) when a span on row 0 is re-emitted
+        int32_t rx0 = -1, rx1 = -1;
         if (doubleSided)
         {
-            ry = static_cast<int32_t>((mirroredLoc - 1u) / kTessTextureWidth);
+            ry = (mirroredLoc - 1u) / static_cast<uint32_t>(kTessTextureWidth);
             rx0 = static_cast<int32_t>((mirroredLoc - 1u) % kTessTextureWidth) + 1;
             rx1 = rx0 - static_cast<int32_t>(total);
         }

@@ -115,6 +115,23 @@ def load_paths(path: str) -> PathDump:
                     (np.concatenate(points) if points else np.zeros(0, np.float32)).reshape(-1, 2), bool(complete))
 
 
+def write_paths(path: str, dump: PathDump, thickness) -> None:
+    """Writes a PathDump in the "RPT2" format of host/player/path_dump.hpp (the scene player draws
+    such a file with `--scene paths:FILE`). thickness: stroke thickness per path (0 for fills)."""
+    out = [struct.pack("<4I", 0x32545052, dump.paths.size, 1, 0)]
+    for i, p in enumerate(dump.paths):
+        out.append(np.asarray(p["matrix"], np.float32).tobytes())
+        out.append(struct.pack("<4I", int(p["fill_rule"]), int(p["color"]), int(p["verb_count"]), 0))
+        v = dump.verbs[int(p["first_verb"]):int(p["first_verb"]) + int(p["verb_count"])]
+        n_pts = int((v == 0).sum() + (v == 1).sum() + 3 * (v == 4).sum())
+        out[-1] = struct.pack("<4I", int(p["fill_rule"]), int(p["color"]), int(p["verb_count"]), n_pts)
+        out.append(struct.pack("<IfII", int(p["stroke"]), float(thickness[i]), int(p["join"]), int(p["cap"])))
+        out.append(v.tobytes() + b"\0" * ((4 - v.size % 4) % 4))
+        out.append(np.ascontiguousarray(dump.points[int(p["first_point"]):int(p["first_point"]) + n_pts], np.float32).tobytes())
+    with open(path, "wb") as f:
+        f.write(b"".join(out))
+
+
 def load_front_end_call(path: str):
     """Reads what the call recorder (librivecuda_trace.so with $RIVECUDA_TRACE_FRONT_END_OUT)
     saw in rivecuda_front_end_paths: (PathDump, frame_width, frame_height)."""

@@ -189,3 +189,47 @@ def test_cpp_path_renderer_hands_over_what_the_reference_front_end_saw(scene, go
         if a.dtype.kind == "f":
             a, b = a.view(np.uint32), b.view(np.uint32)
         assert np.array_equal(a, b), field
+
+
+@pytest.mark.parametrize("seed", [11, 12, 13, 14, 15, 16, 17, 18])
+def test_front_end_core_matches_the_reference_on_random_paths(seed, tmp_path):
+    """Fuzz, pinned on the reference itself: random RawPaths (lines, generic / cusped / looping /
+    degenerate cubics, closed, open and move-only contours, random matrices, joins, caps and
+    thicknesses, many partly or wholly outside the frame) are drawn through the reference's own
+    front end (scene player `--scene paths:FILE` on the call recorder); the host build of the
+    F1 kernels' core must reproduce its spans, contours, path and paint records byte for byte."""
+    import subprocess
+    from conftest import ROOT
+    from path_fuzz import prune_empty_segments, random_paths
+    player = os.path.join(ROOT, "rive-runtime_b200", "_build", "rive_cuda_player")
+    recorder = os.path.join(ROOT, "rive-runtime_b200", "_build", "librivecuda_trace.so")
+    if not os.path.exists(player) or not os.path.exists(recorder):
+        pytest.skip("scene player not built (needs the reference tree at build time)")
+    width, height = 1920, 1080
+    dump, thickness = prune_empty_segments(*random_paths(seed, 1500, width=width, height=height))
+    dump_file, trace_file = str(tmp_path / "fuzz.paths"), str(tmp_path / "fuzz.rvct")
+    F.write_paths(dump_file, dump, thickness)
+    env = dict(os.environ, RIVECUDA_LIB=recorder, RIVECUDA_TRACE_OUT=trace_file)
+    subprocess.check_call([player, "--scene", "paths:" + dump_file, "--budget-ms", "0", "--width", str(width), "--height", str(height)],
+                          env=env, stdout=subprocess.DEVNULL, timeout=120)
+    recs = T.parse(trace_file)
+    host = {r.fields["kind"]: r.data for r in recs if r.tag == T.BUFFER_UNMAP}
+    flushes = [r.fields["flush"] for r in recs if r.tag == T.FLUSH]
+    assert len(flushes) == 1 and len(flushes[0].batches) == 1 and flushes[0].batches[0].draw_type == 0
+    d = flushes[0].desc
+    out = front_end_host.run(dump, width, height)
+    res = out.result
+    assert (res.path_count, res.contour_count, res.tess_vertex_span_count, res.tess_data_height) == (
+        d.path_count, d.contour_count, d.tess_vertex_span_count, d.tess_data_height)
+    assert res.path_count > 1000  # most paths are on screen, some are culled
+    n = res.tess_vertex_span_count
+    want = np.frombuffer(host[6].tobytes()[:n * 64], dtype=np.uint32).reshape(-1, 16)
+    bad = np.nonzero((out.spans[:n] != want).any(axis=1))[0]
+    assert bad.size == 0, f"{bad.size} spans differ, first {bad[:5]}: got {out.spans[bad[0]]} want {want[bad[0]]}"
+    want = np.frombuffer(host[4].tobytes()[:res.contour_count * 16], dtype=np.uint32).reshape(-1, 4)
+    assert np.array_equal(out.contours[:res.contour_count], want)
+    n = res.path_count
+    want = np.frombuffer(host[1].tobytes()[:n * 64], dtype=np.uint32).reshape(-1, 16)
+    assert np.array_equal(out.path_data[1:n, :8], want[1:, :8])
+    want = np.frombuffer(host[2].tobytes()[:n * 8], dtype=np.uint32).reshape(-1, 2)
+    assert np.array_equal(out.paint_data[1:n], want[1:])

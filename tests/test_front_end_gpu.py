@@ -67,66 +67,6 @@ def test_gpu_front_end_matches_reference_front_end(built, name):
     assert np.array_equal(frame, want_frame)
 
 
-def random_paths(seed, n_paths, strokes=True):
-    """Random RawPaths in the dump format: lines, cubics (generic, cusps, loops, degenerate),
-    closed / open / move-only contours, random matrices and stroke styles."""
-    from rive_runtime_b200 import front_end as F
-    rng = np.random.default_rng(seed)
-    verbs, points, paths = [], [], np.zeros(n_paths, dtype=F.PATH_DTYPE)
-    nv = npnt = 0
-    for i in range(n_paths):
-        side = float(rng.choice([1.0, 30.0, 300.0, 1000.0]))
-        pv, pp = [], []
-        for _ in range(int(rng.integers(1, 4))):
-            cur = rng.uniform(-side, side, 2).astype(np.float32)
-            start = cur.copy()
-            pv.append(0)
-            pp.append(cur)
-            for _ in range(int(rng.integers(0, 6))):
-                kind = int(rng.integers(0, 8))
-                end = rng.uniform(-side, side, 2).astype(np.float32)
-                if kind < 2:
-                    pv.append(1)
-                    pp.append(end)
-                else:
-                    c1 = rng.uniform(-side, side, 2).astype(np.float32)
-                    c2 = rng.uniform(-side, side, 2).astype(np.float32)
-                    if kind == 2:      # collinear overshoot: a cusp
-                        d = end - cur
-                        c1, c2 = cur + d * np.float32(1.5), cur - d * np.float32(.5)
-                    elif kind == 3:    # coincident control points
-                        c1, c2 = cur.copy(), end.copy()
-                    elif kind == 4:    # a loop
-                        d = end - cur
-                        perp = np.array([d[1], -d[0]], np.float32)
-                        c1, c2 = end + perp, cur + perp
-                    pv.append(4)
-                    pp.extend([c1.astype(np.float32), c2.astype(np.float32), end])
-                cur = end
-            if rng.integers(0, 4) == 0 and len(pp) > 1:
-                pv.append(1)
-                pp.append(start)
-            if rng.integers(0, 2) == 0:
-                pv.append(5)
-        ang = rng.uniform(-3.2, 3.2)
-        sx, sy = rng.uniform(.1, 4.0, 2)
-        m = np.array([np.cos(ang) * sx, np.sin(ang) * sx, -np.sin(ang) * sy, np.cos(ang) * sy,
-                      rng.uniform(0, 3840), rng.uniform(0, 2160)], np.float32)
-        if rng.integers(0, 3) == 0:
-            m[1] = m[2] = 0
-        color = int(rng.integers(0, 1 << 32))
-        if strokes and rng.integers(0, 2) == 0:
-            radius, max_scale, psr = F.stroke_scalars(m, float(rng.uniform(.2, 60.0)))
-            paths[i] = (nv, len(pv), npnt, 0, m, color, 1, radius, int(rng.integers(0, 3)), int(rng.integers(0, 3)), psr, max_scale, 0)
-        else:
-            paths[i] = (nv, len(pv), npnt, int(rng.integers(0, 2)), m, color, 0, 0.0, 0, 0, 0.0, 0.0, 0)
-        verbs.extend(pv)
-        points.extend(pp)
-        nv += len(pv)
-        npnt += len(pp)
-    return F.PathDump(paths, np.array(verbs, np.uint8), np.array(points, np.float32).reshape(-1, 2), True)
-
-
 @pytest.mark.parametrize("seed,n_paths", [(1, 2000), (2, 12000)])
 def test_device_front_end_equals_its_host_build_on_random_paths(built, seed, n_paths):
     """Size-independent property: for arbitrary finite RawPaths the kernels and the host build of
@@ -134,8 +74,9 @@ def test_device_front_end_equals_its_host_build_on_random_paths(built, seed, n_p
     bytes -- spans, contours, path and paint records, counts -- including the frame cull."""
     from oracle import front_end_host
     from rive_runtime_b200 import abi, front_end as F, replay as R
+    from path_fuzz import prune_empty_segments, random_paths
     abi.load()
-    dump = random_paths(seed, n_paths)
+    dump, _ = prune_empty_segments(*random_paths(seed, n_paths))
     want = front_end_host.run(dump, 3840, 2160)
     with R.Replayer(0) as rp:
         res = F.run(rp, dump, 3840, 2160)
