@@ -385,234 +385,238 @@ FE_HD ContourShape contour_shape(const uint8_t* verbs, uint32_t verbCount, bool 
     return s;
 }
 
-// One contour: pts[0] is the move point, verbs[] are the verbs after the move (up to the next
-// move). Sink: void span(const V2 cubic[4], V2 joinTangent, uint32_t parametric, uint32_t polar,
-// uint32_t joinSegments, uint32_t flags);
-template <typename Sink>
-FE_HD void enumerate_contour(const rivecuda_path& path, const V2* pts, uint32_t pointCount, const uint8_t* verbs, uint32_t verbCount, Sink& sink)
+// One contour, as the list of "items" that emit spans independently of each other: item v < verbCount
+// is verb v after the move (closes emit nothing), item verbCount is the tail (the implicit closing
+// line, or the two caps of an empty stroked contour). Everything an item needs besides its own
+// points is in the ContourCtx or derived from the neighbouring verbs, so a thread can walk the
+// items in order (enumerate_contour) or a warp can take one item per lane (kernels_front_end.cu).
+struct ContourCtx
 {
-    const bool isStroke = path.stroke != 0;
-    const ContourShape shape = contour_shape(verbs, verbCount, isStroke);
-    const V2 movePt = pts[0];
-    V2 joinTangent = {0.f, 1.f};
-    uint32_t joinSegments = 1;
-    V2 c[4];
+    const rivecuda_path* path;
+    const V2* pts; // pts[0] is the move point
+    const uint8_t* verbs; // the verbs after the move, up to the next move
+    uint32_t pointCount, verbCount;
+    bool isStroke, closed, empty, roundJoin;
+    uint32_t joinTypeFlags;          // of the stroke's join
+    uint32_t capSegments, capFlags;  // emulated caps (draw.cpp:1283-1340, 2019-2045); 0 = none
+    V2 firstTangent;                 // tan0 of the first curve (round joins close back onto it)
+};
 
-    if (!isStroke)
+FE_HD uint32_t verb_point_count(uint8_t verb) { return verb == kVerbLine ? 1u : verb == kVerbCubic ? 3u : 0u; }
+FE_HD bool verb_draws(uint8_t verb) { return verb == kVerbLine || verb == kVerbCubic; }
+
+FE_HD ContourCtx make_contour_ctx(const rivecuda_path& path, const V2* pts, uint32_t pointCount, const uint8_t* verbs, uint32_t verbCount)
+{
+    ContourCtx ctx;
+    ctx.path = &path;
+    ctx.pts = pts;
+    ctx.verbs = verbs;
+    ctx.pointCount = pointCount;
+    ctx.verbCount = verbCount;
+    ctx.isStroke = path.stroke != 0;
+    // A contour's curves come first; only a close can follow them (RawPath re-opens with a move).
+    ctx.closed = !ctx.isStroke || (verbCount != 0 && verbs[verbCount - 1] == kVerbClose);
+    ctx.empty = verbCount == 0 || !verb_draws(verbs[0]);
+    ctx.roundJoin = path.join == kJoinRound;
+    ctx.joinTypeFlags = path.join == kJoinMiter ? kFlagMiterRevertJoin : ctx.roundJoin ? kFlagRoundJoin : kFlagBevelJoin;
+    ctx.capSegments = ctx.capFlags = 0;
+    ctx.firstTangent = V2{0.f, 1.f};
+    if (!ctx.isStroke)
+        return ctx;
+    if (!ctx.empty)
+        ctx.firstTangent = verbs[0] == kVerbLine ? pts[1] - pts[0] : cubic_tan0(pts);
+    uint32_t cap;
+    bool needsCaps;
+    if (!ctx.empty)
     {
-        uint32_t k = 1;
-        for (uint32_t v = 0; v < verbCount; ++v)
+        cap = path.cap;
+        needsCaps = !ctx.closed;
+    }
+    else
+    {
+        cap = empty_stroke_cap(ctx.closed, path.join, path.cap);
+        needsCaps = cap != kCapButt;
+    }
+    if (needsCaps)
+    {
+        if (cap == kCapRound)
         {
-            if (verbs[v] == kVerbLine)
-            {
-                line_to_cubic(pts[k - 1], pts[k], c);
-                sink.span(c, joinTangent, 1u, 1u, 1u, 0u);
-                k += 1;
-            }
-            else if (verbs[v] == kVerbCubic)
-            {
-                sink.span(pts + k - 1, V2{0.f, 0.f}, wang_cubic_segments(pts + k - 1, path.matrix), 1u, 1u, 0u);
-                k += 3;
-            }
+            float n = ceilf(path.polar_segments_per_radian * 3.14159265f);
+            n += 2.f;
+            n = fminf(n, static_cast<float>(kMaxPolarSegments));
+            ctx.capSegments = static_cast<uint32_t>(n);
         }
-        if (!same_bits(pts[pointCount - 1], movePt))
+        else
         {
-            line_to_cubic(pts[pointCount - 1], movePt, c);
-            sink.span(c, joinTangent, 1u, 1u, 1u, 0u);
+            ctx.capSegments = kMiterOrBevelJoinSegments;
+        }
+        const uint32_t flagCap = !ctx.closed ? path.cap : empty_stroke_cap(true, path.join, path.cap);
+        ctx.capFlags = (flagCap == kCapButt ? kFlagBevelJoin : flagCap == kCapSquare ? kFlagMiterClipJoin : kFlagRoundJoin) | kFlagEmulatedStrokeCap;
+    }
+    return ctx;
+}
+
+struct Join
+{
+    V2 tangent;
+    uint32_t segments, flags;
+};
+
+// The join that follows stroked verb v, whose last point is pts[kEnd] and end tangent tan1
+// (draw.cpp:2095-2135, 2252-2285; the round joins' rotations are the tangent pairs pass 1
+// records, draw.cpp:925-948, 1004-1047).
+FE_HD Join join_after_verb(const ContourCtx& ctx, uint32_t v, uint32_t kEnd, V2 tan1)
+{
+    const bool finalVerb = v + 1 == ctx.verbCount;
+    if (!ctx.closed && finalVerb)
+        return {-find_ending_tangent(ctx.pts, ctx.pointCount), ctx.capSegments, ctx.capFlags}; // the end cap
+    if (!ctx.roundJoin)
+        return {find_join_tangent(ctx.pts, ctx.pointCount, kEnd, ctx.closed), kMiterOrBevelJoinSegments, ctx.joinTypeFlags};
+    V2 next;
+    if (!finalVerb && verb_draws(ctx.verbs[v + 1]))
+        next = ctx.verbs[v + 1] == kVerbLine ? ctx.pts[kEnd + 1] - ctx.pts[kEnd] : cubic_tan0(ctx.pts + kEnd);
+    else if (!same_bits(ctx.pts[0], ctx.pts[kEnd]))
+        next = ctx.pts[0] - ctx.pts[kEnd]; // the implicit closing line
+    else
+        next = ctx.firstTangent;
+    return {next, polar_segments(tan1, next, ctx.path->polar_segments_per_radian), ctx.joinTypeFlags};
+}
+
+// Item v of the contour; k = index in pts of the verb's first own point (1 + the points of the
+// verbs before it). Sink: void span(const V2 cubic[4], V2 joinTangent, uint32_t parametric,
+// uint32_t polar, uint32_t joinSegments, uint32_t flags);
+template <typename Sink> FE_HD void emit_item(const ContourCtx& ctx, uint32_t v, uint32_t k, Sink& sink)
+{
+    const rivecuda_path& path = *ctx.path;
+    const V2* pts = ctx.pts;
+    const V2 movePt = pts[0];
+    V2 c[4];
+    if (v == ctx.verbCount)
+    {
+        // The tail.
+        const V2 lastPt = pts[ctx.pointCount - 1];
+        if (ctx.isStroke && ctx.empty)
+        {
+            if (ctx.capSegments != 0)
+            {
+                // An empty contour: both caps on p0 (draw.cpp:2308-2322), each pushed like
+                // pushEmulatedStrokeCapAsJoinBeforeCubic (draw.cpp:2377-2400).
+                const V2 left = {movePt.x - 1.f, movePt.y}, right = {movePt.x + 1.f, movePt.y};
+                const V2 a[4] = {movePt, right, right, right}, b[4] = {movePt, left, left, left};
+                const V2 ra[4] = {a[3], a[2], a[1], a[0]}, rb[4] = {b[3], b[2], b[1], b[0]};
+                sink.span(ra, cubic_tan0(a), 0u, 0u, ctx.capSegments, ctx.capFlags);
+                sink.span(rb, cubic_tan0(b), 0u, 0u, ctx.capSegments, ctx.capFlags);
+            }
+            return;
+        }
+        if (!ctx.closed || same_bits(lastPt, movePt))
+            return;
+        line_to_cubic(lastPt, movePt, c);
+        if (!ctx.isStroke)
+        {
+            sink.span(c, V2{0.f, 1.f}, 1u, 1u, 1u, 0u);
+        }
+        else if (ctx.roundJoin)
+        {
+            sink.span(c, ctx.firstTangent, 1u, 1u, polar_segments(movePt - lastPt, ctx.firstTangent, path.polar_segments_per_radian), ctx.joinTypeFlags);
+        }
+        else
+        {
+            sink.span(c, find_starting_tangent(pts, ctx.pointCount), 1u, 1u, kMiterOrBevelJoinSegments, ctx.joinTypeFlags);
         }
         return;
     }
 
-    const uint32_t join = path.join;
-    const bool roundJoin = join == kJoinRound;
-    const float psr = path.polar_segments_per_radian;
-    uint32_t joinTypeFlags = join == kJoinMiter ? kFlagMiterRevertJoin : roundJoin ? kFlagRoundJoin : kFlagBevelJoin;
-
-    // Caps (draw.cpp:1283-1340, 2019-2045).
-    uint32_t capSegments = 0, capFlags = 0;
+    const uint8_t verb = ctx.verbs[v];
+    if (!verb_draws(verb))
+        return;
+    if (!ctx.isStroke)
     {
-        uint32_t cap;
-        bool needsCaps;
-        if (!shape.empty)
+        if (verb == kVerbLine)
         {
-            cap = path.cap;
-            needsCaps = !shape.closed;
+            line_to_cubic(pts[k - 1], pts[k], c);
+            sink.span(c, V2{0.f, 1.f}, 1u, 1u, 1u, 0u);
         }
         else
         {
-            cap = empty_stroke_cap(shape.closed, join, path.cap);
-            needsCaps = cap != kCapButt;
+            sink.span(pts + k - 1, V2{0.f, 0.f}, wang_cubic_segments(pts + k - 1, path.matrix), 1u, 1u, 0u);
         }
-        if (needsCaps)
-        {
-            if (cap == kCapRound)
-            {
-                float n = ceilf(psr * 3.14159265f);
-                n += 2.f;
-                n = fminf(n, static_cast<float>(kMaxPolarSegments));
-                capSegments = static_cast<uint32_t>(n);
-            }
-            else
-            {
-                capSegments = kMiterOrBevelJoinSegments;
-            }
-            const uint32_t flagCap = !shape.closed ? path.cap : empty_stroke_cap(true, join, path.cap);
-            capFlags = (flagCap == kCapButt ? kFlagBevelJoin : flagCap == kCapSquare ? kFlagMiterClipJoin : kFlagRoundJoin) | kFlagEmulatedStrokeCap;
-        }
+        return;
     }
-    bool needsFirstCap = capSegments != 0;
 
-    auto push_cap_before = [&](const V2* cubic) {
-        // pushEmulatedStrokeCapAsJoinBeforeCubic (draw.cpp:2377-2400)
-        const V2 reversed[4] = {cubic[3], cubic[2], cubic[1], cubic[0]};
-        sink.span(reversed, cubic_tan0(cubic), 0u, 0u, capSegments, capFlags);
-    };
+    const float psr = path.polar_segments_per_radian;
+    const bool firstCurve = v == 0; // curves come first in a contour
+    if (verb == kVerbLine)
+    {
+        const Join join = join_after_verb(ctx, v, k, pts[k] - pts[k - 1]);
+        line_to_cubic(pts[k - 1], pts[k], c);
+        if (firstCurve && ctx.capSegments != 0)
+        {
+            const V2 reversed[4] = {c[3], c[2], c[1], c[0]};
+            sink.span(reversed, cubic_tan0(c), 0u, 0u, ctx.capSegments, ctx.capFlags);
+        }
+        sink.span(c, join.tangent, 1u, 1u, join.segments, join.flags);
+        return;
+    }
 
-    // The tangent the NEXT verb starts with (round joins measure the rotation up to it). Inside a
-    // contour only a close can follow the last line / cubic, so looking one verb ahead is enough.
-    auto has_next_curve = [&](uint32_t v) { return v + 1 < verbCount && (verbs[v + 1] == kVerbLine || verbs[v + 1] == kVerbCubic); };
-    auto next_tangent = [&](uint32_t v, uint32_t kNext, V2 lastPt) -> V2 {
-        if (has_next_curve(v))
-            return verbs[v + 1] == kVerbLine ? pts[kNext] - pts[kNext - 1] : cubic_tan0(pts + kNext - 1);
-        // Last curve of a closed contour: the implicit closing line, else back to the first tangent.
-        if (!same_bits(movePt, lastPt))
-            return movePt - lastPt;
-        return V2{0.f, 0.f}; // replaced by firstTangent by the caller
-    };
+    const V2* p = pts + k - 1;
+    const Join join = join_after_verb(ctx, v, k + 2, cubic_tan1(p));
+    V2 chopped[16];
+    float t[2] = {0.f, 0.f};
+    bool areCusps = false;
+    int numChops = find_cubic_convex_180_chops(p, t, &areCusps);
+    if (numChops != 0)
+    {
+        if (areCusps)
+        {
+            chop_cubic_around_cusps(p, chopped, t, numChops, path.matrix_max_scale);
+            numChops *= 2;
+        }
+        else if (numChops == 2)
+        {
+            chop_cubic_at(p, chopped, t[0], t[1]);
+        }
+        else
+        {
+            chop_cubic_at(p, chopped, t[0]);
+        }
+        p = chopped;
+    }
+    if (firstCurve && ctx.capSegments != 0)
+    {
+        const V2 reversed[4] = {p[3], p[2], p[1], p[0]};
+        sink.span(reversed, cubic_tan0(p), 0u, 0u, ctx.capSegments, ctx.capFlags);
+    }
+    if (numChops != 0)
+    {
+        // Chops before the final one carry the join tangent the PREVIOUS verb left behind
+        // ({0, 1} at the start of a contour) and no join of their own (draw.cpp:2225-2243).
+        V2 staleTangent = {0.f, 1.f};
+        if (!firstCurve)
+        {
+            const uint8_t prevVerb = ctx.verbs[v - 1];
+            const uint32_t prevK = k - verb_point_count(prevVerb);
+            const V2 prevTan1 = prevVerb == kVerbLine ? pts[prevK] - pts[prevK - 1] : cubic_tan1(pts + prevK - 1);
+            staleTangent = join_after_verb(ctx, v - 1, k - 1, prevTan1).tangent;
+        }
+        for (int i = 0; i < numChops; ++i, p += 3)
+            sink.span(p, staleTangent, wang_cubic_segments(p, path.matrix), polar_segments(cubic_tan0(p), cubic_tan1(p), psr), 1u, ctx.joinTypeFlags);
+    }
+    sink.span(p, join.tangent, wang_cubic_segments(p, path.matrix), polar_segments(cubic_tan0(p), cubic_tan1(p), psr), join.segments, join.flags);
+}
 
-    V2 firstTangent = {0.f, 1.f};
-    bool haveFirst = false;
+// One contour, walked in order by one thread.
+template <typename Sink>
+FE_HD void enumerate_contour(const rivecuda_path& path, const V2* pts, uint32_t pointCount, const uint8_t* verbs, uint32_t verbCount, Sink& sink)
+{
+    const ContourCtx ctx = make_contour_ctx(path, pts, pointCount, verbs, verbCount);
     uint32_t k = 1;
     for (uint32_t v = 0; v < verbCount; ++v)
     {
-        const uint8_t verb = verbs[v];
-        if (verb != kVerbLine && verb != kVerbCubic)
-            continue;
-        const bool finalVerb = v + 1 == verbCount;
-        const bool joins = shape.closed || !finalVerb;
-        const uint32_t kEnd = verb == kVerbLine ? k : k + 2; // index of this verb's last point
-        V2 tan0, tan1;
-        if (verb == kVerbLine)
-        {
-            tan0 = tan1 = pts[k] - pts[k - 1];
-        }
-        else
-        {
-            tan0 = cubic_tan0(pts + k - 1);
-            tan1 = cubic_tan1(pts + k - 1);
-        }
-        if (!haveFirst)
-        {
-            firstTangent = tan0;
-            haveFirst = true;
-        }
-        // The join after this verb.
-        V2 thisJoinTangent;
-        uint32_t thisJoinSegments, thisJoinFlags = joinTypeFlags;
-        if (joins)
-        {
-            if (roundJoin)
-            {
-                V2 nt = next_tangent(v, kEnd + 1, pts[kEnd]);
-                if (!has_next_curve(v) && same_bits(movePt, pts[kEnd]))
-                    nt = firstTangent;
-                thisJoinTangent = nt;
-                thisJoinSegments = polar_segments(tan1, nt, psr);
-            }
-            else
-            {
-                thisJoinTangent = find_join_tangent(pts, pointCount, kEnd, shape.closed);
-                thisJoinSegments = kMiterOrBevelJoinSegments;
-            }
-        }
-        else
-        {
-            thisJoinTangent = -find_ending_tangent(pts, pointCount);
-            thisJoinFlags = capFlags;
-            thisJoinSegments = capSegments;
-        }
-
-        if (verb == kVerbLine)
-        {
-            joinTangent = thisJoinTangent;
-            joinSegments = thisJoinSegments;
-            joinTypeFlags = thisJoinFlags;
-            line_to_cubic(pts[k - 1], pts[k], c);
-            if (needsFirstCap)
-            {
-                push_cap_before(c);
-                needsFirstCap = false;
-            }
-            sink.span(c, joinTangent, 1u, 1u, joinSegments, joinTypeFlags);
-            k += 1;
-        }
-        else
-        {
-            const V2* p = pts + k - 1;
-            V2 chopped[16];
-            float t[2] = {0.f, 0.f};
-            bool areCusps = false;
-            int numChops = find_cubic_convex_180_chops(p, t, &areCusps);
-            if (numChops != 0)
-            {
-                if (areCusps)
-                {
-                    chop_cubic_around_cusps(p, chopped, t, numChops, path.matrix_max_scale);
-                    numChops *= 2;
-                }
-                else if (numChops == 2)
-                {
-                    chop_cubic_at(p, chopped, t[0], t[1]);
-                }
-                else
-                {
-                    chop_cubic_at(p, chopped, t[0]);
-                }
-                p = chopped;
-            }
-            if (needsFirstCap)
-            {
-                push_cap_before(p);
-                needsFirstCap = false;
-            }
-            // Chops before the final one carry the previous verb's join tangent and no join.
-            for (int i = 0; i < numChops; ++i, p += 3)
-                sink.span(p, joinTangent, wang_cubic_segments(p, path.matrix), polar_segments(cubic_tan0(p), cubic_tan1(p), psr), 1u, joinTypeFlags);
-            joinTangent = thisJoinTangent;
-            joinSegments = thisJoinSegments;
-            joinTypeFlags = thisJoinFlags;
-            sink.span(p, joinTangent, wang_cubic_segments(p, path.matrix), polar_segments(cubic_tan0(p), cubic_tan1(p), psr), joinSegments, joinTypeFlags);
-            k += 3;
-        }
+        emit_item(ctx, v, k, sink);
+        k += verb_point_count(verbs[v]);
     }
-
-    if (needsFirstCap)
-    {
-        // An empty contour: both caps on p0 (draw.cpp:2308-2322).
-        const V2 p0 = pts[0], left = {p0.x - 1.f, p0.y}, right = {p0.x + 1.f, p0.y};
-        const V2 a[4] = {p0, right, right, right}, b[4] = {p0, left, left, left};
-        push_cap_before(a);
-        push_cap_before(b);
-    }
-    else if (shape.closed)
-    {
-        const V2 lastPt = pts[pointCount - 1];
-        if (!same_bits(lastPt, movePt))
-        {
-            line_to_cubic(lastPt, movePt, c);
-            if (roundJoin)
-            {
-                joinTangent = firstTangent;
-                joinSegments = polar_segments(movePt - lastPt, firstTangent, psr);
-            }
-            else
-            {
-                joinTangent = find_starting_tangent(pts, pointCount);
-                joinSegments = kMiterOrBevelJoinSegments;
-            }
-            sink.span(c, joinTangent, 1u, 1u, joinSegments, joinTypeFlags);
-        }
-    }
+    emit_item(ctx, verbCount, k, sink);
 }
 
 // Iterates a path's contours. Visitor: void contour(const V2* pts, uint32_t pointCount,

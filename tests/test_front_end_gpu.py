@@ -118,3 +118,24 @@ def test_cpp_path_renderer_draws_the_same_frame(built, scene, golden):
                               stdout=subprocess.DEVNULL, timeout=300)
         px = np.fromfile(out, dtype=np.uint8)
     assert px.size == want.size and np.array_equal(px.reshape(want.shape), want)
+
+
+def test_front_end_refuses_what_one_flush_cannot_hold(built):
+    """Error behaviour: more paths / contours / tessellation vertices than one logical flush admits
+    (RenderContext::LogicalFlush::pushDraws, render_context.cpp:528-536) is an error with a
+    message, not a truncated frame; bad arguments likewise."""
+    import ctypes
+    from path_fuzz import random_paths
+    from rive_runtime_b200 import abi, front_end as F, replay as R
+    lib = abi.load()
+    dump, _ = random_paths(5, 200)
+    big = F.PathDump(np.tile(dump.paths, 200), dump.verbs, dump.points, True)  # 40 000 paths > 30 720 path ids
+    with R.Replayer(0) as rp:
+        with pytest.raises(RuntimeError, match="exceed one flush"):
+            F.run(rp, big, 3840, 2160)
+        res = F.FrontEndResult()
+        assert lib.rivecuda_front_end_paths(rp.ctx, None, 1, None, 1, None, 1, 0, 0, ctypes.byref(res)) != 0
+        assert b"bad arguments" in lib.rivecuda_last_error()
+        # ... and the context is still usable afterwards.
+        ok = F.run(rp, dump, 3840, 2160)
+        assert ok.path_count > 1
