@@ -705,9 +705,8 @@ FE_HD Box map_bounding_box(const float* m, const V2* pts, uint32_t n)
 
 // PathDraw::Make's frame cull (draw.cpp:439-509; RenderContext::isOutsideCurrentFrame,
 // render_context.cpp:445-454): the mapped bounds, outset for strokes, rounded out to pixels.
-FE_HD bool is_outside_frame(const rivecuda_path& path, const V2* pts, uint32_t pointCount, uint32_t frameWidth, uint32_t frameHeight)
+FE_HD bool is_outside_frame(const rivecuda_path& path, Box box, uint32_t frameWidth, uint32_t frameHeight)
 {
-    Box box = map_bounding_box(path.matrix, pts, pointCount);
     if (path.stroke != 0)
     {
         float outset = path.stroke_radius;
@@ -723,6 +722,11 @@ FE_HD bool is_outside_frame(const rivecuda_path& path, const V2* pts, uint32_t p
     const int32_t l = static_cast<int32_t>(floorf(box.l)), t = static_cast<int32_t>(floorf(box.t));
     const int32_t r = static_cast<int32_t>(ceilf(box.r)), b = static_cast<int32_t>(ceilf(box.b));
     return l >= static_cast<int32_t>(frameWidth) || t >= static_cast<int32_t>(frameHeight) || r <= 0 || b <= 0 || l >= r || t >= b;
+}
+
+FE_HD bool is_outside_frame(const rivecuda_path& path, const V2* pts, uint32_t pointCount, uint32_t frameWidth, uint32_t frameHeight)
+{
+    return is_outside_frame(path, map_bounding_box(path.matrix, pts, pointCount), frameWidth, frameHeight);
 }
 
 FE_HD uint32_t path_point_count(const rivecuda_path& path, const uint8_t* verbs)
@@ -850,6 +854,26 @@ template <bool EMIT> struct PlaceSink
 
 constexpr uint32_t kPaintTypeSolidColor = 1, kPaintFlagNonZeroFill = 0x100, kPaintFlagEvenOddFill = 0x200; // constants.glsl
 
+// pushPath: PathData / PaintData / PaintAuxData (gpu.cpp:859-1063) for a solid colour.
+FE_HD void write_path_records(const rivecuda_path& path, uint32_t pathID, const FrontEndOut& out)
+{
+    const bool isStroke = path.stroke != 0;
+    uint32_t w[16] = {};
+    for (int i = 0; i < 6; ++i)
+        w[i] = bits(path.matrix[i]);
+    w[6] = isStroke ? bits(path.stroke_radius) : 0u; // 0 => fill
+    store_words16(out.pathData + static_cast<size_t>(pathID) * 16, w);
+    // PaintData: SOLID_COLOR_PAINT_TYPE | fill-rule flag; colour swizzled ARGB -> RGBA bytes.
+    const uint32_t argb = path.color;
+    const uint32_t rgba = ((argb >> 16) & 0xffu) | (argb & 0xff00u) | ((argb & 0xffu) << 16) | (argb & 0xff000000u);
+    out.paintData[static_cast<size_t>(pathID) * 2 + 0] = kPaintTypeSolidColor | (isStroke ? 0u : path.fill_rule == 1u ? kPaintFlagEvenOddFill : kPaintFlagNonZeroFill);
+    out.paintData[static_cast<size_t>(pathID) * 2 + 1] = rgba;
+    uint32_t aux[16] = {};
+    store_words16(out.paintAux + static_cast<size_t>(pathID) * 32 + 16, aux);
+    aux[12] = aux[13] = bits(1.f); // ClipRectInverseMatrix::WideOpen translate; inverseFwidth 0
+    store_words16(out.paintAux + static_cast<size_t>(pathID) * 32, aux);
+}
+
 // Passes 2 and 3 for one path. prefix: the exclusive scan of PathTotals up to this path;
 // ownTessVertices: this path's PathTotals::tessVertices. Returns the number of spans.
 template <bool EMIT>
@@ -901,23 +925,7 @@ FE_HD uint32_t place_path(const rivecuda_path& path, const V2* points, const uin
         }
     });
     if (EMIT)
-    {
-        // pushPath: PathData / PaintData / PaintAuxData (gpu.cpp:859-1063) for a solid colour.
-        uint32_t w[16] = {};
-        for (int i = 0; i < 6; ++i)
-            w[i] = bits(path.matrix[i]);
-        w[6] = isStroke ? bits(path.stroke_radius) : 0u; // 0 => fill
-        store_words16(out.pathData + static_cast<size_t>(pathID) * 16, w);
-        // PaintData: SOLID_COLOR_PAINT_TYPE | fill-rule flag; colour swizzled ARGB -> RGBA bytes.
-        const uint32_t argb = path.color;
-        const uint32_t rgba = ((argb >> 16) & 0xffu) | (argb & 0xff00u) | ((argb & 0xffu) << 16) | (argb & 0xff000000u);
-        out.paintData[static_cast<size_t>(pathID) * 2 + 0] = kPaintTypeSolidColor | (isStroke ? 0u : path.fill_rule == 1u ? kPaintFlagEvenOddFill : kPaintFlagNonZeroFill);
-        out.paintData[static_cast<size_t>(pathID) * 2 + 1] = rgba;
-        uint32_t aux[16] = {};
-        store_words16(out.paintAux + static_cast<size_t>(pathID) * 32 + 16, aux);
-        aux[12] = aux[13] = bits(1.f); // ClipRectInverseMatrix::WideOpen translate; inverseFwidth 0
-        store_words16(out.paintAux + static_cast<size_t>(pathID) * 32, aux);
-    }
+        write_path_records(path, pathID, out);
     return sink.spanCount;
 }
 

@@ -18,8 +18,10 @@
  *   pushPath (PathData/PaintData/        render_context.cpp:3037, gpu.cpp:859-1063
  *     PaintAuxData::set)
  *
- * Here: three thread-per-path passes separated by exclusive scans (warp-shuffle scans inside a
- * block scan) -- count vertices / contours -> scan -> count spans -> scan -> emit -- that write
+ * Here: three warp-per-path passes separated by exclusive scans (warp-shuffle scans inside a
+ * block scan) -- count vertices / contours -> scan -> count spans -> scan -> emit --; inside a
+ * path the lanes take one verb each and warp scans stand in for the reference's running offsets.
+ * The passes write
  * the reference's exact byte layout straight into the device copies of the flush's span /
  * contour / path / paint / paintAux buffers. The per-contour arithmetic lives in
  * front_end_core.h (shared with a host build the CPU test-suite checks against the reference's
@@ -42,21 +44,193 @@ using fe::FrontEndOut;
 using fe::PathTotals;
 using fe::V2;
 
-__global__ void __launch_bounds__(128) front_end_count_kernel(const rivecuda_path* __restrict__ paths,
-                                                              uint32_t pathCount,
-                                                              const V2* __restrict__ points,
-                                                              const uint8_t* __restrict__ verbs,
-                                                              uint32_t frameWidth,
-                                                              uint32_t frameHeight,
-                                                              PathTotals* __restrict__ totals,
-                                                              uint32_t* __restrict__ ownTessVertices)
+// ---- warp-per-path execution of the per-item core (front_end_core.h) -------------------------
+// One warp owns one path. Inside a contour the lanes take one item each (a verb, or the tail);
+// everything sequential in the reference -- point offsets, vertex locations, span indices -- is
+// an exclusive scan over the items, so a path of thousands of verbs costs as many rounds of 32
+// as it has verbs / 32 instead of one thread walking it five times. All control flow below is
+// warp-uniform (the path, its contours and the chunk loops are the same for the 32 lanes); the
+// shuffles use the full mask.
+constexpr uint32_t kFullMask = 0xffffffffu;
+constexpr int kWarpsPerBlock = 4;
+
+__device__ __forceinline__ uint32_t warp_exclusive_scan(uint32_t v, int lane, uint32_t* total)
 {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1)
+    {
+        const uint32_t t = __shfl_up_sync(kFullMask, incl, o);
+        if (lane >= o)
+            incl += t;
+    }
+    *total = __shfl_sync(kFullMask, incl, 31);
+    return incl - v;
+}
+
+__device__ __forceinline__ uint32_t warp_sum(uint32_t v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+        v += __shfl_xor_sync(kFullMask, v, o);
+    return v;
+}
+
+// First move verb at or after `from` (or `count`).
+__device__ __forceinline__ uint32_t warp_find_move(const uint8_t* __restrict__ vb, uint32_t from, uint32_t count, int lane)
+{
+    for (uint32_t base = from; base < count; base += 32)
+    {
+        const uint32_t v = base + lane;
+        const uint32_t hit = __ballot_sync(kFullMask, v < count && vb[v] == fe::kVerbMove);
+        if (hit != 0u)
+            return base + static_cast<uint32_t>(__ffs(hit)) - 1u;
+    }
+    return count;
+}
+
+// Points of the verbs [0, count) of a contour (after its move).
+__device__ __forceinline__ uint32_t warp_point_count(const uint8_t* __restrict__ vb, uint32_t count, int lane)
+{
+    uint32_t n = 0;
+    for (uint32_t base = 0; base < count; base += 32)
+        n += (base + lane < count) ? fe::verb_point_count(vb[base + lane]) : 0u;
+    return warp_sum(n);
+}
+
+// Calls f(v, k, valid) for the items of a contour, 32 at a time, on every lane (valid tells
+// whether the lane holds an item), so that f may use warp collectives.
+template <typename F> __device__ __forceinline__ void warp_for_each_item(const fe::ContourCtx& ctx, int lane, F&& f)
+{
+    uint32_t kCarry = 1;
+    for (uint32_t base = 0; base <= ctx.verbCount; base += 32)
+    {
+        const uint32_t v = base + lane;
+        const uint32_t np = v < ctx.verbCount ? fe::verb_point_count(ctx.verbs[v]) : 0u;
+        uint32_t total;
+        const uint32_t k = kCarry + warp_exclusive_scan(np, lane, &total);
+        f(v, k, v <= ctx.verbCount);
+        kCarry += total;
+    }
+}
+
+__device__ __forceinline__ uint32_t item_vertices(const fe::ContourCtx& ctx, uint32_t v, uint32_t k, bool valid)
+{
+    fe::VertexCountSink sink;
+    if (valid)
+        fe::emit_item(ctx, v, k, sink);
+    return sink.vertices;
+}
+
+// Mat2D::mapBoundingBox over the path's points with the lanes striding the points: min / max
+// skip NaNs, so the partial results are never NaN and combine exactly (fe::map_bounding_box).
+__device__ bool warp_is_outside_frame(const rivecuda_path& path, const V2* __restrict__ pts, uint32_t pointCount, uint32_t frameWidth, uint32_t frameHeight, int lane)
+{
+    const float* m = path.matrix;
+    const float inf = __uint_as_float(0x7f800000u);
+    float l = inf, t = inf, r = -inf, b = -inf;
+    const bool scaleTranslate = m[1] == 0.f && m[2] == 0.f;
+    for (uint32_t i = lane; i < pointCount; i += 32)
+    {
+        const V2 p = pts[i];
+        float x, y;
+        if (scaleTranslate)
+        {
+            x = m[0] * p.x;
+            y = m[3] * p.y;
+        }
+        else
+        {
+            const float sx = m[2] * p.y, sy = m[1] * p.x;
+            x = m[0] * p.x + sx;
+            y = m[3] * p.y + sy;
+        }
+        l = fe::simd_min(x, l), t = fe::simd_min(y, t), r = fe::simd_max(x, r), b = fe::simd_max(y, b);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+    {
+        l = fminf(l, __shfl_xor_sync(kFullMask, l, o));
+        t = fminf(t, __shfl_xor_sync(kFullMask, t, o));
+        r = fmaxf(r, __shfl_xor_sync(kFullMask, r, o));
+        b = fmaxf(b, __shfl_xor_sync(kFullMask, b, o));
+    }
+    fe::Box box;
+    if (!(r - l >= 0.f && b - t >= 0.f))
+        box = {0.f, 0.f, 0.f, 0.f};
+    else
+        box = {l + m[4], t + m[5], r + m[4], b + m[5]};
+    return fe::is_outside_frame(path, box, frameWidth, frameHeight);
+}
+
+// Pass 1: tessellation vertices / contours per path.
+__global__ void __launch_bounds__(kWarpsPerBlock * 32) front_end_count_kernel(const rivecuda_path* __restrict__ paths,
+                                                                               uint32_t pathCount,
+                                                                               const V2* __restrict__ points,
+                                                                               const uint8_t* __restrict__ verbs,
+                                                                               uint32_t frameWidth,
+                                                                               uint32_t frameHeight,
+                                                                               uint32_t pointCount,
+                                                                               uint32_t* __restrict__ badPathFlag,
+                                                                               PathTotals* __restrict__ totals,
+                                                                               uint32_t* __restrict__ ownTessVertices)
+{
+    const int lane = threadIdx.x & 31;
+    const uint32_t i = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
     if (i >= pathCount)
         return;
-    const PathTotals t = fe::count_path(paths[i], points, verbs, frameWidth, frameHeight);
-    totals[i] = t;
-    ownTessVertices[i] = t.tessVertices; // survives the in-place exclusive scan of totals
+    const rivecuda_path path = paths[i];
+    const V2* pt = points + path.first_point;
+    const uint8_t* vb = verbs + path.first_verb;
+    uint32_t vertices = 0, contours = 0;
+    bool culled = false;
+    {
+        uint32_t n = 0;
+        for (uint32_t base = 0; base < path.verb_count; base += 32)
+        {
+            const uint8_t verb = base + lane < path.verb_count ? vb[base + lane] : fe::kVerbClose;
+            n += verb == fe::kVerbMove ? 1u : fe::verb_point_count(verb);
+        }
+        n = warp_sum(n);
+        if (static_cast<uint64_t>(path.first_point) + n > pointCount)
+        {
+            // The verbs ask for points beyond the caller's array: touch nothing, report it.
+            if (lane == 0)
+                atomicOr(badPathFlag, 1u);
+            culled = true;
+        }
+        else if (frameWidth != 0u)
+        {
+            culled = warp_is_outside_frame(path, pt, n, frameWidth, frameHeight, lane);
+        }
+    }
+    if (!culled)
+    {
+        uint32_t v = warp_find_move(vb, 0, path.verb_count, lane);
+        while (v < path.verb_count)
+        {
+            const uint32_t next = warp_find_move(vb, v + 1, path.verb_count, lane);
+            const uint32_t nv = next - v - 1;
+            const uint32_t np = 1u + warp_point_count(vb + v + 1, nv, lane);
+            const fe::ContourCtx ctx = fe::make_contour_ctx(path, pt, np, vb + v + 1, nv);
+            uint32_t mine = 0;
+            warp_for_each_item(ctx, lane, [&](uint32_t item, uint32_t k, bool valid) { mine += item_vertices(ctx, item, k, valid); });
+            vertices += fe::pad_to_patch(warp_sum(mine));
+            ++contours;
+            pt += np;
+            v = next;
+        }
+    }
+    if (lane == 0)
+    {
+        PathTotals t;
+        t.tessVertices = path.stroke != 0 ? vertices : vertices * 2u; // draw.cpp:1387-1390
+        t.contours = vertices != 0u ? contours : 0u;
+        t.paths = vertices != 0u ? 1u : 0u;
+        t.spans = 0u;
+        totals[i] = t;
+        ownTessVertices[i] = t.tessVertices; // survives the in-place exclusive scan of totals
+    }
 }
 
 // Exclusive scan of one uint32 field (stride 4 words) over all paths, in place, by one block:
@@ -113,22 +287,140 @@ __global__ void __launch_bounds__(1024) front_end_scan_kernel(uint32_t* __restri
 
 // Passes 2 (EMIT false: spans per path) and 3 (EMIT true: write everything).
 template <bool EMIT>
-__global__ void __launch_bounds__(128) front_end_place_kernel(const rivecuda_path* __restrict__ paths,
-                                                              uint32_t pathCount,
-                                                              const V2* __restrict__ points,
-                                                              const uint8_t* __restrict__ verbs,
-                                                              PathTotals* __restrict__ totals, // exclusive-scanned
-                                                              const uint32_t* __restrict__ ownTessVertices,
-                                                              FrontEndOut out)
+__global__ void __launch_bounds__(kWarpsPerBlock * 32) front_end_place_kernel(const rivecuda_path* __restrict__ paths,
+                                                                               uint32_t pathCount,
+                                                                               const V2* __restrict__ points,
+                                                                               const uint8_t* __restrict__ verbs,
+                                                                               PathTotals* __restrict__ totals, // exclusive-scanned
+                                                                               const uint32_t* __restrict__ ownTessVertices,
+                                                                               FrontEndOut out)
 {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const uint32_t i = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
     if (i >= pathCount)
         return;
+    const uint32_t own = ownTessVertices[i];
+    if (own == 0u)
+    {
+        if (!EMIT && lane == 0)
+            totals[i].spans = 0u;
+        return;
+    }
     const rivecuda_path path = paths[i];
     const PathTotals prefix = totals[i];
-    const uint32_t spans = fe::place_path<EMIT>(path, points, verbs, prefix, ownTessVertices[i], out);
+    const bool isStroke = path.stroke != 0;
+    const V2* pt = points + path.first_point;
+    const uint8_t* vb = verbs + path.first_verb;
+    const uint32_t pathID = prefix.paths + 1u; // 1-based; 0 is the flush's reserved record
+    uint32_t contourID = prefix.contours;      // 1-based: incremented before use
+    // The midpoint-fan region starts after one patch of padding (draw.cpp:1899-1947).
+    const uint32_t location = fe::kPatchSpan + prefix.tessVertices;
+    uint32_t forwardLoc = isStroke ? location : location + own / 2u, mirroredLoc = forwardLoc;
+    uint32_t spanCarry = 0; // spans of this path so far
+
+    uint32_t v = warp_find_move(vb, 0, path.verb_count, lane);
+    while (v < path.verb_count)
+    {
+        const uint32_t next = warp_find_move(vb, v + 1, path.verb_count, lane);
+        const uint32_t nv = next - v - 1;
+        const uint32_t np = 1u + warp_point_count(vb + v + 1, nv, lane);
+        const fe::ContourCtx ctx = fe::make_contour_ctx(path, pt, np, vb + v + 1, nv);
+        // The contour's vertex count decides the padding its first span carries.
+        uint32_t mine = 0;
+        warp_for_each_item(ctx, lane, [&](uint32_t item, uint32_t k, bool valid) { mine += item_vertices(ctx, item, k, valid); });
+        const uint32_t contourVertices = warp_sum(mine);
+        const uint32_t padding = fe::pad_to_patch(contourVertices) - contourVertices;
+        ++contourID;
+        uint32_t vertexCarry = 0;
+        warp_for_each_item(ctx, lane, [&](uint32_t item, uint32_t k, bool valid) {
+            const uint32_t vertices = item_vertices(ctx, item, k, valid);
+            uint32_t chunkVertices;
+            const uint32_t before = vertexCarry + warp_exclusive_scan(vertices, lane, &chunkVertices);
+            vertexCarry += chunkVertices;
+            // The first span of the contour carries the padding; everything after it is shifted.
+            const uint32_t offset = before + (before != 0u ? padding : 0u);
+            fe::PlaceSink<false> counter;
+            counter.doubleSided = !isStroke;
+            counter.forwardLoc = forwardLoc + offset;
+            counter.mirroredLoc = mirroredLoc - offset;
+            counter.nextPadding = before == 0u ? padding : 0u;
+            if (valid && vertices != 0u)
+                fe::emit_item(ctx, item, k, counter);
+            uint32_t chunkSpans;
+            const uint32_t spanOffset = warp_exclusive_scan(counter.spanCount, lane, &chunkSpans);
+            if (EMIT && valid && vertices != 0u)
+            {
+                fe::PlaceSink<true> sink;
+                sink.out = out;
+                sink.doubleSided = !isStroke;
+                sink.contourID = contourID;
+                sink.spanIndex = prefix.spans + spanCarry + spanOffset;
+                sink.forwardLoc = forwardLoc + offset;
+                sink.mirroredLoc = mirroredLoc - offset;
+                sink.nextPadding = before == 0u ? padding : 0u;
+                fe::emit_item(ctx, item, k, sink);
+            }
+            spanCarry += chunkSpans;
+        });
+        if (EMIT && lane == 0)
+        {
+            uint32_t mx, my;
+            if (isStroke)
+            {
+                // LogicalFlush::pushContour: midpoint.x = closed ? 1 : 0 (render_context.cpp:3121-3126)
+                mx = __float_as_uint(ctx.closed ? 1.f : 0.f);
+                my = 0u;
+            }
+            else
+            {
+                // ContourInfo::midpoint = endpointsSum / preChopVerbCount (draw.cpp:945): a float sum
+                // in verb order, so one lane adds the end points up in that order.
+                V2 sum = {0.f, 0.f};
+                uint32_t n = 0, k = 1;
+                for (uint32_t w = 0; w < nv; ++w)
+                {
+                    const uint32_t c = fe::verb_point_count(ctx.verbs[w]);
+                    if (c != 0u)
+                    {
+                        sum = sum + pt[k + c - 1u];
+                        ++n;
+                    }
+                    k += c;
+                }
+                if (!fe::same_bits(pt[np - 1u], pt[0]))
+                {
+                    sum = sum + pt[0]; // the implicit closing line
+                    ++n;
+                }
+                if (n == 0u)
+                {
+                    mx = my = 0xffc00000u; // a move-only contour: 0 * inf, with the NaN encoding SSE produces
+                }
+                else
+                {
+                    const float inv = 1.f / static_cast<float>(n);
+                    mx = __float_as_uint(sum.x * inv);
+                    my = __float_as_uint(sum.y * inv);
+                }
+            }
+            // ContourData::vertexIndex0 = the forward location before the contour's first curve.
+            uint32_t* dst = out.contours + static_cast<size_t>(contourID - 1u) * 4;
+            dst[0] = mx, dst[1] = my, dst[2] = pathID, dst[3] = forwardLoc;
+        }
+        const uint32_t padded = contourVertices + padding;
+        forwardLoc += padded;
+        mirroredLoc -= padded;
+        pt += np;
+        v = next;
+    }
+    if (lane != 0)
+        return;
     if (!EMIT)
-        totals[i].spans = spans;
+    {
+        totals[i].spans = spanCarry;
+        return;
+    }
+    fe::write_path_records(path, pathID, out);
 }
 
 __global__ void front_end_padding_kernel(uint32_t* __restrict__ spans, const uint32_t* __restrict__ sums, uint32_t* __restrict__ result)
@@ -156,6 +448,15 @@ int rivecuda_front_end_paths(rivecuda_ctx* ctx,
     RC_CUDA(cudaSetDevice(ctx->device));
     cudaStream_t stream = ctx->stream;
     memset(result, 0, sizeof(*result));
+    // Paths may share verbs / points; what the output buffers must hold follows the verbs the
+    // paths reference, not the size of the arrays.
+    size_t referencedVerbs = 0;
+    for (uint32_t i = 0; i < path_count; ++i)
+    {
+        if (static_cast<uint64_t>(paths[i].first_verb) + paths[i].verb_count > verb_count || paths[i].first_point > point_count)
+            return set_error("rivecuda_front_end_paths: bad arguments (path %u references verbs / points outside the arrays)", i);
+        referencedVerbs += paths[i].verb_count;
+    }
 
     // Inputs -> device.
     const size_t pointBytes = static_cast<size_t>(point_count) * 8, verbBytes = verb_count, pathBytes = static_cast<size_t>(path_count) * sizeof(rivecuda_path);
@@ -170,7 +471,7 @@ int rivecuda_front_end_paths(rivecuda_ctx* ctx,
     rivecuda_path* dPaths = reinterpret_cast<rivecuda_path*>(base + pathOffset);
     PathTotals* dTotals = reinterpret_cast<PathTotals*>(base + totalsOffset);
     uint32_t* dOwn = reinterpret_cast<uint32_t*>(base + ownOffset);
-    uint32_t* dSums = reinterpret_cast<uint32_t*>(dTotals + path_count); // [0] verts [1] contours [2] paths [3] spans [4..5] padding result
+    uint32_t* dSums = reinterpret_cast<uint32_t*>(dTotals + path_count); // [0] verts [1] contours [2] paths [3] spans [4..5] padding result [6] bad-path flag
     if (path_count != 0)
     {
         RC_CUDA(cudaMemcpyAsync(dPoints, points_xy, pointBytes, cudaMemcpyHostToDevice, stream));
@@ -181,9 +482,9 @@ int rivecuda_front_end_paths(rivecuda_ctx* ctx,
     // The five buffers this front end fills, at the sizes the worst case needs (a stroked cubic
     // chops into at most 5 pieces; per contour two caps and one implicit closing line; plus one
     // extra span per wrapped row).
-    const size_t maxSpans = static_cast<size_t>(verb_count) * 8 + 2 * 2048 + 3;
+    const size_t maxSpans = referencedVerbs * 8 + 2 * 2048 + 3;
     const size_t need[RIVECUDA_BUFFER_KIND_COUNT] = {256, (static_cast<size_t>(path_count) + 1) * 64, (static_cast<size_t>(path_count) + 1) * 8,
-                                                    (static_cast<size_t>(path_count) + 1) * 128, static_cast<size_t>(verb_count + 1) * 16, 0, maxSpans * 64, 0, 0};
+                                                    (static_cast<size_t>(path_count) + 1) * 128, (referencedVerbs + 1) * 16, 0, maxSpans * 64, 0, 0};
     for (int kind = 0; kind < RIVECUDA_BUFFER_KIND_COUNT; ++kind)
     {
         if (need[kind] > ctx->rings[kind].capacity)
@@ -208,11 +509,12 @@ int rivecuda_front_end_paths(rivecuda_ctx* ctx,
     RC_CUDA(cudaMemsetAsync(out.paintData, 0, 8, stream));
     RC_CUDA(cudaMemsetAsync(out.paintAux, 0, 128, stream));
 
-    const uint32_t blocks = (path_count + 127) / 128;
+    RC_CUDA(cudaMemsetAsync(dSums + 6, 0, sizeof(uint32_t), stream)); // the count kernel's bad-path flag
+    const uint32_t blocks = (path_count + kWarpsPerBlock - 1) / kWarpsPerBlock;
     uint32_t* field = reinterpret_cast<uint32_t*>(dTotals);
     if (path_count != 0)
     {
-        front_end_count_kernel<<<blocks, 128, 0, stream>>>(dPaths, path_count, dPoints, dVerbs, frame_width, frame_height, dTotals, dOwn);
+        front_end_count_kernel<<<blocks, kWarpsPerBlock * 32, 0, stream>>>(dPaths, path_count, dPoints, dVerbs, frame_width, frame_height, point_count, dSums + 6, dTotals, dOwn);
         front_end_scan_kernel<<<1, 1024, 0, stream>>>(field + 0, path_count, dSums + 0);
         front_end_scan_kernel<<<1, 1024, 0, stream>>>(field + 1, path_count, dSums + 1);
         front_end_scan_kernel<<<1, 1024, 0, stream>>>(field + 2, path_count, dSums + 2);
@@ -222,25 +524,27 @@ int rivecuda_front_end_paths(rivecuda_ctx* ctx,
         RC_CUDA(cudaMemsetAsync(dSums, 0, 16, stream));
     }
     front_end_padding_kernel<<<1, 1, 0, stream>>>(out.spans, dSums, dSums + 4);
-    RC_CUDA(cudaMemcpyAsync(ctx->pinnedTotals + 8, dSums, 6 * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+    RC_CUDA(cudaMemcpyAsync(ctx->pinnedTotals + 8, dSums, 7 * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
     RC_CUDA(cudaStreamSynchronize(stream)); // the span base (2 or 3 padding spans) and the totals
     out.spanBase = ctx->pinnedTotals[8 + 4];
-    if (path_count != 0)
-    {
-        front_end_place_kernel<false><<<blocks, 128, 0, stream>>>(dPaths, path_count, dPoints, dVerbs, dTotals, dOwn, out);
-        front_end_scan_kernel<<<1, 1024, 0, stream>>>(field + 3, path_count, dSums + 3);
-        front_end_place_kernel<true><<<blocks, 128, 0, stream>>>(dPaths, path_count, dPoints, dVerbs, dTotals, dOwn, out);
-    }
-    RC_CUDA(cudaGetLastError());
-    RC_CUDA(cudaMemcpyAsync(ctx->pinnedTotals + 8 + 3, dSums + 3, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
-    RC_CUDA(cudaStreamSynchronize(stream));
     const uint32_t* sums = ctx->pinnedTotals + 8;
+    if (sums[6] != 0u)
+        return set_error("rivecuda_front_end_paths: bad arguments (a path's verbs need more points than the point array holds)");
     // One flush holds what RenderContext::LogicalFlush::pushDraws admits (render_context.cpp:528-536):
     // path ids fit the fp16 id encoding, contour ids 16 bits, the tessellation texture 2048 rows.
     if (sums[2] > 30720u || sums[1] > 0xffffu || sums[5] > static_cast<uint32_t>(kTessWidth) * 2048u)
         return set_error("rivecuda_front_end_paths: %u paths / %u contours / %u tessellation vertices exceed one flush "
                          "(30720 / 65535 / 2048 x 2048); split the draw list as the reference starts a new logical flush",
                          sums[2], sums[1], sums[5]);
+    if (path_count != 0)
+    {
+        front_end_place_kernel<false><<<blocks, kWarpsPerBlock * 32, 0, stream>>>(dPaths, path_count, dPoints, dVerbs, dTotals, dOwn, out);
+        front_end_scan_kernel<<<1, 1024, 0, stream>>>(field + 3, path_count, dSums + 3);
+        front_end_place_kernel<true><<<blocks, kWarpsPerBlock * 32, 0, stream>>>(dPaths, path_count, dPoints, dVerbs, dTotals, dOwn, out);
+    }
+    RC_CUDA(cudaGetLastError());
+    RC_CUDA(cudaMemcpyAsync(ctx->pinnedTotals + 8 + 3, dSums + 3, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+    RC_CUDA(cudaStreamSynchronize(stream));
     result->midpoint_fan_tess_vertex_count = sums[0];
     result->contour_count = sums[1];
     result->path_count = sums[2] + 1; // + the reserved record 0

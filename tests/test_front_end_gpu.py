@@ -136,6 +136,14 @@ def test_front_end_refuses_what_one_flush_cannot_hold(built):
         res = F.FrontEndResult()
         assert lib.rivecuda_front_end_paths(rp.ctx, None, 1, None, 1, None, 1, 0, 0, ctypes.byref(res)) != 0
         assert b"bad arguments" in lib.rivecuda_last_error()
+        # Verbs that need more points than the caller passed: caught on the device, nothing is read.
+        short = F.PathDump(dump.paths, dump.verbs, dump.points[:-1], True)
+        with pytest.raises(RuntimeError, match="more points than the point array holds"):
+            F.run(rp, short, 3840, 2160)
+        outside = dump.paths.copy()
+        outside["first_verb"][3] = dump.verbs.size
+        with pytest.raises(RuntimeError, match="outside the arrays"):
+            F.run(rp, F.PathDump(outside, dump.verbs, dump.points, True), 3840, 2160)
         # ... and the context is still usable afterwards.
         ok = F.run(rp, dump, 3840, 2160)
         assert ok.path_count > 1
