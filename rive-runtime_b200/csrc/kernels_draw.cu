@@ -106,6 +106,7 @@ struct FlushParams
     // Raster target / tiling.
     uint32_t* target;
     uint32_t targetWidth, targetHeight;
+    uint32_t cullPatches; // the update bounds are a part of the target (band sharding): drop whole patches early
     int32_t boundsL, boundsT, boundsR, boundsB;
     int32_t tileX0, tileY0; // first tile (in tile units)
     uint32_t tilesX, tilesY;
@@ -818,6 +819,73 @@ __device__ __forceinline__ uint32_t find_batch(const DeviceBatch* __restrict__ b
     return lo;
 }
 
+// Screen-band sharding narrows the update bounds: a patch whose every possible vertex lies outside
+// them produces no triangle that survives binning, so setup_patches_kernel drops it before its
+// vertices are shaded. Out of line: it only runs in band mode and must not cost the common path
+// registers. Warp-uniform result.
+struct PatchCullArgs
+{
+    const uint4* tess;
+    uint32_t tessVertexCount;
+    const uint4* contourBuffer;
+    const uint4* pathBuffer;
+    int32_t boundsL, boundsT, boundsR, boundsB;
+};
+__device__ __noinline__ static bool patch_outside_bounds(PatchCullArgs P, uint4 firstVertex, int instanceID, int span, int lane)
+{
+    auto tess_fetch = [&](const PatchCullArgs& a, int idx) {
+        return (idx < 0 || static_cast<uint32_t>(idx) >= a.tessVertexCount) ? make_uint4(0, 0, 0, 0) : __ldg(a.tess + idx);
+    };
+    // Candidates: the instance's tessellation vertices and their
+    // two neighbours, the contour's first vertex (closed contours wrap to it) and, for
+    // fills, the fan midpoint; grown by the stroke's reach (miter limit 4, plus slack) and
+    // 4 px for the anti-aliasing ramps. Feathered paths are left alone.
+    const uint32_t contourID = max(firstVertex.w & kContourIDMask, 1u);
+    const uint4 contourData = __ldg(P.contourBuffer + (contourID - 1u));
+    const uint32_t pathID = contourData.z & 0xffffu;
+    const uint4 m4 = __ldg(P.pathBuffer + pathID * 4u);
+    const uint4 pd = __ldg(P.pathBuffer + pathID * 4u + 1u);
+    const m22 M = {__uint_as_float(m4.x), __uint_as_float(m4.y), __uint_as_float(m4.z), __uint_as_float(m4.w)};
+    const float strokeRadius = __uint_as_float(pd.z), featherRadius = __uint_as_float(pd.w);
+    f2 p = mk2(0.f, 0.f);
+    bool have = false;
+    if (lane < span + 2)
+    {
+        const uint4 tv = tess_fetch(P, instanceID * span - 1 + lane);
+        p = mk2(__uint_as_float(tv.x), __uint_as_float(tv.y));
+        have = true;
+    }
+    else if (lane == 31)
+    {
+        const uint4 tv = tess_fetch(P, static_cast<int>(contourData.w));
+        p = mk2(__uint_as_float(tv.x), __uint_as_float(tv.y));
+        have = true;
+    }
+    else if (lane == 30 && strokeRadius == 0.f)
+    {
+        p = mk2(__uint_as_float(contourData.x), __uint_as_float(contourData.y));
+        have = true;
+    }
+    const f2 q = mul(M, p) + mk2(__uint_as_float(pd.x), __uint_as_float(pd.y));
+    const bool finite = !have || (fabsf(q.x) < 1e30f && fabsf(q.y) < 1e30f); // false for NaN / inf
+    const float inf = __int_as_float(0x7f800000);
+    float x0 = have ? q.x : inf, x1 = have ? q.x : -inf, y0 = have ? q.y : inf, y1 = have ? q.y : -inf;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+    {
+        x0 = fminf(x0, __shfl_xor_sync(0xffffffffu, x0, o));
+        x1 = fmaxf(x1, __shfl_xor_sync(0xffffffffu, x1, o));
+        y0 = fminf(y0, __shfl_xor_sync(0xffffffffu, y0, o));
+        y1 = fmaxf(y1, __shfl_xor_sync(0xffffffffu, y1, o));
+    }
+    const bool allFinite = __all_sync(0xffffffffu, finite);
+    const float reach = strokeRadius * 5.f;
+    const float growX = (fabsf(M.xx) + fabsf(M.yx)) * reach + 4.f, growY = (fabsf(M.xy) + fabsf(M.yy)) * reach + 4.f;
+    const bool outside = x1 + growX < static_cast<float>(P.boundsL) || x0 - growX > static_cast<float>(P.boundsR) ||
+                         y1 + growY < static_cast<float>(P.boundsT) || y0 - growY > static_cast<float>(P.boundsB);
+    return allFinite && featherRadius == 0.f && outside;
+}
+
 // One warp per patch instance.
 __global__ void __launch_bounds__(kSetupWarpsPerBlock * 32, 2048 / (kSetupWarpsPerBlock * 32) / 2) setup_patches_kernel(FlushParams P,
                                                                                 const DeviceBatch* __restrict__ batches,
@@ -864,7 +932,15 @@ __global__ void __launch_bounds__(kSetupWarpsPerBlock * 32, 2048 / (kSetupWarpsP
         // are padded to whole patches, forward and mirrored copies are allocated apart),
         // so one flag says which reading of the patch vertex table applies, and with it
         // which patch vertices shade identically.
-        const bool mirrored = (tess_fetch(P, instanceID * static_cast<int>(span)).w & kMirroredContourFlag) != 0u;
+        const uint4 firstVertex = tess_fetch(P, instanceID * static_cast<int>(span));
+        const bool mirrored = (firstVertex.w & kMirroredContourFlag) != 0u;
+        if (P.cullPatches != 0u && !enableFeather && patch_outside_bounds(PatchCullArgs{P.tess, P.tessVertexCount, P.contourBuffer, P.pathBuffer, P.boundsL, P.boundsT, P.boundsR, P.boundsB},
+                                                                                    firstVertex, instanceID, static_cast<int>(span), lane))
+        {
+            for (uint32_t t = lane; t < b.trisPerElement; t += 32)
+                bins.binCount[b.firstTriangle + inst * b.trisPerElement + t] = 0;
+            continue;
+        }
         const PatchDedup* __restrict__ dedup = P.patchDedup + patchType * 2 + (mirrored ? 1 : 0);
         const uint32_t uniqueCount = __ldg(&dedup->uniqueCount);
         __syncwarp();
@@ -1457,6 +1533,7 @@ int launch_draw_list(rivecuda_ctx* ctx, const rivecuda_flush_desc& desc, const r
     P.boundsT = std::max(desc.update_bounds[1], 0);
     P.boundsR = std::min<int32_t>(desc.update_bounds[2], target->width);
     P.boundsB = std::min<int32_t>(desc.update_bounds[3], target->height);
+    P.cullPatches = (P.boundsL > 0 || P.boundsT > 0 || P.boundsR < static_cast<int32_t>(target->width) || P.boundsB < static_cast<int32_t>(target->height)) ? 1u : 0u;
     P.loadAction = desc.color_load_action;
     P.clearColorPremulRGBA = premul_clear_color(desc.color_clear_value);
     P.ditherScale = desc.dither_mode == 0 ? 0.f : 1.f / 256.f;

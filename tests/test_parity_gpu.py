@@ -124,6 +124,36 @@ def test_c2_full_size_parity_and_properties(libs):
     assert np.array_equal(banded, got.frames[0])
 
 
+@pytest.mark.parametrize("name", ["s1", "c3", "c1", "strokes_round", "trickycubicstrokes", "feather_strokes", "img", "riv_off_road_car"])
+def test_band_decomposition_is_bit_identical(libs, name):
+    """Screen-band sharding on strokes, joins, caps, feathers, clips, images and a real
+    .riv frame: every flush rendered as 5 bands -- with whole patches outside a band dropped before
+    their vertices are shaded -- must composite to exactly the single-pass frame."""
+    replay, T, _ = libs
+    from rive_runtime_b200 import sharding
+    recs = T.parse(os.path.join(GOLDEN, name + ".rvct.xz"))
+    want = replay.replay(recs).frames[-1]
+    result = replay.ReplayResult()
+    target_id = None
+    with replay.Replayer(0) as rp:
+        for r in recs:
+            if r.tag in (T.CREATE, T.DESTROY, T.TARGET_READ, T.TARGET_DESTROY):
+                continue
+            if r.tag == T.FLUSH:
+                fr = r.fields["flush"]
+                target_id = fr.target_id
+                pf = rp.prepare_flush(fr)
+                full = pf.desc
+                h = rp.target_shapes[fr.target_id][0]
+                for band_rank in range(5):
+                    pf.desc = sharding.restrict_to_band(full, sharding.band_for_rank(h, band_rank, 5))
+                    rp.flush(pf)
+                continue
+            rp.apply(r, result)
+        banded = rp.read_target(target_id)
+    assert np.array_equal(banded, want)
+
+
 def test_clear_only_and_preserve(libs):
     """Empty draw list: clear fills exactly the premultiplied clear colour inside the
     update bounds; preserveRenderTarget leaves pixels untouched."""
