@@ -446,7 +446,10 @@ int rivecuda_front_end_paths(rivecuda_ctx* ctx,
     if (ctx == nullptr || result == nullptr || (path_count != 0 && (points_xy == nullptr || verbs == nullptr || paths == nullptr)))
         return set_error("rivecuda_front_end_paths: bad arguments");
     RC_CUDA(cudaSetDevice(ctx->device));
-    cudaStream_t stream = ctx->stream;
+    // Like the uploads of mapped buffers, the front end runs on the upload stream: it fills fresh
+    // ring slots while the render stream may still be rasterising the previous frame, and the
+    // next flush waits for it through the same event (uploadsPending).
+    cudaStream_t stream = ctx->uploadStream;
     memset(result, 0, sizeof(*result));
     // Paths may share verbs / points; what the output buffers must hold follows the verbs the
     // paths reference, not the size of the arrays.
@@ -554,6 +557,7 @@ int rivecuda_front_end_paths(rivecuda_ctx* ctx,
     result->patch_count = sums[0] / fe::kPatchSpan;
     for (int kind : {RIVECUDA_BUFFER_PATH, RIVECUDA_BUFFER_PAINT, RIVECUDA_BUFFER_PAINT_AUX, RIVECUDA_BUFFER_CONTOUR, RIVECUDA_BUFFER_TESS_SPAN})
         ctx->rings[kind].submittedBytes = ctx->rings[kind].capacity;
+    ctx->uploadsPending = true;
     return 0;
 }
 
