@@ -886,7 +886,8 @@ __device__ __noinline__ static bool patch_outside_bounds(PatchCullArgs P, uint4 
     return allFinite && featherRadius == 0.f && outside;
 }
 
-// One warp per patch instance.
+// One warp per patch instance. CULL: the update bounds cover part of the target (band sharding).
+template <bool CULL>
 __global__ void __launch_bounds__(kSetupWarpsPerBlock * 32, 2048 / (kSetupWarpsPerBlock * 32) / 2) setup_patches_kernel(FlushParams P,
                                                                                 const DeviceBatch* __restrict__ batches,
                                                                                 uint32_t batchCount,
@@ -934,7 +935,7 @@ __global__ void __launch_bounds__(kSetupWarpsPerBlock * 32, 2048 / (kSetupWarpsP
         // which patch vertices shade identically.
         const uint4 firstVertex = tess_fetch(P, instanceID * static_cast<int>(span));
         const bool mirrored = (firstVertex.w & kMirroredContourFlag) != 0u;
-        if (P.cullPatches != 0u && !enableFeather && patch_outside_bounds(PatchCullArgs{P.tess, P.tessVertexCount, P.contourBuffer, P.pathBuffer, P.boundsL, P.boundsT, P.boundsR, P.boundsB},
+        if (CULL && !enableFeather && patch_outside_bounds(PatchCullArgs{P.tess, P.tessVertexCount, P.contourBuffer, P.pathBuffer, P.boundsL, P.boundsT, P.boundsR, P.boundsB},
                                                                                     firstVertex, instanceID, static_cast<int>(span), lane))
         {
             for (uint32_t t = lane; t < b.trisPerElement; t += 32)
@@ -1708,7 +1709,10 @@ int launch_draw_list(rivecuda_ctx* ctx, const rivecuda_flush_desc& desc, const r
         if (patchInstances > 0)
         {
             const uint32_t blocks = std::min<uint32_t>((patchInstances + kSetupWarpsPerBlock - 1) / kSetupWarpsPerBlock, ctx->smCount * 16);
-            setup_patches_kernel<<<blocks, kSetupWarpsPerBlock * 32, 0, stream>>>(P, devPatch, static_cast<uint32_t>(patchBatches.size()), patchInstances, triGeom, triAttr, bins);
+            if (P.cullPatches != 0u)
+                setup_patches_kernel<true><<<blocks, kSetupWarpsPerBlock * 32, 0, stream>>>(P, devPatch, static_cast<uint32_t>(patchBatches.size()), patchInstances, triGeom, triAttr, bins);
+            else
+                setup_patches_kernel<false><<<blocks, kSetupWarpsPerBlock * 32, 0, stream>>>(P, devPatch, static_cast<uint32_t>(patchBatches.size()), patchInstances, triGeom, triAttr, bins);
             ctx->lastLaunches += 1;
             RC_CUDA(cudaGetLastError());
         }
