@@ -350,7 +350,12 @@ typedef struct rivecuda_front_end_result
  * A non-zero frame size applies PathDraw::Make's frame cull (draw.cpp:439-509): paths whose
  * pixel bounds (outset for strokes) miss the render target produce no records, as in the
  * reference. The caller skips what RiveRenderer::drawPath skips before that point (empty
- * RawPaths, strokes with !(thickness > 0); rive_renderer.cpp:127-145). */
+ * RawPaths, strokes with !(thickness > 0); rive_renderer.cpp:127-145).
+ * Returns RIVECUDA_STATUS_EXCEEDS_FLUSH (and writes nothing) when the paths need more path ids,
+ * contour ids or tessellation vertices than one logical flush admits
+ * (RenderContext::LogicalFlush::pushDraws, render_context.cpp:528-536): the caller splits the
+ * draw list, as the reference starts a new logical flush. */
+#define RIVECUDA_STATUS_EXCEEDS_FLUSH 2
 int rivecuda_front_end_paths(rivecuda_ctx* ctx,
                              const float* points_xy,
                              uint32_t point_count,

@@ -536,9 +536,12 @@ int rivecuda_front_end_paths(rivecuda_ctx* ctx,
     // One flush holds what RenderContext::LogicalFlush::pushDraws admits (render_context.cpp:528-536):
     // path ids fit the fp16 id encoding, contour ids 16 bits, the tessellation texture 2048 rows.
     if (sums[2] > 30720u || sums[1] > 0xffffu || sums[5] > static_cast<uint32_t>(kTessWidth) * 2048u)
-        return set_error("rivecuda_front_end_paths: %u paths / %u contours / %u tessellation vertices exceed one flush "
-                         "(30720 / 65535 / 2048 x 2048); split the draw list as the reference starts a new logical flush",
-                         sums[2], sums[1], sums[5]);
+    {
+        set_error("rivecuda_front_end_paths: %u paths / %u contours / %u tessellation vertices exceed one flush "
+                  "(30720 / 65535 / 2048 x 2048); split the draw list as the reference starts a new logical flush",
+                  sums[2], sums[1], sums[5]);
+        return RIVECUDA_STATUS_EXCEEDS_FLUSH;
+    }
     if (path_count != 0)
     {
         front_end_place_kernel<false><<<blocks, kWarpsPerBlock * 32, 0, stream>>>(dPaths, path_count, dPoints, dVerbs, dTotals, dOwn, out);

@@ -5,6 +5,8 @@
  */
 #include "render_context_cuda_impl.hpp"
 
+#include <algorithm>
+
 #include "rive/renderer/rive_render_image.hpp"
 
 #include <dlfcn.h>
@@ -421,31 +423,60 @@ static void convert_atlas_batches(const AtlasDrawBatch* batches,
 
 bool RenderContextCUDAImpl::flushPlainPaths(const PlainPathFrame& frame)
 {
+    // One logical flush holds a bounded number of paths, contours and tessellation vertices
+    // (render_context.cpp:528-536). The reference finds the split points while it pushes draws;
+    // here the device counts, so a chunk that does not fit is halved and retried. Later chunks
+    // preserve what the earlier ones drew.
+    constexpr size_t kMaxPathsPerFlush = 30720;
+    size_t first = 0;
+    size_t chunk = std::min(frame.pathCount, kMaxPathsPerFlush);
+    bool firstFlush = true;
+    do
+    {
+        const size_t count = std::min(chunk, frame.pathCount - first);
+        const int status = flushPlainPathChunk(frame, first, count, firstFlush);
+        if (status == RIVECUDA_STATUS_EXCEEDS_FLUSH && count > 1)
+        {
+            chunk = (count + 1) / 2;
+            continue;
+        }
+        if (status != 0)
+        {
+            fprintf(stderr, "RenderContextCUDAImpl::flushPlainPaths: %s\n", m_abi.last_error());
+            return false;
+        }
+        first += count;
+        firstFlush = false;
+    } while (first < frame.pathCount);
+    return true;
+}
+
+int RenderContextCUDAImpl::flushPlainPathChunk(const PlainPathFrame& frame, size_t firstPath, size_t pathCount, bool firstFlush)
+{
     RenderTargetCUDA* target = frame.renderTarget;
     rivecuda_front_end_result r;
     memset(&r, 0, sizeof(r));
-    if (m_abi.front_end_paths(m_ctx,
-                              frame.pointCount != 0 ? &frame.points->x : nullptr,
-                              static_cast<uint32_t>(frame.pointCount),
-                              frame.verbs,
-                              static_cast<uint32_t>(frame.verbCount),
-                              frame.paths,
-                              static_cast<uint32_t>(frame.pathCount),
-                              target->width(),
-                              target->height(),
-                              &r) != 0)
+    if (int status = m_abi.front_end_paths(m_ctx,
+                                           frame.pointCount != 0 ? &frame.points->x : nullptr,
+                                           static_cast<uint32_t>(frame.pointCount),
+                                           frame.verbs,
+                                           static_cast<uint32_t>(frame.verbCount),
+                                           frame.paths + firstPath,
+                                           static_cast<uint32_t>(pathCount),
+                                           target->width(),
+                                           target->height(),
+                                           &r))
     {
-        fprintf(stderr, "RenderContextCUDAImpl::flushPlainPaths: %s\n", m_abi.last_error());
-        return false;
+        return status;
     }
     resizeTessellationTexture(kTessTextureWidth, r.tess_data_height);
 
-    // The descriptor LogicalFlush::layoutResources would have produced for this frame
+    // The descriptor LogicalFlush::layoutResources would have produced for this chunk
     // (render_context.cpp:1240-1392): one logical flush, everything at offset 0.
     FlushDescriptor desc;
     desc.renderTarget = target;
     desc.interlockMode = InterlockMode::rasterOrdering;
-    desc.colorLoadAction = frame.loadAction;
+    desc.colorLoadAction = firstFlush ? frame.loadAction : LoadAction::preserveRenderTarget;
     desc.colorClearValue = frame.clearColor;
     desc.coverageClearValue = 0;
     desc.renderTargetUpdateBounds = {0, 0, static_cast<int32_t>(target->width()), static_cast<int32_t>(target->height())};
@@ -459,7 +490,7 @@ bool RenderContextCUDAImpl::flushPlainPaths(const PlainPathFrame& frame)
         resizeFlushUniformBuffer(size);
         void* mapped = mapFlushUniformBuffer(size);
         if (mapped == nullptr)
-            return false;
+            return 1;
         new (mapped) FlushUniforms(desc, m_platformFeatures);
         unmapFlushUniformBuffer(size);
     }
@@ -491,12 +522,7 @@ bool RenderContextCUDAImpl::flushPlainPaths(const PlainPathFrame& frame)
     batch.base_index = kMidpointFanPatchBaseIndex;
     batch.first_blend_mode = static_cast<uint32_t>(BlendMode::srcOver);
     const uint32_t batchCount = r.patch_count != 0 ? 1u : 0u;
-    if (m_abi.flush(m_ctx, &d, &batch, batchCount, nullptr, 0, nullptr, 0) != 0)
-    {
-        fprintf(stderr, "RenderContextCUDAImpl::flushPlainPaths: %s\n", m_abi.last_error());
-        return false;
-    }
-    return true;
+    return m_abi.flush(m_ctx, &d, &batch, batchCount, nullptr, 0, nullptr, 0);
 }
 
 void RenderContextCUDAImpl::flush(const FlushDescriptor& desc)

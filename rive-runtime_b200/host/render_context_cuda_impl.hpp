@@ -128,9 +128,9 @@ public:
     // no feather; nonZero / evenOdd fills and strokes), handed over as RawPaths. The device does
     // what PathDraw::initForMidpointFan / pushMidpointFanTessellationData / pushPath and
     // LogicalFlush::layoutResources do on the CPU (rivecuda_front_end_paths), then the frame is
-    // flushed like any other. See CudaPathRenderer (cuda_path_renderer.hpp) for the
-    // rive::Renderer that collects such a frame. Returns false (with a message on stderr) when
-    // the paths exceed one logical flush or the ABI reports an error.
+    // flushed like any other -- in as many logical flushes as its paths need. See
+    // CudaPathRenderer (cuda_path_renderer.hpp) for the rive::Renderer that collects such a
+    // frame. Returns false (with a message on stderr) when the ABI reports an error.
     struct PlainPathFrame
     {
         RenderTargetCUDA* renderTarget = nullptr;
@@ -212,6 +212,7 @@ public:
 private:
     RenderContextCUDAImpl(const RiveCudaABI&, rivecuda_ctx*);
 
+    int flushPlainPathChunk(const PlainPathFrame&, size_t firstPath, size_t pathCount, bool firstFlush);
     void resizeBuffer(rivecuda_buffer_kind, size_t sizeInBytes);
     void* mapBuffer(rivecuda_buffer_kind, size_t mapSizeInBytes);
     void unmapBuffer(rivecuda_buffer_kind, size_t mapSizeInBytes);

@@ -147,3 +147,25 @@ def test_front_end_refuses_what_one_flush_cannot_hold(built):
         # ... and the context is still usable afterwards.
         ok = F.run(rp, dump, 3840, 2160)
         assert ok.path_count > 1
+
+
+def test_cpp_path_renderer_splits_frames_that_exceed_one_flush(built):
+    """40 000 paths (more path ids and 2.5x more tessellation vertices than one logical flush
+    admits): rivecuda_front_end_paths answers RIVECUDA_STATUS_EXCEEDS_FLUSH, the C++ host halves
+    the chunk until it fits and draws the frame in several flushes. The result must equal the
+    frame the reference front end (which splits on its own) produces through the same backend."""
+    import subprocess
+    import tempfile
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    player = os.path.join(root, "rive-runtime_b200", "_build", "rive_cuda_player")
+    if not os.path.exists(player):
+        pytest.skip("scene player not built (needs the reference tree at build time)")
+    env = dict(os.environ, RIVECUDA_LIB=os.path.join(root, "rive-runtime_b200", "_build", "librivecuda.so"))
+    frames = []
+    with tempfile.TemporaryDirectory() as tmp:
+        for extra in ([], ["--gpu-front-end"]):
+            out = os.path.join(tmp, "frame%d.rgba" % len(frames))
+            subprocess.check_call([player, "--scene", "c2", "--paths", "40000", "--budget-ms", "0", "--out", out, *extra], env=env,
+                                  stdout=subprocess.DEVNULL, timeout=300)
+            frames.append(np.fromfile(out, dtype=np.uint8))
+    assert frames[0].size == 3840 * 2160 * 4 and np.array_equal(frames[0], frames[1])
