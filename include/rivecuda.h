@@ -351,7 +351,8 @@ typedef struct rivecuda_front_end_result
  * pixel bounds (outset for strokes) miss the render target produce no records, as in the
  * reference. The caller skips what RiveRenderer::drawPath skips before that point (empty
  * RawPaths, strokes with !(thickness > 0); rive_renderer.cpp:127-145).
- * Returns RIVECUDA_STATUS_EXCEEDS_FLUSH (and writes nothing) when the paths need more path ids,
+ * Returns RIVECUDA_STATUS_EXCEEDS_FLUSH (nothing is drawn; result holds the path, contour and
+ * tessellation-vertex counts the paths would have needed) when the paths need more path ids,
  * contour ids or tessellation vertices than one logical flush admits
  * (RenderContext::LogicalFlush::pushDraws, render_context.cpp:528-536): the caller splits the
  * draw list, as the reference starts a new logical flush. */

@@ -540,6 +540,10 @@ int rivecuda_front_end_paths(rivecuda_ctx* ctx,
         set_error("rivecuda_front_end_paths: %u paths / %u contours / %u tessellation vertices exceed one flush "
                   "(30720 / 65535 / 2048 x 2048); split the draw list as the reference starts a new logical flush",
                   sums[2], sums[1], sums[5]);
+        // What the paths would have needed, so that the caller can size its next attempt.
+        result->midpoint_fan_tess_vertex_count = sums[0];
+        result->contour_count = sums[1];
+        result->path_count = sums[2] + 1;
         return RIVECUDA_STATUS_EXCEEDS_FLUSH;
     }
     if (path_count != 0)

@@ -391,6 +391,7 @@ void RenderContextCUDAImpl::resizeTessellationTexture(uint32_t width,
                                                       uint32_t height)
 {
     ABI_CHECK(m_abi.resize_tessellation_texture(m_ctx, width, height));
+    m_plainTessHeight = height;
 }
 
 void RenderContextCUDAImpl::resizeFeatherAtlasTexture(uint32_t width,
@@ -434,10 +435,17 @@ bool RenderContextCUDAImpl::flushPlainPaths(const PlainPathFrame& frame)
     do
     {
         const size_t count = std::min(chunk, frame.pathCount - first);
-        const int status = flushPlainPathChunk(frame, first, count, firstFlush);
+        rivecuda_front_end_result needed;
+        const int status = flushPlainPathChunk(frame, first, count, firstFlush, &needed);
         if (status == RIVECUDA_STATUS_EXCEEDS_FLUSH && count > 1)
         {
-            chunk = (count + 1) / 2;
+            // Scale the chunk by what did not fit (with a little slack), at least halving it.
+            constexpr double kMaxTessVertices = 2048.0 * 2048.0 - 64, kMaxContours = 65535;
+            const double over = std::max({needed.midpoint_fan_tess_vertex_count / kMaxTessVertices,
+                                          needed.contour_count / kMaxContours,
+                                          (needed.path_count - 1.0) / kMaxPathsPerFlush,
+                                          2.0 / 1.9});
+            chunk = std::max<size_t>(1, static_cast<size_t>(count / over * 0.95));
             continue;
         }
         if (status != 0)
@@ -451,10 +459,10 @@ bool RenderContextCUDAImpl::flushPlainPaths(const PlainPathFrame& frame)
     return true;
 }
 
-int RenderContextCUDAImpl::flushPlainPathChunk(const PlainPathFrame& frame, size_t firstPath, size_t pathCount, bool firstFlush)
+int RenderContextCUDAImpl::flushPlainPathChunk(const PlainPathFrame& frame, size_t firstPath, size_t pathCount, bool firstFlush, rivecuda_front_end_result* needed)
 {
     RenderTargetCUDA* target = frame.renderTarget;
-    rivecuda_front_end_result r;
+    rivecuda_front_end_result& r = *needed;
     memset(&r, 0, sizeof(r));
     if (int status = m_abi.front_end_paths(m_ctx,
                                            frame.pointCount != 0 ? &frame.points->x : nullptr,
@@ -469,7 +477,9 @@ int RenderContextCUDAImpl::flushPlainPathChunk(const PlainPathFrame& frame, size
     {
         return status;
     }
-    resizeTessellationTexture(kTessTextureWidth, r.tess_data_height);
+    // The tessellation texture only grows (the reference sizes it once per frame).
+    if (r.tess_data_height > m_plainTessHeight)
+        resizeTessellationTexture(kTessTextureWidth, r.tess_data_height);
 
     // The descriptor LogicalFlush::layoutResources would have produced for this chunk
     // (render_context.cpp:1240-1392): one logical flush, everything at offset 0.

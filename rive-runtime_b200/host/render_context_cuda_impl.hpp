@@ -212,7 +212,8 @@ public:
 private:
     RenderContextCUDAImpl(const RiveCudaABI&, rivecuda_ctx*);
 
-    int flushPlainPathChunk(const PlainPathFrame&, size_t firstPath, size_t pathCount, bool firstFlush);
+    int flushPlainPathChunk(const PlainPathFrame&, size_t firstPath, size_t pathCount, bool firstFlush, rivecuda_front_end_result* needed);
+    uint32_t m_plainTessHeight = 0; // what flushPlainPaths last sized the tessellation texture to
     void resizeBuffer(rivecuda_buffer_kind, size_t sizeInBytes);
     void* mapBuffer(rivecuda_buffer_kind, size_t mapSizeInBytes);
     void unmapBuffer(rivecuda_buffer_kind, size_t mapSizeInBytes);
