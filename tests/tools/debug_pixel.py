@@ -1,7 +1,7 @@
 """Print the per-fragment history of one pixel from both the oracle and the CUDA path.
-usage: python tools/debug_pixel.py <trace> <x> <y>"""
+usage: python tests/tools/debug_pixel.py <trace> <x> <y>"""
 import os, sys
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 trace, x, y = sys.argv[1], int(sys.argv[2]), int(sys.argv[3])
 os.environ["REFCPU_DEBUG_PIXEL"] = f"{x},{y}"

@@ -1,7 +1,7 @@
 """Find the worst pixel of one stream (CUDA vs oracle) among a spread of frames and print both
 sides' per-fragment history of that pixel (needs librivecuda_debug.so: make -C csrc debug)."""
 import os, sys
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 import numpy as np
 from rive_runtime_b200 import trace as T, replay as R

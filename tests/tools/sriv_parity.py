@@ -4,7 +4,7 @@ quartiles, last) is also rendered by the CPU oracle and compared (max channel de
 above 2/255, PSNR). Prints one line per stream and a JSON summary.
 
   tools/record_sriv_traces.sh <dir>          # here (needs /root/reference): 261 streams, ~21 MB xz
-  python tools/sriv_parity.py <dir> [out.json]
+  python tests/tools/sriv_parity.py <dir> [out.json]
 """
 import glob
 import json
@@ -14,7 +14,7 @@ import time
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 from rive_runtime_b200 import trace as T, replay as R  # noqa: E402
 from oracle import refcpu  # noqa: E402
