@@ -365,26 +365,6 @@ FE_HD uint32_t empty_stroke_cap(bool closed, uint32_t join, uint32_t cap)
     return cap;
 }
 
-// What a contour is before walking it: the ContourInfo fields pass 2 needs.
-struct ContourShape
-{
-    bool closed;  // strokes: an explicit close verb; fills: always
-    bool empty;   // no lines or curves
-};
-
-FE_HD ContourShape contour_shape(const uint8_t* verbs, uint32_t verbCount, bool isStroke)
-{
-    ContourShape s{!isStroke, true};
-    for (uint32_t v = 0; v < verbCount; ++v)
-    {
-        if (verbs[v] == kVerbClose)
-            s.closed = true;
-        else if (verbs[v] == kVerbLine || verbs[v] == kVerbCubic)
-            s.empty = false;
-    }
-    return s;
-}
-
 // One contour, as the list of "items" that emit spans independently of each other: item v < verbCount
 // is verb v after the move (closes emit nothing), item verbCount is the tail (the implicit closing
 // line, or the two caps of an empty stroked contour). Everything an item needs besides its own
@@ -907,7 +887,7 @@ FE_HD uint32_t place_path(const rivecuda_path& path, const V2* points, const uin
             if (isStroke)
             {
                 // LogicalFlush::pushContour: midpoint.x = closed ? 1 : 0 (render_context.cpp:3121-3126)
-                mx = bits(contour_shape(vb, nv, true).closed ? 1.f : 0.f);
+                mx = bits((nv != 0 && vb[nv - 1] == kVerbClose) ? 1.f : 0.f);
                 my = 0u;
             }
             else if (sink.preChopVerbCount == 0u)
