@@ -285,6 +285,73 @@ __global__ void __launch_bounds__(1024) front_end_scan_kernel(uint32_t* __restri
         out[0] = s_carry;
 }
 
+// The three per-path counts of pass 1 (tessellation vertices, contours, paths) scanned together:
+// one 16-byte load per path instead of three strided passes. out[0..2] = the grand totals.
+__global__ void __launch_bounds__(1024) front_end_scan3_kernel(uint4* __restrict__ totals, uint32_t n, uint32_t* __restrict__ out)
+{
+    __shared__ uint32_t s_warp[3][32];
+    __shared__ uint32_t s_carry[3];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x < 3)
+        s_carry[threadIdx.x] = 0u;
+    __syncthreads();
+    for (uint32_t base = 0; base < n; base += blockDim.x)
+    {
+        const uint32_t i = base + threadIdx.x;
+        const uint4 t = i < n ? totals[i] : make_uint4(0u, 0u, 0u, 0u);
+        const uint32_t v[3] = {t.x, t.y, t.z};
+        uint32_t incl[3] = {t.x, t.y, t.z};
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1)
+        {
+#pragma unroll
+            for (int f = 0; f < 3; ++f)
+            {
+                const uint32_t up = __shfl_up_sync(0xffffffffu, incl[f], o);
+                if (lane >= o)
+                    incl[f] += up;
+            }
+        }
+        if (lane == 31)
+        {
+#pragma unroll
+            for (int f = 0; f < 3; ++f)
+                s_warp[f][warp] = incl[f];
+        }
+        __syncthreads();
+        if (warp < 3)
+        {
+            const uint32_t w = s_warp[warp][lane];
+            uint32_t wi = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1)
+            {
+                const uint32_t up = __shfl_up_sync(0xffffffffu, wi, o);
+                if (lane >= o)
+                    wi += up;
+            }
+            s_warp[warp][lane] = wi - w;
+        }
+        __syncthreads();
+        uint32_t excl[3];
+#pragma unroll
+        for (int f = 0; f < 3; ++f)
+            excl[f] = s_carry[f] + s_warp[f][warp] + incl[f] - v[f];
+        if (i < n)
+            totals[i] = make_uint4(excl[0], excl[1], excl[2], t.w);
+        __syncthreads();
+        if (threadIdx.x == blockDim.x - 1)
+        {
+#pragma unroll
+            for (int f = 0; f < 3; ++f)
+                s_carry[f] = excl[f] + v[f];
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x < 3)
+        out[threadIdx.x] = s_carry[threadIdx.x];
+}
+
 // Passes 2 (EMIT false: spans per path) and 3 (EMIT true: write everything).
 template <bool EMIT>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32) front_end_place_kernel(const rivecuda_path* __restrict__ paths,
@@ -518,9 +585,7 @@ int rivecuda_front_end_paths(rivecuda_ctx* ctx,
     if (path_count != 0)
     {
         front_end_count_kernel<<<blocks, kWarpsPerBlock * 32, 0, stream>>>(dPaths, path_count, dPoints, dVerbs, frame_width, frame_height, point_count, dSums + 6, dTotals, dOwn);
-        front_end_scan_kernel<<<1, 1024, 0, stream>>>(field + 0, path_count, dSums + 0);
-        front_end_scan_kernel<<<1, 1024, 0, stream>>>(field + 1, path_count, dSums + 1);
-        front_end_scan_kernel<<<1, 1024, 0, stream>>>(field + 2, path_count, dSums + 2);
+        front_end_scan3_kernel<<<1, 1024, 0, stream>>>(reinterpret_cast<uint4*>(dTotals), path_count, dSums);
     }
     else
     {
