@@ -111,7 +111,8 @@ def run_reference(args, rank: int) -> None:
     from rive_runtime_b200 import trace as T
     workload, trace_path, metric = WORKLOADS[args.workload]
     records = T.parse(trace_path)
-    n_frames = max(T.summarize(records)["frames"], 1)
+    summary = T.summarize(records)
+    n_frames = max(summary["frames"], 1)
     cores = os.cpu_count() or 1
     for _ in range(min(args.warmup, 1)):
         refcpu.replay(records, threads=cores, keep_intermediates=False)
@@ -124,7 +125,10 @@ def run_reference(args, rank: int) -> None:
         "impl": "reference", "metric": metric, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": min(args.warmup, 1), "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload},
+        "config": {"workload": workload, "width": summary["width"], "height": summary["height"], "frames_per_step_per_gpu": n_frames,
+                   "paths": summary["paths"] // n_frames, "tess_vertices": summary["tess_vertices"] // n_frames,
+                   "mpixels_per_s": fps * summary["width"] * summary["height"] / 1e6,
+                   "parallelism": "host threads of rank 0 (the other ranks exit without work)"},
         "cpu_baseline": {"value": fps, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": f"{args.steps} pass(es) over the workload's {n_frames} full-size frame(s), oracle (CPU "
                                    "restatement of the reference shaders), all host threads"},
