@@ -566,6 +566,10 @@ int rivecuda_front_end_paths(rivecuda_ctx* ctx,
         BufferRing& ring = ctx->rings[kind];
         ring.current = (ring.current + 1) % kRingSize; // what map() does: a fresh ring slot
     }
+    // The slot was last read by the flush three flushes back. Every rivecuda_flush() first waits
+    // (resolve_pending_flush) for the previous flush's tile counts, which that flush produced
+    // after ITS predecessor's raster on the same stream: by the time a third call gets here, the
+    // slot's readers have finished -- the same pacing the mapped buffers rely on.
     auto dev = [&](int kind) { return ctx->rings[kind].device[ctx->rings[kind].current]; };
     FrontEndOut out;
     out.spans = static_cast<uint32_t*>(dev(RIVECUDA_BUFFER_TESS_SPAN));
