@@ -419,7 +419,7 @@ def main() -> None:
                          "algorithmic_bytes": alg_bytes, "peak_source": peak_src,
                          "other_kernels_ms": {"tessellate": float(np.mean(tess_ms)), "setup_bin_sort": float(np.mean(setup_ms))},
                          "note": "per frame; the kernel is instruction-issue bound, not HBM bound (DESIGN.md section 5): "
-                                 "ncu smsp__issue_active 73 % of peak, dram throughput 2 % of peak on c2 "
+                                 "ncu smsp__issue_active 73 % of peak, shared-memory wavefronts 54 % of the LSU pipe, dram throughput 2 % of peak on c2 "
                                  "(profiles/r01_ncu_summary_final.txt)"},
             "cpu_baseline": cpu,
             "clocks": clocks.summary(),
