@@ -802,7 +802,10 @@ __device__ __forceinline__ bool store_triangle(const FlushParams& P,
 // ---------------------------------------------------------------------------
 // Setup kernels
 
-constexpr int kSetupWarpsPerBlock = 4;
+#ifndef RIVECUDA_SETUP_WARPS
+#define RIVECUDA_SETUP_WARPS 4
+#endif
+constexpr int kSetupWarpsPerBlock = RIVECUDA_SETUP_WARPS;
 constexpr int kMaxPatchVertices = 153;
 
 __device__ __forceinline__ uint32_t find_batch(const DeviceBatch* __restrict__ batches, uint32_t batchCount, uint32_t workItem)
