@@ -61,3 +61,35 @@ extern "C" int front_end_host_paths(const float* pointsXY,
     result->reserved0 = 0;
     return 0;
 }
+
+// Single functions of the core, for known-answer tests that follow the reference's own unit tests
+// (tests/unit_tests/runtime/bezier_utils_test.cpp, wangs_formula_test.cpp).
+extern "C" int fe_find_cubic_convex_180_chops(const float pts[8], float T[2], int* areCusps)
+{
+    bool cusps = false;
+    const int n = find_cubic_convex_180_chops(reinterpret_cast<const V2*>(pts), T, &cusps);
+    *areCusps = cusps ? 1 : 0;
+    return n;
+}
+
+extern "C" void fe_chop_cubic_at(const float pts[8], float dst[14], float t)
+{
+    chop_cubic_at(reinterpret_cast<const V2*>(pts), reinterpret_cast<V2*>(dst), t);
+}
+
+extern "C" void fe_chop_cubic_at2(const float pts[8], float dst[20], float t0, float t1)
+{
+    chop_cubic_at(reinterpret_cast<const V2*>(pts), reinterpret_cast<V2*>(dst), t0, t1);
+}
+
+extern "C" void fe_eval_cubic_at(const float pts[8], float t, float out[2])
+{
+    const V2 p = eval_cubic_at(reinterpret_cast<const V2*>(pts), t);
+    out[0] = p.x;
+    out[1] = p.y;
+}
+
+extern "C" uint32_t fe_polar_segments(const float t0[2], const float t1[2], float polarSegmentsPerRadian)
+{
+    return polar_segments(V2{t0[0], t0[1]}, V2{t1[0], t1[1]}, polarSegmentsPerRadian);
+}

@@ -233,3 +233,96 @@ def test_front_end_core_matches_the_reference_on_random_paths(seed, tmp_path):
     assert np.array_equal(out.path_data[1:n, :8], want[1:, :8])
     want = np.frombuffer(host[2].tobytes()[:n * 8], dtype=np.uint32).reshape(-1, 2)
     assert np.array_equal(out.paint_data[1:n], want[1:])
+
+
+def _core():
+    import ctypes
+    lib = ctypes.CDLL(front_end_host.build())
+    lib.fe_find_cubic_convex_180_chops.restype = ctypes.c_int
+    return lib, ctypes
+
+
+def _chops(lib, ctypes, pts):
+    p = (ctypes.c_float * 8)(*np.asarray(pts, np.float32).ravel())
+    T = (ctypes.c_float * 2)()
+    cusps = ctypes.c_int(-1)
+    n = lib.fe_find_cubic_convex_180_chops(p, T, ctypes.byref(cusps))
+    return n, bool(cusps.value), [T[0], T[1]][:n]
+
+
+def test_convex_180_chops_known_answers_of_the_reference_unit_test():
+    """The cases of tests/unit_tests/runtime/bezier_utils_test.cpp:451-556
+    ("find_cubic_convex_180_chops", "..._lines") against the core's restatement."""
+    lib, ctypes = _core()
+    assert _chops(lib, ctypes, [(0, 0), (2, 2), (4, 2), (6, 0)])[0] == 0           # an exact quadratic
+    n, cusps, _ = _chops(lib, ctypes, [(0, 0), (1, 1), (1, 0), (0, 1)])            # a cusp
+    assert (n, cusps) == (1, True)
+    epsilon = 1.0 / (1 << 11)
+    h = (1 - epsilon * epsilon) / (3 * epsilon * epsilon + 1)
+    dy = (1 - h) / 2
+    n, cusps, T = _chops(lib, ctypes, [(0, 0), (1, np.float32(1 - 4 * dy)), (1, np.float32(4 * dy)), (0, 1)])
+    assert (n, cusps) == (2, False) and 0 < T[0] < T[1] < 1                        # inflections > epsilon apart
+    n, cusps, _ = _chops(lib, ctypes, [(0, 0), (1, np.float32(1 - .9 * dy)), (1, np.float32(.9 * dy)), (0, 1)])
+    assert (n, cusps) == (1, True)                                                 # < epsilon apart: one cusp
+    # "Ensure fast floatingpoint is not enabled" (bezier_utils_test.cpp:516-532)
+    f = np.float32
+    p3, p4, p5 = np.array([460, 460], f), np.array([667, 460], f), np.array([1060, 460], f)
+    t = f(2 / f(3))
+    c0, c1 = (p4 - p3) * t + p3, (p4 - p5) * t + p5
+    assert _chops(lib, ctypes, [p3, c0, c1, p5])[0] == 0
+    # Flat lines with ordered points are never cusps (:536-556).
+    p0, p3 = np.array([123, 200], f), np.array([223, 432], f)
+    t0 = f(1e-3)
+    while t0 < 1:
+        t1 = f(t0 + f(.097))
+        while t1 < 1:
+            line = [p0, p0 + (p3 - p0) * t0, p0 + (p3 - p0) * t1, p3]
+            assert _chops(lib, ctypes, line)[1] is False
+            t1 = f(t1 + f(.097))
+        t0 = f(t0 + f(.12))
+    # Every cubic on the corners of the unit square (:453-463): chop parameters are inside (0, 1)
+    # and sorted.
+    for i in range(256):
+        pts = [((i >> 0) & 1, (i >> 1) & 1), ((i >> 2) & 1, (i >> 3) & 1), ((i >> 4) & 1, (i >> 5) & 1), ((i >> 6) & 1, (i >> 7) & 1)]
+        n, cusps, T = _chops(lib, ctypes, pts)
+        assert 0 <= n <= 2 and all(0 < t < 1 for t in T) and T == sorted(T)
+
+
+def test_chop_cubic_at_known_answers_of_the_reference_unit_test():
+    """tests/unit_tests/runtime/bezier_utils_test.cpp:34-128 ("chop_cubic_at")."""
+    lib, ctypes = _core()
+    f4 = ctypes.c_float
+    # The diagonal 0..3 chopped at 1/2 gives points at multiples of 1/2 (:37-49).
+    pts = (f4 * 8)(*[v for i in range(4) for v in (float(i), float(i))])
+    dst = (f4 * 14)()
+    lib.fe_chop_cubic_at(pts, dst, f4(.5))
+    assert [dst[2 * i] for i in range(7)] == [i * .5 for i in range(7)] and all(dst[2 * i] == dst[2 * i + 1] for i in range(7))
+    rng = np.random.default_rng(7)
+    chop_ts = [0.0] + [3 / d for d in (83, 79, 73, 71, 67, 61, 59, 53, 47, 43, 41, 37, 31, 29, 23, 19, 17, 13, 11, 7, 5)] + [1.0]
+    for _ in range(5):
+        p = rng.uniform(0, 1, 8).astype(np.float32)
+        pts = (f4 * 8)(*p)
+        for t in chop_ts:
+            t = np.float32(t)
+            two = (f4 * 20)()
+            lib.fe_chop_cubic_at2(pts, two, f4(t), f4(t))
+            q = np.array(two[:], np.float32).reshape(10, 2)
+            assert (q[3] == q[4]).all() and (q[3] == q[5]).all() and (q[3] == q[6]).all()  # the middle is exactly degenerate
+            want = (f4 * 2)()
+            lib.fe_eval_cubic_at(pts, f4(t), want)
+            assert np.allclose(q[3], [want[0], want[1]], atol=1e-5)                       # ... at the right point
+            if t == 0:
+                assert (q[:4] == p[:2]).all()
+            if t == 1:
+                assert (q[6:] == p[6:]).all()
+
+
+def test_polar_segment_count_of_degenerate_tangents():
+    """simd::clamp returns lo for NaN (include/rive/math/simd.hpp:244-254): a zero tangent makes
+    cosTheta NaN -> -1 -> half a turn of polar segments, as the reference computes it."""
+    lib, ctypes = _core()
+    lib.fe_polar_segments.restype = ctypes.c_uint32
+    t = (ctypes.c_float * 2)
+    assert lib.fe_polar_segments(t(1, 0), t(1, 0), ctypes.c_float(10)) == 1
+    assert lib.fe_polar_segments(t(1, 0), t(-1, 0), ctypes.c_float(10)) == 32   # ceil(pi * 10)
+    assert lib.fe_polar_segments(t(0, 0), t(1, 0), ctypes.c_float(10)) == 32    # NaN -> -1 -> pi
