@@ -93,3 +93,10 @@ extern "C" uint32_t fe_polar_segments(const float t0[2], const float t1[2], floa
 {
     return polar_segments(V2{t0[0], t0[1]}, V2{t1[0], t1[1]}, polarSegmentsPerRadian);
 }
+
+extern "C" float fe_fast_acos(float x) { return fast_acos(x); }
+
+extern "C" uint32_t fe_wang_cubic_segments(const float pts[8], const float matrix[6])
+{
+    return wang_cubic_segments(reinterpret_cast<const V2*>(pts), matrix);
+}

@@ -326,3 +326,26 @@ def test_polar_segment_count_of_degenerate_tangents():
     assert lib.fe_polar_segments(t(1, 0), t(1, 0), ctypes.c_float(10)) == 1
     assert lib.fe_polar_segments(t(1, 0), t(-1, 0), ctypes.c_float(10)) == 32   # ceil(pi * 10)
     assert lib.fe_polar_segments(t(0, 0), t(1, 0), ctypes.c_float(10)) == 32    # NaN -> -1 -> pi
+
+
+def test_core_scalar_functions_equal_the_numpy_restatement():
+    """The core's fast_acos and Wang's-formula count against oracle/front_end_ref.py (which the tests
+    at the top of this file pin on the reference's own spans): bit-equal on a grid / random cubics,
+    and fast_acos within SIMD_FAST_ACOS_MAX_ERROR = 0.0167552 of acos, the bound the reference's
+    simd_test.cpp checks ("fast_acos", include/rive/math/simd.hpp:495)."""
+    lib, ctypes = _core()
+    lib.fe_fast_acos.restype = ctypes.c_float
+    lib.fe_fast_acos.argtypes = [ctypes.c_float]
+    lib.fe_wang_cubic_segments.restype = ctypes.c_uint32
+    xs = np.linspace(-1, 1, 4097).astype(np.float32)
+    got = np.array([lib.fe_fast_acos(float(x)) for x in xs], np.float32)
+    assert np.array_equal(got.view(np.uint32), front_end_ref.fast_acos(xs).view(np.uint32))
+    assert np.abs(got - np.arccos(xs.astype(np.float64))).max() <= 0.0167552
+    rng = np.random.default_rng(3)
+    pts = rng.uniform(-500, 500, (2000, 4, 2)).astype(np.float32)
+    mats = rng.uniform(-3, 3, (2000, 6)).astype(np.float32)
+    want = front_end_ref.wang_cubic_segments(pts, mats)
+    for i in range(2000):
+        p = (ctypes.c_float * 8)(*pts[i].ravel())
+        m = (ctypes.c_float * 6)(*mats[i])
+        assert lib.fe_wang_cubic_segments(p, m) == want[i]
