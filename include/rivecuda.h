@@ -356,7 +356,7 @@ typedef struct rivecuda_front_end_result
  * contour ids or tessellation vertices than one logical flush admits
  * (RenderContext::LogicalFlush::pushDraws, render_context.cpp:528-536): the caller splits the
  * draw list, as the reference starts a new logical flush. */
-#define RIVECUDA_STATUS_EXCEEDS_FLUSH 2
+#define RIVECUDA_STATUS_EXCEEDS_FLUSH 0x10002 /* outside the cudaError_t range other failures return */
 int rivecuda_front_end_paths(rivecuda_ctx* ctx,
                              const float* points_xy,
                              uint32_t point_count,

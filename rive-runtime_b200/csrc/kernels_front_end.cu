@@ -566,6 +566,16 @@ int rivecuda_front_end_paths(rivecuda_ctx* ctx,
         BufferRing& ring = ctx->rings[kind];
         ring.current = (ring.current + 1) % kRingSize; // what map() does: a fresh ring slot
     }
+    // A call that fails below is followed by no flush: it hands its slots back, so that the
+    // rings advance exactly once per flush (the pacing argument that follows depends on it;
+    // what such a call has written so far went to slots no flush in flight reads).
+    auto unrotate = [&]() {
+        for (int kind : {RIVECUDA_BUFFER_FLUSH_UNIFORM, RIVECUDA_BUFFER_PATH, RIVECUDA_BUFFER_PAINT, RIVECUDA_BUFFER_PAINT_AUX, RIVECUDA_BUFFER_CONTOUR, RIVECUDA_BUFFER_TESS_SPAN})
+        {
+            BufferRing& ring = ctx->rings[kind];
+            ring.current = (ring.current + kRingSize - 1) % kRingSize;
+        }
+    };
     // The slot was last read by the flush three flushes back. Every rivecuda_flush() first waits
     // (resolve_pending_flush) for the previous flush's tile counts, which that flush produced
     // after ITS predecessor's raster on the same stream: by the time a third call gets here, the
@@ -601,7 +611,10 @@ int rivecuda_front_end_paths(rivecuda_ctx* ctx,
     out.spanBase = ctx->pinnedTotals[8 + 4];
     const uint32_t* sums = ctx->pinnedTotals + 8;
     if (sums[6] != 0u)
+    {
+        unrotate();
         return set_error("rivecuda_front_end_paths: bad arguments (a path's verbs need more points than the point array holds)");
+    }
     // One flush holds what RenderContext::LogicalFlush::pushDraws admits (render_context.cpp:528-536):
     // path ids fit the fp16 id encoding, contour ids 16 bits, the tessellation texture 2048 rows.
     if (sums[2] > 30720u || sums[1] > 0xffffu || sums[5] > static_cast<uint32_t>(kTessWidth) * 2048u)
@@ -613,6 +626,7 @@ int rivecuda_front_end_paths(rivecuda_ctx* ctx,
         result->midpoint_fan_tess_vertex_count = sums[0];
         result->contour_count = sums[1];
         result->path_count = sums[2] + 1;
+        unrotate();
         return RIVECUDA_STATUS_EXCEEDS_FLUSH;
     }
     if (path_count != 0)
