@@ -96,7 +96,25 @@ def lib():
         _lib.refcpu_half_to_float.restype = ctypes.c_float
         _lib.refcpu_raster_mask.argtypes = [ctypes.POINTER(ctypes.c_float), ctypes.c_int, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_void_p]
         _lib.refcpu_raster_mask.restype = ctypes.c_int
+        _bind_pin_exports(_lib, "refcpu")
     return _lib
+
+
+def _bind_pin_exports(L, prefix: str) -> None:
+    """The stage-level exports oracle/refcpu and oracle/glslref share (refcpu.h)."""
+    vp = ctypes.c_void_p
+    fn = getattr(L, prefix + "_path_vertices")
+    fn.argtypes = [ctypes.POINTER(RefFlush), ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, vp] + ([vp] if prefix == "refcpu" else [])
+    fn.restype = ctypes.c_int
+    fn = getattr(L, prefix + "_path_fragments")
+    fn.argtypes = [ctypes.POINTER(RefFlush), ctypes.c_uint32, ctypes.c_uint32, vp, vp, vp]
+    fn.restype = ctypes.c_int
+    fn = getattr(L, prefix + "_advanced_color_blend_n")
+    fn.argtypes = [ctypes.c_uint32, vp, vp, vp, vp, ctypes.c_int]
+    fn.restype = None
+    fn = getattr(L, prefix + "_cubic_helpers_n")
+    fn.argtypes = [ctypes.c_uint32, vp, vp, vp]
+    fn.restype = None
 
 
 def _ptr(a: Optional[np.ndarray]):
@@ -118,10 +136,13 @@ class ReplayResult:
 
 
 def replay(records: List[T.Record], threads: int = 1, keep_intermediates: bool = True,
-           max_frames: Optional[int] = None, only_frames: Optional[set] = None) -> ReplayResult:
+           max_frames: Optional[int] = None, only_frames: Optional[set] = None, on_flush=None) -> ReplayResult:
     """Run every flush of a trace through the oracle; returns the frames read
     back (one per RVCT_TARGET_READ) and, per flush, the gradient / tessellation /
-    atlas textures the oracle produced."""
+    atlas textures the oracle produced. on_flush(rf, outputs, flush_record), if given, runs
+    after each flush with the RefFlush struct the oracle was called with (its pointers are
+    alive for the duration of the call): the pinning tests use it to run oracle/glslref on
+    the very same inputs."""
     L = lib()
     buffers: Dict[int, np.ndarray] = {}
     targets: Dict[int, np.ndarray] = {}
@@ -219,6 +240,8 @@ def replay(records: List[T.Record], threads: int = 1, keep_intermediates: bool =
             rf.atlas_height = ah
             if L.refcpu_flush_run(ctypes.byref(rf)) != 0:
                 raise RuntimeError(L.refcpu_last_error().decode())
+            if on_flush is not None:
+                on_flush(rf, fo, fr)
             if keep_intermediates:
                 out.flushes.append(fo)
             else:

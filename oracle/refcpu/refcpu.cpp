@@ -604,7 +604,7 @@ float4 pack_feathered_fill_coverages(float cornerTheta, float2 spokeNorm, float 
     }
     else
     {
-        float tanTheta = tanf(cornerTheta);
+        float tanTheta = cr_tan(cornerTheta);
         cotTheta = signf(PI_OVER_2 - cornerTheta) / fmaxf(fabsf(tanTheta), 1.f / HORIZONTAL_COTANGENT_VALUE);
         y0 = cotTheta >= 0.f ? cornerLocalCoord.y - (1.f - cornerLocalCoord.x) * tanTheta : cornerLocalCoord.y + cornerLocalCoord.x * tanTheta;
     }
@@ -635,7 +635,7 @@ float eval_feathered_fill(const Context& c, float4 coverages)
             float u = t * -cotTheta + (y * cotTheta + x);
             float feather = c.lut.FEATHER(u);
             float t_ = t * 5.09593080173f + -2.54796540086f;
-            float ddtFeather = exp2f(-t_ * t_);
+            float ddtFeather = cr_exp2(-t_ * t_);
             sum += feather * ddtFeather;
         }
         featherCoverage += sum * dt;
@@ -980,7 +980,7 @@ void path_vertex_paint(const Context& c, const BatchState& bs, uint32_t pathID, 
     const bool unmultiplied = bs.advancedBlend; // GENERATE_UNMULTIPLIED_PAINT_COLORS
     if (paintType == SOLID_COLOR_PAINT_TYPE)
     {
-        float4 color = unpackUnorm4x8(paintY);
+        float4 color = unpackUnorm4x8_builtin(paintY); // draw_path.vert:300
         if (!unmultiplied)
         {
             color.x *= color.w;
@@ -1967,6 +1967,138 @@ int refcpu_raster_mask(const float xy[6], int cull_ccw, uint32_t w, uint32_t h, 
         ++count;
     });
     return count;
+}
+
+// ---- pinning exports: the shader stages of one batch on explicit inputs, so that
+// tests/test_oracle_glslref_cpu.py can compare them with the reference's own shader
+// sources compiled as C++ (oracle/glslref). Layouts are documented in refcpu.h.
+
+struct PinArgs
+{
+    uint32_t batchIndex, first, count;
+    float* out;
+    const float* fragIn;
+    const uint32_t* plsIn;
+    uint32_t* plsOut;
+    uint32_t result;
+};
+static thread_local PinArgs t_pin;
+
+int refcpu_path_vertices(const refcpu_flush* f, uint32_t batch_index, uint32_t first_instance, uint32_t instance_count, float* out, uint32_t* out_vertices_per_instance)
+{
+    t_pin = {batch_index, first_instance, instance_count, out, nullptr, nullptr, nullptr, 0};
+    int r = with_context(f, [](Context& c) {
+        if (t_pin.batchIndex >= c.f->batch_count)
+            return fail("refcpu_path_vertices: batch index");
+        const rivecuda_draw_batch& batch = c.f->batches[t_pin.batchIndex];
+        if (batch.draw_type != RIVECUDA_DRAW_MIDPOINT_FAN_PATCHES && batch.draw_type != RIVECUDA_DRAW_MIDPOINT_FAN_CENTER_AA_PATCHES &&
+            batch.draw_type != RIVECUDA_DRAW_OUTER_CURVE_PATCHES)
+            return fail("refcpu_path_vertices: not a patch batch");
+        BatchState bs(batch);
+        uint32_t vmin = 0xffffffffu, vmax = 0;
+        for (uint32_t i = 0; i < batch.index_count_per_instance; ++i)
+        {
+            uint32_t vi = c.patchIndices[batch.base_index + i];
+            vmin = std::min(vmin, vi);
+            vmax = std::max(vmax, vi);
+        }
+        const uint32_t vcount = vmax - vmin + 1;
+        t_pin.result = vcount;
+        if (t_pin.out == nullptr)
+            return 0;
+        for (uint32_t inst = 0; inst < t_pin.count; ++inst)
+        {
+            for (uint32_t vi = 0; vi < vcount; ++vi)
+            {
+                VSOut o = {};
+                uint32_t pathID;
+                float2 pos;
+                float4 coverages;
+                bool ok = unpack_tessellated_path_vertex(c, c.patchVertices[vmin + vi], static_cast<int>(batch.base_element + t_pin.first + inst), bs.feather, pathID, pos, coverages);
+                o.coverages = bs.feather ? coverages : float4{coverages.x, coverages.y, 0.f, 0.f};
+                path_vertex_paint(c, bs, pathID, pos, false, o);
+                float* w = t_pin.out + (static_cast<size_t>(inst) * vcount + vi) * 24;
+                w[0] = pos.x;
+                w[1] = pos.y;
+                w[2] = ok ? 0.f : 1.f;
+                w[3] = static_cast<float>(pathID);
+                w[4] = o.paint.x, w[5] = o.paint.y, w[6] = o.paint.z, w[7] = o.paint.w;
+                w[8] = o.coverages.x, w[9] = o.coverages.y, w[10] = o.coverages.z, w[11] = o.coverages.w;
+                w[12] = o.pathID, w[13] = o.clipIDs.x, w[14] = o.clipIDs.y, w[15] = o.blendMode;
+                w[16] = o.clipRect.x, w[17] = o.clipRect.y, w[18] = o.clipRect.z, w[19] = o.clipRect.w;
+                w[20] = o.image.x, w[21] = o.image.y, w[22] = o.image.z, w[23] = 0.f;
+            }
+        }
+        return 0;
+    });
+    if (out_vertices_per_instance != nullptr)
+        *out_vertices_per_instance = t_pin.result;
+    return r;
+}
+
+int refcpu_path_fragments(const refcpu_flush* f, uint32_t batch_index, uint32_t n, const float* frag_in, const uint32_t* pls_in, uint32_t* pls_out)
+{
+    t_pin = {batch_index, 0, n, nullptr, frag_in, pls_in, pls_out, 0};
+    return with_context(f, [](Context& c) {
+        if (t_pin.batchIndex >= c.f->batch_count)
+            return fail("refcpu_path_fragments: batch index");
+        BatchState bs(c.f->batches[t_pin.batchIndex]);
+        const uint32_t n = t_pin.count;
+        std::vector<uint32_t> color(n), clip(n), scratch(n), coverage(n);
+        for (uint32_t k = 0; k < n; ++k)
+        {
+            color[k] = t_pin.plsIn[k * 4 + 0];
+            clip[k] = t_pin.plsIn[k * 4 + 1];
+            scratch[k] = t_pin.plsIn[k * 4 + 2];
+            coverage[k] = t_pin.plsIn[k * 4 + 3];
+        }
+        PLS pls = {color.data(), clip.data(), scratch.data(), coverage.data()};
+        for (uint32_t k = 0; k < n; ++k)
+        {
+            const float* w = t_pin.fragIn + static_cast<size_t>(k) * 24;
+            FragIn in;
+            in.paint = {w[0], w[1], w[2], w[3]};
+            in.image = {w[4], w[5], w[6]};
+            in.windingWeight = w[7];
+            in.coverages = {w[8], w[9], w[10], w[11]};
+            in.pathID = w[12];
+            in.clipIDs = {w[13], w[14]};
+            in.blendMode = w[15];
+            in.clipRect = {w[16], w[17], w[18], w[19]};
+            path_fragment_main(c, bs, in, false, static_cast<int>(w[20]), static_cast<int>(w[21]), k, pls);
+            t_pin.plsOut[k * 4 + 0] = color[k];
+            t_pin.plsOut[k * 4 + 1] = clip[k];
+            t_pin.plsOut[k * 4 + 2] = scratch[k];
+            t_pin.plsOut[k * 4 + 3] = coverage[k];
+        }
+        return 0;
+    });
+}
+
+void refcpu_advanced_color_blend_n(uint32_t n, const float* src_rgb, const float* dst_premul, const uint32_t* modes, float* out_rgb, int coeffs_only)
+{
+    for (uint32_t k = 0; k < n; ++k)
+    {
+        const float* s = src_rgb + k * 3;
+        const float* d = dst_premul + k * 4;
+        half3 r = coeffs_only ? advanced_blend_coeffs({s[0], s[1], s[2]}, {d[0], d[1], d[2], d[3]}, modes[k], true)
+                              : advanced_color_blend({s[0], s[1], s[2]}, {d[0], d[1], d[2], d[3]}, modes[k], true);
+        out_rgb[k * 3 + 0] = r.r;
+        out_rgb[k * 3 + 1] = r.g;
+        out_rgb[k * 3 + 2] = r.b;
+    }
+}
+
+void refcpu_cubic_helpers_n(uint32_t n, const float* pts8, const float* spreads, float* out3)
+{
+    for (uint32_t k = 0; k < n; ++k)
+    {
+        const float* p = pts8 + k * 8;
+        float t;
+        out3[k * 3 + 0] = find_cubic_max_height({p[0], p[1]}, {p[2], p[3]}, {p[4], p[5]}, {p[6], p[7]}, t);
+        out3[k * 3 + 1] = t;
+        out3[k * 3 + 2] = measure_cubic_local_curvature({p[0], p[1]}, {p[2], p[3]}, {p[4], p[5]}, {p[6], p[7]}, t, spreads[k]);
+    }
 }
 
 } // extern "C"

@@ -12,16 +12,20 @@
  *   - front half of the path (segment counts, span offsets, batches, records):
  *     produced by the REFERENCE ITSELF, compiled in place (oracle/ref/Makefile
  *     -> oracle/_ref/librive_front.a) and captured as flush traces. Pinned.
- *   - shader helper math (bezier_utils.glsl, advanced_blend.glsl): pinned
- *     against the reference's own known-answer unit tests
- *     (tests/unit_tests/runtime/bezier_utils_test.cpp GLSL cases,
- *     tests/unit_tests/renderer/advanced_blend_test.cpp), see
- *     tests/test_oracle_known_answers.py.
- *   - whole-frame pixels: PARITY UNPINNED by reference artefacts -- the
- *     reference ships no golden PNGs and its pixel stage (GLSL -> SPIR-V on
- *     Vulkan/SwiftShader) cannot be built here (no glslang, Vulkan headers,
- *     SwiftShader or python ply). Pixels are pinned only by this literal
- *     restatement agreeing with the CUDA path.
+ *   - shader arithmetic (tessellate.glsl, bezier_utils.glsl, draw_path_common.glsl,
+ *     draw_path.vert, draw_raster_order_path.frag, advanced_blend.glsl, common.glsl):
+ *     PINNED BIT FOR BIT to the reference's own shader sources compiled as C++
+ *     (oracle/glslref -> oracle/_ref/libglslref.so) by
+ *     tests/test_oracle_glslref_cpu.py -- every tessellation texel, every patch
+ *     vertex and randomised fragments of 38 committed traces, the 6^6 colour
+ *     grid x 15 blend modes, 10^6 random cubics; the reference's known-answer
+ *     unit tests (tests/test_oracle_known_answers.py) are the secondary check.
+ *   - the fixed-function rules around the shaders (triangle rasterisation,
+ *     noperspective interpolation in double barycentrics, texture filtering,
+ *     unorm8 / fp16 conversion): defined here from the Vulkan specification;
+ *     UNPINNED by reference artefacts -- the reference ships no golden PNGs and
+ *     its pixel stage (GLSL -> SPIR-V on Vulkan/SwiftShader) cannot be run here
+ *     (no glslang, Vulkan headers, SwiftShader or python ply).
  *
  * Everything operates on the C-ABI PODs of include/rivecuda.h plus raw
  * pointers to the nine host buffers, exactly what a flush trace holds.
@@ -109,6 +113,21 @@ float refcpu_half_to_float(uint16_t h);
  * bits) into a w x h byte mask (1 = covered). cull_ccw: drop counter-clockwise
  * (y-down) triangles. Returns the number of covered pixels. */
 int refcpu_raster_mask(const float xy[6], int cull_ccw, uint32_t w, uint32_t h, uint8_t* mask);
+
+/* ---- pinning exports (compared with oracle/glslref: the reference's own shader sources
+ * compiled as C++) ------------------------------------------------------------------- */
+/* The vertex stage of patch batch `batch_index` (needs tess_texture rendered): 24 floats per
+ * (instance, patch vertex): pos.xy, discarded, pathID | v_paint | v_coverages | v_pathID,
+ * v_clipIDs.xy, v_blendMode | v_clipRect | v_image.xyz, 0. out == NULL: only the count. */
+int refcpu_path_vertices(const refcpu_flush* f, uint32_t batch_index, uint32_t first_instance, uint32_t instance_count, float* out, uint32_t* out_vertices_per_instance);
+/* draw_raster_order_path.frag on n explicit fragments with the features of batch `batch_index`
+ * (needs grad_texture rendered). frag_in: 24 floats each: v_paint | v_image.xyz,
+ * windingWeight | v_coverages | v_pathID, v_clipIDs.xy, v_blendMode | v_clipRect | pixel x, y,
+ * 0, 0. pls_in / pls_out: colour (RGBA8), clip, scratch (RGBA8), coverage per fragment. */
+int refcpu_path_fragments(const refcpu_flush* f, uint32_t batch_index, uint32_t n, const float* frag_in, const uint32_t* pls_in, uint32_t* pls_out);
+void refcpu_advanced_color_blend_n(uint32_t n, const float* src_rgb, const float* dst_premul, const uint32_t* modes, float* out_rgb, int coeffs_only);
+/* per cubic: find_cubic_max_height, its T, measure_cubic_local_curvature(T, spread). */
+void refcpu_cubic_helpers_n(uint32_t n, const float* pts8, const float* spreads, float* out3);
 
 #ifdef __cplusplus
 }

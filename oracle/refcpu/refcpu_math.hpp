@@ -51,6 +51,8 @@ inline float clampf(float x, float lo, float hi) { return fminf(fmaxf(x, lo), hi
 inline float cr_cos(float x) { return static_cast<float>(std::cos(static_cast<double>(x))); }
 inline float cr_sin(float x) { return static_cast<float>(std::sin(static_cast<double>(x))); }
 inline float cr_acos(float x) { return static_cast<float>(std::acos(static_cast<double>(x))); }
+inline float cr_tan(float x) { return static_cast<float>(std::tan(static_cast<double>(x))); }
+inline float cr_exp2(float x) { return static_cast<float>(std::exp2(static_cast<double>(x))); }
 inline float cr_pow(float x, float y) { return static_cast<float>(std::pow(static_cast<double>(x), static_cast<double>(y))); }
 inline float mixf(float a, float b, float t) { return a * (1.f - t) + b * t; }
 inline float2 mix2(float2 a, float2 b, float t) { return a * (1.f - t) + b * t; }
@@ -164,9 +166,16 @@ inline uint32_t float_to_unorm8(float f)
         return 255;
     return static_cast<uint32_t>(f * 255.f + .5f);
 }
+// Fixed-function UNORM8 -> float (texel fetches, attachment / image loads): k * (1/255).
 inline float4 unpackUnorm4x8(uint32_t u)
 {
     return {unorm8_to_float(u & 0xff), unorm8_to_float((u >> 8) & 0xff), unorm8_to_float((u >> 16) & 0xff), unorm8_to_float(u >> 24)};
+}
+// The GLSL built-in of the same name as shader code calls it: "f / 255.0" (GLSL ES 3.10 8.4).
+inline float4 unpackUnorm4x8_builtin(uint32_t u)
+{
+    return {static_cast<float>(u & 0xff) / 255.f, static_cast<float>((u >> 8) & 0xff) / 255.f, static_cast<float>((u >> 16) & 0xff) / 255.f,
+            static_cast<float>(u >> 24) / 255.f};
 }
 inline uint32_t packUnorm4x8(float4 c)
 {

@@ -91,6 +91,7 @@ __device__ __forceinline__ m22 inverse(m22 m)
 // double-rounding tie, ~1e-8 per call) and the tessellator's discontinuous decisions -- the
 // binary search "cosRotation >= cos(maxRotation)" on nearly straight stroke pieces next to a
 // cusp -- fall the same way. CUDA's float cosf / acosf are 1-2 ulp off glibc's.
+__device__ __forceinline__ float cr_tan(float x) { return static_cast<float>(tan(static_cast<double>(x))); }
 __device__ __forceinline__ float cr_cos(float x) { return static_cast<float>(cos(static_cast<double>(x))); }
 __device__ __forceinline__ float cr_sin(float x) { return static_cast<float>(sin(static_cast<double>(x))); }
 __device__ __forceinline__ void cr_sincos(float x, float* s, float* c)
@@ -167,5 +168,12 @@ __device__ __forceinline__ float4 unpack_rgba8(uint32_t u)
 {
     const float s = 1.f / 255.f;
     return make_float4((u & 0xff) * s, ((u >> 8) & 0xff) * s, ((u >> 16) & 0xff) * s, (u >> 24) * s);
+}
+// The GLSL built-in unpackUnorm4x8 as shader code calls it (draw_path.vert:300): "f / 255.0",
+// correctly rounded. unpack_rgba8 above is the fixed-function texel / attachment conversion.
+__device__ __forceinline__ float4 unpack_rgba8_builtin(uint32_t u)
+{
+    return make_float4(__fdiv_rn(static_cast<float>(u & 0xff), 255.f), __fdiv_rn(static_cast<float>((u >> 8) & 0xff), 255.f),
+                       __fdiv_rn(static_cast<float>((u >> 16) & 0xff), 255.f), __fdiv_rn(static_cast<float>(u >> 24), 255.f));
 }
 } // namespace rivecuda

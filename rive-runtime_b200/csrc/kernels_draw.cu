@@ -177,7 +177,7 @@ __device__ float4 pack_feathered_fill_coverages(float cornerTheta, f2 spokeNorm,
     }
     else
     {
-        float tanTheta = tanf(cornerTheta);
+        float tanTheta = cr_tan(cornerTheta); // once-rounded, as the oracle
         cotTheta = signf(kPI_2 - cornerTheta) / fmaxf(fabsf(tanTheta), 1.f / kHorizontalCotangentValue);
         y0 = cotTheta >= 0.f ? corner.y - (1.f - corner.x) * tanTheta : corner.y + corner.x * tanTheta;
     }

@@ -216,7 +216,7 @@ __device__ void prepare_triangle(const FlushParams& P,
     out.meta = meta;
     // draw_path.vert:298-312: solid colours are premultiplied in the vertex stage
     // unless the batch runs with advanced blend.
-    float4 pc = unpack_rgba8(paint.y);
+    float4 pc = unpack_rgba8_builtin(paint.y);
     if ((g.meta & kMetaUnmultiplied) == 0u)
     {
         pc.x *= pc.w;
