@@ -97,7 +97,17 @@ def lib():
         _lib.refcpu_raster_mask.argtypes = [ctypes.POINTER(ctypes.c_float), ctypes.c_int, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_void_p]
         _lib.refcpu_raster_mask.restype = ctypes.c_int
         _bind_pin_exports(_lib, "refcpu")
+        _lib.refcpu_set_atlas_mode.argtypes = [ctypes.c_int]
+        _lib.refcpu_set_atlas_mode.restype = None
     return _lib
+
+
+ATLAS_R16F_BLEND, ATLAS_R32I_ATOMIC = 0, 1
+
+
+def set_atlas_mode(mode: int) -> None:
+    """Which of render_atlas.glsl's accumulation variants the oracle restates (refcpu.h)."""
+    lib().refcpu_set_atlas_mode(mode)
 
 
 def _bind_pin_exports(L, prefix: str) -> None:

@@ -35,7 +35,8 @@ using namespace refcpu;
 static thread_local std::string t_error;
 // Debug aid: REFCPU_DEBUG_PIXEL="x,y" prints every fragment that hits the pixel.
 static int g_debugX = -1, g_debugY = -1;
-static thread_local bool g_debugTrace = false; // the fragment being shaded is REFCPU_DEBUG_PIXEL
+static thread_local bool g_debugTrace = false;
+static int g_atlasMode = REFCPU_ATLAS_R32I_ATOMIC; // the fragment being shaded is REFCPU_DEBUG_PIXEL
 static int fail(const char* msg)
 {
     t_error = msg;
@@ -1804,6 +1805,16 @@ void render_atlas(Context& c)
     rivecuda_draw_batch dummy = {};
     dummy.shader_features = RIVECUDA_FEATURE_FEATHER;
     BatchState bs(dummy);
+    // render_atlas.glsl offers several ways to accumulate atlas coverage, chosen per platform:
+    // fixed-function blending into the float target (:233-249; Vulkan: R16F, every blend result
+    // stored as fp16, in primitive order) or, where that is unavailable, 16:16 fixed point in an
+    // r32i image updated with atomics (:146-170, @ATLAS_RENDER_TARGET_R32I_ATOMIC_TEXTURE;
+    // resolve_atlas.glsl:62-71). The atomic variant is order-independent, which is why the CUDA
+    // backend uses it; g_atlasMode selects which one this oracle restates.
+    const bool fixedPoint = g_atlasMode == REFCPU_ATLAS_R32I_ATOMIC;
+    std::vector<int32_t> fixed;
+    if (fixedPoint)
+        fixed.assign(static_cast<size_t>(AW) * c.atlasHeight, 0);
 
     auto draw = [&](const rivecuda_atlas_batch& ab, bool isStroke) {
         // Fills: kMidpointFanCenterAAPatch (120 indices from base 72), cull none,
@@ -1840,6 +1851,24 @@ void render_atlas(Context& c)
                 TriSetup setup = setup_triangle(xs, ys, /*cullCCW=*/isStroke, sx0, sy0, sx1, sy1);
                 raster_triangle(setup, sy0, sy1, [&](int x, int y, double b0, double b1, double b2) {
                     float4 coverages = interp4(cov[0], cov[1], cov[2], b0, b1, b2);
+                    if (fixedPoint)
+                    {
+                        // fixedpoint_coverage(): int(coverage * ATLAS_R32I_FIXED_POINT_FACTOR), then
+                        // imageAtomicMax / imageAtomicAdd.
+                        int32_t& acc = fixed[static_cast<size_t>(y) * AW + x];
+                        if (isStroke)
+                        {
+                            acc = std::max(acc, static_cast<int32_t>(eval_feathered_stroke(c, coverages) * 65536.f));
+                        }
+                        else
+                        {
+                            float coverage = eval_feathered_fill(c, coverages);
+                            if (!setup.frontFacing)
+                                coverage = -coverage;
+                            acc += static_cast<int32_t>(coverage * 65536.f);
+                        }
+                        return;
+                    }
                     float& texel = c.atlas[static_cast<size_t>(y) * AW + x];
                     float result;
                     if (isStroke)
@@ -1863,6 +1892,14 @@ void render_atlas(Context& c)
         draw(f.atlas_fill_batches[i], false);
     for (uint32_t i = 0; i < f.atlas_stroke_batch_count; ++i)
         draw(f.atlas_stroke_batches[i], true);
+    if (fixedPoint)
+    {
+        // resolve_atlas.glsl:66-70 into the atlas texture the draw pass samples (R16F on Vulkan).
+        for (uint32_t y = 0; y < std::min(d.feather_atlas_content_height, c.atlasHeight); ++y)
+            for (uint32_t x = 0; x < std::min(d.feather_atlas_content_width, AW); ++x)
+                c.atlas[static_cast<size_t>(y) * AW + x] =
+                    half_to_float(float_to_half(static_cast<float>(fixed[static_cast<size_t>(y) * AW + x]) * (1.f / 65536.f)));
+    }
 }
 } // namespace
 
@@ -1872,6 +1909,8 @@ void render_atlas(Context& c)
 extern "C" {
 
 const char* refcpu_last_error(void) { return t_error.c_str(); }
+
+void refcpu_set_atlas_mode(int mode) { g_atlasMode = mode; }
 
 static int with_context(const refcpu_flush* f, int (*fn)(Context&))
 {

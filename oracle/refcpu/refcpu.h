@@ -100,6 +100,15 @@ int refcpu_flush_run(const refcpu_flush* f);
 
 const char* refcpu_last_error(void);
 
+/* How render_atlas accumulates coverage (render_atlas.glsl offers both, per platform):
+ * REFCPU_ATLAS_R16F_BLEND   fixed-function blending into an R16F target, in primitive order,
+ *                           every blend result rounded to fp16 (:233-249; what Vulkan does);
+ * REFCPU_ATLAS_R32I_ATOMIC  16:16 fixed point with image atomics (:146-170, resolve_atlas.glsl:62-71),
+ *                           resolved into the R16F atlas texture. Order-independent; the CUDA
+ *                           backend's method and the default here. */
+enum { REFCPU_ATLAS_R16F_BLEND = 0, REFCPU_ATLAS_R32I_ATOMIC = 1 };
+void refcpu_set_atlas_mode(int mode);
+
 /* ---- helper math exposed for the known-answer tests ---------------------- */
 float refcpu_find_cubic_max_height(const float pts[8], float* out_t);
 float refcpu_measure_cubic_local_curvature(const float pts[8], float t, float desired_spread);

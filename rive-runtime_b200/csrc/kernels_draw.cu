@@ -66,6 +66,7 @@ constexpr uint32_t kMetaUnmultiplied = 1u << 29; // batch has ENABLE_ADVANCED_BL
 constexpr uint32_t kMetaModulatedImage = 1u << 28; // batch has ENABLE_MODULATED_IMAGE and binds a texture
 constexpr uint32_t kMetaClipRect = 1u << 27;       // image meshes: batch has ENABLE_CLIP_RECT
 constexpr uint32_t kMetaClipping = 1u << 26;       // image meshes: batch has ENABLE_CLIPPING
+constexpr uint32_t kMetaRewound = 1u << 24;        // vertices 1 and 2 were exchanged to make the triangle clockwise (image meshes)
 constexpr uint32_t kMetaSimplePaint = 1u << 25;    // set by the rasteriser's prepare step, never stored
 constexpr uint32_t kMetaKindShift = 16;
 
@@ -81,6 +82,12 @@ struct TriAttr // 48 B: attr[c*3 + k] = component c at vertex k
 {
     float attr[12];
 };
+
+struct TriPos // 24 B: fp32 vertex positions in TriGeom's vertex order (exact-interpolation flushes only)
+{
+    float x0, y0, x1, y1, x2, y2;
+};
+static_assert(sizeof(TriPos) == 24, "TriPos");
 
 struct FlushParams
 {
@@ -116,6 +123,7 @@ struct FlushParams
     int32_t debugX, debugY; // RIVECUDA_DEBUG_PIXEL="x,y": printf every accumulate/resolve at this pixel
     const struct ImageSlot* images; // per-flush table of (texture, sampler) for batches that bind one
     uint16_t* pathImageSlots;       // pathID -> index into `images` (written by setup for image paints)
+    TriPos* triPos;                 // non-null: the flush runs raster_tiles_exact_kernel (raster_tiles_exact.cuh)
 };
 
 // A bound image: rivecuda_draw_batch::image_texture + image_sampler.
@@ -750,8 +758,13 @@ __device__ __forceinline__ bool store_triangle(const FlushParams& P,
         if (area2 == 0 || (area2 < 0 && cullCCW))
             ok = false;
     }
+    float px[3] = {xs[0], xs[1], xs[2]}, py[3] = {ys[0], ys[1], ys[2]};
     if (ok && area2 < 0)
     {
+        px[1] = xs[2];
+        px[2] = xs[1];
+        py[1] = ys[2];
+        py[2] = ys[1];
         int32_t t = X[1];
         X[1] = X[2];
         X[2] = t;
@@ -787,7 +800,7 @@ __device__ __forceinline__ bool store_triangle(const FlushParams& P,
     g.y1 = Y[1];
     g.x2 = X[2];
     g.y2 = Y[2];
-    g.meta = meta | kMetaValid;
+    g.meta = meta | kMetaValid | (area2 < 0 ? kMetaRewound : 0u);
     g.aux = aux;
     triGeom[rawTri] = g;
     float4* dst = reinterpret_cast<float4*>(triAttr + rawTri);
@@ -796,6 +809,13 @@ __device__ __forceinline__ bool store_triangle(const FlushParams& P,
         dst[1] = make_float4(attr[4], attr[5], attr[6], attr[7]);
     if (attrComponents > 2)
         dst[2] = make_float4(attr[8], attr[9], attr[10], attr[11]);
+    if (P.triPos != nullptr)
+    {
+        float2* pos = reinterpret_cast<float2*>(P.triPos + rawTri);
+        pos[0] = make_float2(px[0], py[0]);
+        pos[1] = make_float2(px[1], py[1]);
+        pos[2] = make_float2(px[2], py[2]);
+    }
     return true;
 }
 
@@ -1473,6 +1493,7 @@ __global__ void __launch_bounds__(256) sort_tiles_kernel(const uint32_t* __restr
 }
 
 #include "raster_tiles.cuh"
+#include "raster_tiles_exact.cuh"
 
 // ---------------------------------------------------------------------------
 // Host orchestration
@@ -1662,10 +1683,27 @@ int launch_draw_list(rivecuda_ctx* ctx, const rivecuda_flush_desc& desc, const r
     RC_CUDA(cudaMemsetAsync(hugeCount, 0, (static_cast<size_t>(tileCount) * 3 + 4) * sizeof(uint32_t), stream));
     BinTables bins = {smallCounts, bigCounts, nullptr, nullptr, hugeCount, nullptr, 0u};
 
+    // Exact interpolation (raster_tiles_exact.cuh) where a blend can amplify a one-LSB difference
+    // of the destination or a varying is discontinuous / badly conditioned: advanced blend modes,
+    // clip rectangles, image paints and meshes. RIVECUDA_EXACT=0 / 1 forces either rasteriser.
+    bool exact = false;
+    for (uint32_t i = 0; i < batchCount; ++i)
+        if ((batches[i].shader_features & (RIVECUDA_FEATURE_ADVANCED_BLEND | RIVECUDA_FEATURE_CLIP_RECT | RIVECUDA_FEATURE_MODULATED_IMAGE)) != 0u ||
+            batches[i].draw_type == RIVECUDA_DRAW_IMAGE_MESH)
+            exact = true;
+    if (const char* env = getenv("RIVECUDA_EXACT"))
+        exact = env[0] != '0';
+    P.triPos = nullptr;
     TriGeom* triGeom = nullptr;
     TriAttr* triAttr = nullptr;
     if (rawTriangles > 0)
     {
+        if (exact)
+        {
+            if (int s = ctx->triPos.reserve(static_cast<size_t>(rawTriangles) * sizeof(TriPos)))
+                return s;
+            P.triPos = ctx->triPos.as<TriPos>();
+        }
         if (int s = ctx->triGeom.reserve(static_cast<size_t>(rawTriangles) * sizeof(TriGeom)))
             return s;
         if (int s = ctx->triAttr.reserve(static_cast<size_t>(rawTriangles) * sizeof(TriAttr)))
@@ -1783,6 +1821,7 @@ int launch_draw_list(rivecuda_ctx* ctx, const rivecuda_flush_desc& desc, const r
     tail.params = std::make_shared<FlushParams>(P);
     tail.triGeom = triGeom;
     tail.triAttr = triAttr;
+    tail.triPos = P.triPos;
     tail.bins = std::make_shared<BinTables>(bins);
     tail.tileOffsets = tileOffsets;
     tail.tileCounts = tileCounts;
@@ -1823,7 +1862,11 @@ int launch_tail(rivecuda_ctx* ctx)
         cudaMemcpyToSymbol(g_rasterStats, zero, sizeof(zero));
     }
 #endif
-    raster_tiles_kernel<<<tail.tileCount, 256, 0, stream>>>(P, triGeom, static_cast<const TriAttr*>(tail.triAttr), tail.tileOffsets, tail.tileCounts, entries, tail.entryTotal, capacity);
+    if (tail.triPos != nullptr)
+        raster_tiles_exact_kernel<<<tail.tileCount, 256, 0, stream>>>(P, triGeom, static_cast<const TriAttr*>(tail.triAttr), static_cast<const TriPos*>(tail.triPos), tail.tileOffsets,
+                                                                     tail.tileCounts, entries, tail.entryTotal, capacity);
+    else
+        raster_tiles_kernel<<<tail.tileCount, 256, 0, stream>>>(P, triGeom, static_cast<const TriAttr*>(tail.triAttr), tail.tileOffsets, tail.tileCounts, entries, tail.entryTotal, capacity);
     ctx->lastLaunches += 1;
 #ifdef RIVECUDA_STATS
     {
@@ -1887,6 +1930,7 @@ struct AtlasTriangle
     EdgeEq E[3];
     float4 cov[3];
     double invArea2;
+    int32_t bias[3]; // what edge_equations() folded into E[k].C for the top-left rule
     int32_t px0, py0, w, h; // pixel bounds (clipped to the batch scissor); w <= 0 => nothing to draw
     uint32_t isStroke, frontFacing;
 };
@@ -1899,31 +1943,35 @@ __device__ __forceinline__ void atlas_pixel(const FlushParams& P, const AtlasTri
     const int64_t e2 = T.E[2].A * px + T.E[2].B * py + T.E[2].C;
     if ((e0 | e1 | e2) < 0)
         return;
-    // Barycentrics (the top-left bias of at most one unit is far below fp32 resolution here).
-    const float b0 = static_cast<float>(static_cast<double>(e0) * T.invArea2);
-    const float b1 = static_cast<float>(static_cast<double>(e1) * T.invArea2);
-    const float b2 = static_cast<float>(static_cast<double>(e2) * T.invArea2);
-    const float4 c = make_float4(T.cov[0].x * b0 + T.cov[1].x * b1 + T.cov[2].x * b2,
-                                 T.cov[0].y * b0 + T.cov[1].y * b1 + T.cov[2].y * b2,
-                                 T.cov[0].z * b0 + T.cov[1].z * b1 + T.cov[2].z * b2,
-                                 T.cov[0].w * b0 + T.cov[1].w * b1 + T.cov[2].w * b2);
-    // Coverage is accumulated in 16.16 fixed point: integer add / max are associative, so
-    // the atlas is deterministic whatever order the triangles' threads arrive in (the
-    // reference blends in primitive order into an R16F target; fp32 atomics would depend on
-    // scheduling).
+    // Noperspective interpolation as the oracle does it (refcpu_raster.hpp): fp64 barycentrics from
+    // the unbiased edge functions, a0*b0 + a1*b1 + a2*b2 in fp64, rounded to fp32 once.
+    const double b0 = __dmul_rn(static_cast<double>(e0 + T.bias[0]), T.invArea2);
+    // (A re-wound back-facing triangle has its vertices 1 and 2 exchanged: hand the weights back to
+    // the original vertices so that the sum runs in the original order.)
+    const double w1 = __dmul_rn(static_cast<double>(e1 + T.bias[1]), T.invArea2);
+    const double w2 = __dmul_rn(static_cast<double>(e2 + T.bias[2]), T.invArea2);
+    const double b1 = T.frontFacing != 0u ? w1 : w2, b2 = T.frontFacing != 0u ? w2 : w1;
+    auto interp = [&](float a0, float a1, float a2) {
+        return static_cast<float>(__dadd_rn(__dadd_rn(__dmul_rn(static_cast<double>(a0), b0), __dmul_rn(static_cast<double>(a1), b1)), __dmul_rn(static_cast<double>(a2), b2)));
+    };
+    const float4 c = make_float4(interp(T.cov[0].x, T.cov[1].x, T.cov[2].x), interp(T.cov[0].y, T.cov[1].y, T.cov[2].y),
+                                 interp(T.cov[0].z, T.cov[1].z, T.cov[2].z), interp(T.cov[0].w, T.cov[1].w, T.cov[2].w));
+    // render_atlas.glsl:146-170 (@ATLAS_RENDER_TARGET_R32I_ATOMIC_TEXTURE): coverage accumulates as
+    // 16:16 fixed point, int(coverage * 65536), with integer atomics -- associative, so the atlas is
+    // deterministic whatever order the triangles' threads arrive in.
     int* texel = reinterpret_cast<int*>(atlas) + static_cast<size_t>(y) * atlasWidth + x;
     if (T.isStroke != 0u)
     {
-        const float v = eval_feathered_stroke(P.featherLUT, c.x, c.y);
-        if (v > 0.f)
-            atomicMax(texel, __float2int_rn(v * kAtlasFixedOne));
+        const int v = static_cast<int>(eval_feathered_stroke(P.featherLUT, c.x, c.y) * kAtlasFixedOne);
+        if (v > 0)
+            atomicMax(texel, v);
     }
     else
     {
-        float v = eval_feathered_fill(P.featherLUT, c);
+        float v = eval_feathered_fill_exact(P.featherLUT, c);
         if (T.frontFacing == 0u)
             v = -v;
-        atomicAdd(texel, __float2int_rn(v * kAtlasFixedOne));
+        atomicAdd(texel, static_cast<int>(v * kAtlasFixedOne));
     }
 }
 
@@ -2000,12 +2048,15 @@ __global__ void __launch_bounds__(kAtlasWarpsPerBlock * 32) atlas_kernel(FlushPa
                     tmp = Y[1];
                     Y[1] = Y[2];
                     Y[2] = tmp;
-                    const float4 tc = T.cov[1];
-                    T.cov[1] = T.cov[2];
-                    T.cov[2] = tc;
-                    area2 = -area2;
+                    area2 = -area2; // (T.cov stays in the original vertex order: atlas_pixel swaps the weights instead)
                 }
                 edge_equations(X, Y, T.E);
+#pragma unroll
+                for (int e = 0; e < 3; ++e)
+                {
+                    const int32_t dx = X[(e + 2) % 3] - X[(e + 1) % 3], dy = Y[(e + 2) % 3] - Y[(e + 1) % 3];
+                    T.bias[e] = ((dy == 0 && dx > 0) || dy < 0) ? 0 : 1;
+                }
                 const int32_t minX = min(X[0], min(X[1], X[2])), maxX = max(X[0], max(X[1], X[2]));
                 const int32_t minY = min(Y[0], min(Y[1], Y[2])), maxY = max(Y[0], max(Y[1], Y[2]));
                 const int sx1 = min(static_cast<int>(b.scissorR), static_cast<int>(atlasWidth));

@@ -123,6 +123,7 @@ struct PendingTail
     std::shared_ptr<void> params, bins; // FlushParams / BinTables (types private to kernels_draw.cu)
     const void* triGeom = nullptr;
     const void* triAttr = nullptr;
+    const void* triPos = nullptr; // non-null: raster_tiles_exact_kernel
     uint32_t* tileOffsets = nullptr;
     uint32_t* tileCounts = nullptr;
     uint32_t* bigCursors = nullptr;
@@ -162,6 +163,7 @@ struct rivecuda_ctx
     uint32_t atlasWidth = 0, atlasHeight = 0;
 
     // Raster work buffers (grow-only).
+    rivecuda::DeviceBuffer triPos; // fp32 vertex positions per raw triangle (exact-interpolation flushes)
     rivecuda::DeviceBuffer triGeom, triAttr, tileCounts, tileOffsets, tileEntries, batchTable, imageTable,
         scanScratch, clipPlane, pathImageSlots, atlasTable, binCount, binPairs, hugeList, frontEnd;
     uint32_t* pinnedTotals = nullptr; // pinned host words for small D2H results

@@ -16,27 +16,15 @@ pytestmark = pytest.mark.gpu
 MAX_DELTA = 2          # /255, per channel
 MIN_PSNR = 45.0        # dB
 
-# Scenes where a handful of pixels exceed 2/255 for a reason that is understood
-# and documented in DESIGN.md ("Known deviations"); everything else is strict.
-#   name -> (max delta allowed, max number of pixels above 2/255)
-KNOWN_DEVIATIONS = {
-    # The reference interpolates fp32 per-vertex clip-rect distances; this GM draws a
-    # rect with vertices at +-1e6 px, where those values only resolve 1/16 px. We
-    # evaluate the same affine function at the pixel centre, exactly.
-    "cliprectintersections.rvct.xz": (5, 3000),
-    # colorburn / colordodge / HSL blends divide by small numbers: a 1-LSB difference
-    # in the destination (fp16 coverage-plane rounding flips) is amplified.
-    "interleavedfeather.rvct.xz": (8, 8),
-    "c3.rvct.xz": (96, 200),
-    # Nearest-filtered image paints are discontinuous at texel boundaries: uv evaluated at
-    # the pixel centre vs. interpolated from fp32 per-vertex values differs in the 6th
-    # digit, which picks the neighbouring texel at 11 of 1.2 M pixels.
-    "img.rvct.xz": (128, 16),
-    # The artboard clip rect: the reference interpolates fp32 per-vertex clip-rect distances over
-    # the big interior triangles (same class as cliprectintersections above); <= 6 pixels on the
-    # rect's edge differ by 3/255 in some frames.
-    "riv_bullet_man.rvct.xz": (3, 8),
-}
+# No scene is exempt. Two rasterisers share the pipeline:
+#   * raster_tiles_exact_kernel interpolates coverage and varyings operation for operation as
+#     the oracle does (fp64 barycentrics of the snapped vertices, the path's last fragment
+#     decides the paint varyings): its frames are BIT-IDENTICAL to the oracle's. It runs
+#     whenever a flush uses advanced blend modes, clip rectangles, image paints or meshes --
+#     wherever a one-LSB difference could be amplified -- and on request (RIVECUDA_EXACT=1);
+#   * raster_tiles_kernel evaluates coverage planes in fp32: within 1/255 of the oracle.
+# Every scene is rendered both ways: default selection within MAX_DELTA with zero outliers,
+# exact rasteriser identical to the oracle.
 
 
 def psnr(a, b):
@@ -84,12 +72,18 @@ def test_scene_parity(libs, name):
                 assert dth.size == 0 or np.nanmax(dth) <= 2.5e-4
         if fr.desc.grad_data_height:
             assert np.array_equal(fr.grad[:fr.desc.grad_data_height], fg.grad), "colour ramps must be bit-exact"
-    max_delta, max_outliers = KNOWN_DEVIATIONS.get(name, (MAX_DELTA, 0))
     for a, b in zip(ref.frames, got.frames):
         d = np.abs(a.astype(int) - b.astype(int)).max(axis=-1)
-        assert int(d.max()) <= max_delta, f"{name}: max channel delta {int(d.max())}/255"
-        assert int((d > MAX_DELTA).sum()) <= max_outliers, f"{name}: {int((d > MAX_DELTA).sum())} pixels above 2/255"
+        assert int(d.max()) <= MAX_DELTA, f"{name}: max channel delta {int(d.max())}/255 on {int((d > MAX_DELTA).sum())} pixels"
         assert psnr(a, b) >= MIN_PSNR, f"{name}: PSNR {psnr(a, b):.1f} dB"
+    os.environ["RIVECUDA_EXACT"] = "1"
+    try:
+        exact = replay.replay(recs)
+    finally:
+        del os.environ["RIVECUDA_EXACT"]
+    for k, (a, b) in enumerate(zip(ref.frames, exact.frames)):
+        differing = int((a != b).any(axis=-1).sum())
+        assert differing == 0, f"{name}: frame {k}: {differing} pixels of the exact rasteriser's frame differ from the oracle's"
 
 
 def test_c2_full_size_parity_and_properties(libs):
