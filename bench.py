@@ -101,6 +101,26 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": reasons}
 
 
+PLAYER = os.path.join(ROOT, "rive-runtime_b200", "_build", "rive_cuda_player")
+
+
+def reference_front_end(scene: str, frames: int = 12, extra=()):
+    """The reference's OWN CPU front end on this host, single-threaded as the class is:
+    RiveRenderer + RenderContext::flush over the reference's RenderContextNULL (what its
+    tests/bench/draw_pls_path.cpp:25 measures), compiled in place from /root/reference into the
+    scene player (`--null-backend`). None where the player binary was not built."""
+    if not os.path.exists(PLAYER):
+        return None
+    try:
+        out = subprocess.check_output([PLAYER, "--scene", scene, "--null-backend", "--frames", str(frames), *extra], text=True, timeout=300)
+        j = json.loads(out.strip().splitlines()[-1])
+        return {"front_end_ms": j["front_end_min_ms"], "scene_build_ms": j["scene_build_min_ms"], "frames": j["frames"], "cores": 1,
+                "kind": "reference", "what": "RiveRenderer + RenderContext::flush on RenderContextNULL (reference code, built in place), "
+                                             "min over frames, scene construction subtracted"}
+    except Exception as e:  # noqa: BLE001
+        return {"error": str(e)[:200]}
+
+
 def run_reference(args, rank: int) -> None:
     """--impl reference: the reference's pixel stage cannot be built here (GLSL ->
     SPIR-V -> Vulkan/SwiftShader), so this arm times its CPU port,
@@ -114,7 +134,7 @@ def run_reference(args, rank: int) -> None:
     summary = T.summarize(records)
     n_frames = max(summary["frames"], 1)
     cores = os.cpu_count() or 1
-    for _ in range(min(args.warmup, 1)):
+    for _ in range(args.warmup):
         refcpu.replay(records, threads=cores, keep_intermediates=False)
     t0 = time.perf_counter()
     for _ in range(args.steps):
@@ -123,7 +143,7 @@ def run_reference(args, rank: int) -> None:
     fps = args.steps * n_frames / dt
     line = {
         "impl": "reference", "metric": metric, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": min(args.warmup, 1), "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload, "width": summary["width"], "height": summary["height"], "frames_per_step_per_gpu": n_frames,
                    "paths": summary["paths"] // n_frames, "tess_vertices": summary["tess_vertices"] // n_frames,
@@ -131,10 +151,106 @@ def run_reference(args, rank: int) -> None:
                    "parallelism": "host threads of rank 0 (the other ranks exit without work)"},
         "cpu_baseline": {"value": fps, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": f"{args.steps} pass(es) over the workload's {n_frames} full-size frame(s), oracle (CPU "
-                                   "restatement of the reference shaders), all host threads"},
+                                   "restatement of the reference shaders, bit-identical to the reference's shader sources compiled "
+                                   "as C++: tests/test_oracle_glslref_cpu.py), all host threads",
+                         "front_end": reference_front_end("c2") if args.workload == "c2" else None},
         "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
+
+
+def sharded_configs(args, rank: int, local_rank: int, world: int):
+    """BASELINE.json configs[3] and configs[4], the two ways the path shards, measured
+    with `world` ranks (device-timed, max over ranks):
+
+    c4        1000 animation frames at 1080p, frame i -> rank i mod N (sharding.frames_for_rank):
+              each rank uploads and renders only its own frames; no collective on the render path.
+              Then ONE NCCL gather brings every rank's last frame to rank 0, which checks each
+              against its own render of the same frame index (bit-identical).
+    c5_bands  one 16384x16384 frame of 200k paths as N screen bands + one NCCL gather
+              (rive_runtime_b200.band_render); rank 0 also renders the whole frame alone and checks
+              the composite bit for bit."""
+    import torch
+    import torch.distributed as dist
+    from rive_runtime_b200 import band_render, replay as R, sharding, trace as T
+    dev = torch.device("cuda", local_rank)
+    out = {}
+
+    # ---- c4: frames sharded round-robin -------------------------------------------------
+    records = T.parse(WORKLOADS["c4"][1])
+    summary = T.summarize(records)
+    width, height = summary["width"], summary["height"]
+    setup, trace_frames = R.split_frames(records)
+    total_frames = 1000
+    rp = R.Replayer(device=local_rank)
+    result = R.ReplayResult()
+    for r in setup:
+        rp.apply(r, result)
+    frames = []
+    target_id = None
+    for ups, fls in trace_frames:
+        frames.append(([(u.fields["kind"], np.ascontiguousarray(u.data)) for u in ups], [rp.prepare_flush(f.fields["flush"]) for f in fls]))
+        target_id = fls[0].fields["flush"].target_id
+    stream_ptr = ctypes.c_void_p()
+    rp._call("rivecuda_stream", ctypes.byref(stream_ptr))
+    stream = torch.cuda.ExternalStream(stream_ptr.value, device=dev)
+
+    def render(index):
+        ups, fls = frames[index % len(frames)]
+        for kind, data in ups:
+            rp.upload_buffer(kind, data)
+        for pf in fls:
+            rp.flush(pf)
+
+    mine = sharding.frames_for_rank(total_frames, rank, world)
+    for i in mine[:8]:
+        render(i)
+    rp.sync()
+    torch.cuda.synchronize()
+    dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record(stream)
+    for i in mine:
+        render(i)
+    e1.record(stream)
+    rp.sync()
+    wall = time.perf_counter() - t0
+    t = torch.tensor([e0.elapsed_time(e1) / 1e3, wall], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    # The data-plane collective: each rank's last frame -> rank 0 over NVLink.
+    last = torch.from_numpy(rp.read_target(target_id)).to(dev)
+    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    gathered = [torch.empty_like(last) for _ in range(world)] if rank == 0 else None
+    torch.cuda.synchronize()
+    g0.record()
+    dist.gather(last, gathered, dst=0)
+    g1.record()
+    torch.cuda.synchronize()
+    identical = None
+    if rank == 0:
+        identical = True
+        for r in range(world):
+            idx = sharding.frames_for_rank(total_frames, r, world)[-1]
+            render(idx)
+            rp.sync()
+            identical = identical and bool(np.array_equal(rp.read_target(target_id), gathered[r].cpu().numpy()))
+    rp.close()
+    out["c4"] = {"workload": "c4: 1000 frames of the off_road_car.riv state-machine animation at 1920x1080, frame i -> rank i mod N, "
+                             "each frame's inputs uploaded inside the timed region (BASELINE.json configs[3])",
+                 "frames": total_frames, "frames_per_rank": len(mine), "value": total_frames / float(t[0]), "unit": UNIT,
+                 "e2e_value": total_frames / float(t[1]), "device_s_max_over_ranks": float(t[0]),
+                 "gather_ms": g0.elapsed_time(g1), "gather_bytes_per_rank": int(last.numel()), "identical": identical}
+
+    # ---- c5: one huge frame as screen bands + NCCL gather ----------------------------------
+    if not args.no_c5 and os.path.exists(PLAYER):
+        try:
+            line = band_render.run("scene:c5", 1, rank, local_rank, world)
+            if rank == 0:
+                out["c5_bands"] = line
+        except Exception as e:  # noqa: BLE001
+            out["c5_bands"] = {"error": str(e)[:300]}
+    return out
 
 
 def main() -> None:
@@ -145,6 +261,8 @@ def main() -> None:
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-sharded", action="store_true", help="world > 1: skip the c4 / c5_bands sharded configurations")
+    ap.add_argument("--no-c5", action="store_true", help="world > 1: skip c5_bands (records a 370 MB trace on the box)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "cuda" else args.warmup
 
@@ -246,6 +364,33 @@ def main() -> None:
     device_ms = float(t.item())
     value = world * n_frames * args.steps / (device_ms / 1e3)
 
+    # ---- the same with every step's inputs uploaded inside the device-timed region (BASELINE.md
+    # section 3 counts the input H2D; `value` follows the bench contract: inputs resident) ----
+    value_h2d = value
+    if resident:
+        def step_with_uploads():
+            for kind, data in frames[0][0]:
+                rp.upload_buffer(kind, data)
+            step_all_frames()
+        for _ in range(3):
+            step_with_uploads()
+        barrier()
+        s2 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+        e2 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+        for i in range(args.steps):
+            with torch.cuda.stream(stream):
+                l2_flush.fill_(i & 0xff)
+            rp.sync()  # the upload stream is ordered behind the render stream from here on
+            s2[i].record(stream)
+            step_with_uploads()
+            e2[i].record(stream)
+        barrier()
+        ms2 = sum(a.elapsed_time(b) for a, b in zip(s2, e2))
+        t = torch.tensor([ms2], dtype=torch.float64, device=f"cuda:{local_rank}")
+        if distributed:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        value_h2d = world * n_frames * args.steps / (float(t.item()) / 1e3)
+
     # ---- roofline: the dominant kernel (tile raster), CUDA events on its stream --
     rp.lib.rivecuda_set_profiling(rp.ctx, 1)
     raster_ms, setup_ms, tess_ms, launches = [], [], [], 0
@@ -275,11 +420,14 @@ def main() -> None:
     peak, peak_src = measured_peak_gbs()
     traffic = None
     if args.workload == "c2":
-        try:  # dram__bytes_read+write of the same kernel on the same workload, from the committed ncu capture
-            tj = json.load(open(os.path.join(ROOT, "profiles", "raster_traffic.json")))
+        # dram__bytes_read + dram__bytes_write of this kernel on this workload from this round's
+        # `ncu --set full` capture (profiles/r02_raster_traffic.json, written by tools/ncu_summary.py
+        # from the .ncu-rep; its `kernel_sha` must match the library being benchmarked).
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r02_raster_traffic.json")))
             traffic = int(tj["dram_bytes_read"]) + int(tj["dram_bytes_write"])
         except Exception:  # noqa: BLE001
-            pass
+            traffic = None
     achieved = alg_bytes / (raster / 1e3) / 1e9
 
     # ---- e2e: host buffers in, host frame out, through the C ABI ----------------
@@ -374,8 +522,8 @@ def main() -> None:
                      "note": "RawPaths + matrices + colours in (host), RGBA8 frame out (host): rivecuda_front_end_paths (Wang's "
                              "formula counts, warp-scan span allocation, span/contour/path records on the device; byte-identical "
                              "to the reference front end, tests/test_front_end_gpu.py) + the same flush; front_end_ms includes "
-                             "the H2D of the paths and two stream syncs. The reference's CPU front end alone takes ~16 ms for "
-                             "this frame (host/player, one thread)."}
+                             "the H2D of the paths and two stream syncs; cpu_baseline.front_end times the reference's own "
+                             "CPU front end on the same frame."}
 
     # ---- CPU baseline (rank 0, N=1 only): bounded sample of the same workload ---
     cpu = None
@@ -389,8 +537,16 @@ def main() -> None:
             n += 1
         cpu_dt = time.perf_counter() - t0
         cpu = {"value": n * n_frames / cpu_dt, "unit": UNIT, "cores": cores, "kind": "port",
+               "front_end": reference_front_end("c2") if args.workload == "c2" else None,
                "sample": f"{n} pass(es) over the workload's {n_frames} full-size frame(s) on the oracle (CPU restatement of "
-                         "the reference shaders; the reference's own pixel stage needs Vulkan/SwiftShader, unbuildable here)"}
+                         "the reference shaders, bit-identical to the reference's shader sources compiled as C++; the reference's "
+                         "own pixel stage needs Vulkan/SwiftShader, unbuildable here); front_end = the reference's own CPU front "
+                         "end (RiveRenderer + RenderContext::flush, one thread) on the same frame"}
+
+    sharded = None
+    if distributed and not args.no_sharded and args.workload == "c2":
+        rp.sync()
+        sharded = sharded_configs(args, rank, local_rank, world)
 
     if rank == 0:
         inputs = ("inputs resident in HBM" if resident else
@@ -403,6 +559,7 @@ def main() -> None:
                        "paths": summary["paths"] // n_frames, "tess_vertices": summary["tess_vertices"] // n_frames,
                        "raw_triangles": int(tri_count) // n_frames, "tile_entries": int(entry_count) // n_frames,
                        "mpixels_per_s": value * width * height / 1e6, "inputs": inputs,
+                       "value_with_input_h2d": value_h2d,
                        "l2": "256 MiB written between timed iterations (outside the per-step event pairs); "
                              "the per-frame working set (triangle records + tile lists) also exceeds L2 on c2",
                        "parallelism": f"independent frames / artboard instances on {world} GPU(s) (every GPU renders the "
@@ -424,6 +581,10 @@ def main() -> None:
             "cpu_baseline": cpu,
             "clocks": clocks.summary(),
         }
+        if sharded is not None:
+            line["sharded"] = sharded
+            line["config"]["parallelism"] += ("; `sharded` holds the configurations that partition work across the ranks: c4 (1000 frames, "
+                                              "frame i -> rank i mod N) and c5_bands (one 16384^2 frame as screen bands + NCCL gather)")
         print(json.dumps(line), flush=True)
     rp.close()
     if distributed:

@@ -1,0 +1,146 @@
+"""Screen-band sharding of one very large frame over N GPUs (BASELINE.json
+configs[4]): every rank replays the same flush inputs with renderTargetUpdateBounds narrowed
+to its band of whole tile rows; ONE NCCL gather of W x (H/N) x 4 bytes per rank composites the
+frame on rank 0, which checks it bit for bit against its own single-GPU render of the whole
+frame. Used by tools/band_shard_check.py and by bench.py (`c5_bands`, world > 1).
+"""
+import json
+import os
+import subprocess
+import sys
+import time
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import replay as R, sharding, trace as T
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def record_scene(scene: str, out: str, extra) -> None:
+    build = os.path.join(ROOT, "rive-runtime_b200", "_build")
+    env = dict(os.environ, RIVECUDA_LIB=os.path.join(build, "librivecuda_trace.so"), RIVECUDA_TRACE_OUT=out)
+    subprocess.check_call([os.path.join(build, "rive_cuda_player"), "--scene", scene, *extra], env=env,
+                          stdout=subprocess.DEVNULL)
+
+
+class BandRenderer:
+    """One context per rank, kept alive across repetitions so that device allocations
+    (which only grow) happen in the warm-up repetition, not in the timed ones."""
+
+    def __init__(self, records, device, frame_tensor):
+        import ctypes
+        self.records = records
+        self.rp = R.Replayer(device)
+        self.first = True
+        self.prepared = {}
+        sp = ctypes.c_void_p()
+        self.rp._call("rivecuda_stream", ctypes.byref(sp))
+        self.stream = torch.cuda.ExternalStream(sp.value, device=torch.device("cuda", device))
+        self.frame = frame_tensor
+
+    def render(self, band):
+        """Replay every flush restricted to `band` (rows); returns device ms of the flushes."""
+        rp, result = self.rp, R.ReplayResult()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        started = False
+        for r in self.records:
+            if r.tag in (T.CREATE, T.DESTROY, T.TARGET_READ, T.TARGET_DESTROY):
+                continue
+            if r.tag == T.TARGET_CREATE:
+                rp.external_targets[r.fields["id"]] = self.frame.data_ptr()
+            if r.tag == T.FLUSH:
+                if not started:
+                    ev0.record(self.stream)
+                    started = True
+                # The ctypes mirror of a flush (C5: ~9300 draw batches each) is built once; a host
+                # written in C++ passes the reference's own arrays. Only the band changes per call.
+                key = id(r)
+                if key not in self.prepared:
+                    prepared = rp.prepare_flush(r.fields["flush"])
+                    self.prepared[key] = (prepared, prepared.desc)
+                pf, full_desc = self.prepared[key]
+                pf.desc = sharding.restrict_to_band(full_desc, band)
+                rp.flush(pf)
+                continue
+            if not self.first and r.tag not in (T.BUFFER_UNMAP, T.PREPARE_TO_FLUSH, T.POST_FLUSH):
+                continue  # targets, textures, tables and sizes persist across repetitions
+            rp.apply(r, result)
+        ev1.record(self.stream)
+        rp.sync()
+        self.first = False
+        return ev0.elapsed_time(ev1)
+
+    def close(self):
+        self.rp.close()
+
+
+
+def run(src: str, reps: int, rank: int, local: int, world: int, scene_args=()):
+    """Render `src` (a trace path, or scene:NAME recorded on the spot by the scene player) as
+    `world` bands + one gather; returns the measurement dict on rank 0 (None elsewhere).
+    Requires an initialised NCCL process group when world > 1."""
+    path = src
+    if src.startswith("scene:"):
+        path = f"/tmp/band_{src[6:]}.rvct"
+        if local == 0:
+            record_scene(src[6:], path, list(scene_args))
+        if world > 1:
+            dist.barrier()
+    records = T.parse(path)
+    s = T.summarize(records)
+    W, H = s["width"], s["height"]
+    dev = torch.device("cuda", local)
+    band = sharding.band_for_rank(H, rank, world)
+    frame = torch.zeros((H, W, 4), dtype=torch.uint8, device=dev)
+
+    band_ms, gather_ms = [], []
+    composite = None
+    renderer = BandRenderer(records, local, frame)
+    for _ in range(reps + 1):  # first repetition is the warm-up
+        frame.zero_()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t_render = renderer.render(band)
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        composite = sharding.gather_bands(frame[band[0]:band[1]], H, W, dst_rank=0) if world > 1 else frame
+        g1.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([t_render, g0.elapsed_time(g1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        band_ms.append(float(t[0]))
+        gather_ms.append(float(t[1]))
+    band_ms, gather_ms = band_ms[1:], gather_ms[1:]
+    renderer.close()
+
+    line = None
+    if rank == 0:
+        full = torch.zeros((H, W, 4), dtype=torch.uint8, device=dev)
+        single_ms = []
+        single = BandRenderer(records, local, full)
+        for _ in range(reps + 1):
+            full.zero_()
+            single_ms.append(single.render((0, H)))
+        single.close()
+        single_ms = single_ms[1:]
+        identical = bool(torch.equal(full, composite))
+        line = {
+            "workload": src, "width": W, "height": H, "paths": s["paths"], "flushes": s["flushes"], "n_gpus": world,
+            "bands": [sharding.band_for_rank(H, r, world) for r in range(world)],
+            "single_gpu_ms": float(np.mean(single_ms)), "banded_render_ms_max_over_ranks": float(np.mean(band_ms)),
+            "render_ms": float(np.mean(band_ms)),
+            "gather_ms": float(np.mean(gather_ms)), "gather_bytes_per_rank": int(W * (band[1] - band[0]) * 4),
+            "speedup_vs_single": float(np.mean(single_ms)) / (float(np.mean(band_ms)) + float(np.mean(gather_ms))),
+            "composite_identical_to_single_pass": identical, "identical": identical,
+        }
+        del full
+    del frame, composite
+    torch.cuda.empty_cache()
+    if world > 1:
+        dist.barrier()
+    return line
