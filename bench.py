@@ -222,6 +222,7 @@ def sharded_configs(args, rank: int, local_rank: int, world: int):
     last = torch.from_numpy(rp.read_target(target_id)).to(dev)
     g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     gathered = [torch.empty_like(last) for _ in range(world)] if rank == 0 else None
+    dist.gather(last, gathered, dst=0)  # untimed: NCCL sets its peer connections up lazily
     torch.cuda.synchronize()
     g0.record()
     dist.gather(last, gathered, dst=0)

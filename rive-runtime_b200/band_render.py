@@ -97,7 +97,9 @@ def run(src: str, reps: int, rank: int, local: int, world: int, scene_args=()):
     frame = torch.zeros((H, W, 4), dtype=torch.uint8, device=dev)
 
     band_ms, gather_ms = [], []
-    composite = None
+    # The composite lives on rank 0 for the whole measurement: the gather's receive buffers are
+    # its row ranges, and nothing is allocated inside the timed region.
+    composite = torch.empty((H, W, 4), dtype=torch.uint8, device=dev) if (rank == 0 and world > 1) else None
     renderer = BandRenderer(records, local, frame)
     for _ in range(reps + 1):  # first repetition is the warm-up
         frame.zero_()
@@ -107,7 +109,10 @@ def run(src: str, reps: int, rank: int, local: int, world: int, scene_args=()):
         t_render = renderer.render(band)
         g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         g0.record()
-        composite = sharding.gather_bands(frame[band[0]:band[1]], H, W, dst_rank=0) if world > 1 else frame
+        if world > 1:
+            sharding.gather_bands(frame[band[0]:band[1]], H, W, dst_rank=0, out_frame=composite)
+        else:
+            composite = frame
         g1.record()
         torch.cuda.synchronize()
         t = torch.tensor([t_render, g0.elapsed_time(g1)], dtype=torch.float64, device=dev)

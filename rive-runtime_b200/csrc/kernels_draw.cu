@@ -1181,7 +1181,9 @@ __global__ void __launch_bounds__(kScanBlock) scan_reduce_kernel(const uint32_t*
 {
     __shared__ uint32_t s[32];
     const uint32_t i = blockIdx.x * kScanBlock + threadIdx.x;
-    uint32_t v = i < n ? countsA[i] + countsB[i] : 0u;
+    // Lists start on 16-byte boundaries (4 entries): the rasteriser fetches them with bulk
+    // asynchronous copies (TMA), which need 16-byte aligned sources.
+    uint32_t v = i < n ? ((countsA[i] + countsB[i] + 3u) & ~3u) : 0u;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1)
         v += __shfl_down_sync(0xffffffffu, v, o);
@@ -1247,7 +1249,8 @@ __global__ void __launch_bounds__(kScanBlock) scan_apply_kernel(const uint32_t* 
     __shared__ uint32_t s[32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t i = blockIdx.x * kScanBlock + threadIdx.x;
-    const uint32_t v = i < n ? countsA[i] + countsB[i] : 0u;
+    const uint32_t count = i < n ? countsA[i] + countsB[i] : 0u;
+    const uint32_t v = (count + 3u) & ~3u; // padded: see scan_reduce_kernel
     uint32_t incl = v;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1)
@@ -1276,7 +1279,7 @@ __global__ void __launch_bounds__(kScanBlock) scan_apply_kernel(const uint32_t* 
     if (i < n)
     {
         offsets[i] = blockOffsets[blockIdx.x] + s[warp] + incl - v;
-        totals[i] = v;
+        totals[i] = count;
     }
 }
 

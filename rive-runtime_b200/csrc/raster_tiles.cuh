@@ -633,16 +633,18 @@ __device__ __forceinline__ float4 paint_color(const FlushParams& P,
     return color;
 }
 
-// Resolve one path at one pixel (draw_raster_order_path.frag:61-232).
-__device__ __forceinline__ void resolve_path(const FlushParams& P,
-                                             uint32_t meta,
-                                             uint32_t paintX,
-                                             uint32_t paintY,
-                                             float4 solid,
-                                             float coverageCount,
-                                             int px,
-                                             int py,
-                                             PixelState& s)
+// Resolve one path at one pixel (draw_raster_order_path.frag:61-232): everything but the
+// straight-line case below. Out of line: it runs once per path boundary, and kept out of the walk
+// loop its kernel-parameter loads and registers do not burden every triangle visit.
+__device__ __noinline__ uint4 resolve_path_general(const FlushParams& P,
+                                                    uint32_t meta,
+                                                    uint32_t paintX,
+                                                    uint32_t paintY,
+                                                    float4 solid,
+                                                    float coverageCount,
+                                                    int px,
+                                                    int py,
+                                                    PixelState s)
 {
     const uint32_t pathID = meta & 0xffffu;
 #ifdef RIVECUDA_DEBUG
@@ -661,22 +663,6 @@ __device__ __forceinline__ void resolve_path(const FlushParams& P,
             coverage = 1.f - fabsf(fractf(coverage * .5f) * 2.f + -1.f);
         coverage = fminf(coverage, 1.f);
     }
-    if ((meta & kMetaSimplePaint) != 0u)
-    {
-        // The common case, straight-line: premultiplied solid colour, src-over,
-        // no clip / clip rect / image (same arithmetic as the general path below).
-        const float4 dst = unpack_rgba8(s.color);
-        const float a = solid.w * coverage;
-        const float oneMinusA = 1.f - a;
-        const float dither = a != 0.f ? s.dither : 0.f;
-        s.color = pack_rgba8_fast((solid.x * coverage + dst.x * oneMinusA) + dither,
-                                  (solid.y * coverage + dst.y * oneMinusA) + dither,
-                                  (solid.z * coverage + dst.z * oneMinusA) + dither,
-                                  a + dst.w * oneMinusA);
-        return;
-    }
-    // (Keeps the float pixel centre below from being hoisted into the walk loop.)
-    asm volatile("" : "+r"(px), "+r"(py));
     const uint32_t paintType = paintX & 0xfu;
     if (paintType == kPaintTypeClipUpdate)
     {
@@ -689,7 +675,7 @@ __device__ __forceinline__ void resolve_path(const FlushParams& P,
         }
         s.clipCoverage = round_to_half(coverage); // the clip plane stores fp16
         s.clipID = clipID;
-        return;
+        return make_uint4(s.color, __float_as_uint(s.clipCoverage), s.clipID, 0u);
     }
     const uint32_t clipID = paintX >> 16;
     if (clipID != 0u)
@@ -722,6 +708,49 @@ __device__ __forceinline__ void resolve_path(const FlushParams& P,
     const float b = (color.z + dst.z * oneMinusA) + dither;
     const float outA = a + dst.w * oneMinusA;
     s.color = pack_rgba8_fast(r, g, b, outA);
+    return make_uint4(s.color, __float_as_uint(s.clipCoverage), s.clipID, 0u);
+}
+
+__device__ __forceinline__ void resolve_path(const FlushParams& P,
+                                             uint32_t meta,
+                                             uint32_t paintX,
+                                             uint32_t paintY,
+                                             float4 solid,
+                                             float coverageCount,
+                                             int px,
+                                             int py,
+                                             PixelState& s)
+{
+    if ((meta & kMetaSimplePaint) != 0u)
+    {
+        // The common case, straight-line: premultiplied solid colour, src-over, no clip / clip
+        // rect / image (same arithmetic as the general path).
+        float coverage;
+        if ((meta & kMetaClockwiseFill) != 0u)
+        {
+            coverage = clamp01(coverageCount);
+        }
+        else
+        {
+            coverage = fabsf(coverageCount);
+            if ((paintX & kPaintFlagEvenOdd) != 0u)
+                coverage = 1.f - fabsf(fractf(coverage * .5f) * 2.f + -1.f);
+            coverage = fminf(coverage, 1.f);
+        }
+        const float4 dst = unpack_rgba8(s.color);
+        const float a = solid.w * coverage;
+        const float oneMinusA = 1.f - a;
+        const float dither = a != 0.f ? s.dither : 0.f;
+        s.color = pack_rgba8_fast((solid.x * coverage + dst.x * oneMinusA) + dither,
+                                  (solid.y * coverage + dst.y * oneMinusA) + dither,
+                                  (solid.z * coverage + dst.z * oneMinusA) + dither,
+                                  a + dst.w * oneMinusA);
+        return;
+    }
+    const uint4 r = resolve_path_general(P, meta, paintX, paintY, solid, coverageCount, px, py, s);
+    s.color = r.x;
+    s.clipCoverage = __uint_as_float(r.y);
+    s.clipID = r.z;
 }
 
 // draw_mesh.frag:147-234: blend `color` (paint or image colour, before coverage)
@@ -798,10 +827,89 @@ __device__ void resolve_image_mesh(const FlushParams& P, uint32_t meta, uint32_t
     blend_mesh_fragment(color, coverage, (meta & kMetaUnmultiplied) != 0u, true, packed.z, s);
 }
 
+// The fragment kinds that are not plain fills / strokes, out of line so that their code and the
+// kernel parameters they read stay out of the walk loop: returns (coverageCount, coverageStored,
+// colour plane, touched).
+__device__ __noinline__ uint4 fragment_special(const FlushParams& P,
+                                               uint32_t T,
+                                               uint32_t kind,
+                                               float c0,
+                                               float c1,
+                                               float fi,
+                                               float fj,
+                                               uint32_t curMeta,
+                                               uint32_t curPaintX,
+                                               uint32_t curPaintY,
+                                               float4 curSolid,
+                                               float coverageCount,
+                                               float coverageStored,
+                                               int px,
+                                               int py,
+                                               PixelState s,
+                                               uint32_t triMeta)
+{
+    uint32_t touched = 0u;
+    switch (kind)
+    {
+        case kKindFeatherFill:
+        {
+            const float4 p2 = lds_f32x4(T + 64); // plane2, plane3[0]
+            const uint2 p3 = lds_u32x2(T + 80);  // plane3[1..2]
+            const float c2 = p2.x + p2.y * fi + p2.z * fj;
+            const float c3 = p2.w + __uint_as_float(p3.x) * fi + __uint_as_float(p3.y) * fj;
+            coverageCount = coverageStored + eval_feathered_fill(P.featherLUT, make_float4(c0, c1, c2, c3));
+            coverageStored = round_to_half(coverageCount);
+            touched = 1u;
+            break;
+        }
+        case kKindFeatherStroke:
+            coverageCount = fmaxf(eval_feathered_stroke(P.featherLUT, c0, c1), coverageStored);
+            coverageStored = round_to_half(coverageCount);
+            touched = 1u;
+            break;
+        case kKindAtlasBlit:
+            resolve_atlas_blit(P, curMeta, curPaintX, curPaintY, curSolid, c0, c1, px, py, s);
+            break;
+        case kKindImageMesh:
+            // Consecutive meshes share "path" 0, so the flags come from the triangle itself.
+            resolve_image_mesh(P, triMeta, lds_u32(T + 88), c0, c1, lds_f32(T + 64), px, py, s);
+            break;
+        default:
+            break;
+    }
+    return make_uint4(__float_as_uint(coverageCount), __float_as_uint(coverageStored), s.color, touched);
+}
+
+// ---- bulk asynchronous copies (TMA, cp.async.bulk) of the tile's triangle-id list ----------
+// The list is contiguous and 16-byte aligned (scan_reduce_kernel): one elected thread asks the
+// TMA unit for the next chunk of ids while the CTA walks the current one; completion is
+// signalled on an mbarrier in shared memory.
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void tma_load_1d(uint32_t dstShared, const void* srcGlobal, uint32_t bytes, uint32_t bar)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dstShared), "l"(srcGlobal), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    asm volatile("{\n"
+                 ".reg .pred p;\n"
+                 "WAIT_%=:\n"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+                 "@!p bra WAIT_%=;\n"
+                 "}\n" ::"r"(bar),
+                 "r"(parity)
+                 : "memory");
+}
+
 #ifndef RIVECUDA_RASTER_MIN_BLOCKS
 #define RIVECUDA_RASTER_MIN_BLOCKS 4
 #endif
-__global__ void __launch_bounds__(256, RIVECUDA_RASTER_MIN_BLOCKS) raster_tiles_kernel(FlushParams P,
+__global__ void __launch_bounds__(256, RIVECUDA_RASTER_MIN_BLOCKS) raster_tiles_kernel(const __grid_constant__ FlushParams P,
                                                               const TriGeom* __restrict__ triGeom,
                                                               const TriAttr* __restrict__ triAttr,
                                                               const uint32_t* __restrict__ tileOffsets,
@@ -811,6 +919,8 @@ __global__ void __launch_bounds__(256, RIVECUDA_RASTER_MIN_BLOCKS) raster_tiles_
                                                               uint32_t entryCapacity)
 {
     __shared__ __align__(16) Prepared s_prep[kRasterChunk];
+    __shared__ __align__(16) uint32_t s_ids[2][kRasterChunk]; // the list, chunk by chunk, double-buffered (TMA destination)
+    __shared__ __align__(8) uint64_t s_bar[2];
     // The tile lists did not fit the buffer they were given: nothing has been written to
     // them and nothing may be drawn; the host re-runs scatter / sort / raster with a larger
     // buffer (resolve_pending_flush). The target is untouched.
@@ -825,8 +935,13 @@ __global__ void __launch_bounds__(256, RIVECUDA_RASTER_MIN_BLOCKS) raster_tiles_
     const int tileX = static_cast<int>(tile % P.tilesX) + P.tileX0, tileY = static_cast<int>(tile / P.tilesX) + P.tileY0;
     const int originX = tileX << kTileSizeLog2, originY = tileY << kTileSizeLog2;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int i = (warp & 1) * 8 + (lane & 7), j = (warp >> 1) * 4 + (lane >> 3);
-    const float fi = static_cast<float>(i), fj = static_cast<float>(j);
+    int i = (warp & 1) * 8 + (lane & 7), j = (warp >> 1) * 4 + (lane >> 3);
+    float fi = static_cast<float>(i), fj = static_cast<float>(j);
+    // Opaque to the compiler: kept in registers for the walk loop instead of being re-derived
+    // from the thread id at every triangle visit.
+#ifndef RIVECUDA_NO_PIN
+    asm volatile("" : "+r"(i), "+r"(j), "+f"(fi), "+f"(fj));
+#endif
     const int px = originX + i, py = originY + j;
     const bool inBounds = px >= P.boundsL && px < P.boundsR && py >= P.boundsT && py < P.boundsB;
 
@@ -839,10 +954,27 @@ __global__ void __launch_bounds__(256, RIVECUDA_RASTER_MIN_BLOCKS) raster_tiles_
         const float v1 = fractf(0.06711056f * (px + .5f) + 0.00583715f * (py + .5f));
         s.dither = fractf(52.9829189f * v1) * P.ditherScale + P.ditherBias;
     }
+    // The framebuffer is read (preserve) and written in 128-bit pieces: of every four horizontally
+    // adjacent lanes the first moves the four pixels (LDG.128 / STG.128) and a warp shuffle
+    // distributes / collects them. Rows of a target whose width is a multiple of 4 pixels are 16-byte
+    // aligned at every tile column; partially covered groups fall back to 32-bit accesses.
+    const bool groupInBounds = ((__ballot_sync(0xffffffffu, inBounds) >> (lane & ~3)) & 0xfu) == 0xfu;
+    const bool vectorised = (P.targetWidth & 3u) == 0u && groupInBounds;
     if (P.loadAction == RIVECUDA_LOAD_CLEAR)
+    {
         s.color = P.clearColorPremulRGBA;
+    }
     else
-        s.color = inBounds ? P.target[static_cast<size_t>(py) * P.targetWidth + px] : 0u;
+    {
+        uint4 quad = make_uint4(0u, 0u, 0u, 0u);
+        if (vectorised && (lane & 3) == 0)
+            quad = *reinterpret_cast<const uint4*>(P.target + static_cast<size_t>(py) * P.targetWidth + px);
+        const int leader = lane & ~3;
+        const uint32_t q0 = __shfl_sync(0xffffffffu, quad.x, leader), q1 = __shfl_sync(0xffffffffu, quad.y, leader);
+        const uint32_t q2 = __shfl_sync(0xffffffffu, quad.z, leader), q3 = __shfl_sync(0xffffffffu, quad.w, leader);
+        const int k = lane & 3;
+        s.color = vectorised ? (k == 0 ? q0 : (k == 1 ? q1 : (k == 2 ? q2 : q3))) : (inBounds ? P.target[static_cast<size_t>(py) * P.targetWidth + px] : 0u);
+    }
 
     const uint32_t* list = entries + tileOffsets[tile];
 
@@ -856,13 +988,26 @@ __global__ void __launch_bounds__(256, RIVECUDA_RASTER_MIN_BLOCKS) raster_tiles_
     uint32_t prepAddr = static_cast<uint32_t>(__cvta_generic_to_shared(s_prep));
     asm volatile("" : "+r"(prepAddr)); // opaque: computed once, not re-derived from %cluster_ctaid per visit
 
-    for (uint32_t base = 0; base < n; base += kRasterChunk)
+    const uint32_t idsAddr = static_cast<uint32_t>(__cvta_generic_to_shared(&s_ids[0][0]));
+    const uint32_t barAddr = static_cast<uint32_t>(__cvta_generic_to_shared(&s_bar[0]));
+    if (threadIdx.x == 0)
+    {
+        mbar_init(barAddr, 1u);
+        mbar_init(barAddr + 8u, 1u);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        if (n != 0u)
+            tma_load_1d(idsAddr, list, (min(static_cast<uint32_t>(kRasterChunk), n) * 4u + 15u) & ~15u, barAddr);
+    }
+    uint32_t chunkIndex = 0u;
+    for (uint32_t base = 0; base < n; base += kRasterChunk, ++chunkIndex)
     {
         const uint32_t chunk = min(static_cast<uint32_t>(kRasterChunk), n - base);
-        __syncthreads(); // every warp is done with the previous chunk
+        const uint32_t buf = chunkIndex & 1u;
+        __syncthreads(); // every warp is done with the previous chunk (and, first time round, sees the barriers)
+        mbar_wait(barAddr + buf * 8u, (chunkIndex >> 1) & 1u);
         if (threadIdx.x < chunk)
         {
-            const uint32_t t = __ldg(list + base + threadIdx.x);
+            const uint32_t t = s_ids[buf][threadIdx.x];
             TriGeom g;
             const uint4* src = reinterpret_cast<const uint4*>(triGeom + t);
             *reinterpret_cast<uint4*>(&g) = __ldg(src);
@@ -876,6 +1021,11 @@ __global__ void __launch_bounds__(256, RIVECUDA_RASTER_MIN_BLOCKS) raster_tiles_
 #endif
         }
         __syncthreads();
+        // Everyone has consumed this chunk's ids and has passed the other buffer's barrier phase:
+        // fetch the next chunk while this one is walked.
+        if (threadIdx.x == 0 && base + kRasterChunk < n)
+            tma_load_1d(idsAddr + (buf ^ 1u) * static_cast<uint32_t>(kRasterChunk * 4), list + base + kRasterChunk,
+                        (min(static_cast<uint32_t>(kRasterChunk), n - base - kRasterChunk) * 4u + 15u) & ~15u, barAddr + (buf ^ 1u) * 8u);
         // Each warp visits only the entries whose block mask names it.
         for (uint32_t sub = 0; sub < chunk; sub += 32)
         {
@@ -960,45 +1110,34 @@ __global__ void __launch_bounds__(256, RIVECUDA_RASTER_MIN_BLOCKS) raster_tiles_
                 }
                 const float4 p1 = lds_f32x4(T + 48); // plane1, meta
                 const float c1 = p1.x + p1.y * fi + p1.z * fj;
-                switch (kind)
+                if (kind == kKindStroke)
                 {
-                    case kKindStroke:
-                        coverageCount = fmaxf(fminf(c0, c1), coverageStored);
-                        coverageStored = round_to_half(coverageCount);
-                        touched = true;
-                        break;
-                    case kKindFeatherFill:
-                    {
-                        const float4 p2 = lds_f32x4(T + 64); // plane2, plane3[0]
-                        const uint2 p3 = lds_u32x2(T + 80);  // plane3[1..2]
-                        const float c2 = p2.x + p2.y * fi + p2.z * fj;
-                        const float c3 = p2.w + __uint_as_float(p3.x) * fi + __uint_as_float(p3.y) * fj;
-                        coverageCount = coverageStored + eval_feathered_fill(P.featherLUT, make_float4(c0, c1, c2, c3));
-                        coverageStored = round_to_half(coverageCount);
-                        touched = true;
-                        break;
-                    }
-                    case kKindFeatherStroke:
-                        coverageCount = fmaxf(eval_feathered_stroke(P.featherLUT, c0, c1), coverageStored);
-                        coverageStored = round_to_half(coverageCount);
-                        touched = true;
-                        break;
-                    case kKindAtlasBlit:
-                        resolve_atlas_blit(P, curMeta, curPaintX, curPaintY, curSolid, c0, c1, px, py, s);
-                        break;
-                    case kKindImageMesh:
-                        // Consecutive meshes share "path" 0, so the flags come
-                        // from the triangle itself.
-                        resolve_image_mesh(P, __float_as_uint(p1.w), lds_u32(T + 88), c0, c1, lds_f32(T + 64), px, py, s);
-                        break;
-                    default:
-                        break;
+                    coverageCount = fmaxf(fminf(c0, c1), coverageStored);
+                    coverageStored = round_to_half(coverageCount);
+                    touched = true;
+                    continue;
                 }
+                // Feathers, atlas blits, image meshes: out of line (fragment_special).
+                const uint4 r = fragment_special(P, T, kind, c0, c1, fi, fj, curMeta, curPaintX, curPaintY, curSolid, coverageCount, coverageStored, px, py, s, __float_as_uint(p1.w));
+                coverageCount = __uint_as_float(r.x);
+                coverageStored = __uint_as_float(r.y);
+                s.color = r.z;
+                touched = touched || r.w != 0u;
             }
         }
     }
     if (touched)
         resolve_path(P, curMeta, curPaintX, curPaintY, curSolid, coverageCount, px, py, s);
-    if (inBounds)
-        P.target[static_cast<size_t>(py) * P.targetWidth + px] = s.color;
+    {
+        const uint32_t c1 = __shfl_down_sync(0xffffffffu, s.color, 1), c2 = __shfl_down_sync(0xffffffffu, s.color, 2), c3 = __shfl_down_sync(0xffffffffu, s.color, 3);
+        if (vectorised)
+        {
+            if ((lane & 3) == 0)
+                *reinterpret_cast<uint4*>(P.target + static_cast<size_t>(py) * P.targetWidth + px) = make_uint4(s.color, c1, c2, c3);
+        }
+        else if (inBounds)
+        {
+            P.target[static_cast<size_t>(py) * P.targetWidth + px] = s.color;
+        }
+    }
 }

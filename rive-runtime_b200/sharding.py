@@ -50,31 +50,34 @@ def restrict_to_band(desc: T.FlushDesc, band: Tuple[int, int]) -> T.FlushDesc:
     return d
 
 
-def gather_bands(local_rows, height: int, width: int, dst_rank: int = 0, group=None):
-    """Gather each rank's band (a [rows, width, 4] uint8 tensor on the rank's
-    device -- CUDA with NCCL, CPU with gloo) into the full frame on dst_rank.
-    Bands may differ in height by one tile row, so rows are padded to the
-    largest band for the collective."""
+def gather_bands(local_rows, height: int, width: int, dst_rank: int = 0, group=None, out_frame=None):
+    """Gather each rank's band (a [rows, width, 4] uint8 tensor on the rank's device -- CUDA
+    with NCCL over NVLink, CPU with gloo) into the full frame on dst_rank.
+
+    When every band has the same number of rows (the usual case: whole tile rows divide evenly),
+    the collective lands each band directly in its rows of the composite -- the receive buffers
+    ARE row ranges of `out_frame` (allocated here if not given), no staging copy on either side.
+    Otherwise rows are padded to the tallest band and copied out afterwards."""
     import torch
     import torch.distributed as dist
 
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
     bands = [band_for_rank(height, r, world) for r in range(world)]
-    max_rows = max(b[1] - b[0] for b in bands)
+    rows = [b[1] - b[0] for b in bands]
+    frame = None
+    if rank == dst_rank:
+        frame = out_frame if out_frame is not None else torch.empty((height, width, 4), dtype=torch.uint8, device=local_rows.device)
+    if len(set(rows)) == 1:
+        dist.gather(local_rows.contiguous(), [frame[r0:r1] for r0, r1 in bands] if rank == dst_rank else None, dst=dst_rank, group=group)
+        return frame
+    max_rows = max(rows)
     padded = torch.zeros((max_rows, width, 4), dtype=torch.uint8, device=local_rows.device)
     padded[: local_rows.shape[0]] = local_rows
-    out = None
-    if rank == dst_rank:
-        out = [torch.empty_like(padded) for _ in range(world)]
-    if dist.get_backend(group) == "nccl":
-        # NCCL gather over NVLink; all ranks participate.
-        dist.gather(padded, out, dst=dst_rank, group=group)
-    else:
-        dist.gather(padded, out, dst=dst_rank, group=group)
+    out = [torch.empty_like(padded) for _ in range(world)] if rank == dst_rank else None
+    dist.gather(padded, out, dst=dst_rank, group=group)
     if rank != dst_rank:
         return None
-    frame = torch.empty((height, width, 4), dtype=torch.uint8, device=local_rows.device)
     for r, (r0, r1) in enumerate(bands):
         frame[r0:r1] = out[r][: r1 - r0]
     return frame
