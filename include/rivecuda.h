@@ -368,6 +368,24 @@ int rivecuda_front_end_paths(rivecuda_ctx* ctx,
                              uint32_t frame_height,
                              rivecuda_front_end_result* result);
 
+/* ---- screen-band sharding of one frame over the GPUs of one box --------- */
+
+/* One very large frame is partitioned into horizontal bands of whole 16-pixel tile rows, one per
+ * GPU: every rank's RenderContext receives the identical flushes with renderTargetUpdateBounds
+ * narrowed to its band (rivecuda_band_rows), and ONE NCCL exchange over NVLink lands every
+ * band in its rows of the root rank's target (rivecuda_band_gather) -- no staging copy: the
+ * receive buffers are row ranges of the target itself. One process (or thread) per GPU; the
+ * 128-byte id is NCCL's ncclUniqueId, created by rank 0 and handed to the other ranks by the
+ * host application (file, socket, environment...).
+ * There is no reference counterpart: the reference's backends drive one GPU. */
+#define RIVECUDA_BAND_ID_BYTES 128
+int rivecuda_band_unique_id(void* out_id);
+int rivecuda_band_init(rivecuda_ctx* ctx, uint32_t rank, uint32_t count, const void* unique_id);
+/* Rows [row0, row1) of a target of `target_height` rows that `rank` of `count` renders. */
+int rivecuda_band_rows(uint32_t target_height, uint32_t rank, uint32_t count, uint32_t* out_row0, uint32_t* out_row1);
+/* Enqueued on the context's render stream behind the flushes issued so far. */
+int rivecuda_band_gather(rivecuda_ctx* ctx, rivecuda_target* target, uint32_t root_rank);
+
 /* ---- introspection (parity tests, bench) --------------------------------- */
 
 /* Copy bytes [offset, offset + size) of the current device slot of a buffer ring. */

@@ -158,6 +158,7 @@ void rivecuda_destroy(rivecuda_ctx* ctx)
         return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    rivecuda::band_destroy(ctx);
     for (auto& ring : ctx->rings)
     {
         for (int i = 0; i < kRingSize; ++i)

@@ -26,6 +26,7 @@ constexpr int kSubpixelBits = 8;     // vertex snapping, like the oracle
 
 // Sets the thread-local error string returned by rivecuda_last_error().
 int set_error(const char* fmt, ...);
+void band_destroy(rivecuda_ctx* ctx); // rivecuda_band.cu: releases the context's NCCL communicator, if any
 int check_cuda(cudaError_t err, const char* what);
 
 #define RC_CUDA(CALL)                                                          \
@@ -141,6 +142,9 @@ struct rivecuda_ctx
     PendingTail pendingTail;
     bool uploadsPending = false; // buffer uploads enqueued on copyStream since the last flush
     int smCount = 148;
+    // Screen-band sharding (rivecuda_band_*): NCCL communicator over the GPUs that share a frame.
+    void* bandComm = nullptr;
+    uint32_t bandRank = 0, bandCount = 1;
 
     rivecuda::BufferRing rings[RIVECUDA_BUFFER_KIND_COUNT];
 

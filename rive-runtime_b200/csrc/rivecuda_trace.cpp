@@ -460,6 +460,25 @@ int rivecuda_stream(rivecuda_ctx*, void** out)
     return 0;
 }
 
+// Band sharding: the recorder runs on one "rank"; it records nothing for these calls.
+int rivecuda_band_unique_id(void* out_id)
+{
+    memset(out_id, 0, RIVECUDA_BAND_ID_BYTES);
+    return 0;
+}
+int rivecuda_band_init(rivecuda_ctx*, uint32_t, uint32_t, const void*) { return 0; }
+int rivecuda_band_rows(uint32_t target_height, uint32_t rank, uint32_t count, uint32_t* out_row0, uint32_t* out_row1)
+{
+    if (count == 0 || rank >= count)
+        return fail("rivecuda_band_rows: bad arguments");
+    const uint64_t tileRows = (target_height + 15) / 16;
+    const uint64_t t0 = tileRows * rank / count * 16, t1 = tileRows * (rank + 1) / count * 16;
+    *out_row0 = static_cast<uint32_t>(t0 < target_height ? t0 : target_height);
+    *out_row1 = static_cast<uint32_t>(t1 < target_height ? t1 : target_height);
+    return 0;
+}
+int rivecuda_band_gather(rivecuda_ctx*, rivecuda_target*, uint32_t) { return 0; }
+
 int rivecuda_set_profiling(rivecuda_ctx*, int) { return 0; }
 
 int rivecuda_get_flush_timings(rivecuda_ctx*, rivecuda_flush_timings* out)

@@ -129,6 +129,8 @@ void TestingWindowCUDA::endFrame(std::vector<uint8_t>* pixelData)
         return;
     }
     flushPLSContext(nullptr);
+    // Band sharding: one NCCL exchange composites the ranks' bands in rank 0's target.
+    m_renderContext->static_impl_cast<RenderContextCUDAImpl>()->gatherBands(m_renderTarget.get(), 0);
     if (m_pathDump != nullptr)
         m_pathDump->active = false; // only the first frame is dumped
     if (pixelData != nullptr)

@@ -231,7 +231,41 @@ std::unique_ptr<RenderContext> RenderContextCUDAImpl::MakeContext(
     }
     std::unique_ptr<RenderContextCUDAImpl> impl(
         new RenderContextCUDAImpl(abi, ctx));
+    if (options.bandCount > 1)
+    {
+        if (options.bandUniqueId == nullptr || options.bandRank >= options.bandCount ||
+            abi.band_init(ctx, options.bandRank, options.bandCount, options.bandUniqueId) != 0)
+        {
+            fprintf(stderr, "RenderContextCUDAImpl: band sharding (rank %u of %u) failed: %s\n", options.bandRank, options.bandCount, abi.last_error());
+            return nullptr;
+        }
+        impl->m_bandRank = options.bandRank;
+        impl->m_bandCount = options.bandCount;
+    }
     return std::make_unique<RenderContext>(std::move(impl));
+}
+
+bool RenderContextCUDAImpl::MakeBandUniqueId(const ContextOptions& options, uint8_t outId[128])
+{
+    const RiveCudaABI& abi = RiveCudaABI::Load(options.abiLibraryPath);
+    if (abi.band_unique_id(outId) != 0)
+    {
+        fprintf(stderr, "RenderContextCUDAImpl: rivecuda_band_unique_id failed: %s\n", abi.last_error());
+        return false;
+    }
+    return true;
+}
+
+bool RenderContextCUDAImpl::gatherBands(RenderTargetCUDA* target, uint32_t rootRank)
+{
+    if (m_bandCount <= 1)
+        return true;
+    if (m_abi.band_gather(m_ctx, target->handle(), rootRank) != 0)
+    {
+        fprintf(stderr, "RenderContextCUDAImpl: rivecuda_band_gather failed: %s\n", m_abi.last_error());
+        return false;
+    }
+    return true;
 }
 
 RenderContextCUDAImpl::RenderContextCUDAImpl(const RiveCudaABI& abi,
@@ -561,6 +595,18 @@ void RenderContextCUDAImpl::flush(const FlushDescriptor& desc)
     d.update_bounds[1] = desc.renderTargetUpdateBounds.top;
     d.update_bounds[2] = desc.renderTargetUpdateBounds.right;
     d.update_bounds[3] = desc.renderTargetUpdateBounds.bottom;
+    if (m_bandCount > 1)
+    {
+        // Screen-band sharding: this rank touches only its band's rows (the tile grid, binning
+        // and rasterisation follow the update bounds; patches that cannot reach them are
+        // dropped before their vertices are shaded).
+        uint32_t row0 = 0, row1 = 0;
+        m_abi.band_rows(desc.renderTarget->height(), m_bandRank, m_bandCount, &row0, &row1);
+        d.update_bounds[1] = std::max<int32_t>(d.update_bounds[1], static_cast<int32_t>(row0));
+        d.update_bounds[3] = std::min<int32_t>(d.update_bounds[3], static_cast<int32_t>(row1));
+        if (d.update_bounds[3] < d.update_bounds[1])
+            d.update_bounds[3] = d.update_bounds[1];
+    }
     d.feather_atlas_texture_width = desc.featherAtlasTextureWidth;
     d.feather_atlas_texture_height = desc.featherAtlasTextureHeight;
     d.feather_atlas_content_width = desc.featherAtlasContentWidth;

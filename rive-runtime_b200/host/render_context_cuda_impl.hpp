@@ -106,7 +106,21 @@ public:
         // Path of the shared library that implements include/rivecuda.h.
         // nullptr => $RIVECUDA_LIB, else "librivecuda.so".
         const char* abiLibraryPath = nullptr;
+        // Screen-band sharding of every frame over `bandCount` GPUs of one box (SURVEY.md 8e,
+        // BASELINE.json configs[4]): this context renders only the rows of band `bandRank`
+        // (whole tile rows); gatherBands() composites the frame on one rank with a single
+        // NCCL exchange over NVLink. bandUniqueId: the 128-byte NCCL id rank 0 obtained from
+        // MakeBandUniqueId() and passed to the other ranks (one process or thread per GPU).
+        uint32_t bandRank = 0;
+        uint32_t bandCount = 1;
+        const void* bandUniqueId = nullptr;
     };
+    static bool MakeBandUniqueId(const ContextOptions&, uint8_t outId[128]);
+    // After the frame's flushes: lands every rank's band in its rows of `rootRank`'s target.
+    // Asynchronous (render stream); a read-back of the target waits for it.
+    bool gatherBands(RenderTargetCUDA*, uint32_t rootRank = 0);
+    uint32_t bandRank() const { return m_bandRank; }
+    uint32_t bandCount() const { return m_bandCount; }
 
     static std::unique_ptr<RenderContext> MakeContext(const ContextOptions&);
     static std::unique_ptr<RenderContext> MakeContext()
@@ -220,6 +234,7 @@ private:
 
     const RiveCudaABI& m_abi;
     rivecuda_ctx* m_ctx;
+    uint32_t m_bandRank = 0, m_bandCount = 1;
     std::vector<rivecuda_draw_batch> m_batchScratch;
     std::vector<rivecuda_atlas_batch> m_atlasScratch;
     std::chrono::steady_clock::time_point m_localEpoch =

@@ -200,6 +200,36 @@ def test_band_sharding_over_two_gpus_with_nccl_gather():
     assert line["composite_identical_to_single_pass"] and line["n_gpus"] == 2
 
 
+def test_cxx_host_band_mode_over_two_gpus(libs):
+    """Band sharding from the C++ host, no Python on the data path: two rive_cuda_player
+    processes (RenderContextCUDAImpl::ContextOptions{bandRank, bandCount}), one per GPU, render
+    the bands of the same frame and rivecuda_band_gather (NCCL send / recv straight into the root
+    target's rows) composites it; rank 0's frame must equal the single-process render bit for bit."""
+    import subprocess
+    import tempfile
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    player = os.path.join(root, "rive-runtime_b200", "_build", "rive_cuda_player")
+    if not os.path.exists(player):
+        pytest.skip("scene player not built (needs /root/reference at build time)")
+    with tempfile.TemporaryDirectory() as tmp:
+        scene = ["--scene", "c3", "--width", "1920", "--height", "1080", "--paths", "600"]
+        single = os.path.join(tmp, "single.rgba")
+        subprocess.run([player, *scene, "--out", single], check=True, capture_output=True, timeout=300)
+        idfile = os.path.join(tmp, "nccl.id")
+        procs = [subprocess.Popen([player, *scene, "--device", str(r), "--band-rank", str(r), "--band-count", "2", "--band-id-file", idfile,
+                                   "--out", os.path.join(tmp, f"band{r}.rgba")], stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+                 for r in range(2)]
+        for p in procs:
+            out, err = p.communicate(timeout=300)
+            assert p.returncode == 0, err.decode()[-2000:]
+        want = np.fromfile(single, dtype=np.uint8)
+        got = np.fromfile(os.path.join(tmp, "band0.rgba"), dtype=np.uint8)
+        assert want.size == 1920 * 1080 * 4 and np.array_equal(want, got)
+
+
 @pytest.mark.parametrize("scene,trace_name,size", [("gm:beziers", "beziers", (800, 400)), ("c1", "c1", (1600, 1600)),
                                                    ("img", "img", (960, 1280)), ("gm:feather_shapes", "feather_shapes", None)])
 def test_reference_front_end_drives_the_cuda_backend(libs, scene, trace_name, size):
