@@ -85,8 +85,10 @@ std::unique_ptr<rive::Renderer> TestingWindowCUDA::beginFrame(
         .wireframe = options.wireframe,
         .fillsDisabled = options.fillsDisabled,
         .strokesDisabled = options.strokesDisabled,
-        .clockwiseFillOverride = false,
+        .clockwiseFillOverride = options.clockwiseFillOverride || m_clockwiseFillOverride,
     };
+    frameDescriptor.virtualTileWidth = m_virtualTileWidth;
+    frameDescriptor.virtualTileHeight = m_virtualTileHeight;
     if (m_gpuFrontEnd)
     {
         auto pathRenderer = std::make_unique<CudaPathRenderer>(m_renderContext->static_impl_cast<RenderContextCUDAImpl>(),

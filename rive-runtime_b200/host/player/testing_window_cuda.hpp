@@ -37,9 +37,20 @@ public:
     // aborts if the frame contained anything but plain fills and strokes.
     void setGpuFrontEnd(bool enabled) { m_gpuFrontEnd = enabled; }
 
+    // FrameDescriptor options the reference exposes per frame: every fill drawn with
+    // the clockwise rule; the frame drawn virtual tile by virtual tile.
+    void setClockwiseFillOverride(bool enabled) { m_clockwiseFillOverride = enabled; }
+    void setVirtualTiles(uint32_t width, uint32_t height)
+    {
+        m_virtualTileWidth = width;
+        m_virtualTileHeight = height;
+    }
+
 private:
     struct PathDumpSink* m_pathDump = nullptr;
     bool m_gpuFrontEnd = false;
+    bool m_clockwiseFillOverride = false;
+    uint32_t m_virtualTileWidth = 0, m_virtualTileHeight = 0;
     class rive::gpu::CudaPathRenderer* m_pathRenderer = nullptr; // owned by beginFrame()'s caller
     std::unique_ptr<rive::gpu::RenderContext> m_renderContext;
     rive::rcp<rive::gpu::RenderTargetCUDA> m_renderTarget;

@@ -679,15 +679,49 @@ void RenderContextCUDAImpl::flush(const FlushDescriptor& desc)
     const rivecuda_atlas_batch* strokes =
         m_atlasScratch.data() + desc.featherAtlasFillBatchCount;
 
-    ABI_CHECK(m_abi.flush(
-        m_ctx,
-        &d,
-        m_batchScratch.data(),
-        static_cast<uint32_t>(m_batchScratch.size()),
-        fills,
-        static_cast<uint32_t>(desc.featherAtlasFillBatchCount),
-        strokes,
-        static_cast<uint32_t>(desc.featherAtlasStrokeBatchCount)));
+    // FrameDescriptor::virtualTileWidth / Height (gpu.hpp:1336-1347; the Vulkan backend's loop is
+    // render_context_vulkan_impl.cpp:3378-3560): the flush is drawn virtual tile by virtual tile,
+    // each as a pass of its own restricted to the tile, so that other work can pre-empt the GPU
+    // between tiles. Pixels are those of the single pass (restricting the update bounds never
+    // changes what is drawn inside them: tests/test_parity_gpu.py band / virtual-tile tests).
+    const int32_t boundsL = d.update_bounds[0], boundsT = d.update_bounds[1], boundsR = d.update_bounds[2], boundsB = d.update_bounds[3];
+    int32_t tileW = boundsR - boundsL, tileH = boundsB - boundsT;
+    if (desc.virtualTileWidth != 0 && desc.virtualTileHeight != 0)
+    {
+        tileW = static_cast<int32_t>(desc.virtualTileWidth);
+        tileH = static_cast<int32_t>(desc.virtualTileHeight);
+    }
+    bool flushed = false;
+    for (int32_t y = boundsT; (y < boundsB || !flushed) && tileH > 0; y += tileH)
+    {
+        for (int32_t x = boundsL; (x < boundsR || !flushed) && tileW > 0; x += tileW)
+        {
+            d.update_bounds[0] = x;
+            d.update_bounds[1] = y;
+            d.update_bounds[2] = std::min(x + tileW, boundsR);
+            d.update_bounds[3] = std::min(y + tileH, boundsB);
+            ABI_CHECK(m_abi.flush(m_ctx,
+                                  &d,
+                                  m_batchScratch.data(),
+                                  static_cast<uint32_t>(m_batchScratch.size()),
+                                  fills,
+                                  static_cast<uint32_t>(desc.featherAtlasFillBatchCount),
+                                  strokes,
+                                  static_cast<uint32_t>(desc.featherAtlasStrokeBatchCount)));
+            flushed = true;
+        }
+    }
+    if (!flushed) // empty update bounds: the flush still runs (clears nothing, draws nothing)
+    {
+        ABI_CHECK(m_abi.flush(m_ctx,
+                              &d,
+                              m_batchScratch.data(),
+                              static_cast<uint32_t>(m_batchScratch.size()),
+                              fills,
+                              static_cast<uint32_t>(desc.featherAtlasFillBatchCount),
+                              strokes,
+                              static_cast<uint32_t>(desc.featherAtlasStrokeBatchCount)));
+    }
 }
 
 void RenderContextCUDAImpl::postFlush(const RenderContext::FlushResources&)

@@ -200,6 +200,33 @@ def test_band_sharding_over_two_gpus_with_nccl_gather():
     assert line["composite_identical_to_single_pass"] and line["n_gpus"] == 2
 
 
+@pytest.mark.parametrize("tiled,whole", [("c1_virtual_tiles", "c1"), ("feather_shapes_virtual_tiles", "feather_shapes")])
+def test_virtual_tiles_render_the_same_pixels(libs, tiled, whole):
+    """FrameDescriptor::virtualTileWidth / Height (SURVEY 8 f4): RenderContextCUDAImpl draws the flush
+    virtual tile by virtual tile (20 / 42 passes in these traces, recorded through the C++ host);
+    the frame must be the single-pass frame bit for bit."""
+    replay, T, _ = libs
+    a = replay.replay(T.parse(os.path.join(GOLDEN, tiled + ".rvct.xz"))).frames
+    b = replay.replay(T.parse(os.path.join(GOLDEN, whole + ".rvct.xz"))).frames
+    assert len(a) == len(b) == 1 and np.array_equal(a[0], b[0])
+
+
+def test_committed_cuda_pngs_are_current(libs, tmp_path):
+    """tests/golden/cuda_png/ holds CUDA-rendered frames as PNGs; the CPU suite runs the reference's
+    own image_diff.py on them against the oracle (tests/test_image_diff_cpu.py). They must be exactly
+    what the kernels render now (regenerate: tests/tools/gms_compare.py --write-cuda tests/golden/cuda_png)."""
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, os.path.join(root, "tests", "tools"))
+    import gms_compare as G
+    committed = os.path.join(root, "tests", "golden", "cuda_png")
+    names = sorted(n for n in os.listdir(committed) if n.endswith(".png"))
+    assert len(names) >= 8
+    G.write_set(str(tmp_path), sorted({n.split(".")[0] for n in names}), "cuda")
+    for n in names:
+        assert np.array_equal(G.read_png(os.path.join(committed, n)), G.read_png(str(tmp_path / n))), n
+
+
 def test_cxx_host_band_mode_over_two_gpus(libs):
     """Band sharding from the C++ host, no Python on the data path: two rive_cuda_player
     processes (RenderContextCUDAImpl::ContextOptions{bandRank, bandCount}), one per GPU, render
