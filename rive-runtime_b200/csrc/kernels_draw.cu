@@ -1497,6 +1497,7 @@ __global__ void __launch_bounds__(256) sort_tiles_kernel(const uint32_t* __restr
 
 #include "raster_tiles.cuh"
 #include "raster_tiles_exact.cuh"
+#include "raster_tiles_span.cuh"
 
 // ---------------------------------------------------------------------------
 // Host orchestration
@@ -1696,6 +1697,16 @@ int launch_draw_list(rivecuda_ctx* ctx, const rivecuda_flush_desc& desc, const r
             exact = true;
     if (const char* env = getenv("RIVECUDA_EXACT"))
         exact = env[0] != '0';
+    // The span rasteriser (raster_tiles_span.cuh) takes the flushes whose coverage is
+    // order-independent inside a path: plain fills / strokes and interior triangles. Feathers,
+    // atlas blits and image meshes keep the in-order kernel. RIVECUDA_SPANS=0 forces the latter.
+    bool spans = !exact;
+    for (uint32_t i = 0; i < batchCount; ++i)
+        if ((batches[i].shader_features & RIVECUDA_FEATURE_FEATHER) != 0u || batches[i].draw_type == RIVECUDA_DRAW_FEATHER_ATLAS_BLIT ||
+            batches[i].draw_type == RIVECUDA_DRAW_IMAGE_MESH)
+            spans = false;
+    if (const char* env = getenv("RIVECUDA_SPANS"))
+        spans = spans && env[0] != '0';
     P.triPos = nullptr;
     TriGeom* triGeom = nullptr;
     TriAttr* triAttr = nullptr;
@@ -1825,6 +1836,7 @@ int launch_draw_list(rivecuda_ctx* ctx, const rivecuda_flush_desc& desc, const r
     tail.triGeom = triGeom;
     tail.triAttr = triAttr;
     tail.triPos = P.triPos;
+    tail.spans = spans;
     tail.bins = std::make_shared<BinTables>(bins);
     tail.tileOffsets = tileOffsets;
     tail.tileCounts = tileCounts;
@@ -1863,11 +1875,14 @@ int launch_tail(rivecuda_ctx* ctx)
     {
         unsigned long long zero[32] = {};
         cudaMemcpyToSymbol(g_rasterStats, zero, sizeof(zero));
+        cudaMemcpyToSymbol(g_bboxHist, zero, sizeof(unsigned long long) * 24);
     }
 #endif
     if (tail.triPos != nullptr)
         raster_tiles_exact_kernel<<<tail.tileCount, 256, 0, stream>>>(P, triGeom, static_cast<const TriAttr*>(tail.triAttr), static_cast<const TriPos*>(tail.triPos), tail.tileOffsets,
                                                                      tail.tileCounts, entries, tail.entryTotal, capacity);
+    else if (tail.spans)
+        raster_spans_kernel<<<tail.tileCount, 256, 0, stream>>>(P, triGeom, static_cast<const TriAttr*>(tail.triAttr), tail.tileOffsets, tail.tileCounts, entries, tail.entryTotal, capacity);
     else
         raster_tiles_kernel<<<tail.tileCount, 256, 0, stream>>>(P, triGeom, static_cast<const TriAttr*>(tail.triAttr), tail.tileOffsets, tail.tileCounts, entries, tail.entryTotal, capacity);
     ctx->lastLaunches += 1;
@@ -1879,6 +1894,10 @@ int launch_tail(rivecuda_ctx* ctx)
         const char* names[3] = {"border", "inner-fan", "midpoint-fan"};
         for (int c = 0; c < 3; ++c)
             fprintf(stderr, "[stats] %-12s entries %llu visits %llu fast %llu hit %llu lanes-inside %llu\n", names[c], st[c * 8], st[c * 8 + 1], st[c * 8 + 2], st[c * 8 + 3], st[c * 8 + 4]);
+        unsigned long long hist[24];
+        cudaMemcpyFromSymbol(hist, g_bboxHist, sizeof(hist));
+        for (int c = 0; c < 3; ++c)
+            fprintf(stderr, "[stats] %-12s bbox area <=1:%llu <=4:%llu <=9:%llu <=16:%llu <=32:%llu <=64:%llu <=128:%llu >128:%llu\n", names[c], hist[c * 8], hist[c * 8 + 1], hist[c * 8 + 2], hist[c * 8 + 3], hist[c * 8 + 4], hist[c * 8 + 5], hist[c * 8 + 6], hist[c * 8 + 7]);
         fprintf(stderr, "[stats] warp resolves %llu lanes with coverage %llu\n", st[30], st[31]);
     }
 #endif

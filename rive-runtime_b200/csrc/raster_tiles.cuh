@@ -50,6 +50,10 @@ constexpr int kRasterChunk = 256;
 // visits, 3 visits with a lane inside, 4 lanes inside. [30] warp resolves, [31] lanes
 // resolved with nonzero coverage.
 __device__ unsigned long long g_rasterStats[32];
+// [class*8 + bucket]: tile-clipped bounding-box area of each (triangle, tile) entry:
+// buckets <=1, <=4, <=9, <=16, <=32, <=64, <=128, >128 pixels.
+__device__ unsigned long long g_bboxHist[24];
+__device__ unsigned long long g_pathTilePairs[4]; // [0] (path, tile) groups, [1] tiles with work
 #define RC_STAT(IDX, N)                                                                                               \
     do                                                                                                                \
     {                                                                                                                 \
@@ -133,6 +137,9 @@ __device__ void prepare_triangle(const FlushParams& P,
     const int by0 = max(((minY - 128 + 255) >> 8) - originY, 0), by1 = min(((maxY - 128) >> 8) - originY, kTileSize - 1);
     if (bx0 > bx1 || by0 > by1)
         return;
+#ifdef RIVECUDA_STATS
+    out.pad1 = static_cast<uint32_t>((bx1 - bx0 + 1) * (by1 - by0 + 1));
+#endif
     // Classify the eight 8x4 warp blocks (block w: x0 = (w&1)*8, y0 = (w>>1)*4): which ones
     // the bounding box reaches, which ones every edge reaches (any), which ones lie inside
     // every edge (all). Per edge, the function's minimum over a block is its value at the
@@ -1017,7 +1024,12 @@ __global__ void __launch_bounds__(256, RIVECUDA_RASTER_MIN_BLOCKS) raster_tiles_
             const uint32_t cls = (t % 24u) < 16u ? 0u : ((t % 24u) < 23u ? 1u : 2u);
             s_prep[threadIdx.x].pad0 = cls;
             if (s_prep[threadIdx.x].masks != 0u)
+            {
                 atomicAdd(&g_rasterStats[cls * 8], 1ull);
+                const uint32_t a = s_prep[threadIdx.x].pad1;
+                const uint32_t bucket = a <= 1 ? 0 : a <= 4 ? 1 : a <= 9 ? 2 : a <= 16 ? 3 : a <= 32 ? 4 : a <= 64 ? 5 : a <= 128 ? 6 : 7;
+                atomicAdd(&g_bboxHist[cls * 8 + bucket], 1ull);
+            }
 #endif
         }
         __syncthreads();

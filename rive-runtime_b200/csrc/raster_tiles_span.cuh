@@ -1,0 +1,479 @@
+/*
+ * raster_tiles_span.cuh -- K5s, the span rasteriser (included by kernels_draw.cu).
+ *
+ * Runs instead of raster_tiles_kernel on flushes whose coverage is order-independent inside a
+ * path: plain fills (coverage += c, interior triangles included) and plain strokes
+ * (coverage = max(coverage, min(c0, c1))). Feathers (whose fp16 round-per-fragment order is
+ * visible), atlas blits and image meshes (immediate blends) keep the in-order kernel.
+ *
+ * One CTA (256 threads) per 16x16 tile. The tile's sorted list is consumed 256 entries at a
+ * time:
+ *   prepare   thread k turns entry k into its tile-local form (three exact int32 edge functions,
+ *             coverage planes, the rows of the tile it can touch) -- once per (triangle, tile).
+ *   group     consecutive entries of one path form a group; a group owns one of kSpanSlots
+ *             coverage planes (256 x int32 in shared memory) until it is resolved.
+ *   expand    every (entry, pixel row) pair becomes one 16-bit work unit (block-wide scan of the
+ *             row counts), so that the fill work is balanced over the CTA row by row, not
+ *             triangle by triangle.
+ *   fill      a LANE per unit: the row's pixel span [lo, hi] comes from the three edge functions
+ *             by a float estimate corrected with one exact integer evaluation, and each pixel
+ *             of the span receives its coverage with one shared-memory atomic: fills add a
+ *             14-bit fixed-point value (integer adds commute: deterministic), strokes take the
+ *             maximum of the float bits. A lane is busy for the pixels the triangle covers,
+ *             instead of 32 lanes testing one triangle of which 2-8 are inside.
+ *   resolve   thread = pixel: for each complete group, in API order, a pixel whose plane word is
+ *             non-zero blends the path once (resolve_path, shared with the in-order kernel)
+ *             and clears the word.
+ * Colour / clip state stay in registers for the whole flush and the framebuffer is written once,
+ * exactly as in raster_tiles_kernel.
+ *
+ * Difference to the in-order kernel (and the reference): the coverage plane is not rounded to
+ * fp16 after every fragment; plain fills / strokes accumulate a handful of fragments per pixel,
+ * where that rounding is below 1/255 (parity tests: tests/test_parity_gpu.py).
+ */
+#pragma once
+
+#ifndef RIVECUDA_SPAN_SLOTS
+#define RIVECUDA_SPAN_SLOTS 16
+#endif
+constexpr int kSpanSlots = RIVECUDA_SPAN_SLOTS; // power of two
+constexpr int kSpanChunk = 256;
+constexpr float kSpanFixedOne = 4194304.f; // 2^22: coverage 1.0 in a plane word (14 fractional bits above an 8-bit fragment count)
+
+constexpr uint32_t kSpanStroke = 1u << 24;
+constexpr uint32_t kSpanFlat = 1u << 25;
+
+struct SpanTri // 16 words (64 B), one per (triangle, tile), in shared memory
+{
+    int32_t A0, B0, q0, A1; // words 0-3   } three int32 edge functions
+    int32_t B1, q1, A2, B2; // words 4-7   }   e = q + A*i + B*j >= 0
+    int32_t q2;             // word 8      }
+    float p0[3];            // words 9-11: fills: coverage * 2^22 as P0 + Px*i + Py*j; strokes: c0
+    float p1[3];            // words 12-14: strokes: c1
+    uint32_t info;          // word 15: by0 | by1 << 4 | bx0 << 8 | bx1 << 12 | slot << 16 | kSpan* flags
+};
+static_assert(sizeof(SpanTri) == 64, "SpanTri");
+
+struct SpanSlot // what resolve_path needs of a group's path
+{
+    uint32_t meta, paintX, paintY, pad;
+    float solid[4];
+};
+
+// Tile-local form of one triangle: false if it cannot touch the tile.
+__device__ __forceinline__ bool prepare_span_triangle(const TriGeom& g, const TriAttr* __restrict__ attrPtr, int originX, int originY, SpanTri& out, uint32_t& rowRange)
+{
+    const int32_t X[3] = {g.x0, g.x1, g.x2}, Y[3] = {g.y0, g.y1, g.y2};
+    const int32_t px0 = (originX << 8) + 128, py0 = (originY << 8) + 128; // pixel centre of tile pixel (0,0)
+    int32_t A[3], B[3];
+    int64_t E0u[3];
+    int32_t Ai[3], Bi[3], qi[3];
+    bool reject = false;
+#pragma unroll
+    for (int e = 0; e < 3; ++e)
+    {
+        const int a = (e + 1) % 3, b = (e + 2) % 3;
+        const int32_t dx = X[b] - X[a], dy = Y[b] - Y[a];
+        const bool topLeft = (dy == 0 && dx > 0) || (dy < 0);
+        A[e] = -dy;
+        B[e] = dx;
+        const int64_t C = static_cast<int64_t>(dy) * X[a] - static_cast<int64_t>(dx) * Y[a];
+        E0u[e] = static_cast<int64_t>(-dy) * px0 + static_cast<int64_t>(dx) * py0 + C;
+        const int64_t q = (E0u[e] - (topLeft ? 0 : 1)) >> 8;
+        const int32_t negSum = min(-dy, 0) + min(dx, 0), posSum = max(-dy, 0) + max(dx, 0);
+        const int64_t emin = q + static_cast<int64_t>(negSum) * (kTileSize - 1);
+        const int64_t emax = q + static_cast<int64_t>(posSum) * (kTileSize - 1);
+        if (emax < 0)
+            reject = true;
+        if (emin >= 0)
+        {
+            Ai[e] = Bi[e] = qi[e] = 0; // true for every pixel of the tile
+        }
+        else if ((static_cast<int64_t>(posSum) - negSum) < (1ll << 25))
+        {
+            Ai[e] = A[e];
+            Bi[e] = B[e];
+            qi[e] = static_cast<int32_t>(q);
+        }
+        else
+        {
+            // Edges longer than 2^17 px: scaled (approximate), as in prepare_triangle.
+            int64_t a64 = A[e], b64 = B[e], q64 = q;
+            while ((a64 < 0 ? -a64 : a64) + (b64 < 0 ? -b64 : b64) >= (1ll << 25))
+            {
+                a64 >>= 1;
+                b64 >>= 1;
+                q64 >>= 1;
+            }
+            Ai[e] = static_cast<int32_t>(a64);
+            Bi[e] = static_cast<int32_t>(b64);
+            qi[e] = static_cast<int32_t>(q64);
+        }
+    }
+    if (reject)
+        return false;
+    const int32_t minX = min(X[0], min(X[1], X[2])), maxX = max(X[0], max(X[1], X[2]));
+    const int32_t minY = min(Y[0], min(Y[1], Y[2])), maxY = max(Y[0], max(Y[1], Y[2]));
+    const int bx0 = max(((minX - 128 + 255) >> 8) - originX, 0), bx1 = min(((maxX - 128) >> 8) - originX, kTileSize - 1);
+    const int by0 = max(((minY - 128 + 255) >> 8) - originY, 0), by1 = min(((maxY - 128) >> 8) - originY, kTileSize - 1);
+    if (bx0 > bx1 || by0 > by1)
+        return false;
+    out.A0 = Ai[0];
+    out.B0 = Bi[0];
+    out.q0 = qi[0];
+    out.A1 = Ai[1];
+    out.B1 = Bi[1];
+    out.q1 = qi[1];
+    out.A2 = Ai[2];
+    out.B2 = Bi[2];
+    out.q2 = qi[2];
+    const uint32_t kind = (g.meta >> kMetaKindShift) & 0xf;
+    const float4 a0 = __ldg(reinterpret_cast<const float4*>(attrPtr));
+    uint32_t flags = 0u;
+    if (kind == kKindFill && a0.x == a0.y && a0.y == a0.z)
+    {
+        // Constant coverage (fan / interior triangles): exact.
+        out.p0[0] = a0.x * kSpanFixedOne;
+        out.p0[1] = 0.f;
+        out.p0[2] = 0.f;
+        flags = kSpanFlat;
+    }
+    else
+    {
+        // Attribute planes from exact barycentrics at tile pixel (0,0):
+        //   attr(i,j) = sum_k c_k * (E0u_k + 256*(A_k*i + B_k*j)) / area2
+        const double inv = 1.0 / static_cast<double>(E0u[0] + E0u[1] + E0u[2]);
+        const double e0 = static_cast<double>(E0u[0]) * inv, e1 = static_cast<double>(E0u[1]) * inv, e2 = static_cast<double>(E0u[2]) * inv;
+        const double ax0 = static_cast<double>(A[0]) * 256.0 * inv, ax1 = static_cast<double>(A[1]) * 256.0 * inv, ax2 = static_cast<double>(A[2]) * 256.0 * inv;
+        const double bx0d = static_cast<double>(B[0]) * 256.0 * inv, bx1d = static_cast<double>(B[1]) * 256.0 * inv, bx2d = static_cast<double>(B[2]) * 256.0 * inv;
+        const double scale = kind == kKindFill ? static_cast<double>(kSpanFixedOne) : 1.0;
+        const double c0 = a0.x * scale, c1 = a0.y * scale, c2 = a0.z * scale;
+        out.p0[0] = static_cast<float>(c0 * e0 + c1 * e1 + c2 * e2);
+        out.p0[1] = static_cast<float>(c0 * ax0 + c1 * ax1 + c2 * ax2);
+        out.p0[2] = static_cast<float>(c0 * bx0d + c1 * bx1d + c2 * bx2d);
+        if (kind != kKindFill)
+        {
+            const float4 a1 = __ldg(reinterpret_cast<const float4*>(attrPtr) + 1);
+            const double d0 = a0.w, d1 = a1.x, d2 = a1.y; // attr[3..5]
+            out.p1[0] = static_cast<float>(d0 * e0 + d1 * e1 + d2 * e2);
+            out.p1[1] = static_cast<float>(d0 * ax0 + d1 * ax1 + d2 * ax2);
+            out.p1[2] = static_cast<float>(d0 * bx0d + d1 * bx1d + d2 * bx2d);
+            flags = kSpanStroke;
+        }
+    }
+    rowRange = static_cast<uint32_t>(by0) | (static_cast<uint32_t>(by1) << 4);
+    out.info = rowRange | (static_cast<uint32_t>(bx0) << 8) | (static_cast<uint32_t>(bx1) << 12) | flags;
+    return true;
+}
+
+// One edge's constraint on a pixel row: A*i + v >= 0 narrows [lo, hi]. The crossing is estimated
+// in float (|error| << 1e-3 px inside the tile) on the safe side and corrected with one exact
+// integer evaluation, so the span is exactly the set of pixels whose edge value is >= 0.
+__device__ __forceinline__ void span_edge(int A, int v, int& lo, int& hi)
+{
+    if (A == 0)
+    {
+        if (v < 0)
+            hi = -1;
+        return;
+    }
+    const bool pos = A > 0;
+    float t = __fdividef(-static_cast<float>(v), static_cast<float>(A));
+    t = pos ? t - 1e-3f : t + 1e-3f;
+    t = fminf(fmaxf(t, -2.f), 17.f);
+    int cand = pos ? __float2int_ru(t) : __float2int_rd(t);
+    if (v + A * cand < 0)
+        cand += pos ? 1 : -1;
+    if (pos)
+        lo = max(lo, cand);
+    else
+        hi = min(hi, cand);
+}
+
+__device__ __forceinline__ void red_add_shared(uint32_t addr, int v)
+{
+    asm volatile("red.shared.add.s32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ void red_max_shared(uint32_t addr, int v)
+{
+    asm volatile("red.shared.max.s32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+
+#ifndef RIVECUDA_SPAN_MIN_BLOCKS
+#define RIVECUDA_SPAN_MIN_BLOCKS 4
+#endif
+__global__ void __launch_bounds__(256, RIVECUDA_SPAN_MIN_BLOCKS) raster_spans_kernel(const __grid_constant__ FlushParams P,
+                                                                                  const TriGeom* __restrict__ triGeom,
+                                                                                  const TriAttr* __restrict__ triAttr,
+                                                                                  const uint32_t* __restrict__ tileOffsets,
+                                                                                  const uint32_t* __restrict__ tileCounts,
+                                                                                  const uint32_t* __restrict__ entries,
+                                                                                  const uint32_t* __restrict__ entryTotal,
+                                                                                  uint32_t entryCapacity)
+{
+    __shared__ __align__(16) int s_plane[kSpanSlots][256];
+    __shared__ __align__(16) SpanTri s_tri[kSpanChunk];
+    __shared__ __align__(16) uint16_t s_units[kSpanChunk * kTileSize];
+    __shared__ __align__(16) uint32_t s_ids[2][kSpanChunk];
+    __shared__ __align__(16) SpanSlot s_slot[kSpanSlots];
+    __shared__ uint32_t s_path[kSpanChunk + 1];
+    __shared__ uint32_t s_warpSums[2][8];
+    __shared__ __align__(8) uint64_t s_bar[2];
+    if (__ldg(entryTotal) > entryCapacity)
+        return;
+    const uint32_t tile = blockIdx.x;
+    const uint32_t n = tileCounts[tile];
+    if (n == 0u && P.loadAction != RIVECUDA_LOAD_CLEAR)
+        return;
+    const int tileX = static_cast<int>(tile % P.tilesX) + P.tileX0, tileY = static_cast<int>(tile / P.tilesX) + P.tileY0;
+    const int originX = tileX << kTileSizeLog2, originY = tileY << kTileSizeLog2;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int i = (warp & 1) * 8 + (lane & 7), j = (warp >> 1) * 4 + (lane >> 3);
+    const int px = originX + i, py = originY + j;
+    const bool inBounds = px >= P.boundsL && px < P.boundsR && py >= P.boundsT && py < P.boundsB;
+
+    PixelState s;
+    s.clipCoverage = 0.f;
+    s.clipID = 0u;
+    s.dither = 0.f;
+    if (P.ditherScale != 0.f)
+    {
+        const float v1 = fractf(0.06711056f * (px + .5f) + 0.00583715f * (py + .5f));
+        s.dither = fractf(52.9829189f * v1) * P.ditherScale + P.ditherBias;
+    }
+    const bool groupInBounds = ((__ballot_sync(0xffffffffu, inBounds) >> (lane & ~3)) & 0xfu) == 0xfu;
+    const bool vectorised = (P.targetWidth & 3u) == 0u && groupInBounds;
+    if (P.loadAction == RIVECUDA_LOAD_CLEAR)
+    {
+        s.color = P.clearColorPremulRGBA;
+    }
+    else
+    {
+        uint4 quad = make_uint4(0u, 0u, 0u, 0u);
+        if (vectorised && (lane & 3) == 0)
+            quad = *reinterpret_cast<const uint4*>(P.target + static_cast<size_t>(py) * P.targetWidth + px);
+        const int leader = lane & ~3;
+        const uint32_t q0 = __shfl_sync(0xffffffffu, quad.x, leader), q1 = __shfl_sync(0xffffffffu, quad.y, leader);
+        const uint32_t q2 = __shfl_sync(0xffffffffu, quad.z, leader), q3 = __shfl_sync(0xffffffffu, quad.w, leader);
+        const int k = lane & 3;
+        s.color = vectorised ? (k == 0 ? q0 : (k == 1 ? q1 : (k == 2 ? q2 : q3))) : (inBounds ? P.target[static_cast<size_t>(py) * P.targetWidth + px] : 0u);
+    }
+
+    const uint32_t* list = entries + tileOffsets[tile];
+    const uint32_t idsAddr = static_cast<uint32_t>(__cvta_generic_to_shared(&s_ids[0][0]));
+    const uint32_t barAddr = static_cast<uint32_t>(__cvta_generic_to_shared(&s_bar[0]));
+    const uint32_t triAddr = static_cast<uint32_t>(__cvta_generic_to_shared(&s_tri[0]));
+    const uint32_t planesAddr = static_cast<uint32_t>(__cvta_generic_to_shared(&s_plane[0][0]));
+    // This pixel's word inside a plane. Rows 2,3 (mod 4) exchange their 8-pixel halves so that the
+    // 8x4 block a warp resolves falls into 32 distinct banks.
+    const uint32_t myWord = static_cast<uint32_t>(j * 16 + (i ^ ((j & 2) << 2)));
+    for (int k = threadIdx.x; k < kSpanSlots * 256; k += 256)
+        (&s_plane[0][0])[k] = 0;
+    if (threadIdx.x == 0)
+    {
+        mbar_init(barAddr, 1u);
+        mbar_init(barAddr + 8u, 1u);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        if (n != 0u)
+            tma_load_1d(idsAddr, list, (min(static_cast<uint32_t>(kSpanChunk), n) * 4u + 15u) & ~15u, barAddr);
+    }
+
+    uint32_t openGroup = 0u;   // absolute index of the group that may continue into the next chunk
+    uint32_t carryPath = ~0u;  // its path id
+    uint32_t scanBuf = 0u;
+    uint32_t chunkIndex = 0u;
+    for (uint32_t base = 0; base < n; base += kSpanChunk, ++chunkIndex)
+    {
+        const uint32_t chunk = min(static_cast<uint32_t>(kSpanChunk), n - base);
+        const bool lastChunk = base + kSpanChunk >= n;
+        const uint32_t buf = chunkIndex & 1u;
+        __syncthreads(); // the previous chunk is resolved (and, first time round, the planes are clear and the barriers visible)
+        mbar_wait(barAddr + buf * 8u, (chunkIndex >> 1) & 1u);
+        const bool have = threadIdx.x < chunk;
+        TriGeom g;
+        uint32_t t = 0u;
+        uint32_t pathID = carryPath;
+        if (have)
+        {
+            t = s_ids[buf][threadIdx.x];
+            const uint4* src = reinterpret_cast<const uint4*>(triGeom + t);
+            *reinterpret_cast<uint4*>(&g) = __ldg(src);
+            *(reinterpret_cast<uint4*>(&g) + 1) = __ldg(src + 1);
+            pathID = g.meta & 0xffffu;
+        }
+        s_path[threadIdx.x + 1] = pathID;
+        if (threadIdx.x == 0)
+            s_path[0] = carryPath;
+        __syncthreads();
+        if (threadIdx.x == 0 && !lastChunk)
+            tma_load_1d(idsAddr + (buf ^ 1u) * static_cast<uint32_t>(kSpanChunk * 4), list + base + kSpanChunk,
+                        (min(static_cast<uint32_t>(kSpanChunk), n - base - kSpanChunk) * 4u + 15u) & ~15u, barAddr + (buf ^ 1u) * 8u);
+        // Groups: a flag wherever the path changes; the entry's group = open group + flags up to it.
+        const bool flag = have && s_path[threadIdx.x] != pathID;
+        const uint32_t flagBits = __ballot_sync(0xffffffffu, flag);
+        if (lane == 0)
+            s_warpSums[scanBuf][warp] = __popc(flagBits);
+        // Prepare while the warp sums settle.
+        uint32_t rowRange = 0u;
+        bool live = false;
+        if (have && (g.meta & kMetaValid) != 0u)
+            live = prepare_span_triangle(g, triAttr + t, originX, originY, s_tri[threadIdx.x], rowRange);
+        __syncthreads();
+        uint32_t groupsBefore = 0u, groupsInChunk = 0u;
+#pragma unroll
+        for (int w = 0; w < 8; ++w)
+        {
+            const uint32_t c = s_warpSums[scanBuf][w];
+            groupsBefore += w < warp ? c : 0u;
+            groupsInChunk += c;
+        }
+        scanBuf ^= 1u;
+        const uint32_t group = openGroup + groupsBefore + __popc(flagBits & ((2u << lane) - 1u));
+        const uint32_t lastGroup = openGroup + groupsInChunk;
+        const uint32_t rows = live ? ((rowRange >> 4) - (rowRange & 15u) + 1u) : 0u;
+        if (live)
+            s_tri[threadIdx.x].info |= (group & (kSpanSlots - 1)) << 16;
+
+        // Windows of kSpanSlots groups: fill, then resolve the complete ones in order.
+        for (uint32_t windowStart = openGroup; windowStart <= lastGroup; windowStart += kSpanSlots)
+        {
+            const bool inWindow = have && group >= windowStart && group < windowStart + kSpanSlots;
+            if (flag && inWindow)
+            {
+                // First entry of a group: its path's paint for resolve_path.
+                const uint2 paint = __ldg(P.paintBuffer + pathID);
+                uint32_t meta = g.meta;
+                if ((paint.x & 0xffff0cffu) == kPaintTypeSolid && (g.meta & (kMetaUnmultiplied | kMetaModulatedImage)) == 0u)
+                    meta |= kMetaSimplePaint;
+                float4 pc = unpack_rgba8_builtin(paint.y);
+                if ((g.meta & kMetaUnmultiplied) == 0u)
+                {
+                    pc.x *= pc.w;
+                    pc.y *= pc.w;
+                    pc.z *= pc.w;
+                }
+                SpanSlot& slot = s_slot[group & (kSpanSlots - 1)];
+                slot.meta = meta;
+                slot.paintX = paint.x;
+                slot.paintY = paint.y;
+                slot.solid[0] = pc.x;
+                slot.solid[1] = pc.y;
+                slot.solid[2] = pc.z;
+                slot.solid[3] = pc.w;
+            }
+            // Expand (entry, row) units: exclusive scan of the row counts over the CTA.
+            const uint32_t myRows = inWindow ? rows : 0u;
+            uint32_t incl = myRows;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1)
+            {
+                const uint32_t up = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o)
+                    incl += up;
+            }
+            if (lane == 31)
+                s_warpSums[scanBuf][warp] = incl;
+            __syncthreads();
+            uint32_t unitBase = 0u, unitCount = 0u;
+#pragma unroll
+            for (int w = 0; w < 8; ++w)
+            {
+                const uint32_t c = s_warpSums[scanBuf][w];
+                unitBase += w < warp ? c : 0u;
+                unitCount += c;
+            }
+            scanBuf ^= 1u;
+            {
+                uint32_t dst = unitBase + incl - myRows;
+                const uint32_t first = rowRange & 15u;
+                for (uint32_t r = 0; r < myRows; ++r)
+                    s_units[dst + r] = static_cast<uint16_t>((threadIdx.x << 4) | (first + r));
+            }
+            __syncthreads();
+
+            // Fill: a lane per (entry, row).
+            for (uint32_t u = threadIdx.x; u < unitCount; u += 256)
+            {
+                const uint32_t unit = s_units[u];
+                const uint32_t T = triAddr + (unit >> 4) * static_cast<uint32_t>(sizeof(SpanTri));
+                const int row = static_cast<int>(unit & 15u);
+                const uint4 w0 = lds_u32x4(T), w1 = lds_u32x4(T + 16), w2 = lds_u32x4(T + 32), w3 = lds_u32x4(T + 48);
+                const uint32_t info = w3.w;
+                int lo = static_cast<int>((info >> 8) & 15u), hi = static_cast<int>((info >> 12) & 15u);
+                span_edge(static_cast<int>(w0.x), static_cast<int>(w0.z) + static_cast<int>(w0.y) * row, lo, hi);
+                span_edge(static_cast<int>(w0.w), static_cast<int>(w1.y) + static_cast<int>(w1.x) * row, lo, hi);
+                span_edge(static_cast<int>(w1.z), static_cast<int>(w2.x) + static_cast<int>(w1.w) * row, lo, hi);
+                if (lo > hi)
+                    continue;
+                const uint32_t rowAddr = planesAddr + ((info >> 16) & 0xffu) * 1024u + static_cast<uint32_t>(row) * 64u;
+                const uint32_t swz = static_cast<uint32_t>(row & 2) << 2;
+                const float frow = static_cast<float>(row);
+                if ((info & kSpanFlat) != 0u)
+                {
+                    const int add = ((__float2int_rn(__uint_as_float(w2.y)) + 128) & ~0xff) | 1;
+                    for (int x = lo; x <= hi; ++x)
+                        red_add_shared(rowAddr + ((static_cast<uint32_t>(x) ^ swz) << 2), add);
+                }
+                else if ((info & kSpanStroke) == 0u)
+                {
+                    const float c0 = __fmaf_rn(__uint_as_float(w2.w), frow, __uint_as_float(w2.y)), cx = __uint_as_float(w2.z);
+                    for (int x = lo; x <= hi; ++x)
+                    {
+                        const int add = ((__float2int_rn(__fmaf_rn(cx, static_cast<float>(x), c0)) + 128) & ~0xff) | 1;
+                        red_add_shared(rowAddr + ((static_cast<uint32_t>(x) ^ swz) << 2), add);
+                    }
+                }
+                else
+                {
+                    const float c0 = __fmaf_rn(__uint_as_float(w2.w), frow, __uint_as_float(w2.y)), c0x = __uint_as_float(w2.z);
+                    const float c1 = __fmaf_rn(__uint_as_float(w3.z), frow, __uint_as_float(w3.x)), c1x = __uint_as_float(w3.y);
+                    for (int x = lo; x <= hi; ++x)
+                    {
+                        const float fx = static_cast<float>(x);
+                        const float c = fminf(__fmaf_rn(c0x, fx, c0), __fmaf_rn(c1x, fx, c1));
+                        if (c > 0.f)
+                            red_max_shared(rowAddr + ((static_cast<uint32_t>(x) ^ swz) << 2), __float_as_int(c));
+                    }
+                }
+            }
+            __syncthreads();
+
+            // Resolve, in order, the groups of the window that are complete.
+            const uint32_t windowEnd = min(windowStart + kSpanSlots, lastGroup + 1u);
+            const uint32_t resolveEnd = (windowEnd == lastGroup + 1u && !lastChunk) ? lastGroup : windowEnd;
+            for (uint32_t gi = windowStart; gi < resolveEnd; ++gi)
+            {
+                const uint32_t slotIdx = gi & (kSpanSlots - 1);
+                const uint32_t wordAddr = planesAddr + slotIdx * 1024u + myWord * 4u;
+                const int v = static_cast<int>(lds_u32(wordAddr));
+                if (v == 0)
+                    continue;
+                asm volatile("st.shared.u32 [%0], %1;" ::"r"(wordAddr), "r"(0) : "memory");
+                const uint32_t slotAddr = static_cast<uint32_t>(__cvta_generic_to_shared(&s_slot[slotIdx]));
+                const uint4 rec = lds_u32x4(slotAddr);
+                const float4 solid = lds_f32x4(slotAddr + 16);
+                const uint32_t kind = (rec.x >> kMetaKindShift) & 0xf;
+                const float coverageCount = kind == kKindStroke ? __int_as_float(v) : static_cast<float>(v >> 8) * (1.f / 16384.f);
+                resolve_path(P, rec.x, rec.y, rec.z, solid, coverageCount, px, py, s);
+            }
+            // (No barrier here: the next window's slot records and fills are separated from this
+            // resolve by the scan barrier below / the chunk barrier above.)
+            if (windowStart + kSpanSlots <= lastGroup)
+                __syncthreads();
+        }
+        openGroup = lastGroup;
+        carryPath = s_path[chunk];
+    }
+    {
+        const uint32_t c1 = __shfl_down_sync(0xffffffffu, s.color, 1), c2 = __shfl_down_sync(0xffffffffu, s.color, 2), c3 = __shfl_down_sync(0xffffffffu, s.color, 3);
+        if (vectorised)
+        {
+            if ((lane & 3) == 0)
+                *reinterpret_cast<uint4*>(P.target + static_cast<size_t>(py) * P.targetWidth + px) = make_uint4(s.color, c1, c2, c3);
+        }
+        else if (inBounds)
+        {
+            P.target[static_cast<size_t>(py) * P.targetWidth + px] = s.color;
+        }
+    }
+}

@@ -125,6 +125,7 @@ struct PendingTail
     const void* triGeom = nullptr;
     const void* triAttr = nullptr;
     const void* triPos = nullptr; // non-null: raster_tiles_exact_kernel
+    bool spans = false;           // raster_spans_kernel instead of raster_tiles_kernel
     uint32_t* tileOffsets = nullptr;
     uint32_t* tileCounts = nullptr;
     uint32_t* bigCursors = nullptr;
