@@ -9,27 +9,33 @@
  * One CTA (256 threads) per 16x16 tile. The tile's sorted list is consumed 256 entries at a
  * time:
  *   prepare   thread k turns entry k into its tile-local form (three exact int32 edge functions,
- *             coverage planes, the rows of the tile it can touch) -- once per (triangle, tile).
+ *             coverage planes, the rows of the tile it can touch) -- once per (entry, tile).
  *   group     consecutive entries of one path form a group; a group owns one of kSpanSlots
  *             coverage planes (256 x int32 in shared memory) until it is resolved.
  *   expand    every (entry, pixel row) pair becomes one 16-bit work unit (block-wide scan of the
  *             row counts), so that the fill work is balanced over the CTA row by row, not
  *             triangle by triangle.
- *   fill      a LANE per unit: the row's pixel span [lo, hi] comes from the three edge functions
- *             by a float estimate corrected with one exact integer evaluation, and each pixel
- *             of the span receives its coverage with one shared-memory atomic: fills add a
- *             14-bit fixed-point value (integer adds commute: deterministic), strokes take the
- *             maximum of the float bits. A lane is busy for the pixels the triangle covers,
- *             instead of 32 lanes testing one triangle of which 2-8 are inside.
- *   resolve   thread = pixel: for each complete group, in API order, a pixel whose plane word is
- *             non-zero blends the path once (resolve_path, shared with the in-order kernel)
- *             and clears the word.
+ *   fill      a LANE per unit. A fill's plane holds DELTAS along each pixel row (the resolve step
+ *             prefix-sums them): a triangle's row span [lo, hi] of constant coverage c is +c at
+ *             lo and -c at hi + 1 (two shared-memory atomics however long the span), an
+ *             anti-aliasing ramp adds its per-pixel differences, and a fan-edge record (the
+ *             boundary edges of a midpoint-fan wedge, FanTables in kernels_draw.cu) adds +-1 at
+ *             the pixel where the row crosses the edge. The span ends come from the edge
+ *             functions by a float estimate corrected with one exact integer evaluation. Values
+ *             are 16.16 fixed point: integer adds commute, so the result is deterministic.
+ *             Strokes keep the maximum of min(c0, c1) per pixel (atomic max on the float bits).
+ *   resolve   thread = pixel, a warp = two pixel rows: for each complete group, in API order, the
+ *             warp prefix-sums its rows' deltas (4 shuffle steps), adds the path's backdrop at
+ *             this tile (fan winding) and blends the path once (resolve_path, shared with the
+ *             in-order kernel) wherever the coverage is not zero.
  * Colour / clip state stay in registers for the whole flush and the framebuffer is written once,
  * exactly as in raster_tiles_kernel.
  *
- * Difference to the in-order kernel (and the reference): the coverage plane is not rounded to
- * fp16 after every fragment; plain fills / strokes accumulate a handful of fragments per pixel,
- * where that rounding is below 1/255 (parity tests: tests/test_parity_gpu.py).
+ * Differences to the in-order kernel (and the reference): the coverage plane is not rounded to
+ * fp16 after every fragment (plain fills / strokes accumulate a handful of fragments per pixel,
+ * where that rounding is far below 1/255), and a pixel whose fragments cancel to exactly zero
+ * is left alone rather than resolved with zero coverage (visible only through the clip id a
+ * nested clip update would have written there). Parity: tests/test_parity_gpu.py.
  */
 #pragma once
 
@@ -38,37 +44,37 @@
 #endif
 constexpr int kSpanSlots = RIVECUDA_SPAN_SLOTS; // power of two
 constexpr int kSpanChunk = 256;
-constexpr float kSpanFixedOne = 4194304.f; // 2^22: coverage 1.0 in a plane word (14 fractional bits above an 8-bit fragment count)
+constexpr float kSpanFixedOne = 65536.f; // coverage 1.0 in a fill's plane word
 
 constexpr uint32_t kSpanStroke = 1u << 24;
 constexpr uint32_t kSpanFlat = 1u << 25;
+constexpr uint32_t kSpanFanEdges = 1u << 26;
 
-struct SpanTri // 16 words (64 B), one per (triangle, tile), in shared memory
+struct SpanTri // 16 words (64 B), one per (entry, tile), in shared memory
 {
     int32_t A0, B0, q0, A1; // words 0-3   } three int32 edge functions
     int32_t B1, q1, A2, B2; // words 4-7   }   e = q + A*i + B*j >= 0
     int32_t q2;             // word 8      }
-    float p0[3];            // words 9-11: fills: coverage * 2^22 as P0 + Px*i + Py*j; strokes: c0
+    float p0[3];            // words 9-11: fills: coverage * 2^16 as P0 + Px*i + Py*j; strokes: c0;
+                            //             fan edges: [0] weight * 2^16 (int), [1] per edge e, bits 10e..10e+9: first row | last row << 4 | rows valid << 8 | straddles column 0 << 9
     float p1[3];            // words 12-14: strokes: c1
     uint32_t info;          // word 15: by0 | by1 << 4 | bx0 << 8 | bx1 << 12 | slot << 16 | kSpan* flags
 };
 static_assert(sizeof(SpanTri) == 64, "SpanTri");
 
-struct SpanSlot // what resolve_path needs of a group's path
+struct SpanSlot // what the resolve step needs of a group's path
 {
-    uint32_t meta, paintX, paintY, pad;
+    uint32_t meta, paintX, paintY;
+    int32_t backdrop; // fan winding at the tile's pixel (0,0), 16.16
     float solid[4];
 };
 
-// Tile-local form of one triangle: false if it cannot touch the tile.
-__device__ __forceinline__ bool prepare_span_triangle(const TriGeom& g, const TriAttr* __restrict__ attrPtr, int originX, int originY, SpanTri& out, uint32_t& rowRange)
+// The three tile-local edge functions of a record's triangle (exact below 2^17 px of Manhattan
+// length, as prepare_triangle): false if some edge excludes the whole tile.
+__device__ __forceinline__ bool span_edge_functions(const int32_t X[3], const int32_t Y[3], int32_t px0, int32_t py0, int32_t A[3], int32_t B[3], int64_t E0u[3], int32_t Ai[3], int32_t Bi[3], int32_t qi[3], uint32_t& allOutside)
 {
-    const int32_t X[3] = {g.x0, g.x1, g.x2}, Y[3] = {g.y0, g.y1, g.y2};
-    const int32_t px0 = (originX << 8) + 128, py0 = (originY << 8) + 128; // pixel centre of tile pixel (0,0)
-    int32_t A[3], B[3];
-    int64_t E0u[3];
-    int32_t Ai[3], Bi[3], qi[3];
     bool reject = false;
+    allOutside = 0u;
 #pragma unroll
     for (int e = 0; e < 3; ++e)
     {
@@ -84,8 +90,13 @@ __device__ __forceinline__ bool prepare_span_triangle(const TriGeom& g, const Tr
         const int64_t emin = q + static_cast<int64_t>(negSum) * (kTileSize - 1);
         const int64_t emax = q + static_cast<int64_t>(posSum) * (kTileSize - 1);
         if (emax < 0)
+        {
             reject = true;
-        if (emin >= 0)
+            allOutside |= 1u << e;
+            Ai[e] = Bi[e] = 0; // false for every pixel of the tile
+            qi[e] = -1;
+        }
+        else if (emin >= 0)
         {
             Ai[e] = Bi[e] = qi[e] = 0; // true for every pixel of the tile
         }
@@ -110,14 +121,20 @@ __device__ __forceinline__ bool prepare_span_triangle(const TriGeom& g, const Tr
             qi[e] = static_cast<int32_t>(q64);
         }
     }
-    if (reject)
-        return false;
-    const int32_t minX = min(X[0], min(X[1], X[2])), maxX = max(X[0], max(X[1], X[2]));
-    const int32_t minY = min(Y[0], min(Y[1], Y[2])), maxY = max(Y[0], max(Y[1], Y[2]));
-    const int bx0 = max(((minX - 128 + 255) >> 8) - originX, 0), bx1 = min(((maxX - 128) >> 8) - originX, kTileSize - 1);
-    const int by0 = max(((minY - 128 + 255) >> 8) - originY, 0), by1 = min(((maxY - 128) >> 8) - originY, kTileSize - 1);
-    if (bx0 > bx1 || by0 > by1)
-        return false;
+    return !reject;
+}
+
+// Tile-local form of one entry: false if it cannot touch the tile.
+__device__ __forceinline__ bool prepare_span_entry(const TriGeom& g, const TriAttr* __restrict__ attrPtr, int originX, int originY, SpanTri& out, uint32_t& rowRange)
+{
+    const int32_t X[3] = {g.x0, g.x1, g.x2}, Y[3] = {g.y0, g.y1, g.y2};
+    const int32_t px0 = (originX << 8) + 128, py0 = (originY << 8) + 128; // pixel centre of tile pixel (0,0)
+    int32_t A[3], B[3];
+    int64_t E0u[3];
+    int32_t Ai[3], Bi[3], qi[3];
+    uint32_t allOutside;
+    const bool overlaps = span_edge_functions(X, Y, px0, py0, A, B, E0u, Ai, Bi, qi, allOutside);
+    const uint32_t kind = (g.meta >> kMetaKindShift) & 0xf;
     out.A0 = Ai[0];
     out.B0 = Bi[0];
     out.q0 = qi[0];
@@ -127,8 +144,53 @@ __device__ __forceinline__ bool prepare_span_triangle(const TriGeom& g, const Tr
     out.A2 = Ai[2];
     out.B2 = Bi[2];
     out.q2 = qi[2];
-    const uint32_t kind = (g.meta >> kMetaKindShift) & 0xf;
     const float4 a0 = __ldg(reinterpret_cast<const float4*>(attrPtr));
+    if (kind == kKindFanEdges)
+    {
+        // The active boundary edges of a wedge: per edge the pixel rows it straddles
+        // (min y <= centre y < max y) and whether it straddles the tile's pixel column 0.
+        uint32_t packed = 0u;
+        int first = kTileSize, last = -1;
+#pragma unroll
+        for (int e = 0; e < 3; ++e)
+        {
+            if ((g.aux & (1u << e)) == 0u)
+                continue;
+            const int a = (e + 1) % 3, b = (e + 2) % 3;
+            const int32_t ylo = min(Y[a], Y[b]), yhi = max(Y[a], Y[b]);
+            const int j0 = max((ylo - py0 + 255) >> 8, 0), j1 = min(((yhi - py0 + 255) >> 8) - 1, kTileSize - 1);
+            uint32_t bits = 0u;
+            if (j0 <= j1 && Ai[e] != 0)
+            {
+                bits = static_cast<uint32_t>(j0) | (static_cast<uint32_t>(j1) << 4) | 0x100u;
+                first = min(first, j0);
+                last = max(last, j1);
+            }
+            if (min(X[a], X[b]) <= px0 && px0 < max(X[a], X[b]) && ((qi[e] >= 0) != (qi[e] + Bi[e] * (kTileSize - 1) >= 0)))
+            {
+                // Somewhere down column 0 the pixel changes sides: every row from there on.
+                bits |= 0x200u;
+                first = min(first, 1);
+                last = kTileSize - 1;
+            }
+            packed |= bits << (10 * e);
+        }
+        if (first > last)
+            return false;
+        out.p0[0] = __int_as_float(a0.x < 0.f ? -65536 : 65536);
+        out.p0[1] = __uint_as_float(packed);
+        rowRange = static_cast<uint32_t>(first) | (static_cast<uint32_t>(last) << 4);
+        out.info = rowRange | kSpanFanEdges;
+        return true;
+    }
+    if (!overlaps)
+        return false;
+    const int32_t minX = min(X[0], min(X[1], X[2])), maxX = max(X[0], max(X[1], X[2]));
+    const int32_t minY = min(Y[0], min(Y[1], Y[2])), maxY = max(Y[0], max(Y[1], Y[2]));
+    const int bx0 = max(((minX - 128 + 255) >> 8) - originX, 0), bx1 = min(((maxX - 128) >> 8) - originX, kTileSize - 1);
+    const int by0 = max(((minY - 128 + 255) >> 8) - originY, 0), by1 = min(((maxY - 128) >> 8) - originY, kTileSize - 1);
+    if (bx0 > bx1 || by0 > by1)
+        return false;
     uint32_t flags = 0u;
     if (kind == kKindFill && a0.x == a0.y && a0.y == a0.z)
     {
@@ -199,6 +261,15 @@ __device__ __forceinline__ void red_max_shared(uint32_t addr, int v)
     asm volatile("red.shared.max.s32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
 }
 
+#ifdef RIVECUDA_STATS
+// [0] triangle entries, [1] live, [2] their row units; [3] fan-edge entries, [4] live, [5] their row units; [6] markers;
+// [7] groups; [8] (group, warp) resolve visits that pass the empty test, [9] warp-level resolve_path calls, [10] lanes blended;
+// [11] wedges drawn (setup), [12] their active edges (setup); [13] chunks, [14] windows
+#define SPAN_STAT(IDX, N) atomicAdd(&g_spanStats[IDX], static_cast<unsigned long long>(N))
+#else
+#define SPAN_STAT(IDX, N)
+#endif
+
 #ifndef RIVECUDA_SPAN_MIN_BLOCKS
 #define RIVECUDA_SPAN_MIN_BLOCKS 4
 #endif
@@ -228,7 +299,9 @@ __global__ void __launch_bounds__(256, RIVECUDA_SPAN_MIN_BLOCKS) raster_spans_ke
     const int tileX = static_cast<int>(tile % P.tilesX) + P.tileX0, tileY = static_cast<int>(tile / P.tilesX) + P.tileY0;
     const int originX = tileX << kTileSizeLog2, originY = tileY << kTileSizeLog2;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int i = (warp & 1) * 8 + (lane & 7), j = (warp >> 1) * 4 + (lane >> 3);
+    // A warp owns two pixel rows: the row prefix sums of the resolve step stay inside a half warp
+    // and a plane's words are read lane by lane (no bank conflicts).
+    const int i = lane & 15, j = warp * 2 + (lane >> 4);
     const int px = originX + i, py = originY + j;
     const bool inBounds = px >= P.boundsL && px < P.boundsR && py >= P.boundsT && py < P.boundsB;
 
@@ -264,11 +337,12 @@ __global__ void __launch_bounds__(256, RIVECUDA_SPAN_MIN_BLOCKS) raster_spans_ke
     const uint32_t barAddr = static_cast<uint32_t>(__cvta_generic_to_shared(&s_bar[0]));
     const uint32_t triAddr = static_cast<uint32_t>(__cvta_generic_to_shared(&s_tri[0]));
     const uint32_t planesAddr = static_cast<uint32_t>(__cvta_generic_to_shared(&s_plane[0][0]));
-    // This pixel's word inside a plane. Rows 2,3 (mod 4) exchange their 8-pixel halves so that the
-    // 8x4 block a warp resolves falls into 32 distinct banks.
-    const uint32_t myWord = static_cast<uint32_t>(j * 16 + (i ^ ((j & 2) << 2)));
+    const uint32_t slotsAddr = static_cast<uint32_t>(__cvta_generic_to_shared(&s_slot[0]));
     for (int k = threadIdx.x; k < kSpanSlots * 256; k += 256)
         (&s_plane[0][0])[k] = 0;
+    // (Group 0 is the empty group before the first entry: nothing in its plane, no backdrop.)
+    if (threadIdx.x < kSpanSlots * sizeof(SpanSlot) / 4)
+        reinterpret_cast<uint32_t*>(&s_slot[0])[threadIdx.x] = 0u;
     if (threadIdx.x == 0)
     {
         mbar_init(barAddr, 1u);
@@ -291,11 +365,15 @@ __global__ void __launch_bounds__(256, RIVECUDA_SPAN_MIN_BLOCKS) raster_spans_ke
         mbar_wait(barAddr + buf * 8u, (chunkIndex >> 1) & 1u);
         const bool have = threadIdx.x < chunk;
         TriGeom g;
+        g.meta = 0u;
         uint32_t t = 0u;
+        bool marker = false;
         uint32_t pathID = carryPath;
         if (have)
         {
-            t = s_ids[buf][threadIdx.x];
+            const uint32_t key = s_ids[buf][threadIdx.x];
+            t = key >> P.keyShift;
+            marker = (key & P.keyShift) != 0u; // keyShift is 0 or 1: bit 0 of a shifted key marks a backdrop marker
             const uint4* src = reinterpret_cast<const uint4*>(triGeom + t);
             *reinterpret_cast<uint4*>(&g) = __ldg(src);
             *(reinterpret_cast<uint4*>(&g) + 1) = __ldg(src + 1);
@@ -316,8 +394,8 @@ __global__ void __launch_bounds__(256, RIVECUDA_SPAN_MIN_BLOCKS) raster_spans_ke
         // Prepare while the warp sums settle.
         uint32_t rowRange = 0u;
         bool live = false;
-        if (have && (g.meta & kMetaValid) != 0u)
-            live = prepare_span_triangle(g, triAttr + t, originX, originY, s_tri[threadIdx.x], rowRange);
+        if (have && !marker && (g.meta & kMetaValid) != 0u)
+            live = prepare_span_entry(g, triAttr + t, originX, originY, s_tri[threadIdx.x], rowRange);
         __syncthreads();
         uint32_t groupsBefore = 0u, groupsInChunk = 0u;
 #pragma unroll
@@ -331,6 +409,24 @@ __global__ void __launch_bounds__(256, RIVECUDA_SPAN_MIN_BLOCKS) raster_spans_ke
         const uint32_t group = openGroup + groupsBefore + __popc(flagBits & ((2u << lane) - 1u));
         const uint32_t lastGroup = openGroup + groupsInChunk;
         const uint32_t rows = live ? ((rowRange >> 4) - (rowRange & 15u) + 1u) : 0u;
+#ifdef RIVECUDA_STATS
+        if (have)
+        {
+            const bool isFan = ((g.meta >> kMetaKindShift) & 0xf) == kKindFanEdges;
+            if (marker)
+                SPAN_STAT(6, 1);
+            else
+            {
+                SPAN_STAT(isFan ? 3 : 0, 1);
+                SPAN_STAT(isFan ? 4 : 1, live ? 1 : 0);
+                SPAN_STAT(isFan ? 5 : 2, rows);
+            }
+            if (flag)
+                SPAN_STAT(7, 1);
+        }
+        if (threadIdx.x == 0)
+            SPAN_STAT(13, 1);
+#endif
         if (live)
             s_tri[threadIdx.x].info |= (group & (kSpanSlots - 1)) << 16;
 
@@ -338,9 +434,13 @@ __global__ void __launch_bounds__(256, RIVECUDA_SPAN_MIN_BLOCKS) raster_spans_ke
         for (uint32_t windowStart = openGroup; windowStart <= lastGroup; windowStart += kSpanSlots)
         {
             const bool inWindow = have && group >= windowStart && group < windowStart + kSpanSlots;
+#ifdef RIVECUDA_STATS
+            if (threadIdx.x == 0)
+                SPAN_STAT(14, 1);
+#endif
             if (flag && inWindow)
             {
-                // First entry of a group: its path's paint for resolve_path.
+                // First entry of a group: what the resolve step needs of its path.
                 const uint2 paint = __ldg(P.paintBuffer + pathID);
                 uint32_t meta = g.meta;
                 if ((paint.x & 0xffff0cffu) == kPaintTypeSolid && (g.meta & (kMetaUnmultiplied | kMetaModulatedImage)) == 0u)
@@ -352,10 +452,19 @@ __global__ void __launch_bounds__(256, RIVECUDA_SPAN_MIN_BLOCKS) raster_spans_ke
                     pc.y *= pc.w;
                     pc.z *= pc.w;
                 }
+                int backdrop = 0;
+                if (P.fanPathInfo != nullptr)
+                {
+                    const uint4 info = __ldg(P.fanPathInfo + pathID);
+                    const uint32_t cx = static_cast<uint32_t>(tileX - P.tileX0) - (info.x & 0xffffu), cy = static_cast<uint32_t>(tileY - P.tileY0) - (info.x >> 16);
+                    if (info.z != kFanNoTable && cx < (info.y & 0xffffu) && cy < (info.y >> 16))
+                        backdrop = __ldg(P.fanBackdrop + info.z + cy * (info.y & 0xffffu) + cx) << 16;
+                }
                 SpanSlot& slot = s_slot[group & (kSpanSlots - 1)];
                 slot.meta = meta;
                 slot.paintX = paint.x;
                 slot.paintY = paint.y;
+                slot.backdrop = backdrop;
                 slot.solid[0] = pc.x;
                 slot.solid[1] = pc.y;
                 slot.solid[2] = pc.z;
@@ -399,29 +508,66 @@ __global__ void __launch_bounds__(256, RIVECUDA_SPAN_MIN_BLOCKS) raster_spans_ke
                 const int row = static_cast<int>(unit & 15u);
                 const uint4 w0 = lds_u32x4(T), w1 = lds_u32x4(T + 16), w2 = lds_u32x4(T + 32), w3 = lds_u32x4(T + 48);
                 const uint32_t info = w3.w;
+                const uint32_t rowAddr = planesAddr + ((info >> 16) & 0xffu) * 1024u + static_cast<uint32_t>(row) * 64u;
+                const int v0 = static_cast<int>(w0.z) + static_cast<int>(w0.y) * row;
+                const int v1 = static_cast<int>(w1.y) + static_cast<int>(w1.x) * row;
+                const int v2 = static_cast<int>(w2.x) + static_cast<int>(w1.w) * row;
+                if ((info & kSpanFanEdges) != 0u)
+                {
+                    // Boundary edges of a wedge: +-weight from the pixel where this row crosses the
+                    // edge, and at pixel 0 if the tile's column 0 crossed the edge above this row.
+                    const int weight = static_cast<int>(w2.y);
+                    const uint32_t packed = w2.z;
+                    const int A[3] = {static_cast<int>(w0.x), static_cast<int>(w0.w), static_cast<int>(w1.z)};
+                    const int v[3] = {v0, v1, v2};
+                    const int q[3] = {static_cast<int>(w0.z), static_cast<int>(w1.y), static_cast<int>(w2.x)};
+#pragma unroll
+                    for (int e = 0; e < 3; ++e)
+                    {
+                        const uint32_t bits = (packed >> (10 * e)) & 0x3ffu;
+                        if ((bits & 0x100u) != 0u && row >= static_cast<int>(bits & 15u) && row <= static_cast<int>((bits >> 4) & 15u))
+                        {
+                            int lo = -100, hi = 100;
+                            span_edge(A[e], v[e], lo, hi);
+                            const int ic = A[e] > 0 ? lo : hi + 1;
+                            if (ic >= 1 && ic <= kTileSize - 1)
+                                red_add_shared(rowAddr + static_cast<uint32_t>(ic) * 4u, A[e] > 0 ? weight : -weight);
+                        }
+                        if ((bits & 0x200u) != 0u)
+                        {
+                            const int d = (v[e] >= 0 ? 1 : 0) - (q[e] >= 0 ? 1 : 0);
+                            if (d != 0)
+                                red_add_shared(rowAddr, d > 0 ? weight : -weight);
+                        }
+                    }
+                    continue;
+                }
                 int lo = static_cast<int>((info >> 8) & 15u), hi = static_cast<int>((info >> 12) & 15u);
-                span_edge(static_cast<int>(w0.x), static_cast<int>(w0.z) + static_cast<int>(w0.y) * row, lo, hi);
-                span_edge(static_cast<int>(w0.w), static_cast<int>(w1.y) + static_cast<int>(w1.x) * row, lo, hi);
-                span_edge(static_cast<int>(w1.z), static_cast<int>(w2.x) + static_cast<int>(w1.w) * row, lo, hi);
+                span_edge(static_cast<int>(w0.x), v0, lo, hi);
+                span_edge(static_cast<int>(w0.w), v1, lo, hi);
+                span_edge(static_cast<int>(w1.z), v2, lo, hi);
                 if (lo > hi)
                     continue;
-                const uint32_t rowAddr = planesAddr + ((info >> 16) & 0xffu) * 1024u + static_cast<uint32_t>(row) * 64u;
-                const uint32_t swz = static_cast<uint32_t>(row & 2) << 2;
                 const float frow = static_cast<float>(row);
                 if ((info & kSpanFlat) != 0u)
                 {
-                    const int add = ((__float2int_rn(__uint_as_float(w2.y)) + 128) & ~0xff) | 1;
-                    for (int x = lo; x <= hi; ++x)
-                        red_add_shared(rowAddr + ((static_cast<uint32_t>(x) ^ swz) << 2), add);
+                    const int add = __float2int_rn(__uint_as_float(w2.y));
+                    red_add_shared(rowAddr + static_cast<uint32_t>(lo) * 4u, add);
+                    if (hi < kTileSize - 1)
+                        red_add_shared(rowAddr + static_cast<uint32_t>(hi + 1) * 4u, -add);
                 }
                 else if ((info & kSpanStroke) == 0u)
                 {
                     const float c0 = __fmaf_rn(__uint_as_float(w2.w), frow, __uint_as_float(w2.y)), cx = __uint_as_float(w2.z);
+                    int prev = 0;
                     for (int x = lo; x <= hi; ++x)
                     {
-                        const int add = ((__float2int_rn(__fmaf_rn(cx, static_cast<float>(x), c0)) + 128) & ~0xff) | 1;
-                        red_add_shared(rowAddr + ((static_cast<uint32_t>(x) ^ swz) << 2), add);
+                        const int cur = __float2int_rn(__fmaf_rn(cx, static_cast<float>(x), c0));
+                        red_add_shared(rowAddr + static_cast<uint32_t>(x) * 4u, cur - prev);
+                        prev = cur;
                     }
+                    if (hi < kTileSize - 1)
+                        red_add_shared(rowAddr + static_cast<uint32_t>(hi + 1) * 4u, -prev);
                 }
                 else
                 {
@@ -432,7 +578,7 @@ __global__ void __launch_bounds__(256, RIVECUDA_SPAN_MIN_BLOCKS) raster_spans_ke
                         const float fx = static_cast<float>(x);
                         const float c = fminf(__fmaf_rn(c0x, fx, c0), __fmaf_rn(c1x, fx, c1));
                         if (c > 0.f)
-                            red_max_shared(rowAddr + ((static_cast<uint32_t>(x) ^ swz) << 2), __float_as_int(c));
+                            red_max_shared(rowAddr + static_cast<uint32_t>(x) * 4u, __float_as_int(c));
                     }
                 }
             }
@@ -444,20 +590,53 @@ __global__ void __launch_bounds__(256, RIVECUDA_SPAN_MIN_BLOCKS) raster_spans_ke
             for (uint32_t gi = windowStart; gi < resolveEnd; ++gi)
             {
                 const uint32_t slotIdx = gi & (kSpanSlots - 1);
-                const uint32_t wordAddr = planesAddr + slotIdx * 1024u + myWord * 4u;
+                const uint32_t wordAddr = planesAddr + slotIdx * 1024u + threadIdx.x * 4u;
+                const uint32_t slotAddr = slotsAddr + slotIdx * static_cast<uint32_t>(sizeof(SpanSlot));
                 const int v = static_cast<int>(lds_u32(wordAddr));
-                if (v == 0)
-                    continue;
-                asm volatile("st.shared.u32 [%0], %1;" ::"r"(wordAddr), "r"(0) : "memory");
-                const uint32_t slotAddr = static_cast<uint32_t>(__cvta_generic_to_shared(&s_slot[slotIdx]));
                 const uint4 rec = lds_u32x4(slotAddr);
+                const bool any = __any_sync(0xffffffffu, v != 0);
+                if (!any && rec.w == 0u)
+                    continue;
+                if (v != 0)
+                    asm volatile("st.shared.u32 [%0], %1;" ::"r"(wordAddr), "r"(0) : "memory");
+                float coverageCount;
+                if (((rec.x >> kMetaKindShift) & 0xf) == kKindStroke)
+                {
+                    coverageCount = __int_as_float(v);
+                }
+                else
+                {
+                    int acc = v;
+                    if (any)
+                    {
+#pragma unroll
+                        for (int o = 1; o < 16; o <<= 1)
+                        {
+                            const int up = __shfl_up_sync(0xffffffffu, acc, o, 16);
+                            if (i >= o)
+                                acc += up;
+                        }
+                    }
+                    acc += static_cast<int>(rec.w);
+                    coverageCount = static_cast<float>(acc) * (1.f / kSpanFixedOne);
+                }
+#ifdef RIVECUDA_STATS
+                if (lane == 0)
+                    SPAN_STAT(8, 1);
+                {
+                    const uint32_t nz = __ballot_sync(__activemask(), coverageCount != 0.f);
+                    if (lane == 0)
+                    {
+                        SPAN_STAT(9, nz != 0u ? 1 : 0);
+                        SPAN_STAT(10, __popc(nz));
+                    }
+                }
+#endif
+                if (coverageCount == 0.f)
+                    continue;
                 const float4 solid = lds_f32x4(slotAddr + 16);
-                const uint32_t kind = (rec.x >> kMetaKindShift) & 0xf;
-                const float coverageCount = kind == kKindStroke ? __int_as_float(v) : static_cast<float>(v >> 8) * (1.f / 16384.f);
                 resolve_path(P, rec.x, rec.y, rec.z, solid, coverageCount, px, py, s);
             }
-            // (No barrier here: the next window's slot records and fills are separated from this
-            // resolve by the scan barrier below / the chunk barrier above.)
             if (windowStart + kSpanSlots <= lastGroup)
                 __syncthreads();
         }
