@@ -55,7 +55,6 @@ enum TriKind : uint32_t
     kKindFeatherStroke = 3, // coverage = max(coverage, eval_feathered_stroke)
     kKindAtlasBlit = 4,     // immediate blend, coverage from the atlas
     kKindImageMesh = 5,     // immediate blend, colour from an image
-    kKindFanEdges = 6,      // span rasteriser only: the boundary edges of a fill's midpoint-fan wedge (see FanTables)
 };
 
 constexpr float kAtlasFixedOne = 65536.f; // the feather atlas holds 16.16 fixed-point coverage
@@ -70,6 +69,9 @@ constexpr uint32_t kMetaClipping = 1u << 26;       // image meshes: batch has EN
 constexpr uint32_t kMetaRewound = 1u << 24;        // vertices 1 and 2 were exchanged to make the triangle clockwise (image meshes)
 constexpr uint32_t kMetaSimplePaint = 1u << 25;    // set by the rasteriser's prepare step, never stored
 constexpr uint32_t kMetaKindShift = 16;
+// TriGeom::aux of a plain fill's patch triangle in a span-rasterised flush: bits 2k..2k+1 = the
+// coverage at vertex k (0: 0, 1: +1, 2: -1); such a triangle has no TriAttr record.
+constexpr uint32_t kAuxCoverageCodes = 1u << 31;
 
 struct TriGeom // 32 B
 {
@@ -125,35 +127,8 @@ struct FlushParams
     const struct ImageSlot* images; // per-flush table of (texture, sampler) for batches that bind one
     uint16_t* pathImageSlots;       // pathID -> index into `images` (written by setup for image paints)
     TriPos* triPos;                 // non-null: the flush runs raster_tiles_exact_kernel (raster_tiles_exact.cuh)
-    // Span rasteriser, fan winding (see FanTables below). Null / 0 otherwise.
-    const uint4* fanPathInfo;       // per path: tile rect of its backdrop cells, their base, the marker key
-    const int32_t* fanBackdrop;     // cells: the path's winding at pixel (0,0) of each tile of its rect
-    uint32_t keyShift;              // tile-list entries are raw id << keyShift (| 1: backdrop marker)
+    uint32_t spans;                 // the flush runs raster_spans_kernel (raster_tiles_span.cuh)
 };
-
-// Fan winding (span rasteriser). The midpoint-fan wedges of a fill -- triangles (F_k, F_k+1, M) from
-// two patch-boundary fan vertices to the contour midpoint, drawn only when clockwise -- cover many
-// times the path's area with +1 / -1 that mostly cancel. Their sum is a winding number: instead of
-// rasterising the wedges, the span rasteriser accumulates the crossings of their boundary edges
-// (rim F_k -> F_k+1 plus the spokes that no drawn neighbour wedge cancels), with exactly the
-// inside tests the triangles would use (top-left rule on the snapped vertices), so the result is
-// the same integer at every pixel:
-//   W(i,j) = W(C_T) + sum_{e straddles column 0 of the tile} w (in_e(0,j) - in_e(0,0))
-//                   + sum_{e straddles row j}               w (in_e(i,j) - in_e(0,j))
-// where in_e is the edge's biased half-plane test and W(C_T), the winding at the tile's pixel (0,0)
-// ("backdrop"), is a prefix sum along the tile row of the edges that cross that row's first pixel
-// row. Backdrop cells live in one table per path covering the tile rectangle of its bounds; tiles
-// with a non-zero backdrop get a marker entry in their list so that the path resolves there.
-struct FanTables
-{
-    int4* pathBounds;     // per path: pixel bounds of its fan vertices (min x, min y, max x, max y)
-    uint4* pathInfo;      // per path: tx0 | ty0 << 16, w | h << 16 (tile rect in the flush grid), cell base (~0u: none), marker key
-    int32_t* backdrop;    // cells
-    uint32_t* totals;     // [0] cells used, [1] cells the flush would need
-    uint32_t capacity;    // cells available
-    uint32_t pathCount;   // path ids 0..pathCount
-};
-constexpr uint32_t kFanNoTable = 0xffffffffu;
 
 // A bound image: rivecuda_draw_batch::image_texture + image_sampler.
 struct ImageSlot
@@ -572,61 +547,6 @@ __device__ __forceinline__ bool tile_overlaps(const EdgeEq E[3], int tileX, int 
     return true;
 }
 
-// Fan-edge records (kKindFanEdges) are binned by their active edges, not by the wedge's area:
-// edge e of the record's triangle runs from vertex (e+1)%3 to vertex (e+2)%3, as prepare_triangle
-// numbers them. A tile needs an edge iff the segment meets the closed box of the tile's pixel
-// centres (that is where the tile's column 0 and its pixel rows can cross it).
-__device__ __forceinline__ TileRange edges_tile_range(const FlushParams& P, const int32_t X[3], const int32_t Y[3], uint32_t edgeMask)
-{
-    // Vertices the active edges use: one edge -> its two ends, more -> all three.
-    const bool v0 = (edgeMask & 6u) != 0u, v1 = (edgeMask & 5u) != 0u, v2 = (edgeMask & 3u) != 0u;
-    const int32_t big = 0x7fffffff;
-    const int32_t minX = min(v0 ? X[0] : big, min(v1 ? X[1] : big, v2 ? X[2] : big)), maxX = max(v0 ? X[0] : -big, max(v1 ? X[1] : -big, v2 ? X[2] : -big));
-    const int32_t minY = min(v0 ? Y[0] : big, min(v1 ? Y[1] : big, v2 ? Y[2] : big)), maxY = max(v0 ? Y[0] : -big, max(v1 ? Y[1] : -big, v2 ? Y[2] : -big));
-    constexpr int shift = kTileSizeLog2 + 8, last = ((kTileSize - 1) << 8) + 128; // a tile's centres span [t << shift) + 128, (t << shift) + last]
-    int tx0 = (minX - last + (1 << shift) - 1) >> shift, tx1 = (maxX - 128) >> shift;
-    int ty0 = (minY - last + (1 << shift) - 1) >> shift, ty1 = (maxY - 128) >> shift;
-    tx0 = max(tx0 - P.tileX0, 0);
-    ty0 = max(ty0 - P.tileY0, 0);
-    tx1 = min(tx1 - P.tileX0, static_cast<int>(P.tilesX) - 1);
-    ty1 = min(ty1 - P.tileY0, static_cast<int>(P.tilesY) - 1);
-    TileRange r;
-    r.tx0 = tx0;
-    r.tx1 = tx1;
-    r.ty0 = ty0;
-    r.ty1 = ty1;
-    if (tx0 > tx1 || ty0 > ty1)
-    {
-        r.tx0 = 1;
-        r.tx1 = 0;
-        r.ty0 = 1;
-        r.ty1 = 0;
-    }
-    return r;
-}
-
-__device__ __forceinline__ bool edges_overlap_tile(const int32_t X[3], const int32_t Y[3], uint32_t edgeMask, int tileX, int tileY)
-{
-    const int32_t cx0 = (tileX << (kTileSizeLog2 + 8)) + 128, cy0 = (tileY << (kTileSizeLog2 + 8)) + 128;
-    const int32_t span = (kTileSize - 1) << 8;
-#pragma unroll
-    for (int e = 0; e < 3; ++e)
-    {
-        if ((edgeMask & (1u << e)) == 0u)
-            continue;
-        const int a = (e + 1) % 3, b = (e + 2) % 3;
-        if (max(min(X[a], X[b]), cx0) > min(max(X[a], X[b]), cx0 + span) || max(min(Y[a], Y[b]), cy0) > min(max(Y[a], Y[b]), cy0 + span))
-            continue;
-        const int32_t dx = X[b] - X[a], dy = Y[b] - Y[a];
-        const int64_t base = static_cast<int64_t>(dx) * (cy0 - Y[a]) - static_cast<int64_t>(dy) * (cx0 - X[a]);
-        const int64_t ex = -static_cast<int64_t>(dy) * span, ey = static_cast<int64_t>(dx) * span;
-        const int64_t lo = base + (ex < 0 ? ex : 0) + (ey < 0 ? ey : 0), hi = base + (ex > 0 ? ex : 0) + (ey > 0 ? ey : 0);
-        if (lo <= 0 && hi >= 0)
-            return true;
-    }
-    return false;
-}
-
 // Visits the tiles a triangle overlaps (tile index = ty*tilesX+tx in the flush's tile
 // grid), warp-cooperatively: every lane of the warp calls this (valid = lane has a
 // triangle). Triangles that overlap only a few tiles are walked by their own
@@ -647,7 +567,7 @@ enum TileWalk : int
 };
 
 template <typename Fn>
-__device__ __forceinline__ TileWalk warp_for_each_tile(const FlushParams& P, const int32_t X[3], const int32_t Y[3], bool valid, Fn&& fn, uint32_t edgeMask = 0u)
+__device__ __forceinline__ TileWalk warp_for_each_tile(const FlushParams& P, const int32_t X[3], const int32_t Y[3], bool valid, Fn&& fn)
 {
     const int lane = threadIdx.x & 31;
     TileRange r;
@@ -656,7 +576,7 @@ __device__ __forceinline__ TileWalk warp_for_each_tile(const FlushParams& P, con
     r.ty0 = 1;
     r.ty1 = 0;
     if (valid)
-        r = edgeMask != 0u ? edges_tile_range(P, X, Y, edgeMask) : triangle_tile_range(P, X, Y);
+        r = triangle_tile_range(P, X, Y);
     const int w = r.tx1 - r.tx0 + 1, h = r.ty1 - r.ty0 + 1;
     const int count = (r.tx0 > r.tx1) ? 0 : w * h;
     if (count > 0 && count <= kSmallTileCount)
@@ -665,7 +585,7 @@ __device__ __forceinline__ TileWalk warp_for_each_tile(const FlushParams& P, con
         edge_equations(X, Y, E);
         for (int ty = r.ty0; ty <= r.ty1; ++ty)
             for (int tx = r.tx0; tx <= r.tx1; ++tx)
-                if (edgeMask != 0u ? edges_overlap_tile(X, Y, edgeMask, tx + P.tileX0, ty + P.tileY0) : (count == 1 || tile_overlaps(E, tx + P.tileX0, ty + P.tileY0)))
+                if (count == 1 || tile_overlaps(E, tx + P.tileX0, ty + P.tileY0))
                     fn(static_cast<uint32_t>(ty) * P.tilesX + static_cast<uint32_t>(tx), lane, false);
     }
     uint32_t big = __ballot_sync(0xffffffffu, count > kSmallTileCount && count <= kHugeTileCount);
@@ -682,13 +602,12 @@ __device__ __forceinline__ TileWalk warp_for_each_tile(const FlushParams& P, con
         }
         const int tx0 = __shfl_sync(0xffffffffu, r.tx0, src), ty0 = __shfl_sync(0xffffffffu, r.ty0, src);
         const int bw = __shfl_sync(0xffffffffu, w, src), bcount = __shfl_sync(0xffffffffu, count, src);
-        const uint32_t bmask = __shfl_sync(0xffffffffu, edgeMask, src);
         EdgeEq E[3];
         edge_equations(BX, BY, E);
         for (int idx = lane; idx < bcount; idx += 32)
         {
             const int ty = ty0 + idx / bw, tx = tx0 + idx % bw;
-            if (bmask != 0u ? edges_overlap_tile(BX, BY, bmask, tx + P.tileX0, ty + P.tileY0) : tile_overlaps(E, tx + P.tileX0, ty + P.tileY0))
+            if (tile_overlaps(E, tx + P.tileX0, ty + P.tileY0))
                 fn(static_cast<uint32_t>(ty) * P.tilesX + static_cast<uint32_t>(tx), src, true);
         }
     }
@@ -713,7 +632,7 @@ struct BinTables
 };
 constexpr uint8_t kBinBig = 0xff, kBinHuge = 0xfe;
 
-__device__ __forceinline__ void bin_triangle(const FlushParams& P, const BinTables& B, const int32_t X[3], const int32_t Y[3], bool stored, bool hasSlot, uint32_t rawTri, uint32_t edgeMask = 0u)
+__device__ __forceinline__ void bin_triangle(const FlushParams& P, const BinTables& B, const int32_t X[3], const int32_t Y[3], bool stored, bool hasSlot, uint32_t rawTri)
 {
     uint32_t n = 0;
     const TileWalk walk = warp_for_each_tile(P, X, Y, stored, [&](uint32_t tile, int, bool cooperative) {
@@ -727,12 +646,12 @@ __device__ __forceinline__ void bin_triangle(const FlushParams& P, const BinTabl
             B.binPairs[static_cast<size_t>(rawTri) * kSmallTileCount + n] = make_uint2(tile, rank);
             ++n;
         }
-    }, edgeMask);
+    });
     if (walk == kWalkHuge)
     {
         // A few per frame (backgrounds, big interior triangles): queue the tile
         // range in chunks, one CTA of bin_huge_kernel each.
-        const TileRange r = edgeMask != 0u ? edges_tile_range(P, X, Y, edgeMask) : triangle_tile_range(P, X, Y);
+        const TileRange r = triangle_tile_range(P, X, Y);
         const uint32_t total = static_cast<uint32_t>(r.tx1 - r.tx0 + 1) * static_cast<uint32_t>(r.ty1 - r.ty0 + 1);
         const uint32_t chunks = (total + kHugeChunkTiles - 1) / kHugeChunkTiles;
         const uint32_t first = atomicAdd(B.hugeCount, chunks);
@@ -772,9 +691,7 @@ __global__ void __launch_bounds__(256) bin_huge_kernel(FlushParams P,
         const uint2 hi = __ldg(reinterpret_cast<const uint2*>(triGeom + t) + 2);
         const int32_t X[3] = {static_cast<int32_t>(lo.x), static_cast<int32_t>(lo.z), static_cast<int32_t>(hi.x)};
         const int32_t Y[3] = {static_cast<int32_t>(lo.y), static_cast<int32_t>(lo.w), static_cast<int32_t>(hi.y)};
-        const uint2 tail = __ldg(reinterpret_cast<const uint2*>(triGeom + t) + 3); // meta, aux
-        const uint32_t edgeMask = ((tail.x >> kMetaKindShift) & 0xf) == kKindFanEdges ? (tail.y & 7u) : 0u;
-        const TileRange r = edgeMask != 0u ? edges_tile_range(P, X, Y, edgeMask) : triangle_tile_range(P, X, Y);
+        const TileRange r = triangle_tile_range(P, X, Y);
         if (r.tx0 > r.tx1)
             continue;
         const uint32_t w = static_cast<uint32_t>(r.tx1 - r.tx0 + 1), total = w * static_cast<uint32_t>(r.ty1 - r.ty0 + 1);
@@ -784,14 +701,14 @@ __global__ void __launch_bounds__(256) bin_huge_kernel(FlushParams P,
         for (uint32_t idx = work.y * kHugeChunkTiles + threadIdx.x; idx < end; idx += blockDim.x)
         {
             const int ty = r.ty0 + static_cast<int>(idx / w), tx = r.tx0 + static_cast<int>(idx % w);
-            if (edgeMask != 0u ? !edges_overlap_tile(X, Y, edgeMask, tx + P.tileX0, ty + P.tileY0) : !tile_overlaps(E, tx + P.tileX0, ty + P.tileY0))
+            if (!tile_overlaps(E, tx + P.tileX0, ty + P.tileY0))
                 continue;
             const uint32_t tile = static_cast<uint32_t>(ty) * P.tilesX + static_cast<uint32_t>(tx);
             if (SCATTER)
             {
                 const uint32_t pos = __ldg(tileOffsets + tile) + __ldg(bins.smallCounts + tile) + atomicAdd(bigCursors + tile, 1u);
                 if (pos < entryCapacity)
-                    entries[pos] = t << P.keyShift;
+                    entries[pos] = t;
             }
             else
             {
@@ -891,7 +808,8 @@ __device__ __forceinline__ bool store_triangle(const FlushParams& P,
     g.aux = aux;
     triGeom[rawTri] = g;
     float4* dst = reinterpret_cast<float4*>(triAttr + rawTri);
-    dst[0] = make_float4(attr[0], attr[1], attr[2], attr[3]);
+    if (attrComponents > 0)
+        dst[0] = make_float4(attr[0], attr[1], attr[2], attr[3]);
     if (attrComponents > 1)
         dst[1] = make_float4(attr[4], attr[5], attr[6], attr[7]);
     if (attrComponents > 2)
@@ -904,276 +822,6 @@ __device__ __forceinline__ bool store_triangle(const FlushParams& P,
         pos[2] = make_float2(px[2], py[2]);
     }
     return true;
-}
-
-#ifdef RIVECUDA_STATS
-__device__ unsigned long long g_spanStats[16]; // see raster_tiles_span.cuh
-#endif
-// ---------------------------------------------------------------------------
-// Fan winding tables (see FanTables)
-
-__device__ __forceinline__ uint32_t find_batch(const DeviceBatch* __restrict__ batches, uint32_t batchCount, uint32_t workItem);
-
-__device__ __forceinline__ int64_t floor_div64(int64_t a, int64_t b) // b > 0
-{
-    int64_t q = a / b;
-    if ((a % b) < 0)
-        --q;
-    return q;
-}
-__device__ __forceinline__ int64_t ceil_div64(int64_t a, int64_t b) { return -floor_div64(-a, b); }
-
-// Pixel bounds of every fill's midpoint-fan vertices: one thread per patch instance, warp-aggregated
-// per path. pathBounds holds (min x, min y, -max x, -max y), all reduced with atomicMin.
-__global__ void __launch_bounds__(256) fan_bounds_kernel(FlushParams P, const DeviceBatch* __restrict__ batches, uint32_t batchCount, uint32_t totalInstances, int4* __restrict__ pathBounds)
-{
-    for (uint32_t itemBase = blockIdx.x * blockDim.x; itemBase < totalInstances; itemBase += gridDim.x * blockDim.x)
-    {
-        const uint32_t item = itemBase + threadIdx.x;
-        uint32_t pathID = 0xffffffffu;
-        float x0 = 3e38f, y0 = 3e38f, x1 = -3e38f, y1 = -3e38f;
-        if (item < totalInstances)
-        {
-            const uint32_t bi = find_batch(batches, batchCount, item);
-            const uint32_t drawType = __ldg(&batches[bi].drawType);
-            if (drawType == RIVECUDA_DRAW_MIDPOINT_FAN_PATCHES)
-            {
-                const int instanceID = static_cast<int>(__ldg(&batches[bi].baseElement) + (item - __ldg(&batches[bi].firstWorkItem)));
-                const uint4 first = tess_fetch(P, instanceID * 8);
-                const uint32_t contourID = max(first.w & kContourIDMask, 1u);
-                const uint4 contourData = __ldg(P.contourBuffer + (contourID - 1u));
-                const uint32_t id = contourData.z & 0xffffu;
-                const uint4 m4 = __ldg(P.pathBuffer + id * 4u);
-                const uint4 pd = __ldg(P.pathBuffer + id * 4u + 1u);
-                if (__uint_as_float(pd.z) == 0.f) // fills only
-                {
-                    pathID = id;
-                    const m22 M = {__uint_as_float(m4.x), __uint_as_float(m4.y), __uint_as_float(m4.z), __uint_as_float(m4.w)};
-                    const f2 translate = mk2(__uint_as_float(pd.x), __uint_as_float(pd.y));
-                    for (int v = -1; v <= 9; ++v)
-                    {
-                        f2 local;
-                        if (v == 9)
-                        {
-                            local = mk2(__uint_as_float(contourData.x), __uint_as_float(contourData.y));
-                        }
-                        else
-                        {
-                            const uint4 tv = tess_fetch(P, instanceID * 8 + v);
-                            local = mk2(__uint_as_float(tv.x), __uint_as_float(tv.y));
-                        }
-                        const f2 q = mul(M, local) + translate;
-                        if (fabsf(q.x) < 1e30f && fabsf(q.y) < 1e30f)
-                        {
-                            x0 = fminf(x0, q.x);
-                            x1 = fmaxf(x1, q.x);
-                            y0 = fminf(y0, q.y);
-                            y1 = fmaxf(y1, q.y);
-                        }
-                    }
-                }
-            }
-        }
-        // Two pixels of margin: the fan vertices sit half a pixel (Manhattan) off the curve.
-        const float lim = 2097152.f;
-        int ix0 = static_cast<int>(floorf(fminf(fmaxf(x0, -lim), lim))) - 2, iy0 = static_cast<int>(floorf(fminf(fmaxf(y0, -lim), lim))) - 2;
-        int ix1 = static_cast<int>(ceilf(fminf(fmaxf(x1, -lim), lim))) + 2, iy1 = static_cast<int>(ceilf(fminf(fmaxf(y1, -lim), lim))) + 2;
-        const bool have = pathID != 0xffffffffu && x0 <= x1;
-        const uint32_t key = have ? pathID : 0xffffffffu;
-        const uint32_t group = __match_any_sync(0xffffffffu, key);
-        ix0 = __reduce_min_sync(group, ix0);
-        iy0 = __reduce_min_sync(group, iy0);
-        ix1 = __reduce_max_sync(group, ix1);
-        iy1 = __reduce_max_sync(group, iy1);
-        if (have && (__ffs(group) - 1) == static_cast<int>(threadIdx.x & 31))
-        {
-            int* dst = reinterpret_cast<int*>(pathBounds + pathID);
-            atomicMin(dst + 0, ix0);
-            atomicMin(dst + 1, iy0);
-            atomicMin(dst + 2, -ix1);
-            atomicMin(dst + 3, -iy1);
-        }
-    }
-}
-
-// One CTA: the tile rectangle of every path's bounds inside the flush's tile grid, and its cells.
-__global__ void __launch_bounds__(1024) fan_alloc_kernel(FlushParams P, FanTables F)
-{
-    __shared__ uint32_t s[32];
-    __shared__ uint32_t s_running;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (threadIdx.x == 0)
-        s_running = 0u;
-    __syncthreads();
-    for (uint32_t base = 0; base <= F.pathCount; base += 1024)
-    {
-        const uint32_t p = base + threadIdx.x;
-        uint32_t cells = 0u, rectXY = 0u, rectWH = 0u;
-        if (p <= F.pathCount)
-        {
-            const int4 b = F.pathBounds[p];
-            const int px0 = max(b.x, P.boundsL), py0 = max(b.y, P.boundsT), px1 = min(-b.z, P.boundsR - 1), py1 = min(-b.w, P.boundsB - 1);
-            if (b.x != 0x7f7f7f7f && px0 <= px1 && py0 <= py1)
-            {
-                const int tx0 = (px0 >> kTileSizeLog2) - P.tileX0, ty0 = (py0 >> kTileSizeLog2) - P.tileY0;
-                const int tx1 = (px1 >> kTileSizeLog2) - P.tileX0, ty1 = (py1 >> kTileSizeLog2) - P.tileY0;
-                const uint32_t w = static_cast<uint32_t>(tx1 - tx0 + 1), h = static_cast<uint32_t>(ty1 - ty0 + 1);
-                cells = w * h;
-                rectXY = static_cast<uint32_t>(tx0) | (static_cast<uint32_t>(ty0) << 16);
-                rectWH = w | (h << 16);
-            }
-        }
-        uint32_t incl = cells;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1)
-        {
-            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o)
-                incl += t;
-        }
-        if (lane == 31)
-            s[warp] = incl;
-        __syncthreads();
-        uint32_t before = 0u, total = 0u;
-        for (int w = 0; w < 32; ++w)
-        {
-            const uint32_t c = s[w];
-            before += w < warp ? c : 0u;
-            total += c;
-        }
-        const uint32_t running = s_running;
-        const uint64_t start = static_cast<uint64_t>(running) + before + incl - cells;
-        if (p <= F.pathCount)
-            F.pathInfo[p] = make_uint4(rectXY, rectWH, (cells != 0u && start + cells <= F.capacity) ? static_cast<uint32_t>(start) : kFanNoTable, 0xffffffffu);
-        __syncthreads();
-        if (threadIdx.x == 0)
-            s_running = static_cast<uint32_t>(min(static_cast<uint64_t>(running) + total, static_cast<uint64_t>(0xfffffff0u)));
-        __syncthreads();
-    }
-    if (threadIdx.x == 0)
-    {
-        F.totals[0] = min(s_running, F.capacity);
-        F.totals[1] = s_running;
-    }
-}
-
-__global__ void __launch_bounds__(256) fan_zero_kernel(FanTables F)
-{
-    const uint32_t n = F.totals[0];
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
-        F.backdrop[i] = 0;
-}
-
-// The crossings of one wedge record's active edges with the first pixel row of every tile row:
-// a delta in the path's backdrop table at the first tile whose pixel (0,0) lies beyond the
-// crossing (fan_backdrop_kernel turns the deltas into prefix sums along each tile row).
-__device__ __forceinline__ void fan_edge_deltas(const FlushParams& P, const FanTables& F, uint4 info, const int32_t X[3], const int32_t Y[3], uint32_t edgeMask, int weight)
-{
-    const int tx0 = static_cast<int>(info.x & 0xffffu) + P.tileX0, ty0 = static_cast<int>(info.x >> 16) + P.tileY0; // absolute tile coordinates
-    const int w = static_cast<int>(info.y & 0xffffu), h = static_cast<int>(info.y >> 16);
-    constexpr int shift = kTileSizeLog2 + 8;
-#pragma unroll
-    for (int e = 0; e < 3; ++e)
-    {
-        if ((edgeMask & (1u << e)) == 0u)
-            continue;
-        const int a = (e + 1) % 3, b = (e + 2) % 3;
-        const int32_t dx = X[b] - X[a], dy = Y[b] - Y[a];
-        if (dy == 0)
-            continue;
-        const int32_t ylo = min(Y[a], Y[b]), yhi = max(Y[a], Y[b]);
-        // Tile rows r whose first pixel row y_r = (r << shift) + 128 satisfies ylo <= y_r < yhi.
-        int r0 = (ylo - 128 + (1 << shift) - 1) >> shift, r1 = ((yhi - 128 + (1 << shift) - 1) >> shift) - 1;
-        r0 = max(r0, ty0);
-        r1 = min(r1, ty0 + h - 1);
-        for (int r = r0; r <= r1; ++r)
-        {
-            const int32_t yr = (r << shift) + 128;
-            // E(px) = K - 256 dy px at pixel column px of that row.
-            const int64_t K = static_cast<int64_t>(dx) * (yr - Y[a]) - static_cast<int64_t>(dy) * (128 - X[a]);
-            int64_t pstar;
-            int delta;
-            if (dy > 0)
-            {
-                pstar = floor_div64(K - 1, 256ll * dy) + 1; // inside (E - 1 >= 0) up to pstar - 1
-                delta = -weight;
-            }
-            else
-            {
-                pstar = ceil_div64(-K, -256ll * dy); // inside (E >= 0) from pstar on
-                delta = weight;
-            }
-            const int64_t tstar = pstar <= static_cast<int64_t>(tx0) * kTileSize ? tx0 : ((pstar + kTileSize - 1) >> kTileSizeLog2);
-            const int64_t col = tstar - tx0;
-            if (col >= w)
-                continue;
-            atomicAdd(const_cast<int32_t*>(F.backdrop) + info.z + static_cast<uint32_t>(r - ty0) * static_cast<uint32_t>(w) + static_cast<uint32_t>(col), delta);
-        }
-    }
-}
-
-// One warp per path: prefix sums of the backdrop deltas along every tile row of the path's
-// rectangle (COUNT pass, in place), and a marker entry for every tile whose backdrop is not zero
-// (counted in the COUNT pass, written after the tile scan in the SCATTER pass).
-template <bool SCATTER>
-__global__ void __launch_bounds__(256) fan_backdrop_kernel(FlushParams P,
-                                                           FanTables F,
-                                                           BinTables bins,
-                                                           const uint32_t* __restrict__ tileOffsets,
-                                                           uint32_t* __restrict__ bigCursors,
-                                                           uint32_t* __restrict__ entries,
-                                                           const uint32_t* __restrict__ entryTotal,
-                                                           uint32_t entryCapacity)
-{
-    if (SCATTER && __ldg(entryTotal) > entryCapacity)
-        return;
-    const int lane = threadIdx.x & 31;
-    const uint32_t warpsPerGrid = gridDim.x * (blockDim.x >> 5);
-    for (uint32_t p = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); p <= F.pathCount; p += warpsPerGrid)
-    {
-        const uint4 info = F.pathInfo[p];
-        if (info.z == kFanNoTable || info.w == 0xffffffffu)
-            continue; // no table, or no wedge was drawn: every cell is zero
-        const uint32_t tx0 = info.x & 0xffffu, ty0 = info.x >> 16, w = info.y & 0xffffu, h = info.y >> 16;
-        const uint32_t markerKey = (info.w << 1) | 1u;
-        for (uint32_t row = 0; row < h; ++row)
-        {
-            int32_t* cells = F.backdrop + info.z + row * w;
-            const uint32_t tileRow = (ty0 + row) * P.tilesX + tx0;
-            int carry = 0;
-            for (uint32_t colBase = 0; colBase < w; colBase += 32)
-            {
-                const uint32_t col = colBase + lane;
-                int v = col < w ? cells[col] : 0;
-                if (!SCATTER)
-                {
-                    int incl = v;
-#pragma unroll
-                    for (int o = 1; o < 32; o <<= 1)
-                    {
-                        const int t = __shfl_up_sync(0xffffffffu, incl, o);
-                        if (lane >= o)
-                            incl += t;
-                    }
-                    v = incl + carry;
-                    carry = __shfl_sync(0xffffffffu, v, 31);
-                    if (col < w)
-                    {
-                        cells[col] = v;
-                        if (v != 0)
-                            atomicAdd(bins.bigCounts + tileRow + col, 1u);
-                    }
-                }
-                else if (col < w && v != 0)
-                {
-                    const uint32_t tile = tileRow + col;
-                    const uint32_t pos = __ldg(tileOffsets + tile) + __ldg(bins.smallCounts + tile) + atomicAdd(bigCursors + tile, 1u);
-                    if (pos < entryCapacity)
-                        entries[pos] = markerKey;
-                }
-            }
-        }
-    }
 }
 
 // ---------------------------------------------------------------------------
@@ -1274,8 +922,7 @@ __global__ void __launch_bounds__(kSetupWarpsPerBlock * 32, 2048 / (kSetupWarpsP
                                                                                 uint32_t totalInstances,
                                                                                 TriGeom* __restrict__ triGeom,
                                                                                 TriAttr* __restrict__ triAttr,
-                                                                                BinTables bins,
-                                                                                FanTables fan)
+                                                                                BinTables bins)
 {
     __shared__ ShadedVertex s_verts[kSetupWarpsPerBlock][kMaxPatchVertices];
     const int lane = threadIdx.x & 31;
@@ -1325,24 +972,9 @@ __global__ void __launch_bounds__(kSetupWarpsPerBlock * 32, 2048 / (kSetupWarpsP
         }
         const PatchDedup* __restrict__ dedup = P.patchDedup + patchType * 2 + (mirrored ? 1 : 0);
         const uint32_t uniqueCount = __ldg(&dedup->uniqueCount);
-        // Fan winding (FanTables): the wedge of a midpoint-fan patch needs to know whether the
-        // wedges of the two neighbouring patches are drawn (then the shared spoke cancels). Two
-        // otherwise idle lanes shade the neighbours' outer fan vertices: the previous patch's fan
-        // vertex 0 and the next patch's fan vertex 8 (patch vertices 32 and 40 of the midpoint-fan
-        // patch, gpu.cpp generate_buffer_data_for_patch_type). Not in band mode, where whole
-        // patches are dropped: there every wedge keeps all of its edges.
-        const bool fanPatch = P.fanPathInfo != nullptr && patchType == 0u;
-        const bool fanNeighbours = fanPatch && !CULL && uniqueCount + 2u <= kMaxPatchVertices;
         __syncwarp();
-        for (uint32_t u = lane; u < uniqueCount + (fanNeighbours ? 2u : 0u); u += 32)
-        {
-            if (u < uniqueCount)
-                verts[u] = shade_patch_vertex(P, P.patchVertices + __ldg(&dedup->unique[u]) * 8, instanceID, enableFeather);
-            else if (u == uniqueCount)
-                verts[u] = shade_patch_vertex(P, P.patchVertices + 32 * 8, instanceID - 1, enableFeather);
-            else
-                verts[u] = shade_patch_vertex(P, P.patchVertices + 40 * 8, instanceID + 1, enableFeather);
-        }
+        for (uint32_t u = lane; u < uniqueCount; u += 32)
+            verts[u] = shade_patch_vertex(P, P.patchVertices + __ldg(&dedup->unique[u]) * 8, instanceID, enableFeather);
         __syncwarp();
         const uint32_t tris = b.trisPerElement;
         for (uint32_t tbase = 0; tbase < tris; tbase += 32)
@@ -1350,7 +982,6 @@ __global__ void __launch_bounds__(kSetupWarpsPerBlock * 32, 2048 / (kSetupWarpsP
             const uint32_t t = tbase + lane;
             int32_t X[3] = {0, 0, 0}, Y[3] = {0, 0, 0};
             bool stored = false;
-            uint32_t edgeMask = 0u;
             const uint32_t rawTri = b.firstTriangle + inst * tris + t;
             if (t < tris)
             {
@@ -1371,71 +1002,32 @@ __global__ void __launch_bounds__(kSetupWarpsPerBlock * 32, 2048 / (kSetupWarpsP
                 float attr[12] = {a.c0, c.c0, d.c0, a.c1, c.c1, d.c1, a.c2, c.c2, d.c2, a.c3, c.c3, d.c3};
                 const int comps = kind == kKindFill ? 1 : (kind == kKindFeatherFill ? 4 : 2);
                 const uint32_t meta = pathID | (kind << kMetaKindShift) | batch_meta_bits(b);
-                uint4 fanInfo = make_uint4(0u, 0u, kFanNoTable, 0u);
-                if (fanPatch && t == tris - 1u && kind == kKindFill)
-                    fanInfo = fan.pathInfo[pathID];
-                if (fanInfo.z != kFanNoTable)
+                // Plain fills of a span-rasterised flush: the three coverages are 0 / +1 / -1 and
+                // travel in the triangle record itself.
+                uint32_t aux = 0u;
+                int storedComps = comps;
+                if (P.spans != 0u && kind == kKindFill)
                 {
-                    // The wedge (fan vertex 0, fan vertex 8, midpoint) of a fill whose fan winding
-                    // comes from edge crossings: no triangle, but a record of its boundary edges.
-                    bool okv = ok;
+                    uint32_t codes = 0u;
+                    bool exactCodes = true;
 #pragma unroll
                     for (int k = 0; k < 3; ++k)
-                        okv = snap_coord(xs[k], X[k]) && snap_coord(ys[k], Y[k]) && okv;
-                    const auto clockwise = [](int32_t ax, int32_t ay, int32_t bx, int32_t by, int32_t cx, int32_t cy) {
-                        return static_cast<int64_t>(bx - ax) * (cy - ay) - static_cast<int64_t>(cx - ax) * (by - ay) > 0;
-                    };
-                    if (okv && clockwise(X[0], Y[0], X[1], Y[1], X[2], Y[2]))
                     {
-                        bool prevDrawn = false, nextDrawn = false;
-                        if (fanNeighbours)
-                        {
-                            const uint32_t copyMask = kMirroredContourFlag | kContourIDMask;
-                            int32_t nx, ny;
-                            if (inst > 0u)
-                            {
-                                const ShadedVertex pv = verts[uniqueCount];
-                                if ((pv.pathID_ok & 0x10000u) != 0u && ((tess_fetch(P, (instanceID - 1) * 8).w ^ firstVertex.w) & copyMask) == 0u && snap_coord(pv.x, nx) && snap_coord(pv.y, ny))
-                                    prevDrawn = clockwise(nx, ny, X[0], Y[0], X[2], Y[2]);
-                            }
-                            if (inst + 1u < b.elementCount)
-                            {
-                                const ShadedVertex nv = verts[uniqueCount + 1u];
-                                if ((nv.pathID_ok & 0x10000u) != 0u && ((tess_fetch(P, (instanceID + 1) * 8).w ^ firstVertex.w) & copyMask) == 0u && snap_coord(nv.x, nx) && snap_coord(nv.y, ny))
-                                    nextDrawn = clockwise(X[1], Y[1], nx, ny, X[2], Y[2]);
-                            }
-                        }
-                        // Edge e runs from vertex (e+1)%3 to (e+2)%3: e2 the rim, e0 the spoke at fan
-                        // vertex 8 (shared with the next wedge), e1 the spoke at fan vertex 0.
-                        edgeMask = 4u | (nextDrawn ? 0u : 1u) | (prevDrawn ? 0u : 2u);
-                        TriGeom g;
-                        g.x0 = X[0];
-                        g.y0 = Y[0];
-                        g.x1 = X[1];
-                        g.y1 = Y[1];
-                        g.x2 = X[2];
-                        g.y2 = Y[2];
-                        g.meta = pathID | (kKindFanEdges << kMetaKindShift) | batch_meta_bits(b) | kMetaValid;
-                        g.aux = edgeMask;
-                        triGeom[rawTri] = g;
-                        *reinterpret_cast<float4*>(triAttr + rawTri) = make_float4(a.c0, a.c0, a.c0, 0.f);
-                        fan_edge_deltas(P, fan, fanInfo, X, Y, edgeMask, a.c0 < 0.f ? -1 : 1);
-                        atomicMin(reinterpret_cast<uint32_t*>(fan.pathInfo + pathID) + 3, rawTri);
-                        stored = true;
-#ifdef RIVECUDA_STATS
-                        atomicAdd(&g_spanStats[11], 1ull);
-                        atomicAdd(&g_spanStats[12], static_cast<unsigned long long>(__popc(edgeMask)));
-#endif
+                        const float c0 = attr[k];
+                        exactCodes = exactCodes && (c0 == 0.f || c0 == 1.f || c0 == -1.f);
+                        codes |= (c0 == 1.f ? 1u : (c0 == -1.f ? 2u : 0u)) << (2 * k);
+                    }
+                    if (exactCodes)
+                    {
+                        aux = kAuxCoverageCodes | codes;
+                        storedComps = 0;
                     }
                 }
-                else
-                {
-                    stored = store_triangle(P, triGeom, triAttr, X, Y, rawTri, xs, ys, attr, comps, meta, 0u, /*cullCCW=*/true);
-                    if (stored && (meta & kMetaModulatedImage) != 0u)
-                        P.pathImageSlots[pathID] = static_cast<uint16_t>(b.imageSlot);
-                }
+                stored = store_triangle(P, triGeom, triAttr, X, Y, rawTri, xs, ys, attr, storedComps, meta, aux, /*cullCCW=*/true);
+                if (stored && (meta & kMetaModulatedImage) != 0u)
+                    P.pathImageSlots[pathID] = static_cast<uint16_t>(b.imageSlot);
             }
-            bin_triangle(P, bins, X, Y, stored, t < tris, rawTri, edgeMask);
+            bin_triangle(P, bins, X, Y, stored, t < tris, rawTri);
         }
     }
 }
@@ -1747,33 +1339,30 @@ __global__ void __launch_bounds__(256) scatter_kernel(FlushParams P,
                 const uint2 pr = pairs[k];
                 const uint32_t pos = __ldg(tileOffsets + pr.x) + pr.y;
                 if (pos < entryCapacity)
-                    entries[pos] = t << P.keyShift;
+                    entries[pos] = t;
             }
         }
         const bool big = n == kBinBig;
         if (__ballot_sync(0xffffffffu, big) == 0u)
             continue;
         int32_t X[3] = {0, 0, 0}, Y[3] = {0, 0, 0};
-        uint32_t edgeMask = 0u;
         if (big)
         {
             const uint4 lo = __ldg(reinterpret_cast<const uint4*>(triGeom + t));
-            const uint4 hi = __ldg(reinterpret_cast<const uint4*>(triGeom + t) + 1);
+            const uint2 hi = __ldg(reinterpret_cast<const uint2*>(triGeom + t) + 2);
             X[0] = static_cast<int32_t>(lo.x);
             Y[0] = static_cast<int32_t>(lo.y);
             X[1] = static_cast<int32_t>(lo.z);
             Y[1] = static_cast<int32_t>(lo.w);
             X[2] = static_cast<int32_t>(hi.x);
             Y[2] = static_cast<int32_t>(hi.y);
-            if (((hi.z >> kMetaKindShift) & 0xf) == kKindFanEdges)
-                edgeMask = hi.w & 7u;
         }
         const uint32_t warpBase = t - (threadIdx.x & 31);
         warp_for_each_tile(P, X, Y, big, [&](uint32_t tile, int ownerLane, bool) {
             const uint32_t pos = __ldg(tileOffsets + tile) + __ldg(bins.smallCounts + tile) + atomicAdd(bigCursors + tile, 1u);
             if (pos < entryCapacity)
-                entries[pos] = (warpBase + static_cast<uint32_t>(ownerLane)) << P.keyShift;
-        }, edgeMask);
+                entries[pos] = warpBase + static_cast<uint32_t>(ownerLane);
+        });
     }
 }
 
@@ -2144,13 +1733,7 @@ int launch_draw_list(rivecuda_ctx* ctx, const rivecuda_flush_desc& desc, const r
             spans = false;
     if (const char* env = getenv("RIVECUDA_SPANS"))
         spans = spans && env[0] != '0';
-    // Fan winding (FanTables): the span rasteriser takes the wedges of midpoint-fan fills as edge
-    // crossings. RIVECUDA_FAN_WINDING=0 keeps them as triangles.
-    bool fanWinding = spans;
-    if (const char* env = getenv("RIVECUDA_FAN_WINDING"))
-        fanWinding = fanWinding && env[0] != '0';
-    FanTables fan = {};
-    P.keyShift = fanWinding ? 1u : 0u;
+    P.spans = spans ? 1u : 0u;
     P.triPos = nullptr;
     TriGeom* triGeom = nullptr;
     TriAttr* triAttr = nullptr;
@@ -2205,40 +1788,13 @@ int launch_draw_list(rivecuda_ctx* ctx, const rivecuda_flush_desc& desc, const r
         // The batch vectors are pageable host memory: the copies above are
         // staged by the runtime before returning, so the vectors may die.
 
-        if (fanWinding && patchInstances > 0)
-        {
-            // Fan winding tables (FanTables): bounds per path, cell allocation, cleared cells.
-            const size_t paths = static_cast<size_t>(desc.path_count) + 2;
-            if (ctx->fanCells.capacity == 0)
-                if (int s = ctx->fanCells.reserve(static_cast<size_t>(8u << 20) * sizeof(int32_t)))
-                    return s;
-            if (int s = ctx->fanPaths.reserve(paths * (sizeof(int4) + sizeof(uint4)) + 16))
-                return s;
-            fan.pathBounds = ctx->fanPaths.as<int4>();
-            fan.pathInfo = reinterpret_cast<uint4*>(fan.pathBounds + paths);
-            fan.backdrop = ctx->fanCells.as<int32_t>();
-            fan.totals = ctx->fanTotals;
-            fan.capacity = static_cast<uint32_t>(std::min<size_t>(ctx->fanCells.capacity / sizeof(int32_t), 0xfffffff0u));
-            fan.pathCount = static_cast<uint32_t>(paths - 1);
-            RC_CUDA(cudaMemsetAsync(fan.pathBounds, 0x7f, paths * sizeof(int4), stream));
-            P.fanPathInfo = fan.pathInfo;
-            P.fanBackdrop = fan.backdrop;
-            const uint32_t blocks = std::min<uint32_t>((patchInstances + 255) / 256, ctx->smCount * 8);
-            fan_bounds_kernel<<<blocks, 256, 0, stream>>>(P, devPatch, static_cast<uint32_t>(patchBatches.size()), patchInstances, fan.pathBounds);
-            fan_alloc_kernel<<<1, 1024, 0, stream>>>(P, fan);
-            fan_zero_kernel<<<ctx->smCount * 4, 256, 0, stream>>>(fan);
-            ctx->lastLaunches += 3;
-            RC_CUDA(cudaGetLastError());
-            // How many cells the flush would have liked: looked at with the list size (resolve_pending_flush).
-            RC_CUDA(cudaMemcpyAsync(ctx->pinnedTotals + 2, fan.totals + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
-        }
         if (patchInstances > 0)
         {
             const uint32_t blocks = std::min<uint32_t>((patchInstances + kSetupWarpsPerBlock - 1) / kSetupWarpsPerBlock, ctx->smCount * 16);
             if (P.cullPatches != 0u)
-                setup_patches_kernel<true><<<blocks, kSetupWarpsPerBlock * 32, 0, stream>>>(P, devPatch, static_cast<uint32_t>(patchBatches.size()), patchInstances, triGeom, triAttr, bins, fan);
+                setup_patches_kernel<true><<<blocks, kSetupWarpsPerBlock * 32, 0, stream>>>(P, devPatch, static_cast<uint32_t>(patchBatches.size()), patchInstances, triGeom, triAttr, bins);
             else
-                setup_patches_kernel<false><<<blocks, kSetupWarpsPerBlock * 32, 0, stream>>>(P, devPatch, static_cast<uint32_t>(patchBatches.size()), patchInstances, triGeom, triAttr, bins, fan);
+                setup_patches_kernel<false><<<blocks, kSetupWarpsPerBlock * 32, 0, stream>>>(P, devPatch, static_cast<uint32_t>(patchBatches.size()), patchInstances, triGeom, triAttr, bins);
             ctx->lastLaunches += 1;
             RC_CUDA(cudaGetLastError());
         }
@@ -2265,12 +1821,6 @@ int launch_draw_list(rivecuda_ctx* ctx, const rivecuda_flush_desc& desc, const r
     if (rawTriangles > 0)
     {
         bin_huge_kernel<false><<<hugeBlocks, 256, 0, stream>>>(P, triGeom, bins, nullptr, nullptr, nullptr, nullptr, 0u);
-        ctx->lastLaunches += 1;
-        RC_CUDA(cudaGetLastError());
-    }
-    if (P.fanPathInfo != nullptr)
-    {
-        fan_backdrop_kernel<false><<<std::min<uint32_t>((fan.pathCount + 8) / 8, ctx->smCount * 8), 256, 0, stream>>>(P, fan, bins, nullptr, nullptr, nullptr, nullptr, 0u);
         ctx->lastLaunches += 1;
         RC_CUDA(cudaGetLastError());
     }
@@ -2314,7 +1864,6 @@ int launch_draw_list(rivecuda_ctx* ctx, const rivecuda_flush_desc& desc, const r
     tail.triAttr = triAttr;
     tail.triPos = P.triPos;
     tail.spans = spans;
-    tail.fan = P.fanPathInfo != nullptr ? std::make_shared<FanTables>(fan) : nullptr;
     tail.bins = std::make_shared<BinTables>(bins);
     tail.tileOffsets = tileOffsets;
     tail.tileCounts = tileCounts;
@@ -2343,12 +1892,6 @@ int launch_tail(rivecuda_ctx* ctx)
         const uint32_t hugeBlocks = static_cast<uint32_t>(ctx->smCount) * 4;
         scatter_kernel<<<blocks, 256, 0, stream>>>(P, triGeom, tail.rawTriangles, bins, tail.tileOffsets, tail.bigCursors, entries, tail.entryTotal, capacity);
         bin_huge_kernel<true><<<hugeBlocks, 256, 0, stream>>>(P, triGeom, bins, tail.tileOffsets, tail.bigCursors, entries, tail.entryTotal, capacity);
-        if (tail.fan)
-        {
-            const FanTables& fan = *static_cast<const FanTables*>(tail.fan.get());
-            fan_backdrop_kernel<true><<<std::min<uint32_t>((fan.pathCount + 8) / 8, ctx->smCount * 8), 256, 0, stream>>>(P, fan, bins, tail.tileOffsets, tail.bigCursors, entries, tail.entryTotal, capacity);
-            ctx->lastLaunches += 1;
-        }
         sort_tiles_kernel<<<tail.tileCount, 256, 0, stream>>>(tail.tileOffsets, tail.tileCounts, entries, tail.entryTotal, capacity);
         ctx->lastLaunches += 3;
         RC_CUDA(cudaGetLastError());
@@ -2360,15 +1903,22 @@ int launch_tail(rivecuda_ctx* ctx)
         unsigned long long zero[32] = {};
         cudaMemcpyToSymbol(g_rasterStats, zero, sizeof(zero));
         cudaMemcpyToSymbol(g_bboxHist, zero, sizeof(unsigned long long) * 24);
-        if (!tail.spans)
-            cudaMemcpyToSymbol(g_spanStats, zero, sizeof(unsigned long long) * 16);
+        cudaMemcpyToSymbol(g_spanStats, zero, sizeof(unsigned long long) * 16);
     }
 #endif
     if (tail.triPos != nullptr)
         raster_tiles_exact_kernel<<<tail.tileCount, 256, 0, stream>>>(P, triGeom, static_cast<const TriAttr*>(tail.triAttr), static_cast<const TriPos*>(tail.triPos), tail.tileOffsets,
                                                                      tail.tileCounts, entries, tail.entryTotal, capacity);
     else if (tail.spans)
-        raster_spans_kernel<<<tail.tileCount, 256, 0, stream>>>(P, triGeom, static_cast<const TriAttr*>(tail.triAttr), tail.tileOffsets, tail.tileCounts, entries, tail.entryTotal, capacity);
+    {
+        static bool configured = false;
+        if (!configured)
+        {
+            RC_CUDA(cudaFuncSetAttribute(raster_spans_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(SpanShared))));
+            configured = true;
+        }
+        raster_spans_kernel<<<tail.tileCount, 256, sizeof(SpanShared), stream>>>(P, triGeom, static_cast<const TriAttr*>(tail.triAttr), tail.tileOffsets, tail.tileCounts, entries, tail.entryTotal, capacity);
+    }
     else
         raster_tiles_kernel<<<tail.tileCount, 256, 0, stream>>>(P, triGeom, static_cast<const TriAttr*>(tail.triAttr), tail.tileOffsets, tail.tileCounts, entries, tail.entryTotal, capacity);
     ctx->lastLaunches += 1;
@@ -2380,10 +1930,8 @@ int launch_tail(rivecuda_ctx* ctx)
         {
             unsigned long long sp[16];
             cudaMemcpyFromSymbol(sp, g_spanStats, sizeof(sp));
-            fprintf(stderr, "[span stats] tri entries %llu live %llu units %llu | fan entries %llu live %llu units %llu | markers %llu | groups %llu | resolve visits %llu warp-resolves %llu lanes %llu | wedges %llu edges %llu | chunks %llu windows %llu\n",
-                    sp[0], sp[1], sp[2], sp[3], sp[4], sp[5], sp[6], sp[7], sp[8], sp[9], sp[10], sp[11], sp[12], sp[13], sp[14]);
-            unsigned long long zero16[16] = {};
-            cudaMemcpyToSymbol(g_spanStats, zero16, sizeof(zero16));
+            fprintf(stderr, "[span stats] entries %llu live %llu units %llu whole-tile %llu | groups %llu | resolve visits %llu warp-blends %llu lanes %llu | chunks %llu windows %llu\n",
+                    sp[0], sp[1], sp[2], sp[3], sp[7], sp[8], sp[9], sp[10], sp[13], sp[14]);
         }
         cudaMemcpyFromSymbol(st, g_rasterStats, sizeof(st));
         const char* names[3] = {"border", "inner-fan", "midpoint-fan"};
@@ -2415,14 +1963,6 @@ int resolve_pending_flush(rivecuda_ctx* ctx)
     tail.valid = false;
     if (ctx->pinnedTotals[1] != 0u)
         return set_error("rivecuda_flush: huge-triangle queue overflow (%u chunks dropped)", ctx->pinnedTotals[1]);
-    // Fan winding: paths whose backdrop cells did not fit kept their wedges as triangles (correct,
-    // slower); size the table for the next flush of this shape.
-    if (tail.fan && static_cast<size_t>(ctx->pinnedTotals[2]) * sizeof(int32_t) > ctx->fanCells.capacity)
-    {
-        RC_CUDA(cudaStreamSynchronize(ctx->stream));
-        if (int s = ctx->fanCells.reserve(std::min<size_t>(static_cast<size_t>(ctx->pinnedTotals[2]) * sizeof(int32_t) * 5 / 4, static_cast<size_t>(2) << 30)))
-            return s;
-    }
     if (entryCount <= tail.capacity)
         return 0;
     if (int s = ctx->tileEntries.reserve((static_cast<size_t>(entryCount) + 1) * sizeof(uint32_t)))

@@ -17,17 +17,14 @@
  *             triangle by triangle.
  *   fill      a LANE per unit. A fill's plane holds DELTAS along each pixel row (the resolve step
  *             prefix-sums them): a triangle's row span [lo, hi] of constant coverage c is +c at
- *             lo and -c at hi + 1 (two shared-memory atomics however long the span), an
- *             anti-aliasing ramp adds its per-pixel differences, and a fan-edge record (the
- *             boundary edges of a midpoint-fan wedge, FanTables in kernels_draw.cu) adds +-1 at
- *             the pixel where the row crosses the edge. The span ends come from the edge
+ *             lo and -c at hi + 1 (two shared-memory atomics however long the span) and an
+ *             anti-aliasing ramp adds its per-pixel differences. The span ends come from the edge
  *             functions by a float estimate corrected with one exact integer evaluation. Values
  *             are 16.16 fixed point: integer adds commute, so the result is deterministic.
  *             Strokes keep the maximum of min(c0, c1) per pixel (atomic max on the float bits).
  *   resolve   thread = pixel, a warp = two pixel rows: for each complete group, in API order, the
- *             warp prefix-sums its rows' deltas (4 shuffle steps), adds the path's backdrop at
- *             this tile (fan winding) and blends the path once (resolve_path, shared with the
- *             in-order kernel) wherever the coverage is not zero.
+ *             warp prefix-sums its rows' deltas (4 shuffle steps) and blends the path once
+ *             (resolve_path, shared with the in-order kernel) wherever the coverage is not zero.
  * Colour / clip state stay in registers for the whole flush and the framebuffer is written once,
  * exactly as in raster_tiles_kernel.
  *
@@ -48,33 +45,62 @@ constexpr float kSpanFixedOne = 65536.f; // coverage 1.0 in a fill's plane word
 
 constexpr uint32_t kSpanStroke = 1u << 24;
 constexpr uint32_t kSpanFlat = 1u << 25;
-constexpr uint32_t kSpanFanEdges = 1u << 26;
 
 struct SpanTri // 16 words (64 B), one per (entry, tile), in shared memory
 {
     int32_t A0, B0, q0, A1; // words 0-3   } three int32 edge functions
     int32_t B1, q1, A2, B2; // words 4-7   }   e = q + A*i + B*j >= 0
     int32_t q2;             // word 8      }
-    float p0[3];            // words 9-11: fills: coverage * 2^16 as P0 + Px*i + Py*j; strokes: c0;
-                            //             fan edges: [0] weight * 2^16 (int), [1] per edge e, bits 10e..10e+9: first row | last row << 4 | rows valid << 8 | straddles column 0 << 9
-    float p1[3];            // words 12-14: strokes: c1
+    float p0[3];            // words 9-11: fills: coverage * 2^16 as P0 + Px*i + Py*j; strokes: c0
+    float p1[3];            // words 12-14: fills: 1 / A of the three edges (0 for A = 0); strokes: c1
     uint32_t info;          // word 15: by0 | by1 << 4 | bx0 << 8 | bx1 << 12 | slot << 16 | kSpan* flags
 };
 static_assert(sizeof(SpanTri) == 64, "SpanTri");
 
-struct SpanSlot // what the resolve step needs of a group's path
+struct SpanSlot // a group: what the resolve step needs of its path, and which warps it touched
 {
     uint32_t meta, paintX, paintY;
-    int32_t backdrop; // fan winding at the tile's pixel (0,0), 16.16
+    uint32_t touch;   // bit w: some entry of the group reaches the pixel rows of warp w
     float solid[4];
+    int32_t backdrop; // coverage (16.16) of the group's triangles that cover the whole tile with a constant
+    uint32_t pad[3];
+};
+static_assert(sizeof(SpanSlot) == 48, "SpanSlot");
+
+// Shared memory of raster_spans_kernel (dynamic: more than 48 KB with 32 slots).
+struct SpanShared
+{
+    int plane[kSpanSlots][256];
+    SpanTri tri[kSpanChunk];
+    uint16_t units[kSpanChunk * kTileSize];
+    uint32_t ids[2][kSpanChunk];
+    SpanSlot slot[kSpanSlots];
+    uint32_t path[kSpanChunk + 4];
+    uint32_t warpSums[2][8];
+    uint64_t bar[2];
 };
 
-// The three tile-local edge functions of a record's triangle (exact below 2^17 px of Manhattan
-// length, as prepare_triangle): false if some edge excludes the whole tile.
-__device__ __forceinline__ bool span_edge_functions(const int32_t X[3], const int32_t Y[3], int32_t px0, int32_t py0, int32_t A[3], int32_t B[3], int64_t E0u[3], int32_t Ai[3], int32_t Bi[3], int32_t qi[3], uint32_t& allOutside)
+#ifdef RIVECUDA_STATS
+// [0] entries, [1] live, [2] (entry, row) units, [3] whole-tile entries, [7] groups, [8] (group, warp) resolve visits
+// that pass the touch test, [9] warp-level blends, [10] lanes blended, [13] chunks, [14] windows
+__device__ unsigned long long g_spanStats[16];
+#define SPAN_STAT(IDX, N) atomicAdd(&g_spanStats[IDX], static_cast<unsigned long long>(N))
+#else
+#define SPAN_STAT(IDX, N)
+#endif
+
+// Tile-local form of one entry: false if it cannot touch the tile. wholeTile: a constant-coverage
+// triangle that contains every pixel centre of the tile (then nothing but p0[0] is written).
+__device__ __forceinline__ bool prepare_span_entry(const TriGeom& g, const TriAttr* __restrict__ attrPtr, int originX, int originY, SpanTri& out, uint32_t& rowRange, bool& wholeTile)
 {
+    const int32_t X[3] = {g.x0, g.x1, g.x2}, Y[3] = {g.y0, g.y1, g.y2};
+    const int32_t px0 = (originX << 8) + 128, py0 = (originY << 8) + 128; // pixel centre of tile pixel (0,0)
+    // Vertices are clamped to +-2^29 sub-pixel units (snap_coord), so every coordinate
+    // difference fits int32 and each 64-bit product below is ONE widening multiply.
+    int32_t A[3], B[3];
+    int64_t E0u[3];
+    int32_t Ai[3], Bi[3], qi[3];
     bool reject = false;
-    allOutside = 0u;
 #pragma unroll
     for (int e = 0; e < 3; ++e)
     {
@@ -85,18 +111,14 @@ __device__ __forceinline__ bool span_edge_functions(const int32_t X[3], const in
         B[e] = dx;
         const int64_t C = static_cast<int64_t>(dy) * X[a] - static_cast<int64_t>(dx) * Y[a];
         E0u[e] = static_cast<int64_t>(-dy) * px0 + static_cast<int64_t>(dx) * py0 + C;
+        // E(i,j) - bias = E0u - bias + 256*(A*i + B*j) >= 0  <=>  q + A*i + B*j >= 0
         const int64_t q = (E0u[e] - (topLeft ? 0 : 1)) >> 8;
         const int32_t negSum = min(-dy, 0) + min(dx, 0), posSum = max(-dy, 0) + max(dx, 0);
         const int64_t emin = q + static_cast<int64_t>(negSum) * (kTileSize - 1);
         const int64_t emax = q + static_cast<int64_t>(posSum) * (kTileSize - 1);
         if (emax < 0)
-        {
             reject = true;
-            allOutside |= 1u << e;
-            Ai[e] = Bi[e] = 0; // false for every pixel of the tile
-            qi[e] = -1;
-        }
-        else if (emin >= 0)
+        if (emin >= 0)
         {
             Ai[e] = Bi[e] = qi[e] = 0; // true for every pixel of the tile
         }
@@ -121,69 +143,7 @@ __device__ __forceinline__ bool span_edge_functions(const int32_t X[3], const in
             qi[e] = static_cast<int32_t>(q64);
         }
     }
-    return !reject;
-}
-
-// Tile-local form of one entry: false if it cannot touch the tile.
-__device__ __forceinline__ bool prepare_span_entry(const TriGeom& g, const TriAttr* __restrict__ attrPtr, int originX, int originY, SpanTri& out, uint32_t& rowRange)
-{
-    const int32_t X[3] = {g.x0, g.x1, g.x2}, Y[3] = {g.y0, g.y1, g.y2};
-    const int32_t px0 = (originX << 8) + 128, py0 = (originY << 8) + 128; // pixel centre of tile pixel (0,0)
-    int32_t A[3], B[3];
-    int64_t E0u[3];
-    int32_t Ai[3], Bi[3], qi[3];
-    uint32_t allOutside;
-    const bool overlaps = span_edge_functions(X, Y, px0, py0, A, B, E0u, Ai, Bi, qi, allOutside);
-    const uint32_t kind = (g.meta >> kMetaKindShift) & 0xf;
-    out.A0 = Ai[0];
-    out.B0 = Bi[0];
-    out.q0 = qi[0];
-    out.A1 = Ai[1];
-    out.B1 = Bi[1];
-    out.q1 = qi[1];
-    out.A2 = Ai[2];
-    out.B2 = Bi[2];
-    out.q2 = qi[2];
-    const float4 a0 = __ldg(reinterpret_cast<const float4*>(attrPtr));
-    if (kind == kKindFanEdges)
-    {
-        // The active boundary edges of a wedge: per edge the pixel rows it straddles
-        // (min y <= centre y < max y) and whether it straddles the tile's pixel column 0.
-        uint32_t packed = 0u;
-        int first = kTileSize, last = -1;
-#pragma unroll
-        for (int e = 0; e < 3; ++e)
-        {
-            if ((g.aux & (1u << e)) == 0u)
-                continue;
-            const int a = (e + 1) % 3, b = (e + 2) % 3;
-            const int32_t ylo = min(Y[a], Y[b]), yhi = max(Y[a], Y[b]);
-            const int j0 = max((ylo - py0 + 255) >> 8, 0), j1 = min(((yhi - py0 + 255) >> 8) - 1, kTileSize - 1);
-            uint32_t bits = 0u;
-            if (j0 <= j1 && Ai[e] != 0)
-            {
-                bits = static_cast<uint32_t>(j0) | (static_cast<uint32_t>(j1) << 4) | 0x100u;
-                first = min(first, j0);
-                last = max(last, j1);
-            }
-            if (min(X[a], X[b]) <= px0 && px0 < max(X[a], X[b]) && ((qi[e] >= 0) != (qi[e] + Bi[e] * (kTileSize - 1) >= 0)))
-            {
-                // Somewhere down column 0 the pixel changes sides: every row from there on.
-                bits |= 0x200u;
-                first = min(first, 1);
-                last = kTileSize - 1;
-            }
-            packed |= bits << (10 * e);
-        }
-        if (first > last)
-            return false;
-        out.p0[0] = __int_as_float(a0.x < 0.f ? -65536 : 65536);
-        out.p0[1] = __uint_as_float(packed);
-        rowRange = static_cast<uint32_t>(first) | (static_cast<uint32_t>(last) << 4);
-        out.info = rowRange | kSpanFanEdges;
-        return true;
-    }
-    if (!overlaps)
+    if (reject)
         return false;
     const int32_t minX = min(X[0], min(X[1], X[2])), maxX = max(X[0], max(X[1], X[2]));
     const int32_t minY = min(Y[0], min(Y[1], Y[2])), maxY = max(Y[0], max(Y[1], Y[2]));
@@ -191,11 +151,27 @@ __device__ __forceinline__ bool prepare_span_entry(const TriGeom& g, const TriAt
     const int by0 = max(((minY - 128 + 255) >> 8) - originY, 0), by1 = min(((maxY - 128) >> 8) - originY, kTileSize - 1);
     if (bx0 > bx1 || by0 > by1)
         return false;
+    const uint32_t kind = (g.meta >> kMetaKindShift) & 0xf;
+    float4 a0;
+    if ((g.aux & kAuxCoverageCodes) != 0u)
+    {
+        const auto decode = [](uint32_t code) { return code == 0u ? 0.f : (code == 1u ? 1.f : -1.f); };
+        a0 = make_float4(decode(g.aux & 3u), decode((g.aux >> 2) & 3u), decode((g.aux >> 4) & 3u), 0.f);
+    }
+    else
+    {
+        a0 = __ldg(reinterpret_cast<const float4*>(attrPtr));
+    }
     uint32_t flags = 0u;
     if (kind == kKindFill && a0.x == a0.y && a0.y == a0.z)
     {
         // Constant coverage (fan / interior triangles): exact.
         out.p0[0] = a0.x * kSpanFixedOne;
+        if ((Ai[0] | Bi[0] | qi[0] | Ai[1] | Bi[1] | qi[1] | Ai[2] | Bi[2] | qi[2]) == 0)
+        {
+            wholeTile = true;
+            return true;
+        }
         out.p0[1] = 0.f;
         out.p0[2] = 0.f;
         flags = kSpanFlat;
@@ -223,29 +199,41 @@ __device__ __forceinline__ bool prepare_span_entry(const TriGeom& g, const TriAt
             flags = kSpanStroke;
         }
     }
+    out.A0 = Ai[0];
+    out.B0 = Bi[0];
+    out.q0 = qi[0];
+    out.A1 = Ai[1];
+    out.B1 = Bi[1];
+    out.q1 = qi[1];
+    out.A2 = Ai[2];
+    out.B2 = Bi[2];
+    out.q2 = qi[2];
+    if (kind == kKindFill)
+    {
+#pragma unroll
+        for (int e = 0; e < 3; ++e)
+            out.p1[e] = Ai[e] != 0 ? 1.f / static_cast<float>(Ai[e]) : 0.f;
+    }
     rowRange = static_cast<uint32_t>(by0) | (static_cast<uint32_t>(by1) << 4);
     out.info = rowRange | (static_cast<uint32_t>(bx0) << 8) | (static_cast<uint32_t>(bx1) << 12) | flags;
     return true;
 }
 
-// One edge's constraint on a pixel row: A*i + v >= 0 narrows [lo, hi]. The crossing is estimated
-// in float (|error| << 1e-3 px inside the tile) on the safe side and corrected with one exact
-// integer evaluation, so the span is exactly the set of pixels whose edge value is >= 0.
-__device__ __forceinline__ void span_edge(int A, int v, int& lo, int& hi)
+// One edge's constraint on a pixel row: A*i + v >= 0 narrows [lo, hi]. The crossing -v / A is
+// estimated in float (|error| << 1e-3 px inside the tile) on the safe side and corrected with one
+// exact integer evaluation, so the span is exactly the set of pixels whose edge value is >= 0.
+// invA: 1 / A, or anything for A = 0.
+__device__ __forceinline__ void span_edge(int A, int v, float invA, int& lo, int& hi)
 {
-    if (A == 0)
-    {
-        if (v < 0)
-            hi = -1;
-        return;
-    }
     const bool pos = A > 0;
-    float t = __fdividef(-static_cast<float>(v), static_cast<float>(A));
-    t = pos ? t - 1e-3f : t + 1e-3f;
+    float t = -static_cast<float>(v) * invA;
+    t += pos ? -1e-3f : 1e-3f;
     t = fminf(fmaxf(t, -2.f), 17.f);
     int cand = pos ? __float2int_ru(t) : __float2int_rd(t);
     if (v + A * cand < 0)
         cand += pos ? 1 : -1;
+    if (A == 0)
+        cand = v < 0 ? -1 : 100; // a row is inside or outside as a whole
     if (pos)
         lo = max(lo, cand);
     else
@@ -260,15 +248,10 @@ __device__ __forceinline__ void red_max_shared(uint32_t addr, int v)
 {
     asm volatile("red.shared.max.s32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
 }
-
-#ifdef RIVECUDA_STATS
-// [0] triangle entries, [1] live, [2] their row units; [3] fan-edge entries, [4] live, [5] their row units; [6] markers;
-// [7] groups; [8] (group, warp) resolve visits that pass the empty test, [9] warp-level resolve_path calls, [10] lanes blended;
-// [11] wedges drawn (setup), [12] their active edges (setup); [13] chunks, [14] windows
-#define SPAN_STAT(IDX, N) atomicAdd(&g_spanStats[IDX], static_cast<unsigned long long>(N))
-#else
-#define SPAN_STAT(IDX, N)
-#endif
+__device__ __forceinline__ void red_or_shared(uint32_t addr, uint32_t v)
+{
+    asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
 
 #ifndef RIVECUDA_SPAN_MIN_BLOCKS
 #define RIVECUDA_SPAN_MIN_BLOCKS 4
@@ -282,14 +265,8 @@ __global__ void __launch_bounds__(256, RIVECUDA_SPAN_MIN_BLOCKS) raster_spans_ke
                                                                                   const uint32_t* __restrict__ entryTotal,
                                                                                   uint32_t entryCapacity)
 {
-    __shared__ __align__(16) int s_plane[kSpanSlots][256];
-    __shared__ __align__(16) SpanTri s_tri[kSpanChunk];
-    __shared__ __align__(16) uint16_t s_units[kSpanChunk * kTileSize];
-    __shared__ __align__(16) uint32_t s_ids[2][kSpanChunk];
-    __shared__ __align__(16) SpanSlot s_slot[kSpanSlots];
-    __shared__ uint32_t s_path[kSpanChunk + 1];
-    __shared__ uint32_t s_warpSums[2][8];
-    __shared__ __align__(8) uint64_t s_bar[2];
+    extern __shared__ __align__(16) uint8_t s_raw[];
+    SpanShared& S = *reinterpret_cast<SpanShared*>(s_raw);
     if (__ldg(entryTotal) > entryCapacity)
         return;
     const uint32_t tile = blockIdx.x;
@@ -301,24 +278,30 @@ __global__ void __launch_bounds__(256, RIVECUDA_SPAN_MIN_BLOCKS) raster_spans_ke
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     // A warp owns two pixel rows: the row prefix sums of the resolve step stay inside a half warp
     // and a plane's words are read lane by lane (no bank conflicts).
-    const int i = lane & 15, j = warp * 2 + (lane >> 4);
+    int i = lane & 15, j = warp * 2 + (lane >> 4);
+    uint32_t warpBit = 1u << warp, tid4 = threadIdx.x * 4u;
+    // Opaque to the compiler: kept in registers instead of being re-derived from the thread id
+    // at every use inside the loops.
+    asm volatile("" : "+r"(i), "+r"(j), "+r"(warpBit), "+r"(tid4));
     const int px = originX + i, py = originY + j;
     const bool inBounds = px >= P.boundsL && px < P.boundsR && py >= P.boundsT && py < P.boundsB;
 
-    PixelState s;
-    s.clipCoverage = 0.f;
-    s.clipID = 0u;
-    s.dither = 0.f;
+    // The pixel: RGBA8 premultiplied as in the reference's colour plane, each channel held as the
+    // float 0..255 it was last quantised to (no unpack / repack between the paths of a tile).
+    float dither = 0.f;
     if (P.ditherScale != 0.f)
     {
         const float v1 = fractf(0.06711056f * (px + .5f) + 0.00583715f * (py + .5f));
-        s.dither = fractf(52.9829189f * v1) * P.ditherScale + P.ditherBias;
+        dither = fractf(52.9829189f * v1) * P.ditherScale + P.ditherBias;
     }
+    float clipCoverage = 0.f;
+    uint32_t clipID = 0u;
     const bool groupInBounds = ((__ballot_sync(0xffffffffu, inBounds) >> (lane & ~3)) & 0xfu) == 0xfu;
     const bool vectorised = (P.targetWidth & 3u) == 0u && groupInBounds;
+    uint32_t packed;
     if (P.loadAction == RIVECUDA_LOAD_CLEAR)
     {
-        s.color = P.clearColorPremulRGBA;
+        packed = P.clearColorPremulRGBA;
     }
     else
     {
@@ -329,20 +312,24 @@ __global__ void __launch_bounds__(256, RIVECUDA_SPAN_MIN_BLOCKS) raster_spans_ke
         const uint32_t q0 = __shfl_sync(0xffffffffu, quad.x, leader), q1 = __shfl_sync(0xffffffffu, quad.y, leader);
         const uint32_t q2 = __shfl_sync(0xffffffffu, quad.z, leader), q3 = __shfl_sync(0xffffffffu, quad.w, leader);
         const int k = lane & 3;
-        s.color = vectorised ? (k == 0 ? q0 : (k == 1 ? q1 : (k == 2 ? q2 : q3))) : (inBounds ? P.target[static_cast<size_t>(py) * P.targetWidth + px] : 0u);
+        packed = vectorised ? (k == 0 ? q0 : (k == 1 ? q1 : (k == 2 ? q2 : q3))) : (inBounds ? P.target[static_cast<size_t>(py) * P.targetWidth + px] : 0u);
     }
+    float colR = static_cast<float>(packed & 0xffu), colG = static_cast<float>((packed >> 8) & 0xffu), colB = static_cast<float>((packed >> 16) & 0xffu), colA = static_cast<float>(packed >> 24);
 
     const uint32_t* list = entries + tileOffsets[tile];
-    const uint32_t idsAddr = static_cast<uint32_t>(__cvta_generic_to_shared(&s_ids[0][0]));
-    const uint32_t barAddr = static_cast<uint32_t>(__cvta_generic_to_shared(&s_bar[0]));
-    const uint32_t triAddr = static_cast<uint32_t>(__cvta_generic_to_shared(&s_tri[0]));
-    const uint32_t planesAddr = static_cast<uint32_t>(__cvta_generic_to_shared(&s_plane[0][0]));
-    const uint32_t slotsAddr = static_cast<uint32_t>(__cvta_generic_to_shared(&s_slot[0]));
-    for (int k = threadIdx.x; k < kSpanSlots * 256; k += 256)
-        (&s_plane[0][0])[k] = 0;
-    // (Group 0 is the empty group before the first entry: nothing in its plane, no backdrop.)
+    // One shared-memory base; the members are constant offsets from it.
+    uint32_t smemBase = static_cast<uint32_t>(__cvta_generic_to_shared(s_raw));
+    asm volatile("" : "+r"(smemBase));
+    const uint32_t idsAddr = smemBase + static_cast<uint32_t>(offsetof(SpanShared, ids));
+    const uint32_t barAddr = smemBase + static_cast<uint32_t>(offsetof(SpanShared, bar));
+    const uint32_t triAddr = smemBase + static_cast<uint32_t>(offsetof(SpanShared, tri));
+    const uint32_t planesAddr = smemBase + static_cast<uint32_t>(offsetof(SpanShared, plane));
+    const uint32_t slotsAddr = smemBase + static_cast<uint32_t>(offsetof(SpanShared, slot));
+    for (int k = threadIdx.x; k < kSpanSlots * 64; k += 256)
+        reinterpret_cast<uint4*>(&S.plane[0][0])[k] = make_uint4(0u, 0u, 0u, 0u);
+    // (Group 0 is the empty group before the first entry: nothing touched.)
     if (threadIdx.x < kSpanSlots * sizeof(SpanSlot) / 4)
-        reinterpret_cast<uint32_t*>(&s_slot[0])[threadIdx.x] = 0u;
+        reinterpret_cast<uint32_t*>(&S.slot[0])[threadIdx.x] = 0u;
     if (threadIdx.x == 0)
     {
         mbar_init(barAddr, 1u);
@@ -367,68 +354,60 @@ __global__ void __launch_bounds__(256, RIVECUDA_SPAN_MIN_BLOCKS) raster_spans_ke
         TriGeom g;
         g.meta = 0u;
         uint32_t t = 0u;
-        bool marker = false;
         uint32_t pathID = carryPath;
         if (have)
         {
-            const uint32_t key = s_ids[buf][threadIdx.x];
-            t = key >> P.keyShift;
-            marker = (key & P.keyShift) != 0u; // keyShift is 0 or 1: bit 0 of a shifted key marks a backdrop marker
+            t = S.ids[buf][threadIdx.x];
             const uint4* src = reinterpret_cast<const uint4*>(triGeom + t);
             *reinterpret_cast<uint4*>(&g) = __ldg(src);
             *(reinterpret_cast<uint4*>(&g) + 1) = __ldg(src + 1);
             pathID = g.meta & 0xffffu;
         }
-        s_path[threadIdx.x + 1] = pathID;
+        S.path[threadIdx.x + 1] = pathID;
         if (threadIdx.x == 0)
-            s_path[0] = carryPath;
+            S.path[0] = carryPath;
         __syncthreads();
         if (threadIdx.x == 0 && !lastChunk)
             tma_load_1d(idsAddr + (buf ^ 1u) * static_cast<uint32_t>(kSpanChunk * 4), list + base + kSpanChunk,
                         (min(static_cast<uint32_t>(kSpanChunk), n - base - kSpanChunk) * 4u + 15u) & ~15u, barAddr + (buf ^ 1u) * 8u);
         // Groups: a flag wherever the path changes; the entry's group = open group + flags up to it.
-        const bool flag = have && s_path[threadIdx.x] != pathID;
+        const bool flag = have && S.path[threadIdx.x] != pathID;
         const uint32_t flagBits = __ballot_sync(0xffffffffu, flag);
         if (lane == 0)
-            s_warpSums[scanBuf][warp] = __popc(flagBits);
+            S.warpSums[scanBuf][warp] = __popc(flagBits);
         // Prepare while the warp sums settle.
         uint32_t rowRange = 0u;
-        bool live = false;
-        if (have && !marker && (g.meta & kMetaValid) != 0u)
-            live = prepare_span_entry(g, triAttr + t, originX, originY, s_tri[threadIdx.x], rowRange);
+        bool live = false, wholeTile = false;
+        if (have && (g.meta & kMetaValid) != 0u)
+            live = prepare_span_entry(g, triAttr + t, originX, originY, S.tri[threadIdx.x], rowRange, wholeTile);
         __syncthreads();
         uint32_t groupsBefore = 0u, groupsInChunk = 0u;
 #pragma unroll
         for (int w = 0; w < 8; ++w)
         {
-            const uint32_t c = s_warpSums[scanBuf][w];
+            const uint32_t c = S.warpSums[scanBuf][w];
             groupsBefore += w < warp ? c : 0u;
             groupsInChunk += c;
         }
         scanBuf ^= 1u;
         const uint32_t group = openGroup + groupsBefore + __popc(flagBits & ((2u << lane) - 1u));
         const uint32_t lastGroup = openGroup + groupsInChunk;
-        const uint32_t rows = live ? ((rowRange >> 4) - (rowRange & 15u) + 1u) : 0u;
+        const uint32_t rows = (live && !wholeTile) ? ((rowRange >> 4) - (rowRange & 15u) + 1u) : 0u;
+        const uint32_t mySlotAddr = slotsAddr + (group & (kSpanSlots - 1)) * static_cast<uint32_t>(sizeof(SpanSlot));
+        if (rows != 0u)
+            S.tri[threadIdx.x].info |= (group & (kSpanSlots - 1)) << 16;
 #ifdef RIVECUDA_STATS
         if (have)
         {
-            const bool isFan = ((g.meta >> kMetaKindShift) & 0xf) == kKindFanEdges;
-            if (marker)
-                SPAN_STAT(6, 1);
-            else
-            {
-                SPAN_STAT(isFan ? 3 : 0, 1);
-                SPAN_STAT(isFan ? 4 : 1, live ? 1 : 0);
-                SPAN_STAT(isFan ? 5 : 2, rows);
-            }
-            if (flag)
-                SPAN_STAT(7, 1);
+            SPAN_STAT(0, 1);
+            SPAN_STAT(1, live ? 1 : 0);
+            SPAN_STAT(2, rows);
+            SPAN_STAT(3, wholeTile ? 1 : 0);
+            SPAN_STAT(7, flag ? 1 : 0);
         }
         if (threadIdx.x == 0)
             SPAN_STAT(13, 1);
 #endif
-        if (live)
-            s_tri[threadIdx.x].info |= (group & (kSpanSlots - 1)) << 16;
 
         // Windows of kSpanSlots groups: fill, then resolve the complete ones in order.
         for (uint32_t windowStart = openGroup; windowStart <= lastGroup; windowStart += kSpanSlots)
@@ -452,23 +431,16 @@ __global__ void __launch_bounds__(256, RIVECUDA_SPAN_MIN_BLOCKS) raster_spans_ke
                     pc.y *= pc.w;
                     pc.z *= pc.w;
                 }
-                int backdrop = 0;
-                if (P.fanPathInfo != nullptr)
-                {
-                    const uint4 info = __ldg(P.fanPathInfo + pathID);
-                    const uint32_t cx = static_cast<uint32_t>(tileX - P.tileX0) - (info.x & 0xffffu), cy = static_cast<uint32_t>(tileY - P.tileY0) - (info.x >> 16);
-                    if (info.z != kFanNoTable && cx < (info.y & 0xffffu) && cy < (info.y >> 16))
-                        backdrop = __ldg(P.fanBackdrop + info.z + cy * (info.y & 0xffffu) + cx) << 16;
-                }
-                SpanSlot& slot = s_slot[group & (kSpanSlots - 1)];
+                SpanSlot& slot = S.slot[group & (kSpanSlots - 1)];
                 slot.meta = meta;
                 slot.paintX = paint.x;
                 slot.paintY = paint.y;
-                slot.backdrop = backdrop;
+                slot.touch = 0u;
                 slot.solid[0] = pc.x;
                 slot.solid[1] = pc.y;
                 slot.solid[2] = pc.z;
                 slot.solid[3] = pc.w;
+                slot.backdrop = 0;
             }
             // Expand (entry, row) units: exclusive scan of the row counts over the CTA.
             const uint32_t myRows = inWindow ? rows : 0u;
@@ -481,29 +453,40 @@ __global__ void __launch_bounds__(256, RIVECUDA_SPAN_MIN_BLOCKS) raster_spans_ke
                     incl += up;
             }
             if (lane == 31)
-                s_warpSums[scanBuf][warp] = incl;
+                S.warpSums[scanBuf][warp] = incl;
             __syncthreads();
             uint32_t unitBase = 0u, unitCount = 0u;
 #pragma unroll
             for (int w = 0; w < 8; ++w)
             {
-                const uint32_t c = s_warpSums[scanBuf][w];
+                const uint32_t c = S.warpSums[scanBuf][w];
                 unitBase += w < warp ? c : 0u;
                 unitCount += c;
             }
             scanBuf ^= 1u;
+            if (inWindow && live)
             {
-                uint32_t dst = unitBase + incl - myRows;
-                const uint32_t first = rowRange & 15u;
-                for (uint32_t r = 0; r < myRows; ++r)
-                    s_units[dst + r] = static_cast<uint16_t>((threadIdx.x << 4) | (first + r));
+                if (wholeTile)
+                {
+                    // The triangle contains the whole tile: a constant for every pixel.
+                    red_add_shared(mySlotAddr + 32u, __float2int_rn(S.tri[threadIdx.x].p0[0]));
+                    red_or_shared(mySlotAddr + 12u, 0xffu);
+                }
+                else
+                {
+                    const uint32_t first = rowRange & 15u, last = rowRange >> 4;
+                    red_or_shared(mySlotAddr + 12u, (2u << (last >> 1)) - (1u << (first >> 1)));
+                    uint32_t dst = unitBase + incl - myRows;
+                    for (uint32_t r = 0; r < myRows; ++r)
+                        S.units[dst + r] = static_cast<uint16_t>((threadIdx.x << 4) | (first + r));
+                }
             }
             __syncthreads();
 
             // Fill: a lane per (entry, row).
             for (uint32_t u = threadIdx.x; u < unitCount; u += 256)
             {
-                const uint32_t unit = s_units[u];
+                const uint32_t unit = S.units[u];
                 const uint32_t T = triAddr + (unit >> 4) * static_cast<uint32_t>(sizeof(SpanTri));
                 const int row = static_cast<int>(unit & 15u);
                 const uint4 w0 = lds_u32x4(T), w1 = lds_u32x4(T + 16), w2 = lds_u32x4(T + 32), w3 = lds_u32x4(T + 48);
@@ -512,65 +495,42 @@ __global__ void __launch_bounds__(256, RIVECUDA_SPAN_MIN_BLOCKS) raster_spans_ke
                 const int v0 = static_cast<int>(w0.z) + static_cast<int>(w0.y) * row;
                 const int v1 = static_cast<int>(w1.y) + static_cast<int>(w1.x) * row;
                 const int v2 = static_cast<int>(w2.x) + static_cast<int>(w1.w) * row;
-                if ((info & kSpanFanEdges) != 0u)
-                {
-                    // Boundary edges of a wedge: +-weight from the pixel where this row crosses the
-                    // edge, and at pixel 0 if the tile's column 0 crossed the edge above this row.
-                    const int weight = static_cast<int>(w2.y);
-                    const uint32_t packed = w2.z;
-                    const int A[3] = {static_cast<int>(w0.x), static_cast<int>(w0.w), static_cast<int>(w1.z)};
-                    const int v[3] = {v0, v1, v2};
-                    const int q[3] = {static_cast<int>(w0.z), static_cast<int>(w1.y), static_cast<int>(w2.x)};
-#pragma unroll
-                    for (int e = 0; e < 3; ++e)
-                    {
-                        const uint32_t bits = (packed >> (10 * e)) & 0x3ffu;
-                        if ((bits & 0x100u) != 0u && row >= static_cast<int>(bits & 15u) && row <= static_cast<int>((bits >> 4) & 15u))
-                        {
-                            int lo = -100, hi = 100;
-                            span_edge(A[e], v[e], lo, hi);
-                            const int ic = A[e] > 0 ? lo : hi + 1;
-                            if (ic >= 1 && ic <= kTileSize - 1)
-                                red_add_shared(rowAddr + static_cast<uint32_t>(ic) * 4u, A[e] > 0 ? weight : -weight);
-                        }
-                        if ((bits & 0x200u) != 0u)
-                        {
-                            const int d = (v[e] >= 0 ? 1 : 0) - (q[e] >= 0 ? 1 : 0);
-                            if (d != 0)
-                                red_add_shared(rowAddr, d > 0 ? weight : -weight);
-                        }
-                    }
-                    continue;
-                }
                 int lo = static_cast<int>((info >> 8) & 15u), hi = static_cast<int>((info >> 12) & 15u);
-                span_edge(static_cast<int>(w0.x), v0, lo, hi);
-                span_edge(static_cast<int>(w0.w), v1, lo, hi);
-                span_edge(static_cast<int>(w1.z), v2, lo, hi);
-                if (lo > hi)
-                    continue;
                 const float frow = static_cast<float>(row);
-                if ((info & kSpanFlat) != 0u)
+                if ((info & kSpanStroke) == 0u)
                 {
-                    const int add = __float2int_rn(__uint_as_float(w2.y));
-                    red_add_shared(rowAddr + static_cast<uint32_t>(lo) * 4u, add);
-                    if (hi < kTileSize - 1)
-                        red_add_shared(rowAddr + static_cast<uint32_t>(hi + 1) * 4u, -add);
-                }
-                else if ((info & kSpanStroke) == 0u)
-                {
-                    const float c0 = __fmaf_rn(__uint_as_float(w2.w), frow, __uint_as_float(w2.y)), cx = __uint_as_float(w2.z);
-                    int prev = 0;
-                    for (int x = lo; x <= hi; ++x)
+                    span_edge(static_cast<int>(w0.x), v0, __uint_as_float(w3.x), lo, hi);
+                    span_edge(static_cast<int>(w0.w), v1, __uint_as_float(w3.y), lo, hi);
+                    span_edge(static_cast<int>(w1.z), v2, __uint_as_float(w3.z), lo, hi);
+                    if (lo > hi)
+                        continue;
+                    if ((info & kSpanFlat) != 0u)
                     {
-                        const int cur = __float2int_rn(__fmaf_rn(cx, static_cast<float>(x), c0));
-                        red_add_shared(rowAddr + static_cast<uint32_t>(x) * 4u, cur - prev);
-                        prev = cur;
+                        const int add = __float2int_rn(__uint_as_float(w2.y));
+                        red_add_shared(rowAddr + static_cast<uint32_t>(lo) * 4u, add);
+                        if (hi < kTileSize - 1)
+                            red_add_shared(rowAddr + static_cast<uint32_t>(hi + 1) * 4u, -add);
                     }
-                    if (hi < kTileSize - 1)
-                        red_add_shared(rowAddr + static_cast<uint32_t>(hi + 1) * 4u, -prev);
+                    else
+                    {
+                        const float c0 = __fmaf_rn(__uint_as_float(w2.w), frow, __uint_as_float(w2.y)), cx = __uint_as_float(w2.z);
+                        int prev = 0;
+                        for (int x = lo; x <= hi; ++x)
+                        {
+                            const int cur = __float2int_rn(__fmaf_rn(cx, static_cast<float>(x), c0));
+                            red_add_shared(rowAddr + static_cast<uint32_t>(x) * 4u, cur - prev);
+                            prev = cur;
+                        }
+                        if (hi < kTileSize - 1)
+                            red_add_shared(rowAddr + static_cast<uint32_t>(hi + 1) * 4u, -prev);
+                    }
                 }
                 else
                 {
+                    const int A0 = static_cast<int>(w0.x), A1 = static_cast<int>(w0.w), A2 = static_cast<int>(w1.z);
+                    span_edge(A0, v0, 1.f / static_cast<float>(A0), lo, hi);
+                    span_edge(A1, v1, 1.f / static_cast<float>(A1), lo, hi);
+                    span_edge(A2, v2, 1.f / static_cast<float>(A2), lo, hi);
                     const float c0 = __fmaf_rn(__uint_as_float(w2.w), frow, __uint_as_float(w2.y)), c0x = __uint_as_float(w2.z);
                     const float c1 = __fmaf_rn(__uint_as_float(w3.z), frow, __uint_as_float(w3.x)), c1x = __uint_as_float(w3.y);
                     for (int x = lo; x <= hi; ++x)
@@ -590,13 +550,12 @@ __global__ void __launch_bounds__(256, RIVECUDA_SPAN_MIN_BLOCKS) raster_spans_ke
             for (uint32_t gi = windowStart; gi < resolveEnd; ++gi)
             {
                 const uint32_t slotIdx = gi & (kSpanSlots - 1);
-                const uint32_t wordAddr = planesAddr + slotIdx * 1024u + threadIdx.x * 4u;
                 const uint32_t slotAddr = slotsAddr + slotIdx * static_cast<uint32_t>(sizeof(SpanSlot));
-                const int v = static_cast<int>(lds_u32(wordAddr));
                 const uint4 rec = lds_u32x4(slotAddr);
-                const bool any = __any_sync(0xffffffffu, v != 0);
-                if (!any && rec.w == 0u)
-                    continue;
+                if ((rec.w & warpBit) == 0u)
+                    continue; // nothing of this path reaches the warp's two pixel rows
+                const uint32_t wordAddr = planesAddr + slotIdx * 1024u + tid4;
+                const int v = static_cast<int>(lds_u32(wordAddr));
                 if (v != 0)
                     asm volatile("st.shared.u32 [%0], %1;" ::"r"(wordAddr), "r"(0) : "memory");
                 float coverageCount;
@@ -606,9 +565,16 @@ __global__ void __launch_bounds__(256, RIVECUDA_SPAN_MIN_BLOCKS) raster_spans_ke
                 }
                 else
                 {
-                    int acc = v;
-                    if (any)
+                    int acc;
+                    if ((__ballot_sync(0xffffffffu, v != 0) & 0xfffefffeu) == 0u)
                     {
+                        // Deltas at most at pixel 0 of the two rows (rows a triangle covers from
+                        // the tile's left edge on): the row's value is that delta.
+                        acc = __shfl_sync(0xffffffffu, v, 0, 16);
+                    }
+                    else
+                    {
+                        acc = v;
 #pragma unroll
                         for (int o = 1; o < 16; o <<= 1)
                         {
@@ -617,16 +583,15 @@ __global__ void __launch_bounds__(256, RIVECUDA_SPAN_MIN_BLOCKS) raster_spans_ke
                                 acc += up;
                         }
                     }
-                    acc += static_cast<int>(rec.w);
+                    acc += static_cast<int>(lds_u32(slotAddr + 32u));
                     coverageCount = static_cast<float>(acc) * (1.f / kSpanFixedOne);
                 }
 #ifdef RIVECUDA_STATS
-                if (lane == 0)
-                    SPAN_STAT(8, 1);
                 {
-                    const uint32_t nz = __ballot_sync(__activemask(), coverageCount != 0.f);
+                    const uint32_t nz = __ballot_sync(0xffffffffu, coverageCount != 0.f);
                     if (lane == 0)
                     {
+                        SPAN_STAT(8, 1);
                         SPAN_STAT(9, nz != 0u ? 1 : 0);
                         SPAN_STAT(10, __popc(nz));
                     }
@@ -635,24 +600,67 @@ __global__ void __launch_bounds__(256, RIVECUDA_SPAN_MIN_BLOCKS) raster_spans_ke
                 if (coverageCount == 0.f)
                     continue;
                 const float4 solid = lds_f32x4(slotAddr + 16);
-                resolve_path(P, rec.x, rec.y, rec.z, solid, coverageCount, px, py, s);
+                if ((rec.x & kMetaSimplePaint) != 0u)
+                {
+                    // The common case, straight-line: premultiplied solid colour, src-over, no clip /
+                    // clip rect / image (resolve_path's arithmetic on the unpacked pixel).
+                    float coverage;
+                    if ((rec.x & kMetaClockwiseFill) != 0u)
+                    {
+                        coverage = clamp01(coverageCount);
+                    }
+                    else
+                    {
+                        coverage = fabsf(coverageCount);
+                        if ((rec.y & kPaintFlagEvenOdd) != 0u)
+                            coverage = 1.f - fabsf(fractf(coverage * .5f) * 2.f + -1.f);
+                        coverage = fminf(coverage, 1.f);
+                    }
+                    const float a = solid.w * coverage;
+                    const float oneMinusA = (1.f - a) * (1.f / 255.f); // the pixel's channels are 0..255
+                    const float d = a != 0.f ? dither : 0.f;
+                    const float r = (solid.x * coverage + colR * oneMinusA) + d;
+                    const float gch = (solid.y * coverage + colG * oneMinusA) + d;
+                    const float b = (solid.z * coverage + colB * oneMinusA) + d;
+                    const float outA = a + colA * oneMinusA;
+                    colR = truncf(__saturatef(r) * 255.f + .5f);
+                    colG = truncf(__saturatef(gch) * 255.f + .5f);
+                    colB = truncf(__saturatef(b) * 255.f + .5f);
+                    colA = truncf(__saturatef(outA) * 255.f + .5f);
+                }
+                else
+                {
+                    PixelState s;
+                    s.color = static_cast<uint32_t>(colR) | (static_cast<uint32_t>(colG) << 8) | (static_cast<uint32_t>(colB) << 16) | (static_cast<uint32_t>(colA) << 24);
+                    s.clipCoverage = clipCoverage;
+                    s.clipID = clipID;
+                    s.dither = dither;
+                    const uint4 res = resolve_path_general(P, rec.x, rec.y, rec.z, solid, coverageCount, px, py, s);
+                    colR = static_cast<float>(res.x & 0xffu);
+                    colG = static_cast<float>((res.x >> 8) & 0xffu);
+                    colB = static_cast<float>((res.x >> 16) & 0xffu);
+                    colA = static_cast<float>(res.x >> 24);
+                    clipCoverage = __uint_as_float(res.y);
+                    clipID = res.z;
+                }
             }
             if (windowStart + kSpanSlots <= lastGroup)
                 __syncthreads();
         }
         openGroup = lastGroup;
-        carryPath = s_path[chunk];
+        carryPath = S.path[chunk];
     }
     {
-        const uint32_t c1 = __shfl_down_sync(0xffffffffu, s.color, 1), c2 = __shfl_down_sync(0xffffffffu, s.color, 2), c3 = __shfl_down_sync(0xffffffffu, s.color, 3);
+        const uint32_t color = static_cast<uint32_t>(colR) | (static_cast<uint32_t>(colG) << 8) | (static_cast<uint32_t>(colB) << 16) | (static_cast<uint32_t>(colA) << 24);
+        const uint32_t c1 = __shfl_down_sync(0xffffffffu, color, 1), c2 = __shfl_down_sync(0xffffffffu, color, 2), c3 = __shfl_down_sync(0xffffffffu, color, 3);
         if (vectorised)
         {
             if ((lane & 3) == 0)
-                *reinterpret_cast<uint4*>(P.target + static_cast<size_t>(py) * P.targetWidth + px) = make_uint4(s.color, c1, c2, c3);
+                *reinterpret_cast<uint4*>(P.target + static_cast<size_t>(py) * P.targetWidth + px) = make_uint4(color, c1, c2, c3);
         }
         else if (inBounds)
         {
-            P.target[static_cast<size_t>(py) * P.targetWidth + px] = s.color;
+            P.target[static_cast<size_t>(py) * P.targetWidth + px] = color;
         }
     }
 }

@@ -146,7 +146,6 @@ int rivecuda_create(int device, rivecuda_ctx** out_ctx)
     for (auto& e : ctx->events)
         RC_CUDA(cudaEventCreate(&e));
     RC_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&ctx->pinnedTotals), 64 * sizeof(uint32_t), cudaHostAllocDefault));
-    RC_CUDA(cudaMalloc(reinterpret_cast<void**>(&ctx->fanTotals), 4 * sizeof(uint32_t)));
     *out_ctx = ctx;
     return 0;
 }
@@ -179,9 +178,8 @@ void rivecuda_destroy(rivecuda_ctx* ctx)
     cudaFree(ctx->tessNormals);
     cudaFree(ctx->atlas);
     for (DeviceBuffer* b : {&ctx->triGeom, &ctx->triAttr, &ctx->tileCounts, &ctx->tileOffsets, &ctx->tileEntries,
-                            &ctx->batchTable, &ctx->imageTable, &ctx->scanScratch, &ctx->clipPlane, &ctx->pathImageSlots, &ctx->atlasTable, &ctx->binCount, &ctx->binPairs, &ctx->hugeList, &ctx->frontEnd, &ctx->fanCells, &ctx->fanPaths})
+                            &ctx->batchTable, &ctx->imageTable, &ctx->scanScratch, &ctx->clipPlane, &ctx->pathImageSlots, &ctx->atlasTable, &ctx->binCount, &ctx->binPairs, &ctx->hugeList, &ctx->frontEnd})
         b->release();
-    cudaFree(ctx->fanTotals);
     cudaFreeHost(ctx->pinnedTotals);
     for (auto& e : ctx->events)
         cudaEventDestroy(e);

@@ -126,7 +126,6 @@ struct PendingTail
     const void* triAttr = nullptr;
     const void* triPos = nullptr; // non-null: raster_tiles_exact_kernel
     bool spans = false;           // raster_spans_kernel instead of raster_tiles_kernel
-    std::shared_ptr<void> fan;    // FanTables (fan winding of the span rasteriser), if the flush uses them
     uint32_t* tileOffsets = nullptr;
     uint32_t* tileCounts = nullptr;
     uint32_t* bigCursors = nullptr;
@@ -171,8 +170,7 @@ struct rivecuda_ctx
     // Raster work buffers (grow-only).
     rivecuda::DeviceBuffer triPos; // fp32 vertex positions per raw triangle (exact-interpolation flushes)
     rivecuda::DeviceBuffer triGeom, triAttr, tileCounts, tileOffsets, tileEntries, batchTable, imageTable,
-        scanScratch, clipPlane, pathImageSlots, atlasTable, binCount, binPairs, hugeList, frontEnd, fanCells, fanPaths;
-    uint32_t* fanTotals = nullptr; // device: [0] backdrop cells in use, [1] cells the flush would need
+        scanScratch, clipPlane, pathImageSlots, atlasTable, binCount, binPairs, hugeList, frontEnd;
     uint32_t* pinnedTotals = nullptr; // pinned host words for small D2H results
 
     // Profiling.
