@@ -40,7 +40,10 @@
 #define RIVECUDA_SPAN_SLOTS 16
 #endif
 constexpr int kSpanSlots = RIVECUDA_SPAN_SLOTS; // power of two
-constexpr int kSpanChunk = 256;
+#ifndef RIVECUDA_SPAN_CHUNK
+#define RIVECUDA_SPAN_CHUNK 256
+#endif
+constexpr int kSpanChunk = RIVECUDA_SPAN_CHUNK; // list entries per round (<= 256, the CTA size)
 constexpr float kSpanFixedOne = 65536.f; // coverage 1.0 in a fill's plane word
 
 constexpr uint32_t kSpanStroke = 1u << 24;
@@ -57,15 +60,13 @@ struct SpanTri // 16 words (64 B), one per (entry, tile), in shared memory
 };
 static_assert(sizeof(SpanTri) == 64, "SpanTri");
 
-struct SpanSlot // a group: what the resolve step needs of its path, and which warps it touched
+struct SpanSlot // a group: what the resolve step needs of its path
 {
     uint32_t meta, paintX, paintY;
-    uint32_t touch;   // bit w: some entry of the group reaches the pixel rows of warp w
+    uint32_t pad0;
     float solid[4];
-    int32_t backdrop; // coverage (16.16) of the group's triangles that cover the whole tile with a constant
-    uint32_t pad[3];
 };
-static_assert(sizeof(SpanSlot) == 48, "SpanSlot");
+static_assert(sizeof(SpanSlot) == 32, "SpanSlot");
 
 // Shared memory of raster_spans_kernel (dynamic: more than 48 KB with 32 slots).
 struct SpanShared
@@ -75,7 +76,8 @@ struct SpanShared
     uint16_t units[kSpanChunk * kTileSize];
     uint32_t ids[2][kSpanChunk];
     SpanSlot slot[kSpanSlots];
-    uint32_t path[kSpanChunk + 4];
+    uint32_t path[kSpanChunk + 3];
+    uint32_t unitCount;
     uint32_t warpSums[2][8];
     uint64_t bar[2];
 };
@@ -279,10 +281,10 @@ __global__ void __launch_bounds__(256, RIVECUDA_SPAN_MIN_BLOCKS) raster_spans_ke
     // A warp owns two pixel rows: the row prefix sums of the resolve step stay inside a half warp
     // and a plane's words are read lane by lane (no bank conflicts).
     int i = lane & 15, j = warp * 2 + (lane >> 4);
-    uint32_t warpBit = 1u << warp, tid4 = threadIdx.x * 4u;
+    uint32_t tid4 = threadIdx.x * 4u;
     // Opaque to the compiler: kept in registers instead of being re-derived from the thread id
     // at every use inside the loops.
-    asm volatile("" : "+r"(i), "+r"(j), "+r"(warpBit), "+r"(tid4));
+    asm volatile("" : "+r"(i), "+r"(j), "+r"(tid4));
     const int px = originX + i, py = originY + j;
     const bool inBounds = px >= P.boundsL && px < P.boundsR && py >= P.boundsT && py < P.boundsB;
 
@@ -332,6 +334,7 @@ __global__ void __launch_bounds__(256, RIVECUDA_SPAN_MIN_BLOCKS) raster_spans_ke
         reinterpret_cast<uint32_t*>(&S.slot[0])[threadIdx.x] = 0u;
     if (threadIdx.x == 0)
     {
+        S.unitCount = 0u;
         mbar_init(barAddr, 1u);
         mbar_init(barAddr + 8u, 1u);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -363,7 +366,8 @@ __global__ void __launch_bounds__(256, RIVECUDA_SPAN_MIN_BLOCKS) raster_spans_ke
             *(reinterpret_cast<uint4*>(&g) + 1) = __ldg(src + 1);
             pathID = g.meta & 0xffffu;
         }
-        S.path[threadIdx.x + 1] = pathID;
+        if (threadIdx.x < kSpanChunk)
+            S.path[threadIdx.x + 1] = pathID;
         if (threadIdx.x == 0)
             S.path[0] = carryPath;
         __syncthreads();
@@ -393,7 +397,6 @@ __global__ void __launch_bounds__(256, RIVECUDA_SPAN_MIN_BLOCKS) raster_spans_ke
         const uint32_t group = openGroup + groupsBefore + __popc(flagBits & ((2u << lane) - 1u));
         const uint32_t lastGroup = openGroup + groupsInChunk;
         const uint32_t rows = (live && !wholeTile) ? ((rowRange >> 4) - (rowRange & 15u) + 1u) : 0u;
-        const uint32_t mySlotAddr = slotsAddr + (group & (kSpanSlots - 1)) * static_cast<uint32_t>(sizeof(SpanSlot));
         if (rows != 0u)
             S.tri[threadIdx.x].info |= (group & (kSpanSlots - 1)) << 16;
 #ifdef RIVECUDA_STATS
@@ -435,53 +438,36 @@ __global__ void __launch_bounds__(256, RIVECUDA_SPAN_MIN_BLOCKS) raster_spans_ke
                 slot.meta = meta;
                 slot.paintX = paint.x;
                 slot.paintY = paint.y;
-                slot.touch = 0u;
+                slot.pad0 = 0u;
                 slot.solid[0] = pc.x;
                 slot.solid[1] = pc.y;
                 slot.solid[2] = pc.z;
                 slot.solid[3] = pc.w;
-                slot.backdrop = 0;
             }
-            // Expand (entry, row) units: exclusive scan of the row counts over the CTA.
-            const uint32_t myRows = inWindow ? rows : 0u;
-            uint32_t incl = myRows;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1)
-            {
-                const uint32_t up = __shfl_up_sync(0xffffffffu, incl, o);
-                if (lane >= o)
-                    incl += up;
-            }
-            if (lane == 31)
-                S.warpSums[scanBuf][warp] = incl;
-            __syncthreads();
-            uint32_t unitBase = 0u, unitCount = 0u;
-#pragma unroll
-            for (int w = 0; w < 8; ++w)
-            {
-                const uint32_t c = S.warpSums[scanBuf][w];
-                unitBase += w < warp ? c : 0u;
-                unitCount += c;
-            }
-            scanBuf ^= 1u;
+            // Expand (entry, row) units: every entry claims its run of units with one shared-memory
+            // atomic (their order does not matter); the counter was cleared during the previous
+            // resolve step.
             if (inWindow && live)
             {
                 if (wholeTile)
                 {
-                    // The triangle contains the whole tile: a constant for every pixel.
-                    red_add_shared(mySlotAddr + 32u, __float2int_rn(S.tri[threadIdx.x].p0[0]));
-                    red_or_shared(mySlotAddr + 12u, 0xffu);
+                    // The triangle contains the whole tile: its constant at pixel 0 of every row.
+                    const int add = __float2int_rn(S.tri[threadIdx.x].p0[0]);
+                    const uint32_t planeAddr = planesAddr + (group & (kSpanSlots - 1)) * 1024u;
+#pragma unroll
+                    for (int r = 0; r < kTileSize; ++r)
+                        red_add_shared(planeAddr + static_cast<uint32_t>(r) * 64u, add);
                 }
                 else
                 {
-                    const uint32_t first = rowRange & 15u, last = rowRange >> 4;
-                    red_or_shared(mySlotAddr + 12u, (2u << (last >> 1)) - (1u << (first >> 1)));
-                    uint32_t dst = unitBase + incl - myRows;
-                    for (uint32_t r = 0; r < myRows; ++r)
+                    const uint32_t first = rowRange & 15u;
+                    const uint32_t dst = atomicAdd(&S.unitCount, rows);
+                    for (uint32_t r = 0; r < rows; ++r)
                         S.units[dst + r] = static_cast<uint16_t>((threadIdx.x << 4) | (first + r));
                 }
             }
             __syncthreads();
+            const uint32_t unitCount = S.unitCount;
 
             // Fill: a lane per (entry, row).
             for (uint32_t u = threadIdx.x; u < unitCount; u += 256)
@@ -545,28 +531,39 @@ __global__ void __launch_bounds__(256, RIVECUDA_SPAN_MIN_BLOCKS) raster_spans_ke
             __syncthreads();
 
             // Resolve, in order, the groups of the window that are complete.
+            if (threadIdx.x == 0)
+                S.unitCount = 0u; // (every thread has read it; the next window's claims come after a barrier)
+            if (!lastChunk && windowStart + kSpanSlots > lastGroup)
+            {
+                // Last window of the chunk: the next chunk's ids have landed by now; start its
+                // triangle records on their way while this window resolves.
+                mbar_wait(barAddr + (buf ^ 1u) * 8u, ((chunkIndex + 1u) >> 1) & 1u);
+                if (threadIdx.x < min(static_cast<uint32_t>(kSpanChunk), n - base - kSpanChunk))
+                {
+                    const void* next = triGeom + S.ids[buf ^ 1u][threadIdx.x];
+                    asm volatile("prefetch.global.L1 [%0];" ::"l"(next));
+                }
+            }
             const uint32_t windowEnd = min(windowStart + kSpanSlots, lastGroup + 1u);
             const uint32_t resolveEnd = (windowEnd == lastGroup + 1u && !lastChunk) ? lastGroup : windowEnd;
             for (uint32_t gi = windowStart; gi < resolveEnd; ++gi)
             {
                 const uint32_t slotIdx = gi & (kSpanSlots - 1);
                 const uint32_t slotAddr = slotsAddr + slotIdx * static_cast<uint32_t>(sizeof(SpanSlot));
-                const uint4 rec = lds_u32x4(slotAddr);
-                if ((rec.w & warpBit) == 0u)
-                    continue; // nothing of this path reaches the warp's two pixel rows
                 const uint32_t wordAddr = planesAddr + slotIdx * 1024u + tid4;
                 const int v = static_cast<int>(lds_u32(wordAddr));
+                const uint32_t nonZero = __ballot_sync(0xffffffffu, v != 0);
+                if (nonZero == 0u)
+                    continue; // nothing of this path in the warp's two pixel rows
                 if (v != 0)
                     asm volatile("st.shared.u32 [%0], %1;" ::"r"(wordAddr), "r"(0) : "memory");
-                float coverageCount;
-                if (((rec.x >> kMetaKindShift) & 0xf) == kKindStroke)
+                const uint4 rec = lds_u32x4(slotAddr);
+                // Coverage count: a float for strokes (the plane holds float bits), 16.16 for fills.
+                const bool isStroke = ((rec.x >> kMetaKindShift) & 0xf) == kKindStroke;
+                int acc = 0;
+                if (!isStroke)
                 {
-                    coverageCount = __int_as_float(v);
-                }
-                else
-                {
-                    int acc;
-                    if ((__ballot_sync(0xffffffffu, v != 0) & 0xfffefffeu) == 0u)
+                    if ((nonZero & 0xfffefffeu) == 0u)
                     {
                         // Deltas at most at pixel 0 of the two rows (rows a triangle covers from
                         // the tile's left edge on): the row's value is that delta.
@@ -583,9 +580,8 @@ __global__ void __launch_bounds__(256, RIVECUDA_SPAN_MIN_BLOCKS) raster_spans_ke
                                 acc += up;
                         }
                     }
-                    acc += static_cast<int>(lds_u32(slotAddr + 32u));
-                    coverageCount = static_cast<float>(acc) * (1.f / kSpanFixedOne);
                 }
+                const float coverageCount = isStroke ? __int_as_float(v) : static_cast<float>(acc) * (1.f / kSpanFixedOne);
 #ifdef RIVECUDA_STATS
                 {
                     const uint32_t nz = __ballot_sync(0xffffffffu, coverageCount != 0.f);
@@ -605,16 +601,28 @@ __global__ void __launch_bounds__(256, RIVECUDA_SPAN_MIN_BLOCKS) raster_spans_ke
                     // The common case, straight-line: premultiplied solid colour, src-over, no clip /
                     // clip rect / image (resolve_path's arithmetic on the unpacked pixel).
                     float coverage;
-                    if ((rec.x & kMetaClockwiseFill) != 0u)
+                    if (isStroke)
                     {
-                        coverage = clamp01(coverageCount);
+                        coverage = fminf(fabsf(coverageCount), 1.f);
                     }
                     else
                     {
-                        coverage = fabsf(coverageCount);
-                        if ((rec.y & kPaintFlagEvenOdd) != 0u)
-                            coverage = 1.f - fabsf(fractf(coverage * .5f) * 2.f + -1.f);
-                        coverage = fminf(coverage, 1.f);
+                        // Fill rules on the 16.16 count (exact: the same values as in float).
+                        int c;
+                        if ((rec.x & kMetaClockwiseFill) != 0u)
+                        {
+                            c = max(acc, 0);
+                        }
+                        else
+                        {
+                            c = abs(acc);
+                            if ((rec.y & kPaintFlagEvenOdd) != 0u)
+                            {
+                                c &= 0x1ffff; // mod 2
+                                c = c > 0x10000 ? 0x20000 - c : c;
+                            }
+                        }
+                        coverage = static_cast<float>(min(c, 0x10000)) * (1.f / kSpanFixedOne);
                     }
                     const float a = solid.w * coverage;
                     const float oneMinusA = (1.f - a) * (1.f / 255.f); // the pixel's channels are 0..255
