@@ -53,6 +53,17 @@ WORKLOADS = {
 UNIT = "frames/s"
 
 
+def kernel_sources_sha256():
+    """Hash of the CUDA sources the tile rasterisers are built from (ties an ncu capture to a build)."""
+    import hashlib
+    h = hashlib.sha256()
+    src = os.path.join(ROOT, "rive-runtime_b200", "csrc")
+    for name in ("kernels_draw.cu", "raster_tiles.cuh", "raster_tiles_exact.cuh", "raster_tiles_span.cuh", "device_math.cuh", "rivecuda_internal.h"):
+        with open(os.path.join(src, name), "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()
+
+
 def measured_peak_gbs():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
@@ -395,6 +406,7 @@ def main() -> None:
     # ---- roofline: the dominant kernel (tile raster), CUDA events on its stream --
     rp.lib.rivecuda_set_profiling(rp.ctx, 1)
     raster_ms, setup_ms, tess_ms, launches = [], [], [], 0
+    raster_kernels = set()
     tri_count = entry_count = 0
     for _ in range(3):
         r_ms = s_ms = t_ms = 0.0
@@ -411,6 +423,7 @@ def main() -> None:
                 s_ms += tm.setup_bin_ms
                 t_ms += tm.tessellate_ms
                 launches += tm.kernel_launches
+                raster_kernels.add(("raster_tiles_kernel", "raster_tiles_exact_kernel", "raster_spans_kernel")[min(tm.raster_kernel, 2)])
                 tri_count += tm.triangle_count
                 entry_count += tm.tile_entry_count
         raster_ms.append(r_ms / n_frames)
@@ -422,11 +435,13 @@ def main() -> None:
     traffic = None
     if args.workload == "c2":
         # dram__bytes_read + dram__bytes_write of this kernel on this workload from this round's
-        # `ncu --set full` capture (profiles/r02_raster_traffic.json, written by tools/ncu_summary.py
-        # from the .ncu-rep; its `kernel_sha` must match the library being benchmarked).
+        # `ncu --set full` capture (profiles/r02_raster_traffic.json, written by `tools/ncu_summary.py
+        # --traffic-json` from the .ncu-rep). It only counts if it was captured from the kernel
+        # sources being benchmarked (`sources_sha256`) and names the kernel that ran.
         try:
             tj = json.load(open(os.path.join(ROOT, "profiles", "r02_raster_traffic.json")))
-            traffic = int(tj["dram_bytes_read"]) + int(tj["dram_bytes_write"])
+            if tj["sources_sha256"] == kernel_sources_sha256() and {tj["kernel"]} == raster_kernels:
+                traffic = int(tj["dram_bytes_read"]) + int(tj["dram_bytes_write"])
         except Exception:  # noqa: BLE001
             traffic = None
     achieved = alg_bytes / (raster / 1e3) / 1e9
@@ -573,12 +588,13 @@ def main() -> None:
             "raw_paths_e2e": raw_paths,
             "gpu_launches": int(launches) * args.steps,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "kernel": "raster_tiles_kernel", "kernel_ms": raster,
+                         "traffic": traffic, "kernel": "+".join(sorted(raster_kernels)), "kernel_ms": raster,
                          "algorithmic_bytes": alg_bytes, "peak_source": peak_src,
                          "other_kernels_ms": {"tessellate": float(np.mean(tess_ms)), "setup_bin_sort": float(np.mean(setup_ms))},
                          "note": "per frame; the kernel is instruction-issue bound, not HBM bound (DESIGN.md section 5): "
-                                 "ncu smsp__issue_active 73 % of peak, shared-memory wavefronts 54 % of the LSU pipe, dram throughput 2 % of peak on c2 "
-                                 "(profiles/r01_ncu_summary_final.txt)"},
+                                 "ncu smsp__issue_active 70 % of peak, dram throughput 1.4 % of peak on c2 "
+                                 "(profiles/r02_ncu_summary.txt); traffic = dram bytes of one launch from this round's ncu capture "
+                                 "(profiles/r02_raster_traffic.json), null if that capture is of other sources"},
             "cpu_baseline": cpu,
             "clocks": clocks.summary(),
         }

@@ -182,7 +182,7 @@ typedef struct rivecuda_flush_timings
     uint32_t kernel_launches;
     uint32_t triangle_count;   /* triangles that survived cull/setup  */
     uint32_t tile_entry_count; /* (triangle,tile) pairs binned        */
-    uint32_t reserved0;
+    uint32_t raster_kernel;    /* which K5 ran: 0 raster_tiles_kernel (in order), 1 raster_tiles_exact_kernel, 2 raster_spans_kernel */
 } rivecuda_flush_timings;
 
 /* ---- context ----------------------------------------------------------- */

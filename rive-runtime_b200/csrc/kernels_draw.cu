@@ -556,8 +556,12 @@ __device__ __forceinline__ bool tile_overlaps(const EdgeEq E[3], int tileX, int 
 // invoked by whichever lane found the overlap; ownerLane says whose triangle it
 // is. Returns how the calling lane's own triangle was handled.
 constexpr int kSmallTileCount = 4;
-constexpr int kHugeTileCount = 512;   // above this a triangle's tile range is walked by bin_huge_kernel,
-constexpr int kHugeChunkTiles = 2048; // one CTA per chunk of this many tiles of the range
+#ifndef RIVECUDA_HUGE_TILES
+#define RIVECUDA_HUGE_TILES 128
+#define RIVECUDA_HUGE_CHUNK 512
+#endif
+constexpr int kHugeTileCount = RIVECUDA_HUGE_TILES;   // above this a triangle's tile range is walked by bin_huge_kernel,
+constexpr int kHugeChunkTiles = RIVECUDA_HUGE_CHUNK; // one CTA per chunk of this many tiles of the range
 
 enum TileWalk : int
 {
@@ -1755,7 +1759,7 @@ int launch_draw_list(rivecuda_ctx* ctx, const rivecuda_flush_desc& desc, const r
             return s;
         triGeom = ctx->triGeom.as<TriGeom>();
         triAttr = ctx->triAttr.as<TriAttr>();
-        bins.hugeCapacity = rawTriangles + 65536u;
+        bins.hugeCapacity = rawTriangles + (1u << 20);
         if (int s = ctx->hugeList.reserve(static_cast<size_t>(bins.hugeCapacity) * sizeof(uint2)))
             return s;
         bins.binCount = ctx->binCount.as<uint8_t>();
@@ -1846,6 +1850,7 @@ int launch_draw_list(rivecuda_ctx* ctx, const rivecuda_flush_desc& desc, const r
     RC_CUDA(cudaMemcpyAsync(ctx->pinnedTotals + 1, hugeCount + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
     RC_CUDA(cudaEventRecord(ctx->countsReady, stream));
     ctx->lastTimings.triangle_count = rawTriangles;
+    ctx->lastTimings.raster_kernel = exact ? 1u : (spans ? 2u : 0u);
 
     if (ctx->tileEntries.capacity == 0)
     {

@@ -327,19 +327,21 @@ __global__ void __launch_bounds__(256, RIVECUDA_SPAN_MIN_BLOCKS) raster_spans_ke
     const uint32_t triAddr = smemBase + static_cast<uint32_t>(offsetof(SpanShared, tri));
     const uint32_t planesAddr = smemBase + static_cast<uint32_t>(offsetof(SpanShared, plane));
     const uint32_t slotsAddr = smemBase + static_cast<uint32_t>(offsetof(SpanShared, slot));
-    for (int k = threadIdx.x; k < kSpanSlots * 64; k += 256)
-        reinterpret_cast<uint4*>(&S.plane[0][0])[k] = make_uint4(0u, 0u, 0u, 0u);
-    // (Group 0 is the empty group before the first entry: nothing touched.)
-    if (threadIdx.x < kSpanSlots * sizeof(SpanSlot) / 4)
-        reinterpret_cast<uint32_t*>(&S.slot[0])[threadIdx.x] = 0u;
-    if (threadIdx.x == 0)
+    if (n != 0u)
+    {
+        for (int k = threadIdx.x; k < kSpanSlots * 64; k += 256)
+            reinterpret_cast<uint4*>(&S.plane[0][0])[k] = make_uint4(0u, 0u, 0u, 0u);
+        // (Group 0 is the empty group before the first entry: nothing touched.)
+        if (threadIdx.x < kSpanSlots * sizeof(SpanSlot) / 4)
+            reinterpret_cast<uint32_t*>(&S.slot[0])[threadIdx.x] = 0u;
+    }
+    if (threadIdx.x == 0 && n != 0u)
     {
         S.unitCount = 0u;
         mbar_init(barAddr, 1u);
         mbar_init(barAddr + 8u, 1u);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        if (n != 0u)
-            tma_load_1d(idsAddr, list, (min(static_cast<uint32_t>(kSpanChunk), n) * 4u + 15u) & ~15u, barAddr);
+        tma_load_1d(idsAddr, list, (min(static_cast<uint32_t>(kSpanChunk), n) * 4u + 15u) & ~15u, barAddr);
     }
 
     uint32_t openGroup = 0u;   // absolute index of the group that may continue into the next chunk

@@ -119,7 +119,7 @@ class FlushTimings(ctypes.Structure):
         ("kernel_launches", ctypes.c_uint32),
         ("triangle_count", ctypes.c_uint32),
         ("tile_entry_count", ctypes.c_uint32),
-        ("reserved0", ctypes.c_uint32),
+        ("raster_kernel", ctypes.c_uint32),
     ]
 
 

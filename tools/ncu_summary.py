@@ -54,7 +54,33 @@ def report(path, top=0.006):
             print(f"{i:5d} {int(r[ia]):12d} {r[ist]:>7s}  {r[isrc][:100]}")
 
 
+def traffic_json(rep, out):
+    """profiles/r02_raster_traffic.json: DRAM bytes of one launch of the captured kernel (bench.py's
+    roofline.traffic), tied to the kernel sources by bench.kernel_sources_sha256()."""
+    import json
+    import os
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    h, units, v = rows[0], rows[1], rows[2]
+
+    def val(name):
+        i = h.index(name)
+        x = float(v[i].replace(",", ""))
+        return x * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1e-6, "us": 1e-3, "ms": 1.0, "s": 1e3}.get(units[i], 1)
+
+    kernel = v[h.index("Kernel Name")].split("(")[0].split("::")[-1]
+    json.dump({"kernel": kernel, "dram_bytes_read": int(val("dram__bytes_read.sum")), "dram_bytes_write": int(val("dram__bytes_write.sum")),
+               "duration_ms_under_ncu": val("gpu__time_duration.sum"), "workload": "c2 (tests/golden/c2_4k.rvct.xz via tools/quickbench.py)",
+               "capture": os.path.basename(rep), "sources_sha256": bench.kernel_sources_sha256()}, open(out, "w"), indent=1)
+    print(open(out).read())
+
+
 if __name__ == "__main__":
+    if len(sys.argv) == 4 and sys.argv[1] == "--traffic-json":
+        traffic_json(sys.argv[3], sys.argv[2])
+        sys.exit(0)
     for p in sys.argv[1:]:
         print("==", p)
         if p.endswith(".csv"):
