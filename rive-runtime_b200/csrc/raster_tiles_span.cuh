@@ -46,6 +46,7 @@ constexpr int kSpanSlots = RIVECUDA_SPAN_SLOTS; // power of two
 constexpr int kSpanChunk = RIVECUDA_SPAN_CHUNK; // list entries per round (<= 256, the CTA size)
 constexpr float kSpanFixedOne = 65536.f; // coverage 1.0 in a fill's plane word
 
+constexpr uint32_t kSpanModeSimple = 1u, kSpanModeStroke = 2u, kSpanModeClockwise = 4u, kSpanModeEvenOdd = 8u; // SpanSlot::mode
 constexpr uint32_t kSpanStroke = 1u << 24;
 constexpr uint32_t kSpanFlat = 1u << 25;
 
@@ -63,7 +64,7 @@ static_assert(sizeof(SpanTri) == 64, "SpanTri");
 struct SpanSlot // a group: what the resolve step needs of its path
 {
     uint32_t meta, paintX, paintY;
-    uint32_t pad0;
+    uint32_t mode; // kSpanMode*
     float solid[4];
 };
 static_assert(sizeof(SpanSlot) == 32, "SpanSlot");
@@ -440,7 +441,11 @@ __global__ void __launch_bounds__(256, RIVECUDA_SPAN_MIN_BLOCKS) raster_spans_ke
                 slot.meta = meta;
                 slot.paintX = paint.x;
                 slot.paintY = paint.y;
-                slot.pad0 = 0u;
+                // How the resolve step turns the plane word into coverage.
+                const bool strokeKind = ((g.meta >> kMetaKindShift) & 0xf) == kKindStroke;
+                slot.mode = ((meta & kMetaSimplePaint) != 0u ? kSpanModeSimple : 0u) | (strokeKind ? kSpanModeStroke : 0u) |
+                            ((g.meta & kMetaClockwiseFill) != 0u ? kSpanModeClockwise : 0u) |
+                            (!strokeKind && (g.meta & kMetaClockwiseFill) == 0u && (paint.x & kPaintFlagEvenOdd) != 0u ? kSpanModeEvenOdd : 0u);
                 slot.solid[0] = pc.x;
                 slot.solid[1] = pc.y;
                 slot.solid[2] = pc.z;
@@ -561,7 +566,8 @@ __global__ void __launch_bounds__(256, RIVECUDA_SPAN_MIN_BLOCKS) raster_spans_ke
                     asm volatile("st.shared.u32 [%0], %1;" ::"r"(wordAddr), "r"(0) : "memory");
                 const uint4 rec = lds_u32x4(slotAddr);
                 // Coverage count: a float for strokes (the plane holds float bits), 16.16 for fills.
-                const bool isStroke = ((rec.x >> kMetaKindShift) & 0xf) == kKindStroke;
+                const uint32_t mode = rec.w;
+                const bool isStroke = (mode & kSpanModeStroke) != 0u;
                 int acc = 0;
                 if (!isStroke)
                 {
@@ -583,10 +589,9 @@ __global__ void __launch_bounds__(256, RIVECUDA_SPAN_MIN_BLOCKS) raster_spans_ke
                         }
                     }
                 }
-                const float coverageCount = isStroke ? __int_as_float(v) : static_cast<float>(acc) * (1.f / kSpanFixedOne);
 #ifdef RIVECUDA_STATS
                 {
-                    const uint32_t nz = __ballot_sync(0xffffffffu, coverageCount != 0.f);
+                    const uint32_t nz = __ballot_sync(0xffffffffu, isStroke ? v != 0 : acc != 0);
                     if (lane == 0)
                     {
                         SPAN_STAT(8, 1);
@@ -595,48 +600,40 @@ __global__ void __launch_bounds__(256, RIVECUDA_SPAN_MIN_BLOCKS) raster_spans_ke
                     }
                 }
 #endif
-                if (coverageCount == 0.f)
+                if ((isStroke ? v : acc) == 0)
                     continue;
                 const float4 solid = lds_f32x4(slotAddr + 16);
-                if ((rec.x & kMetaSimplePaint) != 0u)
+                if ((mode & kSpanModeSimple) != 0u)
                 {
                     // The common case, straight-line: premultiplied solid colour, src-over, no clip /
-                    // clip rect / image (resolve_path's arithmetic on the unpacked pixel).
+                    // clip rect / image (resolve_path's arithmetic on the unpacked pixel; the fill
+                    // rules on the 16.16 count give the same values as in float).
                     float coverage;
                     if (isStroke)
                     {
-                        coverage = fminf(fabsf(coverageCount), 1.f);
+                        coverage = fminf(__int_as_float(v), 1.f);
                     }
                     else
                     {
-                        // Fill rules on the 16.16 count (exact: the same values as in float).
-                        int c;
-                        if ((rec.x & kMetaClockwiseFill) != 0u)
+                        int c = (mode & kSpanModeClockwise) != 0u ? max(acc, 0) : abs(acc);
+                        if ((mode & kSpanModeEvenOdd) != 0u)
                         {
-                            c = max(acc, 0);
-                        }
-                        else
-                        {
-                            c = abs(acc);
-                            if ((rec.y & kPaintFlagEvenOdd) != 0u)
-                            {
-                                c &= 0x1ffff; // mod 2
-                                c = c > 0x10000 ? 0x20000 - c : c;
-                            }
+                            c &= 0x1ffff; // mod 2
+                            c = c > 0x10000 ? 0x20000 - c : c;
                         }
                         coverage = static_cast<float>(min(c, 0x10000)) * (1.f / kSpanFixedOne);
                     }
                     const float a = solid.w * coverage;
                     const float oneMinusA = (1.f - a) * (1.f / 255.f); // the pixel's channels are 0..255
                     const float d = a != 0.f ? dither : 0.f;
-                    const float r = (solid.x * coverage + colR * oneMinusA) + d;
-                    const float gch = (solid.y * coverage + colG * oneMinusA) + d;
-                    const float b = (solid.z * coverage + colB * oneMinusA) + d;
-                    const float outA = a + colA * oneMinusA;
-                    colR = truncf(__saturatef(r) * 255.f + .5f);
-                    colG = truncf(__saturatef(gch) * 255.f + .5f);
-                    colB = truncf(__saturatef(b) * 255.f + .5f);
-                    colA = truncf(__saturatef(outA) * 255.f + .5f);
+                    const float r = __fmaf_rn(colR, oneMinusA, solid.x * coverage) + d;
+                    const float gch = __fmaf_rn(colG, oneMinusA, solid.y * coverage) + d;
+                    const float b = __fmaf_rn(colB, oneMinusA, solid.z * coverage) + d;
+                    const float outA = __fmaf_rn(colA, oneMinusA, a);
+                    colR = truncf(__fmaf_rn(__saturatef(r), 255.f, .5f));
+                    colG = truncf(__fmaf_rn(__saturatef(gch), 255.f, .5f));
+                    colB = truncf(__fmaf_rn(__saturatef(b), 255.f, .5f));
+                    colA = truncf(__fmaf_rn(__saturatef(outA), 255.f, .5f));
                 }
                 else
                 {
@@ -645,6 +642,7 @@ __global__ void __launch_bounds__(256, RIVECUDA_SPAN_MIN_BLOCKS) raster_spans_ke
                     s.clipCoverage = clipCoverage;
                     s.clipID = clipID;
                     s.dither = dither;
+                    const float coverageCount = isStroke ? __int_as_float(v) : static_cast<float>(acc) * (1.f / kSpanFixedOne);
                     const uint4 res = resolve_path_general(P, rec.x, rec.y, rec.z, solid, coverageCount, px, py, s);
                     colR = static_cast<float>(res.x & 0xffu);
                     colG = static_cast<float>((res.x >> 8) & 0xffu);
