@@ -215,7 +215,7 @@ __device__ __forceinline__ bool prepare_span_entry(const TriGeom& g, const TriAt
     {
 #pragma unroll
         for (int e = 0; e < 3; ++e)
-            out.p1[e] = Ai[e] != 0 ? 1.f / static_cast<float>(Ai[e]) : 0.f;
+            out.p1[e] = Ai[e] != 0 ? __frcp_rn(static_cast<float>(Ai[e])) : 0.f;
     }
     rowRange = static_cast<uint32_t>(by0) | (static_cast<uint32_t>(by1) << 4);
     out.info = rowRange | (static_cast<uint32_t>(bx0) << 8) | (static_cast<uint32_t>(bx1) << 12) | flags;

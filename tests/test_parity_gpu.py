@@ -86,6 +86,42 @@ def test_scene_parity(libs, name):
         assert differing == 0, f"{name}: frame {k}: {differing} pixels of the exact rasteriser's frame differ from the oracle's"
 
 
+
+SPAN_SCENES = ["c1", "s1", "beziers", "parallelclips", "largeclippedpath_winding_nested", "verycomplexgrad", "negative_interior_triangles",
+               "batchedtriangulations", "strokes_round", "poly_evenOdd", "retrofitcubictristrips", "interleavedfillrule", "overfill_transparent"]
+
+
+@pytest.mark.parametrize("name", SPAN_SCENES)
+def test_span_rasteriser_agrees_with_the_in_order_rasteriser(libs, name, monkeypatch):
+    """raster_spans_kernel (per-row spans into shared-memory delta planes, any order inside a path)
+    against raster_tiles_kernel (every fragment in API order, fp16 rounding per fragment) on fills,
+    strokes, interior triangulation, clips, nested clips, gradients and both fill rules: the same
+    frame to within 1/255, and the flush timings must name the kernel that ran -- a silent switch
+    of rasteriser would otherwise go unnoticed."""
+    replay, T, _ = libs
+    recs = T.parse(os.path.join(GOLDEN, name + ".rvct.xz"))
+
+    def render(spans):
+        monkeypatch.setenv("RIVECUDA_EXACT", "0")
+        monkeypatch.setenv("RIVECUDA_SPANS", "1" if spans else "0")
+        kernels = set()
+        result = replay.ReplayResult()
+        with replay.Replayer(0, profiling=True) as rp:
+            for r in recs:
+                if r.tag in (T.CREATE, T.DESTROY):
+                    continue
+                rp.apply(r, result)
+                if r.tag == T.FLUSH:
+                    kernels.add(rp.timings().raster_kernel)
+        return result.frames, kernels
+
+    fast, fast_kernels = render(True)
+    ordered, ordered_kernels = render(False)
+    assert 2 in fast_kernels and ordered_kernels == {0}
+    assert len(fast) == len(ordered) >= 1
+    for a, b in zip(fast, ordered):
+        assert int(np.abs(a.astype(int) - b.astype(int)).max()) <= 1
+
 def test_c2_full_size_parity_and_properties(libs):
     """BASELINE.json configs[1] at full size (10k paths, 3840x2160): parity with the
     oracle, idempotence, and band decomposition (size-independent properties)."""
