@@ -4,6 +4,7 @@
  * No device code lives here.
  */
 #include "render_context_cuda_impl.hpp"
+#include "png_decode.hpp"
 
 #include <algorithm>
 
@@ -328,6 +329,30 @@ rcp<RenderBuffer> RenderContextCUDAImpl::makeRenderBuffer(
     size_t sizeInBytes)
 {
     return make_rcp<RenderBufferCUDA>(m_abi, m_ctx, type, flags, sizeInBytes);
+}
+
+rcp<Texture> RenderContextCUDAImpl::platformDecodeImageTexture(
+    Span<const uint8_t> encodedBytes)
+{
+    uint32_t width = 0, height = 0;
+    std::vector<uint8_t> pixels;
+    if (!rivecuda_host::decode_png_rgba_premul(encodedBytes.data(),
+                                               encodedBytes.size(),
+                                               &width,
+                                               &height,
+                                               &pixels))
+    {
+        return nullptr; // not a PNG this decoder reads: the front end tries its own decoders, if built
+    }
+    return makeImageTexture(width,
+                            height,
+                            math::msb(height | width),
+                            GPUTextureFormat::rgba32,
+                            pixels.data(),
+                            /*blockWidth=*/1,
+                            /*blockHeight=*/1,
+                            /*srgb=*/false,
+                            /*generateRemainingMips=*/true);
 }
 
 rcp<Texture> RenderContextCUDAImpl::makeImageTexture(

@@ -164,6 +164,10 @@ public:
                                        RenderBufferFlags,
                                        size_t) override;
 
+    // PNG decoding for Factory::decodeImage (png_decode.hpp), premultiplied and mip-mapped as
+    // RenderContext::decodeImage does with the reference's own decoders (render_context.cpp:238-262).
+    rcp<Texture> platformDecodeImageTexture(
+        Span<const uint8_t> encodedBytes) override;
     rcp<Texture> makeImageTexture(uint32_t width,
                                   uint32_t height,
                                   uint32_t mipLevelCount,

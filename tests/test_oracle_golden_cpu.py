@@ -80,7 +80,9 @@ def test_committed_traces_are_what_the_reference_front_end_emits(built, tmp_path
     recorder = os.path.join(ROOT, "rive-runtime_b200", "_build", "librivecuda_trace.so")
     import lzma
     for name, scene, extra in [("beziers", "gm:beziers", []), ("poly_evenOdd", "gm:poly_evenOdd", []),
-                               ("feather_shapes", "gm:feather_shapes", []), ("c1", "c1", [])]:
+                               ("feather_shapes", "gm:feather_shapes", []), ("c1", "c1", []),
+                               # image GMs: PNG assets decoded by RenderContextCUDAImpl::platformDecodeImageTexture
+                               ("image_paint", "gm:image_paint", []), ("mesh", "gm:mesh", [])]:
         out = tmp_path / (name + ".rvct")
         env = dict(os.environ, RIVECUDA_LIB=recorder, RIVECUDA_TRACE_OUT=str(out))
         subprocess.check_call([player, "--scene", scene, *extra], env=env, stdout=subprocess.DEVNULL)
