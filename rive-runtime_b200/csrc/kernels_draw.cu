@@ -39,6 +39,7 @@
 #include <cuda_fp16.h>
 
 #include <algorithm>
+#include <map>
 #include <memory>
 #include <cstring>
 
@@ -1627,6 +1628,7 @@ int launch_draw_list(rivecuda_ctx* ctx, const rivecuda_flush_desc& desc, const r
     std::vector<DeviceBatch> patchBatches, runBatches;
     std::vector<MeshBatchDev> meshBatches;
     std::vector<ImageSlot> imageSlots;
+    std::map<std::pair<const void*, uint32_t>, uint32_t> imageSlotOf;
     uint32_t rawTriangles = 0, patchInstances = 0, runTriangles = 0, meshTriangles = 0;
     for (uint32_t i = 0; i < batchCount; ++i)
     {
@@ -1643,13 +1645,21 @@ int launch_draw_list(rivecuda_ctx* ctx, const rivecuda_flush_desc& desc, const r
         d.samplerKey = b.image_sampler;
         if (b.image_texture != nullptr)
         {
-            if (imageSlots.size() >= kAuxNoImage)
-                return set_error("rivecuda_flush: too many image bindings in one flush");
-            ImageSlot slot = {};
-            slot.texture = b.image_texture->dev;
-            slot.samplerKey = b.image_sampler;
-            d.imageSlot = static_cast<uint32_t>(imageSlots.size());
-            imageSlots.push_back(slot);
+            // One slot per distinct (texture, sampler): a flush may draw thousands of images out
+            // of a handful of textures (GM lots_of_images: 10 000 draws, 512 textures).
+            const auto key = std::make_pair(static_cast<const void*>(b.image_texture), b.image_sampler);
+            auto found = imageSlotOf.find(key);
+            if (found == imageSlotOf.end())
+            {
+                if (imageSlots.size() >= kAuxNoImage)
+                    return set_error("rivecuda_flush: more than %u distinct image bindings in one flush", kAuxNoImage);
+                ImageSlot slot = {};
+                slot.texture = b.image_texture->dev;
+                slot.samplerKey = b.image_sampler;
+                found = imageSlotOf.emplace(key, static_cast<uint32_t>(imageSlots.size())).first;
+                imageSlots.push_back(slot);
+            }
+            d.imageSlot = found->second;
         }
         switch (b.draw_type)
         {
