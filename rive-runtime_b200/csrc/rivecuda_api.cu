@@ -305,11 +305,11 @@ int rivecuda_buffer_resize(rivecuda_ctx* ctx, uint32_t kind, size_t size)
     ring.submittedBytes = 0;
     if (size == 0)
         return 0;
+    // Device slots now; the pinned host copy of a slot when it is first mapped: rings that only
+    // the device front end fills (rivecuda_front_end_paths sizes them for its worst case) never
+    // pay for pinned memory.
     for (int i = 0; i < kRingSize; ++i)
-    {
-        RC_CUDA(cudaHostAlloc(&ring.host[i], size, cudaHostAllocDefault));
         RC_CUDA(cudaMalloc(&ring.device[i], size));
-    }
     return 0;
 }
 
@@ -321,6 +321,8 @@ int rivecuda_buffer_map(rivecuda_ctx* ctx, uint32_t kind, size_t size, void** ou
     if (size > ring.capacity)
         return set_error("rivecuda_buffer_map: map size %zu exceeds capacity %zu (kind %u)", size, ring.capacity, kind);
     ring.current = (ring.current + 1) % kRingSize;
+    if (ring.host[ring.current] == nullptr)
+        RC_CUDA(cudaHostAlloc(&ring.host[ring.current], ring.capacity, cudaHostAllocDefault));
     *out = ring.host[ring.current];
     return 0;
 }

@@ -11,8 +11,9 @@
  * What RiveRenderer::drawPath checks before building a PathDraw is mirrored here
  * (rive_renderer.cpp:121-154): empty paths and strokes with !(thickness > 0) are skipped.
  * Per stroked path the two scalars PathDraw computes with libm are computed here the same way
- * (draw.cpp:603-607, 776-813). Anything else -- clips, gradients, images, feathers, blend modes,
- * opacity -- is not handled by the device front end: the renderer records the first such call
+ * (draw.cpp:603-607, 776-813), and a modulated opacity goes into the colour as PathDraw puts it
+ * there (draw.cpp:727-737). Anything else -- clips, gradients, images, feathers, blend modes --
+ * is not handled by the device front end: the renderer records the first such call
  * and flush() refuses the frame, so the caller can draw it with RiveRenderer (no silent fallback).
  */
 #pragma once
@@ -23,9 +24,11 @@
 #include "rive/math/mat2d.hpp"
 #include "rive/renderer.hpp"
 #include "rive/renderer/gpu.hpp"
+#include "rive/shapes/paint/color.hpp"
 #include "rive_render_paint.hpp"
 #include "rive_render_path.hpp"
 
+#include <algorithm>
 #include <cfloat>
 #include <cmath>
 #include <string>
@@ -46,7 +49,9 @@ public:
         if (m_stack.size() > 1)
             m_stack.pop_back();
     }
-    void transform(const Mat2D& m) override { m_stack.back() = m_stack.back() * m; }
+    void transform(const Mat2D& m) override { m_stack.back().matrix = m_stack.back().matrix * m; }
+    // RiveRenderer::modulateOpacity (rive_renderer.cpp:115-119): part of the save / restore state.
+    void modulateOpacity(float opacity) override { m_stack.back().opacity = std::max(0.0f, m_stack.back().opacity * opacity); }
 
     void drawPath(RenderPath* renderPath, RenderPaint* renderPaint) override
     {
@@ -61,7 +66,7 @@ public:
             refuse("drawPath with a feather / gradient / image / blend mode / clockwise fill");
             return;
         }
-        const Mat2D& m = m_stack.back();
+        const Mat2D& m = m_stack.back().matrix;
         rivecuda_path p;
         memset(&p, 0, sizeof(p));
         p.first_verb = static_cast<uint32_t>(m_verbs.size());
@@ -69,7 +74,8 @@ public:
         p.first_point = static_cast<uint32_t>(m_points.size());
         for (int i = 0; i < 6; ++i)
             p.matrix[i] = m[i];
-        p.color = paint->getColor();
+        // PathDraw applies the modulated opacity to a solid colour (draw.cpp:727-737).
+        p.color = m_stack.back().opacity != 1.0f ? colorModulateOpacity(paint->getColor(), m_stack.back().opacity) : paint->getColor();
         if (paint->getIsStroked())
         {
             p.stroke = 1;
@@ -104,7 +110,6 @@ public:
     {
         refuse("drawImageMesh");
     }
-    void modulateOpacity(float) override { refuse("modulateOpacity"); }
 
     // The first call this renderer cannot express, or nullptr.
     const char* refusedCall() const { return m_refused.empty() ? nullptr : m_refused.c_str(); }
@@ -142,7 +147,12 @@ private:
     RenderTargetCUDA* m_target;
     LoadAction m_loadAction;
     ColorInt m_clearColor;
-    std::vector<Mat2D> m_stack{Mat2D()};
+    struct State
+    {
+        Mat2D matrix;
+        float opacity = 1.0f;
+    };
+    std::vector<State> m_stack{State()};
     std::vector<Vec2D> m_points;
     std::vector<uint8_t> m_verbs;
     std::vector<rivecuda_path> m_paths;
