@@ -322,7 +322,9 @@ typedef struct rivecuda_path
     uint32_t cap;       /* rive::StrokeCap: butt 0, round 1, square 2 */
     float polar_segments_per_radian;
     float matrix_max_scale;
-    uint32_t reserved0;
+    uint32_t blend_mode; /* gpu::ConvertBlendModeToPLSBlendMode(paint blend mode) (gpu.cpp:717): 0 = srcOver; a call with
+                          * any other mode must flush with RIVECUDA_FEATURE_ADVANCED_BLEND on the batch, as the
+                          * reference's batches do (DrawContents::advancedBlend) */
 } rivecuda_path;
 
 /* What the host needs to fill in the FlushDescriptor / the one midpointFanPatches batch. */
@@ -337,7 +339,7 @@ typedef struct rivecuda_front_end_result
     uint32_t reserved0;
 } rivecuda_front_end_result;
 
-/* Device-side replacement, for non-feathered solid-colour nonZero / evenOdd fills and strokes, of the
+/* Device-side replacement, for non-feathered solid-colour nonZero / evenOdd fills and strokes (any blend mode), of the
  * per-path CPU work the reference does before a flush: PathDraw::initForMidpointFan
  * (renderer/src/draw.cpp:768-1392; Wang's-formula segment counts, contour padding),
  * LogicalFlush::allocateMidpointFanTessVertices (render_context.cpp:3019; prefix-summed span

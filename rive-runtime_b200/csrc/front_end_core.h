@@ -846,7 +846,8 @@ FE_HD void write_path_records(const rivecuda_path& path, uint32_t pathID, const 
     // PaintData: SOLID_COLOR_PAINT_TYPE | fill-rule flag; colour swizzled ARGB -> RGBA bytes.
     const uint32_t argb = path.color;
     const uint32_t rgba = ((argb >> 16) & 0xffu) | (argb & 0xff00u) | ((argb & 0xffu) << 16) | (argb & 0xff000000u);
-    out.paintData[static_cast<size_t>(pathID) * 2 + 0] = kPaintTypeSolidColor | (isStroke ? 0u : path.fill_rule == 1u ? kPaintFlagEvenOddFill : kPaintFlagNonZeroFill);
+    out.paintData[static_cast<size_t>(pathID) * 2 + 0] =
+        kPaintTypeSolidColor | ((path.blend_mode & 0xfu) << 4) | (isStroke ? 0u : path.fill_rule == 1u ? kPaintFlagEvenOddFill : kPaintFlagNonZeroFill); // PaintData::set (gpu.cpp:879-939)
     out.paintData[static_cast<size_t>(pathID) * 2 + 1] = rgba;
     uint32_t aux[16] = {};
     store_words16(out.paintAux + static_cast<size_t>(pathID) * 32 + 16, aux);

@@ -17,7 +17,7 @@ class Path(ctypes.Structure):
                 ("fill_rule", ctypes.c_uint32), ("matrix", ctypes.c_float * 6), ("color", ctypes.c_uint32),
                 ("stroke", ctypes.c_uint32), ("stroke_radius", ctypes.c_float), ("join", ctypes.c_uint32),
                 ("cap", ctypes.c_uint32), ("polar_segments_per_radian", ctypes.c_float),
-                ("matrix_max_scale", ctypes.c_float), ("reserved0", ctypes.c_uint32)]
+                ("matrix_max_scale", ctypes.c_float), ("blend_mode", ctypes.c_uint32)]
 
 
 class FrontEndResult(ctypes.Structure):
@@ -42,7 +42,7 @@ class PathDump:
 PATH_DTYPE = np.dtype([("first_verb", "<u4"), ("verb_count", "<u4"), ("first_point", "<u4"), ("fill_rule", "<u4"),
                        ("matrix", "<f4", (6,)), ("color", "<u4"), ("stroke", "<u4"), ("stroke_radius", "<f4"),
                        ("join", "<u4"), ("cap", "<u4"), ("polar_segments_per_radian", "<f4"),
-                       ("matrix_max_scale", "<f4"), ("reserved0", "<u4")])
+                       ("matrix_max_scale", "<f4"), ("blend_mode", "<u4")])
 assert PATH_DTYPE.itemsize == 72
 
 

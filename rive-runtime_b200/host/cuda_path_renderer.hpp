@@ -12,7 +12,7 @@
  * (rive_renderer.cpp:121-154): empty paths and strokes with !(thickness > 0) are skipped.
  * Per stroked path the two scalars PathDraw computes with libm are computed here the same way
  * (draw.cpp:603-607, 776-813), and a modulated opacity goes into the colour as PathDraw puts it
- * there (draw.cpp:727-737). Anything else -- clips, gradients, images, feathers, blend modes --
+ * there (draw.cpp:727-737); blend modes travel in the paint record. Anything else -- clips, gradients, images, feathers --
  * is not handled by the device front end: the renderer records the first such call
  * and flush() refuses the frame, so the caller can draw it with RiveRenderer (no silent fallback).
  */
@@ -60,10 +60,10 @@ public:
         const RawPath& raw = path->getRawPath();
         if (raw.empty() || (paint->getIsStroked() && !(paint->getThickness() > 0)) || !(paint->getFeather() >= 0))
             return;
-        if (paint->getFeather() != 0 || paint->getType() != PaintType::solidColor || paint->getBlendMode() != BlendMode::srcOver ||
-            paint->getImageTexture() != nullptr || (!paint->getIsStroked() && path->getFillRule() == FillRule::clockwise))
+        if (paint->getFeather() != 0 || paint->getType() != PaintType::solidColor || paint->getImageTexture() != nullptr ||
+            (!paint->getIsStroked() && path->getFillRule() == FillRule::clockwise))
         {
-            refuse("drawPath with a feather / gradient / image / blend mode / clockwise fill");
+            refuse("drawPath with a feather / gradient / image / clockwise fill");
             return;
         }
         const Mat2D& m = m_stack.back().matrix;
@@ -75,6 +75,7 @@ public:
         for (int i = 0; i < 6; ++i)
             p.matrix[i] = m[i];
         // PathDraw applies the modulated opacity to a solid colour (draw.cpp:727-737).
+        p.blend_mode = ConvertBlendModeToPLSBlendMode(paint->getBlendMode()); // PaintData::set (gpu.cpp:889)
         p.color = m_stack.back().opacity != 1.0f ? colorModulateOpacity(paint->getColor(), m_stack.back().opacity) : paint->getColor();
         if (paint->getIsStroked())
         {

@@ -590,6 +590,15 @@ int RenderContextCUDAImpl::flushPlainPathChunk(const PlainPathFrame& frame, size
     batch.index_count_per_instance = kMidpointFanPatchIndexCount;
     batch.base_index = kMidpointFanPatchBaseIndex;
     batch.first_blend_mode = static_cast<uint32_t>(BlendMode::srcOver);
+    // In rasterOrdering mode the reference merges path draws of any blend mode into one batch whose
+    // features are the union of its draws' (LogicalFlush::pushDraw, render_context.cpp:3890-3990;
+    // DrawContents::advancedBlend -> ENABLE_ADVANCED_BLEND, HSL modes -> ENABLE_HSL_BLEND_MODES).
+    for (size_t i = 0; i < pathCount; ++i)
+    {
+        const uint32_t mode = frame.paths[firstPath + i].blend_mode;
+        if (mode != 0u)
+            batch.shader_features |= RIVECUDA_FEATURE_ADVANCED_BLEND | (mode >= 12u ? RIVECUDA_FEATURE_HSL_BLEND_MODES : 0u);
+    }
     const uint32_t batchCount = r.patch_count != 0 ? 1u : 0u;
     return m_abi.flush(m_ctx, &d, &batch, batchCount, nullptr, 0, nullptr, 0);
 }
