@@ -316,7 +316,8 @@ typedef struct rivecuda_path
     uint32_t fill_rule; /* fills: 0 nonZero, 1 evenOdd */
     float matrix[6];
     uint32_t color;     /* rive::ColorInt, 0xAARRGGBB, unpremultiplied */
-    uint32_t stroke;    /* 0 fill, 1 stroke */
+    uint32_t stroke;    /* bit 0: 0 fill, 1 stroke; bits 8-31: 1 + index of the path's clip rectangle in the table of
+                         * rivecuda_front_end_clip_rects (0: not clipped by a rectangle) */
     float stroke_radius; /* RenderPaint thickness * .5, at least FLT_MIN (draw.cpp:603-607) */
     uint32_t join;      /* rive::StrokeJoin: miter 0, round 1, bevel 2 */
     uint32_t cap;       /* rive::StrokeCap: butt 0, round 1, square 2 */
@@ -326,6 +327,18 @@ typedef struct rivecuda_path
                           * any other mode must flush with RIVECUDA_FEATURE_ADVANCED_BLEND on the batch, as the
                           * reference's batches do (DrawContents::advancedBlend) */
 } rivecuda_path;
+
+/* A clip rectangle (RiveRenderer::clipRectImpl, rive_renderer.cpp:268-322) as a draw carries it
+ * (Draw::setClipRect, draw.hpp:103-110): the matrix PaintAuxData::set stores for it with its
+ * inverse fwidth (gpu.cpp:1044-1054), computed by the host with the reference's own
+ * gpu::ClipRectInverseMatrix, and the pixel bounds every draw under it is culled against
+ * (RiveRenderer::applyClip, rive_renderer.cpp:636-646). */
+typedef struct rivecuda_clip_rect
+{
+    float inverse_matrix[6];
+    float inverse_fwidth[2];
+    int32_t pixel_bounds[4]; /* RenderState::overallClipPixelBounds: left, top, right, bottom */
+} rivecuda_clip_rect;
 
 /* What the host needs to fill in the FlushDescriptor / the one midpointFanPatches batch. */
 typedef struct rivecuda_front_end_result
@@ -359,6 +372,8 @@ typedef struct rivecuda_front_end_result
  * (RenderContext::LogicalFlush::pushDraws, render_context.cpp:528-536): the caller splits the
  * draw list, as the reference starts a new logical flush. */
 #define RIVECUDA_STATUS_EXCEEDS_FLUSH 0x10002 /* outside the cudaError_t range other failures return */
+/* The clip rectangles the paths of the next rivecuda_front_end_paths() call refer to (copied). */
+int rivecuda_front_end_clip_rects(rivecuda_ctx* ctx, const rivecuda_clip_rect* rects, uint32_t count);
 int rivecuda_front_end_paths(rivecuda_ctx* ctx,
                              const float* points_xy,
                              uint32_t point_count,

@@ -393,7 +393,7 @@ FE_HD ContourCtx make_contour_ctx(const rivecuda_path& path, const V2* pts, uint
     ctx.verbs = verbs;
     ctx.pointCount = pointCount;
     ctx.verbCount = verbCount;
-    ctx.isStroke = path.stroke != 0;
+    ctx.isStroke = (path.stroke & 1u) != 0u;
     // A contour's curves come first; only a close can follow them (RawPath re-opens with a move).
     ctx.closed = !ctx.isStroke || (verbCount != 0 && verbs[verbCount - 1] == kVerbClose);
     ctx.empty = verbCount == 0 || !verb_draws(verbs[0]);
@@ -685,9 +685,9 @@ FE_HD Box map_bounding_box(const float* m, const V2* pts, uint32_t n)
 
 // PathDraw::Make's frame cull (draw.cpp:439-509; RenderContext::isOutsideCurrentFrame,
 // render_context.cpp:445-454): the mapped bounds, outset for strokes, rounded out to pixels.
-FE_HD bool is_outside_frame(const rivecuda_path& path, Box box, uint32_t frameWidth, uint32_t frameHeight)
+FE_HD bool is_outside_frame(const rivecuda_path& path, Box box, uint32_t frameWidth, uint32_t frameHeight, const rivecuda_clip_rect* clipRects = nullptr)
 {
-    if (path.stroke != 0)
+    if ((path.stroke & 1u) != 0u)
     {
         float outset = path.stroke_radius;
         if (path.join == kJoinMiter)
@@ -699,14 +699,30 @@ FE_HD bool is_outside_frame(const rivecuda_path& path, Box box, uint32_t frameWi
         const float dx = (o.r - o.l) + 1.f, dy = (o.b - o.t) + 1.f;
         box = {box.l + -dx, box.t + -dy, box.r - -dx, box.b - -dy};
     }
-    const int32_t l = static_cast<int32_t>(floorf(box.l)), t = static_cast<int32_t>(floorf(box.t));
-    const int32_t r = static_cast<int32_t>(ceilf(box.r)), b = static_cast<int32_t>(ceilf(box.b));
-    return l >= static_cast<int32_t>(frameWidth) || t >= static_cast<int32_t>(frameHeight) || r <= 0 || b <= 0 || l >= r || t >= b;
+    int32_t l = static_cast<int32_t>(floorf(box.l)), t = static_cast<int32_t>(floorf(box.t));
+    int32_t r = static_cast<int32_t>(ceilf(box.r)), b = static_cast<int32_t>(ceilf(box.b));
+    const int32_t w = static_cast<int32_t>(frameWidth), h = static_cast<int32_t>(frameHeight);
+    if (l >= w || t >= h || r <= 0 || b <= 0 || l >= r || t >= b)
+        return true;
+    // Under a clip rectangle: the draw's bounds intersected with the clip's pixel bounds must be
+    // non-empty and inside the frame too (RiveRenderer::applyClip, rive_renderer.cpp:636-646).
+    const uint32_t clipIndex = path.stroke >> 8;
+    if (clipIndex != 0u && clipRects != nullptr)
+    {
+        const int32_t* cb = clipRects[clipIndex - 1u].pixel_bounds;
+        l = l > cb[0] ? l : cb[0];
+        t = t > cb[1] ? t : cb[1];
+        r = r < cb[2] ? r : cb[2];
+        b = b < cb[3] ? b : cb[3];
+        if (l >= w || t >= h || r <= 0 || b <= 0 || l >= r || t >= b)
+            return true;
+    }
+    return false;
 }
 
-FE_HD bool is_outside_frame(const rivecuda_path& path, const V2* pts, uint32_t pointCount, uint32_t frameWidth, uint32_t frameHeight)
+FE_HD bool is_outside_frame(const rivecuda_path& path, const V2* pts, uint32_t pointCount, uint32_t frameWidth, uint32_t frameHeight, const rivecuda_clip_rect* clipRects = nullptr)
 {
-    return is_outside_frame(path, map_bounding_box(path.matrix, pts, pointCount), frameWidth, frameHeight);
+    return is_outside_frame(path, map_bounding_box(path.matrix, pts, pointCount), frameWidth, frameHeight, clipRects);
 }
 
 FE_HD uint32_t path_point_count(const rivecuda_path& path, const uint8_t* verbs)
@@ -722,17 +738,17 @@ FE_HD uint32_t path_point_count(const rivecuda_path& path, const uint8_t* verbs)
 
 // Pass 1 (draw.cpp:1167-1392): vertices per contour padded to the patch span, summed per path.
 // Paths outside the frame (when a frame size is given) count nothing, as PathDraw::Make drops them.
-FE_HD PathTotals count_path(const rivecuda_path& path, const V2* points, const uint8_t* verbs, uint32_t frameWidth, uint32_t frameHeight)
+FE_HD PathTotals count_path(const rivecuda_path& path, const V2* points, const uint8_t* verbs, uint32_t frameWidth, uint32_t frameHeight, const rivecuda_clip_rect* clipRects = nullptr)
 {
     uint32_t vertices = 0, contours = 0;
-    if (frameWidth != 0u && is_outside_frame(path, points + path.first_point, path_point_count(path, verbs), frameWidth, frameHeight))
+    if (frameWidth != 0u && is_outside_frame(path, points + path.first_point, path_point_count(path, verbs), frameWidth, frameHeight, clipRects))
         return {0u, 0u, 0u, 0u};
     for_each_contour(path, points, verbs, [&](const V2* pts, uint32_t n, const uint8_t* vb, uint32_t nv) {
         vertices += pad_to_patch(contour_vertices(path, pts, n, vb, nv));
         ++contours;
     });
     PathTotals t;
-    t.tessVertices = path.stroke != 0 ? vertices : vertices * 2u; // draw.cpp:1387-1390
+    t.tessVertices = (path.stroke & 1u) != 0u ? vertices : vertices * 2u; // draw.cpp:1387-1390
     t.contours = vertices != 0u ? contours : 0u;
     t.paths = vertices != 0u ? 1u : 0u;
     t.spans = 0u;
@@ -747,6 +763,7 @@ struct FrontEndOut
     uint32_t* pathData;  // PathData, 16 words
     uint32_t* paintData; // PaintData, 2 words
     uint32_t* paintAux;  // PaintAuxData, 32 words
+    const rivecuda_clip_rect* clipRects = nullptr; // the table paths' clip indices refer to
     uint32_t spanBase;   // spans [0, spanBase) are the flush's padding spans
 };
 
@@ -832,12 +849,12 @@ template <bool EMIT> struct PlaceSink
     }
 };
 
-constexpr uint32_t kPaintTypeSolidColor = 1, kPaintFlagNonZeroFill = 0x100, kPaintFlagEvenOddFill = 0x200; // constants.glsl
+constexpr uint32_t kPaintTypeSolidColor = 1, kPaintFlagNonZeroFill = 0x100, kPaintFlagEvenOddFill = 0x200, kPaintFlagHasClipRect = 0x400; // constants.glsl
 
 // pushPath: PathData / PaintData / PaintAuxData (gpu.cpp:859-1063) for a solid colour.
 FE_HD void write_path_records(const rivecuda_path& path, uint32_t pathID, const FrontEndOut& out)
 {
-    const bool isStroke = path.stroke != 0;
+    const bool isStroke = (path.stroke & 1u) != 0u;
     uint32_t w[16] = {};
     for (int i = 0; i < 6; ++i)
         w[i] = bits(path.matrix[i]);
@@ -846,12 +863,26 @@ FE_HD void write_path_records(const rivecuda_path& path, uint32_t pathID, const 
     // PaintData: SOLID_COLOR_PAINT_TYPE | fill-rule flag; colour swizzled ARGB -> RGBA bytes.
     const uint32_t argb = path.color;
     const uint32_t rgba = ((argb >> 16) & 0xffu) | (argb & 0xff00u) | ((argb & 0xffu) << 16) | (argb & 0xff000000u);
+    const uint32_t clipIndex = path.stroke >> 8;
+    const rivecuda_clip_rect* clip = clipIndex != 0u && out.clipRects != nullptr ? out.clipRects + (clipIndex - 1u) : nullptr;
     out.paintData[static_cast<size_t>(pathID) * 2 + 0] =
-        kPaintTypeSolidColor | ((path.blend_mode & 0xfu) << 4) | (isStroke ? 0u : path.fill_rule == 1u ? kPaintFlagEvenOddFill : kPaintFlagNonZeroFill); // PaintData::set (gpu.cpp:879-939)
+        kPaintTypeSolidColor | ((path.blend_mode & 0xfu) << 4) | (isStroke ? 0u : path.fill_rule == 1u ? kPaintFlagEvenOddFill : kPaintFlagNonZeroFill) |
+        (clip != nullptr ? kPaintFlagHasClipRect : 0u); // PaintData::set (gpu.cpp:879-939)
     out.paintData[static_cast<size_t>(pathID) * 2 + 1] = rgba;
     uint32_t aux[16] = {};
     store_words16(out.paintAux + static_cast<size_t>(pathID) * 32 + 16, aux);
-    aux[12] = aux[13] = bits(1.f); // ClipRectInverseMatrix::WideOpen translate; inverseFwidth 0
+    if (clip != nullptr)
+    {
+        // PaintAuxData::m_clipRectInverseMatrix, m_inverseFwidth (gpu.cpp:1044-1054)
+        for (int i = 0; i < 6; ++i)
+            aux[8 + i] = bits(clip->inverse_matrix[i]);
+        aux[14] = bits(clip->inverse_fwidth[0]);
+        aux[15] = bits(clip->inverse_fwidth[1]);
+    }
+    else
+    {
+        aux[12] = aux[13] = bits(1.f); // ClipRectInverseMatrix::WideOpen translate; inverseFwidth 0
+    }
     store_words16(out.paintAux + static_cast<size_t>(pathID) * 32, aux);
 }
 
@@ -862,7 +893,7 @@ FE_HD uint32_t place_path(const rivecuda_path& path, const V2* points, const uin
 {
     if (ownTessVertices == 0u)
         return 0u;
-    const bool isStroke = path.stroke != 0;
+    const bool isStroke = (path.stroke & 1u) != 0u;
     PlaceSink<EMIT> sink;
     sink.out = out;
     sink.doubleSided = !isStroke;

@@ -124,7 +124,7 @@ __device__ __forceinline__ uint32_t item_vertices(const fe::ContourCtx& ctx, uin
 
 // Mat2D::mapBoundingBox over the path's points with the lanes striding the points: min / max
 // skip NaNs, so the partial results are never NaN and combine exactly (fe::map_bounding_box).
-__device__ bool warp_is_outside_frame(const rivecuda_path& path, const V2* __restrict__ pts, uint32_t pointCount, uint32_t frameWidth, uint32_t frameHeight, int lane)
+__device__ bool warp_is_outside_frame(const rivecuda_path& path, const V2* __restrict__ pts, uint32_t pointCount, uint32_t frameWidth, uint32_t frameHeight, int lane, const rivecuda_clip_rect* __restrict__ clipRects)
 {
     const float* m = path.matrix;
     const float inf = __uint_as_float(0x7f800000u);
@@ -160,7 +160,7 @@ __device__ bool warp_is_outside_frame(const rivecuda_path& path, const V2* __res
         box = {0.f, 0.f, 0.f, 0.f};
     else
         box = {l + m[4], t + m[5], r + m[4], b + m[5]};
-    return fe::is_outside_frame(path, box, frameWidth, frameHeight);
+    return fe::is_outside_frame(path, box, frameWidth, frameHeight, clipRects);
 }
 
 // Pass 1: tessellation vertices / contours per path.
@@ -173,7 +173,9 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) front_end_count_kernel(co
                                                                                uint32_t pointCount,
                                                                                uint32_t* __restrict__ badPathFlag,
                                                                                PathTotals* __restrict__ totals,
-                                                                               uint32_t* __restrict__ ownTessVertices)
+                                                                               uint32_t* __restrict__ ownTessVertices,
+                                                                               const rivecuda_clip_rect* __restrict__ clipRects,
+                                                                               uint32_t clipRectCount)
 {
     const int lane = threadIdx.x & 31;
     const uint32_t i = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
@@ -199,9 +201,16 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) front_end_count_kernel(co
                 atomicOr(badPathFlag, 1u);
             culled = true;
         }
+        else if ((path.stroke >> 8) > clipRectCount)
+        {
+            // A clip rectangle the caller did not pass: touch nothing, report it.
+            if (lane == 0)
+                atomicOr(badPathFlag, 1u);
+            culled = true;
+        }
         else if (frameWidth != 0u)
         {
-            culled = warp_is_outside_frame(path, pt, n, frameWidth, frameHeight, lane);
+            culled = warp_is_outside_frame(path, pt, n, frameWidth, frameHeight, lane, clipRects);
         }
     }
     if (!culled)
@@ -224,7 +233,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) front_end_count_kernel(co
     if (lane == 0)
     {
         PathTotals t;
-        t.tessVertices = path.stroke != 0 ? vertices : vertices * 2u; // draw.cpp:1387-1390
+        t.tessVertices = (path.stroke & 1u) != 0u ? vertices : vertices * 2u; // draw.cpp:1387-1390
         t.contours = vertices != 0u ? contours : 0u;
         t.paths = vertices != 0u ? 1u : 0u;
         t.spans = 0u;
@@ -375,7 +384,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) front_end_place_kernel(co
     }
     const rivecuda_path path = paths[i];
     const PathTotals prefix = totals[i];
-    const bool isStroke = path.stroke != 0;
+    const bool isStroke = (path.stroke & 1u) != 0u;
     const V2* pt = points + path.first_point;
     const uint8_t* vb = verbs + path.first_verb;
     const uint32_t pathID = prefix.paths + 1u; // 1-based; 0 is the flush's reserved record
@@ -499,6 +508,14 @@ __global__ void front_end_padding_kernel(uint32_t* __restrict__ spans, const uin
 
 using namespace rivecuda;
 
+int rivecuda_front_end_clip_rects(rivecuda_ctx* ctx, const rivecuda_clip_rect* rects, uint32_t count)
+{
+    if (ctx == nullptr || (count != 0 && rects == nullptr) || count >= (1u << 24) - 1u)
+        return set_error("rivecuda_front_end_clip_rects: bad arguments");
+    ctx->frontEndClipRects.assign(rects, rects + count);
+    return 0;
+}
+
 int rivecuda_front_end_paths(rivecuda_ctx* ctx,
                              const float* points_xy,
                              uint32_t point_count,
@@ -533,7 +550,9 @@ int rivecuda_front_end_paths(rivecuda_ctx* ctx,
     const size_t verbOffset = (pointBytes + 15) & ~size_t(15), pathOffset = (verbOffset + verbBytes + 15) & ~size_t(15);
     const size_t totalsOffset = (pathOffset + pathBytes + 15) & ~size_t(15);
     const size_t ownOffset = totalsOffset + static_cast<size_t>(path_count) * sizeof(PathTotals) + 64;
-    if (int s = ctx->frontEnd.reserve(ownOffset + static_cast<size_t>(path_count) * sizeof(uint32_t)))
+    const size_t clipOffset = (ownOffset + static_cast<size_t>(path_count) * sizeof(uint32_t) + 15) & ~size_t(15);
+    const size_t clipBytes = ctx->frontEndClipRects.size() * sizeof(rivecuda_clip_rect);
+    if (int s = ctx->frontEnd.reserve(clipOffset + clipBytes))
         return s;
     uint8_t* base = ctx->frontEnd.as<uint8_t>();
     V2* dPoints = reinterpret_cast<V2*>(base);
@@ -547,6 +566,14 @@ int rivecuda_front_end_paths(rivecuda_ctx* ctx,
         RC_CUDA(cudaMemcpyAsync(dPoints, points_xy, pointBytes, cudaMemcpyHostToDevice, stream));
         RC_CUDA(cudaMemcpyAsync(dVerbs, verbs, verbBytes, cudaMemcpyHostToDevice, stream));
         RC_CUDA(cudaMemcpyAsync(dPaths, paths, pathBytes, cudaMemcpyHostToDevice, stream));
+    }
+    // The clip rectangles of this call (rivecuda_front_end_clip_rects); one call's worth.
+    const rivecuda_clip_rect* dClipRects = nullptr;
+    const uint32_t clipRectCount = static_cast<uint32_t>(ctx->frontEndClipRects.size());
+    if (clipBytes != 0)
+    {
+        RC_CUDA(cudaMemcpyAsync(base + clipOffset, ctx->frontEndClipRects.data(), clipBytes, cudaMemcpyHostToDevice, stream));
+        dClipRects = reinterpret_cast<const rivecuda_clip_rect*>(base + clipOffset);
     }
 
     // The five buffers this front end fills, at the sizes the worst case needs (a stroked cubic
@@ -588,6 +615,7 @@ int rivecuda_front_end_paths(rivecuda_ctx* ctx,
     out.paintData = static_cast<uint32_t*>(dev(RIVECUDA_BUFFER_PAINT));
     out.paintAux = static_cast<uint32_t*>(dev(RIVECUDA_BUFFER_PAINT_AUX));
     out.spanBase = 0;
+    out.clipRects = dClipRects;
     // Record 0 of path / paint / paintAux is the flush's reserved (clear colour) record.
     RC_CUDA(cudaMemsetAsync(out.pathData, 0, 64, stream));
     RC_CUDA(cudaMemsetAsync(out.paintData, 0, 8, stream));
@@ -598,7 +626,7 @@ int rivecuda_front_end_paths(rivecuda_ctx* ctx,
     uint32_t* field = reinterpret_cast<uint32_t*>(dTotals);
     if (path_count != 0)
     {
-        front_end_count_kernel<<<blocks, kWarpsPerBlock * 32, 0, stream>>>(dPaths, path_count, dPoints, dVerbs, frame_width, frame_height, point_count, dSums + 6, dTotals, dOwn);
+        front_end_count_kernel<<<blocks, kWarpsPerBlock * 32, 0, stream>>>(dPaths, path_count, dPoints, dVerbs, frame_width, frame_height, point_count, dSums + 6, dTotals, dOwn, dClipRects, clipRectCount);
         front_end_scan3_kernel<<<1, 1024, 0, stream>>>(reinterpret_cast<uint4*>(dTotals), path_count, dSums);
     }
     else

@@ -12,7 +12,8 @@
  * (rive_renderer.cpp:121-154): empty paths and strokes with !(thickness > 0) are skipped.
  * Per stroked path the two scalars PathDraw computes with libm are computed here the same way
  * (draw.cpp:603-607, 776-813), and a modulated opacity goes into the colour as PathDraw puts it
- * there (draw.cpp:727-737); blend modes travel in the paint record. Anything else -- clips, gradients, images, feathers --
+ * there (draw.cpp:727-737); blend modes travel in the paint record; clip RECTANGLES (clipPath with an
+ * axis-aligned rectangle, nested ones intersected) travel as a table the paths index. Anything else -- clip paths, gradients, images, feathers --
  * is not handled by the device front end: the renderer records the first such call
  * and flush() refuses the frame, so the caller can draw it with RiveRenderer (no silent fallback).
  */
@@ -27,6 +28,7 @@
 #include "rive/shapes/paint/color.hpp"
 #include "rive_render_paint.hpp"
 #include "rive_render_path.hpp"
+#include "rive/renderer/rive_renderer.hpp"
 
 #include <algorithm>
 #include <cfloat>
@@ -66,6 +68,8 @@ public:
             refuse("drawPath with a feather / gradient / image / clockwise fill");
             return;
         }
+        if (m_stack.back().overallClipPixelBounds.empty())
+            return; // rive_renderer.cpp:151
         const Mat2D& m = m_stack.back().matrix;
         rivecuda_path p;
         memset(&p, 0, sizeof(p));
@@ -77,9 +81,10 @@ public:
         // PathDraw applies the modulated opacity to a solid colour (draw.cpp:727-737).
         p.blend_mode = ConvertBlendModeToPLSBlendMode(paint->getBlendMode()); // PaintData::set (gpu.cpp:889)
         p.color = m_stack.back().opacity != 1.0f ? colorModulateOpacity(paint->getColor(), m_stack.back().opacity) : paint->getColor();
+        p.stroke = m_stack.back().clipRectIndex << 8; // 0: no clip rectangle
         if (paint->getIsStroked())
         {
-            p.stroke = 1;
+            p.stroke |= 1;
             p.stroke_radius = fmaxf(paint->getThickness() * .5f, FLT_MIN); // draw.cpp:603-607
             p.join = static_cast<uint32_t>(paint->getJoin());
             p.cap = static_cast<uint32_t>(paint->getCap());
@@ -97,7 +102,82 @@ public:
         m_paths.push_back(p);
     }
 
-    void clipPath(RenderPath*) override { refuse("clipPath"); }
+    // Clip rectangles (the ENABLE_CLIP_RECT feature): what RiveRenderer::clipPath / clipRectImpl do
+    // with an axis-aligned rectangle (rive_renderer.cpp:199-322). Any other clip is a clip PATH
+    // (stencil-like updates of the clip plane between the draws), which this renderer refuses.
+    void clipPath(RenderPath* renderPath) override
+    {
+        auto* path = static_cast<RiveRenderPath*>(renderPath);
+        State& state = m_stack.back();
+        if (state.overallClipPixelBounds.empty())
+            return;
+        if (path->getRawPath().empty())
+        {
+            state.overallClipPixelBounds = {};
+            return;
+        }
+        AABB rect;
+        if (!RiveRenderer::IsAABB(path->getRawPath(), &rect))
+        {
+            refuse("clipPath with something other than an axis-aligned rectangle");
+            return;
+        }
+        if (rect.isEmptyOrNaN())
+        {
+            state.overallClipPixelBounds = {};
+            return;
+        }
+        if (state.hasClipRect && !(state.matrix == state.clipRectMatrix))
+        {
+            // A second rectangle only intersects with the first in the first one's space, and
+            // only if it is still a rectangle there (transform_rect_to_new_space).
+            Mat2D currentToNew;
+            if (!state.clipRectMatrix.invert(&currentToNew))
+            {
+                refuse("clipPath: nested clip rectangle under a singular matrix");
+                return;
+            }
+            currentToNew = currentToNew * state.matrix;
+            const float maxSkew = fmaxf(fabsf(currentToNew.xy()), fabsf(currentToNew.yx()));
+            const float maxScale = fmaxf(fabsf(currentToNew.xx()), fabsf(currentToNew.yy()));
+            if (maxSkew > math::EPSILON && maxScale > math::EPSILON)
+            {
+                refuse("clipPath: nested clip rectangle that is not axis-aligned with the first");
+                return;
+            }
+            Vec2D pts[2] = {{rect.left(), rect.top()}, {rect.right(), rect.bottom()}};
+            currentToNew.mapPoints(pts, pts, 2);
+            rect = {std::min(pts[0].x, pts[1].x), std::min(pts[0].y, pts[1].y), std::max(pts[0].x, pts[1].x), std::max(pts[0].y, pts[1].y)};
+        }
+        if (!state.hasClipRect)
+        {
+            state.clipRect = rect;
+            state.clipRectMatrix = state.matrix;
+            state.hasClipRect = true;
+        }
+        else
+        {
+            state.clipRect = {std::max(state.clipRect.left(), rect.left()), std::max(state.clipRect.top(), rect.top()),
+                              std::min(state.clipRect.right(), rect.right()), std::min(state.clipRect.bottom(), rect.bottom())};
+        }
+        const IAABB clipRectPixelBounds = state.clipRectMatrix.mapBoundingBox(state.clipRect).roundOut();
+        state.overallClipPixelBounds = state.overallClipPixelBounds.intersect(clipRectPixelBounds);
+        // The record every draw under this state carries (Draw::setClipRect + PaintAuxData::set).
+        const ClipRectInverseMatrix inverse(state.clipRectMatrix, state.clipRect);
+        const Mat2D& m = inverse.inverseMatrix();
+        rivecuda_clip_rect record;
+        for (int i = 0; i < 6; ++i)
+            record.inverse_matrix[i] = m[i];
+        record.inverse_fwidth[0] = -1.f / (fabsf(m.xx()) + fabsf(m.xy())); // gpu.cpp:1052-1053
+        record.inverse_fwidth[1] = -1.f / (fabsf(m.yx()) + fabsf(m.yy()));
+        // (The bounds only change in this function, so they are the state's at every draw under it.)
+        record.pixel_bounds[0] = state.overallClipPixelBounds.left;
+        record.pixel_bounds[1] = state.overallClipPixelBounds.top;
+        record.pixel_bounds[2] = state.overallClipPixelBounds.right;
+        record.pixel_bounds[3] = state.overallClipPixelBounds.bottom;
+        m_clipRects.push_back(record);
+        state.clipRectIndex = static_cast<uint32_t>(m_clipRects.size());
+    }
     void drawImage(const RenderImage*, ImageSampler, BlendMode, float) override { refuse("drawImage"); }
     void drawImageMesh(const RenderImage*,
                        ImageSampler,
@@ -134,6 +214,8 @@ public:
         frame.verbCount = m_verbs.size();
         frame.paths = m_paths.data();
         frame.pathCount = m_paths.size();
+        frame.clipRects = m_clipRects.data();
+        frame.clipRectCount = m_clipRects.size();
         return m_impl->flushPlainPaths(frame);
     }
 
@@ -152,11 +234,18 @@ private:
     {
         Mat2D matrix;
         float opacity = 1.0f;
+        // RiveRenderer::RenderState's clip-rectangle members (rive_renderer.hpp:100-110).
+        IAABB overallClipPixelBounds = IAABB::makeMaximal();
+        bool hasClipRect = false;
+        AABB clipRect;
+        Mat2D clipRectMatrix;
+        uint32_t clipRectIndex = 0; // 1 + index into m_clipRects of the state's rectangle
     };
     std::vector<State> m_stack{State()};
     std::vector<Vec2D> m_points;
     std::vector<uint8_t> m_verbs;
     std::vector<rivecuda_path> m_paths;
+    std::vector<rivecuda_clip_rect> m_clipRects;
     std::string m_refused;
 };
 } // namespace rive::gpu

@@ -523,6 +523,8 @@ int RenderContextCUDAImpl::flushPlainPathChunk(const PlainPathFrame& frame, size
     RenderTargetCUDA* target = frame.renderTarget;
     rivecuda_front_end_result& r = *needed;
     memset(&r, 0, sizeof(r));
+    if (int status = m_abi.front_end_clip_rects(m_ctx, frame.clipRects, static_cast<uint32_t>(frame.clipRectCount)))
+        return status;
     if (int status = m_abi.front_end_paths(m_ctx,
                                            frame.pointCount != 0 ? &frame.points->x : nullptr,
                                            static_cast<uint32_t>(frame.pointCount),
@@ -598,6 +600,8 @@ int RenderContextCUDAImpl::flushPlainPathChunk(const PlainPathFrame& frame, size
         const uint32_t mode = frame.paths[firstPath + i].blend_mode;
         if (mode != 0u)
             batch.shader_features |= RIVECUDA_FEATURE_ADVANCED_BLEND | (mode >= 12u ? RIVECUDA_FEATURE_HSL_BLEND_MODES : 0u);
+        if ((frame.paths[firstPath + i].stroke >> 8) != 0u)
+            batch.shader_features |= RIVECUDA_FEATURE_CLIP_RECT; // DrawContents::clipRect... -> ENABLE_CLIP_RECT
     }
     const uint32_t batchCount = r.patch_count != 0 ? 1u : 0u;
     return m_abi.flush(m_ctx, &d, &batch, batchCount, nullptr, 0, nullptr, 0);

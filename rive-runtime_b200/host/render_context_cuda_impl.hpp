@@ -156,6 +156,9 @@ public:
         size_t verbCount = 0;
         const rivecuda_path* paths = nullptr;
         size_t pathCount = 0;
+        // The clip rectangles the paths' `stroke >> 8` index (1-based; rivecuda.h).
+        const rivecuda_clip_rect* clipRects = nullptr;
+        size_t clipRectCount = 0;
     };
     bool flushPlainPaths(const PlainPathFrame&);
 
