@@ -153,7 +153,7 @@ void bind_path_pipeline(const refcpu_flush* f, const rivecuda_draw_batch& batch)
     path::gaussianIntegralTexture.width = 512;
     path::gradTexture.texels = reinterpret_cast<const uint32_t*>(f->grad_texture);
     path::gradTexture.width = 512;
-    path::gradTexture.height = static_cast<int>(f->desc->grad_data_height > 0 ? f->desc->grad_data_height : 1);
+    path::gradTexture.height = static_cast<int>(f->grad_rows > 0 ? f->grad_rows : 1); // allocated height (render_context.cpp:1442-1443)
     const uint32_t features = batch.shader_features;
     path::EnableClipping = features & RIVECUDA_FEATURE_CLIPPING;
     path::EnableClipRect = features & RIVECUDA_FEATURE_CLIP_RECT;

@@ -161,6 +161,7 @@ def replay(records: List[T.Record], threads: int = 1, keep_intermediates: bool =
     tables = None
     keepalive = []
     atlas_size = (0, 0)
+    grad_alloc_rows = 0  # height of the last resizeGradientTexture(): what gradTextureY is normalised by
     out = ReplayResult()
     for r in records:
         if r.tag == T.STATIC_TABLES:
@@ -174,6 +175,8 @@ def replay(records: List[T.Record], threads: int = 1, keep_intermediates: bool =
             buffers[r.fields["kind"]] = np.ascontiguousarray(r.data)
         elif r.tag == T.RESIZE_ATLAS:
             atlas_size = (r.fields["width"], r.fields["height"])
+        elif r.tag == T.RESIZE_GRADIENT:
+            grad_alloc_rows = r.fields["height"]
         elif r.tag == T.TARGET_CREATE:
             targets[r.fields["id"]] = np.zeros((r.fields["height"], r.fields["width"], 4), dtype=np.uint8)
         elif r.tag == T.TARGET_WRITE:
@@ -221,7 +224,7 @@ def replay(records: List[T.Record], threads: int = 1, keep_intermediates: bool =
             fills = (T.AtlasBatch * max(len(fr.atlas_fills), 1))(*fr.atlas_fills)
             strokes = (T.AtlasBatch * max(len(fr.atlas_strokes), 1))(*fr.atlas_strokes)
             fo = FlushOutputs(d)
-            fo.grad = np.zeros((max(d.grad_data_height, 1), 512, 4), dtype=np.uint8)
+            fo.grad = np.zeros((max(grad_alloc_rows, d.grad_data_height, 1), 512, 4), dtype=np.uint8)
             fo.tess = np.zeros((max(d.tess_data_height, 1) * 2048, 4), dtype=np.uint32)
             aw = max(atlas_size[0], d.feather_atlas_texture_width, 1)
             ah = max(atlas_size[1], d.feather_atlas_texture_height, 1)

@@ -1051,11 +1051,15 @@ inline float4 lerp4(float4 a, float4 b, float t)
 // TEXTURE_SAMPLE_LOD(@gradTexture, gradSampler, uv, 0): linear, clamp to edge.
 float4 sample_grad_texture(const Context& c, float u, float v)
 {
-    float x = u * 512.f - .5f, y = v * static_cast<float>(c.desc->grad_data_height) - .5f;
+    // The sampler normalises over the ALLOCATED texture height: PaintData::set() writes
+    // gradTextureY = (row + .5) * inverseHeight with inverseHeight = 1 / gradTextureHeight, the
+    // height of the last resizeGradientTexture() (render_context.cpp:1442-1443), which is
+    // usually larger than this flush's gradDataHeight (125% growth, render_context.cpp:879).
+    float x = u * 512.f - .5f, y = v * static_cast<float>(c.gradRows) - .5f;
     float fx = floorf(x), fy = floorf(y);
     float tx = x - fx, ty = y - fy;
     int ix = static_cast<int>(clampf(fx, -1.f, 512.f)), iy = static_cast<int>(clampf(fy, -1.f, 65536.f));
-    uint32_t h = std::max<uint32_t>(c.desc->grad_data_height, 1);
+    uint32_t h = std::max<uint32_t>(c.gradRows, 1);
     float4 c00 = fetch_rgba8(c.gradTexture, 512, h, ix, iy), c10 = fetch_rgba8(c.gradTexture, 512, h, ix + 1, iy);
     float4 c01 = fetch_rgba8(c.gradTexture, 512, h, ix, iy + 1), c11 = fetch_rgba8(c.gradTexture, 512, h, ix + 1, iy + 1);
     return lerp4(lerp4(c00, c10, tx), lerp4(c01, c11, tx), ty);

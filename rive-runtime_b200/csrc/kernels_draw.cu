@@ -1579,7 +1579,9 @@ int launch_draw_list(rivecuda_ctx* ctx, const rivecuda_flush_desc& desc, const r
     P.patchDedup = ctx->patchDedup;
     P.featherLUT = ctx->featherLUT;
     P.gradTexture = ctx->gradTexture;
-    P.gradHeight = std::max<uint32_t>(desc.grad_data_height, 1u);
+    // gradTextureY is normalised by the ALLOCATED height (render_context.cpp:1442-1443), not by
+    // this flush's gradDataHeight.
+    P.gradHeight = std::max<uint32_t>(ctx->gradHeight, 1u);
     P.atlas = ctx->atlas;
     P.atlasWidth = std::max<uint32_t>(ctx->atlasWidth, 1u);
     P.atlasHeight = std::max<uint32_t>(ctx->atlasHeight, 1u);

@@ -475,8 +475,11 @@ int launch_color_ramps(rivecuda_ctx* ctx, const rivecuda_flush_desc& desc, const
 {
     if (gradSpans == nullptr || ctx->gradTexture == nullptr)
         return set_error("rivecuda_flush: gradient spans present but no span buffer / gradient texture");
-    // The reference's render pass clears the rows it is about to draw.
-    RC_CUDA(cudaMemsetAsync(ctx->gradTexture, 0, static_cast<size_t>(desc.grad_data_height) * kGradWidth * 4, ctx->stream));
+    // The reference's render pass clears the rows it is about to draw. One more row is cleared
+    // here: the bilinear footprint of the last ramp can touch it with a rounding-sized weight, and
+    // the oracle starts every flush from a zeroed texture.
+    const uint32_t clearRows = std::min<uint32_t>(desc.grad_data_height + 1, ctx->gradHeight);
+    RC_CUDA(cudaMemsetAsync(ctx->gradTexture, 0, static_cast<size_t>(clearRows) * kGradWidth * 4, ctx->stream));
     uint32_t warps = desc.grad_span_count;
     uint32_t blocks = min((warps + 3) / 4, static_cast<uint32_t>(ctx->smCount * 8));
     color_ramp_kernel<<<blocks, 128, 0, ctx->stream>>>(static_cast<const GradSpan*>(gradSpans), desc.grad_span_count, ctx->gradTexture, desc.grad_data_height);

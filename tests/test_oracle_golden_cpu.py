@@ -71,6 +71,38 @@ def test_reference_data_invariants(name):
                     assert b.index_count_per_instance == {0: 72, 1: 120, 2: 249}[b.draw_type]
 
 
+@pytest.mark.parametrize("name", ["riv_off_road_car.rvct.xz", "riv_bullet_man.rvct.xz", "lots_of_grads_mixed.rvct.xz",
+                                  "degengrad.rvct.xz", "verycomplexgrad.rvct.xz"])
+def test_gradient_rows_are_normalised_by_the_allocated_texture_height(name):
+    """PaintData::set() writes gradTextureY = (row + .5) / gradTextureHeight with the height of the last
+    resizeGradientTexture() (render_context.cpp:1442-1443, gpu.cpp:911), NOT this flush's
+    gradDataHeight: the recorded paints only land on texel-row centres below gradDataHeight when the
+    sampler (oracle and kernels) scales v by the allocated height."""
+    recs = T.parse(os.path.join(GOLDEN, name))
+    bufs, alloc_rows, seen, differs = {}, 0, 0, False
+    for r in recs:
+        if r.tag == T.BUFFER_UNMAP:
+            bufs[r.fields["kind"]] = r.data
+        elif r.tag == T.RESIZE_GRADIENT:
+            alloc_rows = r.fields["height"]
+        elif r.tag == T.FLUSH:
+            d = r.fields["flush"].desc
+            if d.grad_data_height == 0:
+                continue
+            assert d.grad_data_height <= alloc_rows
+            differs |= d.grad_data_height != alloc_rows
+            paint = np.frombuffer(bufs[2].tobytes(), dtype=np.uint32).reshape(-1, 2)[d.first_paint:d.first_paint + d.path_count + 1]
+            grads = paint[np.isin(paint[:, 0] & 0xf, (2, 3))]  # PaintType::linearGradient / radialGradient
+            v = grads[:, 1].copy().view(np.float32)
+            rows = v * np.float32(alloc_rows) - np.float32(.5)
+            assert np.all(np.abs(rows - np.round(rows)) < 1e-3)
+            assert np.all((np.round(rows) >= 0) & (np.round(rows) < d.grad_data_height))
+            seen += len(grads)
+    assert seen > 0
+    if name.startswith("riv_off_road_car"):
+        assert differs  # the case that tells the two normalisers apart (10 rows allocated, 8 used)
+
+
 @pytest.mark.skipif(not os.path.isdir("/root/reference"), reason="needs the reference tree to re-derive the traces")
 def test_committed_traces_are_what_the_reference_front_end_emits(built, tmp_path):
     """Bit-exact front half: re-run the reference's RiveRenderer/RenderContext
