@@ -313,7 +313,7 @@ typedef struct rivecuda_path
 {
     uint32_t first_verb, verb_count;
     uint32_t first_point;
-    uint32_t fill_rule; /* fills: 0 nonZero, 1 evenOdd */
+    uint32_t fill_rule; /* fills: 0 nonZero, 1 evenOdd, 2 clockwise (its batch carries RIVECUDA_MISC_CLOCKWISE_FILL) */
     float matrix[6];
     uint32_t color;     /* rive::ColorInt, 0xAARRGGBB, unpremultiplied */
     uint32_t stroke;    /* bit 0: 0 fill, 1 stroke; bits 8-31: 1 + index of the path's clip rectangle in the table of
@@ -384,6 +384,13 @@ int rivecuda_front_end_paths(rivecuda_ctx* ctx,
                              uint32_t frame_width,
                              uint32_t frame_height,
                              rivecuda_front_end_result* result);
+/* first_patch[i] = the first midpoint-fan patch (DrawBatch::baseElement) of path i of the last
+ * rivecuda_front_end_paths() call, for i in [0, path_count]; a culled path's equals its
+ * successor's, entry path_count is the end of the last path. A frame whose fills mix clockwise
+ * with nonZero / evenOdd needs it to split the patches into batches the way
+ * LogicalFlush::pushPathDraw does (render_context.cpp:3631-3640: ShaderMiscFlags::clockwiseFill
+ * is per batch). first_patch holds path_count + 1 entries. */
+int rivecuda_front_end_path_patches(rivecuda_ctx* ctx, uint32_t* first_patch, uint32_t path_count);
 
 /* ---- screen-band sharding of one frame over the GPUs of one box --------- */
 

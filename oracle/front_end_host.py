@@ -22,8 +22,8 @@ _LIB_PATH = os.path.join(_HERE, "front_end_host", "libfront_end_host.so")
 
 
 def build(force: bool = False) -> str:
-    if force or not os.path.exists(_LIB_PATH):
-        subprocess.check_call(["make", "-s", "-C", os.path.join(_HERE, "front_end_host")])
+    # make decides (the library depends on csrc/front_end_core.h, which changes with the kernels)
+    subprocess.check_call(["make", "-s", "-C", os.path.join(_HERE, "front_end_host")] + (["-B"] if force else []))
     return _LIB_PATH
 
 

@@ -791,6 +791,7 @@ template <bool EMIT> struct PlaceSink
     FrontEndOut out;
     uint32_t contourID = 0, spanIndex = 0, spanCount = 0;
     uint32_t forwardLoc = 0, mirroredLoc = 0, nextPadding = 0;
+    uint32_t contourFlags = 0; // PathDraw::m_contourFlags: on every span of the path
     bool doubleSided = false;
     // fills: ContourInfo::midpoint = endpointsSum / preChopVerbCount (draw.cpp:945)
     V2 endpointsSum = {0.f, 0.f};
@@ -825,7 +826,7 @@ template <bool EMIT> struct PlaceSink
                 w[12] = static_cast<uint32_t>((x1 << 16) | (x0 & 0xffff));
                 w[13] = static_cast<uint32_t>((rx1 << 16) | (rx0 & 0xffff));
                 w[14] = (joinSegments << 20) | (polar << 10) | parametric;
-                w[15] = contourID | flags;
+                w[15] = contourID | flags | contourFlags;
                 store_words16(out.spans + static_cast<size_t>(out.spanBase + spanIndex + spanCount) * 16, w);
             }
             ++spanCount;
@@ -849,6 +850,19 @@ template <bool EMIT> struct PlaceSink
     }
 };
 
+// Clockwise fills (rivecuda_path::fill_rule 2) under a left-handed matrix are emitted forward first,
+// mirrored copy second, with their coverage negated, so that the intended forward triangles stay
+// clockwise (PathDraw::PathDraw, draw.cpp:657-680: ContourDirections::forwardThenReverse +
+// NEGATE_PATH_FILL_COVERAGE_FLAG); every other fill is reverseThenForward.
+constexpr uint32_t kNegatePathFillCoverageFlag = 1u << 24; // constants.glsl:100
+FE_HD bool is_forward_then_reverse(const rivecuda_path& path)
+{
+    if ((path.stroke & 1u) != 0u || path.fill_rule != 2u)
+        return false;
+    const float det = path.matrix[0] * path.matrix[3] - path.matrix[2] * path.matrix[1];
+    return det < 0.f;
+}
+
 constexpr uint32_t kPaintTypeSolidColor = 1, kPaintFlagNonZeroFill = 0x100, kPaintFlagEvenOddFill = 0x200, kPaintFlagHasClipRect = 0x400; // constants.glsl
 
 // pushPath: PathData / PaintData / PaintAuxData (gpu.cpp:859-1063) for a solid colour.
@@ -866,7 +880,7 @@ FE_HD void write_path_records(const rivecuda_path& path, uint32_t pathID, const 
     const uint32_t clipIndex = path.stroke >> 8;
     const rivecuda_clip_rect* clip = clipIndex != 0u && out.clipRects != nullptr ? out.clipRects + (clipIndex - 1u) : nullptr;
     out.paintData[static_cast<size_t>(pathID) * 2 + 0] =
-        kPaintTypeSolidColor | ((path.blend_mode & 0xfu) << 4) | (isStroke ? 0u : path.fill_rule == 1u ? kPaintFlagEvenOddFill : kPaintFlagNonZeroFill) |
+        kPaintTypeSolidColor | ((path.blend_mode & 0xfu) << 4) | (isStroke || path.fill_rule == 2u ? 0u : path.fill_rule == 1u ? kPaintFlagEvenOddFill : kPaintFlagNonZeroFill) |
         (clip != nullptr ? kPaintFlagHasClipRect : 0u); // PaintData::set (gpu.cpp:879-939)
     out.paintData[static_cast<size_t>(pathID) * 2 + 1] = rgba;
     uint32_t aux[16] = {};
@@ -903,6 +917,13 @@ FE_HD uint32_t place_path(const rivecuda_path& path, const V2* points, const uin
     // The midpoint-fan region starts after one patch of padding (draw.cpp:1899-1947).
     const uint32_t location = kPatchSpan + prefix.tessVertices;
     sink.forwardLoc = sink.mirroredLoc = isStroke ? location : location + ownTessVertices / 2u;
+    if (is_forward_then_reverse(path))
+    {
+        // PathDraw::pushTessellationData (draw.cpp:1945-1968)
+        sink.forwardLoc = location;
+        sink.mirroredLoc = location + ownTessVertices;
+        sink.contourFlags = kNegatePathFillCoverageFlag;
+    }
     for_each_contour(path, points, verbs, [&](const V2* pts, uint32_t n, const uint8_t* vb, uint32_t nv) {
         const uint32_t vertices = contour_vertices(path, pts, n, vb, nv);
         sink.nextPadding = pad_to_patch(vertices) - vertices;

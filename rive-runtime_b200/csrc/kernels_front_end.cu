@@ -392,6 +392,12 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) front_end_place_kernel(co
     // The midpoint-fan region starts after one patch of padding (draw.cpp:1899-1947).
     const uint32_t location = fe::kPatchSpan + prefix.tessVertices;
     uint32_t forwardLoc = isStroke ? location : location + own / 2u, mirroredLoc = forwardLoc;
+    const bool forwardThenReverse = fe::is_forward_then_reverse(path);
+    if (forwardThenReverse)
+    {
+        forwardLoc = location; // PathDraw::pushTessellationData (draw.cpp:1945-1968)
+        mirroredLoc = location + own;
+    }
     uint32_t spanCarry = 0; // spans of this path so far
 
     uint32_t v = warp_find_move(vb, 0, path.verb_count, lane);
@@ -430,6 +436,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) front_end_place_kernel(co
                 sink.out = out;
                 sink.doubleSided = !isStroke;
                 sink.contourID = contourID;
+                sink.contourFlags = forwardThenReverse ? fe::kNegatePathFillCoverageFlag : 0u;
                 sink.spanIndex = prefix.spans + spanCarry + spanOffset;
                 sink.forwardLoc = forwardLoc + offset;
                 sink.mirroredLoc = mirroredLoc - offset;
@@ -671,11 +678,32 @@ int rivecuda_front_end_paths(rivecuda_ctx* ctx,
     result->path_count = sums[2] + 1; // + the reserved record 0
     result->tess_vertex_span_count = out.spanBase + (path_count != 0 ? sums[3] : 0u);
     result->tess_data_height = (sums[5] + kTessWidth - 1) / kTessWidth;
+    ctx->frontEndTotalsOffset = totalsOffset;
+    ctx->frontEndPathCount = path_count;
+    ctx->frontEndTessVertices = sums[0];
     result->first_patch = 1; // after the one patch of padding
     result->patch_count = sums[0] / fe::kPatchSpan;
     for (int kind : {RIVECUDA_BUFFER_PATH, RIVECUDA_BUFFER_PAINT, RIVECUDA_BUFFER_PAINT_AUX, RIVECUDA_BUFFER_CONTOUR, RIVECUDA_BUFFER_TESS_SPAN})
         ctx->rings[kind].submittedBytes = ctx->rings[kind].capacity;
     ctx->uploadsPending = true;
+    return 0;
+}
+
+int rivecuda_front_end_path_patches(rivecuda_ctx* ctx, uint32_t* first_patch, uint32_t path_count)
+{
+    if (ctx == nullptr || first_patch == nullptr || path_count != ctx->frontEndPathCount)
+        return set_error("rivecuda_front_end_path_patches: bad arguments (the path count must be the last rivecuda_front_end_paths call's)");
+    RC_CUDA(cudaSetDevice(ctx->device));
+    if (path_count != 0)
+    {
+        // PathTotals::tessVertices after the exclusive scan: the path's offset into the midpoint-fan region.
+        const uint8_t* totals = ctx->frontEnd.as<uint8_t>() + ctx->frontEndTotalsOffset;
+        RC_CUDA(cudaMemcpy2DAsync(first_patch, sizeof(uint32_t), totals, sizeof(PathTotals), sizeof(uint32_t), path_count, cudaMemcpyDeviceToHost, ctx->uploadStream));
+        RC_CUDA(cudaStreamSynchronize(ctx->uploadStream));
+    }
+    first_patch[path_count] = ctx->frontEndTessVertices;
+    for (uint32_t i = 0; i <= path_count; ++i)
+        first_patch[i] = 1u + first_patch[i] / fe::kPatchSpan; // after the one patch of padding
     return 0;
 }
 

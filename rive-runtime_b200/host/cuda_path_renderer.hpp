@@ -1,6 +1,6 @@
 /*
  * CudaPathRenderer -- a rive::Renderer for frames made only of plain draws (solid colour,
- * src-over, unclipped, unfeathered nonZero / evenOdd fills and strokes) that hands the frame's
+ * unfeathered nonZero / evenOdd / clockwise fills and strokes) that hands the frame's
  * RawPaths to the device instead of running the reference's per-path CPU front end
  * (SURVEY.md 8(f1)). It sits where RiveRenderer sits:
  *
@@ -62,12 +62,12 @@ public:
         const RawPath& raw = path->getRawPath();
         if (raw.empty() || (paint->getIsStroked() && !(paint->getThickness() > 0)) || !(paint->getFeather() >= 0))
             return;
-        if (paint->getFeather() != 0 || paint->getType() != PaintType::solidColor || paint->getImageTexture() != nullptr ||
-            (!paint->getIsStroked() && path->getFillRule() == FillRule::clockwise))
-        {
-            refuse("drawPath with a feather / gradient / image / clockwise fill");
-            return;
-        }
+        if (paint->getFeather() != 0)
+            return refuse("drawPath with a feather");
+        if (paint->getType() != PaintType::solidColor)
+            return refuse("drawPath with a gradient");
+        if (paint->getImageTexture() != nullptr)
+            return refuse("drawPath with an image paint");
         if (m_stack.back().overallClipPixelBounds.empty())
             return; // rive_renderer.cpp:151
         const Mat2D& m = m_stack.back().matrix;
@@ -94,7 +94,9 @@ public:
         }
         else
         {
-            p.fill_rule = path->getFillRule() == FillRule::evenOdd ? 1 : 0;
+            // clockwise: the device front end picks the contour directions from the matrix
+            // (draw.cpp:657-680) and the host gives its batch ShaderMiscFlags::clockwiseFill.
+            p.fill_rule = path->getFillRule() == FillRule::evenOdd ? 1 : path->getFillRule() == FillRule::clockwise ? 2 : 0;
         }
         for (PathVerb v : raw.verbs())
             m_verbs.push_back(static_cast<uint8_t>(v));
@@ -224,6 +226,8 @@ private:
     {
         if (m_refused.empty())
             m_refused = what;
+        if (getenv("RIVECUDA_FRONT_END_VERBOSE") != nullptr)
+            fprintf(stderr, "CudaPathRenderer: refused %s\n", what);
     }
 
     RenderContextCUDAImpl* m_impl;

@@ -1,6 +1,6 @@
 /*
  * --dump-paths: a Renderer that forwards to the real one and records every plain draw it
- * sees -- solid-colour, src-over, non-feathered nonZero/evenOdd fills and strokes: RawPath
+ * sees -- solid-colour, src-over, non-feathered nonZero / evenOdd / clockwise fills and strokes: RawPath
  * verbs + points, view matrix, fill rule, colour, stroke thickness / join / cap. That is the
  * input of the GPU path front end (rivecuda_front_end_paths), so its output can be compared
  * with what the reference front end emitted for the very same draws. Anything else (clips,
@@ -66,8 +66,7 @@ public:
         auto* rp = static_cast<RiveRenderPath*>(path);
         auto* pt = static_cast<RiveRenderPaint*>(paint);
         const bool plain = pt->getFeather() == 0 && pt->getType() == gpu::PaintType::solidColor &&
-                           pt->getBlendMode() == BlendMode::srcOver && pt->getImageTexture() == nullptr &&
-                           (pt->getIsStroked() || rp->getFillRule() != FillRule::clockwise);
+                           pt->getBlendMode() == BlendMode::srcOver && pt->getImageTexture() == nullptr;
         // RiveRenderer::drawPath drops these before they reach the front end (rive_renderer.cpp:127-145).
         const bool dropped = rp->getRawPath().empty() || (pt->getIsStroked() && !(pt->getThickness() > 0));
         if (dropped)
@@ -79,7 +78,7 @@ public:
             const Mat2D& m = m_stack.back();
             for (int i = 0; i < 6; ++i)
                 put(m[i]);
-            put(static_cast<uint32_t>(rp->getFillRule() == FillRule::evenOdd ? 1 : 0));
+            put(static_cast<uint32_t>(rp->getFillRule() == FillRule::evenOdd ? 1 : rp->getFillRule() == FillRule::clockwise ? 2 : 0));
             put(static_cast<uint32_t>(pt->getColor()));
             put(static_cast<uint32_t>(raw.verbs().size()));
             put(static_cast<uint32_t>(raw.points().size()));

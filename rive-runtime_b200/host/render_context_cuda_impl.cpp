@@ -582,29 +582,81 @@ int RenderContextCUDAImpl::flushPlainPathChunk(const PlainPathFrame& frame, size
     d.tess_data_height = r.tess_data_height;
     d.dither_mode = static_cast<uint8_t>(desc.ditherMode);
 
-    // One midpointFanPatches batch over all patches (LogicalFlush::pushMidpointFanDraw,
-    // render_context.cpp:3426-3450).
-    rivecuda_draw_batch batch;
-    memset(&batch, 0, sizeof(batch));
-    batch.draw_type = RIVECUDA_DRAW_MIDPOINT_FAN_PATCHES;
-    batch.element_count = r.patch_count;
-    batch.base_element = r.first_patch;
-    batch.index_count_per_instance = kMidpointFanPatchIndexCount;
-    batch.base_index = kMidpointFanPatchBaseIndex;
-    batch.first_blend_mode = static_cast<uint32_t>(BlendMode::srcOver);
+    // midpointFanPatches batches (LogicalFlush::pushMidpointFanDraw, render_context.cpp:3426-3450).
     // In rasterOrdering mode the reference merges path draws of any blend mode into one batch whose
     // features are the union of its draws' (LogicalFlush::pushDraw, render_context.cpp:3890-3990;
-    // DrawContents::advancedBlend -> ENABLE_ADVANCED_BLEND, HSL modes -> ENABLE_HSL_BLEND_MODES).
+    // DrawContents::advancedBlend -> ENABLE_ADVANCED_BLEND, HSL modes -> ENABLE_HSL_BLEND_MODES),
+    // but ShaderMiscFlags::clockwiseFill is per batch (pushPathDraw, render_context.cpp:3631-3640):
+    // a fill only joins a batch whose fills have its kind; strokes join either
+    // (can_combine_shader_misc_flags, render_context.cpp:3679-3700).
+    auto new_batch = [&](uint32_t firstPatch) {
+        rivecuda_draw_batch batch;
+        memset(&batch, 0, sizeof(batch));
+        batch.draw_type = RIVECUDA_DRAW_MIDPOINT_FAN_PATCHES;
+        batch.base_element = firstPatch;
+        batch.index_count_per_instance = kMidpointFanPatchIndexCount;
+        batch.base_index = kMidpointFanPatchBaseIndex;
+        batch.first_blend_mode = static_cast<uint32_t>(BlendMode::srcOver);
+        return batch;
+    };
+    auto add_features = [](rivecuda_draw_batch& batch, const rivecuda_path& path) {
+        if (path.blend_mode != 0u)
+            batch.shader_features |= RIVECUDA_FEATURE_ADVANCED_BLEND | (path.blend_mode >= 12u ? RIVECUDA_FEATURE_HSL_BLEND_MODES : 0u);
+        if ((path.stroke >> 8) != 0u)
+            batch.shader_features |= RIVECUDA_FEATURE_CLIP_RECT; // DrawContents::clipRect... -> ENABLE_CLIP_RECT
+        if ((path.stroke & 1u) == 0u && path.fill_rule == 1u)
+            batch.shader_features |= RIVECUDA_FEATURE_EVEN_ODD; // pushPathDraw, render_context.cpp:3655-3660
+    };
+    bool anyClockwise = false, anyOtherFill = false;
     for (size_t i = 0; i < pathCount; ++i)
     {
-        const uint32_t mode = frame.paths[firstPath + i].blend_mode;
-        if (mode != 0u)
-            batch.shader_features |= RIVECUDA_FEATURE_ADVANCED_BLEND | (mode >= 12u ? RIVECUDA_FEATURE_HSL_BLEND_MODES : 0u);
-        if ((frame.paths[firstPath + i].stroke >> 8) != 0u)
-            batch.shader_features |= RIVECUDA_FEATURE_CLIP_RECT; // DrawContents::clipRect... -> ENABLE_CLIP_RECT
+        const rivecuda_path& path = frame.paths[firstPath + i];
+        if ((path.stroke & 1u) == 0u)
+            (path.fill_rule == 2u ? anyClockwise : anyOtherFill) = true;
     }
-    const uint32_t batchCount = r.patch_count != 0 ? 1u : 0u;
-    return m_abi.flush(m_ctx, &d, &batch, batchCount, nullptr, 0, nullptr, 0);
+    std::vector<rivecuda_draw_batch> batches;
+    if (r.patch_count != 0 && !(anyClockwise && anyOtherFill))
+    {
+        rivecuda_draw_batch batch = new_batch(r.first_patch);
+        batch.element_count = r.patch_count;
+        batch.shader_misc_flags = anyClockwise ? RIVECUDA_MISC_CLOCKWISE_FILL : 0u;
+        for (size_t i = 0; i < pathCount; ++i)
+            add_features(batch, frame.paths[firstPath + i]);
+        batches.push_back(batch);
+    }
+    else if (r.patch_count != 0)
+    {
+        // Mixed fills: where each path's patches start decides the batch boundaries.
+        std::vector<uint32_t> firstPatch(pathCount + 1);
+        if (int status = m_abi.front_end_path_patches(m_ctx, firstPatch.data(), static_cast<uint32_t>(pathCount)))
+            return status;
+        bool batchHasFills = false;
+        for (size_t i = 0; i < pathCount; ++i)
+        {
+            const rivecuda_path& path = frame.paths[firstPath + i];
+            const uint32_t patches = firstPatch[i + 1] - firstPatch[i];
+            if (patches == 0)
+                continue; // culled, or nothing to draw
+            const bool isFill = (path.stroke & 1u) == 0u;
+            const uint32_t misc = isFill && path.fill_rule == 2u ? RIVECUDA_MISC_CLOCKWISE_FILL : 0u;
+            if (batches.empty() || (isFill && batchHasFills && batches.back().shader_misc_flags != misc))
+            {
+                batches.push_back(new_batch(firstPatch[i]));
+                batchHasFills = false;
+            }
+            rivecuda_draw_batch& batch = batches.back();
+            if (isFill && !batchHasFills)
+            {
+                batch.shader_misc_flags = misc;
+                batchHasFills = true;
+            }
+            batch.element_count += patches;
+            add_features(batch, path);
+        }
+    }
+    for (const rivecuda_draw_batch& batch : batches)
+        d.combined_shader_features |= batch.shader_features;
+    return m_abi.flush(m_ctx, &d, batches.data(), static_cast<uint32_t>(batches.size()), nullptr, 0, nullptr, 0);
 }
 
 void RenderContextCUDAImpl::flush(const FlushDescriptor& desc)

@@ -98,7 +98,7 @@ def test_polar_segment_counts_match_the_reference(name):
     assert checked > 0
 
 
-FRONT_END_SCENES = ["f1", "s1", "c2_4k", "trickycubicstrokes", "trickycubicstrokes_roundcaps", "emptystroke", "strokes3",
+FRONT_END_SCENES = ["f1", "f1w", "s1", "c2_4k", "trickycubicstrokes", "trickycubicstrokes_roundcaps", "emptystroke", "strokes3",
                     "labyrinth_round", "labyrinth_square", "zero_control_stroke", "zerolinestroke", "OverStroke",
                     "bevel180strokes", "roundjoinstrokes", "widebuttcaps", "beziers", "CubicStroke", "inner_join_geometry",
                     "teenyStrokes", "quadcap", "strokefill", "zeroPath", "lots_of_tess_spans_stroke"]
@@ -124,13 +124,22 @@ def test_front_end_core_matches_the_reference_front_end(name):
     res = out.result
     assert (res.path_count, res.contour_count, res.tess_vertex_span_count, res.tess_data_height) == (
         d.path_count, d.contour_count, d.tess_vertex_span_count, d.tess_data_height)
-    batch = flushes[0].batches[0]
-    assert len(flushes[0].batches) == 1 and batch.draw_type == 0
-    assert (res.first_patch, res.patch_count) == (batch.base_element, batch.element_count)
+    # One midpointFanPatches batch -- or, when clockwise fills alternate with nonZero / evenOdd ones
+    # (f1w), contiguous batches whose ShaderMiscFlags::clockwiseFill alternates.
+    batches = flushes[0].batches
+    assert all(b.draw_type == 0 for b in batches) and (len(batches) == 1 or name == "f1w")
+    assert all(a.base_element + a.element_count == b.base_element and a.shader_misc_flags != b.shader_misc_flags
+               for a, b in zip(batches, batches[1:]))
+    assert (res.first_patch, res.patch_count) == (batches[0].base_element, sum(b.element_count for b in batches))
     n = res.tess_vertex_span_count
     want = np.frombuffer(host[6].tobytes()[:n * 64], dtype=np.uint32).reshape(-1, 16)
     bad = np.nonzero((out.spans[:n] != want).any(axis=1))[0]
     assert bad.size == 0, f"{bad.size} spans differ, first {bad[:5]}"
+    if name == "f1w":
+        # clockwise fills under a left-handed matrix: forward copy first, coverage negated
+        # (ContourDirections::forwardThenReverse + NEGATE_PATH_FILL_COVERAGE_FLAG, draw.cpp:657-680)
+        negated = (want[:, 15] & (1 << 24)) != 0
+        assert 0 < negated.sum() < n and len(batches) > 50
     want = np.frombuffer(host[4].tobytes()[:res.contour_count * 16], dtype=np.uint32).reshape(-1, 4)
     assert np.array_equal(out.contours[:res.contour_count], want)
     n = res.path_count
@@ -159,7 +168,7 @@ def test_stroke_scenes_exercise_every_stroke_feature():
     assert polar.max() > 32 and join.max() > 32
 
 
-@pytest.mark.parametrize("scene,golden", [("s1", "s1"), ("f1", "f1"), ("gm:trickycubicstrokes", "trickycubicstrokes"),
+@pytest.mark.parametrize("scene,golden", [("s1", "s1"), ("f1", "f1"), ("f1w", "f1w"), ("gm:trickycubicstrokes", "trickycubicstrokes"),
                                           ("gm:strokes3", "strokes3")])
 def test_cpp_path_renderer_hands_over_what_the_reference_front_end_saw(scene, golden, tmp_path):
     """host/cuda_path_renderer.hpp (the rive::Renderer that feeds the device front end from C++),

@@ -15,7 +15,7 @@ from conftest import GOLDEN
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("name", ["f1", "s1", "c2_4k", "trickycubicstrokes", "emptystroke", "strokes3", "OverStroke", "zero_control_stroke", "lots_of_tess_spans_stroke"])
+@pytest.mark.parametrize("name", ["f1", "f1w", "s1", "c2_4k", "trickycubicstrokes", "emptystroke", "strokes3", "OverStroke", "zero_control_stroke", "lots_of_tess_spans_stroke"])
 def test_gpu_front_end_matches_reference_front_end(built, name):
     from rive_runtime_b200 import abi, front_end as F, replay as R, trace as T
     abi.load()
@@ -42,8 +42,15 @@ def test_gpu_front_end_matches_reference_front_end(built, name):
         assert res.contour_count == d.contour_count
         assert res.tess_vertex_span_count == d.tess_vertex_span_count
         assert res.tess_data_height == d.tess_data_height
-        assert len(fr.batches) == 1 and fr.batches[0].draw_type == 0
-        assert (res.first_patch, res.patch_count) == (fr.batches[0].base_element, fr.batches[0].element_count)
+        assert (len(fr.batches) == 1 or name == "f1w") and all(b.draw_type == 0 for b in fr.batches)
+        assert (res.first_patch, res.patch_count) == (fr.batches[0].base_element, sum(b.element_count for b in fr.batches))
+        if name == "f1w":
+            # the batch boundaries the reference chose are path boundaries of rivecuda_front_end_path_patches
+            first_patch = np.zeros(dump.paths.size + 1, dtype=np.uint32)
+            rp._call("rivecuda_front_end_path_patches", first_patch.ctypes.data, dump.paths.size)
+            assert first_patch[0] == res.first_patch and first_patch[-1] == res.first_patch + res.patch_count
+            assert np.all(np.diff(first_patch.astype(np.int64)) >= 0)
+            assert set(b.base_element for b in fr.batches) <= set(first_patch.tolist())
         # a2: spans (segment counts, x0x1 / y offsets, reflections, wraps) and contours, byte for byte
         n = res.tess_vertex_span_count * 64
         got = F.read_buffer(rp, 6, n).view(np.uint32).reshape(-1, 16)
@@ -95,7 +102,7 @@ def test_device_front_end_equals_its_host_build_on_random_paths(built, seed, n_p
         assert np.array_equal(F.read_buffer(rp, 2, n * 8).view(np.uint32).reshape(-1, 2)[1:], want.paint_data[1:n])
 
 
-@pytest.mark.parametrize("scene,golden", [("c2", "c2_4k"), ("f1", "f1"), ("f1o", "f1o"), ("f1b", "f1b"), ("f1c", "f1c"), ("s1", "s1"), ("gm:trickycubicstrokes", "trickycubicstrokes"),
+@pytest.mark.parametrize("scene,golden", [("c2", "c2_4k"), ("f1", "f1"), ("f1o", "f1o"), ("f1b", "f1b"), ("f1c", "f1c"), ("f1w", "f1w"), ("s1", "s1"), ("gm:trickycubicstrokes", "trickycubicstrokes"),
                                           ("gm:strokes3", "strokes3")])
 def test_cpp_path_renderer_draws_the_same_frame(built, scene, golden):
     """SURVEY 8 f1 in the compiled host: the scene player with --gpu-front-end draws through
