@@ -127,6 +127,35 @@ def test_cpp_path_renderer_draws_the_same_frame(built, scene, golden):
     assert px.size == want.size and np.array_equal(px.reshape(want.shape), want)
 
 
+@pytest.mark.parametrize("name", ["shapetest", "fix_rectangle", "follow_path_solos", "trim_path_linear", "magic_alley_db_reduced_export",
+                                  "nested_artboard_opacity", "lock_icon_demo", "follow_path_shapes", "solos_collapse_tests", "group_effect"])
+def test_riv_file_through_the_device_front_end(built, name):
+    """Real .riv content (clockwise and nonZero fills, strokes, opacity, artboard clip rectangles)
+    through --gpu-front-end: frame 20 must equal, bit for bit, the frame the reference's CPU front
+    end produces for the same file through the same backend (midpoint fans only: --budget-ms 0
+    switches the reference's interior triangulation of large paths off, which the device front end
+    does not implement). tests/tools/riv_front_end_sweep.py runs the same comparison over a whole
+    directory: all 180 importable assets below 400 kB are identical (profiles/r02_riv_front_end_sweep.md).
+    The assets are the reference's (tools/fetch_riv_assets.sh); the test skips without them."""
+    import subprocess
+    import tempfile
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    player = os.path.join(root, "rive-runtime_b200", "_build", "rive_cuda_player")
+    asset = os.path.join(root, "tests", "_riv_assets", name + ".riv")
+    if not os.path.exists(player) or not os.path.exists(asset):
+        pytest.skip("scene player or .riv asset not present")
+    env = dict(os.environ, RIVECUDA_LIB=os.path.join(root, "rive-runtime_b200", "_build", "librivecuda.so"))
+    frames = []
+    with tempfile.TemporaryDirectory() as tmp:
+        for extra in ([], ["--gpu-front-end"]):
+            out = os.path.join(tmp, "frame%d.rgba" % len(frames))
+            subprocess.check_call([player, "--scene", "riv:" + asset, "--frames", "20", "--budget-ms", "0", "--out", out, *extra], env=env,
+                                  stdout=subprocess.DEVNULL, timeout=300)
+            frames.append(np.fromfile(out, dtype=np.uint8))
+    assert frames[0].size == 1920 * 1080 * 4 and np.array_equal(frames[0], frames[1])
+    assert len(np.unique(frames[0].reshape(-1, 4), axis=0)) > 1  # not an empty frame
+
+
 def test_front_end_refuses_what_one_flush_cannot_hold(built):
     """Error behaviour: more paths / contours / tessellation vertices than one logical flush admits
     (RenderContext::LogicalFlush::pushDraws, render_context.cpp:528-536) is an error with a
