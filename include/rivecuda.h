@@ -313,7 +313,9 @@ typedef struct rivecuda_path
 {
     uint32_t first_verb, verb_count;
     uint32_t first_point;
-    uint32_t fill_rule; /* fills: 0 nonZero, 1 evenOdd, 2 clockwise (its batch carries RIVECUDA_MISC_CLOCKWISE_FILL) */
+    uint32_t fill_rule; /* bits 0-7, fills: 0 nonZero, 1 evenOdd, 2 clockwise (its batch carries RIVECUDA_MISC_CLOCKWISE_FILL);
+                         * bits 8-31: 1 + index of the path's gradient paint in the table passed to
+                         * rivecuda_front_end_gradient_paints (0: solid colour) */
     float matrix[6];
     uint32_t color;     /* rive::ColorInt, 0xAARRGGBB, unpremultiplied */
     uint32_t stroke;    /* bit 0: 0 fill, 1 stroke; bits 8-31: 1 + index of the path's clip rectangle in the table of
@@ -384,6 +386,20 @@ int rivecuda_front_end_paths(rivecuda_ctx* ctx,
                              uint32_t frame_width,
                              uint32_t frame_height,
                              rivecuda_front_end_result* result);
+/* A linear / radial gradient paint of the next rivecuda_front_end_paths() call (copied): what
+ * PaintData::set and PaintAuxData::set (gpu.cpp:879-1040) compute per draw from the gradient, its
+ * colour-ramp location in the gradient texture (LogicalFlush::allocateGradient,
+ * render_context.cpp:588-674; the caller also writes the GradientSpans, as the reference's host
+ * does) and the view matrix. The device front end merges in the fill rule, blend mode and
+ * clip-rectangle bits and writes the records. */
+typedef struct rivecuda_gradient_paint
+{
+    uint32_t paint_type;          /* 2 linear, 3 radial (constants.glsl:129-130) */
+    float grad_texture_y;         /* (row + .5) / allocated gradient texture height */
+    float paint_matrix[6];        /* pixel -> gradient space */
+    float grad_horizontal_span[2];
+} rivecuda_gradient_paint;
+int rivecuda_front_end_gradient_paints(rivecuda_ctx* ctx, const rivecuda_gradient_paint* paints, uint32_t count);
 /* first_patch[i] = the first midpoint-fan patch (DrawBatch::baseElement) of path i of the last
  * rivecuda_front_end_paths() call, for i in [0, path_count]; a culled path's equals its
  * successor's, entry path_count is the end of the last path. A frame whose fills mix clockwise

@@ -764,6 +764,7 @@ struct FrontEndOut
     uint32_t* paintData; // PaintData, 2 words
     uint32_t* paintAux;  // PaintAuxData, 32 words
     const rivecuda_clip_rect* clipRects = nullptr; // the table paths' clip indices refer to
+    const rivecuda_gradient_paint* gradientPaints = nullptr; // the table paths' gradient indices refer to
     uint32_t spanBase;   // spans [0, spanBase) are the flush's padding spans
 };
 
@@ -857,7 +858,7 @@ template <bool EMIT> struct PlaceSink
 constexpr uint32_t kNegatePathFillCoverageFlag = 1u << 24; // constants.glsl:100
 FE_HD bool is_forward_then_reverse(const rivecuda_path& path)
 {
-    if ((path.stroke & 1u) != 0u || path.fill_rule != 2u)
+    if ((path.stroke & 1u) != 0u || (path.fill_rule & 0xffu) != 2u)
         return false;
     const float det = path.matrix[0] * path.matrix[3] - path.matrix[2] * path.matrix[1];
     return det < 0.f;
@@ -879,12 +880,23 @@ FE_HD void write_path_records(const rivecuda_path& path, uint32_t pathID, const 
     const uint32_t rgba = ((argb >> 16) & 0xffu) | (argb & 0xff00u) | ((argb & 0xffu) << 16) | (argb & 0xff000000u);
     const uint32_t clipIndex = path.stroke >> 8;
     const rivecuda_clip_rect* clip = clipIndex != 0u && out.clipRects != nullptr ? out.clipRects + (clipIndex - 1u) : nullptr;
+    const uint32_t fillRule = path.fill_rule & 0xffu, gradientIndex = path.fill_rule >> 8;
+    const rivecuda_gradient_paint* gradient = gradientIndex != 0u && out.gradientPaints != nullptr ? out.gradientPaints + (gradientIndex - 1u) : nullptr;
     out.paintData[static_cast<size_t>(pathID) * 2 + 0] =
-        kPaintTypeSolidColor | ((path.blend_mode & 0xfu) << 4) | (isStroke || path.fill_rule == 2u ? 0u : path.fill_rule == 1u ? kPaintFlagEvenOddFill : kPaintFlagNonZeroFill) |
+        (gradient != nullptr ? gradient->paint_type : kPaintTypeSolidColor) | ((path.blend_mode & 0xfu) << 4) |
+        (isStroke || fillRule == 2u ? 0u : fillRule == 1u ? kPaintFlagEvenOddFill : kPaintFlagNonZeroFill) |
         (clip != nullptr ? kPaintFlagHasClipRect : 0u); // PaintData::set (gpu.cpp:879-939)
-    out.paintData[static_cast<size_t>(pathID) * 2 + 1] = rgba;
+    out.paintData[static_cast<size_t>(pathID) * 2 + 1] = gradient != nullptr ? bits(gradient->grad_texture_y) : rgba;
     uint32_t aux[16] = {};
     store_words16(out.paintAux + static_cast<size_t>(pathID) * 32 + 16, aux);
+    if (gradient != nullptr)
+    {
+        // PaintAuxData::m_paintMatrix, m_gradTextureHorizontalSpan (gpu.cpp:951-999)
+        for (int i = 0; i < 6; ++i)
+            aux[i] = bits(gradient->paint_matrix[i]);
+        aux[6] = bits(gradient->grad_horizontal_span[0]);
+        aux[7] = bits(gradient->grad_horizontal_span[1]);
+    }
     if (clip != nullptr)
     {
         // PaintAuxData::m_clipRectInverseMatrix, m_inverseFwidth (gpu.cpp:1044-1054)

@@ -175,7 +175,8 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) front_end_count_kernel(co
                                                                                PathTotals* __restrict__ totals,
                                                                                uint32_t* __restrict__ ownTessVertices,
                                                                                const rivecuda_clip_rect* __restrict__ clipRects,
-                                                                               uint32_t clipRectCount)
+                                                                               uint32_t clipRectCount,
+                                                                               uint32_t gradientPaintCount)
 {
     const int lane = threadIdx.x & 31;
     const uint32_t i = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
@@ -201,9 +202,9 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) front_end_count_kernel(co
                 atomicOr(badPathFlag, 1u);
             culled = true;
         }
-        else if ((path.stroke >> 8) > clipRectCount)
+        else if ((path.stroke >> 8) > clipRectCount || (path.fill_rule >> 8) > gradientPaintCount)
         {
-            // A clip rectangle the caller did not pass: touch nothing, report it.
+            // A clip rectangle / gradient paint the caller did not pass: touch nothing, report it.
             if (lane == 0)
                 atomicOr(badPathFlag, 1u);
             culled = true;
@@ -523,6 +524,14 @@ int rivecuda_front_end_clip_rects(rivecuda_ctx* ctx, const rivecuda_clip_rect* r
     return 0;
 }
 
+int rivecuda_front_end_gradient_paints(rivecuda_ctx* ctx, const rivecuda_gradient_paint* paints, uint32_t count)
+{
+    if (ctx == nullptr || (count != 0 && paints == nullptr))
+        return set_error("rivecuda_front_end_gradient_paints: bad arguments");
+    ctx->frontEndGradientPaints.assign(paints, paints + count);
+    return 0;
+}
+
 int rivecuda_front_end_paths(rivecuda_ctx* ctx,
                              const float* points_xy,
                              uint32_t point_count,
@@ -559,7 +568,9 @@ int rivecuda_front_end_paths(rivecuda_ctx* ctx,
     const size_t ownOffset = totalsOffset + static_cast<size_t>(path_count) * sizeof(PathTotals) + 64;
     const size_t clipOffset = (ownOffset + static_cast<size_t>(path_count) * sizeof(uint32_t) + 15) & ~size_t(15);
     const size_t clipBytes = ctx->frontEndClipRects.size() * sizeof(rivecuda_clip_rect);
-    if (int s = ctx->frontEnd.reserve(clipOffset + clipBytes))
+    const size_t gradientOffset = (clipOffset + clipBytes + 15) & ~size_t(15);
+    const size_t gradientBytes = ctx->frontEndGradientPaints.size() * sizeof(rivecuda_gradient_paint);
+    if (int s = ctx->frontEnd.reserve(gradientOffset + gradientBytes))
         return s;
     uint8_t* base = ctx->frontEnd.as<uint8_t>();
     V2* dPoints = reinterpret_cast<V2*>(base);
@@ -581,6 +592,14 @@ int rivecuda_front_end_paths(rivecuda_ctx* ctx,
     {
         RC_CUDA(cudaMemcpyAsync(base + clipOffset, ctx->frontEndClipRects.data(), clipBytes, cudaMemcpyHostToDevice, stream));
         dClipRects = reinterpret_cast<const rivecuda_clip_rect*>(base + clipOffset);
+    }
+
+    const rivecuda_gradient_paint* dGradientPaints = nullptr;
+    const uint32_t gradientPaintCount = static_cast<uint32_t>(ctx->frontEndGradientPaints.size());
+    if (gradientBytes != 0)
+    {
+        RC_CUDA(cudaMemcpyAsync(base + gradientOffset, ctx->frontEndGradientPaints.data(), gradientBytes, cudaMemcpyHostToDevice, stream));
+        dGradientPaints = reinterpret_cast<const rivecuda_gradient_paint*>(base + gradientOffset);
     }
 
     // The five buffers this front end fills, at the sizes the worst case needs (a stroked cubic
@@ -623,6 +642,7 @@ int rivecuda_front_end_paths(rivecuda_ctx* ctx,
     out.paintAux = static_cast<uint32_t*>(dev(RIVECUDA_BUFFER_PAINT_AUX));
     out.spanBase = 0;
     out.clipRects = dClipRects;
+    out.gradientPaints = dGradientPaints;
     // Record 0 of path / paint / paintAux is the flush's reserved (clear colour) record.
     RC_CUDA(cudaMemsetAsync(out.pathData, 0, 64, stream));
     RC_CUDA(cudaMemsetAsync(out.paintData, 0, 8, stream));
@@ -633,7 +653,7 @@ int rivecuda_front_end_paths(rivecuda_ctx* ctx,
     uint32_t* field = reinterpret_cast<uint32_t*>(dTotals);
     if (path_count != 0)
     {
-        front_end_count_kernel<<<blocks, kWarpsPerBlock * 32, 0, stream>>>(dPaths, path_count, dPoints, dVerbs, frame_width, frame_height, point_count, dSums + 6, dTotals, dOwn, dClipRects, clipRectCount);
+        front_end_count_kernel<<<blocks, kWarpsPerBlock * 32, 0, stream>>>(dPaths, path_count, dPoints, dVerbs, frame_width, frame_height, point_count, dSums + 6, dTotals, dOwn, dClipRects, clipRectCount, gradientPaintCount);
         front_end_scan3_kernel<<<1, 1024, 0, stream>>>(reinterpret_cast<uint4*>(dTotals), path_count, dSums);
     }
     else

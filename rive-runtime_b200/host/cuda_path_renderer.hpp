@@ -13,27 +13,34 @@
  * Per stroked path the two scalars PathDraw computes with libm are computed here the same way
  * (draw.cpp:603-607, 776-813), and a modulated opacity goes into the colour as PathDraw puts it
  * there (draw.cpp:727-737); blend modes travel in the paint record; clip RECTANGLES (clipPath with an
- * axis-aligned rectangle, nested ones intersected) travel as a table the paths index. Anything else -- clip paths, gradients, images, feathers --
+ * axis-aligned rectangle, nested ones intersected) travel as a table the paths index; linear and
+ * radial gradients get their colour ramps allocated here as LogicalFlush::allocateGradient does, and
+ * travel as GradientSpans plus a table of paint records. Anything else -- clip paths, images, feathers --
  * is not handled by the device front end: the renderer records the first such call
  * and flush() refuses the frame, so the caller can draw it with RiveRenderer (no silent fallback).
  */
 #pragma once
 
 #include "render_context_cuda_impl.hpp"
+#include "../csrc/front_end_core.h" // the frame cull the device applies (fe::is_outside_frame), host build
 
 #include "rive/math/bezier_utils.hpp"
 #include "rive/math/mat2d.hpp"
 #include "rive/renderer.hpp"
 #include "rive/renderer/gpu.hpp"
 #include "rive/shapes/paint/color.hpp"
+#include "gradient.hpp"
 #include "rive_render_paint.hpp"
 #include "rive_render_path.hpp"
 #include "rive/renderer/rive_renderer.hpp"
 
 #include <algorithm>
+#include <array>
 #include <cfloat>
 #include <cmath>
+#include <map>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 namespace rive::gpu
@@ -64,8 +71,8 @@ public:
             return;
         if (paint->getFeather() != 0)
             return refuse("drawPath with a feather");
-        if (paint->getType() != PaintType::solidColor)
-            return refuse("drawPath with a gradient");
+        if (paint->getType() != PaintType::solidColor && paint->getType() != PaintType::linearGradient && paint->getType() != PaintType::radialGradient)
+            return refuse("drawPath with an unknown paint type");
         if (paint->getImageTexture() != nullptr)
             return refuse("drawPath with an image paint");
         if (m_stack.back().overallClipPixelBounds.empty())
@@ -97,6 +104,24 @@ public:
             // clockwise: the device front end picks the contour directions from the matrix
             // (draw.cpp:657-680) and the host gives its batch ShaderMiscFlags::clockwiseFill.
             p.fill_rule = path->getFillRule() == FillRule::evenOdd ? 1 : path->getFillRule() == FillRule::clockwise ? 2 : 0;
+        }
+        if (paint->getType() != PaintType::solidColor)
+        {
+            // A draw PathDraw::Make culls (draw.cpp:439-509) never allocates a colour ramp: apply the
+            // cull the device would apply (the same code, built for the host) before allocating.
+            static_assert(sizeof(Vec2D) == sizeof(rivecuda::fe::V2), "points are passed as they are");
+            if (rivecuda::fe::is_outside_frame(p, reinterpret_cast<const rivecuda::fe::V2*>(raw.points().data()), static_cast<uint32_t>(raw.points().size()),
+                                               m_target->width(), m_target->height(), m_clipRects.data()))
+                return;
+            // PathDraw keeps the gradient with the modulated opacity folded into its colours
+            // (draw.cpp:580) and allocates its colour ramp when the draw is pushed.
+            GradientDraw draw;
+            draw.gradient = paint->getGradientWithOpacity(m_stack.back().opacity);
+            draw.matrix = m;
+            if (draw.gradient == nullptr || !allocateGradient(draw.gradient.get(), &draw.location))
+                return refuse("drawPath with more gradients than one gradient texture holds");
+            m_gradientDraws.push_back(std::move(draw));
+            p.fill_rule |= static_cast<uint32_t>(m_gradientDraws.size()) << 8;
         }
         for (PathVerb v : raw.verbs())
             m_verbs.push_back(static_cast<uint8_t>(v));
@@ -218,10 +243,145 @@ public:
         frame.pathCount = m_paths.size();
         frame.clipRects = m_clipRects.data();
         frame.clipRectCount = m_clipRects.size();
+        std::vector<GradientSpan> gradSpans;
+        std::vector<rivecuda_gradient_paint> gradientPaints;
+        if (!m_gradientDraws.empty())
+        {
+            // LogicalFlush::layoutResources (render_context.cpp:1206, 1338-1339, 1442-1443): the simple
+            // ramps fill the first rows, 256 to a row, one row per complex ramp follows; the paints
+            // address rows normalised by the ALLOCATED texture height.
+            const uint32_t complexOffsetY = static_cast<uint32_t>((m_simpleRamps.size() + kGradTextureWidthInSimpleRamps - 1) / kGradTextureWidthInSimpleRamps);
+            frame.gradDataHeight = complexOffsetY + static_cast<uint32_t>(m_complexRamps.size());
+            const uint32_t allocatedHeight = m_impl->reservePlainGradientRows(frame.gradDataHeight);
+            const GradTextureLayout layout = {complexOffsetY, 1.f / static_cast<float>(allocatedHeight)};
+            writeGradientSpans(complexOffsetY, &gradSpans);
+            gradientPaints.reserve(m_gradientDraws.size());
+            for (const GradientDraw& draw : m_gradientDraws)
+            {
+                // The reference's own record writers, on the stack; the words the device copies.
+                SimplePaintValue value;
+                value.colorRampLocation = draw.location;
+                PaintData paintData;
+                paintData.set(DrawContents::none, draw.gradient->paintType(), value, layout, 0, false, false, BlendMode::srcOver);
+                PaintAuxData aux;
+                aux.set(draw.matrix, Mat2D(), draw.gradient->paintType(), value, draw.gradient.get(), nullptr, nullptr, m_target, m_impl->platformFeatures());
+                uint32_t paintWords[2];
+                float auxWords[8];
+                memcpy(paintWords, &paintData, sizeof(paintWords));
+                memcpy(auxWords, &aux, sizeof(auxWords));
+                rivecuda_gradient_paint record;
+                record.paint_type = paintWords[0] & 0xfu;
+                memcpy(&record.grad_texture_y, &paintWords[1], 4);
+                memcpy(record.paint_matrix, auxWords, 24);
+                record.grad_horizontal_span[0] = auxWords[6];
+                record.grad_horizontal_span[1] = auxWords[7];
+                gradientPaints.push_back(record);
+            }
+            frame.gradSpans = gradSpans.data();
+            frame.gradSpanCount = gradSpans.size();
+            frame.gradientPaints = gradientPaints.data();
+            frame.gradientPaintCount = gradientPaints.size();
+        }
         return m_impl->flushPlainPaths(frame);
     }
 
 private:
+    // LogicalFlush::allocateGradient (render_context.cpp:588-674): two-stop 0..1 (and one-stop)
+    // gradients share two-texel ramps keyed by their colours, everything else gets a row of its own,
+    // shared by gradients of equal content.
+    bool allocateGradient(const Gradient* gradient, ColorRampLocation* location)
+    {
+        const float* stops = gradient->stops();
+        const ColorInt* colors = gradient->colors();
+        const size_t stopCount = gradient->count();
+        auto data_height = [](size_t simple, size_t complex) { return (simple + kGradTextureWidthInSimpleRamps - 1) / kGradTextureWidthInSimpleRamps + complex; };
+        if (stopCount == 1 || (stopCount == 2 && stops[0] == 0 && stops[1] == 1))
+        {
+            const ColorInt ramp[2] = {colors[0], colors[std::min<size_t>(1, stopCount - 1)]};
+            const uint64_t key = (static_cast<uint64_t>(ramp[1]) << 32) | ramp[0];
+            uint32_t texelIndex;
+            auto it = m_simpleGradients.find(key);
+            if (it != m_simpleGradients.end())
+            {
+                texelIndex = it->second;
+            }
+            else
+            {
+                if (data_height(m_simpleRamps.size() + 1, m_complexRamps.size()) > RenderContextCUDAImpl::kMaxGradTextureHeight)
+                    return false;
+                texelIndex = static_cast<uint32_t>(m_simpleRamps.size() * 2);
+                m_simpleGradients.emplace(key, texelIndex);
+                m_simpleRamps.push_back({ramp[0], ramp[1]});
+            }
+            location->row = static_cast<uint16_t>(texelIndex / kGradTextureWidth);
+            location->col = static_cast<uint16_t>(texelIndex % kGradTextureWidth);
+        }
+        else
+        {
+            std::vector<uint32_t> key(stopCount * 2);
+            memcpy(key.data(), stops, stopCount * 4);
+            memcpy(key.data() + stopCount, colors, stopCount * 4);
+            auto it = m_complexGradients.find(key);
+            uint16_t row;
+            if (it != m_complexGradients.end())
+            {
+                row = it->second;
+            }
+            else
+            {
+                if (data_height(m_simpleRamps.size(), m_complexRamps.size() + 1) > RenderContextCUDAImpl::kMaxGradTextureHeight)
+                    return false;
+                row = static_cast<uint16_t>(m_complexRamps.size());
+                m_complexGradients.emplace(std::move(key), row);
+                m_complexRamps.push_back(ref_rcp(gradient));
+            }
+            location->row = row; // relative to the first complex row until the layout is known
+            location->col = ColorRampLocation::kComplexGradientMarker;
+        }
+        return true;
+    }
+
+    // The GradientSpan instances LogicalFlush::writeResources emits (render_context.cpp:1462-1533).
+    void writeGradientSpans(uint32_t complexOffsetY, std::vector<GradientSpan>* spans) const
+    {
+        constexpr uint32_t kOneTexelFixed = 65536 / kGradTextureWidth;
+        // constants.glsl:61-63 (a generated header in the reference's build)
+        constexpr uint32_t GRAD_SPAN_FLAG_LEFT_BORDER = 0x80000000u, GRAD_SPAN_FLAG_RIGHT_BORDER = 0x40000000u, GRAD_SPAN_FLAG_COMPLEX_BORDER = 0x20000000u;
+        for (size_t i = 0; i < m_simpleRamps.size(); ++i)
+        {
+            // one empty span with one-texel borders to the left and right
+            const uint32_t y = static_cast<uint32_t>(i / kGradTextureWidthInSimpleRamps);
+            const uint32_t centerXFixed = static_cast<uint32_t>(((i % kGradTextureWidthInSimpleRamps) * 2 + 1) * kOneTexelFixed);
+            GradientSpan span;
+            span.set(centerXFixed, centerXFixed, y, GRAD_SPAN_FLAG_LEFT_BORDER | GRAD_SPAN_FLAG_RIGHT_BORDER, m_simpleRamps[i][0], m_simpleRamps[i][1]);
+            spans->push_back(span);
+        }
+        for (size_t i = 0; i < m_complexRamps.size(); ++i)
+        {
+            const Gradient* gradient = m_complexRamps[i].get();
+            const float* stops = gradient->stops();
+            const ColorInt* colors = gradient->colors();
+            const uint32_t y = static_cast<uint32_t>(i) + complexOffsetY;
+            const float m = (kGradTextureWidth - 1.f) * kOneTexelFixed, a = .5f * kOneTexelFixed;
+            uint32_t lastXFixed = static_cast<uint32_t>(stops[0] * m + a);
+            ColorInt lastColor = colors[0];
+            for (size_t k = 1; k < gradient->count(); ++k)
+            {
+                const uint32_t xFixed = static_cast<uint32_t>(stops[k] * m + a);
+                uint32_t flags = GRAD_SPAN_FLAG_COMPLEX_BORDER;
+                if (k == 1)
+                    flags |= GRAD_SPAN_FLAG_LEFT_BORDER;
+                if (k == gradient->count() - 1)
+                    flags |= GRAD_SPAN_FLAG_RIGHT_BORDER;
+                GradientSpan span;
+                span.set(lastXFixed, xFixed, y, flags, lastColor, colors[k]);
+                spans->push_back(span);
+                lastColor = colors[k];
+                lastXFixed = xFixed;
+            }
+        }
+    }
+
     void refuse(const char* what)
     {
         if (m_refused.empty())
@@ -250,6 +410,17 @@ private:
     std::vector<uint8_t> m_verbs;
     std::vector<rivecuda_path> m_paths;
     std::vector<rivecuda_clip_rect> m_clipRects;
+    struct GradientDraw
+    {
+        rcp<const Gradient> gradient;
+        ColorRampLocation location;
+        Mat2D matrix;
+    };
+    std::vector<GradientDraw> m_gradientDraws; // indexed (1-based) from rivecuda_path::fill_rule >> 8
+    std::unordered_map<uint64_t, uint32_t> m_simpleGradients;         // two colours -> first texel
+    std::vector<std::array<ColorInt, 2>> m_simpleRamps;
+    std::map<std::vector<uint32_t>, uint16_t> m_complexGradients;     // stops + colours -> row
+    std::vector<rcp<const Gradient>> m_complexRamps;
     std::string m_refused;
 };
 } // namespace rive::gpu

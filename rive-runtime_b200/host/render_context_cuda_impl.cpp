@@ -444,6 +444,14 @@ void RenderContextCUDAImpl::resizeGradientTexture(uint32_t width,
                                                   uint32_t height)
 {
     ABI_CHECK(m_abi.resize_gradient_texture(m_ctx, width, height));
+    m_plainGradHeight = height;
+}
+
+uint32_t RenderContextCUDAImpl::reservePlainGradientRows(uint32_t rows)
+{
+    if (rows > m_plainGradHeight)
+        resizeGradientTexture(kGradTextureWidth, std::min<uint32_t>((rows * 5u) >> 2, kMaxGradTextureHeight));
+    return m_plainGradHeight;
 }
 
 void RenderContextCUDAImpl::resizeTessellationTexture(uint32_t width,
@@ -525,6 +533,8 @@ int RenderContextCUDAImpl::flushPlainPathChunk(const PlainPathFrame& frame, size
     memset(&r, 0, sizeof(r));
     if (int status = m_abi.front_end_clip_rects(m_ctx, frame.clipRects, static_cast<uint32_t>(frame.clipRectCount)))
         return status;
+    if (int status = m_abi.front_end_gradient_paints(m_ctx, frame.gradientPaints, static_cast<uint32_t>(frame.gradientPaintCount)))
+        return status;
     if (int status = m_abi.front_end_paths(m_ctx,
                                            frame.pointCount != 0 ? &frame.points->x : nullptr,
                                            static_cast<uint32_t>(frame.pointCount),
@@ -556,6 +566,19 @@ int RenderContextCUDAImpl::flushPlainPathChunk(const PlainPathFrame& frame, size
     desc.tessVertexSpanCount = r.tess_vertex_span_count;
     desc.tessDataHeight = r.tess_data_height;
     desc.ditherMode = DitherMode::interleavedGradientNoise; // FrameDescriptor's default
+    desc.gradSpanCount = static_cast<uint32_t>(frame.gradSpanCount);
+    desc.gradDataHeight = frame.gradDataHeight;
+    if (frame.gradSpanCount != 0)
+    {
+        // Every chunk of the frame renders the frame's colour ramps (they are few).
+        const size_t size = frame.gradSpanCount * sizeof(GradientSpan);
+        resizeGradSpanBuffer(size);
+        void* mapped = mapGradSpanBuffer(size);
+        if (mapped == nullptr)
+            return 1;
+        memcpy(mapped, frame.gradSpans, size);
+        unmapGradSpanBuffer(size);
+    }
     {
         const size_t size = sizeof(FlushUniforms);
         resizeFlushUniformBuffer(size);
@@ -580,6 +603,8 @@ int RenderContextCUDAImpl::flushPlainPathChunk(const PlainPathFrame& frame, size
     d.contour_count = r.contour_count;
     d.tess_vertex_span_count = r.tess_vertex_span_count;
     d.tess_data_height = r.tess_data_height;
+    d.grad_span_count = desc.gradSpanCount;
+    d.grad_data_height = desc.gradDataHeight;
     d.dither_mode = static_cast<uint8_t>(desc.ditherMode);
 
     // midpointFanPatches batches (LogicalFlush::pushMidpointFanDraw, render_context.cpp:3426-3450).

@@ -159,8 +159,20 @@ public:
         // The clip rectangles the paths' `stroke >> 8` index (1-based; rivecuda.h).
         const rivecuda_clip_rect* clipRects = nullptr;
         size_t clipRectCount = 0;
+        // Gradients: the colour-ramp spans of the frame (as LogicalFlush::writeResources emits
+        // them), the rows they fill, and the paint records the paths' `fill_rule >> 8` index.
+        const gpu::GradientSpan* gradSpans = nullptr;
+        size_t gradSpanCount = 0;
+        uint32_t gradDataHeight = 0;
+        const rivecuda_gradient_paint* gradientPaints = nullptr;
+        size_t gradientPaintCount = 0;
     };
     bool flushPlainPaths(const PlainPathFrame&);
+    // Grows the gradient texture to hold `rows` rows the way RenderContext does (125% of what is
+    // needed when it no longer fits, render_context.cpp:866-899); returns the allocated height,
+    // which gradient paints are normalised by.
+    uint32_t reservePlainGradientRows(uint32_t rows);
+    constexpr static uint32_t kMaxGradTextureHeight = 2048; // render_context.cpp:44 (kMaxTextureHeight)
 
     // RenderContextImpl overrides.
     rcp<RenderBuffer> makeRenderBuffer(RenderBufferType,
@@ -234,6 +246,7 @@ private:
     RenderContextCUDAImpl(const RiveCudaABI&, rivecuda_ctx*);
 
     int flushPlainPathChunk(const PlainPathFrame&, size_t firstPath, size_t pathCount, bool firstFlush, rivecuda_front_end_result* needed);
+    uint32_t m_plainGradHeight = 0; // what the gradient texture was last sized to
     uint32_t m_plainTessHeight = 0; // what flushPlainPaths last sized the tessellation texture to
     void resizeBuffer(rivecuda_buffer_kind, size_t sizeInBytes);
     void* mapBuffer(rivecuda_buffer_kind, size_t mapSizeInBytes);
