@@ -317,7 +317,8 @@ typedef struct rivecuda_path
                          * bits 8-31: 1 + index of the path's gradient paint in the table passed to
                          * rivecuda_front_end_gradient_paints (0: solid colour) */
     float matrix[6];
-    uint32_t color;     /* rive::ColorInt, 0xAARRGGBB, unpremultiplied */
+    uint32_t color;     /* rive::ColorInt, 0xAARRGGBB, unpremultiplied; a clip update (blend_mode bit 8): the clip ID
+                         * the update itself is clipped against (outerClipID, 0: not nested) */
     uint32_t stroke;    /* bit 0: 0 fill, 1 stroke; bits 8-31: 1 + index of the path's clip rectangle in the table of
                          * rivecuda_front_end_clip_rects (0: not clipped by a rectangle) */
     float stroke_radius; /* RenderPaint thickness * .5, at least FLT_MIN (draw.cpp:603-607) */
@@ -325,9 +326,14 @@ typedef struct rivecuda_path
     uint32_t cap;       /* rive::StrokeCap: butt 0, round 1, square 2 */
     float polar_segments_per_radian;
     float matrix_max_scale;
-    uint32_t blend_mode; /* gpu::ConvertBlendModeToPLSBlendMode(paint blend mode) (gpu.cpp:717): 0 = srcOver; a call with
-                          * any other mode must flush with RIVECUDA_FEATURE_ADVANCED_BLEND on the batch, as the
-                          * reference's batches do (DrawContents::advancedBlend) */
+    uint32_t blend_mode; /* bits 0-7: gpu::ConvertBlendModeToPLSBlendMode(paint blend mode) (gpu.cpp:717): 0 = srcOver; a call
+                          * with any other mode must flush with RIVECUDA_FEATURE_ADVANCED_BLEND on the batch, as the
+                          * reference's batches do (DrawContents::advancedBlend).
+                          * Clip PATHS (RiveRenderer::applyClip, rive_renderer.cpp:631-822): bits 16-31 = the clip ID
+                          * the draw is clipped against (0: none); bit 8 = the path is a clip UPDATE
+                          * (PaintType::clipUpdate): it writes clip ID bits 16-31 into the clip plane, nested in
+                          * `color`. Batches holding such paths carry RIVECUDA_FEATURE_CLIPPING (and
+                          * _NESTED_CLIPPING for nested updates), as the reference's do. */
 } rivecuda_path;
 
 /* A clip rectangle (RiveRenderer::clipRectImpl, rive_renderer.cpp:268-322) as a draw carries it

@@ -882,11 +882,21 @@ FE_HD void write_path_records(const rivecuda_path& path, uint32_t pathID, const 
     const rivecuda_clip_rect* clip = clipIndex != 0u && out.clipRects != nullptr ? out.clipRects + (clipIndex - 1u) : nullptr;
     const uint32_t fillRule = path.fill_rule & 0xffu, gradientIndex = path.fill_rule >> 8;
     const rivecuda_gradient_paint* gradient = gradientIndex != 0u && out.gradientPaints != nullptr ? out.gradientPaints + (gradientIndex - 1u) : nullptr;
-    out.paintData[static_cast<size_t>(pathID) * 2 + 0] =
-        (gradient != nullptr ? gradient->paint_type : kPaintTypeSolidColor) | ((path.blend_mode & 0xfu) << 4) |
-        (isStroke || fillRule == 2u ? 0u : fillRule == 1u ? kPaintFlagEvenOddFill : kPaintFlagNonZeroFill) |
-        (clip != nullptr ? kPaintFlagHasClipRect : 0u); // PaintData::set (gpu.cpp:879-939)
-    out.paintData[static_cast<size_t>(pathID) * 2 + 1] = gradient != nullptr ? bits(gradient->grad_texture_y) : rgba;
+    const uint32_t fillFlag = isStroke || fillRule == 2u ? 0u : fillRule == 1u ? kPaintFlagEvenOddFill : kPaintFlagNonZeroFill;
+    const uint32_t clipID = path.blend_mode >> 16;
+    if ((path.blend_mode & 0x100u) != 0u)
+    {
+        // PaintType::clipUpdate (0): [outerClipID | fill flag], the clip ID it writes (gpu.cpp:915-920)
+        out.paintData[static_cast<size_t>(pathID) * 2 + 0] = (path.color << 16) | fillFlag;
+        out.paintData[static_cast<size_t>(pathID) * 2 + 1] = clipID << 16;
+    }
+    else
+    {
+        out.paintData[static_cast<size_t>(pathID) * 2 + 0] =
+            (gradient != nullptr ? gradient->paint_type : kPaintTypeSolidColor) | (clipID << 16) | ((path.blend_mode & 0xfu) << 4) | fillFlag |
+            (clip != nullptr ? kPaintFlagHasClipRect : 0u); // PaintData::set (gpu.cpp:879-939)
+        out.paintData[static_cast<size_t>(pathID) * 2 + 1] = gradient != nullptr ? bits(gradient->grad_texture_y) : rgba;
+    }
     uint32_t aux[16] = {};
     store_words16(out.paintAux + static_cast<size_t>(pathID) * 32 + 16, aux);
     if (gradient != nullptr)

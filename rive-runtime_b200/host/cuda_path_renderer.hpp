@@ -15,7 +15,9 @@
  * there (draw.cpp:727-737); blend modes travel in the paint record; clip RECTANGLES (clipPath with an
  * axis-aligned rectangle, nested ones intersected) travel as a table the paths index; linear and
  * radial gradients get their colour ramps allocated here as LogicalFlush::allocateGradient does, and
- * travel as GradientSpans plus a table of paint records. Anything else -- clip paths, images, feathers --
+ * travel as GradientSpans plus a table of paint records; clip PATHS become clipUpdate paths in
+ * front of the draws that need them, under the clip IDs RiveRenderer::applyClip would hand out.
+ * Anything else -- images, feathers --
  * is not handled by the device front end: the renderer records the first such call
  * and flush() refuses the frame, so the caller can draw it with RiveRenderer (no silent fallback).
  */
@@ -105,14 +107,37 @@ public:
             // (draw.cpp:657-680) and the host gives its batch ShaderMiscFlags::clockwiseFill.
             p.fill_rule = path->getFillRule() == FillRule::evenOdd ? 1 : path->getFillRule() == FillRule::clockwise ? 2 : 0;
         }
+        const State& state = m_stack.back();
+        if (state.clipStackHeight != 0 || paint->getType() != PaintType::solidColor)
+        {
+            // A draw that PathDraw::Make (draw.cpp:439-509) or RiveRenderer::applyClip
+            // (rive_renderer.cpp:636-646) culls allocates no colour ramp and triggers no clip update:
+            // apply the cull the device would apply (the same code, built for the host) first.
+            static_assert(sizeof(Vec2D) == sizeof(rivecuda::fe::V2), "points are passed as they are");
+            rivecuda_clip_rect bounds;
+            memset(&bounds, 0, sizeof(bounds));
+            bounds.pixel_bounds[0] = state.overallClipPixelBounds.left;
+            bounds.pixel_bounds[1] = state.overallClipPixelBounds.top;
+            bounds.pixel_bounds[2] = state.overallClipPixelBounds.right;
+            bounds.pixel_bounds[3] = state.overallClipPixelBounds.bottom;
+            rivecuda_path probe = p;
+            probe.stroke = (p.stroke & 1u) | (1u << 8);
+            if (rivecuda::fe::is_outside_frame(probe, reinterpret_cast<const rivecuda::fe::V2*>(raw.points().data()), static_cast<uint32_t>(raw.points().size()),
+                                               m_target->width(), m_target->height(), &bounds))
+                return;
+        }
+        if (state.clipStackHeight != 0)
+        {
+            const uint32_t clipID = applyClip(state.clipStackHeight);
+            if (clipID == 0)
+                return refuse("drawPath under more clip updates than one flush has clip IDs");
+            p.blend_mode |= clipID << 16;
+            // (applyClip appended the clip updates' verbs and points)
+            p.first_verb = static_cast<uint32_t>(m_verbs.size());
+            p.first_point = static_cast<uint32_t>(m_points.size());
+        }
         if (paint->getType() != PaintType::solidColor)
         {
-            // A draw PathDraw::Make culls (draw.cpp:439-509) never allocates a colour ramp: apply the
-            // cull the device would apply (the same code, built for the host) before allocating.
-            static_assert(sizeof(Vec2D) == sizeof(rivecuda::fe::V2), "points are passed as they are");
-            if (rivecuda::fe::is_outside_frame(p, reinterpret_cast<const rivecuda::fe::V2*>(raw.points().data()), static_cast<uint32_t>(raw.points().size()),
-                                               m_target->width(), m_target->height(), m_clipRects.data()))
-                return;
             // PathDraw keeps the gradient with the modulated opacity folded into its colours
             // (draw.cpp:580) and allocates its colour ramp when the draw is pushed.
             GradientDraw draw;
@@ -145,10 +170,7 @@ public:
         }
         AABB rect;
         if (!RiveRenderer::IsAABB(path->getRawPath(), &rect))
-        {
-            refuse("clipPath with something other than an axis-aligned rectangle");
-            return;
-        }
+            return clipPathImpl(path);
         if (rect.isEmptyOrNaN())
         {
             state.overallClipPixelBounds = {};
@@ -160,18 +182,12 @@ public:
             // only if it is still a rectangle there (transform_rect_to_new_space).
             Mat2D currentToNew;
             if (!state.clipRectMatrix.invert(&currentToNew))
-            {
-                refuse("clipPath: nested clip rectangle under a singular matrix");
-                return;
-            }
+                return clipPathImpl(path); // not a rectangle in the first one's space: a clip path
             currentToNew = currentToNew * state.matrix;
             const float maxSkew = fmaxf(fabsf(currentToNew.xy()), fabsf(currentToNew.yx()));
             const float maxScale = fmaxf(fabsf(currentToNew.xx()), fabsf(currentToNew.yy()));
             if (maxSkew > math::EPSILON && maxScale > math::EPSILON)
-            {
-                refuse("clipPath: nested clip rectangle that is not axis-aligned with the first");
-                return;
-            }
+                return clipPathImpl(path);
             Vec2D pts[2] = {{rect.left(), rect.top()}, {rect.right(), rect.bottom()}};
             currentToNew.mapPoints(pts, pts, 2);
             rect = {std::min(pts[0].x, pts[1].x), std::min(pts[0].y, pts[1].y), std::max(pts[0].x, pts[1].x), std::max(pts[0].y, pts[1].y)};
@@ -243,6 +259,7 @@ public:
         frame.pathCount = m_paths.size();
         frame.clipRects = m_clipRects.data();
         frame.clipRectCount = m_clipRects.size();
+        frame.hasClipPaths = m_hasClipPaths;
         std::vector<GradientSpan> gradSpans;
         std::vector<rivecuda_gradient_paint> gradientPaints;
         if (!m_gradientDraws.empty())
@@ -286,6 +303,88 @@ public:
     }
 
 private:
+    // RiveRenderer::clipPathImpl (rive_renderer.cpp:322-381): the clip stack is shared by all states
+    // (a state holds its height), so that a path clipped again after a restore() reuses its element
+    // -- and the clip it may still have in the clip plane.
+    void clipPathImpl(const RiveRenderPath* path)
+    {
+        State& state = m_stack.back();
+        if (path->getBounds().isEmptyOrNaN())
+        {
+            state.overallClipPixelBounds = {};
+            return;
+        }
+        const size_t height = state.clipStackHeight;
+        if (m_clipStack.size() == height || !m_clipStack[height].isEquivalent(state.matrix, path))
+        {
+            const IAABB pixelBounds = state.matrix.mapBoundingBox(path->getRawPath().points()).roundOut();
+            state.overallClipPixelBounds = state.overallClipPixelBounds.intersect(pixelBounds);
+            if (state.overallClipPixelBounds.empty())
+                return;
+            m_clipStack.resize(height);
+            ClipElement element;
+            element.matrix = state.matrix;
+            element.path = ref_rcp(path);
+            element.rawPathMutationID = path->getRawPathMutationID();
+            element.fillRule = path->getFillRule();
+            element.pixelBounds = pixelBounds;
+            m_clipStack.push_back(std::move(element));
+        }
+        else
+        {
+            state.overallClipPixelBounds = state.overallClipPixelBounds.intersect(m_clipStack[height].pixelBounds);
+            if (state.overallClipPixelBounds.empty())
+                return;
+        }
+        state.clipStackHeight = height + 1;
+        m_hasClipPaths = true;
+    }
+
+    // RiveRenderer::applyClip in rasterOrdering mode (rive_renderer.cpp:648-822): every clip element
+    // above the one currently in the clip plane is drawn as a PaintType::clipUpdate path, nested in
+    // its predecessor, under a fresh clip ID. Returns the clip ID the draw is clipped against.
+    uint32_t applyClip(size_t clipStackHeight)
+    {
+        size_t current = static_cast<size_t>(-1);
+        if (m_clipContentID != 0)
+        {
+            for (size_t i = clipStackHeight - 1; i != static_cast<size_t>(-1); --i)
+            {
+                if (m_clipStack[i].clipID == m_clipContentID)
+                {
+                    current = i;
+                    break;
+                }
+            }
+        }
+        uint32_t parentClipID = current == static_cast<size_t>(-1) ? 0u : m_clipStack[current].clipID;
+        for (size_t i = current + 1; i < clipStackHeight; ++i)
+        {
+            ClipElement& clip = m_clipStack[i];
+            if (m_clipCount >= kMaxClipID)
+                return 0;
+            clip.clipID = ++m_clipCount; // LogicalFlush::generateClipID (render_context.cpp:480-492)
+            const RawPath& raw = clip.path->getRawPath();
+            rivecuda_path c;
+            memset(&c, 0, sizeof(c));
+            c.first_verb = static_cast<uint32_t>(m_verbs.size());
+            c.verb_count = static_cast<uint32_t>(raw.verbs().size());
+            c.first_point = static_cast<uint32_t>(m_points.size());
+            for (int k = 0; k < 6; ++k)
+                c.matrix[k] = clip.matrix[k];
+            c.fill_rule = clip.fillRule == FillRule::evenOdd ? 1 : clip.fillRule == FillRule::clockwise ? 2 : 0;
+            c.color = parentClipID;                      // RiveRenderPaint::clipUpdate(outerClipID)
+            c.blend_mode = 0x100u | (clip.clipID << 16); // Draw::setClipID
+            for (PathVerb v : raw.verbs())
+                m_verbs.push_back(static_cast<uint8_t>(v));
+            m_points.insert(m_points.end(), raw.points().begin(), raw.points().end());
+            m_paths.push_back(c);
+            parentClipID = clip.clipID;
+        }
+        m_clipContentID = parentClipID;
+        return parentClipID;
+    }
+
     // LogicalFlush::allocateGradient (render_context.cpp:588-674): two-stop 0..1 (and one-stop)
     // gradients share two-texel ramps keyed by their colours, everything else gets a row of its own,
     // shared by gradients of equal content.
@@ -404,7 +503,27 @@ private:
         AABB clipRect;
         Mat2D clipRectMatrix;
         uint32_t clipRectIndex = 0; // 1 + index into m_clipRects of the state's rectangle
+        size_t clipStackHeight = 0; // clip PATHS: how much of m_clipStack applies to this state
     };
+    // RiveRenderer::ClipElement (rive_renderer.hpp:52-72)
+    struct ClipElement
+    {
+        Mat2D matrix;
+        rcp<const RiveRenderPath> path;
+        uint64_t rawPathMutationID = 0;
+        FillRule fillRule = FillRule::nonZero;
+        IAABB pixelBounds;
+        uint32_t clipID = 0; // assigned every time the element is (re-)rendered to the clip plane
+        bool isEquivalent(const Mat2D& matrix_, const RiveRenderPath* path_) const
+        {
+            return matrix_ == matrix && path_->getRawPathMutationID() == rawPathMutationID && path_->getFillRule() == fillRule;
+        }
+    };
+    constexpr static uint32_t kMaxClipID = 30720; // maxClipID == maxPathID (render_context.cpp:484)
+    std::vector<ClipElement> m_clipStack;
+    uint32_t m_clipContentID = 0; // RenderContext::getClipContentID(): the clip ID now in the clip plane
+    uint32_t m_clipCount = 0;
+    bool m_hasClipPaths = false;
     std::vector<State> m_stack{State()};
     std::vector<Vec2D> m_points;
     std::vector<uint8_t> m_verbs;

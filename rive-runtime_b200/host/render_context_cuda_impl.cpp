@@ -504,6 +504,13 @@ bool RenderContextCUDAImpl::flushPlainPaths(const PlainPathFrame& frame)
         const size_t count = std::min(chunk, frame.pathCount - first);
         rivecuda_front_end_result needed;
         const int status = flushPlainPathChunk(frame, first, count, firstFlush, &needed);
+        if (status == RIVECUDA_STATUS_EXCEEDS_FLUSH && frame.hasClipPaths)
+        {
+            // The reference re-renders the clips after starting a new logical flush; the clip IDs
+            // CudaPathRenderer handed out assume one flush.
+            fprintf(stderr, "RenderContextCUDAImpl::flushPlainPaths: a frame with clip paths must fit one flush\n");
+            return false;
+        }
         if (status == RIVECUDA_STATUS_EXCEEDS_FLUSH && count > 1)
         {
             // Scale the chunk by what did not fit (with a little slack), at least halving it.
@@ -625,19 +632,24 @@ int RenderContextCUDAImpl::flushPlainPathChunk(const PlainPathFrame& frame, size
         return batch;
     };
     auto add_features = [](rivecuda_draw_batch& batch, const rivecuda_path& path) {
-        if (path.blend_mode != 0u)
-            batch.shader_features |= RIVECUDA_FEATURE_ADVANCED_BLEND | (path.blend_mode >= 12u ? RIVECUDA_FEATURE_HSL_BLEND_MODES : 0u);
+        const uint32_t blendMode = path.blend_mode & 0xffu;
+        if (blendMode != 0u)
+            batch.shader_features |= RIVECUDA_FEATURE_ADVANCED_BLEND | (blendMode >= 12u ? RIVECUDA_FEATURE_HSL_BLEND_MODES : 0u);
         if ((path.stroke >> 8) != 0u)
             batch.shader_features |= RIVECUDA_FEATURE_CLIP_RECT; // DrawContents::clipRect... -> ENABLE_CLIP_RECT
-        if ((path.stroke & 1u) == 0u && path.fill_rule == 1u)
+        if ((path.stroke & 1u) == 0u && (path.fill_rule & 0xffu) == 1u)
             batch.shader_features |= RIVECUDA_FEATURE_EVEN_ODD; // pushPathDraw, render_context.cpp:3655-3660
+        if ((path.blend_mode >> 16) != 0u)
+            batch.shader_features |= RIVECUDA_FEATURE_CLIPPING; // pushDraw, render_context.cpp:4012-4015
+        if ((path.blend_mode & 0x100u) != 0u && path.color != 0u)
+            batch.shader_features |= RIVECUDA_FEATURE_NESTED_CLIPPING; // clipUpdate | activeClip (pushPathDraw)
     };
     bool anyClockwise = false, anyOtherFill = false;
     for (size_t i = 0; i < pathCount; ++i)
     {
         const rivecuda_path& path = frame.paths[firstPath + i];
         if ((path.stroke & 1u) == 0u)
-            (path.fill_rule == 2u ? anyClockwise : anyOtherFill) = true;
+            ((path.fill_rule & 0xffu) == 2u ? anyClockwise : anyOtherFill) = true;
     }
     std::vector<rivecuda_draw_batch> batches;
     if (r.patch_count != 0 && !(anyClockwise && anyOtherFill))
@@ -663,7 +675,7 @@ int RenderContextCUDAImpl::flushPlainPathChunk(const PlainPathFrame& frame, size
             if (patches == 0)
                 continue; // culled, or nothing to draw
             const bool isFill = (path.stroke & 1u) == 0u;
-            const uint32_t misc = isFill && path.fill_rule == 2u ? RIVECUDA_MISC_CLOCKWISE_FILL : 0u;
+            const uint32_t misc = isFill && (path.fill_rule & 0xffu) == 2u ? RIVECUDA_MISC_CLOCKWISE_FILL : 0u;
             if (batches.empty() || (isFill && batchHasFills && batches.back().shader_misc_flags != misc))
             {
                 batches.push_back(new_batch(firstPatch[i]));

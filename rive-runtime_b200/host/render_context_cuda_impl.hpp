@@ -166,6 +166,9 @@ public:
         uint32_t gradDataHeight = 0;
         const rivecuda_gradient_paint* gradientPaints = nullptr;
         size_t gradientPaintCount = 0;
+        // Clip paths: the frame holds clipUpdate paths and clip IDs (rivecuda_path::blend_mode);
+        // they are valid within one flush, so such a frame is not split.
+        bool hasClipPaths = false;
     };
     bool flushPlainPaths(const PlainPathFrame&);
     // Grows the gradient texture to hold `rows` rows the way RenderContext does (125% of what is

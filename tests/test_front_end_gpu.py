@@ -102,7 +102,7 @@ def test_device_front_end_equals_its_host_build_on_random_paths(built, seed, n_p
         assert np.array_equal(F.read_buffer(rp, 2, n * 8).view(np.uint32).reshape(-1, 2)[1:], want.paint_data[1:n])
 
 
-@pytest.mark.parametrize("scene,golden", [("c2", "c2_4k"), ("f1", "f1"), ("f1o", "f1o"), ("f1b", "f1b"), ("f1c", "f1c"), ("f1w", "f1w"), ("f1g", "f1g"), ("s1", "s1"), ("gm:trickycubicstrokes", "trickycubicstrokes"),
+@pytest.mark.parametrize("scene,golden", [("c2", "c2_4k"), ("f1", "f1"), ("f1o", "f1o"), ("f1b", "f1b"), ("f1c", "f1c"), ("f1w", "f1w"), ("f1g", "f1g"), ("f1p", "f1p"), ("s1", "s1"), ("gm:trickycubicstrokes", "trickycubicstrokes"),
                                           ("gm:strokes3", "strokes3")])
 def test_cpp_path_renderer_draws_the_same_frame(built, scene, golden):
     """SURVEY 8 f1 in the compiled host: the scene player with --gpu-front-end draws through
@@ -127,11 +127,11 @@ def test_cpp_path_renderer_draws_the_same_frame(built, scene, golden):
     assert px.size == want.size and np.array_equal(px.reshape(want.shape), want)
 
 
-@pytest.mark.parametrize("name", ["shapetest", "fix_rectangle", "follow_path_solos", "trim_path_linear", "magic_alley_db_reduced_export",
+@pytest.mark.parametrize("name", ["off_road_car", "bullet_man", "shapetest", "fix_rectangle", "follow_path_solos", "trim_path_linear", "magic_alley_db_reduced_export",
                                   "nested_artboard_opacity", "lock_icon_demo", "follow_path_shapes", "solos_collapse_tests", "group_effect"])
 def test_riv_file_through_the_device_front_end(built, name):
-    """Real .riv content (clockwise and nonZero fills, strokes, opacity, artboard clip rectangles)
-    through --gpu-front-end: frame 20 must equal, bit for bit, the frame the reference's CPU front
+    """Real .riv content (clockwise and nonZero fills, strokes, opacity, artboard clip rectangles;
+    off_road_car and bullet_man: gradients and nested clip paths too) through --gpu-front-end: frame 20 must equal, bit for bit, the frame the reference's CPU front
     end produces for the same file through the same backend (midpoint fans only: --budget-ms 0
     switches the reference's interior triangulation of large paths off, which the device front end
     does not implement). tests/tools/riv_front_end_sweep.py runs the same comparison over a whole
