@@ -323,7 +323,8 @@ typedef struct rivecuda_path
                          * rivecuda_front_end_clip_rects (0: not clipped by a rectangle) */
     float stroke_radius; /* RenderPaint thickness * .5, at least FLT_MIN (draw.cpp:603-607) */
     uint32_t join;      /* rive::StrokeJoin: miter 0, round 1, bevel 2 */
-    uint32_t cap;       /* rive::StrokeCap: butt 0, round 1, square 2 */
+    uint32_t cap;       /* bits 0-7: rive::StrokeCap: butt 0, round 1, square 2; bits 8-31: 1 + index of the path's image
+                         * paint in the table passed to rivecuda_front_end_image_paints (0: no image) */
     float polar_segments_per_radian;
     float matrix_max_scale;
     uint32_t blend_mode; /* bits 0-7: gpu::ConvertBlendModeToPLSBlendMode(paint blend mode) (gpu.cpp:717): 0 = srcOver; a call
@@ -406,6 +407,18 @@ typedef struct rivecuda_gradient_paint
     float grad_horizontal_span[2];
 } rivecuda_gradient_paint;
 int rivecuda_front_end_gradient_paints(rivecuda_ctx* ctx, const rivecuda_gradient_paint* paints, uint32_t count);
+/* An image paint (RenderPaint::modulatedImage / RiveRenderer::drawImage: the image modulates the
+ * path's colour or gradient) of the next rivecuda_front_end_paths() call (copied): the words
+ * PaintAuxData::set (gpu.cpp:1001-1033) computes for it. The path's record gets PAINT_FLAG_HAS_IMAGE;
+ * its batch carries the texture, the sampler and RIVECUDA_FEATURE_MODULATED_IMAGE, and holds draws
+ * of one (texture, sampler) only (can_combine_draw_images, render_context.cpp:3702-3717). */
+typedef struct rivecuda_image_paint
+{
+    float image_matrix[6]; /* pixel -> normalised image space */
+    float image_texture_lod;
+    uint32_t reserved0;
+} rivecuda_image_paint;
+int rivecuda_front_end_image_paints(rivecuda_ctx* ctx, const rivecuda_image_paint* paints, uint32_t count);
 /* first_patch[i] = the first midpoint-fan patch (DrawBatch::baseElement) of path i of the last
  * rivecuda_front_end_paths() call, for i in [0, path_count]; a culled path's equals its
  * successor's, entry path_count is the end of the last path. A frame whose fills mix clockwise

@@ -56,6 +56,7 @@ SIGNATURES = {
     "rivecuda_front_end_clip_rects": (_int, [_vp, _vp, _u32]),
     "rivecuda_front_end_path_patches": (_int, [_vp, _vp, _u32]),
     "rivecuda_front_end_gradient_paints": (_int, [_vp, _vp, _u32]),
+    "rivecuda_front_end_image_paints": (_int, [_vp, _vp, _u32]),
     "rivecuda_band_unique_id": (_int, [_vp]),
     "rivecuda_band_init": (_int, [_vp, _u32, _u32, _vp]),
     "rivecuda_band_rows": (_int, [_u32, _u32, _u32, ctypes.POINTER(_u32), ctypes.POINTER(_u32)]),

@@ -409,12 +409,12 @@ FE_HD ContourCtx make_contour_ctx(const rivecuda_path& path, const V2* pts, uint
     bool needsCaps;
     if (!ctx.empty)
     {
-        cap = path.cap;
+        cap = path.cap & 0xffu;
         needsCaps = !ctx.closed;
     }
     else
     {
-        cap = empty_stroke_cap(ctx.closed, path.join, path.cap);
+        cap = empty_stroke_cap(ctx.closed, path.join, path.cap & 0xffu);
         needsCaps = cap != kCapButt;
     }
     if (needsCaps)
@@ -430,7 +430,7 @@ FE_HD ContourCtx make_contour_ctx(const rivecuda_path& path, const V2* pts, uint
         {
             ctx.capSegments = kMiterOrBevelJoinSegments;
         }
-        const uint32_t flagCap = !ctx.closed ? path.cap : empty_stroke_cap(true, path.join, path.cap);
+        const uint32_t flagCap = !ctx.closed ? (path.cap & 0xffu) : empty_stroke_cap(true, path.join, path.cap & 0xffu);
         ctx.capFlags = (flagCap == kCapButt ? kFlagBevelJoin : flagCap == kCapSquare ? kFlagMiterClipJoin : kFlagRoundJoin) | kFlagEmulatedStrokeCap;
     }
     return ctx;
@@ -692,7 +692,7 @@ FE_HD bool is_outside_frame(const rivecuda_path& path, Box box, uint32_t frameWi
         float outset = path.stroke_radius;
         if (path.join == kJoinMiter)
             outset *= 4.f; // RIVE_MITER_LIMIT
-        else if (path.cap == kCapSquare)
+        else if ((path.cap & 0xffu) == kCapSquare)
             outset *= 1.41421356f; // math::SQRT2
         const V2 corners[4] = {{0.f, 0.f}, {outset, 0.f}, {outset, outset}, {0.f, outset}};
         const Box o = map_bounding_box(path.matrix, corners, 4);
@@ -765,6 +765,7 @@ struct FrontEndOut
     uint32_t* paintAux;  // PaintAuxData, 32 words
     const rivecuda_clip_rect* clipRects = nullptr; // the table paths' clip indices refer to
     const rivecuda_gradient_paint* gradientPaints = nullptr; // the table paths' gradient indices refer to
+    const rivecuda_image_paint* imagePaints = nullptr;       // the table paths' image indices refer to
     uint32_t spanBase;   // spans [0, spanBase) are the flush's padding spans
 };
 
@@ -864,7 +865,7 @@ FE_HD bool is_forward_then_reverse(const rivecuda_path& path)
     return det < 0.f;
 }
 
-constexpr uint32_t kPaintTypeSolidColor = 1, kPaintFlagNonZeroFill = 0x100, kPaintFlagEvenOddFill = 0x200, kPaintFlagHasClipRect = 0x400; // constants.glsl
+constexpr uint32_t kPaintTypeSolidColor = 1, kPaintFlagNonZeroFill = 0x100, kPaintFlagEvenOddFill = 0x200, kPaintFlagHasClipRect = 0x400, kPaintFlagHasImage = 0x800; // constants.glsl
 
 // pushPath: PathData / PaintData / PaintAuxData (gpu.cpp:859-1063) for a solid colour.
 FE_HD void write_path_records(const rivecuda_path& path, uint32_t pathID, const FrontEndOut& out)
@@ -884,6 +885,8 @@ FE_HD void write_path_records(const rivecuda_path& path, uint32_t pathID, const 
     const rivecuda_gradient_paint* gradient = gradientIndex != 0u && out.gradientPaints != nullptr ? out.gradientPaints + (gradientIndex - 1u) : nullptr;
     const uint32_t fillFlag = isStroke || fillRule == 2u ? 0u : fillRule == 1u ? kPaintFlagEvenOddFill : kPaintFlagNonZeroFill;
     const uint32_t clipID = path.blend_mode >> 16;
+    const uint32_t imageIndex = path.cap >> 8;
+    const rivecuda_image_paint* image = imageIndex != 0u && out.imagePaints != nullptr ? out.imagePaints + (imageIndex - 1u) : nullptr;
     if ((path.blend_mode & 0x100u) != 0u)
     {
         // PaintType::clipUpdate (0): [outerClipID | fill flag], the clip ID it writes (gpu.cpp:915-920)
@@ -894,11 +897,20 @@ FE_HD void write_path_records(const rivecuda_path& path, uint32_t pathID, const 
     {
         out.paintData[static_cast<size_t>(pathID) * 2 + 0] =
             (gradient != nullptr ? gradient->paint_type : kPaintTypeSolidColor) | (clipID << 16) | ((path.blend_mode & 0xfu) << 4) | fillFlag |
-            (clip != nullptr ? kPaintFlagHasClipRect : 0u); // PaintData::set (gpu.cpp:879-939)
+            (clip != nullptr ? kPaintFlagHasClipRect : 0u) | (image != nullptr ? kPaintFlagHasImage : 0u); // PaintData::set (gpu.cpp:879-939)
         out.paintData[static_cast<size_t>(pathID) * 2 + 1] = gradient != nullptr ? bits(gradient->grad_texture_y) : rgba;
     }
     uint32_t aux[16] = {};
+    if (image != nullptr)
+    {
+        // PaintAuxData::m_imageMatrix, m_imageTextureLOD (gpu.cpp:1001-1033)
+        for (int i = 0; i < 6; ++i)
+            aux[i] = bits(image->image_matrix[i]);
+        aux[6] = bits(image->image_texture_lod);
+    }
     store_words16(out.paintAux + static_cast<size_t>(pathID) * 32 + 16, aux);
+    for (int i = 0; i < 7; ++i)
+        aux[i] = 0u;
     if (gradient != nullptr)
     {
         // PaintAuxData::m_paintMatrix, m_gradTextureHorizontalSpan (gpu.cpp:951-999)

@@ -176,7 +176,8 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) front_end_count_kernel(co
                                                                                uint32_t* __restrict__ ownTessVertices,
                                                                                const rivecuda_clip_rect* __restrict__ clipRects,
                                                                                uint32_t clipRectCount,
-                                                                               uint32_t gradientPaintCount)
+                                                                               uint32_t gradientPaintCount,
+                                                                               uint32_t imagePaintCount)
 {
     const int lane = threadIdx.x & 31;
     const uint32_t i = blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
@@ -202,7 +203,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) front_end_count_kernel(co
                 atomicOr(badPathFlag, 1u);
             culled = true;
         }
-        else if ((path.stroke >> 8) > clipRectCount || (path.fill_rule >> 8) > gradientPaintCount)
+        else if ((path.stroke >> 8) > clipRectCount || (path.fill_rule >> 8) > gradientPaintCount || (path.cap >> 8) > imagePaintCount)
         {
             // A clip rectangle / gradient paint the caller did not pass: touch nothing, report it.
             if (lane == 0)
@@ -532,6 +533,14 @@ int rivecuda_front_end_gradient_paints(rivecuda_ctx* ctx, const rivecuda_gradien
     return 0;
 }
 
+int rivecuda_front_end_image_paints(rivecuda_ctx* ctx, const rivecuda_image_paint* paints, uint32_t count)
+{
+    if (ctx == nullptr || (count != 0 && paints == nullptr))
+        return set_error("rivecuda_front_end_image_paints: bad arguments");
+    ctx->frontEndImagePaints.assign(paints, paints + count);
+    return 0;
+}
+
 int rivecuda_front_end_paths(rivecuda_ctx* ctx,
                              const float* points_xy,
                              uint32_t point_count,
@@ -570,7 +579,9 @@ int rivecuda_front_end_paths(rivecuda_ctx* ctx,
     const size_t clipBytes = ctx->frontEndClipRects.size() * sizeof(rivecuda_clip_rect);
     const size_t gradientOffset = (clipOffset + clipBytes + 15) & ~size_t(15);
     const size_t gradientBytes = ctx->frontEndGradientPaints.size() * sizeof(rivecuda_gradient_paint);
-    if (int s = ctx->frontEnd.reserve(gradientOffset + gradientBytes))
+    const size_t imageOffset = (gradientOffset + gradientBytes + 15) & ~size_t(15);
+    const size_t imageBytes = ctx->frontEndImagePaints.size() * sizeof(rivecuda_image_paint);
+    if (int s = ctx->frontEnd.reserve(imageOffset + imageBytes))
         return s;
     uint8_t* base = ctx->frontEnd.as<uint8_t>();
     V2* dPoints = reinterpret_cast<V2*>(base);
@@ -600,6 +611,14 @@ int rivecuda_front_end_paths(rivecuda_ctx* ctx,
     {
         RC_CUDA(cudaMemcpyAsync(base + gradientOffset, ctx->frontEndGradientPaints.data(), gradientBytes, cudaMemcpyHostToDevice, stream));
         dGradientPaints = reinterpret_cast<const rivecuda_gradient_paint*>(base + gradientOffset);
+    }
+
+    const rivecuda_image_paint* dImagePaints = nullptr;
+    const uint32_t imagePaintCount = static_cast<uint32_t>(ctx->frontEndImagePaints.size());
+    if (imageBytes != 0)
+    {
+        RC_CUDA(cudaMemcpyAsync(base + imageOffset, ctx->frontEndImagePaints.data(), imageBytes, cudaMemcpyHostToDevice, stream));
+        dImagePaints = reinterpret_cast<const rivecuda_image_paint*>(base + imageOffset);
     }
 
     // The five buffers this front end fills, at the sizes the worst case needs (a stroked cubic
@@ -643,6 +662,7 @@ int rivecuda_front_end_paths(rivecuda_ctx* ctx,
     out.spanBase = 0;
     out.clipRects = dClipRects;
     out.gradientPaints = dGradientPaints;
+    out.imagePaints = dImagePaints;
     // Record 0 of path / paint / paintAux is the flush's reserved (clear colour) record.
     RC_CUDA(cudaMemsetAsync(out.pathData, 0, 64, stream));
     RC_CUDA(cudaMemsetAsync(out.paintData, 0, 8, stream));
@@ -653,7 +673,7 @@ int rivecuda_front_end_paths(rivecuda_ctx* ctx,
     uint32_t* field = reinterpret_cast<uint32_t*>(dTotals);
     if (path_count != 0)
     {
-        front_end_count_kernel<<<blocks, kWarpsPerBlock * 32, 0, stream>>>(dPaths, path_count, dPoints, dVerbs, frame_width, frame_height, point_count, dSums + 6, dTotals, dOwn, dClipRects, clipRectCount, gradientPaintCount);
+        front_end_count_kernel<<<blocks, kWarpsPerBlock * 32, 0, stream>>>(dPaths, path_count, dPoints, dVerbs, frame_width, frame_height, point_count, dSums + 6, dTotals, dOwn, dClipRects, clipRectCount, gradientPaintCount, imagePaintCount);
         front_end_scan3_kernel<<<1, 1024, 0, stream>>>(reinterpret_cast<uint4*>(dTotals), path_count, dSums);
     }
     else

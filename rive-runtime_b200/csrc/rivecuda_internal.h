@@ -173,6 +173,7 @@ struct rivecuda_ctx
         scanScratch, clipPlane, pathImageSlots, atlasTable, binCount, binPairs, hugeList, frontEnd;
     size_t frontEndTotalsOffset = 0;   // of the last rivecuda_front_end_paths call: where its scanned PathTotals live
     uint32_t frontEndPathCount = 0, frontEndTessVertices = 0;
+    std::vector<rivecuda_image_paint> frontEndImagePaints;       // rivecuda_front_end_image_paints: likewise
     std::vector<rivecuda_gradient_paint> frontEndGradientPaints; // rivecuda_front_end_gradient_paints: for the next rivecuda_front_end_paths
     std::vector<rivecuda_clip_rect> frontEndClipRects; // rivecuda_front_end_clip_rects: for the next rivecuda_front_end_paths
     uint32_t* pinnedTotals = nullptr; // pinned host words for small D2H results

@@ -256,6 +256,7 @@ int rivecuda_target_read_wait(rivecuda_ctx*, rivecuda_target*) { return 0; }
 //   rivecuda_path paths[]; u8 verbs[] (padded to 4); float points[][2]
 int rivecuda_front_end_clip_rects(rivecuda_ctx*, const rivecuda_clip_rect*, uint32_t) { return 0; } // (not part of the dump format)
 int rivecuda_front_end_gradient_paints(rivecuda_ctx*, const rivecuda_gradient_paint*, uint32_t) { return 0; } // (not part of the dump format)
+int rivecuda_front_end_image_paints(rivecuda_ctx*, const rivecuda_image_paint*, uint32_t) { return 0; }       // (not part of the dump format)
 int rivecuda_front_end_path_patches(rivecuda_ctx*, uint32_t*, uint32_t) { return 1; }                     // (needs the device)
 int rivecuda_front_end_paths(rivecuda_ctx*,
                              const float* points,

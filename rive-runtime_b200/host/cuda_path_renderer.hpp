@@ -16,8 +16,9 @@
  * axis-aligned rectangle, nested ones intersected) travel as a table the paths index; linear and
  * radial gradients get their colour ramps allocated here as LogicalFlush::allocateGradient does, and
  * travel as GradientSpans plus a table of paint records; clip PATHS become clipUpdate paths in
- * front of the draws that need them, under the clip IDs RiveRenderer::applyClip would hand out.
- * Anything else -- images, feathers --
+ * front of the draws that need them, under the clip IDs RiveRenderer::applyClip would hand out;
+ * image paints and drawImage travel as a table of image matrices, their textures on the batches.
+ * Anything else -- feathers, image meshes --
  * is not handled by the device front end: the renderer records the first such call
  * and flush() refuses the frame, so the caller can draw it with RiveRenderer (no silent fallback).
  */
@@ -35,6 +36,7 @@
 #include "rive_render_paint.hpp"
 #include "rive_render_path.hpp"
 #include "rive/renderer/rive_renderer.hpp"
+#include "rive/renderer/rive_render_image.hpp"
 
 #include <algorithm>
 #include <array>
@@ -75,8 +77,6 @@ public:
             return refuse("drawPath with a feather");
         if (paint->getType() != PaintType::solidColor && paint->getType() != PaintType::linearGradient && paint->getType() != PaintType::radialGradient)
             return refuse("drawPath with an unknown paint type");
-        if (paint->getImageTexture() != nullptr)
-            return refuse("drawPath with an image paint");
         if (m_stack.back().overallClipPixelBounds.empty())
             return; // rive_renderer.cpp:151
         const Mat2D& m = m_stack.back().matrix;
@@ -135,6 +135,27 @@ public:
             // (applyClip appended the clip updates' verbs and points)
             p.first_verb = static_cast<uint32_t>(m_verbs.size());
             p.first_point = static_cast<uint32_t>(m_points.size());
+        }
+        if (paint->getImageTexture() != nullptr)
+        {
+            // An image paint (RenderPaint::modulatedImage, or drawImage below): the words
+            // PaintAuxData::set computes for it (gpu.cpp:1001-1033), by the reference's own writer.
+            const Mat2D imageMatrix = m * paint->getImageTransform(); // rive_renderer.cpp:156-162
+            PaintAuxData aux;
+            aux.set(m, imageMatrix, PaintType::solidColor, SimplePaintValue(), nullptr, paint->getImageTexture(), nullptr, m_target, m_impl->platformFeatures());
+            float words[32];
+            memcpy(words, &aux, sizeof(words));
+            rivecuda_image_paint record;
+            memcpy(record.image_matrix, words + 16, 24);
+            record.image_texture_lod = words[22];
+            record.reserved0 = 0;
+            m_imagePaints.push_back(record);
+            RenderContextCUDAImpl::PlainImageBinding binding;
+            binding.texture = static_cast<const TextureCUDA*>(paint->getImageTexture())->handle();
+            binding.samplerKey = paint->getImageSampler().asKey();
+            m_imageBindings.push_back(binding);
+            m_imageTextures.push_back(ref_rcp(paint->getImageTexture()));
+            p.cap |= static_cast<uint32_t>(m_imagePaints.size()) << 8;
         }
         if (paint->getType() != PaintType::solidColor)
         {
@@ -221,7 +242,32 @@ public:
         m_clipRects.push_back(record);
         state.clipRectIndex = static_cast<uint32_t>(m_clipRects.size());
     }
-    void drawImage(const RenderImage*, ImageSampler, BlendMode, float) override { refuse("drawImage"); }
+    // RiveRenderer::drawImage (rive_renderer.cpp:383-446): the unit rectangle under a matrix scaled
+    // by the image size, with an image paint. (The opacity goes through drawPath's modulation again,
+    // as it does in the reference.)
+    void drawImage(const RenderImage* renderImage, ImageSampler sampler, BlendMode blendMode, float opacity) override
+    {
+        auto* image = static_cast<const RiveRenderImage*>(renderImage);
+        rcp<Texture> texture = image->refTexture();
+        if (texture == nullptr)
+            return;
+        const float finalOpacity = std::max(0.0f, opacity * m_stack.back().opacity);
+        save();
+        transform(Mat2D::fromScale(static_cast<float>(image->width()), static_cast<float>(image->height())));
+        if (m_unitRectPath == nullptr)
+        {
+            m_unitRectPath = make_rcp<RiveRenderPath>();
+            m_unitRectPath->line({1, 0});
+            m_unitRectPath->line({1, 1});
+            m_unitRectPath->line({0, 1});
+        }
+        RiveRenderPaint paint;
+        paint.image(std::move(texture), finalOpacity);
+        paint.blendMode(blendMode);
+        paint.imageSampler(sampler);
+        drawPath(m_unitRectPath.get(), &paint);
+        restore();
+    }
     void drawImageMesh(const RenderImage*,
                        ImageSampler,
                        rcp<RenderBuffer>,
@@ -260,6 +306,9 @@ public:
         frame.clipRects = m_clipRects.data();
         frame.clipRectCount = m_clipRects.size();
         frame.hasClipPaths = m_hasClipPaths;
+        frame.imagePaints = m_imagePaints.data();
+        frame.imageBindings = m_imageBindings.data();
+        frame.imagePaintCount = m_imagePaints.size();
         std::vector<GradientSpan> gradSpans;
         std::vector<rivecuda_gradient_paint> gradientPaints;
         if (!m_gradientDraws.empty())
@@ -529,6 +578,11 @@ private:
     std::vector<uint8_t> m_verbs;
     std::vector<rivecuda_path> m_paths;
     std::vector<rivecuda_clip_rect> m_clipRects;
+    // image paints, indexed (1-based) from rivecuda_path::cap >> 8
+    std::vector<rivecuda_image_paint> m_imagePaints;
+    std::vector<RenderContextCUDAImpl::PlainImageBinding> m_imageBindings;
+    std::vector<rcp<Texture>> m_imageTextures; // alive until the flush
+    rcp<RiveRenderPath> m_unitRectPath;
     struct GradientDraw
     {
         rcp<const Gradient> gradient;

@@ -540,6 +540,8 @@ int RenderContextCUDAImpl::flushPlainPathChunk(const PlainPathFrame& frame, size
     memset(&r, 0, sizeof(r));
     if (int status = m_abi.front_end_clip_rects(m_ctx, frame.clipRects, static_cast<uint32_t>(frame.clipRectCount)))
         return status;
+    if (int status = m_abi.front_end_image_paints(m_ctx, frame.imagePaints, static_cast<uint32_t>(frame.imagePaintCount)))
+        return status;
     if (int status = m_abi.front_end_gradient_paints(m_ctx, frame.gradientPaints, static_cast<uint32_t>(frame.gradientPaintCount)))
         return status;
     if (int status = m_abi.front_end_paths(m_ctx,
@@ -644,15 +646,16 @@ int RenderContextCUDAImpl::flushPlainPathChunk(const PlainPathFrame& frame, size
         if ((path.blend_mode & 0x100u) != 0u && path.color != 0u)
             batch.shader_features |= RIVECUDA_FEATURE_NESTED_CLIPPING; // clipUpdate | activeClip (pushPathDraw)
     };
-    bool anyClockwise = false, anyOtherFill = false;
+    bool anyClockwise = false, anyOtherFill = false, anyImage = false;
     for (size_t i = 0; i < pathCount; ++i)
     {
         const rivecuda_path& path = frame.paths[firstPath + i];
+        anyImage |= (path.cap >> 8) != 0u;
         if ((path.stroke & 1u) == 0u)
             ((path.fill_rule & 0xffu) == 2u ? anyClockwise : anyOtherFill) = true;
     }
     std::vector<rivecuda_draw_batch> batches;
-    if (r.patch_count != 0 && !(anyClockwise && anyOtherFill))
+    if (r.patch_count != 0 && !(anyClockwise && anyOtherFill) && !anyImage)
     {
         rivecuda_draw_batch batch = new_batch(r.first_patch);
         batch.element_count = r.patch_count;
@@ -676,12 +679,22 @@ int RenderContextCUDAImpl::flushPlainPathChunk(const PlainPathFrame& frame, size
                 continue; // culled, or nothing to draw
             const bool isFill = (path.stroke & 1u) == 0u;
             const uint32_t misc = isFill && (path.fill_rule & 0xffu) == 2u ? RIVECUDA_MISC_CLOCKWISE_FILL : 0u;
-            if (batches.empty() || (isFill && batchHasFills && batches.back().shader_misc_flags != misc))
+            // A batch binds one image texture and sampler (can_combine_draw_images, render_context.cpp:3702-3717).
+            const PlainImageBinding* image = (path.cap >> 8) != 0u ? &frame.imageBindings[(path.cap >> 8) - 1u] : nullptr;
+            const bool imageMismatch = image != nullptr && !batches.empty() && batches.back().image_texture != nullptr &&
+                                       (batches.back().image_texture != image->texture || batches.back().image_sampler != image->samplerKey);
+            if (batches.empty() || (isFill && batchHasFills && batches.back().shader_misc_flags != misc) || imageMismatch)
             {
                 batches.push_back(new_batch(firstPatch[i]));
                 batchHasFills = false;
             }
             rivecuda_draw_batch& batch = batches.back();
+            if (image != nullptr)
+            {
+                batch.image_texture = image->texture;
+                batch.image_sampler = image->samplerKey;
+                batch.shader_features |= RIVECUDA_FEATURE_MODULATED_IMAGE; // pushDraw, render_context.cpp:4028-4033
+            }
             if (isFill && !batchHasFills)
             {
                 batch.shader_misc_flags = misc;

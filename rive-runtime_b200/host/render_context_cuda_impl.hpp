@@ -145,6 +145,11 @@ public:
     // flushed like any other -- in as many logical flushes as its paths need. See
     // CudaPathRenderer (cuda_path_renderer.hpp) for the rive::Renderer that collects such a
     // frame. Returns false (with a message on stderr) when the ABI reports an error.
+    struct PlainImageBinding
+    {
+        const rivecuda_texture* texture = nullptr;
+        uint32_t samplerKey = 0; // ImageSampler::asKey()
+    };
     struct PlainPathFrame
     {
         RenderTargetCUDA* renderTarget = nullptr;
@@ -169,6 +174,10 @@ public:
         // Clip paths: the frame holds clipUpdate paths and clip IDs (rivecuda_path::blend_mode);
         // they are valid within one flush, so such a frame is not split.
         bool hasClipPaths = false;
+        // Image paints: the records the paths' `cap >> 8` index, and what each binds.
+        const rivecuda_image_paint* imagePaints = nullptr;
+        const PlainImageBinding* imageBindings = nullptr;
+        size_t imagePaintCount = 0;
     };
     bool flushPlainPaths(const PlainPathFrame&);
     // Grows the gradient texture to hold `rows` rows the way RenderContext does (125% of what is

@@ -102,7 +102,7 @@ def test_device_front_end_equals_its_host_build_on_random_paths(built, seed, n_p
         assert np.array_equal(F.read_buffer(rp, 2, n * 8).view(np.uint32).reshape(-1, 2)[1:], want.paint_data[1:n])
 
 
-@pytest.mark.parametrize("scene,golden", [("c2", "c2_4k"), ("f1", "f1"), ("f1o", "f1o"), ("f1b", "f1b"), ("f1c", "f1c"), ("f1w", "f1w"), ("f1g", "f1g"), ("f1p", "f1p"), ("s1", "s1"), ("gm:trickycubicstrokes", "trickycubicstrokes"),
+@pytest.mark.parametrize("scene,golden", [("c2", "c2_4k"), ("f1", "f1"), ("f1o", "f1o"), ("f1b", "f1b"), ("f1c", "f1c"), ("f1w", "f1w"), ("f1g", "f1g"), ("f1p", "f1p"), ("f1i", "f1i"), ("s1", "s1"), ("gm:trickycubicstrokes", "trickycubicstrokes"),
                                           ("gm:strokes3", "strokes3")])
 def test_cpp_path_renderer_draws_the_same_frame(built, scene, golden):
     """SURVEY 8 f1 in the compiled host: the scene player with --gpu-front-end draws through
