@@ -120,10 +120,15 @@ void TestingWindowCUDA::endFrame(std::vector<uint8_t>* pixelData)
 {
     if (m_gpuFrontEnd)
     {
+        m_lastFrameRefused = false;
         if (m_pathRenderer == nullptr || !m_pathRenderer->flush())
         {
             fprintf(stderr, "TestingWindowCUDA: --gpu-front-end cannot draw this frame\n");
-            abort();
+            if (!m_softRefusal)
+                abort();
+            m_lastFrameRefused = true;
+            m_pathRenderer = nullptr;
+            return;
         }
         m_pathRenderer = nullptr;
         if (pixelData != nullptr)

@@ -36,6 +36,9 @@ public:
     // --gpu-front-end: beginFrame() hands out a CudaPathRenderer; endFrame()
     // aborts if the frame contained anything but plain fills and strokes.
     void setGpuFrontEnd(bool enabled) { m_gpuFrontEnd = enabled; }
+    // Sweeps: a frame CudaPathRenderer refuses is reported here instead of aborting.
+    void setSoftRefusal(bool enabled) { m_softRefusal = enabled; }
+    bool lastFrameRefused() const { return m_lastFrameRefused; }
 
     // FrameDescriptor options the reference exposes per frame: every fill drawn with
     // the clockwise rule; the frame drawn virtual tile by virtual tile.
@@ -49,6 +52,7 @@ public:
 private:
     struct PathDumpSink* m_pathDump = nullptr;
     bool m_gpuFrontEnd = false;
+    bool m_softRefusal = false, m_lastFrameRefused = false;
     bool m_clockwiseFillOverride = false;
     uint32_t m_virtualTileWidth = 0, m_virtualTileHeight = 0;
     class rive::gpu::CudaPathRenderer* m_pathRenderer = nullptr; // owned by beginFrame()'s caller

@@ -388,6 +388,15 @@ void RenderContextCUDAImpl::resizeBuffer(rivecuda_buffer_kind kind,
                                          size_t sizeInBytes)
 {
     ABI_CHECK(m_abi.buffer_resize(m_ctx, kind, sizeInBytes));
+    m_bufferCapacity[kind] = sizeInBytes;
+}
+
+// flushPlainPaths shares the rings with the owning RenderContext, which resizes them to what IT
+// needs and remembers the sizes: the plain path only ever grows them.
+void RenderContextCUDAImpl::growBuffer(rivecuda_buffer_kind kind, size_t sizeInBytes)
+{
+    if (sizeInBytes > m_bufferCapacity[kind])
+        resizeBuffer(kind, sizeInBytes);
 }
 
 void* RenderContextCUDAImpl::mapBuffer(rivecuda_buffer_kind kind,
@@ -444,13 +453,18 @@ void RenderContextCUDAImpl::resizeGradientTexture(uint32_t width,
                                                   uint32_t height)
 {
     ABI_CHECK(m_abi.resize_gradient_texture(m_ctx, width, height));
-    m_plainGradHeight = height;
+    m_plainGradHeight = m_contextGradHeight = height;
 }
 
 uint32_t RenderContextCUDAImpl::reservePlainGradientRows(uint32_t rows)
 {
     if (rows > m_plainGradHeight)
-        resizeGradientTexture(kGradTextureWidth, std::min<uint32_t>((rows * 5u) >> 2, kMaxGradTextureHeight));
+    {
+        // (not through the override: the owning RenderContext keeps believing in the height it set,
+        // which flush() restores before it draws one of its own frames again)
+        m_plainGradHeight = std::min<uint32_t>((rows * 5u) >> 2, kMaxGradTextureHeight);
+        ABI_CHECK(m_abi.resize_gradient_texture(m_ctx, kGradTextureWidth, m_plainGradHeight));
+    }
     return m_plainGradHeight;
 }
 
@@ -581,7 +595,7 @@ int RenderContextCUDAImpl::flushPlainPathChunk(const PlainPathFrame& frame, size
     {
         // Every chunk of the frame renders the frame's colour ramps (they are few).
         const size_t size = frame.gradSpanCount * sizeof(GradientSpan);
-        resizeGradSpanBuffer(size);
+        growBuffer(RIVECUDA_BUFFER_GRAD_SPAN, size);
         void* mapped = mapGradSpanBuffer(size);
         if (mapped == nullptr)
             return 1;
@@ -590,7 +604,7 @@ int RenderContextCUDAImpl::flushPlainPathChunk(const PlainPathFrame& frame, size
     }
     {
         const size_t size = sizeof(FlushUniforms);
-        resizeFlushUniformBuffer(size);
+        growBuffer(RIVECUDA_BUFFER_FLUSH_UNIFORM, size);
         void* mapped = mapFlushUniformBuffer(size);
         if (mapped == nullptr)
             return 1;
@@ -718,6 +732,14 @@ void RenderContextCUDAImpl::flush(const FlushDescriptor& desc)
                 "(only rasterOrdering is advertised)\n",
                 static_cast<int>(desc.interlockMode));
         abort();
+    }
+
+    if (m_plainGradHeight != m_contextGradHeight)
+    {
+        // A CudaPathRenderer frame grew the gradient texture in between: the RenderContext's paints
+        // are normalised by the height IT allocated (render_context.cpp:1442-1443).
+        ABI_CHECK(m_abi.resize_gradient_texture(m_ctx, kGradTextureWidth, m_contextGradHeight));
+        m_plainGradHeight = m_contextGradHeight;
     }
 
     rivecuda_flush_desc d;

@@ -258,8 +258,11 @@ private:
     RenderContextCUDAImpl(const RiveCudaABI&, rivecuda_ctx*);
 
     int flushPlainPathChunk(const PlainPathFrame&, size_t firstPath, size_t pathCount, bool firstFlush, rivecuda_front_end_result* needed);
-    uint32_t m_plainGradHeight = 0; // what the gradient texture was last sized to
+    size_t m_bufferCapacity[RIVECUDA_BUFFER_KIND_COUNT] = {}; // what resizeBuffer last set
+    uint32_t m_plainGradHeight = 0;   // what the gradient texture was last sized to
+    uint32_t m_contextGradHeight = 0; // what the owning RenderContext last sized it to
     uint32_t m_plainTessHeight = 0; // what flushPlainPaths last sized the tessellation texture to
+    void growBuffer(rivecuda_buffer_kind kind, size_t sizeInBytes);
     void resizeBuffer(rivecuda_buffer_kind, size_t sizeInBytes);
     void* mapBuffer(rivecuda_buffer_kind, size_t mapSizeInBytes);
     void unmapBuffer(rivecuda_buffer_kind, size_t mapSizeInBytes);

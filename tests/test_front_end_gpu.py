@@ -127,15 +127,15 @@ def test_cpp_path_renderer_draws_the_same_frame(built, scene, golden):
     assert px.size == want.size and np.array_equal(px.reshape(want.shape), want)
 
 
-@pytest.mark.parametrize("name", ["off_road_car", "bullet_man", "shapetest", "fix_rectangle", "follow_path_solos", "trim_path_linear", "magic_alley_db_reduced_export",
-                                  "nested_artboard_opacity", "lock_icon_demo", "follow_path_shapes", "solos_collapse_tests", "group_effect"])
+@pytest.mark.parametrize("name", ["off_road_car", "bullet_man", "shapetest"])
 def test_riv_file_through_the_device_front_end(built, name):
     """Real .riv content (clockwise and nonZero fills, strokes, opacity, artboard clip rectangles;
     off_road_car and bullet_man: gradients and nested clip paths too) through --gpu-front-end: frame 20 must equal, bit for bit, the frame the reference's CPU front
     end produces for the same file through the same backend (midpoint fans only: --budget-ms 0
     switches the reference's interior triangulation of large paths off, which the device front end
-    does not implement). tests/tools/riv_front_end_sweep.py runs the same comparison over a whole
-    directory: all 180 importable assets below 400 kB are identical (profiles/r02_riv_front_end_sweep.md).
+    does not implement). The player's `rivs:DIR` scene runs the same comparison over a whole
+    directory in one process: 321 of the reference's 342 assets are drawn by the device front end,
+    all 321 identical (profiles/r02_riv_front_end_sweep.md).
     The assets are the reference's (tools/fetch_riv_assets.sh); the test skips without them."""
     import subprocess
     import tempfile
@@ -154,6 +154,26 @@ def test_riv_file_through_the_device_front_end(built, name):
             frames.append(np.fromfile(out, dtype=np.uint8))
     assert frames[0].size == 1920 * 1080 * 4 and np.array_equal(frames[0], frames[1])
     assert len(np.unique(frames[0].reshape(-1, 4), axis=0)) > 1  # not an empty frame
+
+
+def test_riv_assets_sweep_both_front_ends_in_one_process(built):
+    """`--scene rivs:DIR`: every asset is imported, advanced 20 frames and drawn through RiveRenderer and
+    through CudaPathRenderer on the SAME RenderContextCUDAImpl, alternating -- which also checks that the
+    two front ends can share a context (the plain path only grows the shared rings and hands the
+    gradient texture back at the height the RenderContext allocated)."""
+    import json
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    player = os.path.join(root, "rive-runtime_b200", "_build", "rive_cuda_player")
+    assets = os.path.join(root, "tests", "_riv_assets")
+    if not os.path.exists(player) or not os.path.isdir(assets) or len([n for n in os.listdir(assets) if n.endswith(".riv")]) < 10:
+        pytest.skip("scene player or .riv assets not present")
+    env = dict(os.environ, RIVECUDA_LIB=os.path.join(root, "rive-runtime_b200", "_build", "librivecuda.so"))
+    out = subprocess.run([player, "--scene", "rivs:" + assets, "--frames", "20", "--budget-ms", "0"], env=env, stdout=subprocess.PIPE,
+                         stderr=subprocess.DEVNULL, timeout=600)
+    report = json.loads(out.stdout.decode().strip().splitlines()[-1])
+    assert out.returncode == 0 and report["differing"] == 0 and report["failed"] == 0 and report["refused"] == 0
+    assert report["identical"] == report["assets"] >= 10
 
 
 def test_front_end_refuses_what_one_flush_cannot_hold(built):
