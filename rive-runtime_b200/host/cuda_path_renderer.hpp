@@ -18,7 +18,7 @@
  * travel as GradientSpans plus a table of paint records; clip PATHS become clipUpdate paths in
  * front of the draws that need them, under the clip IDs RiveRenderer::applyClip would hand out;
  * image paints and drawImage travel as a table of image matrices, their textures on the batches.
- * Anything else -- feathers, image meshes --
+ * Image meshes are passed through as batches of their own between the paths'. Anything else -- feathers --
  * is not handled by the device front end: the renderer records the first such call
  * and flush() refuses the frame, so the caller can draw it with RiveRenderer (no silent fallback).
  */
@@ -268,17 +268,54 @@ public:
         drawPath(m_unitRectPath.get(), &paint);
         restore();
     }
-    void drawImageMesh(const RenderImage*,
-                       ImageSampler,
-                       rcp<RenderBuffer>,
-                       rcp<RenderBuffer>,
-                       rcp<RenderBuffer>,
+    // RiveRenderer::drawImageMesh (rive_renderer.cpp:448-494): an ImageMeshDraw over the whole render
+    // target, clipped like any other draw (applyClip); the backend draws it between the path batches.
+    void drawImageMesh(const RenderImage* renderImage,
+                       ImageSampler sampler,
+                       rcp<RenderBuffer> vertices,
+                       rcp<RenderBuffer> uvCoords,
+                       rcp<RenderBuffer> indices,
                        uint32_t,
-                       uint32_t,
-                       BlendMode,
-                       float) override
+                       uint32_t indexCount,
+                       BlendMode blendMode,
+                       float opacity) override
     {
-        refuse("drawImageMesh");
+        auto* image = static_cast<const RiveRenderImage*>(renderImage);
+        rcp<Texture> texture = image->refTexture();
+        const State& state = m_stack.back();
+        if (texture == nullptr || state.overallClipPixelBounds.empty())
+            return;
+        RenderContextCUDAImpl::PlainMeshDraw mesh;
+        mesh.vertexBuffer = RenderContextCUDAImpl::renderBufferHandle(vertices.get());
+        mesh.uvBuffer = RenderContextCUDAImpl::renderBufferHandle(uvCoords.get());
+        mesh.indexBuffer = RenderContextCUDAImpl::renderBufferHandle(indices.get());
+        if (mesh.vertexBuffer == nullptr || mesh.uvBuffer == nullptr || mesh.indexBuffer == nullptr)
+            return; // foreign buffers: skipped, like LITE_RTTI_CAST_OR_BREAK in the backends
+        const float finalOpacity = std::max(0.0f, opacity * state.opacity);
+        // applyClip: the draw's bounds are the whole target, clipped by the state's.
+        const IAABB clipped = state.overallClipPixelBounds.intersect(Draw::FULLSCREEN_PIXEL_BOUNDS);
+        if (clipped.empty() || clipped.left >= static_cast<int32_t>(m_target->width()) || clipped.top >= static_cast<int32_t>(m_target->height()) ||
+            clipped.right <= 0 || clipped.bottom <= 0)
+            return;
+        if (state.clipStackHeight != 0)
+        {
+            mesh.clipID = applyClip(state.clipStackHeight);
+            if (mesh.clipID == 0)
+                return refuse("drawImageMesh under more clip updates than one flush has clip IDs");
+        }
+        mesh.afterPath = m_paths.size();
+        mesh.hasClipRect = state.hasClipRect;
+        const ClipRectInverseMatrix clipRectInverse = state.hasClipRect ? ClipRectInverseMatrix(state.clipRectMatrix, state.clipRect) : ClipRectInverseMatrix::WideOpen();
+        mesh.instance = ImageDrawInstance(state.matrix, finalOpacity, state.hasClipRect ? &clipRectInverse : nullptr, mesh.clipID, blendMode, 0);
+        mesh.texture = static_cast<const TextureCUDA*>(texture.get())->handle();
+        mesh.samplerKey = sampler.asKey();
+        mesh.indexCount = indexCount;
+        mesh.blendMode = ConvertBlendModeToPLSBlendMode(blendMode);
+        m_meshDraws.push_back(mesh);
+        m_imageTextures.push_back(std::move(texture));
+        m_meshBuffers.push_back(std::move(vertices));
+        m_meshBuffers.push_back(std::move(uvCoords));
+        m_meshBuffers.push_back(std::move(indices));
     }
 
     // The first call this renderer cannot express, or nullptr.
@@ -309,6 +346,8 @@ public:
         frame.imagePaints = m_imagePaints.data();
         frame.imageBindings = m_imageBindings.data();
         frame.imagePaintCount = m_imagePaints.size();
+        frame.meshDraws = m_meshDraws.data();
+        frame.meshDrawCount = m_meshDraws.size();
         std::vector<GradientSpan> gradSpans;
         std::vector<rivecuda_gradient_paint> gradientPaints;
         if (!m_gradientDraws.empty())
@@ -583,6 +622,8 @@ private:
     std::vector<RenderContextCUDAImpl::PlainImageBinding> m_imageBindings;
     std::vector<rcp<Texture>> m_imageTextures; // alive until the flush
     rcp<RiveRenderPath> m_unitRectPath;
+    std::vector<RenderContextCUDAImpl::PlainMeshDraw> m_meshDraws; // in draw order
+    std::vector<rcp<RenderBuffer>> m_meshBuffers;                  // alive until the flush
     struct GradientDraw
     {
         rcp<const Gradient> gradient;

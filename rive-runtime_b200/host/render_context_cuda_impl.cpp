@@ -503,6 +503,12 @@ static void convert_atlas_batches(const AtlasDrawBatch* batches,
     }
 }
 
+const rivecuda_renderbuffer* RenderContextCUDAImpl::renderBufferHandle(RenderBuffer* buffer)
+{
+    auto* cuda = lite_rtti_cast<RenderBufferCUDA*>(buffer);
+    return cuda != nullptr ? cuda->handle() : nullptr;
+}
+
 bool RenderContextCUDAImpl::flushPlainPaths(const PlainPathFrame& frame)
 {
     // One logical flush holds a bounded number of paths, contours and tessellation vertices
@@ -518,11 +524,11 @@ bool RenderContextCUDAImpl::flushPlainPaths(const PlainPathFrame& frame)
         const size_t count = std::min(chunk, frame.pathCount - first);
         rivecuda_front_end_result needed;
         const int status = flushPlainPathChunk(frame, first, count, firstFlush, &needed);
-        if (status == RIVECUDA_STATUS_EXCEEDS_FLUSH && frame.hasClipPaths)
+        if (status == RIVECUDA_STATUS_EXCEEDS_FLUSH && (frame.hasClipPaths || frame.meshDrawCount != 0))
         {
             // The reference re-renders the clips after starting a new logical flush; the clip IDs
             // CudaPathRenderer handed out assume one flush.
-            fprintf(stderr, "RenderContextCUDAImpl::flushPlainPaths: a frame with clip paths must fit one flush\n");
+            fprintf(stderr, "RenderContextCUDAImpl::flushPlainPaths: a frame with clip paths or image meshes must fit one flush\n");
             return false;
         }
         if (status == RIVECUDA_STATUS_EXCEEDS_FLUSH && count > 1)
@@ -602,6 +608,17 @@ int RenderContextCUDAImpl::flushPlainPathChunk(const PlainPathFrame& frame, size
         memcpy(mapped, frame.gradSpans, size);
         unmapGradSpanBuffer(size);
     }
+    if (frame.meshDrawCount != 0)
+    {
+        const size_t size = frame.meshDrawCount * sizeof(ImageDrawInstance);
+        growBuffer(RIVECUDA_BUFFER_IMAGE_DRAW, size);
+        void* mapped = mapImageDrawInstanceBuffer(size);
+        if (mapped == nullptr)
+            return 1;
+        for (size_t i = 0; i < frame.meshDrawCount; ++i)
+            memcpy(static_cast<uint8_t*>(mapped) + i * sizeof(ImageDrawInstance), &frame.meshDraws[i].instance, sizeof(ImageDrawInstance));
+        unmapImageDrawInstanceBuffer(size);
+    }
     {
         const size_t size = sizeof(FlushUniforms);
         growBuffer(RIVECUDA_BUFFER_FLUSH_UNIFORM, size);
@@ -669,7 +686,30 @@ int RenderContextCUDAImpl::flushPlainPathChunk(const PlainPathFrame& frame, size
             ((path.fill_rule & 0xffu) == 2u ? anyClockwise : anyOtherFill) = true;
     }
     std::vector<rivecuda_draw_batch> batches;
-    if (r.patch_count != 0 && !(anyClockwise && anyOtherFill) && !anyImage)
+    auto mesh_batch = [&](size_t index) {
+        const PlainMeshDraw& mesh = frame.meshDraws[index];
+        rivecuda_draw_batch batch;
+        memset(&batch, 0, sizeof(batch));
+        batch.draw_type = RIVECUDA_DRAW_IMAGE_MESH;
+        batch.element_count = 1; // one instance (the mesh)
+        batch.base_element = static_cast<uint32_t>(index);
+        batch.index_count_per_instance = mesh.indexCount;
+        batch.first_blend_mode = static_cast<uint32_t>(BlendMode::srcOver);
+        batch.image_texture = mesh.texture;
+        batch.image_sampler = mesh.samplerKey;
+        batch.vertex_buffer = mesh.vertexBuffer;
+        batch.uv_buffer = mesh.uvBuffer;
+        batch.index_buffer = mesh.indexBuffer;
+        // pushDraw (render_context.cpp:4010-4060)
+        if (mesh.clipID != 0u)
+            batch.shader_features |= RIVECUDA_FEATURE_CLIPPING;
+        if (mesh.hasClipRect)
+            batch.shader_features |= RIVECUDA_FEATURE_CLIP_RECT;
+        if (mesh.blendMode != 0u)
+            batch.shader_features |= RIVECUDA_FEATURE_ADVANCED_BLEND | (mesh.blendMode >= 12u ? RIVECUDA_FEATURE_HSL_BLEND_MODES : 0u);
+        return batch;
+    };
+    if (r.patch_count != 0 && !(anyClockwise && anyOtherFill) && !anyImage && frame.meshDrawCount == 0)
     {
         rivecuda_draw_batch batch = new_batch(r.first_patch);
         batch.element_count = r.patch_count;
@@ -678,15 +718,24 @@ int RenderContextCUDAImpl::flushPlainPathChunk(const PlainPathFrame& frame, size
             add_features(batch, frame.paths[firstPath + i]);
         batches.push_back(batch);
     }
-    else if (r.patch_count != 0)
+    else if (r.patch_count != 0 || frame.meshDrawCount != 0)
     {
         // Mixed fills: where each path's patches start decides the batch boundaries.
         std::vector<uint32_t> firstPatch(pathCount + 1);
         if (int status = m_abi.front_end_path_patches(m_ctx, firstPatch.data(), static_cast<uint32_t>(pathCount)))
             return status;
         bool batchHasFills = false;
-        for (size_t i = 0; i < pathCount; ++i)
+        size_t nextMesh = 0;
+        bool meshBreak = false; // the next path starts a batch of its own: a mesh was drawn in between
+        for (size_t i = 0; i <= pathCount; ++i)
         {
+            while (nextMesh < frame.meshDrawCount && frame.meshDraws[nextMesh].afterPath <= firstPath + i)
+            {
+                batches.push_back(mesh_batch(nextMesh++));
+                meshBreak = true;
+            }
+            if (i == pathCount)
+                break;
             const rivecuda_path& path = frame.paths[firstPath + i];
             const uint32_t patches = firstPatch[i + 1] - firstPatch[i];
             if (patches == 0)
@@ -695,10 +744,11 @@ int RenderContextCUDAImpl::flushPlainPathChunk(const PlainPathFrame& frame, size
             const uint32_t misc = isFill && (path.fill_rule & 0xffu) == 2u ? RIVECUDA_MISC_CLOCKWISE_FILL : 0u;
             // A batch binds one image texture and sampler (can_combine_draw_images, render_context.cpp:3702-3717).
             const PlainImageBinding* image = (path.cap >> 8) != 0u ? &frame.imageBindings[(path.cap >> 8) - 1u] : nullptr;
-            const bool imageMismatch = image != nullptr && !batches.empty() && batches.back().image_texture != nullptr &&
+            const bool imageMismatch = image != nullptr && !batches.empty() && !meshBreak && batches.back().image_texture != nullptr &&
                                        (batches.back().image_texture != image->texture || batches.back().image_sampler != image->samplerKey);
-            if (batches.empty() || (isFill && batchHasFills && batches.back().shader_misc_flags != misc) || imageMismatch)
+            if (batches.empty() || meshBreak || (isFill && batchHasFills && batches.back().shader_misc_flags != misc) || imageMismatch)
             {
+                meshBreak = false;
                 batches.push_back(new_batch(firstPatch[i]));
                 batchHasFills = false;
             }

@@ -145,6 +145,24 @@ public:
     // flushed like any other -- in as many logical flushes as its paths need. See
     // CudaPathRenderer (cuda_path_renderer.hpp) for the rive::Renderer that collects such a
     // frame. Returns false (with a message on stderr) when the ABI reports an error.
+    // An image mesh among the plain paths (RiveRenderer::drawImageMesh): drawn after path
+    // `afterPath` - 1, as a batch of its own (LogicalFlush::pushImageMeshDraw, render_context.cpp:3565-3592).
+    struct PlainMeshDraw
+    {
+        size_t afterPath = 0;
+        gpu::ImageDrawInstance instance;
+        const rivecuda_texture* texture = nullptr;
+        uint32_t samplerKey = 0;
+        const rivecuda_renderbuffer* vertexBuffer = nullptr;
+        const rivecuda_renderbuffer* uvBuffer = nullptr;
+        const rivecuda_renderbuffer* indexBuffer = nullptr;
+        uint32_t indexCount = 0;
+        uint32_t blendMode = 0; // PLS blend mode
+        bool hasClipRect = false;
+        uint32_t clipID = 0;
+    };
+    // The ABI handle of a RenderBuffer this impl made (nullptr for a foreign one).
+    static const rivecuda_renderbuffer* renderBufferHandle(RenderBuffer*);
     struct PlainImageBinding
     {
         const rivecuda_texture* texture = nullptr;
@@ -178,6 +196,8 @@ public:
         const rivecuda_image_paint* imagePaints = nullptr;
         const PlainImageBinding* imageBindings = nullptr;
         size_t imagePaintCount = 0;
+        const PlainMeshDraw* meshDraws = nullptr; // ordered by afterPath
+        size_t meshDrawCount = 0;
     };
     bool flushPlainPaths(const PlainPathFrame&);
     // Grows the gradient texture to hold `rows` rows the way RenderContext does (125% of what is

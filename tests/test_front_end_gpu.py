@@ -156,6 +156,29 @@ def test_riv_file_through_the_device_front_end(built, name):
     assert len(np.unique(frames[0].reshape(-1, 4), axis=0)) > 1  # not an empty frame
 
 
+def test_cpp_path_renderer_draws_the_image_scene(built):
+    """The `img` scene -- a gradient background, 24 drawImage calls (three images, every wrap and
+    filter, blend modes, under clip rectangles and an oval clip path) and four warped image MESHES,
+    which CudaPathRenderer passes through as batches of their own between the paths' -- drawn through
+    both front ends (midpoint fans only: --budget-ms 0): the frames must be identical."""
+    import subprocess
+    import tempfile
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    player = os.path.join(root, "rive-runtime_b200", "_build", "rive_cuda_player")
+    if not os.path.exists(player):
+        pytest.skip("scene player not built (needs the reference tree at build time)")
+    env = dict(os.environ, RIVECUDA_LIB=os.path.join(root, "rive-runtime_b200", "_build", "librivecuda.so"))
+    frames = []
+    with tempfile.TemporaryDirectory() as tmp:
+        for extra in ([], ["--gpu-front-end"]):
+            out = os.path.join(tmp, "frame%d.rgba" % len(frames))
+            subprocess.check_call([player, "--scene", "img", "--budget-ms", "0", "--out", out, *extra], env=env,
+                                  stdout=subprocess.DEVNULL, timeout=300)
+            frames.append(np.fromfile(out, dtype=np.uint8))
+    assert frames[0].size > 0 and np.array_equal(frames[0], frames[1])
+    assert len(np.unique(frames[0].reshape(-1, 4), axis=0)) > 1000
+
+
 def test_riv_assets_sweep_both_front_ends_in_one_process(built):
     """`--scene rivs:DIR`: every asset is imported, advanced 20 frames and drawn through RiveRenderer and
     through CudaPathRenderer on the SAME RenderContextCUDAImpl, alternating -- which also checks that the
