@@ -538,7 +538,7 @@ def main() -> None:
                      "note": "RawPaths + matrices + colours in (host), RGBA8 frame out (host): rivecuda_front_end_paths (Wang's "
                              "formula counts, warp-scan span allocation, span/contour/path records on the device; byte-identical "
                              "to the reference front end, tests/test_front_end_gpu.py) + the same flush; front_end_ms includes "
-                             "the H2D of the paths and two stream syncs; cpu_baseline.front_end times the reference's own "
+                             "the H2D of the paths and one stream sync; cpu_baseline.front_end times the reference's own "
                              "CPU front end on the same frame."}
 
     # ---- CPU baseline (rank 0, N=1 only): bounded sample of the same workload ---

@@ -681,8 +681,16 @@ int rivecuda_front_end_paths(rivecuda_ctx* ctx,
         RC_CUDA(cudaMemsetAsync(dSums, 0, 16, stream));
     }
     front_end_padding_kernel<<<1, 1, 0, stream>>>(out.spans, dSums, dSums + 4);
+    if (path_count != 0)
+    {
+        // Pass 2 (spans per path) runs before the host has seen the totals: it only counts (a path
+        // the count kernel rejected owns no vertices and is skipped; a span wraps at most two rows
+        // whatever its location), so that ONE synchronisation returns everything the host needs.
+        front_end_place_kernel<false><<<blocks, kWarpsPerBlock * 32, 0, stream>>>(dPaths, path_count, dPoints, dVerbs, dTotals, dOwn, out);
+        front_end_scan_kernel<<<1, 1024, 0, stream>>>(field + 3, path_count, dSums + 3);
+    }
     RC_CUDA(cudaMemcpyAsync(ctx->pinnedTotals + 8, dSums, 7 * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
-    RC_CUDA(cudaStreamSynchronize(stream)); // the span base (2 or 3 padding spans) and the totals
+    RC_CUDA(cudaStreamSynchronize(stream)); // the totals, the span count and the span base (2 or 3 padding spans)
     out.spanBase = ctx->pinnedTotals[8 + 4];
     const uint32_t* sums = ctx->pinnedTotals + 8;
     if (sums[6] != 0u)
@@ -704,15 +712,10 @@ int rivecuda_front_end_paths(rivecuda_ctx* ctx,
         unrotate();
         return RIVECUDA_STATUS_EXCEEDS_FLUSH;
     }
+    // Pass 3 writes the records; nobody waits for it here: the next flush does, through the upload event.
     if (path_count != 0)
-    {
-        front_end_place_kernel<false><<<blocks, kWarpsPerBlock * 32, 0, stream>>>(dPaths, path_count, dPoints, dVerbs, dTotals, dOwn, out);
-        front_end_scan_kernel<<<1, 1024, 0, stream>>>(field + 3, path_count, dSums + 3);
         front_end_place_kernel<true><<<blocks, kWarpsPerBlock * 32, 0, stream>>>(dPaths, path_count, dPoints, dVerbs, dTotals, dOwn, out);
-    }
     RC_CUDA(cudaGetLastError());
-    RC_CUDA(cudaMemcpyAsync(ctx->pinnedTotals + 8 + 3, dSums + 3, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
-    RC_CUDA(cudaStreamSynchronize(stream));
     result->midpoint_fan_tess_vertex_count = sums[0];
     result->contour_count = sums[1];
     result->path_count = sums[2] + 1; // + the reserved record 0
