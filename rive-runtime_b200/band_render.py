@@ -42,7 +42,8 @@ class BandRenderer:
         self.frame = frame_tensor
 
     def render(self, band):
-        """Replay every flush restricted to `band` (rows); returns device ms of the flushes."""
+        """Replay every flush restricted to `band` (rows); returns device ms of the flushes
+        (and leaves the event recorded before the first one in self.started)."""
         rp, result = self.rp, R.ReplayResult()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         started = False
@@ -71,6 +72,7 @@ class BandRenderer:
         ev1.record(self.stream)
         rp.sync()
         self.first = False
+        self.started = ev0
         return ev0.elapsed_time(ev1)
 
     def close(self):
@@ -96,7 +98,7 @@ def run(src: str, reps: int, rank: int, local: int, world: int, scene_args=()):
     band = sharding.band_for_rank(H, rank, world)
     frame = torch.zeros((H, W, 4), dtype=torch.uint8, device=dev)
 
-    band_ms, gather_ms = [], []
+    band_ms, gather_ms, gather_min_ms, total_ms = [], [], [], []
     # The composite lives on rank 0 for the whole measurement: the gather's receive buffers are
     # its row ranges, and nothing is allocated inside the timed region.
     composite = torch.empty((H, W, 4), dtype=torch.uint8, device=dev) if (rank == 0 and world > 1) else None
@@ -115,12 +117,20 @@ def run(src: str, reps: int, rank: int, local: int, world: int, scene_args=()):
             composite = frame
         g1.record()
         torch.cuda.synchronize()
-        t = torch.tensor([t_render, g0.elapsed_time(g1)], dtype=torch.float64, device=dev)
+        # Device-timed on every rank, max over ranks: the band's flushes; the gather as this rank sees
+        # it (a rank whose band is done early waits in it for the slowest band, so the max holds the
+        # load imbalance; the LAST rank to arrive waits for nobody: the min over ranks is the
+        # exchange proper); and the whole frame, first flush to the end of the gather.
+        t = torch.tensor([t_render, g0.elapsed_time(g1), renderer.started.elapsed_time(g1)], dtype=torch.float64, device=dev)
+        tmin = torch.tensor([g0.elapsed_time(g1)], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dist.all_reduce(tmin, op=dist.ReduceOp.MIN)
         band_ms.append(float(t[0]))
         gather_ms.append(float(t[1]))
-    band_ms, gather_ms = band_ms[1:], gather_ms[1:]
+        total_ms.append(float(t[2]))
+        gather_min_ms.append(float(tmin[0]))
+    band_ms, gather_ms, gather_min_ms, total_ms = band_ms[1:], gather_ms[1:], gather_min_ms[1:], total_ms[1:]
     renderer.close()
 
     line = None
@@ -139,8 +149,10 @@ def run(src: str, reps: int, rank: int, local: int, world: int, scene_args=()):
             "bands": [sharding.band_for_rank(H, r, world) for r in range(world)],
             "single_gpu_ms": float(np.mean(single_ms)), "banded_render_ms_max_over_ranks": float(np.mean(band_ms)),
             "render_ms": float(np.mean(band_ms)),
-            "gather_ms": float(np.mean(gather_ms)), "gather_bytes_per_rank": int(W * (band[1] - band[0]) * 4),
-            "speedup_vs_single": float(np.mean(single_ms)) / (float(np.mean(band_ms)) + float(np.mean(gather_ms))),
+            "gather_ms": float(np.mean(gather_min_ms)), "gather_bytes_per_rank": int(W * (band[1] - band[0]) * 4),
+            "gather_ms_max_over_ranks_incl_wait_for_slowest_band": float(np.mean(gather_ms)),
+            "frame_ms_max_over_ranks": float(np.mean(total_ms)),
+            "speedup_vs_single": float(np.mean(single_ms)) / float(np.mean(total_ms)),
             "composite_identical_to_single_pass": identical, "identical": identical,
         }
         del full
