@@ -14,7 +14,7 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
-from . import replay as R, sharding, trace as T
+from . import abi, replay as R, sharding, trace as T
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -40,10 +40,30 @@ class BandRenderer:
         self.rp._call("rivecuda_stream", ctypes.byref(sp))
         self.stream = torch.cuda.ExternalStream(sp.value, device=torch.device("cuda", device))
         self.frame = frame_tensor
+        self.before_first_flush = None
 
-    def render(self, band):
+    def init_band_gather(self, rank, world):
+        """rivecuda_band_init on this rank's context: the 128-byte NCCL id is created by rank 0 and
+        handed round with torch.distributed (any channel would do: rivecuda.h)."""
+        import ctypes
+        import torch.distributed as dist
+        ident = torch.zeros(128, dtype=torch.uint8)
+        if rank == 0:
+            buf = ctypes.create_string_buffer(128)
+            abi.check(self.rp.lib, self.rp.lib.rivecuda_band_unique_id(buf), "rivecuda_band_unique_id")
+            ident = torch.frombuffer(bytearray(buf.raw), dtype=torch.uint8).clone()
+        ident = ident.to(self.frame.device)
+        dist.broadcast(ident, src=0)
+        raw = bytes(ident.cpu().numpy().tobytes())
+        self.rp._call("rivecuda_band_init", rank, world, ctypes.create_string_buffer(raw, 128))
+        self.abi_gather = True
+
+    def render(self, band, gather_root=None):
         """Replay every flush restricted to `band` (rows); returns device ms of the flushes
-        (and leaves the event recorded before the first one in self.started)."""
+        (and leaves the event recorded before the first one in self.started). With gather_root,
+        rivecuda_band_gather is enqueued behind the flushes on the render stream -- the bands land in
+        their rows of the root's target with no host synchronisation in between -- and self.finished
+        is the event behind it."""
         rp, result = self.rp, R.ReplayResult()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         started = False
@@ -54,6 +74,12 @@ class BandRenderer:
                 rp.external_targets[r.fields["id"]] = self.frame.data_ptr()
             if r.tag == T.FLUSH:
                 if not started:
+                    # The frame's inputs are resident before the clock starts, and (bands) every rank
+                    # starts its first flush together: the frame time is not to hold the ranks'
+                    # host-side skew in getting here.
+                    rp.sync()
+                    if self.before_first_flush is not None:
+                        self.before_first_flush()
                     ev0.record(self.stream)
                     started = True
                 # The ctypes mirror of a flush (C5: ~9300 draw batches each) is built once; a host
@@ -70,6 +96,12 @@ class BandRenderer:
                 continue  # targets, textures, tables and sizes persist across repetitions
             rp.apply(r, result)
         ev1.record(self.stream)
+        self.finished = ev1
+        if gather_root is not None:
+            (target,) = rp.targets.values()
+            rp._call("rivecuda_band_gather", target, gather_root)
+            self.finished = torch.cuda.Event(enable_timing=True)
+            self.finished.record(self.stream)
         rp.sync()
         self.first = False
         self.started = ev0
@@ -101,28 +133,31 @@ def run(src: str, reps: int, rank: int, local: int, world: int, scene_args=()):
     band_ms, gather_ms, gather_min_ms, total_ms = [], [], [], []
     # The composite lives on rank 0 for the whole measurement: the gather's receive buffers are
     # its row ranges, and nothing is allocated inside the timed region.
-    composite = torch.empty((H, W, 4), dtype=torch.uint8, device=dev) if (rank == 0 and world > 1) else None
+    composite = None
     renderer = BandRenderer(records, local, frame)
+    if world > 1:
+        # The gather is the C ABI's (rivecuda_band_gather: NCCL send / recv straight into the rows of
+        # the root's target, enqueued on the render stream), as the C++ host uses it.
+        import ctypes
+        r0, r1 = ctypes.c_uint32(), ctypes.c_uint32()
+        abi.check(renderer.rp.lib, renderer.rp.lib.rivecuda_band_rows(H, rank, world, ctypes.byref(r0), ctypes.byref(r1)), "rivecuda_band_rows")
+        assert (r0.value, r1.value) == tuple(band), "sharding.band_for_rank and rivecuda_band_rows must agree"
+        renderer.init_band_gather(rank, world)
+        renderer.before_first_flush = dist.barrier
     for _ in range(reps + 1):  # first repetition is the warm-up
         frame.zero_()
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
-        t_render = renderer.render(band)
-        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        g0.record()
-        if world > 1:
-            sharding.gather_bands(frame[band[0]:band[1]], H, W, dst_rank=0, out_frame=composite)
-        else:
-            composite = frame
-        g1.record()
-        torch.cuda.synchronize()
+        t_render = renderer.render(band, gather_root=0 if world > 1 else None)
+        composite = frame  # on rank 0: its own band plus the gathered ones, in place
         # Device-timed on every rank, max over ranks: the band's flushes; the gather as this rank sees
-        # it (a rank whose band is done early waits in it for the slowest band, so the max holds the
-        # load imbalance; the LAST rank to arrive waits for nobody: the min over ranks is the
-        # exchange proper); and the whole frame, first flush to the end of the gather.
-        t = torch.tensor([t_render, g0.elapsed_time(g1), renderer.started.elapsed_time(g1)], dtype=torch.float64, device=dev)
-        tmin = torch.tensor([g0.elapsed_time(g1)], dtype=torch.float64, device=dev)
+        # it (a rank whose band is done early waits in it for the root, which joins after its own
+        # band; the min over ranks is the exchange proper); and the whole frame, first flush to the
+        # end of the gather.
+        t_frame = renderer.started.elapsed_time(renderer.finished)
+        t = torch.tensor([t_render, t_frame - t_render, t_frame], dtype=torch.float64, device=dev)
+        tmin = torch.tensor([t_frame - t_render], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dist.all_reduce(tmin, op=dist.ReduceOp.MIN)

@@ -153,6 +153,10 @@ int rivecuda_band_gather(rivecuda_ctx* ctx, rivecuda_target* target, uint32_t ro
     if (ctx->bandComm == nullptr)
         return set_error("rivecuda_band_gather: rivecuda_band_init has not been called");
     RC_CUDA(cudaSetDevice(ctx->device));
+    // The last flush may have to run its tail again (its tile lists did not fit the buffer it was
+    // given): only then are the band's pixels what the exchange should send.
+    if (int pending = rivecuda::resolve_pending_flush(ctx))
+        return pending;
     const size_t rowBytes = static_cast<size_t>(target->width) * 4;
     uint8_t* pixels = reinterpret_cast<uint8_t*>(target->pixels);
     if (int s = check_nccl(g_nccl.groupStart(), "ncclGroupStart"))
