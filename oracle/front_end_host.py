@@ -37,12 +37,12 @@ class HostFrontEndOutput:
     paint_aux: np.ndarray   # (n, 32) uint32
 
 
-def run(dump: F.PathDump, frame_width: int = 0, frame_height: int = 0) -> HostFrontEndOutput:
+def run(dump: F.PathDump, frame_width: int = 0, frame_height: int = 0, tables: "F.FrontEndTables" = None) -> HostFrontEndOutput:
     lib = ctypes.CDLL(build())
     fn = lib.front_end_host_paths
     fn.restype = ctypes.c_int
     fn.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_void_p, ctypes.c_uint32,
-                   ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+                   ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
     pts = np.ascontiguousarray(dump.points, dtype=np.float32)
     verbs = np.ascontiguousarray(dump.verbs, dtype=np.uint8)
     paths = np.ascontiguousarray(dump.paths)
@@ -54,8 +54,10 @@ def run(dump: F.PathDump, frame_width: int = 0, frame_height: int = 0) -> HostFr
     paint_data = np.zeros((n_paths + 1, 2), np.uint32)
     paint_aux = np.zeros((n_paths + 1, 32), np.uint32)
     res = F.FrontEndResult()
+    keep = [np.ascontiguousarray(t) for t in ((tables.clip_rects, tables.gradient_paints, tables.image_paints) if tables is not None else ())]
+    table_ptrs = [t.ctypes.data if t.size else None for t in keep] if keep else [None, None, None]
     rc = fn(pts.ctypes.data, verbs.ctypes.data, paths.ctypes.data, n_paths, frame_width, frame_height, spans.ctypes.data, cap, contours.ctypes.data,
-            path_data.ctypes.data, paint_data.ctypes.data, paint_aux.ctypes.data, ctypes.byref(res))
+            path_data.ctypes.data, paint_data.ctypes.data, paint_aux.ctypes.data, ctypes.byref(res), *table_ptrs)
     if rc != 0:
         raise RuntimeError("front_end_host_paths: span capacity exceeded")
     return HostFrontEndOutput(res, spans, contours, path_data, paint_data, paint_aux)

@@ -25,20 +25,27 @@ extern "C" int front_end_host_paths(const float* pointsXY,
                                     uint32_t* pathData,  // 64-byte records, record 0 reserved
                                     uint32_t* paintData, // 8-byte records
                                     uint32_t* paintAux,  // 128-byte records
-                                    rivecuda_front_end_result* result)
+                                    rivecuda_front_end_result* result,
+                                    // the tables the paths index (rivecuda.h); each may be null
+                                    const rivecuda_clip_rect* clipRects,
+                                    const rivecuda_gradient_paint* gradientPaints,
+                                    const rivecuda_image_paint* imagePaints)
 {
     const V2* points = reinterpret_cast<const V2*>(pointsXY);
     std::vector<PathTotals> own(pathCount), prefix(pathCount);
     PathTotals sum = {0, 0, 0, 0};
     for (uint32_t i = 0; i < pathCount; ++i)
     {
-        own[i] = count_path(paths[i], points, verbs, frameWidth, frameHeight);
+        own[i] = count_path(paths[i], points, verbs, frameWidth, frameHeight, clipRects);
         prefix[i] = sum;
         sum.tessVertices += own[i].tessVertices;
         sum.contours += own[i].contours;
         sum.paths += own[i].paths;
     }
-    FrontEndOut out = {spans, contours, pathData, paintData, paintAux, 0};
+    FrontEndOut out;
+    out.spans = spans, out.contours = contours, out.pathData = pathData, out.paintData = paintData, out.paintAux = paintAux;
+    out.clipRects = clipRects, out.gradientPaints = gradientPaints, out.imagePaints = imagePaints;
+    out.spanBase = 0;
     uint32_t padding[2];
     emit_padding_spans(spans, sum.tessVertices, padding);
     out.spanBase = padding[0];

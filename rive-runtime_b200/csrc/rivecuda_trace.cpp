@@ -252,12 +252,37 @@ int rivecuda_target_read_wait(rivecuda_ctx*, rivecuda_target*) { return 0; }
 // The recorder has no device to run the front end on. With $RIVECUDA_TRACE_FRONT_END_OUT set it
 // writes the call's inputs there (what the host collected: tests compare them with the
 // --dump-paths file of the same scene) and reports an empty frame; otherwise it fails.
-//   u32 magic "RPF1", pathCount, pointCount, verbCount, frameWidth, frameHeight, 0, 0;
-//   rivecuda_path paths[]; u8 verbs[] (padded to 4); float points[][2]
-int rivecuda_front_end_clip_rects(rivecuda_ctx*, const rivecuda_clip_rect*, uint32_t) { return 0; } // (not part of the dump format)
-int rivecuda_front_end_gradient_paints(rivecuda_ctx*, const rivecuda_gradient_paint*, uint32_t) { return 0; } // (not part of the dump format)
-int rivecuda_front_end_image_paints(rivecuda_ctx*, const rivecuda_image_paint*, uint32_t) { return 0; }       // (not part of the dump format)
-int rivecuda_front_end_path_patches(rivecuda_ctx*, uint32_t*, uint32_t) { return 1; }                     // (needs the device)
+//   u32 magic "RPF2", pathCount, pointCount, verbCount, frameWidth, frameHeight, clipRectCount, gradientPaintCount;
+//   u32 imagePaintCount, 0, 0, 0;
+//   rivecuda_path paths[]; u8 verbs[] (padded to 4); float points[][2];
+//   rivecuda_clip_rect clipRects[]; rivecuda_gradient_paint gradientPaints[]; rivecuda_image_paint imagePaints[]
+// The tables of the next rivecuda_front_end_paths call, kept for its record ("RPF2" appends them).
+static std::vector<rivecuda_clip_rect> g_clipRects;
+static std::vector<rivecuda_gradient_paint> g_gradientPaints;
+static std::vector<rivecuda_image_paint> g_imagePaints;
+int rivecuda_front_end_clip_rects(rivecuda_ctx*, const rivecuda_clip_rect* rects, uint32_t count)
+{
+    g_clipRects.assign(rects, rects + count);
+    return 0;
+}
+int rivecuda_front_end_gradient_paints(rivecuda_ctx*, const rivecuda_gradient_paint* paints, uint32_t count)
+{
+    g_gradientPaints.assign(paints, paints + count);
+    return 0;
+}
+int rivecuda_front_end_image_paints(rivecuda_ctx*, const rivecuda_image_paint* paints, uint32_t count)
+{
+    g_imagePaints.assign(paints, paints + count);
+    return 0;
+}
+// (needs the device; the recorder answers "every path starts at patch 1" so that a recorded call can
+// go on to its flush, whose batches then mean nothing)
+int rivecuda_front_end_path_patches(rivecuda_ctx*, uint32_t* firstPatch, uint32_t pathCount)
+{
+    for (uint32_t i = 0; i <= pathCount; ++i)
+        firstPatch[i] = 1;
+    return 0;
+}
 int rivecuda_front_end_paths(rivecuda_ctx*,
                              const float* points,
                              uint32_t pointCount,
@@ -275,13 +300,17 @@ int rivecuda_front_end_paths(rivecuda_ctx*,
     FILE* f = fopen(out, "wb");
     if (f == nullptr)
         return fail("rivecuda_trace: cannot open $RIVECUDA_TRACE_FRONT_END_OUT");
-    const uint32_t header[8] = {0x31465052u, pathCount, pointCount, verbCount, frameWidth, frameHeight, 0u, 0u};
+    const uint32_t header[12] = {0x32465052u, pathCount, pointCount, verbCount, frameWidth, frameHeight, static_cast<uint32_t>(g_clipRects.size()),
+                                 static_cast<uint32_t>(g_gradientPaints.size()), static_cast<uint32_t>(g_imagePaints.size()), 0u, 0u, 0u};
     const uint8_t pad[4] = {0, 0, 0, 0};
     fwrite(header, sizeof(header), 1, f);
     fwrite(paths, sizeof(rivecuda_path), pathCount, f);
     fwrite(verbs, 1, verbCount, f);
     fwrite(pad, 1, (4 - verbCount % 4) % 4, f);
     fwrite(points, 8, pointCount, f);
+    fwrite(g_clipRects.data(), sizeof(rivecuda_clip_rect), g_clipRects.size(), f);
+    fwrite(g_gradientPaints.data(), sizeof(rivecuda_gradient_paint), g_gradientPaints.size(), f);
+    fwrite(g_imagePaints.data(), sizeof(rivecuda_image_paint), g_imagePaints.size(), f);
     fclose(f);
     memset(result, 0, sizeof(*result));
     result->path_count = 1; // the reserved record

@@ -132,20 +132,44 @@ def write_paths(path: str, dump: PathDump, thickness) -> None:
         f.write(b"".join(out))
 
 
-def load_front_end_call(path: str):
+CLIP_RECT_DTYPE = np.dtype([("inverse_matrix", "<f4", (6,)), ("inverse_fwidth", "<f4", (2,)), ("pixel_bounds", "<i4", (4,))])
+GRADIENT_PAINT_DTYPE = np.dtype([("paint_type", "<u4"), ("grad_texture_y", "<f4"), ("paint_matrix", "<f4", (6,)), ("grad_horizontal_span", "<f4", (2,))])
+IMAGE_PAINT_DTYPE = np.dtype([("image_matrix", "<f4", (6,)), ("image_texture_lod", "<f4"), ("reserved0", "<u4")])
+
+
+@dataclass
+class FrontEndTables:
+    """The tables a rivecuda_front_end_paths call refers to (rivecuda.h): clip rectangles
+    (path.stroke >> 8), gradient paints (path.fill_rule >> 8), image paints (path.cap >> 8)."""
+    clip_rects: np.ndarray
+    gradient_paints: np.ndarray
+    image_paints: np.ndarray
+
+
+def load_front_end_call(path: str, with_tables: bool = False):
     """Reads what the call recorder (librivecuda_trace.so with $RIVECUDA_TRACE_FRONT_END_OUT)
-    saw in rivecuda_front_end_paths: (PathDump, frame_width, frame_height)."""
+    saw in rivecuda_front_end_paths: (PathDump, frame_width, frame_height[, FrontEndTables])."""
     raw = open(path, "rb").read()
-    magic, n_paths, n_points, n_verbs, width, height, _, _ = struct.unpack_from("<8I", raw, 0)
-    if magic != 0x31465052:
+    magic, n_paths, n_points, n_verbs, width, height, n_clips, n_grads = struct.unpack_from("<8I", raw, 0)
+    if magic != 0x32465052:
         raise ValueError("not a recorded front-end call")
-    pos = 32
+    n_images = struct.unpack_from("<I", raw, 32)[0]
+    pos = 48
     paths = np.frombuffer(raw, dtype=PATH_DTYPE, count=n_paths, offset=pos).copy()
     pos += n_paths * PATH_DTYPE.itemsize
     verbs = np.frombuffer(raw, dtype=np.uint8, count=n_verbs, offset=pos).copy()
     pos += (n_verbs + 3) & ~3
     points = np.frombuffer(raw, dtype=np.float32, count=n_points * 2, offset=pos).reshape(-1, 2).copy()
-    return PathDump(paths, verbs, points, True), width, height
+    pos += n_points * 8
+    clips = np.frombuffer(raw, dtype=CLIP_RECT_DTYPE, count=n_clips, offset=pos).copy()
+    pos += n_clips * CLIP_RECT_DTYPE.itemsize
+    grads = np.frombuffer(raw, dtype=GRADIENT_PAINT_DTYPE, count=n_grads, offset=pos).copy()
+    pos += n_grads * GRADIENT_PAINT_DTYPE.itemsize
+    images = np.frombuffer(raw, dtype=IMAGE_PAINT_DTYPE, count=n_images, offset=pos).copy()
+    dump = PathDump(paths, verbs, points, True)
+    if with_tables:
+        return dump, width, height, FrontEndTables(clips, grads, images)
+    return dump, width, height
 
 
 def run(replayer, dump: PathDump, frame_width: int = 0, frame_height: int = 0) -> FrontEndResult:

@@ -200,6 +200,70 @@ def test_cpp_path_renderer_hands_over_what_the_reference_front_end_saw(scene, go
         assert np.array_equal(a, b), field
 
 
+@pytest.mark.parametrize("scene", ["f1o", "f1b", "f1c", "f1w", "f1g", "f1p", "f1i"])
+def test_cpp_path_renderer_and_core_reproduce_the_reference_records(scene, tmp_path):
+    """The device front end's round-2 features -- modulated opacity, blend modes, clip rectangles,
+    clockwise fills, gradients, clip PATHS, image paints -- pinned on the CPU: the scene is drawn
+    through CudaPathRenderer on the call recorder; what it hands to rivecuda_front_end_paths (paths,
+    incl. the clipUpdate paths it inserts, and the clip-rectangle / gradient / image tables) goes
+    through the host build of the kernels' core; the spans, contours, path, paint and paint-aux
+    records must equal, byte for byte, what the reference's own front end wrote for the same scene
+    (tests/golden/<scene>.rvct.xz) -- clip IDs, ramp rows, paint matrices, image LODs and all -- and
+    so must the GradientSpans CudaPathRenderer wrote and the rows they fill."""
+    import subprocess
+    from conftest import ROOT
+    player = os.path.join(ROOT, "rive-runtime_b200", "_build", "rive_cuda_player")
+    recorder = os.path.join(ROOT, "rive-runtime_b200", "_build", "librivecuda_trace.so")
+    if not os.path.exists(player) or not os.path.exists(recorder):
+        pytest.skip("scene player not built (needs the reference tree at build time)")
+    call, trace = str(tmp_path / "call.rpf"), str(tmp_path / "device.rvct")
+    env = dict(os.environ, RIVECUDA_LIB=recorder, RIVECUDA_TRACE_OUT=trace, RIVECUDA_TRACE_FRONT_END_OUT=call)
+    subprocess.check_call([player, "--scene", scene, "--gpu-front-end", "--budget-ms", "0"], env=env, stdout=subprocess.DEVNULL, timeout=120)
+    dump, width, height, tables = F.load_front_end_call(call, with_tables=True)
+    out = front_end_host.run(dump, width, height, tables)
+    res = out.result
+
+    recs = T.parse(os.path.join(GOLDEN, scene + ".rvct.xz"))
+    host = {r.fields["kind"]: r.data for r in recs if r.tag == T.BUFFER_UNMAP}
+    (flush,) = [r.fields["flush"] for r in recs if r.tag == T.FLUSH]
+    d = flush.desc
+    assert (res.path_count, res.contour_count, res.tess_vertex_span_count, res.tess_data_height) == (
+        d.path_count, d.contour_count, d.tess_vertex_span_count, d.tess_data_height)
+    assert res.patch_count == sum(b.element_count for b in flush.batches)
+    n = res.tess_vertex_span_count
+    want = np.frombuffer(host[6].tobytes()[:n * 64], dtype=np.uint32).reshape(-1, 16)
+    assert np.array_equal(out.spans[:n], want)
+    want = np.frombuffer(host[4].tobytes()[:res.contour_count * 16], dtype=np.uint32).reshape(-1, 4)
+    assert np.array_equal(out.contours[:res.contour_count], want)
+    n = res.path_count
+    want = np.frombuffer(host[1].tobytes()[:n * 64], dtype=np.uint32).reshape(-1, 16)
+    assert np.array_equal(out.path_data[1:n, :8], want[1:, :8])
+    paint = np.frombuffer(host[2].tobytes()[:n * 8], dtype=np.uint32).reshape(-1, 2)
+    assert np.array_equal(out.paint_data[1:n], paint[1:])
+    # PaintAuxData: the words a paint of each kind defines (the reference leaves the others unwritten)
+    aux = np.frombuffer(host[3].tobytes()[:n * 128], dtype=np.uint32).reshape(-1, 32)
+    kind, flags = paint[:, 0] & 0xf, paint[:, 0]
+    gradient, clipped, image = np.isin(kind, (2, 3)), (flags & 0x400) != 0, (flags & 0x800) != 0
+    gradient[0] = clipped[0] = image[0] = False
+    assert np.array_equal(out.paint_aux[:n][gradient][:, 0:8], aux[gradient][:, 0:8])
+    assert np.array_equal(out.paint_aux[:n][clipped][:, 8:16], aux[clipped][:, 8:16])
+    assert np.array_equal(out.paint_aux[:n][image][:, 16:23], aux[image][:, 16:23])
+    expect = {"f1c": clipped, "f1g": gradient, "f1i": image, "f1p": (kind == 0)}.get(scene)
+    if expect is not None:
+        assert expect.sum() > 50  # the scene does exercise its feature (f1p: clipUpdate paints)
+    # what CudaPathRenderer wrote itself: the colour-ramp spans and the flush's gradient counts
+    device_recs = T.parse(trace)
+    device_host = {r.fields["kind"]: r.data for r in device_recs if r.tag == T.BUFFER_UNMAP}
+    (device_flush,) = [r.fields["flush"] for r in device_recs if r.tag == T.FLUSH]
+    dd = device_flush.desc
+    assert (dd.grad_span_count, dd.grad_data_height) == (d.grad_span_count, d.grad_data_height)
+    if d.grad_span_count:
+        first = d.first_grad_span * 16
+        assert device_host[5].tobytes()[:d.grad_span_count * 16] == host[5].tobytes()[first:first + d.grad_span_count * 16]
+        resize = lambda rs: [r.fields["height"] for r in rs if r.tag == T.RESIZE_GRADIENT][-1]
+        assert resize(device_recs) == resize(recs)  # the allocated height the paints are normalised by
+
+
 @pytest.mark.parametrize("seed", [11, 12, 13, 14, 15, 16, 17, 18])
 def test_front_end_core_matches_the_reference_on_random_paths(seed, tmp_path):
     """Fuzz, pinned on the reference itself: random RawPaths (lines, generic / cusped / looping /
