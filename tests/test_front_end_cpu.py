@@ -200,6 +200,53 @@ def test_cpp_path_renderer_hands_over_what_the_reference_front_end_saw(scene, go
         assert np.array_equal(a, b), field
 
 
+def _compare_device_front_end_call_with_reference_trace(call, trace, recs):
+    """call / trace: what the call recorder wrote for a --gpu-front-end run; recs: the flush trace of
+    the reference front end for the same frame. Returns how many paints of each kind were compared."""
+    dump, width, height, tables = F.load_front_end_call(call, with_tables=True)
+    out = front_end_host.run(dump, width, height, tables)
+    res = out.result
+
+    host = {r.fields["kind"]: r.data for r in recs if r.tag == T.BUFFER_UNMAP}
+    flush = [r.fields["flush"] for r in recs if r.tag == T.FLUSH][-1]
+    d = flush.desc
+    assert (res.path_count, res.contour_count, res.tess_vertex_span_count, res.tess_data_height) == (
+        d.path_count, d.contour_count, d.tess_vertex_span_count, d.tess_data_height)
+    assert res.patch_count == sum(b.element_count for b in flush.batches if b.draw_type == 0)
+    n = res.tess_vertex_span_count
+    want = np.frombuffer(host[6].tobytes()[:n * 64], dtype=np.uint32).reshape(-1, 16)
+    assert np.array_equal(out.spans[:n], want)
+    want = np.frombuffer(host[4].tobytes()[:res.contour_count * 16], dtype=np.uint32).reshape(-1, 4)
+    assert np.array_equal(out.contours[:res.contour_count], want)
+    n = res.path_count
+    want = np.frombuffer(host[1].tobytes()[:n * 64], dtype=np.uint32).reshape(-1, 16)
+    assert np.array_equal(out.path_data[1:n, :8], want[1:, :8])
+    paint = np.frombuffer(host[2].tobytes()[:n * 8], dtype=np.uint32).reshape(-1, 2)
+    assert np.array_equal(out.paint_data[1:n], paint[1:])
+    # PaintAuxData: the words a paint of each kind defines (the reference leaves the others unwritten)
+    aux = np.frombuffer(host[3].tobytes()[:n * 128], dtype=np.uint32).reshape(-1, 32)
+    kind, flags = paint[:, 0] & 0xf, paint[:, 0]
+    gradient, clipped, image = np.isin(kind, (2, 3)), (flags & 0x400) != 0, (flags & 0x800) != 0
+    gradient[0] = clipped[0] = image[0] = False
+    assert np.array_equal(out.paint_aux[:n][gradient][:, 0:8], aux[gradient][:, 0:8])
+    assert np.array_equal(out.paint_aux[:n][clipped][:, 8:16], aux[clipped][:, 8:16])
+    assert np.array_equal(out.paint_aux[:n][image][:, 16:23], aux[image][:, 16:23])
+    counts = {"gradient": int(gradient.sum()), "clip_rect": int(clipped.sum()), "image": int(image.sum()), "clip_update": int((kind[1:] == 0).sum()),
+              "clipped_by_path": int(((flags[1:] >> 16) != 0).sum()), "paths": int(n - 1)}
+    # what CudaPathRenderer wrote itself: the colour-ramp spans and the flush's gradient counts
+    device_recs = T.parse(trace)
+    device_host = {r.fields["kind"]: r.data for r in device_recs if r.tag == T.BUFFER_UNMAP}
+    device_flush = [r.fields["flush"] for r in device_recs if r.tag == T.FLUSH][-1]
+    dd = device_flush.desc
+    assert (dd.grad_span_count, dd.grad_data_height) == (d.grad_span_count, d.grad_data_height)
+    if d.grad_span_count:
+        first = d.first_grad_span * 16
+        assert device_host[5].tobytes()[:d.grad_span_count * 16] == host[5].tobytes()[first:first + d.grad_span_count * 16]
+        resize = lambda rs: [r.fields["height"] for r in rs if r.tag == T.RESIZE_GRADIENT][-1]
+        assert resize(device_recs) == resize(recs)  # the allocated height the paints are normalised by
+    return counts
+
+
 @pytest.mark.parametrize("scene", ["f1o", "f1b", "f1c", "f1w", "f1g", "f1p", "f1i"])
 def test_cpp_path_renderer_and_core_reproduce_the_reference_records(scene, tmp_path):
     """The device front end's round-2 features -- modulated opacity, blend modes, clip rectangles,
@@ -219,49 +266,44 @@ def test_cpp_path_renderer_and_core_reproduce_the_reference_records(scene, tmp_p
     call, trace = str(tmp_path / "call.rpf"), str(tmp_path / "device.rvct")
     env = dict(os.environ, RIVECUDA_LIB=recorder, RIVECUDA_TRACE_OUT=trace, RIVECUDA_TRACE_FRONT_END_OUT=call)
     subprocess.check_call([player, "--scene", scene, "--gpu-front-end", "--budget-ms", "0"], env=env, stdout=subprocess.DEVNULL, timeout=120)
-    dump, width, height, tables = F.load_front_end_call(call, with_tables=True)
-    out = front_end_host.run(dump, width, height, tables)
-    res = out.result
-
     recs = T.parse(os.path.join(GOLDEN, scene + ".rvct.xz"))
-    host = {r.fields["kind"]: r.data for r in recs if r.tag == T.BUFFER_UNMAP}
-    (flush,) = [r.fields["flush"] for r in recs if r.tag == T.FLUSH]
-    d = flush.desc
-    assert (res.path_count, res.contour_count, res.tess_vertex_span_count, res.tess_data_height) == (
-        d.path_count, d.contour_count, d.tess_vertex_span_count, d.tess_data_height)
-    assert res.patch_count == sum(b.element_count for b in flush.batches)
-    n = res.tess_vertex_span_count
-    want = np.frombuffer(host[6].tobytes()[:n * 64], dtype=np.uint32).reshape(-1, 16)
-    assert np.array_equal(out.spans[:n], want)
-    want = np.frombuffer(host[4].tobytes()[:res.contour_count * 16], dtype=np.uint32).reshape(-1, 4)
-    assert np.array_equal(out.contours[:res.contour_count], want)
-    n = res.path_count
-    want = np.frombuffer(host[1].tobytes()[:n * 64], dtype=np.uint32).reshape(-1, 16)
-    assert np.array_equal(out.path_data[1:n, :8], want[1:, :8])
-    paint = np.frombuffer(host[2].tobytes()[:n * 8], dtype=np.uint32).reshape(-1, 2)
-    assert np.array_equal(out.paint_data[1:n], paint[1:])
-    # PaintAuxData: the words a paint of each kind defines (the reference leaves the others unwritten)
-    aux = np.frombuffer(host[3].tobytes()[:n * 128], dtype=np.uint32).reshape(-1, 32)
-    kind, flags = paint[:, 0] & 0xf, paint[:, 0]
-    gradient, clipped, image = np.isin(kind, (2, 3)), (flags & 0x400) != 0, (flags & 0x800) != 0
-    gradient[0] = clipped[0] = image[0] = False
-    assert np.array_equal(out.paint_aux[:n][gradient][:, 0:8], aux[gradient][:, 0:8])
-    assert np.array_equal(out.paint_aux[:n][clipped][:, 8:16], aux[clipped][:, 8:16])
-    assert np.array_equal(out.paint_aux[:n][image][:, 16:23], aux[image][:, 16:23])
-    expect = {"f1c": clipped, "f1g": gradient, "f1i": image, "f1p": (kind == 0)}.get(scene)
+    counts = _compare_device_front_end_call_with_reference_trace(call, trace, recs)
+    expect = {"f1c": "clip_rect", "f1g": "gradient", "f1i": "image", "f1p": "clip_update"}.get(scene)
     if expect is not None:
-        assert expect.sum() > 50  # the scene does exercise its feature (f1p: clipUpdate paints)
-    # what CudaPathRenderer wrote itself: the colour-ramp spans and the flush's gradient counts
-    device_recs = T.parse(trace)
-    device_host = {r.fields["kind"]: r.data for r in device_recs if r.tag == T.BUFFER_UNMAP}
-    (device_flush,) = [r.fields["flush"] for r in device_recs if r.tag == T.FLUSH]
-    dd = device_flush.desc
-    assert (dd.grad_span_count, dd.grad_data_height) == (d.grad_span_count, d.grad_data_height)
-    if d.grad_span_count:
-        first = d.first_grad_span * 16
-        assert device_host[5].tobytes()[:d.grad_span_count * 16] == host[5].tobytes()[first:first + d.grad_span_count * 16]
-        resize = lambda rs: [r.fields["height"] for r in rs if r.tag == T.RESIZE_GRADIENT][-1]
-        assert resize(device_recs) == resize(recs)  # the allocated height the paints are normalised by
+        assert counts[expect] > 50  # the scene does exercise its feature
+
+
+RIV_ASSETS = ["off_road_car", "bullet_man", "juice", "shapetest", "fix_rectangle", "follow_path_solos", "nested_artboard_opacity", "lock_icon_demo",
+              "solos_collapse_tests", "group_effect", "tape", "image_fit_alignment_2"]
+
+
+@pytest.mark.parametrize("name", RIV_ASSETS)
+def test_riv_asset_records_of_both_front_ends_match(name, tmp_path):
+    """The same comparison on real content, without a GPU: frame 20 of a .riv asset (the reference's
+    own test assets, imported and animated by its unmodified core runtime) is drawn on the call
+    recorder through the reference front end (midpoint fans only: --budget-ms 0) and through
+    CudaPathRenderer + the host build of the kernels' core; the records must be the same bytes.
+    off_road_car and bullet_man bring gradients and nested clip paths, juice gradients, tape and
+    image_fit_alignment_2 image meshes between the paths. Skips without the assets
+    (tools/fetch_riv_assets.sh) or the player."""
+    import subprocess
+    from conftest import ROOT
+    player = os.path.join(ROOT, "rive-runtime_b200", "_build", "rive_cuda_player")
+    recorder = os.path.join(ROOT, "rive-runtime_b200", "_build", "librivecuda_trace.so")
+    asset = os.path.join(ROOT, "tests", "_riv_assets", name + ".riv")
+    if not os.path.exists(player) or not os.path.exists(recorder) or not os.path.exists(asset):
+        pytest.skip("scene player or .riv asset not present")
+    reference, call, trace = str(tmp_path / "reference.rvct"), str(tmp_path / "call.rpf"), str(tmp_path / "device.rvct")
+    common = [player, "--scene", "riv:" + asset, "--frames", "20", "--budget-ms", "0"]
+    subprocess.check_call(common, env=dict(os.environ, RIVECUDA_LIB=recorder, RIVECUDA_TRACE_OUT=reference), stdout=subprocess.DEVNULL, timeout=120)
+    subprocess.check_call(common + ["--gpu-front-end"], env=dict(os.environ, RIVECUDA_LIB=recorder, RIVECUDA_TRACE_OUT=trace, RIVECUDA_TRACE_FRONT_END_OUT=call),
+                          stdout=subprocess.DEVNULL, timeout=120)
+    counts = _compare_device_front_end_call_with_reference_trace(call, trace, T.parse(reference))
+    assert counts["paths"] > 0
+    if name in ("off_road_car", "bullet_man", "juice"):
+        assert counts["gradient"] > 0
+    if name in ("off_road_car", "bullet_man"):
+        assert counts["clip_update"] > 0 and counts["clipped_by_path"] > 0
 
 
 @pytest.mark.parametrize("seed", [11, 12, 13, 14, 15, 16, 17, 18])
