@@ -1001,6 +1001,13 @@ FE_HD uint32_t place_path(const rivecuda_path& path, const V2* points, const uin
 // end. result[0] = span count, result[1] = total tessellation vertices incl. padding.
 FE_HD void emit_padding_spans(uint32_t* spans, uint32_t midpointFanTessVertices, uint32_t* result)
 {
+    if (midpointFanTessVertices == 0u)
+    {
+        // Nothing is tessellated: no padding either, and a tessellation texture of height 0
+        // (LogicalFlush::layoutResources, render_context.cpp:1150-1185).
+        result[0] = result[1] = 0u;
+        return;
+    }
     constexpr uint32_t kOuterPatchSpan = 17; // gpu::OuterCubicPatchSegmentSpanPlusJoin
     const uint32_t fanEnd = kPatchSpan + midpointFanTessVertices;
     const uint32_t interior = (kOuterPatchSpan - fanEnd % kOuterPatchSpan) % kOuterPatchSpan;

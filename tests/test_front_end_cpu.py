@@ -207,7 +207,9 @@ def _compare_device_front_end_call_with_reference_trace(call, trace, recs):
     out = front_end_host.run(dump, width, height, tables)
     res = out.result
 
-    host = {r.fields["kind"]: r.data for r in recs if r.tag == T.BUFFER_UNMAP}
+    empty = np.zeros(0, np.uint8)
+    host = {kind: empty for kind in range(9)}  # (an empty frame unmaps nothing)
+    host.update({r.fields["kind"]: r.data for r in recs if r.tag == T.BUFFER_UNMAP})
     flush = [r.fields["flush"] for r in recs if r.tag == T.FLUSH][-1]
     d = flush.desc
     assert (res.path_count, res.contour_count, res.tess_vertex_span_count, res.tess_data_height) == (
@@ -235,7 +237,8 @@ def _compare_device_front_end_call_with_reference_trace(call, trace, recs):
               "clipped_by_path": int(((flags[1:] >> 16) != 0).sum()), "paths": int(n - 1)}
     # what CudaPathRenderer wrote itself: the colour-ramp spans and the flush's gradient counts
     device_recs = T.parse(trace)
-    device_host = {r.fields["kind"]: r.data for r in device_recs if r.tag == T.BUFFER_UNMAP}
+    device_host = {kind: empty for kind in range(9)}
+    device_host.update({r.fields["kind"]: r.data for r in device_recs if r.tag == T.BUFFER_UNMAP})
     device_flush = [r.fields["flush"] for r in device_recs if r.tag == T.FLUSH][-1]
     dd = device_flush.desc
     assert (dd.grad_span_count, dd.grad_data_height) == (d.grad_span_count, d.grad_data_height)
