@@ -87,6 +87,8 @@ std::unique_ptr<rive::Renderer> TestingWindowCUDA::beginFrame(
         .strokesDisabled = options.strokesDisabled,
         .clockwiseFillOverride = options.clockwiseFillOverride || m_clockwiseFillOverride,
     };
+    if (m_hasBudgetOverride)
+        frameDescriptor.triangulationThresholds.frameBudgetMs = m_budgetOverride;
     frameDescriptor.virtualTileWidth = m_virtualTileWidth;
     frameDescriptor.virtualTileHeight = m_virtualTileHeight;
     if (m_gpuFrontEnd)

@@ -36,6 +36,13 @@ public:
     // --gpu-front-end: beginFrame() hands out a CudaPathRenderer; endFrame()
     // aborts if the frame contained anything but plain fills and strokes.
     void setGpuFrontEnd(bool enabled) { m_gpuFrontEnd = enabled; }
+    // --budget-ms given on the command line: it also applies to frames whose FrameOptions carry
+    // thresholds of their own (the GMs begin their frames themselves).
+    void setTriangulationBudgetOverride(float ms)
+    {
+        m_budgetOverride = ms;
+        m_hasBudgetOverride = true;
+    }
     // Sweeps: a frame CudaPathRenderer refuses is reported here instead of aborting.
     void setSoftRefusal(bool enabled) { m_softRefusal = enabled; }
     bool lastFrameRefused() const { return m_lastFrameRefused; }
@@ -52,6 +59,8 @@ public:
 private:
     struct PathDumpSink* m_pathDump = nullptr;
     bool m_gpuFrontEnd = false;
+    bool m_hasBudgetOverride = false;
+    float m_budgetOverride = 0;
     bool m_softRefusal = false, m_lastFrameRefused = false;
     bool m_clockwiseFillOverride = false;
     uint32_t m_virtualTileWidth = 0, m_virtualTileHeight = 0;

@@ -4,6 +4,7 @@ segment count PathDraw::initForMidpointFan computed for it; the numpy restatemen
 formula (oracle/front_end_ref.py) must reproduce all of them bit for bit. Also checks the
 `--dump-paths` reader against the traces' path / contour counts."""
 import os
+import sys
 
 import numpy as np
 import pytest
@@ -307,6 +308,28 @@ def test_riv_asset_records_of_both_front_ends_match(name, tmp_path):
         assert counts["gradient"] > 0
     if name in ("off_road_car", "bullet_man"):
         assert counts["clip_update"] > 0 and counts["clipped_by_path"] > 0
+
+
+def test_gm_records_of_both_front_ends_match():
+    """The same comparison over every GM the scene player holds (the reference's own tests/gm sources,
+    compiled in place): 94 of them -- clips of every kind, blend modes, gradients, images, meshes,
+    degenerate strokes, huge paths -- write identical records through both front ends; the others
+    need feathers (18), more gradients than one gradient texture holds (4: the reference starts a new
+    logical flush there, CudaPathRenderer refuses the frame), or drive the RenderContext directly
+    instead of a Renderer (6: flushed twice per frame / retrofitcubictristrips)."""
+    import re
+    import subprocess
+    from conftest import ROOT
+    player = os.path.join(ROOT, "rive-runtime_b200", "_build", "rive_cuda_player")
+    if not os.path.exists(player):
+        pytest.skip("scene player not built (needs the reference tree at build time)")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "tools", "gm_records_sweep.py")], stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
+                         timeout=600).stdout.decode()
+    m = re.search(r"identical (\d+), differing (\d+), refused (\d+), skipped \(several flushes\) (\d+), failed (\d+)", out)
+    assert m is not None, out[-2000:]
+    identical, differing, refused, skipped, failed = (int(g) for g in m.groups())
+    assert differing == 0 and failed == 0, out[-3000:]
+    assert identical >= 90 and refused <= 25 and skipped <= 6
 
 
 @pytest.mark.parametrize("seed", [11, 12, 13, 14, 15, 16, 17, 18])
