@@ -699,11 +699,12 @@ int rivecuda_front_end_paths(rivecuda_ctx* ctx,
         return set_error("rivecuda_front_end_paths: bad arguments (a path's verbs need more points than the point array holds)");
     }
     // One flush holds what RenderContext::LogicalFlush::pushDraws admits (render_context.cpp:528-536):
-    // path ids fit the fp16 id encoding, contour ids 16 bits, the tessellation texture 2048 rows.
-    if (sums[2] > 30720u || sums[1] > 0xffffu || sums[5] > static_cast<uint32_t>(kTessWidth) * 2048u)
+    // path ids fit the fp16 id encoding (MaxPathID - 1 = 30719: one record is the flush's own,
+    // render_context.cpp:136-139), contour ids 16 bits, the tessellation texture 2048 rows.
+    if (sums[2] > 30719u || sums[1] > 0xffffu || sums[5] > static_cast<uint32_t>(kTessWidth) * 2048u)
     {
         set_error("rivecuda_front_end_paths: %u paths / %u contours / %u tessellation vertices exceed one flush "
-                  "(30720 / 65535 / 2048 x 2048); split the draw list as the reference starts a new logical flush",
+                  "(30719 / 65535 / 2048 x 2048); split the draw list as the reference starts a new logical flush",
                   sums[2], sums[1], sums[5]);
         // What the paths would have needed, so that the caller can size its next attempt.
         result->midpoint_fan_tess_vertex_count = sums[0];

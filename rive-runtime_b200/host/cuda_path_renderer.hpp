@@ -126,16 +126,36 @@ public:
                                                m_target->width(), m_target->height(), &bounds))
                 return;
         }
+        GradientDraw gradientDraw;
+        if (paint->getType() != PaintType::solidColor)
+        {
+            // PathDraw keeps the gradient with the modulated opacity folded into its colours
+            // (draw.cpp:580) and allocates its colour ramp when the draw is pushed. When the gradient
+            // texture is full the reference starts a new logical flush and pushes the draw again
+            // (RiveRenderer::clipAndPushDraw, rive_renderer.cpp:508-556): so does this renderer.
+            // (The ramp is allocated before the draw's clip updates are emitted -- they have no
+            // ramps, so the order among ramps is the reference's -- which leaves nothing to undo.)
+            gradientDraw.gradient = paint->getGradientWithOpacity(m_stack.back().opacity);
+            gradientDraw.matrix = m;
+            if (gradientDraw.gradient == nullptr)
+                return refuse("drawPath with a gradient paint that has no gradient");
+            if (!allocateGradient(gradientDraw.gradient.get(), &gradientDraw.location))
+            {
+                flushAndContinue();
+                if (!allocateGradient(gradientDraw.gradient.get(), &gradientDraw.location))
+                    return refuse("drawPath with a gradient that does not fit an empty gradient texture");
+            }
+        }
         if (state.clipStackHeight != 0)
         {
             const uint32_t clipID = applyClip(state.clipStackHeight);
             if (clipID == 0)
                 return refuse("drawPath under more clip updates than one flush has clip IDs");
             p.blend_mode |= clipID << 16;
-            // (applyClip appended the clip updates' verbs and points)
-            p.first_verb = static_cast<uint32_t>(m_verbs.size());
-            p.first_point = static_cast<uint32_t>(m_points.size());
         }
+        // (applyClip and a flush in between move where this path's verbs and points go)
+        p.first_verb = static_cast<uint32_t>(m_verbs.size());
+        p.first_point = static_cast<uint32_t>(m_points.size());
         if (paint->getImageTexture() != nullptr)
         {
             // An image paint (RenderPaint::modulatedImage, or drawImage below): the words
@@ -159,14 +179,7 @@ public:
         }
         if (paint->getType() != PaintType::solidColor)
         {
-            // PathDraw keeps the gradient with the modulated opacity folded into its colours
-            // (draw.cpp:580) and allocates its colour ramp when the draw is pushed.
-            GradientDraw draw;
-            draw.gradient = paint->getGradientWithOpacity(m_stack.back().opacity);
-            draw.matrix = m;
-            if (draw.gradient == nullptr || !allocateGradient(draw.gradient.get(), &draw.location))
-                return refuse("drawPath with more gradients than one gradient texture holds");
-            m_gradientDraws.push_back(std::move(draw));
+            m_gradientDraws.push_back(std::move(gradientDraw));
             p.fill_rule |= static_cast<uint32_t>(m_gradientDraws.size()) << 8;
         }
         for (PathVerb v : raw.verbs())
@@ -330,6 +343,40 @@ public:
             fprintf(stderr, "CudaPathRenderer: the frame contains %s; draw it with RiveRenderer\n", m_refused.c_str());
             return false;
         }
+        return flushCollected() && !m_flushFailed;
+    }
+
+private:
+    // What RenderContext::logicalFlush() is to RiveRenderer: draws what has been collected so far
+    // and goes on collecting on top of it (the frame ran out of something one flush holds: gradient
+    // texture rows). Colour ramps, image bindings and clip IDs do not outlive a flush: the clip
+    // stack's elements are rendered into the clip plane again when the next draw needs them.
+    void flushAndContinue()
+    {
+        if (!flushCollected())
+            m_flushFailed = true;
+        m_points.clear();
+        m_verbs.clear();
+        m_paths.clear();
+        m_gradientDraws.clear();
+        m_simpleGradients.clear();
+        m_simpleRamps.clear();
+        m_complexGradients.clear();
+        m_complexRamps.clear();
+        m_imagePaints.clear();
+        m_imageBindings.clear();
+        m_imageTextures.clear();
+        m_meshDraws.clear();
+        m_meshBuffers.clear();
+        m_clipContentID = 0;
+        m_clipCount = 0;
+        for (ClipElement& clip : m_clipStack)
+            clip.clipID = 0;
+        m_loadAction = LoadAction::preserveRenderTarget;
+    }
+
+    bool flushCollected()
+    {
         RenderContextCUDAImpl::PlainPathFrame frame;
         frame.renderTarget = m_target;
         frame.loadAction = m_loadAction;
@@ -607,7 +654,7 @@ private:
             return matrix_ == matrix && path_->getRawPathMutationID() == rawPathMutationID && path_->getFillRule() == fillRule;
         }
     };
-    constexpr static uint32_t kMaxClipID = 30720; // maxClipID == maxPathID (render_context.cpp:484)
+    constexpr static uint32_t kMaxClipID = 30719; // maxClipID == maxPathID (render_context.cpp:136-139, 484)
     std::vector<ClipElement> m_clipStack;
     uint32_t m_clipContentID = 0; // RenderContext::getClipContentID(): the clip ID now in the clip plane
     uint32_t m_clipCount = 0;
@@ -636,5 +683,6 @@ private:
     std::map<std::vector<uint32_t>, uint16_t> m_complexGradients;     // stops + colours -> row
     std::vector<rcp<const Gradient>> m_complexRamps;
     std::string m_refused;
+    bool m_flushFailed = false;
 };
 } // namespace rive::gpu

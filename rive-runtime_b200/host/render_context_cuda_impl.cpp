@@ -515,7 +515,7 @@ bool RenderContextCUDAImpl::flushPlainPaths(const PlainPathFrame& frame)
     // (render_context.cpp:528-536). The reference finds the split points while it pushes draws;
     // here the device counts, so a chunk that does not fit is halved and retried. Later chunks
     // preserve what the earlier ones drew.
-    constexpr size_t kMaxPathsPerFlush = 30720;
+    constexpr size_t kMaxPathsPerFlush = 30719; // RenderContext::m_maxPathID (render_context.cpp:136-139)
     size_t first = 0;
     size_t chunk = std::min(frame.pathCount, kMaxPathsPerFlush);
     bool firstFlush = true;
