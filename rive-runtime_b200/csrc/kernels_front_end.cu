@@ -529,6 +529,9 @@ int rivecuda_front_end_gradient_paints(rivecuda_ctx* ctx, const rivecuda_gradien
 {
     if (ctx == nullptr || (count != 0 && paints == nullptr))
         return set_error("rivecuda_front_end_gradient_paints: bad arguments");
+    for (uint32_t i = 0; i < count; ++i)
+        if (paints[i].paint_type != 2u && paints[i].paint_type != 3u)
+            return set_error("rivecuda_front_end_gradient_paints: record %u: paint_type %u is neither linear (2) nor radial (3)", i, paints[i].paint_type);
     ctx->frontEndGradientPaints.assign(paints, paints + count);
     return 0;
 }
