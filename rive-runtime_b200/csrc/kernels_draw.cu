@@ -1984,7 +1984,9 @@ int resolve_pending_flush(rivecuda_ctx* ctx)
         return 0;
     if (int s = ctx->tileEntries.reserve((static_cast<size_t>(entryCount) + 1) * sizeof(uint32_t)))
         return s;
-    return launch_tail(ctx);
+    if (int s = launch_tail(ctx))
+        return s;
+    return mark_flush_enqueued(ctx, false); // the flush reads its ring slots again: it is done later
 }
 } // namespace rivecuda
 

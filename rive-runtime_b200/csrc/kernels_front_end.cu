@@ -640,6 +640,8 @@ int rivecuda_front_end_paths(rivecuda_ctx* ctx,
     {
         BufferRing& ring = ctx->rings[kind];
         ring.current = (ring.current + 1) % kRingSize; // what map() does: a fresh ring slot
+        if (int s = rivecuda::wait_for_slot_readers(ctx, ring)) // the kernels below write it on the upload stream
+            return s;
     }
     // A call that fails below is followed by no flush: it hands its slots back, so that the
     // rings advance exactly once per flush (the pacing argument that follows depends on it;

@@ -167,8 +167,13 @@ void rivecuda_destroy(rivecuda_ctx* ctx)
                 cudaFreeHost(ring.host[i]);
             if (ring.device[i])
                 cudaFree(ring.device[i]);
+            if (ring.uploaded[i])
+                cudaEventDestroy(ring.uploaded[i]);
         }
     }
+    for (cudaEvent_t done : ctx->flushDone)
+        if (done)
+            cudaEventDestroy(done);
     cudaFree(ctx->patchVertices);
     cudaFree(ctx->patchIndices);
     cudaFree(ctx->patchDedup);
@@ -280,6 +285,41 @@ int rivecuda_set_static_tables(rivecuda_ctx* ctx,
     return 0;
 }
 
+extern "C++"
+{
+namespace rivecuda
+{
+int wait_for_slot_readers(rivecuda_ctx* ctx, BufferRing& ring)
+{
+    const uint64_t reader = ring.lastReaderFlush[ring.current];
+    if (reader == 0)
+        return 0;
+    // (the event of flush `reader - 1`, or of a later flush that took its place in the ring of
+    // events: later flushes finish later on the render stream, so either will do)
+    cudaEvent_t done = ctx->flushDone[(reader - 1) % rivecuda_ctx::kFlushEventRing];
+    if (done != nullptr)
+        RC_CUDA(cudaStreamWaitEvent(ctx->uploadStream, done, 0));
+    return 0;
+}
+
+int mark_flush_enqueued(rivecuda_ctx* ctx, bool newFlush)
+{
+    if (newFlush)
+        ++ctx->flushCounter;
+    if (ctx->flushCounter == 0)
+        return 0;
+    cudaEvent_t& done = ctx->flushDone[(ctx->flushCounter - 1) % rivecuda_ctx::kFlushEventRing];
+    if (done == nullptr)
+        RC_CUDA(cudaEventCreateWithFlags(&done, cudaEventDisableTiming));
+    RC_CUDA(cudaEventRecord(done, ctx->stream));
+    if (newFlush)
+        for (BufferRing& ring : ctx->rings)
+            ring.lastReaderFlush[ring.current] = ctx->flushCounter;
+    return 0;
+}
+} // namespace rivecuda
+} // extern "C++"
+
 int rivecuda_buffer_resize(rivecuda_ctx* ctx, uint32_t kind, size_t size)
 {
     if (int pending = rivecuda::resolve_pending_flush(ctx))
@@ -300,6 +340,7 @@ int rivecuda_buffer_resize(rivecuda_ctx* ctx, uint32_t kind, size_t size)
         if (ring.device[i])
             cudaFree(ring.device[i]);
         ring.host[i] = ring.device[i] = nullptr;
+        ring.lastReaderFlush[i] = 0; // (both streams are idle: nothing reads the new slots yet)
     }
     ring.capacity = size;
     ring.submittedBytes = 0;
@@ -323,6 +364,9 @@ int rivecuda_buffer_map(rivecuda_ctx* ctx, uint32_t kind, size_t size, void** ou
     ring.current = (ring.current + 1) % kRingSize;
     if (ring.host[ring.current] == nullptr)
         RC_CUDA(cudaHostAlloc(&ring.host[ring.current], ring.capacity, cudaHostAllocDefault));
+    // The caller is about to overwrite the pinned copy: its last upload must have left it.
+    if (ring.uploaded[ring.current] != nullptr)
+        RC_CUDA(cudaEventSynchronize(ring.uploaded[ring.current]));
     *out = ring.host[ring.current];
     return 0;
 }
@@ -336,12 +380,16 @@ int rivecuda_buffer_unmap(rivecuda_ctx* ctx, uint32_t kind, size_t size)
         return set_error("rivecuda_buffer_unmap: size %zu exceeds capacity %zu", size, ring.capacity);
     RC_CUDA(cudaSetDevice(ctx->device));
     // The H2D goes on the upload stream so that it overlaps the previous frame's kernels; the
-    // next flush waits for it (rivecuda_flush). The ring slot is not in use any more: two
-    // whole flushes, each with a stream synchronisation behind the older work, lie between
-    // two uses of a slot.
+    // next flush waits for it (rivecuda_flush). The device slot may still be read by the flush
+    // that used it three maps ago: the upload waits for that flush (BufferRing::lastReaderFlush).
     if (size > 0)
     {
+        if (int s = rivecuda::wait_for_slot_readers(ctx, ring))
+            return s;
         RC_CUDA(cudaMemcpyAsync(ring.device[ring.current], ring.host[ring.current], size, cudaMemcpyHostToDevice, ctx->uploadStream));
+        if (ring.uploaded[ring.current] == nullptr)
+            RC_CUDA(cudaEventCreateWithFlags(&ring.uploaded[ring.current], cudaEventDisableTiming));
+        RC_CUDA(cudaEventRecord(ring.uploaded[ring.current], ctx->uploadStream));
         ctx->uploadsPending = true;
     }
     ring.submittedBytes = size;
@@ -710,6 +758,8 @@ int rivecuda_flush(rivecuda_ctx* ctx,
     if (prof)
         RC_CUDA(cudaEventRecord(ctx->events[3], ctx->stream));
     if (int s = launch_draw_list(ctx, *desc, batches, batchCount))
+        return s;
+    if (int s = rivecuda::mark_flush_enqueued(ctx, true))
         return s;
     if (prof)
         ctx->timingsPending = true; // events[7] was recorded behind the raster kernel

@@ -54,6 +54,12 @@ struct BufferRing
     size_t capacity = 0;
     int current = 0;              // ring slot mapped / last submitted
     size_t submittedBytes = 0;
+    // Slot reuse is fenced explicitly (it used to rest on "every flush waits for its predecessor's
+    // tile counts", which a run of EMPTY flushes does not do): a slot remembers the last flush that
+    // read it, whoever writes it next makes the upload stream wait for that flush; the pinned copy
+    // of a slot is not handed out again before its last host-to-device copy has left it.
+    uint64_t lastReaderFlush[kRingSize] = {}; // 1 + rivecuda_ctx::flushCounter of that flush; 0: none
+    cudaEvent_t uploaded[kRingSize] = {};     // behind the slot's last H2D on the upload stream
 };
 
 // One record per logical batch after flattening the draw list for the device.
@@ -140,6 +146,10 @@ struct rivecuda_ctx
     cudaStream_t copyStream = nullptr;   // asynchronous target read-backs (D2H)
     cudaStream_t uploadStream = nullptr; // buffer ring uploads (H2D), overlapping the previous frame
     cudaEvent_t renderDone = nullptr, uploadDone = nullptr, countsReady = nullptr;
+    // flushDone[k % 8] is recorded on the render stream behind flush k (see BufferRing)
+    static constexpr int kFlushEventRing = 8;
+    cudaEvent_t flushDone[kFlushEventRing] = {};
+    uint64_t flushCounter = 0;
     PendingTail pendingTail;
     bool uploadsPending = false; // buffer uploads enqueued on copyStream since the last flush
     int smCount = 148;
@@ -208,4 +218,9 @@ int launch_draw_list(rivecuda_ctx* ctx,
                      const rivecuda_draw_batch* batches,
                      uint32_t batchCount);
 int resolve_pending_flush(rivecuda_ctx* ctx);
+// The upload stream waits for the flushes that read the current slot of `ring` (before it is written).
+int wait_for_slot_readers(rivecuda_ctx* ctx, BufferRing& ring);
+// Records flushDone for the flush that has just been enqueued (or re-enqueued its tail) and marks
+// the ring slots it reads.
+int mark_flush_enqueued(rivecuda_ctx* ctx, bool newFlush);
 } // namespace rivecuda

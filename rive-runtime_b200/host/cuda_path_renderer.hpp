@@ -42,7 +42,9 @@
 #include <array>
 #include <cfloat>
 #include <cmath>
+#include <functional>
 #include <map>
+#include <memory>
 #include <string>
 #include <unordered_map>
 #include <vector>
@@ -56,15 +58,63 @@ public:
         m_impl(impl), m_target(target), m_loadAction(loadAction), m_clearColor(clearColor)
     {}
 
-    void save() override { m_stack.push_back(m_stack.back()); }
+    // Draws this renderer cannot express (feathers) can be DELEGATED to the reference's own front
+    // end instead of refusing the frame: what has been collected so far is flushed, the draw goes
+    // through a RiveRenderer on the owning RenderContext into the same target (a flush of its own,
+    // LoadAction::preserveRenderTarget), and collecting goes on on top of it -- a frame may be cut
+    // into flushes anywhere, each composites in order (the reference cuts frames into logical
+    // flushes itself). begin(loadAction, clearColor) begins a frame on the RenderContext and returns
+    // a RiveRenderer for it; end() flushes it into the target. Without hooks such a frame is refused.
+    using BeginReferenceFrame = std::function<std::unique_ptr<Renderer>(LoadAction, ColorInt)>;
+    using EndReferenceFrame = std::function<void()>;
+    void setDelegate(BeginReferenceFrame begin, EndReferenceFrame end)
+    {
+        m_beginReference = std::move(begin);
+        m_endReference = std::move(end);
+    }
+    size_t delegatedDrawCount() const { return m_delegatedDraws; }
+
+    // save / restore / transform / clipPath / modulateOpacity are also kept as the calls they were,
+    // per open save() scope: replayed into a fresh RiveRenderer they rebuild its state with the very
+    // float operations that built it here (a closed scope leaves nothing behind).
+    void save() override
+    {
+        m_stack.push_back(m_stack.back());
+        m_scopes.emplace_back();
+        if (m_reference != nullptr)
+            m_reference->save();
+    }
     void restore() override
     {
         if (m_stack.size() > 1)
+        {
             m_stack.pop_back();
+            m_scopes.pop_back();
+            if (m_reference != nullptr)
+                m_reference->restore();
+        }
     }
-    void transform(const Mat2D& m) override { m_stack.back().matrix = m_stack.back().matrix * m; }
+    void transform(const Mat2D& m) override
+    {
+        m_stack.back().matrix = m_stack.back().matrix * m;
+        StateCall call;
+        call.kind = StateCall::Transform;
+        call.matrix = m;
+        m_scopes.back().push_back(call);
+        if (m_reference != nullptr)
+            m_reference->transform(m);
+    }
     // RiveRenderer::modulateOpacity (rive_renderer.cpp:115-119): part of the save / restore state.
-    void modulateOpacity(float opacity) override { m_stack.back().opacity = std::max(0.0f, m_stack.back().opacity * opacity); }
+    void modulateOpacity(float opacity) override
+    {
+        m_stack.back().opacity = std::max(0.0f, m_stack.back().opacity * opacity);
+        StateCall call;
+        call.kind = StateCall::ModulateOpacity;
+        call.opacity = opacity;
+        m_scopes.back().push_back(call);
+        if (m_reference != nullptr)
+            m_reference->modulateOpacity(opacity);
+    }
 
     void drawPath(RenderPath* renderPath, RenderPaint* renderPaint) override
     {
@@ -74,7 +124,15 @@ public:
         if (raw.empty() || (paint->getIsStroked() && !(paint->getThickness() > 0)) || !(paint->getFeather() >= 0))
             return;
         if (paint->getFeather() != 0)
-            return refuse("drawPath with a feather");
+        {
+            if (!m_beginReference)
+                return refuse("drawPath with a feather");
+            openReference();
+            m_reference->drawPath(renderPath, renderPaint);
+            ++m_delegatedDraws;
+            return;
+        }
+        closeReference(); // (a draw of our own: what was delegated before it is flushed first)
         if (paint->getType() != PaintType::solidColor && paint->getType() != PaintType::linearGradient && paint->getType() != PaintType::radialGradient)
             return refuse("drawPath with an unknown paint type");
         if (m_stack.back().overallClipPixelBounds.empty())
@@ -194,6 +252,14 @@ public:
     void clipPath(RenderPath* renderPath) override
     {
         auto* path = static_cast<RiveRenderPath*>(renderPath);
+        {
+            StateCall call;
+            call.kind = StateCall::ClipPath;
+            call.path = ref_rcp(renderPath);
+            m_scopes.back().push_back(std::move(call));
+            if (m_reference != nullptr)
+                m_reference->clipPath(renderPath);
+        }
         State& state = m_stack.back();
         if (state.overallClipPixelBounds.empty())
             return;
@@ -298,6 +364,7 @@ public:
         const State& state = m_stack.back();
         if (texture == nullptr || state.overallClipPixelBounds.empty())
             return;
+        closeReference();
         RenderContextCUDAImpl::PlainMeshDraw mesh;
         mesh.vertexBuffer = RenderContextCUDAImpl::renderBufferHandle(vertices.get());
         mesh.uvBuffer = RenderContextCUDAImpl::renderBufferHandle(uvCoords.get());
@@ -343,6 +410,12 @@ public:
             fprintf(stderr, "CudaPathRenderer: the frame contains %s; draw it with RiveRenderer\n", m_refused.c_str());
             return false;
         }
+        if (m_reference != nullptr)
+        {
+            // the frame ends with delegated draws: they are flushed, nothing of ours is left to draw
+            closeReference();
+            return !m_flushFailed;
+        }
         return flushCollected() && !m_flushFailed;
     }
 
@@ -351,6 +424,50 @@ private:
     // and goes on collecting on top of it (the frame ran out of something one flush holds: gradient
     // texture rows). Colour ramps, image bindings and clip IDs do not outlive a flush: the clip
     // stack's elements are rendered into the clip plane again when the next draw needs them.
+    // Delegation (setDelegate): opens a reference frame behind what has been collected so far and
+    // brings its RiveRenderer to this renderer's state; consecutive delegated draws share the frame.
+    void openReference()
+    {
+        if (m_reference != nullptr)
+            return;
+        if (!m_paths.empty() || !m_meshDraws.empty())
+            flushAndContinue();
+        m_reference = m_beginReference(m_loadAction, m_clearColor);
+        for (size_t scope = 0; scope < m_scopes.size(); ++scope)
+        {
+            if (scope != 0)
+                m_reference->save();
+            for (const StateCall& call : m_scopes[scope])
+            {
+                switch (call.kind)
+                {
+                    case StateCall::Transform:
+                        m_reference->transform(call.matrix);
+                        break;
+                    case StateCall::ClipPath:
+                        m_reference->clipPath(call.path.get());
+                        break;
+                    case StateCall::ModulateOpacity:
+                        m_reference->modulateOpacity(call.opacity);
+                        break;
+                }
+            }
+        }
+    }
+    void closeReference()
+    {
+        if (m_reference == nullptr)
+            return;
+        m_reference.reset();
+        m_endReference();
+        // The reference's flush rendered its own clips and ramps: nothing of ours survives it.
+        m_clipContentID = 0;
+        m_clipCount = 0;
+        for (ClipElement& clip : m_clipStack)
+            clip.clipID = 0;
+        m_loadAction = LoadAction::preserveRenderTarget;
+    }
+
     void flushAndContinue()
     {
         if (!flushCollected())
@@ -684,5 +801,23 @@ private:
     std::vector<rcp<const Gradient>> m_complexRamps;
     std::string m_refused;
     bool m_flushFailed = false;
+    // delegation
+    struct StateCall
+    {
+        enum Kind
+        {
+            Transform,
+            ClipPath,
+            ModulateOpacity
+        } kind = Transform;
+        Mat2D matrix;
+        rcp<RenderPath> path;
+        float opacity = 1.f;
+    };
+    std::vector<std::vector<StateCall>> m_scopes{1}; // one list per open save() scope, parallel to m_stack
+    BeginReferenceFrame m_beginReference;
+    EndReferenceFrame m_endReference;
+    std::unique_ptr<Renderer> m_reference; // open while consecutive draws are being delegated
+    size_t m_delegatedDraws = 0;
 };
 } // namespace rive::gpu

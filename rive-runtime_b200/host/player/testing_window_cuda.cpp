@@ -97,6 +97,20 @@ std::unique_ptr<rive::Renderer> TestingWindowCUDA::beginFrame(
                                                                m_renderTarget.get(),
                                                                frameDescriptor.loadAction,
                                                                frameDescriptor.clearColor);
+        // Feathers go through the reference's own front end, as flushes of their own in between
+        // (CudaPathRenderer::setDelegate); RIVECUDA_FRONT_END_NO_DELEGATE=1 refuses such frames instead.
+        if (getenv("RIVECUDA_FRONT_END_NO_DELEGATE") == nullptr)
+        {
+            pathRenderer->setDelegate(
+                [this, frameDescriptor](LoadAction loadAction, ColorInt clearColor) -> std::unique_ptr<rive::Renderer> {
+                    RenderContext::FrameDescriptor fd = frameDescriptor;
+                    fd.loadAction = loadAction;
+                    fd.clearColor = clearColor;
+                    m_renderContext->beginFrame(fd);
+                    return std::make_unique<RiveRenderer>(m_renderContext.get());
+                },
+                [this]() { flushPLSContext(nullptr); });
+        }
         m_pathRenderer = pathRenderer.get();
         return pathRenderer;
     }

@@ -199,6 +199,30 @@ def test_riv_assets_sweep_both_front_ends_in_one_process(built):
     assert report["identical"] == report["assets"] >= 10
 
 
+def test_riv_assets_with_feathers_are_drawn_by_delegation(built):
+    """Feathers are the one thing the device front end does not tessellate: CudaPathRenderer flushes
+    what it has, hands the feather draws to the reference's own front end on the same context and
+    target (a flush of their own), and goes on. The frame is then cut into several flushes -- up to
+    ~85 per frame in hunter_x_demo.riv, many of them empty: the run of empty flushes is what exposed
+    that ring-slot reuse was only paced implicitly -- each of which picks its rasteriser and packs its
+    own feather atlas, so the result may differ from the reference's single flush by an LSB or two:
+    every asset within 2/255, none refused."""
+    import json
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    player = os.path.join(root, "rive-runtime_b200", "_build", "rive_cuda_player")
+    assets = os.path.join(root, "tests", "_riv_assets", "feathers")
+    if not os.path.exists(player) or not os.path.isdir(assets) or len(os.listdir(assets)) < 4:
+        pytest.skip("scene player or .riv assets not present")
+    env = dict(os.environ, RIVECUDA_LIB=os.path.join(root, "rive-runtime_b200", "_build", "librivecuda.so"), RIVECUDA_SWEEP_TOLERANCE="2")
+    for _ in range(2):  # (the slot-reuse race was intermittent)
+        out = subprocess.run([player, "--scene", "rivs:" + assets, "--frames", "20", "--budget-ms", "0"], env=env, stdout=subprocess.PIPE,
+                             stderr=subprocess.DEVNULL, timeout=600)
+        report = json.loads(out.stdout.decode().strip().splitlines()[-1])
+        assert out.returncode == 0 and report["differing"] == 0 and report["failed"] == 0 and report["refused"] == 0, out.stdout.decode()[-1500:]
+        assert report["identical"] + report["within_tolerance"] == report["assets"] >= 4
+
+
 def test_front_end_refuses_what_one_flush_cannot_hold(built):
     """Error behaviour: more paths / contours / tessellation vertices than one logical flush admits
     (RenderContext::LogicalFlush::pushDraws, render_context.cpp:528-536) is an error with a

@@ -2,7 +2,8 @@
 """Dev tool (no GPU): like riv_records_sweep.py, for the scene player's GMs (the reference's own
 tests/gm sources) and synthetic scenes: each is drawn on the call recorder through the reference
 front end (--budget-ms 0) and through CudaPathRenderer + the host build of the kernels' core, and
-the records are compared byte for byte. Where both flush several times per frame (a frame
+the records are compared byte for byte (frames with feathers are refused here: RIVECUDA_FRONT_END_NO_DELEGATE;
+delegated draws are the reference front end's own). Where both flush several times per frame (a frame
 that needs more gradient rows than one texture holds), the last flush is compared; GMs that flush a
 different number of times (they drive the RenderContext directly) are skipped. usage: gm_records_sweep.py [scene ...]"""
 import os
@@ -32,7 +33,7 @@ with tempfile.TemporaryDirectory() as tmp:
             failed += 1
             print("FAILED", scene, a.stderr.decode(errors="replace")[-120:].strip())
             continue
-        b = subprocess.run(common + ["--gpu-front-end"], env=dict(os.environ, RIVECUDA_LIB=recorder, RIVECUDA_TRACE_OUT=trace, RIVECUDA_TRACE_FRONT_END_OUT=call),
+        b = subprocess.run(common + ["--gpu-front-end"], env=dict(os.environ, RIVECUDA_LIB=recorder, RIVECUDA_TRACE_OUT=trace, RIVECUDA_TRACE_FRONT_END_OUT=call, RIVECUDA_FRONT_END_NO_DELEGATE="1"),
                            stdout=subprocess.DEVNULL, stderr=subprocess.PIPE)
         if b.returncode != 0:
             refused += 1

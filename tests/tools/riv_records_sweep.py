@@ -2,7 +2,8 @@
 """Dev tool (no GPU): for every .riv of a directory, frame N is drawn on the call recorder through
 the reference front end (--budget-ms 0) and through CudaPathRenderer + the host build of the
 kernels' core, and the records (spans, contours, path / paint / paint-aux records, GradientSpans)
-are compared byte for byte (the comparison of tests/test_front_end_cpu.py).
+are compared byte for byte (frames with feathers are refused here: RIVECUDA_FRONT_END_NO_DELEGATE;
+delegated draws are the reference front end's own) (the comparison of tests/test_front_end_cpu.py).
 usage: riv_records_sweep.py <dir> [frame]"""
 import os
 import subprocess
@@ -34,7 +35,7 @@ with tempfile.TemporaryDirectory() as tmp:
             failed += 1
             print("FAILED", name, a.stderr.decode(errors="replace")[-120:].strip())
             continue
-        b = subprocess.run(common + ["--gpu-front-end"], env=dict(os.environ, RIVECUDA_LIB=recorder, RIVECUDA_TRACE_OUT=trace, RIVECUDA_TRACE_FRONT_END_OUT=call),
+        b = subprocess.run(common + ["--gpu-front-end"], env=dict(os.environ, RIVECUDA_LIB=recorder, RIVECUDA_TRACE_OUT=trace, RIVECUDA_TRACE_FRONT_END_OUT=call, RIVECUDA_FRONT_END_NO_DELEGATE="1"),
                            stdout=subprocess.DEVNULL, stderr=subprocess.PIPE)
         if b.returncode != 0:
             refused += 1

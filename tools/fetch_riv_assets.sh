@@ -11,4 +11,9 @@ for n in off_road_car bullet_man shapetest fix_rectangle follow_path_solos trim_
          nested_artboard_opacity lock_icon_demo follow_path_shapes solos_collapse_tests group_effect tape image_fit_alignment_2 juice; do
   cp "/root/reference/tests/unit_tests/assets/$n.riv" "$ROOT/tests/_riv_assets/"
 done
+# feathers: drawn by delegating the feather draws to the reference front end (several flushes per frame)
+mkdir -p "$ROOT/tests/_riv_assets/feathers"
+for n in coin path_effect_with_feathers ai_assitant bankcard rewards_demo hunter_x_demo; do
+  cp "/root/reference/tests/unit_tests/assets/$n.riv" "$ROOT/tests/_riv_assets/feathers/"
+done
 ls -la "$ROOT/tests/_riv_assets"
