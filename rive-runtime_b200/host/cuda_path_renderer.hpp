@@ -125,6 +125,12 @@ public:
             return;
         if (paint->getFeather() != 0)
         {
+            // RiveRenderer::drawPath does not draw feathered fills that are not clockwise
+            // (rive_renderer.cpp:163-171): no need to open a reference frame for those.
+            if (!paint->getIsStroked() && path->getFillRule() != FillRule::clockwise)
+                return;
+            if (m_stack.back().overallClipPixelBounds.empty())
+                return;
             if (!m_beginReference)
                 return refuse("drawPath with a feather");
             openReference();
