@@ -73,6 +73,17 @@ public:
         m_endReference = std::move(end);
     }
     size_t delegatedDrawCount() const { return m_delegatedDraws; }
+    // Optional: also delegate the fills the reference would draw by INTERIOR TRIANGULATION
+    // (TriangulationController::isEligible, triangulation_controller.hpp:70-77: >= 512 x 512 px under
+    // the default thresholds, at most 256 verbs). The device front end draws every fill as a midpoint
+    // fan, which is inside the reference's tessellation tolerance but not the same pixels; with this
+    // on, such fills go through the reference's triangulator (more flushes per frame, the reference's
+    // default pixels).
+    void setLargeFillDelegation(const TriangulationThresholds& thresholds)
+    {
+        m_delegateLargeFills = true;
+        m_thresholds = thresholds;
+    }
 
     // save / restore / transform / clipPath / modulateOpacity are also kept as the calls they were,
     // per open save() scope: replayed into a fresh RiveRenderer they rebuild its state with the very
@@ -137,6 +148,17 @@ public:
             m_reference->drawPath(renderPath, renderPaint);
             ++m_delegatedDraws;
             return;
+        }
+        if (m_delegateLargeFills && m_beginReference && !paint->getIsStroked() && !m_stack.back().overallClipPixelBounds.empty())
+        {
+            const float area = find_transformed_area(path->getBounds(), m_stack.back().matrix); // draw.cpp:518-520
+            if (m_thresholds.frameBudgetMs > 0 && area >= m_thresholds.minArea && raw.verbs().count() <= m_thresholds.maxVerbs)
+            {
+                openReference();
+                m_reference->drawPath(renderPath, renderPaint);
+                ++m_delegatedDraws;
+                return;
+            }
         }
         closeReference(); // (a draw of our own: what was delegated before it is flushed first)
         if (paint->getType() != PaintType::solidColor && paint->getType() != PaintType::linearGradient && paint->getType() != PaintType::radialGradient)
@@ -825,5 +847,7 @@ private:
     EndReferenceFrame m_endReference;
     std::unique_ptr<Renderer> m_reference; // open while consecutive draws are being delegated
     size_t m_delegatedDraws = 0;
+    bool m_delegateLargeFills = false;
+    TriangulationThresholds m_thresholds;
 };
 } // namespace rive::gpu

@@ -110,6 +110,8 @@ std::unique_ptr<rive::Renderer> TestingWindowCUDA::beginFrame(
                     return std::make_unique<RiveRenderer>(m_renderContext.get());
                 },
                 [this]() { flushPLSContext(nullptr); });
+            if (m_delegateLargeFills)
+                pathRenderer->setLargeFillDelegation(frameDescriptor.triangulationThresholds);
         }
         m_pathRenderer = pathRenderer.get();
         return pathRenderer;

@@ -44,6 +44,9 @@ public:
         m_hasBudgetOverride = true;
     }
     // Sweeps: a frame CudaPathRenderer refuses is reported here instead of aborting.
+    // --delegate-large-fills: CudaPathRenderer hands the fills the reference would triangulate to the
+    // reference front end too (CudaPathRenderer::setLargeFillDelegation).
+    void setDelegateLargeFills(bool enabled) { m_delegateLargeFills = enabled; }
     void setSoftRefusal(bool enabled) { m_softRefusal = enabled; }
     bool lastFrameRefused() const { return m_lastFrameRefused; }
 
@@ -62,6 +65,7 @@ private:
     bool m_hasBudgetOverride = false;
     float m_budgetOverride = 0;
     bool m_softRefusal = false, m_lastFrameRefused = false;
+    bool m_delegateLargeFills = false;
     bool m_clockwiseFillOverride = false;
     uint32_t m_virtualTileWidth = 0, m_virtualTileHeight = 0;
     class rive::gpu::CudaPathRenderer* m_pathRenderer = nullptr; // owned by beginFrame()'s caller

@@ -199,6 +199,28 @@ def test_riv_assets_sweep_both_front_ends_in_one_process(built):
     assert report["identical"] == report["assets"] >= 10
 
 
+def test_large_fills_can_be_delegated_to_the_reference_triangulator(built):
+    """With the reference's own (deterministic) triangulation thresholds, fills of 512 x 512 px and more
+    are interior-triangulated by the reference front end; the device front end draws midpoint fans,
+    which is the same shape to within the tessellation tolerance but not the same pixels (11 of these
+    15 assets differ at frame 45). `--delegate-large-fills` hands exactly those fills to the reference
+    front end (CudaPathRenderer::setLargeFillDelegation): every asset within 2/255 of the reference's
+    frame again (the frame is cut into flushes: see the feather test)."""
+    import json
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    player = os.path.join(root, "rive-runtime_b200", "_build", "rive_cuda_player")
+    assets = os.path.join(root, "tests", "_riv_assets")
+    if not os.path.exists(player) or not os.path.isdir(assets) or len([n for n in os.listdir(assets) if n.endswith(".riv")]) < 10:
+        pytest.skip("scene player or .riv assets not present")
+    env = dict(os.environ, RIVECUDA_LIB=os.path.join(root, "rive-runtime_b200", "_build", "librivecuda.so"), RIVECUDA_SWEEP_TOLERANCE="2")
+    out = subprocess.run([player, "--scene", "rivs:" + assets, "--frames", "45", "--delegate-large-fills"], env=env, stdout=subprocess.PIPE,
+                         stderr=subprocess.DEVNULL, timeout=600)
+    report = json.loads(out.stdout.decode().strip().splitlines()[-1])
+    assert out.returncode == 0 and report["differing"] == 0 and report["failed"] == 0 and report["refused"] == 0, out.stdout.decode()[-1500:]
+    assert report["identical"] + report["within_tolerance"] == report["assets"] >= 10
+
+
 def test_riv_assets_with_feathers_are_drawn_by_delegation(built):
     """Feathers are the one thing the device front end does not tessellate: CudaPathRenderer flushes
     what it has, hands the feather draws to the reference's own front end on the same context and
