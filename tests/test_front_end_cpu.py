@@ -312,6 +312,102 @@ def test_riv_asset_records_of_both_front_ends_match(name, tmp_path):
         assert counts["clip_update"] > 0 and counts["clipped_by_path"] > 0
 
 
+def _assert_last_flushes_identical(a, b):
+    """a, b: parsed traces; their last flushes -- descriptor, batches, atlas batches and every mapped
+    buffer -- must be the same bytes."""
+    import ctypes
+    fa = [r.fields["flush"] for r in a if r.tag == T.FLUSH][-1]
+    fb = [r.fields["flush"] for r in b if r.tag == T.FLUSH][-1]
+    raw = lambda st: bytes(ctypes.string_at(ctypes.addressof(st), ctypes.sizeof(st)))
+    da, db = fa.desc, fb.desc
+    for field, _ in type(da)._fields_:
+        if field in ("render_target",):
+            continue
+        va, vb = getattr(da, field), getattr(db, field)
+        va, vb = (list(va), list(vb)) if hasattr(va, "__len__") else (va, vb)
+        assert va == vb, field
+    assert len(fa.batches) == len(fb.batches) and all(raw(x) == raw(y) for x, y in zip(fa.batches, fb.batches))
+    assert [raw(x) for x in fa.atlas_fills] == [raw(x) for x in fb.atlas_fills]
+    assert [raw(x) for x in fa.atlas_strokes] == [raw(x) for x in fb.atlas_strokes]
+    ha = {r.fields["kind"]: r.data for r in a if r.tag == T.BUFFER_UNMAP}
+    hb = {r.fields["kind"]: r.data for r in b if r.tag == T.BUFFER_UNMAP}
+    assert ha.keys() == hb.keys() and da.path_count > 1
+    n = da.path_count
+    for kind in ha:
+        if kind == 3:
+            continue  # PaintAuxData: the reference leaves the words a paint does not define unwritten
+        if kind == 1:
+            # PathData: matrix, stroke radius, feather radius, z index always; the feather-atlas transform
+            # only where there is a feather (PathDraw leaves it uninitialised otherwise); the coverage
+            # buffer range belongs to a mode this backend does not advertise
+            pa = np.frombuffer(ha[1].tobytes()[:n * 64], dtype=np.uint32).reshape(-1, 16)[1:]
+            pb = np.frombuffer(hb[1].tobytes()[:n * 64], dtype=np.uint32).reshape(-1, 16)[1:]
+            assert np.array_equal(pa[:, :9], pb[:, :9])
+            feathered = pa[:, 7] != 0
+            assert np.array_equal(pa[feathered][:, 9:12], pb[feathered][:, 9:12])
+            continue
+        assert ha[kind].tobytes() == hb[kind].tobytes(), "buffer kind %d" % kind
+    aux_a = np.frombuffer(ha[3].tobytes()[:n * 128], dtype=np.uint32).reshape(-1, 32)
+    aux_b = np.frombuffer(hb[3].tobytes()[:n * 128], dtype=np.uint32).reshape(-1, 32)
+    assert np.array_equal(aux_a[1:, 8:16], aux_b[1:, 8:16])  # clip rectangle words (always written)
+
+
+@pytest.mark.parametrize("scene", ["gm:feather_strokes", "gm:feather_shapes", "gm:feather_polyshapes", "gm:feather_corner", "gm:feather_ellipse",
+                                   "gm:feather_cusp", "gm:feather_roundcorner", "gm:trickycubicstrokes_feather", "gm:interleavedfeather"])
+def test_delegated_feather_draws_reach_the_reference_front_end_unchanged(scene, tmp_path):
+    """Feather delegation, pinned on the CPU: CudaPathRenderer rebuilds the state of the RiveRenderer
+    it delegates to by replaying the calls of the scopes still open (save / transform / clipPath /
+    modulateOpacity). These GMs draw feathers only, so the whole frame is delegated: the flush the
+    reference front end writes BEHIND CudaPathRenderer must be, buffer for buffer and batch for batch,
+    the flush it writes when it is driven directly -- same matrices bit for bit, same clips, same
+    atlas allocations."""
+    import subprocess
+    from conftest import ROOT
+    player = os.path.join(ROOT, "rive-runtime_b200", "_build", "rive_cuda_player")
+    recorder = os.path.join(ROOT, "rive-runtime_b200", "_build", "librivecuda_trace.so")
+    if not os.path.exists(player) or not os.path.exists(recorder):
+        pytest.skip("scene player not built (needs the reference tree at build time)")
+    direct, delegated = str(tmp_path / "direct.rvct"), str(tmp_path / "delegated.rvct")
+    common = [player, "--scene", scene, "--budget-ms", "0"]
+    subprocess.check_call(common, env=dict(os.environ, RIVECUDA_LIB=recorder, RIVECUDA_TRACE_OUT=direct), stdout=subprocess.DEVNULL, timeout=120)
+    subprocess.check_call(common + ["--gpu-front-end"], env=dict(os.environ, RIVECUDA_LIB=recorder, RIVECUDA_TRACE_OUT=delegated,
+                                                              RIVECUDA_TRACE_FRONT_END_OUT=str(tmp_path / "call.rpf")),
+                          stdout=subprocess.DEVNULL, timeout=120)
+    a, b = T.parse(direct), T.parse(delegated)
+    assert sum(1 for r in a if r.tag == T.FLUSH) == 1 and sum(1 for r in b if r.tag == T.FLUSH) == 1
+    assert sum(1 for r in b if r.tag == T.PREPARE_TO_FLUSH) == 1  # the one flush is the delegated one
+    _assert_last_flushes_identical(a, b)
+
+
+@pytest.mark.parametrize("name", ["shapetest", "fix_rectangle"])
+def test_large_fills_delegated_to_the_reference_triangulator_are_its_own_draws(name, tmp_path):
+    """--delegate-large-fills on the CPU: with the reference's deterministic thresholds every fill of
+    these assets is interior-triangulated; delegated, the frame is the reference front end's own flush
+    (outer-curve patches + interior triangles), byte for byte."""
+    import subprocess
+    from conftest import ROOT
+    player = os.path.join(ROOT, "rive-runtime_b200", "_build", "rive_cuda_player")
+    recorder = os.path.join(ROOT, "rive-runtime_b200", "_build", "librivecuda_trace.so")
+    asset = os.path.join(ROOT, "tests", "_riv_assets", name + ".riv")
+    if not os.path.exists(player) or not os.path.exists(recorder) or not os.path.exists(asset):
+        pytest.skip("scene player or .riv asset not present")
+    direct, delegated = str(tmp_path / "direct.rvct"), str(tmp_path / "delegated.rvct")
+    common = [player, "--scene", "riv:" + asset, "--frames", "3"]
+    subprocess.check_call(common, env=dict(os.environ, RIVECUDA_LIB=recorder, RIVECUDA_TRACE_OUT=direct), stdout=subprocess.DEVNULL, timeout=120)
+    subprocess.check_call(common + ["--gpu-front-end", "--delegate-large-fills"],
+                          env=dict(os.environ, RIVECUDA_LIB=recorder, RIVECUDA_TRACE_OUT=delegated, RIVECUDA_TRACE_FRONT_END_OUT=str(tmp_path / "call.rpf")),
+                          stdout=subprocess.DEVNULL, timeout=120)
+    a, b = T.parse(direct), T.parse(delegated)
+    last = [r.fields["flush"] for r in a if r.tag == T.FLUSH][-1]
+    assert any(batch.draw_type == 3 for batch in last.batches)  # the reference did triangulate
+    if sum(1 for r in b if r.tag == T.FLUSH) == sum(1 for r in a if r.tag == T.FLUSH):
+        _assert_last_flushes_identical(a, b)  # (every draw of the frame was delegated)
+    else:
+        # some draws were CudaPathRenderer's own: the delegated flushes together still hold the triangulated fills
+        delegated_types = [batch.draw_type for r in b if r.tag == T.FLUSH for batch in r.fields["flush"].batches]
+        assert delegated_types.count(3) == [batch.draw_type for batch in last.batches].count(3) * sum(1 for r in a if r.tag == T.FLUSH)
+
+
 def test_gm_records_of_both_front_ends_match():
     """The same comparison over every GM the scene player holds (the reference's own tests/gm sources,
     compiled in place): 100 of them -- clips of every kind, blend modes, gradients, images, meshes,
