@@ -276,7 +276,7 @@ public:
 
     // Clip rectangles (the ENABLE_CLIP_RECT feature): what RiveRenderer::clipPath / clipRectImpl do
     // with an axis-aligned rectangle (rive_renderer.cpp:199-322). Any other clip is a clip PATH
-    // (stencil-like updates of the clip plane between the draws), which this renderer refuses.
+    // (updates of the clip plane between the draws): clipPathImpl / applyClip below.
     void clipPath(RenderPath* renderPath) override
     {
         auto* path = static_cast<RiveRenderPath*>(renderPath);
