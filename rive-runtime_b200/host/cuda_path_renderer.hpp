@@ -448,10 +448,6 @@ public:
     }
 
 private:
-    // What RenderContext::logicalFlush() is to RiveRenderer: draws what has been collected so far
-    // and goes on collecting on top of it (the frame ran out of something one flush holds: gradient
-    // texture rows). Colour ramps, image bindings and clip IDs do not outlive a flush: the clip
-    // stack's elements are rendered into the clip plane again when the next draw needs them.
     // Delegation (setDelegate): opens a reference frame behind what has been collected so far and
     // brings its RiveRenderer to this renderer's state; consecutive delegated draws share the frame.
     void openReference()
@@ -496,6 +492,11 @@ private:
         m_loadAction = LoadAction::preserveRenderTarget;
     }
 
+    // What RenderContext::logicalFlush() is to RiveRenderer: draws what has been collected so far
+    // and goes on collecting on top of it (the frame ran out of something one flush holds: gradient
+    // texture rows; or a draw is being delegated). Colour ramps, image bindings and clip IDs do not
+    // outlive a flush: the clip stack's elements are rendered into the clip plane again when the
+    // next draw needs them.
     void flushAndContinue()
     {
         if (!flushCollected())
