@@ -129,8 +129,11 @@ public:
 
     void drawPath(RenderPath* renderPath, RenderPaint* renderPaint) override
     {
-        auto* path = static_cast<RiveRenderPath*>(renderPath);
-        auto* paint = static_cast<RiveRenderPaint*>(renderPaint);
+        // (null or foreign objects are ignored, as RiveRenderer's LITE_RTTI_CAST_OR_RETURN does)
+        auto* path = lite_rtti_cast<RiveRenderPath*>(renderPath);
+        auto* paint = lite_rtti_cast<RiveRenderPaint*>(renderPaint);
+        if (path == nullptr || paint == nullptr)
+            return;
         const RawPath& raw = path->getRawPath();
         if (raw.empty() || (paint->getIsStroked() && !(paint->getThickness() > 0)) || !(paint->getFeather() >= 0))
             return;
@@ -279,7 +282,9 @@ public:
     // (updates of the clip plane between the draws): clipPathImpl / applyClip below.
     void clipPath(RenderPath* renderPath) override
     {
-        auto* path = static_cast<RiveRenderPath*>(renderPath);
+        auto* path = lite_rtti_cast<RiveRenderPath*>(renderPath);
+        if (path == nullptr)
+            return;
         {
             StateCall call;
             call.kind = StateCall::ClipPath;
@@ -354,7 +359,9 @@ public:
     // as it does in the reference.)
     void drawImage(const RenderImage* renderImage, ImageSampler sampler, BlendMode blendMode, float opacity) override
     {
-        auto* image = static_cast<const RiveRenderImage*>(renderImage);
+        auto* image = lite_rtti_cast<const RiveRenderImage*>(renderImage);
+        if (image == nullptr)
+            return;
         rcp<Texture> texture = image->refTexture();
         if (texture == nullptr)
             return;
@@ -387,7 +394,9 @@ public:
                        BlendMode blendMode,
                        float opacity) override
     {
-        auto* image = static_cast<const RiveRenderImage*>(renderImage);
+        auto* image = lite_rtti_cast<const RiveRenderImage*>(renderImage);
+        if (image == nullptr)
+            return;
         rcp<Texture> texture = image->refTexture();
         const State& state = m_stack.back();
         if (texture == nullptr || state.overallClipPixelBounds.empty())

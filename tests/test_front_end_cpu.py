@@ -408,6 +408,30 @@ def test_large_fills_delegated_to_the_reference_triangulator_are_its_own_draws(n
         assert delegated_types.count(3) == [batch.draw_type for batch in last.batches].count(3) * sum(1 for r in a if r.tag == T.FLUSH)
 
 
+def test_null_images_are_ignored_like_the_reference_does():
+    """Seven of the reference's .sriv silvers draw images that cannot be decoded here (null RenderImages):
+    RiveRenderer returns from drawImage (LITE_RTTI_CAST_OR_RETURN), and so must CudaPathRenderer (it
+    used to dereference them). image_fit_alignment.sriv is one of them; its records must match too."""
+    import subprocess
+    from conftest import ROOT
+    player = os.path.join(ROOT, "rive-runtime_b200", "_build", "rive_cuda_player")
+    recorder = os.path.join(ROOT, "rive-runtime_b200", "_build", "librivecuda_trace.so")
+    stream = "/root/reference/tests/unit_tests/silvers/image_fit_alignment.sriv"
+    if not os.path.exists(player) or not os.path.exists(recorder) or not os.path.exists(stream):
+        pytest.skip("scene player or the reference's silvers not present")
+    import tempfile
+    with tempfile.TemporaryDirectory() as tmp:
+        reference, call, trace = os.path.join(tmp, "reference.rvct"), os.path.join(tmp, "call.rpf"), os.path.join(tmp, "device.rvct")
+        common = [player, "--scene", "sriv:" + stream, "--frames", "0", "--budget-ms", "0"]
+        subprocess.check_call(common, env=dict(os.environ, RIVECUDA_LIB=recorder, RIVECUDA_TRACE_OUT=reference), stdout=subprocess.DEVNULL,
+                              stderr=subprocess.DEVNULL, timeout=120)
+        subprocess.check_call(common + ["--gpu-front-end"], env=dict(os.environ, RIVECUDA_LIB=recorder, RIVECUDA_TRACE_OUT=trace,
+                                                                  RIVECUDA_TRACE_FRONT_END_OUT=call), stdout=subprocess.DEVNULL,
+                              stderr=subprocess.DEVNULL, timeout=120)
+        counts = _compare_device_front_end_call_with_reference_trace(call, trace, T.parse(reference))
+    assert counts["paths"] > 0
+
+
 def test_gm_records_of_both_front_ends_match():
     """The same comparison over every GM the scene player holds (the reference's own tests/gm sources,
     compiled in place): 100 of them -- clips of every kind, blend modes, gradients, images, meshes,
