@@ -3,10 +3,12 @@ the scene player; GPU: device build against the host build)."""
 import numpy as np
 
 
-def random_paths(seed, n_paths, strokes=True, width=3840, height=2160):
+def random_paths(seed, n_paths, strokes=True, width=3840, height=2160, clockwise=False):
     """Random RawPaths in the dump format: lines, cubics (generic, cusps, loops, degenerate),
     closed / open / move-only contours, random matrices and stroke styles. Returns the PathDump
-    and the stroke thickness per path (0 for fills)."""
+    and the stroke thickness per path (0 for fills). clockwise: a third of the fills are
+    FillRule::clockwise and a third of all matrices left-handed (clockwise fills flip their contour
+    directions and negate their coverage there)."""
     from rive_runtime_b200 import front_end as F
     rng = np.random.default_rng(seed)
     verbs, points, paths = [], [], np.zeros(n_paths, dtype=F.PATH_DTYPE)
@@ -52,13 +54,16 @@ def random_paths(seed, n_paths, strokes=True, width=3840, height=2160):
                       rng.uniform(0, width), rng.uniform(0, height)], np.float32)
         if rng.integers(0, 3) == 0:
             m[1] = m[2] = 0
+        if clockwise and rng.integers(0, 3) == 0:
+            m[0], m[1] = -m[0], -m[1]  # mirror x: determinant < 0
+            m = m + np.float32(0)      # (no -0: a matrix that went through Renderer::transform has none)
         color = int(rng.integers(0, 1 << 32))
         if strokes and rng.integers(0, 2) == 0:
             thickness[i] = np.float32(rng.uniform(.2, 60.0))
             radius, max_scale, psr = F.stroke_scalars(m, float(thickness[i]))
             paths[i] = (nv, len(pv), npnt, 0, m, color, 1, radius, int(rng.integers(0, 3)), int(rng.integers(0, 3)), psr, max_scale, 0)
         else:
-            paths[i] = (nv, len(pv), npnt, int(rng.integers(0, 2)), m, color, 0, 0.0, 0, 0, 0.0, 0.0, 0)
+            paths[i] = (nv, len(pv), npnt, int(rng.integers(0, 3 if clockwise else 2)), m, color, 0, 0.0, 0, 0, 0.0, 0.0, 0)
         verbs.extend(pv)
         points.extend(pp)
         nv += len(pv)
