@@ -279,6 +279,27 @@ def test_cpp_path_renderer_and_core_reproduce_the_reference_records(scene, tmp_p
         assert counts[expect] > 50  # the scene does exercise its feature
 
 
+@pytest.mark.parametrize("seed", [3, 7, 21])
+@pytest.mark.parametrize("scene", ["f1o", "f1b", "f1c", "f1w", "f1g", "f1p", "f1i"])
+def test_feature_scenes_with_other_seeds_live_against_the_reference(scene, seed, tmp_path):
+    """The feature scenes again with other random content (2000 paths), both front ends recorded on the
+    spot: the reference front end and CudaPathRenderer + the host build of the core write the same bytes.
+    (tests/tools/gm_records_sweep.py with RIVECUDA_SWEEP_EXTRA="--seed N" runs any number of seeds.)"""
+    import subprocess
+    from conftest import ROOT
+    player = os.path.join(ROOT, "rive-runtime_b200", "_build", "rive_cuda_player")
+    recorder = os.path.join(ROOT, "rive-runtime_b200", "_build", "librivecuda_trace.so")
+    if not os.path.exists(player) or not os.path.exists(recorder):
+        pytest.skip("scene player not built (needs the reference tree at build time)")
+    reference, call, trace = str(tmp_path / "reference.rvct"), str(tmp_path / "call.rpf"), str(tmp_path / "device.rvct")
+    common = [player, "--scene", scene, "--budget-ms", "0", "--seed", str(seed), "--paths", "2000"]
+    subprocess.check_call(common, env=dict(os.environ, RIVECUDA_LIB=recorder, RIVECUDA_TRACE_OUT=reference), stdout=subprocess.DEVNULL, timeout=120)
+    subprocess.check_call(common + ["--gpu-front-end"], env=dict(os.environ, RIVECUDA_LIB=recorder, RIVECUDA_TRACE_OUT=trace, RIVECUDA_TRACE_FRONT_END_OUT=call),
+                          stdout=subprocess.DEVNULL, timeout=120)
+    counts = _compare_device_front_end_call_with_reference_trace(call, trace, T.parse(reference))
+    assert counts["paths"] > 1000
+
+
 RIV_ASSETS = ["off_road_car", "bullet_man", "juice", "shapetest", "fix_rectangle", "follow_path_solos", "nested_artboard_opacity", "lock_icon_demo",
               "solos_collapse_tests", "group_effect", "tape", "image_fit_alignment_2"]
 

@@ -5,7 +5,8 @@ front end (--budget-ms 0) and through CudaPathRenderer + the host build of the k
 the records are compared byte for byte (frames with feathers are refused here: RIVECUDA_FRONT_END_NO_DELEGATE;
 delegated draws are the reference front end's own). Where both flush several times per frame (a frame
 that needs more gradient rows than one texture holds), the last flush is compared; GMs that flush a
-different number of times (they drive the RenderContext directly) are skipped. usage: gm_records_sweep.py [scene ...]"""
+different number of times (they drive the RenderContext directly) are skipped. $RIVECUDA_SWEEP_EXTRA: more player arguments (e.g. "--seed 7 --paths 2000" for the f1* scenes).
+usage: gm_records_sweep.py [scene ...]"""
 import os
 import subprocess
 import sys
@@ -24,7 +25,7 @@ same = differ = refused = failed = multi = 0
 with tempfile.TemporaryDirectory() as tmp:
     reference, call, trace = os.path.join(tmp, "reference.rvct"), os.path.join(tmp, "call.rpf"), os.path.join(tmp, "device.rvct")
     for scene in scenes:
-        common = [player, "--scene", scene, "--budget-ms", "0"]
+        common = [player, "--scene", scene, "--budget-ms", "0"] + os.environ.get("RIVECUDA_SWEEP_EXTRA", "").split()
         for f in (reference, call, trace):
             if os.path.exists(f):
                 os.remove(f)
