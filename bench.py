@@ -132,6 +132,31 @@ def reference_front_end(scene: str, frames: int = 12, extra=()):
         return {"error": str(e)[:200]}
 
 
+def riv_front_end_host_time(asset: str = "off_road_car", frames: int = 300):
+    """SURVEY 8 f1 on real content, from the C++ host: host milliseconds per frame of the scene player
+    animating a .riv file (the reference's unmodified core runtime) at 1080p and drawing it through
+    RiveRenderer (the reference's CPU front end) and through CudaPathRenderer (--gpu-front-end: RawPaths
+    to rivecuda_front_end_paths), both into the same CUDA backend, each frame read back (8 MB D2H).
+    The frames of the two are bit-identical (tests/test_front_end_gpu.py). None without the player
+    binary or the asset (tools/fetch_riv_assets.sh)."""
+    path = os.path.join(ROOT, "tests", "_riv_assets", asset + ".riv")
+    if not os.path.exists(PLAYER) or not os.path.exists(path):
+        return None
+    env = dict(os.environ)
+    env.setdefault("RIVECUDA_LIB", os.path.join(ROOT, "rive-runtime_b200", "_build", "librivecuda.so"))
+    out = {"asset": asset + ".riv", "frames": frames, "width": 1920, "height": 1080,
+           "what": "rive_cuda_player --scene riv:... --budget-ms 0 [--gpu-front-end]: host ms per frame incl. the state machine's "
+                   "advance, Artboard::draw, the flush and the read-back of the frame"}
+    try:
+        for key, extra in (("reference_front_end_host_ms_per_frame", []), ("device_front_end_host_ms_per_frame", ["--gpu-front-end"])):
+            text = subprocess.check_output([PLAYER, "--scene", "riv:" + path, "--frames", str(frames), "--budget-ms", "0", *extra],
+                                           text=True, timeout=120, env=env, stderr=subprocess.DEVNULL)
+            out[key] = json.loads(text.strip().splitlines()[-1])["host_ms_per_frame"]
+    except Exception as e:  # noqa: BLE001
+        out["error"] = str(e)[:200]
+    return out
+
+
 def run_reference(args, rank: int) -> None:
     """--impl reference: the reference's pixel stage cannot be built here (GLSL ->
     SPIR-V -> Vulkan/SwiftShader), so this arm times its CPU port,
@@ -559,6 +584,11 @@ def main() -> None:
                          "own pixel stage needs Vulkan/SwiftShader, unbuildable here); front_end = the reference's own CPU front "
                          "end (RiveRenderer + RenderContext::flush, one thread) on the same frame"}
 
+    riv_front_end = None
+    if rank == 0 and world == 1 and args.workload == "c2":
+        rp.sync()
+        riv_front_end = riv_front_end_host_time()
+
     sharded = None
     if distributed and not args.no_sharded and args.workload == "c2":
         rp.sync()
@@ -586,6 +616,7 @@ def main() -> None:
                             "frame k's read-back overlaps frame k+1's rendering (two targets); serial_value waits for each "
                             "read-back before the next frame"},
             "raw_paths_e2e": raw_paths,
+            "riv_front_end": riv_front_end,
             "gpu_launches": int(launches) * args.steps,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "kernel": "+".join(sorted(raster_kernels)), "kernel_ms": raster,
